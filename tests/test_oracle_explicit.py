@@ -1,0 +1,73 @@
+"""Check the first-principles restatement (oracle/explicit.py) against torch on CPU: this pins
+the third-party semantics (gate order, packing, LayerNorm, encoder layer, BCE, Adam) that the
+CUDA kernels reproduce."""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from oracle import explicit as E
+
+
+def _np(d):
+    return {k: v.detach().double().numpy() for k, v in d.items()}
+
+
+def test_bilstm_and_encoder_features():
+    torch.manual_seed(0)
+    T, B, I = 6, 5, 4
+    lengths = torch.tensor([3, 6, 1, 6, 2])
+    x = torch.randn(T, B, I, dtype=torch.float64)
+    r1 = nn.LSTM(I, I, bidirectional=True).double()
+    r2 = nn.LSTM(2 * I, I, bidirectional=True).double()
+    ln = nn.LayerNorm(2 * I).double()
+    with torch.no_grad():
+        ln.weight.uniform_(0.5, 1.5); ln.bias.uniform_(-0.5, 0.5)
+    from oracle.misa_oracle import OracleMISA
+    ref = OracleMISA.encode(x, lengths, r1, r2, ln).detach().numpy()
+    got = E.encoder_features(x.numpy(), lengths.numpy(), _np(dict(r1.named_parameters())),
+                             _np(dict(r2.named_parameters())), ln.weight.detach().numpy(),
+                             ln.bias.detach().numpy())
+    np.testing.assert_allclose(got, ref, rtol=0, atol=1e-12)
+
+
+def test_pack_indices_match_torch():
+    g = torch.Generator().manual_seed(3)
+    for B in (1, 7, 40):
+        lengths = torch.randint(1, 9, (B,), generator=g)
+        x = torch.randn(int(lengths.max()), B, 3, generator=g)
+        pk = nn.utils.rnn.pack_padded_sequence(x, lengths, enforce_sorted=False)
+        bs, off, uns = E.pack_indices(lengths.numpy(), pk.sorted_indices.numpy())
+        np.testing.assert_array_equal(bs, pk.batch_sizes.numpy())
+        np.testing.assert_array_equal(uns, pk.unsorted_indices.numpy())
+        # packed row (t, j) holds x[t, sorted_idx[j]]
+        data = pk.data.numpy()
+        si = pk.sorted_indices.numpy()
+        for t in range(len(bs)):
+            for j in range(bs[t]):
+                np.testing.assert_array_equal(data[off[t] + j], x[t, si[j]].numpy())
+
+
+def test_encoder_layer():
+    torch.manual_seed(1)
+    layer = nn.TransformerEncoderLayer(d_model=16, nhead=2).double().eval()
+    x = torch.randn(6, 3, 16, dtype=torch.float64)
+    ref = layer(x).detach().numpy()
+    got = E.encoder_layer(x.numpy(), _np(dict(layer.named_parameters())))
+    np.testing.assert_allclose(got, ref, rtol=0, atol=1e-12)
+
+
+def test_bce_clamp_and_adam():
+    s = np.array([0.0, 1.0, 0.3, 0.9]); y = np.array([1.0, 0.0, 1.0, 0.0])
+    ref = nn.BCELoss()(torch.tensor(s), torch.tensor(y)).item()
+    assert abs(E.bce_mean(s, y) - ref) < 1e-12
+    torch.manual_seed(2)
+    p = torch.randn(50, dtype=torch.float64, requires_grad=True)
+    opt = torch.optim.Adam([p], lr=1e-2)
+    pn, m, v = p.detach().numpy().copy(), np.zeros(50), np.zeros(50)
+    for step in range(1, 4):
+        g = torch.randn(50, dtype=torch.float64) * 3
+        p.grad = g.clone()
+        torch.nn.utils.clip_grad_value_([p], 1.0)
+        opt.step()
+        pn, m, v = E.adam_clip_step(pn, g.numpy(), m, v, step, 1e-2)
+        np.testing.assert_allclose(pn, p.detach().numpy(), rtol=0, atol=1e-12)
