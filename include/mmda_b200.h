@@ -1,0 +1,160 @@
+/* mmda_b200 -- C ABI of the B200-native MISA hot path (libmmda_b200.so, sm_100a only).
+ *
+ * The reference (SoyeonHH/MMDA) has no FFI layer: its hot path is Python calling torch modules
+ * (SURVEY.md section 8b).  These entry points are what a binding for that path binds instead of
+ * the torch ops; every declaration names the reference call site it replaces (paths relative to
+ * the reference root).  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative code (MMDA_ERR_*); nothing throws;
+ *     mmda_last_error() returns a thread-local message for the last failure on this thread;
+ *   - all buffers are caller-owned DEVICE pointers; no hidden allocation, no hidden sync;
+ *   - every launch takes an explicit cudaStream_t (passed as void*-sized handle);
+ *   - matrices are row-major fp32 with an explicit leading dimension (elements);
+ *   - packed-sequence layout: token (t, sorted position j) lives at row offsets[t] + j, i.e.
+ *     torch's PackedSequence.data order.
+ */
+#ifndef MMDA_B200_H
+#define MMDA_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* mmda_stream_t; /* == cudaStream_t */
+
+#define MMDA_OK 0
+#define MMDA_ERR_CUDA (-1)
+#define MMDA_ERR_ARG (-2)
+#define MMDA_ERR_UNSUPPORTED (-3)
+
+/* activation ids for fused epilogues (config.activation, src/config.py:24-27) */
+#define MMDA_ACT_NONE 0
+#define MMDA_ACT_LEAKYRELU 1
+#define MMDA_ACT_SIGMOID 2
+#define MMDA_ACT_RELU 3
+#define MMDA_ACT_TANH 4
+
+const char* mmda_last_error(void);
+int mmda_abi_version(void);
+/* out5 = {SM count, max opt-in smem per block, cc major, cc minor, L2 bytes} */
+int mmda_device_info(int* out5);
+
+/* ---- packing: pack_padded_sequence(enforce_sorted=False), src/models.py:164,173 -------------
+ * lens_sorted: lengths after the host's descending torch.sort (device int32, B entries).
+ * Writes batch_sizes[Tmax], offsets[Tmax+1] and the (t, j) coordinates of each of the N rows. */
+int mmda_pack_build(const int* lens_sorted, int B, int Tmax, int N, int* batch_sizes, int* offsets,
+                    int* row_t, int* row_j, mmda_stream_t stream);
+/* X[row] = src[t][sorted_idx[j]] for a time-major padded (T,B,D) input (visual / acoustic). */
+int mmda_gather_rows(const float* src, float* X, const int* row_t, const int* row_j,
+                     const int* sorted_idx, int N, int B, int D, mmda_stream_t stream);
+
+/* ---- nn.Embedding, src/models.py:47,201 (forward fused with the pack; dense backward) ------ */
+int mmda_embedding_forward(const float* E, const long long* sentences, float* X, const int* row_t,
+                           const int* row_j, const int* sorted_idx, int N, int B, int D, int V,
+                           mmda_stream_t stream);
+int mmda_embedding_backward(float* dE, const long long* sentences, const float* dX,
+                            const int* row_t, const int* row_j, const int* sorted_idx, int N,
+                            int B, int D, int V, mmda_stream_t stream);
+
+/* ---- dense contractions: nn.Linear everywhere in src/models.py:61-153 and the hoisted LSTM
+ * GEMMs of nn.LSTM (src/models.py:48-55).
+ * C = act(alpha*op(A)*op(B) + beta*C + bias + bias2); op(A) = transA ? A[k*lda+m] : A[m*lda+k];
+ * op(B) = transB ? B[n*ldb+k] : B[k*ldb+n].  split_k: 0 = auto, 1 = none, >1 = atomic split-K
+ * (requires beta == 1 and no activation). */
+int mmda_sgemm(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda,
+               const float* B, int ldb, float beta, float* C, int ldc, const float* bias,
+               const float* bias2, int act, int split_k, mmda_stream_t stream);
+
+/* ---- bidirectional LSTM recurrence: nn.LSTM(bidirectional=True), src/models.py:48-55,167,176
+ * gates [N][8H]: in = x*W_ih^T + b_ih + b_hh for (fwd | reverse); out (save_for_backward) =
+ * activated gates.  y [N][2H], c [N][2H].  Final hidden states are scattered straight into the
+ * utterance matrix utt (B, utt_ld) in ORIGINAL batch order at column offsets utt_off_f /
+ * utt_off_r (src/models.py:203: [h1_fwd | h2_fwd | h1_bwd | h2_bwd]). */
+int mmda_lstm_forward(float* gates, const float* whh_f, const float* whh_r, float* y, float* c,
+                      const int* lens_sorted, const int* sorted_idx, const int* offsets, float* utt,
+                      int utt_ld, int utt_off_f, int utt_off_r, int B, int H, int Tmax,
+                      int save_for_backward, mmda_stream_t stream);
+/* BPTT: gates (activated, from forward) is overwritten with d(pre-activation gates).  dy may be
+ * NULL (rnn2: its sequence output is discarded, src/models.py:176); dutt is the gradient of utt. */
+int mmda_lstm_backward(float* gates, const float* whh_f, const float* whh_r, const float* c,
+                       const float* dy, const float* dutt, int utt_ld, int utt_off_f,
+                       int utt_off_r, const int* lens_sorted, const int* sorted_idx,
+                       const int* offsets, float* scratch, int B, int H, int Tmax,
+                       mmda_stream_t stream);
+long long mmda_lstm_scratch_bytes(int B, int H);
+/* out6 = {cluster size, units per CTA, batch tile, n batch tiles, smem fwd, smem bwd} */
+int mmda_lstm_plan(int B, int H, int* out6);
+/* h_{prev} operand for the hoisted dW_hh GEMM: [N][2H] */
+int mmda_lstm_shift_h(const float* y, float* hprev, const int* row_t, const int* row_j,
+                      const int* lens_sorted, const int* offsets, int N, int H,
+                      mmda_stream_t stream);
+
+/* ---- nn.LayerNorm, src/models.py:65-80,155-157,172 and the two norms of the fusion layer ----
+ * y = LN(x + res) (res may be NULL); mean/rstd saved per row for the backward. */
+int mmda_layernorm_forward(const float* x, int ldx, const float* res, int ldr, const float* gamma,
+                           const float* beta, float* y, int ldy, float* mean, float* rstd,
+                           int rows, int width, float eps, mmda_stream_t stream);
+/* dgamma / dbeta are ACCUMULATED into. */
+int mmda_layernorm_backward(const float* dy, int lddy, const float* x, int ldx, const float* res,
+                            int ldr, const float* gamma, const float* mean, const float* rstd,
+                            float* dx, int lddx, float* dgamma, float* dbeta, int rows, int width,
+                            mmda_stream_t stream);
+
+/* ---- elementwise ---------------------------------------------------------------------------- */
+int mmda_act_forward(float* x, int ld, int rows, int cols, int act, mmda_stream_t stream);
+int mmda_act_backward(float* dy, int lddy, const float* y, int ldy, int rows, int cols, int act,
+                      mmda_stream_t stream);
+int mmda_add2d(float* out, int ldo, const float* x, int ldx, float ax, const float* y, int ldy,
+               float ay, int rows, int cols, mmda_stream_t stream);
+/* out[c] += sum_r x[r][c] (bias gradients; out2 optional second destination) */
+int mmda_colsum(const float* x, int ld, int rows, int cols, float* out, float* out2,
+                mmda_stream_t stream);
+/* inverted dropout, mask = f(seed, stream_id, index): nn.Dropout at src/models.py:126,152,160 */
+int mmda_dropout(const float* x, float* out, long long n, float p, unsigned long long seed,
+                 unsigned stream_id, mmda_stream_t stream);
+/* getBinaryTensor, src/utils/functions.py:112-115 */
+int mmda_threshold(const float* x, float* out, long long n, float thr, mmda_stream_t stream);
+
+/* ---- attention core of nn.TransformerEncoderLayer(d, nhead=2), src/models.py:160-161,243-245
+ * qkv rows (b*seq + i) = [q | k | v]; probs (B, nhead, seq, seq) pre-dropout. */
+int mmda_attention_forward(const float* qkv, float* ctx, float* probs, int B, int seq, int nhead,
+                           int head_dim, float p_drop, unsigned long long seed, unsigned stream_id,
+                           mmda_stream_t stream);
+int mmda_attention_backward(const float* qkv, const float* probs, const float* dctx, float* dqkv,
+                            int B, int seq, int nhead, int head_dim, float p_drop,
+                            unsigned long long seed, unsigned stream_id, mmda_stream_t stream);
+
+/* ---- fused losses forward + backward, src/solver.py:163-181,373-462 (see csrc/loss.cu) ------
+ * X0 (B,6,d) tokens [p_t,p_v,p_a,s_t,s_v,s_a]; O,R (3,B,d); scores,tcp,y (B,NC).
+ * segA: 6*d + 6*NC + 3 floats; segB: 12*d + 6*d*d; segC: 6*d.  Bg = GLOBAL batch size. */
+int mmda_loss_phase1(const float* X0, const float* O, const float* R, const float* scores,
+                     const float* tcp, const float* y, float* segA, int B, int d, int NC,
+                     mmda_stream_t stream);
+int mmda_loss_phase2(const float* X0, const float* segA, float* XN, float* inv_norm,
+                     float* moments, int B, int d, float Bg, mmda_stream_t stream);
+/* losses[6] = {cls, diff, sim, recon, conf, total}; coef (3,5,d) */
+int mmda_loss_finalize(const float* segA, const float* segB, float* losses, float* coef, int d,
+                       int NC, float Bg, float w_diff, float w_sim, float w_recon, float w_conf,
+                       mmda_stream_t stream);
+int mmda_loss_phase4a(float* DXN, const float* inv_norm, float* colsum2, int B, int d,
+                      mmda_stream_t stream);
+int mmda_loss_phase4b(const float* X0, const float* DXN, const float* segA, const float* segB,
+                      const float* colsum2, const float* coef, float* dZ, int B, int d, float Bg,
+                      float w_sim, int accumulate, mmda_stream_t stream);
+int mmda_loss_grad_misc(const float* scores, const float* tcp, const float* y, const float* O,
+                        const float* R, const float* segA, float* dscores, float* dtcp, float* dR,
+                        float* dO, int B, int d, int NC, float Bg, float w_recon, float w_conf,
+                        mmda_stream_t stream);
+
+/* ---- clip_grad_value_ + Adam.step, src/solver.py:185-186 ------------------------------------
+ * flat arenas of n floats, 16-byte aligned; step is the 1-based count; grad_scale multiplies the
+ * gradient before clipping (1/world_size after a sum all-reduce, else 1). */
+int mmda_adam_clip_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                        long long n, int step, float lr, float clip, float beta1, float beta2,
+                        float eps, float grad_scale, mmda_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMDA_B200_H */

@@ -1,0 +1,436 @@
+// Row-wise / elementwise kernels of the MISA heads and fusion layer: LayerNorm (plain, residual
+// and packed-sequence), activation forward/backward, bias-gradient column sums, dropout, the
+// 6-token 2-head attention core, thresholding.  fp32 throughout, coalesced along the feature
+// axis, vectorised where the row pitch allows.  Reference sites: nn.LayerNorm at
+// src/models.py:65-80,155-157,172; nn.TransformerEncoderLayer at :160-161,243-245 (post-norm,
+// ReLU, dropout 0.1 at four places); classifier dropout+sigmoid at :150-153; getBinaryTensor at
+// src/utils/functions.py:112-115.
+#include "common.cuh"
+
+// ---------------------------------------------------------------- LayerNorm ----------------
+// y = LN(x + res) * gamma + beta, one warp per row; saves mean / rstd for the backward.
+__global__ void layernorm_fwd_kernel(const float* __restrict__ x, int ldx,
+                                     const float* __restrict__ res, int ldr,
+                                     const float* __restrict__ gamma,
+                                     const float* __restrict__ beta, float* __restrict__ y,
+                                     int ldy, float* __restrict__ mean_out,
+                                     float* __restrict__ rstd_out, int rows, int width,
+                                     float eps) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + (size_t)row * ldx;
+  const float* rr = res ? res + (size_t)row * ldr : nullptr;
+  float s = 0.f;
+  for (int c = lane; c < width; c += 32) s += xr[c] + (rr ? rr[c] : 0.f);
+  const float mean = warp_sum(s) / width;
+  float v = 0.f;
+  for (int c = lane; c < width; c += 32) {
+    const float d = xr[c] + (rr ? rr[c] : 0.f) - mean;
+    v = fmaf(d, d, v);
+  }
+  const float rstd = rsqrtf(warp_sum(v) / width + eps);
+  float* yr = y + (size_t)row * ldy;
+  for (int c = lane; c < width; c += 32) {
+    const float d = xr[c] + (rr ? rr[c] : 0.f) - mean;
+    yr[c] = d * rstd * gamma[c] + beta[c];
+  }
+  if (lane == 0 && mean_out) { mean_out[row] = mean; rstd_out[row] = rstd; }
+}
+
+// dx = rstd * (dy*g - mean(dy*g) - xhat * mean(dy*g*xhat));  dgamma += sum_r dy*xhat;  dbeta += sum_r dy
+constexpr int LN_MAXC = 20;   // width <= 640
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ x, int ldx,
+                     const float* __restrict__ res, int ldr, const float* __restrict__ gamma,
+                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                     float* __restrict__ dx, int lddx, float* __restrict__ dgamma,
+                     float* __restrict__ dbeta, int rows, int width, int rows_per_block) {
+  __shared__ float red[8][33];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r_beg = blockIdx.x * rows_per_block;
+  const int r_end = min(rows, r_beg + rows_per_block);
+  float ag[LN_MAXC], ab[LN_MAXC];
+#pragma unroll
+  for (int i = 0; i < LN_MAXC; ++i) { ag[i] = 0.f; ab[i] = 0.f; }
+  for (int row = r_beg + warp; row < r_end; row += 8) {
+    const float* dyr = dy + (size_t)row * lddy;
+    const float* xr = x + (size_t)row * ldx;
+    const float* rr = res ? res + (size_t)row * ldr : nullptr;
+    const float mu = mean[row], rs = rstd[row];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXC; ++i) {
+      const int c = lane + 32 * i;
+      if (c < width) {
+        const float xh = (xr[c] + (rr ? rr[c] : 0.f) - mu) * rs;
+        const float d = dyr[c];
+        const float dg = d * gamma[c];
+        s1 += dg;
+        s2 = fmaf(dg, xh, s2);
+        ag[i] = fmaf(d, xh, ag[i]);
+        ab[i] += d;
+      }
+    }
+    s1 = warp_sum(s1) / width;
+    s2 = warp_sum(s2) / width;
+    float* dxr = dx + (size_t)row * lddx;
+#pragma unroll
+    for (int i = 0; i < LN_MAXC; ++i) {
+      const int c = lane + 32 * i;
+      if (c < width) {
+        const float xh = (xr[c] + (rr ? rr[c] : 0.f) - mu) * rs;
+        dxr[c] = rs * (dyr[c] * gamma[c] - s1 - xh * s2);
+      }
+    }
+  }
+  // cross-warp reduction of the per-column partials, one atomic per column per block
+#pragma unroll
+  for (int i = 0; i < LN_MAXC; ++i) {
+    if (32 * i < width) {   // block-uniform
+      __syncthreads();
+      red[warp][lane] = ag[i];
+      __syncthreads();
+      if (warp == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += red[w][lane];
+        const int c = lane + 32 * i;
+        if (c < width) atomicAdd(dgamma + c, t);
+      }
+      __syncthreads();
+      red[warp][lane] = ab[i];
+      __syncthreads();
+      if (warp == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += red[w][lane];
+        const int c = lane + 32 * i;
+        if (c < width) atomicAdd(dbeta + c, t);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- elementwise ---------------
+__global__ void act_fwd_kernel(float* __restrict__ x, int ld, int rows, int cols, int act) {
+  const size_t n = (size_t)rows * cols;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i % cols);
+    float* p = x + (size_t)r * ld + c;
+    *p = apply_act(*p, act);
+  }
+}
+__global__ void act_bwd_kernel(float* __restrict__ dy, int lddy, const float* __restrict__ y,
+                               int ldy, int rows, int cols, int act) {
+  const size_t n = (size_t)rows * cols;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i % cols);
+    dy[(size_t)r * lddy + c] *= act_grad_from_output(y[(size_t)r * ldy + c], act);
+  }
+}
+// out = ax * x + ay * y   (y nullable -> out = ax * x); out may alias x or y
+__global__ void add2d_kernel(float* __restrict__ out, int ldo, const float* x, int ldx, float ax,
+                             const float* y, int ldy, float ay, int rows, int cols) {
+  const size_t n = (size_t)rows * cols;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i % cols);
+    float v = ax * x[(size_t)r * ldx + c];
+    if (y) v = fmaf(ay, y[(size_t)r * ldy + c], v);
+    out[(size_t)r * ldo + c] = v;
+  }
+}
+// out[c] += sum_r x[r][c]  (and out2 if given): bias gradients
+__global__ void colsum_kernel(const float* __restrict__ x, int ld, int rows, int cols,
+                              float* __restrict__ out, float* __restrict__ out2,
+                              int rows_per_block) {
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int r_beg = blockIdx.y * rows_per_block, r_end = min(rows, r_beg + rows_per_block);
+  float s = 0.f;
+  if (c < cols)
+    for (int r = r_beg + threadIdx.y; r < r_end; r += 8) s += x[(size_t)r * ld + c];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    atomicAdd(out + c, t);
+    if (out2) atomicAdd(out2 + c, t);
+  }
+}
+// inverted dropout; the keep mask is a pure function of (seed, stream, index) so the backward
+// regenerates it instead of storing it
+__global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ out, size_t n,
+                               float p, float scale, unsigned long long seed, unsigned stream) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x)
+    out[i] = rng_uniform(seed, stream, (uint32_t)i) >= p ? x[i] * scale : 0.f;
+}
+__global__ void threshold_kernel(const float* __restrict__ x, float* __restrict__ out, size_t n,
+                                 float thr) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x)
+    out[i] = x[i] > thr ? 1.f : 0.f;
+}
+
+// ---------------------------------------------------------------- attention -----------------
+// S=6 tokens, 2 heads, head_dim 64 (d=128): one warp per (sample, head); lane owns dims
+// lane, lane+32 of the head.  qkv row (b*S+i) = [q(d) | k(d) | v(d)].
+constexpr int ATT_S = 6;
+template <int R>   // R = ceil(head_dim / 32) registers per lane
+__global__ void attn_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ ctx,
+                                float* __restrict__ probs, int B, int nhead, int HD, float scale,
+                                float p_drop, unsigned long long seed, unsigned stream) {
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (w >= B * nhead) return;
+  const int b = w / nhead, h = w % nhead, d = nhead * HD;
+  float q[ATT_S][R], k[ATT_S][R], v[ATT_S][R];
+#pragma unroll
+  for (int i = 0; i < ATT_S; ++i) {
+    const float* row = qkv + (size_t)(b * ATT_S + i) * 3 * d + h * HD;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const bool ok = lane + 32 * r < HD;
+      q[i][r] = ok ? row[lane + 32 * r] : 0.f;
+      k[i][r] = ok ? row[d + lane + 32 * r] : 0.f;
+      v[i][r] = ok ? row[2 * d + lane + 32 * r] : 0.f;
+    }
+  }
+  const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+#pragma unroll
+  for (int i = 0; i < ATT_S; ++i) {
+    float s[ATT_S], mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < ATT_S; ++j) {
+      float t = 0.f;
+#pragma unroll
+      for (int r = 0; r < R; ++r) t = fmaf(q[i][r], k[j][r], t);
+      s[j] = warp_sum(t) * scale;
+      mx = fmaxf(mx, s[j]);
+    }
+    float den = 0.f;
+#pragma unroll
+    for (int j = 0; j < ATT_S; ++j) { s[j] = expf(s[j] - mx); den += s[j]; }
+    float o[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) o[r] = 0.f;
+#pragma unroll
+    for (int j = 0; j < ATT_S; ++j) {
+      float pj = s[j] / den;
+      const int pidx = (w * ATT_S + i) * ATT_S + j;
+      if (lane == 0 && probs) probs[pidx] = pj;
+      if (p_drop > 0.f) pj = rng_uniform(seed, stream, (uint32_t)pidx) >= p_drop ? pj * keep_scale : 0.f;
+#pragma unroll
+      for (int r = 0; r < R; ++r) o[r] = fmaf(pj, v[j][r], o[r]);
+    }
+    float* orow = ctx + (size_t)(b * ATT_S + i) * d + h * HD;
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (lane + 32 * r < HD) orow[lane + 32 * r] = o[r];
+  }
+}
+
+template <int R>
+__global__ void attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ probs,
+                                const float* __restrict__ dctx, float* __restrict__ dqkv, int B,
+                                int nhead, int HD, float scale, float p_drop,
+                                unsigned long long seed, unsigned stream) {
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (w >= B * nhead) return;
+  const int b = w / nhead, h = w % nhead, d = nhead * HD;
+  float q[ATT_S][R], k[ATT_S][R], v[ATT_S][R], go[ATT_S][R];
+  float dq[ATT_S][R], dk[ATT_S][R], dv[ATT_S][R];
+#pragma unroll
+  for (int i = 0; i < ATT_S; ++i) {
+    const float* row = qkv + (size_t)(b * ATT_S + i) * 3 * d + h * HD;
+    const float* grow = dctx + (size_t)(b * ATT_S + i) * d + h * HD;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const bool ok = lane + 32 * r < HD;
+      q[i][r] = ok ? row[lane + 32 * r] : 0.f;
+      k[i][r] = ok ? row[d + lane + 32 * r] : 0.f;
+      v[i][r] = ok ? row[2 * d + lane + 32 * r] : 0.f;
+      go[i][r] = ok ? grow[lane + 32 * r] : 0.f;
+      dq[i][r] = 0.f; dk[i][r] = 0.f; dv[i][r] = 0.f;
+    }
+  }
+  const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+#pragma unroll
+  for (int i = 0; i < ATT_S; ++i) {
+    float P[ATT_S], dP[ATT_S], dot = 0.f;
+#pragma unroll
+    for (int j = 0; j < ATT_S; ++j) {
+      const int pidx = (w * ATT_S + i) * ATT_S + j;
+      P[j] = probs[pidx];
+      float m = 1.f;
+      if (p_drop > 0.f) m = rng_uniform(seed, stream, (uint32_t)pidx) >= p_drop ? keep_scale : 0.f;
+      float t = 0.f;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        t = fmaf(go[i][r], v[j][r], t);
+        dv[j][r] = fmaf(P[j] * m, go[i][r], dv[j][r]);
+      }
+      dP[j] = warp_sum(t) * m;           // grad wrt pre-dropout probability
+      dot = fmaf(dP[j], P[j], dot);
+    }
+#pragma unroll
+    for (int j = 0; j < ATT_S; ++j) {
+      const float ds = P[j] * (dP[j] - dot) * scale;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        dq[i][r] = fmaf(ds, k[j][r], dq[i][r]);
+        dk[j][r] = fmaf(ds, q[i][r], dk[j][r]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < ATT_S; ++i) {
+    float* row = dqkv + (size_t)(b * ATT_S + i) * 3 * d + h * HD;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (lane + 32 * r < HD) {
+        row[lane + 32 * r] = dq[i][r];
+        row[d + lane + 32 * r] = dk[i][r];
+        row[2 * d + lane + 32 * r] = dv[i][r];
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- C ABI ---------------------
+static inline int ew_grid(size_t n) {
+  size_t g = (n + 255) / 256;
+  return (int)(g < 1 ? 1 : (g > 148 * 8 ? 148 * 8 : g));
+}
+
+extern "C" {
+
+int mmda_layernorm_forward(const float* x, int ldx, const float* res, int ldr, const float* gamma,
+                           const float* beta, float* y, int ldy, float* mean, float* rstd,
+                           int rows, int width, float eps, cudaStream_t stream) {
+  if (rows <= 0) return MMDA_OK;
+  MMDA_REQUIRE(width > 0, "layernorm: width=%d", width);
+  layernorm_fwd_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(x, ldx, res, ldr, gamma, beta, y, ldy,
+                                                           mean, rstd, rows, width, eps);
+  MMDA_CHECK_LAUNCH();
+  return MMDA_OK;
+}
+
+int mmda_layernorm_backward(const float* dy, int lddy, const float* x, int ldx, const float* res,
+                            int ldr, const float* gamma, const float* mean, const float* rstd,
+                            float* dx, int lddx, float* dgamma, float* dbeta, int rows, int width,
+                            cudaStream_t stream) {
+  if (rows <= 0) return MMDA_OK;
+  MMDA_REQUIRE(width > 0 && width <= 32 * LN_MAXC, "layernorm_backward: width=%d (max %d)", width,
+               32 * LN_MAXC);
+  int rpb = (rows + 295) / 296;
+  rpb = (rpb + 7) / 8 * 8;
+  const int grid = (rows + rpb - 1) / rpb;
+  layernorm_bwd_kernel<<<grid, 256, 0, stream>>>(dy, lddy, x, ldx, res, ldr, gamma, mean, rstd, dx,
+                                                 lddx, dgamma, dbeta, rows, width, rpb);
+  MMDA_CHECK_LAUNCH();
+  return MMDA_OK;
+}
+
+int mmda_act_forward(float* x, int ld, int rows, int cols, int act, cudaStream_t stream) {
+  if (rows <= 0 || cols <= 0) return MMDA_OK;
+  act_fwd_kernel<<<ew_grid((size_t)rows * cols), 256, 0, stream>>>(x, ld, rows, cols, act);
+  MMDA_CHECK_LAUNCH();
+  return MMDA_OK;
+}
+
+int mmda_act_backward(float* dy, int lddy, const float* y, int ldy, int rows, int cols, int act,
+                      cudaStream_t stream) {
+  if (rows <= 0 || cols <= 0) return MMDA_OK;
+  act_bwd_kernel<<<ew_grid((size_t)rows * cols), 256, 0, stream>>>(dy, lddy, y, ldy, rows, cols, act);
+  MMDA_CHECK_LAUNCH();
+  return MMDA_OK;
+}
+
+int mmda_add2d(float* out, int ldo, const float* x, int ldx, float ax, const float* y, int ldy,
+               float ay, int rows, int cols, cudaStream_t stream) {
+  if (rows <= 0 || cols <= 0) return MMDA_OK;
+  add2d_kernel<<<ew_grid((size_t)rows * cols), 256, 0, stream>>>(out, ldo, x, ldx, ax, y, ldy, ay,
+                                                                 rows, cols);
+  MMDA_CHECK_LAUNCH();
+  return MMDA_OK;
+}
+
+int mmda_colsum(const float* x, int ld, int rows, int cols, float* out, float* out2,
+                cudaStream_t stream) {
+  if (rows <= 0 || cols <= 0) return MMDA_OK;
+  const int gx = (cols + 31) / 32;
+  int gy = (296 + gx - 1) / gx;
+  if (gy > (rows + 7) / 8) gy = (rows + 7) / 8;
+  if (gy < 1) gy = 1;
+  int rpb = (rows + gy - 1) / gy;
+  gy = (rows + rpb - 1) / rpb;
+  colsum_kernel<<<dim3(gx, gy), dim3(32, 8), 0, stream>>>(x, ld, rows, cols, out, out2, rpb);
+  MMDA_CHECK_LAUNCH();
+  return MMDA_OK;
+}
+
+int mmda_dropout(const float* x, float* out, long long n, float p, unsigned long long seed,
+                 unsigned stream_id, cudaStream_t stream) {
+  if (n <= 0) return MMDA_OK;
+  MMDA_REQUIRE(p >= 0.f && p < 1.f, "dropout: p=%f", p);
+  dropout_kernel<<<ew_grid((size_t)n), 256, 0, stream>>>(x, out, (size_t)n, p, 1.f / (1.f - p),
+                                                         seed, stream_id);
+  MMDA_CHECK_LAUNCH();
+  return MMDA_OK;
+}
+
+int mmda_threshold(const float* x, float* out, long long n, float thr, cudaStream_t stream) {
+  if (n <= 0) return MMDA_OK;
+  threshold_kernel<<<ew_grid((size_t)n), 256, 0, stream>>>(x, out, (size_t)n, thr);
+  MMDA_CHECK_LAUNCH();
+  return MMDA_OK;
+}
+
+int mmda_attention_forward(const float* qkv, float* ctx, float* probs, int B, int seq, int nhead,
+                           int head_dim, float p_drop, unsigned long long seed, unsigned stream_id,
+                           cudaStream_t stream) {
+  MMDA_REQUIRE(seq == ATT_S, "attention: fusion sequence is 6 tokens (got %d)", seq);
+  const int warps = B * nhead;
+  const float scale = 1.0f / sqrtf((float)head_dim);
+  const int grid = (warps + 3) / 4;
+  if (head_dim <= 32)
+    attn_fwd_kernel<1><<<grid, 128, 0, stream>>>(qkv, ctx, probs, B, nhead, head_dim, scale, p_drop, seed, stream_id);
+  else if (head_dim <= 64)
+    attn_fwd_kernel<2><<<grid, 128, 0, stream>>>(qkv, ctx, probs, B, nhead, head_dim, scale, p_drop, seed, stream_id);
+  else if (head_dim <= 128)
+    attn_fwd_kernel<4><<<grid, 128, 0, stream>>>(qkv, ctx, probs, B, nhead, head_dim, scale, p_drop, seed, stream_id);
+  else {
+    mmda_set_error("attention: head_dim=%d unsupported (<= 128)", head_dim);
+    return MMDA_ERR_UNSUPPORTED;
+  }
+  MMDA_CHECK_LAUNCH();
+  return MMDA_OK;
+}
+
+int mmda_attention_backward(const float* qkv, const float* probs, const float* dctx, float* dqkv,
+                            int B, int seq, int nhead, int head_dim, float p_drop,
+                            unsigned long long seed, unsigned stream_id, cudaStream_t stream) {
+  MMDA_REQUIRE(seq == ATT_S, "attention: fusion sequence is 6 tokens (got %d)", seq);
+  const int warps = B * nhead;
+  const float scale = 1.0f / sqrtf((float)head_dim);
+  const int grid = (warps + 3) / 4;
+  if (head_dim <= 32)
+    attn_bwd_kernel<1><<<grid, 128, 0, stream>>>(qkv, probs, dctx, dqkv, B, nhead, head_dim, scale, p_drop, seed, stream_id);
+  else if (head_dim <= 64)
+    attn_bwd_kernel<2><<<grid, 128, 0, stream>>>(qkv, probs, dctx, dqkv, B, nhead, head_dim, scale, p_drop, seed, stream_id);
+  else if (head_dim <= 128)
+    attn_bwd_kernel<4><<<grid, 128, 0, stream>>>(qkv, probs, dctx, dqkv, B, nhead, head_dim, scale, p_drop, seed, stream_id);
+  else {
+    mmda_set_error("attention: head_dim=%d unsupported (<= 128)", head_dim);
+    return MMDA_ERR_UNSUPPORTED;
+  }
+  MMDA_CHECK_LAUNCH();
+  return MMDA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,177 @@
+// fp32 SIMT GEMM with fused epilogue, used for every small dense contraction of the MISA heads
+// (projection / private / shared / recon / fusion-transformer / classifier linears and their
+// backward, reference src/models.py:67-161,243-248) and as the exact-fp32 path of the hoisted LSTM
+// GEMMs (x*W_ih^T, dX, dW_ih, dW_hh) when the tensor-core path (gemm_tc.cu) is not selected.
+//
+//   C[M,N] (ldc) = act( alpha * op(A)[M,K] * op(B)[K,N] + beta * C + bias[N] )
+//   op(A): transA ? A[k*lda+m] : A[m*lda+k]        op(B): transB ? B[n*ldb+k] : B[k*ldb+n]
+//   split_k > 1: grid.z slices of K accumulate into C with atomicAdd (C must hold the value to
+//   accumulate onto; no activation).
+#include "common.cuh"
+
+template <int BM, int BN, int BK, int TM, int TN, bool TA, bool TB>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN))
+sgemm_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C,
+             const float* __restrict__ bias, const float* __restrict__ bias2, int M, int N, int K,
+             int lda, int ldb, int ldc, float alpha, float beta, int act, int k_per_split) {
+  constexpr int NT = (BM / TM) * (BN / TN);
+  constexpr int PAD = 4;
+  constexpr int LA = (BM * BK) / NT, LB = (BN * BK) / NT;
+  static_assert((BM * BK) % NT == 0 && (BN * BK) % NT == 0, "tile/threads mismatch");
+  __shared__ __align__(16) float As[BK][BM + PAD];
+  __shared__ __align__(16) float Bs[BK][BN + PAD];
+
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kbeg = blockIdx.z * k_per_split;
+  const int kend = min(K, kbeg + k_per_split);
+  const int tx = tid % (BN / TN), ty = tid / (BN / TN);
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  float ra[LA], rb[LB];
+  auto load_tiles = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < LA; ++i) {
+      const int e = tid + i * NT;
+      int m, k;
+      if (TA) { m = e % BM; k = e / BM; } else { k = e % BK; m = e / BK; }
+      const int gm = m0 + m, gk = k0 + k;
+      float v = 0.f;
+      if (gm < M && gk < kend) v = TA ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk];
+      ra[i] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < LB; ++i) {
+      const int e = tid + i * NT;
+      int n, k;
+      if (TB) { k = e % BK; n = e / BK; } else { n = e % BN; k = e / BN; }
+      const int gn = n0 + n, gk = k0 + k;
+      float v = 0.f;
+      if (gn < N && gk < kend) v = TB ? B[(size_t)gn * ldb + gk] : B[(size_t)gk * ldb + gn];
+      rb[i] = v;
+    }
+  };
+  auto store_tiles = [&]() {
+#pragma unroll
+    for (int i = 0; i < LA; ++i) {
+      const int e = tid + i * NT;
+      int m, k;
+      if (TA) { m = e % BM; k = e / BM; } else { k = e % BK; m = e / BK; }
+      As[k][m] = ra[i];
+    }
+#pragma unroll
+    for (int i = 0; i < LB; ++i) {
+      const int e = tid + i * NT;
+      int n, k;
+      if (TB) { k = e % BK; n = e / BK; } else { n = e % BN; k = e / BN; }
+      Bs[k][n] = rb[i];
+    }
+  };
+
+  if (kbeg < kend) {
+    load_tiles(kbeg);
+    for (int k0 = kbeg; k0 < kend; k0 += BK) {
+      store_tiles();
+      __syncthreads();
+      if (k0 + BK < kend) load_tiles(k0 + BK);   // global loads in flight during the math
+#pragma unroll
+      for (int k = 0; k < BK; ++k) {
+        float a[TM], b[TN];
+#pragma unroll
+        for (int i = 0; i < TM; i += 4) {
+          const float4 v = *reinterpret_cast<const float4*>(&As[k][ty * TM + i]);
+          a[i] = v.x; a[i + 1] = v.y; a[i + 2] = v.z; a[i + 3] = v.w;
+        }
+#pragma unroll
+        for (int j = 0; j < TN; j += 4) {
+          const float4 v = *reinterpret_cast<const float4*>(&Bs[k][tx * TN + j]);
+          b[j] = v.x; b[j + 1] = v.y; b[j + 2] = v.z; b[j + 3] = v.w;
+        }
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+#pragma unroll
+          for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+  }
+
+  const bool split = gridDim.z > 1;
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int gm = m0 + ty * TM + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int gn = n0 + tx * TN + j;
+      if (gn >= N) continue;
+      float v = alpha * acc[i][j];
+      float* cp = C + (size_t)gm * ldc + gn;
+      if (split) {
+        if (blockIdx.z == 0) {
+          if (bias != nullptr) v += bias[gn];
+          if (bias2 != nullptr) v += bias2[gn];
+        }
+        atomicAdd(cp, v);
+      } else {
+        if (bias != nullptr) v += bias[gn];
+        if (bias2 != nullptr) v += bias2[gn];
+        if (beta != 0.f) v += beta * (*cp);
+        *cp = apply_act(v, act);
+      }
+    }
+  }
+}
+
+template <int BM, int BN, int BK, int TM, int TN>
+static int launch_sgemm(bool ta, bool tb, const float* A, const float* B, float* C,
+                        const float* bias, const float* bias2, int M, int N, int K, int lda, int ldb,
+                        int ldc, float alpha, float beta, int act, int split, cudaStream_t st) {
+  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, split);
+  dim3 block((BM / TM) * (BN / TN));
+  int kps = (K + split - 1) / split;
+  kps = (kps + BK - 1) / BK * BK;
+#define MMDA_SGEMM_GO(TA_, TB_)                                                             \
+  sgemm_kernel<BM, BN, BK, TM, TN, TA_, TB_><<<grid, block, 0, st>>>(A, B, C, bias, bias2, M, N, K, \
+                                                                     lda, ldb, ldc, alpha, beta, act, kps)
+  if (ta && tb) MMDA_SGEMM_GO(true, true);
+  else if (ta) MMDA_SGEMM_GO(true, false);
+  else if (tb) MMDA_SGEMM_GO(false, true);
+  else MMDA_SGEMM_GO(false, false);
+#undef MMDA_SGEMM_GO
+  MMDA_CHECK_LAUNCH();
+  return MMDA_OK;
+}
+
+extern "C" int mmda_sgemm(int transA, int transB, int M, int N, int K, float alpha,
+                          const float* A, int lda, const float* B, int ldb, float beta, float* C,
+                          int ldc, const float* bias, const float* bias2, int act, int split_k,
+                          cudaStream_t stream) {
+  if (M <= 0 || N <= 0) return MMDA_OK;
+  MMDA_REQUIRE(K >= 0 && A && B && C, "sgemm: bad arguments M=%d N=%d K=%d", M, N, K);
+  MMDA_REQUIRE(split_k >= 0 && split_k <= 64, "sgemm: split_k=%d out of range", split_k);
+  const long big_tiles = (long)((M + 127) / 128) * ((N + 127) / 128);
+  const long med_tiles = (long)((M + 63) / 64) * ((N + 63) / 64);
+  if (split_k == 0) {   // auto: split only long-K problems that cannot fill the chip
+    split_k = 1;
+    if (beta == 1.f && act == ACT_NONE && K >= 2048) {
+      long tiles = big_tiles >= 148 ? big_tiles : med_tiles;
+      while (tiles * split_k < 296 && K / (split_k * 2) >= 512 && split_k < 32) split_k *= 2;
+    }
+  }
+  MMDA_REQUIRE(split_k == 1 || (act == ACT_NONE && beta == 1.f),
+               "sgemm: split-K accumulates into C (needs beta=1, no activation)");
+  if (big_tiles >= 148)
+    return launch_sgemm<128, 128, 16, 8, 8>(transA, transB, A, B, C, bias, bias2, M, N, K, lda, ldb, ldc,
+                                            alpha, beta, act, split_k, stream);
+  if (med_tiles * split_k >= 148)
+    return launch_sgemm<64, 64, 16, 4, 4>(transA, transB, A, B, C, bias, bias2, M, N, K, lda, ldb, ldc,
+                                          alpha, beta, act, split_k, stream);
+  return launch_sgemm<32, 32, 32, 4, 4>(transA, transB, A, B, C, bias, bias2, M, N, K, lda, ldb, ldc,
+                                        alpha, beta, act, split_k, stream);
+}

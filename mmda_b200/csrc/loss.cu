@@ -1,0 +1,374 @@
+// Fused loss forward + hand-written backward for the solver contract (reference
+// src/solver.py:163-181, 373-462 and src/utils/functions.py:49-109):
+//   cls  : sum over classes of mean BCE(scores, y)                       (solver.py:373-385)
+//   diff : 6 DiffLoss pairs over the private/shared tokens                (solver.py:422-441)
+//   sim  : CMD with 5 moments over 3 pairs of shared tokens, / 3          (solver.py:409-420)
+//   recon: mean MSE(recon, orig) over 3 modalities, / 3                   (solver.py:443-449)
+//   conf : per class MSE(tcp, y*s)/nnz + soft-label CE over the batch/nnz (solver.py:451-462)
+//   total = cls + w_diff*diff + w_sim*sim + w_recon*recon (+ w_conf*conf)
+//
+// diff, sim and conf are statistics over the *batch* axis, so under batch sharding they do not
+// decompose.  The computation is therefore split into phases whose outputs are
+// plain batch sums; a data-parallel caller all-reduces (sum) the three small stat segments
+// between phases and every rank then holds the global-batch value and gradient:
+//   phase1  -> segA = [colsum 6*d | bce NC | sqtcp NC | sum_ys NC | sum_y NC | nnz NC | sumexp NC | recon_sq 3]
+//   phase2  -> XN (centred, row-normalised tokens), inv_norm; segB = [moments 3*4*d | Gram 6*d*d]
+//              (the six Grams are XN_a^T XN_b, launched by the caller through mmda_sgemm)
+//   finalize-> the six loss values and the CMD coefficient vectors
+//   (caller: DXN = w_diff*2/d^2 * (XN_b G^T | XN_a G) through mmda_sgemm)
+//   phase4a -> dxc = DXN * inv_norm (in place); segC = colsum of dxc
+//   phase4b -> dZ (grad wrt the six tokens), grad_misc -> dscores, dtcp, drecon, dorig
+// Token order everywhere: [p_t, p_v, p_a, s_t, s_v, s_a] (reference src/models.py:243).
+#include "common.cuh"
+
+constexpr int LOSS_MAXC = 8;   // d <= 256
+constexpr int NTOK = 6;
+
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+  // blockDim.x == 256
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) t += red[w];
+  return t;
+}
+
+__global__ void __launch_bounds__(256)
+loss_phase1_kernel(const float* __restrict__ X0, const float* __restrict__ O,
+                   const float* __restrict__ R, const float* __restrict__ scores,
+                   const float* __restrict__ tcp, const float* __restrict__ y,
+                   float* __restrict__ segA, int B, int d, int NC) {
+  __shared__ float red[8];
+  const int blk = blockIdx.x, tid = threadIdx.x;
+  float* colsum = segA;
+  float* cls = segA + NTOK * d;
+  if (blk < NTOK) {
+    for (int c = tid; c < d; c += 256) {
+      float s = 0.f;
+      for (int b = 0; b < B; ++b) s += X0[((size_t)b * NTOK + blk) * d + c];
+      colsum[blk * d + c] = s;
+    }
+  } else if (blk == NTOK) {
+    const int w = tid >> 5, lane = tid & 31;
+    if (w < NC) {
+      float bce = 0.f, sq = 0.f, sys = 0.f, sy = 0.f, nz = 0.f, se = 0.f;
+      for (int b = lane; b < B; b += 32) {
+        const float s = scores[b * NC + w], t = y[b * NC + w], p = tcp[b * NC + w];
+        bce -= t * fmaxf(logf(s), -100.f) + (1.f - t) * fmaxf(logf(1.f - s), -100.f);
+        const float e = p - t * s;
+        sq = fmaf(e, e, sq);
+        sys = fmaf(t, s, sys);
+        sy += t;
+        nz += (t != 0.f) ? 1.f : 0.f;
+        se += expf(s);
+      }
+      bce = warp_sum(bce); sq = warp_sum(sq); sys = warp_sum(sys);
+      sy = warp_sum(sy); nz = warp_sum(nz); se = warp_sum(se);
+      if (lane == 0) {
+        cls[0 * NC + w] = bce; cls[1 * NC + w] = sq; cls[2 * NC + w] = sys;
+        cls[3 * NC + w] = sy; cls[4 * NC + w] = nz; cls[5 * NC + w] = se;
+      }
+    }
+  } else {
+    const int m = blk - NTOK - 1;
+    const size_t n = (size_t)B * d;
+    const float* r = R + m * n;
+    const float* o = O + m * n;
+    float s = 0.f;
+    for (size_t i = tid; i < n; i += 256) { const float e = r[i] - o[i]; s = fmaf(e, e, s); }
+    s = block_sum_256(s, red);
+    if (tid == 0) cls[6 * NC + m] = s;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+loss_phase2_kernel(const float* __restrict__ X0, const float* __restrict__ segA,
+                   float* __restrict__ XN, float* __restrict__ inv_norm,
+                   float* __restrict__ moments, int B, int d, float Bg, int rows_per_block) {
+  __shared__ float red[8][33];
+  const int i = blockIdx.x;   // token
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r_beg = blockIdx.y * rows_per_block, r_end = min(B, r_beg + rows_per_block);
+  float mu[LOSS_MAXC], mom[4][LOSS_MAXC];
+#pragma unroll
+  for (int m = 0; m < LOSS_MAXC; ++m) {
+    const int c = lane + 32 * m;
+    mu[m] = c < d ? segA[i * d + c] / Bg : 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) mom[k][m] = 0.f;
+  }
+  for (int b = r_beg + warp; b < r_end; b += 8) {
+    const float* xr = X0 + ((size_t)b * NTOK + i) * d;
+    float xc[LOSS_MAXC], ss = 0.f;
+#pragma unroll
+    for (int m = 0; m < LOSS_MAXC; ++m) {
+      const int c = lane + 32 * m;
+      xc[m] = c < d ? xr[c] - mu[m] : 0.f;
+      ss = fmaf(xc[m], xc[m], ss);
+    }
+    const float inv = 1.f / (sqrtf(warp_sum(ss)) + 1e-6f);
+    float* out = XN + ((size_t)i * B + b) * d;
+#pragma unroll
+    for (int m = 0; m < LOSS_MAXC; ++m) {
+      const int c = lane + 32 * m;
+      if (c < d) out[c] = xc[m] * inv;
+      if (i >= 3) {
+        const float x2 = xc[m] * xc[m];
+        mom[0][m] += x2; mom[1][m] = fmaf(x2, xc[m], mom[1][m]);
+        mom[2][m] = fmaf(x2, x2, mom[2][m]); mom[3][m] = fmaf(x2 * x2, xc[m], mom[3][m]);
+      }
+    }
+    if (lane == 0) inv_norm[(size_t)i * B + b] = inv;
+  }
+  if (i >= 3) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int m = 0; m < LOSS_MAXC; ++m) {
+        if (32 * m < d) {
+          __syncthreads();
+          red[warp][lane] = mom[k][m];
+          __syncthreads();
+          if (warp == 0) {
+            float t = 0.f;
+            for (int w = 0; w < 8; ++w) t += red[w][lane];
+            const int c = lane + 32 * m;
+            if (c < d) atomicAdd(moments + ((size_t)(i - 3) * 4 + k) * d + c, t);
+          }
+        }
+      }
+  }
+}
+
+// one block: loss values + CMD coefficient vectors coef[3][5][d] (d L / d c_k of shared token a,
+// before the w_sim/3 factor)
+__global__ void __launch_bounds__(256)
+loss_finalize_kernel(const float* __restrict__ segA, const float* __restrict__ segB,
+                     float* __restrict__ losses, float* __restrict__ coef, int d, int NC, float Bg,
+                     float w_diff, float w_sim, float w_recon, float w_conf) {
+  __shared__ float red[8];
+  const int tid = threadIdx.x;
+  const float* colsum = segA;
+  const float* cls = segA + NTOK * d;
+  const float* moments = segB;
+  const float* G = segB + 3 * 4 * d;
+  // diff
+  float s = 0.f;
+  const size_t ng = (size_t)6 * d * d;
+  for (size_t i = tid; i < ng; i += 256) s = fmaf(G[i], G[i], s);
+  const float diff = block_sum_256(s, red) / ((float)d * (float)d);
+  // cmd
+  for (int i = tid; i < 3 * 5 * d; i += 256) coef[i] = 0.f;
+  __syncthreads();
+  const int pa[3] = {0, 0, 2}, pb[3] = {1, 2, 1};
+  float cmd = 0.f;
+  for (int p = 0; p < 3; ++p) {
+    for (int k = 1; k <= 5; ++k) {
+      float part = 0.f;
+      for (int c = tid; c < d; c += 256) {
+        const float va = k == 1 ? colsum[(3 + pa[p]) * d + c] : moments[(pa[p] * 4 + k - 2) * d + c];
+        const float vb = k == 1 ? colsum[(3 + pb[p]) * d + c] : moments[(pb[p] * 4 + k - 2) * d + c];
+        const float dl = (va - vb) / Bg;
+        part = fmaf(dl, dl, part);
+      }
+      const float nrm = sqrtf(block_sum_256(part, red));
+      cmd += nrm;
+      for (int c = tid; c < d; c += 256) {
+        const float va = k == 1 ? colsum[(3 + pa[p]) * d + c] : moments[(pa[p] * 4 + k - 2) * d + c];
+        const float vb = k == 1 ? colsum[(3 + pb[p]) * d + c] : moments[(pb[p] * 4 + k - 2) * d + c];
+        const float g = ((va - vb) / Bg) / nrm;
+        coef[(pa[p] * 5 + k - 1) * d + c] += g;     // same thread owns column c: no race
+        coef[(pb[p] * 5 + k - 1) * d + c] -= g;
+      }
+      __syncthreads();
+    }
+  }
+  cmd /= 3.f;
+  if (tid == 0) {
+    float l_cls = 0.f, l_conf = 0.f;
+    for (int c = 0; c < NC; ++c) {
+      l_cls += cls[0 * NC + c] / Bg;
+      const float nnz = cls[4 * NC + c];
+      l_conf += (cls[1 * NC + c] / Bg) / nnz;
+      l_conf += (-cls[2 * NC + c] + cls[3 * NC + c] * logf(cls[5 * NC + c])) / nnz;
+    }
+    const float recon = (cls[6 * NC + 0] + cls[6 * NC + 1] + cls[6 * NC + 2]) / (Bg * d) / 3.f;
+    float total = l_cls + w_diff * diff + w_sim * cmd + w_recon * recon;
+    if (w_conf != 0.f) total += w_conf * l_conf;
+    losses[0] = l_cls; losses[1] = diff; losses[2] = cmd; losses[3] = recon; losses[4] = l_conf;
+    losses[5] = total;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+loss_phase4a_kernel(float* __restrict__ DXN, const float* __restrict__ inv_norm,
+                    float* __restrict__ colsum2, int B, int d, int rows_per_block) {
+  __shared__ float red[8][33];
+  const int i = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r_beg = blockIdx.y * rows_per_block, r_end = min(B, r_beg + rows_per_block);
+  float acc[LOSS_MAXC];
+#pragma unroll
+  for (int m = 0; m < LOSS_MAXC; ++m) acc[m] = 0.f;
+  for (int b = r_beg + warp; b < r_end; b += 8) {
+    float* row = DXN + ((size_t)i * B + b) * d;
+    const float inv = inv_norm[(size_t)i * B + b];
+#pragma unroll
+    for (int m = 0; m < LOSS_MAXC; ++m) {
+      const int c = lane + 32 * m;
+      if (c < d) { const float v = row[c] * inv; row[c] = v; acc[m] += v; }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < LOSS_MAXC; ++m) {
+    if (32 * m < d) {
+      __syncthreads();
+      red[warp][lane] = acc[m];
+      __syncthreads();
+      if (warp == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += red[w][lane];
+        const int c = lane + 32 * m;
+        if (c < d) atomicAdd(colsum2 + i * d + c, t);
+      }
+    }
+  }
+}
+
+// dZ[b][i][:] (accumulate flag: += or =)
+__global__ void loss_phase4b_kernel(const float* __restrict__ X0, const float* __restrict__ DXN,
+                                    const float* __restrict__ segA, const float* __restrict__ segB,
+                                    const float* __restrict__ colsum2,
+                                    const float* __restrict__ coef, float* __restrict__ dZ, int B,
+                                    int d, float Bg, float w_sim, int accumulate) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // b*6 + i
+  const int lane = threadIdx.x & 31;
+  if (row >= B * NTOK) return;
+  const int b = row / NTOK, i = row % NTOK;
+  const float* moments = segB;
+  for (int c = lane; c < d; c += 32) {
+    float g = DXN[((size_t)i * B + b) * d + c] - colsum2[i * d + c] / Bg;
+    if (i >= 3) {
+      const int a = i - 3;
+      const float xc = X0[(size_t)row * d + c] - segA[i * d + c] / Bg;
+      float t = coef[(a * 5 + 0) * d + c];
+      float pw = xc;                                   // xc^(k-1)
+      float cprev = 0.f;                               // c_{k-1}, c_1 = 0
+#pragma unroll
+      for (int k = 2; k <= 5; ++k) {
+        t = fmaf(coef[(a * 5 + k - 1) * d + c] * (float)k, pw - cprev, t);
+        cprev = moments[(a * 4 + k - 2) * d + c] / Bg;  // c_k for the next term
+        pw *= xc;
+      }
+      g = fmaf(w_sim / (3.f * Bg), t, g);
+    }
+    float* o = dZ + (size_t)row * d + c;
+    *o = accumulate ? *o + g : g;
+  }
+}
+
+__global__ void loss_grad_misc_kernel(const float* __restrict__ scores,
+                                      const float* __restrict__ tcp, const float* __restrict__ y,
+                                      const float* __restrict__ O, const float* __restrict__ R,
+                                      const float* __restrict__ segA, float* __restrict__ dscores,
+                                      float* __restrict__ dtcp, float* __restrict__ dR,
+                                      float* __restrict__ dO, int B, int d, int NC, float Bg,
+                                      float w_recon, float w_conf) {
+  const float* cls = segA + NTOK * d;
+  const size_t n_rec = (size_t)3 * B * d;
+  const size_t n_cls = (size_t)B * NC;
+  const float kr = w_recon * 2.f / (3.f * Bg * d);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_rec + n_cls;
+       i += (size_t)gridDim.x * blockDim.x) {
+    if (i < n_rec) {
+      const float g = kr * (R[i] - O[i]);
+      dR[i] = g;
+      dO[i] = -g;
+    } else {
+      const size_t j = i - n_rec;
+      const int c = (int)(j % NC);
+      const float s = scores[j], t = y[j];
+      float gs = (s - t) / fmaxf((1.f - s) * s, 1e-12f) / Bg;      // BCE
+      float gt = 0.f;
+      if (w_conf != 0.f) {
+        const float nnz = cls[4 * NC + c];
+        const float e = tcp[j] - t * s;
+        gt = w_conf * 2.f * e / (Bg * nnz);
+        gs += -t * gt;
+        gs += w_conf * (-t + cls[3 * NC + c] * expf(s) / cls[5 * NC + c]) / nnz;
+      }
+      dscores[j] = gs;
+      dtcp[j] = gt;
+    }
+  }
+}
+
+extern "C" {
+
+int mmda_loss_phase1(const float* X0, const float* O, const float* R, const float* scores,
+                     const float* tcp, const float* y, float* segA, int B, int d, int NC,
+                     cudaStream_t stream) {
+  MMDA_REQUIRE(NC >= 1 && NC <= 8, "loss: num_classes=%d (max 8)", NC);
+  MMDA_REQUIRE(d >= 1 && d <= 32 * LOSS_MAXC, "loss: hidden_size=%d (max %d)", d, 32 * LOSS_MAXC);
+  loss_phase1_kernel<<<NTOK + 1 + 3, 256, 0, stream>>>(X0, O, R, scores, tcp, y, segA, B, d, NC);
+  MMDA_CHECK_LAUNCH();
+  return MMDA_OK;
+}
+
+int mmda_loss_phase2(const float* X0, const float* segA, float* XN, float* inv_norm,
+                     float* moments, int B, int d, float Bg, cudaStream_t stream) {
+  MMDA_REQUIRE(d >= 1 && d <= 32 * LOSS_MAXC, "loss: hidden_size=%d (max %d)", d, 32 * LOSS_MAXC);
+  int rpb = (B + 23) / 24;
+  rpb = (rpb + 7) / 8 * 8;
+  dim3 grid(NTOK, (B + rpb - 1) / rpb);
+  loss_phase2_kernel<<<grid, 256, 0, stream>>>(X0, segA, XN, inv_norm, moments, B, d, Bg, rpb);
+  MMDA_CHECK_LAUNCH();
+  return MMDA_OK;
+}
+
+int mmda_loss_finalize(const float* segA, const float* segB, float* losses, float* coef, int d,
+                       int NC, float Bg, float w_diff, float w_sim, float w_recon, float w_conf,
+                       cudaStream_t stream) {
+  loss_finalize_kernel<<<1, 256, 0, stream>>>(segA, segB, losses, coef, d, NC, Bg, w_diff, w_sim,
+                                              w_recon, w_conf);
+  MMDA_CHECK_LAUNCH();
+  return MMDA_OK;
+}
+
+int mmda_loss_phase4a(float* DXN, const float* inv_norm, float* colsum2, int B, int d,
+                      cudaStream_t stream) {
+  int rpb = (B + 23) / 24;
+  rpb = (rpb + 7) / 8 * 8;
+  dim3 grid(NTOK, (B + rpb - 1) / rpb);
+  loss_phase4a_kernel<<<grid, 256, 0, stream>>>(DXN, inv_norm, colsum2, B, d, rpb);
+  MMDA_CHECK_LAUNCH();
+  return MMDA_OK;
+}
+
+int mmda_loss_phase4b(const float* X0, const float* DXN, const float* segA, const float* segB,
+                      const float* colsum2, const float* coef, float* dZ, int B, int d, float Bg,
+                      float w_sim, int accumulate, cudaStream_t stream) {
+  const int rows = B * NTOK;
+  loss_phase4b_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(X0, DXN, segA, segB, colsum2, coef, dZ, B,
+                                                          d, Bg, w_sim, accumulate);
+  MMDA_CHECK_LAUNCH();
+  return MMDA_OK;
+}
+
+int mmda_loss_grad_misc(const float* scores, const float* tcp, const float* y, const float* O,
+                        const float* R, const float* segA, float* dscores, float* dtcp, float* dR,
+                        float* dO, int B, int d, int NC, float Bg, float w_recon, float w_conf,
+                        cudaStream_t stream) {
+  const size_t n = (size_t)3 * B * d + (size_t)B * NC;
+  int grid = (int)((n + 255) / 256);
+  if (grid > 1184) grid = 1184;
+  loss_grad_misc_kernel<<<grid, 256, 0, stream>>>(scores, tcp, y, O, R, segA, dscores, dtcp, dR, dO,
+                                                  B, d, NC, Bg, w_recon, w_conf);
+  MMDA_CHECK_LAUNCH();
+  return MMDA_OK;
+}
+
+}  // extern "C"

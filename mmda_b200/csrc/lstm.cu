@@ -1,0 +1,547 @@
+// Length-aware persistent bidirectional LSTM recurrence for sm_100a (forward and BPTT).
+//
+// Replaces the recurrent half of nn.LSTM at reference src/models.py:48-55,167,176 (the x*W_ih
+// half is hoisted into one GEMM over all packed tokens, see gemm_*.cu).  Semantics restated in
+// oracle/explicit.py::lstm_direction: gate order i,f,g,o; h0=c0=0; the reverse direction runs
+// t=L_b-1..0 per sample; rows past a sample's length are never touched.
+//
+// Layout.  Tokens live in torch's PackedSequence order (time-major inside the length-sorted
+// batch): packed row of (t, sorted position j) = offsets[t] + j.  Per layer:
+//   gates [N][2][4H]  in: x-projection + b_ih + b_hh;  out (training): sigma/tanh'ed gates;
+//                     after the backward kernel: d(pre-activation gates), the GEMM operand for
+//                     dW_ih / dW_hh / dX
+//   y     [N][2][H]   hidden states (fwd | bwd), c [N][2][H] cell states
+//
+// Work split.  grid = (C * n_batch_tiles, 2 directions), cluster = C CTAs.  A cluster owns BT
+// consecutive sorted samples of one direction; CTA `rank` of the cluster keeps the 4 gate rows of
+// hidden units [rank*Hs, rank*Hs+Hs) of W_hh resident in shared memory for the whole sequence
+// (H=300: C=8, Hs=38 -> 182 KB/CTA fp32).  Every step each CTA multiplies its W slice with the
+// tile's h_{t-1} (all H columns), finishes the cell update for its units in registers and
+// pushes h_t into every peer's shared memory through DSMEM; one split-phase cluster barrier pair
+// per step.  The backward kernel keeps the same slice, produces partial dh_{t-1} over all H
+// columns, exchanges the partials through an L2-resident scratch and reduces its own columns.
+#include "common.cuh"
+
+struct LstmArgs {
+  float* gates;           // [N][8H]
+  const float* whh[2];    // per direction [4H][H]
+  float* y;               // [N][2H]
+  float* c;               // [N][2H]
+  const int* lens;        // [B] lengths in sorted (descending) order
+  const int* sorted_idx;  // [B] original batch index of sorted position j
+  const int* offsets;     // [Tmax+1]
+  float* utt;             // fwd: final hidden destination, (B, utt_ld) in ORIGINAL batch order
+  const float* dutt;      // bwd: grad of the above
+  const float* dy;        // bwd: grad wrt y [N][2H] (nullable)
+  float* scratch;         // bwd: partial-sum exchange [2][n_clusters][C][BT][Kpad]
+  int utt_ld, utt_off0, utt_off1;
+  int B, H, Hs, Kpad, C, n_tiles, save, Tmax;
+};
+
+template <int N, int BITLO>
+__device__ __forceinline__ void reduce_scatter(float (&v)[N], int lane) {
+  // All lanes hold N partial sums; lanes that differ only in bits >= BITLO hold partials of the
+  // same outputs.  After the call lane (q = lane / BITLO) holds the complete sums of indices
+  // [q*N/RS, (q+1)*N/RS) in v[0 .. N/RS), RS = 32/BITLO.
+  int n = N;
+#pragma unroll
+  for (int bit = 16; bit >= BITLO; bit >>= 1) {
+    const bool hi = (lane & bit) != 0;
+    n >>= 1;
+#pragma unroll
+    for (int j = 0; j < N / 2; ++j) {
+      if (j < n) {
+        const float send = hi ? v[j] : v[j + n];
+        const float keep = hi ? v[j + n] : v[j];
+        v[j] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------
+template <int BT>
+__global__ void __launch_bounds__(640, 1) lstm_fwd_kernel(const LstmArgs p) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int BTP = BT + 4;
+  const int C = p.C, H = p.H, Hs = p.Hs, Kpad = p.Kpad;
+  const int dir = blockIdx.y;
+  const unsigned rank = cluster_ctarank();
+  const int tile = blockIdx.x / C;
+  const int b_base = tile * BT;
+
+  float4* Ws = reinterpret_cast<float4*>(smem);   // [Kpad][Hs] of (i,f,g,o) rows of one unit
+  float* h_s = smem + 4 * Kpad * Hs;              // [Kpad][BTP]
+  int* lens_s = reinterpret_cast<int*>(h_s + Kpad * BTP);
+  int* orig_s = lens_s + BT;
+  int* offs_s = orig_s + BT;                      // [Tmax+1]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = lane >> 3, usub = lane & 7;
+  const int UG = (Hs + 7) >> 3;
+  const int ug = warp % UG, bg = warp / UG;
+  const int u = ug * 8 + usub;
+  const int u_glob = rank * Hs + u;
+  const bool u_ok = (u < Hs) && (u_glob < H);
+  const int u_cl = min(u, Hs - 1);
+
+  {  // stage this CTA's W_hh slice: Ws[k][ul] = (W[0H+ug][k], W[1H+ug][k], W[2H+ug][k], W[3H+ug][k])
+    const float* __restrict__ W = p.whh[dir];
+    const int total = 4 * Hs * Kpad;
+    for (int idx = tid; idx < total; idx += blockDim.x) {
+      const int k = idx % Kpad, r = idx / Kpad, g = r & 3, ul = r >> 2;
+      const int ugl = rank * Hs + ul;
+      const float v = (k < H && ugl < H) ? W[(size_t)(g * H + ugl) * H + k] : 0.f;
+      smem[(k * Hs + ul) * 4 + g] = v;
+    }
+    for (int idx = tid; idx < Kpad * BTP; idx += blockDim.x) h_s[idx] = 0.f;
+    if (tid < BT) {
+      const int b = b_base + tid;
+      lens_s[tid] = b < p.B ? p.lens[b] : 0;
+      orig_s[tid] = b < p.B ? p.sorted_idx[b] : 0;
+    }
+    for (int idx = tid; idx <= p.Tmax; idx += blockDim.x) offs_s[idx] = p.offsets[idx];
+  }
+  __syncthreads();
+  cluster_sync_all();  // every peer's h_s is zeroed before anyone pushes into it
+
+  const int Lmax = lens_s[0];
+  const int bl0 = bg * 8 + 2 * q;
+  const int len0 = lens_s[bl0], len1 = lens_s[bl0 + 1], len_bg = lens_s[bg * 8];
+  const int orig0 = orig_s[bl0], orig1 = orig_s[bl0 + 1];
+  const int H2 = 2 * H, H8 = 8 * H;
+  const int gcol = dir * 4 * H + u_glob;   // + g*H
+  const int ycol = dir * H + u_glob;
+  const int utt_off = dir == 0 ? p.utt_off0 : p.utt_off1;
+  const int K4 = Kpad >> 2;
+  float c0 = 0.f, c1 = 0.f;
+
+  // peers' h_s addresses for my (unit, batch pair)
+  uint32_t peer[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+    peer[r] = dsmem_addr(h_s + min(u_glob, Kpad - 1) * BTP + bl0, r < C ? r : 0);
+
+  for (int s = 0; s < Lmax; ++s) {
+    const int t = dir == 0 ? s : Lmax - 1 - s;
+    const bool a0 = u_ok && t < len0, a1 = u_ok && t < len1;
+    const int off_t = offs_s[t];
+    const size_t row0 = (size_t)(off_t + b_base + bl0), row1 = row0 + 1;
+    float x0[4] = {0.f, 0.f, 0.f, 0.f}, x1[4] = {0.f, 0.f, 0.f, 0.f};
+    if (a0) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) x0[g] = p.gates[row0 * H8 + gcol + g * H];
+    }
+    if (a1) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) x1[g] = p.gates[row1 * H8 + gcol + g * H];
+    }
+
+    float acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+    if (t < len_bg) {  // warp-uniform: some row of this batch group is still running
+      const float4* wp = Ws + q * Hs + u_cl;
+      const float* hp = h_s + q * BTP + bg * 8;
+#pragma unroll 4
+      for (int i = 0; i < K4; ++i) {
+        const float4 w = wp[(size_t)i * 4 * Hs];
+        const float4 ha = *reinterpret_cast<const float4*>(hp + i * 4 * BTP);
+        const float4 hb = *reinterpret_cast<const float4*>(hp + i * 4 * BTP + 4);
+        const float hv[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+          acc[b * 4 + 0] = fmaf(w.x, hv[b], acc[b * 4 + 0]);
+          acc[b * 4 + 1] = fmaf(w.y, hv[b], acc[b * 4 + 1]);
+          acc[b * 4 + 2] = fmaf(w.z, hv[b], acc[b * 4 + 2]);
+          acc[b * 4 + 3] = fmaf(w.w, hv[b], acc[b * 4 + 3]);
+        }
+      }
+      reduce_scatter<32, 8>(acc, lane);  // lane q now owns batch rows 2q, 2q+1 -> acc[0..8)
+    }
+    cluster_arrive();  // A: this CTA is done reading h_{t-1}
+
+    float hn0 = 0.f, hn1 = 0.f;
+    if (a0) {
+      const float ig = sigmoidf_acc(acc[0] + x0[0]), fg = sigmoidf_acc(acc[1] + x0[1]);
+      const float gg = tanhf(acc[2] + x0[2]), og = sigmoidf_acc(acc[3] + x0[3]);
+      c0 = fg * c0 + ig * gg;
+      hn0 = og * tanhf(c0);
+      if (p.save) {
+        float* gp = p.gates + row0 * H8 + gcol;
+        gp[0] = ig; gp[H] = fg; gp[2 * H] = gg; gp[3 * H] = og;
+        p.c[row0 * H2 + ycol] = c0;
+      }
+      p.y[row0 * H2 + ycol] = hn0;
+      const bool fin = dir == 0 ? (t == len0 - 1) : (t == 0);
+      if (fin && p.utt) p.utt[(size_t)orig0 * p.utt_ld + utt_off + u_glob] = hn0;
+    }
+    if (a1) {
+      const float ig = sigmoidf_acc(acc[4] + x1[0]), fg = sigmoidf_acc(acc[5] + x1[1]);
+      const float gg = tanhf(acc[6] + x1[2]), og = sigmoidf_acc(acc[7] + x1[3]);
+      c1 = fg * c1 + ig * gg;
+      hn1 = og * tanhf(c1);
+      if (p.save) {
+        float* gp = p.gates + row1 * H8 + gcol;
+        gp[0] = ig; gp[H] = fg; gp[2 * H] = gg; gp[3 * H] = og;
+        p.c[row1 * H2 + ycol] = c1;
+      }
+      p.y[row1 * H2 + ycol] = hn1;
+      const bool fin = dir == 0 ? (t == len1 - 1) : (t == 0);
+      if (fin && p.utt) p.utt[(size_t)orig1 * p.utt_ld + utt_off + u_glob] = hn1;
+    }
+
+    cluster_wait();  // A: every CTA of the cluster is done reading h_{t-1}
+    if (a0 || a1) {
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+        if (r < C) dsmem_st_f2(peer[r], hn0, hn1);
+    }
+    cluster_arrive();  // B: h_t pushed
+    cluster_wait();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// backward through time
+// ------------------------------------------------------------------------------------------
+template <int BT, int KS>
+__global__ void __launch_bounds__(640, 1) lstm_bwd_kernel(const LstmArgs p) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int BTP = BT + 4;
+  constexpr int RS = 32 / KS;       // lanes that split the contraction over gate rows
+  constexpr int NV = 32 / RS;       // outputs each lane owns after the reduce-scatter
+  const int C = p.C, H = p.H, Hs = p.Hs, Kpad = p.Kpad;
+  const int dir = blockIdx.y;
+  const unsigned rank = cluster_ctarank();
+  const int tile = blockIdx.x / C;
+  const int b_base = tile * BT;
+  const int R = (4 * Hs + RS - 1) / RS * RS;   // gate rows held by this CTA (r = ul*4 + g), padded
+
+  float* Wb = smem;                 // [R][Kpad]
+  float* dG_s = smem + R * Kpad;    // [R][BTP]
+  int* lens_s = reinterpret_cast<int*>(dG_s + R * BTP);
+  int* orig_s = lens_s + BT;
+  int* offs_s = orig_s + BT;        // [Tmax+1]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int BG = BT / 8;
+  const int K4 = Kpad >> 2;
+  // matvec role: lane = q*KS + ksub; warp -> (k group, batch group)
+  const int KG = (K4 + KS - 1) / KS;
+  const int mq = lane / KS, ksub = lane % KS;
+  const int kg = warp % KG, mbg = warp / KG;
+  const bool mv_warp = warp < KG * BG;
+  const int kquad = kg * KS + ksub;
+  const bool kq_ok = kquad < K4;
+  const int kq_cl = min(kquad, K4 - 1);
+  // cell role (same ownership as the forward kernel): lane = q*8 + usub
+  const int UG = (Hs + 7) >> 3;
+  const int eq = lane >> 3, usub = lane & 7;
+  const int ug = warp % UG, ebg = warp / UG;
+  const bool ew_warp = warp < UG * BG;
+  const int u = ug * 8 + usub;
+  const int u_glob = rank * Hs + u;
+  const bool u_ok = ew_warp && (u < Hs) && (u_glob < H);
+
+  {
+    const float* __restrict__ W = p.whh[dir];
+    for (int idx = tid; idx < R * Kpad; idx += blockDim.x) {
+      const int k = idx % Kpad, r = idx / Kpad, g = r & 3, ul = r >> 2;
+      const int ugl = rank * Hs + ul;
+      Wb[idx] = (k < H && ul < Hs && ugl < H) ? W[(size_t)(g * H + ugl) * H + k] : 0.f;
+    }
+    for (int idx = tid; idx <= p.Tmax; idx += blockDim.x) offs_s[idx] = p.offsets[idx];
+    for (int idx = tid; idx < R * BTP; idx += blockDim.x) dG_s[idx] = 0.f;
+    if (tid < BT) {
+      const int b = b_base + tid;
+      lens_s[tid] = b < p.B ? p.lens[b] : 0;
+      orig_s[tid] = b < p.B ? p.sorted_idx[b] : 0;
+    }
+  }
+  __syncthreads();
+  cluster_sync_all();
+
+  const int Lmax = lens_s[0];
+  const int ebl0 = (ew_warp ? ebg : 0) * 8 + 2 * eq;
+  const int len0 = lens_s[ebl0], len1 = lens_s[ebl0 + 1];
+  const int orig0 = orig_s[ebl0], orig1 = orig_s[ebl0 + 1];
+  const int len_mbg = mv_warp ? lens_s[mbg * 8] : 0;
+  const int H2 = 2 * H, H8 = 8 * H;
+  const int gcol = dir * 4 * H + u_glob;
+  const int ycol = dir * H + u_glob;
+  const int utt_off = dir == 0 ? p.utt_off0 : p.utt_off1;
+  const int cl_id = blockIdx.y * p.n_tiles + tile;
+  const size_t slab = (size_t)BT * Kpad;   // one CTA's partial block
+  float dc0 = 0.f, dc1 = 0.f;
+
+  for (int s = 0; s < Lmax; ++s) {
+    const int t = dir == 0 ? Lmax - 1 - s : s;
+    const int par = s & 1;
+    float* scr = p.scratch + ((size_t)(par * 2 * p.n_tiles + cl_id) * C) * slab;
+
+    // ---- prefetch everything the cell update needs (latency hidden behind the matvec) ----
+    const bool a0 = u_ok && t < len0, a1 = u_ok && t < len1;
+    const int off_t = offs_s[t];
+    const size_t row0 = (size_t)(off_t + b_base + ebl0), row1 = row0 + 1;
+    // forward-order predecessor time (its c is c_{prev}); forward-order successor feeds dh_rec
+    const int tp = dir == 0 ? t - 1 : t + 1;
+    float g0[4], g1[4], ct0 = 0.f, ct1 = 0.f, cp0 = 0.f, cp1 = 0.f, dh0 = 0.f, dh1 = 0.f;
+    bool rec0 = false, rec1 = false;
+    if (a0) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) g0[g] = p.gates[row0 * H8 + gcol + g * H];
+      ct0 = p.c[row0 * H2 + ycol];
+      const bool hp = dir == 0 ? (t >= 1) : (t + 1 < len0);
+      if (hp) cp0 = p.c[(size_t)(offs_s[tp] + b_base + ebl0) * H2 + ycol];
+      if (p.dy) dh0 = p.dy[row0 * H2 + ycol];
+      const bool fin = dir == 0 ? (t == len0 - 1) : (t == 0);
+      if (fin && p.dutt) dh0 += p.dutt[(size_t)orig0 * p.utt_ld + utt_off + u_glob];
+      rec0 = dir == 0 ? (t + 1 < len0) : (t >= 1);
+    }
+    if (a1) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) g1[g] = p.gates[row1 * H8 + gcol + g * H];
+      ct1 = p.c[row1 * H2 + ycol];
+      const bool hp = dir == 0 ? (t >= 1) : (t + 1 < len1);
+      if (hp) cp1 = p.c[(size_t)(offs_s[tp] + b_base + ebl0 + 1) * H2 + ycol];
+      if (p.dy) dh1 = p.dy[row1 * H2 + ycol];
+      const bool fin = dir == 0 ? (t == len1 - 1) : (t == 0);
+      if (fin && p.dutt) dh1 += p.dutt[(size_t)orig1 * p.utt_ld + utt_off + u_glob];
+      rec1 = dir == 0 ? (t + 1 < len1) : (t >= 1);
+    }
+
+    // ---- partial dh over all H columns from this CTA's gate rows of the successor step ----
+    // a batch group is needed iff one of its rows is active now AND had a successor step
+    const bool need = mv_warp && s > 0 && (dir == 0 ? (t + 1 < len_mbg) : (t < len_mbg));
+    if (need) {
+      float acc[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+      const float* wp = Wb + (size_t)mq * Kpad + kq_cl * 4;
+      const float* gp = dG_s + mq * BTP + mbg * 8;
+      const int iters = R / RS;
+#pragma unroll 4
+      for (int i = 0; i < iters; ++i) {
+        const float4 w = *reinterpret_cast<const float4*>(wp + (size_t)i * RS * Kpad);
+        const float4 da = *reinterpret_cast<const float4*>(gp + i * RS * BTP);
+        const float4 db = *reinterpret_cast<const float4*>(gp + i * RS * BTP + 4);
+        const float dv[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+          acc[b * 4 + 0] = fmaf(w.x, dv[b], acc[b * 4 + 0]);
+          acc[b * 4 + 1] = fmaf(w.y, dv[b], acc[b * 4 + 1]);
+          acc[b * 4 + 2] = fmaf(w.z, dv[b], acc[b * 4 + 2]);
+          acc[b * 4 + 3] = fmaf(w.w, dv[b], acc[b * 4 + 3]);
+        }
+      }
+      reduce_scatter<32, KS>(acc, lane);
+      if (kq_ok) {
+        // lane mq owns flat outputs [mq*NV, mq*NV+NV) of (b*4 + kk)
+        float* dst = scr + (size_t)rank * slab;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+          const int o = mq * NV + j, b = o >> 2, kk = o & 3;
+          dst[(size_t)(mbg * 8 + b) * Kpad + kquad * 4 + kk] = acc[j];
+        }
+      }
+    }
+    cluster_sync_all();  // partials of every CTA visible (release/acquire at cluster scope)
+
+    // ---- reduce my columns, finish the cell backward, publish d(gates) ----
+    if (a0) {
+      if (rec0) {
+        const float* src = scr + (size_t)ebl0 * Kpad + u_glob;
+        for (int r = 0; r < C; ++r) dh0 += ld_cg(src + (size_t)r * slab);
+      }
+      const float ig = g0[0], fg = g0[1], gg = g0[2], og = g0[3];
+      const float tc = tanhf(ct0);
+      const float dog = dh0 * tc * og * (1.f - og);
+      const float dc = dc0 + dh0 * og * (1.f - tc * tc);
+      const float dig = dc * gg * ig * (1.f - ig);
+      const float dfg = dc * cp0 * fg * (1.f - fg);
+      const float dgg = dc * ig * (1.f - gg * gg);
+      dc0 = dc * fg;
+      float* gp = p.gates + row0 * H8 + gcol;
+      gp[0] = dig; gp[H] = dfg; gp[2 * H] = dgg; gp[3 * H] = dog;
+      float* sp = dG_s + (u * 4) * BTP + ebl0;
+      sp[0] = dig; sp[BTP] = dfg; sp[2 * BTP] = dgg; sp[3 * BTP] = dog;
+    }
+    if (a1) {
+      if (rec1) {
+        const float* src = scr + (size_t)(ebl0 + 1) * Kpad + u_glob;
+        for (int r = 0; r < C; ++r) dh1 += ld_cg(src + (size_t)r * slab);
+      }
+      const float ig = g1[0], fg = g1[1], gg = g1[2], og = g1[3];
+      const float tc = tanhf(ct1);
+      const float dog = dh1 * tc * og * (1.f - og);
+      const float dc = dc1 + dh1 * og * (1.f - tc * tc);
+      const float dig = dc * gg * ig * (1.f - ig);
+      const float dfg = dc * cp1 * fg * (1.f - fg);
+      const float dgg = dc * ig * (1.f - gg * gg);
+      dc1 = dc * fg;
+      float* gp = p.gates + row1 * H8 + gcol;
+      gp[0] = dig; gp[H] = dfg; gp[2 * H] = dgg; gp[3 * H] = dog;
+      float* sp = dG_s + (u * 4) * BTP + ebl0 + 1;
+      sp[0] = dig; sp[BTP] = dfg; sp[2 * BTP] = dgg; sp[3 * BTP] = dog;
+    }
+    __syncthreads();  // dG_s complete before the next step's matvec
+  }
+  cluster_sync_all();
+}
+
+// h_{prev} operand of the hoisted dW_hh GEMM: hp[row][dir*H+u] = y at the forward-order
+// predecessor step of `row` in that direction, or 0 at the start of the sequence.
+__global__ void lstm_shift_kernel(const float* __restrict__ y, float* __restrict__ hp,
+                                  const int* __restrict__ row_t, const int* __restrict__ row_j,
+                                  const int* __restrict__ lens, const int* __restrict__ offsets,
+                                  int N, int H) {
+  const int row = blockIdx.x;
+  if (row >= N) return;
+  const int t = row_t[row], j = row_j[row], L = lens[j];
+  const int prev_f = t >= 1 ? offsets[t - 1] + j : -1;
+  const int prev_b = (t + 1 < L) ? offsets[t + 1] + j : -1;
+  const int H2 = 2 * H;
+  for (int c = threadIdx.x; c < H2; c += blockDim.x) {
+    const int src = c < H ? prev_f : prev_b;
+    hp[(size_t)row * H2 + c] = src >= 0 ? y[(size_t)src * H2 + c] : 0.f;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+struct LstmPlan {
+  int C, Hs, Kpad, BT, KS, n_tiles, threads_fwd, threads_bwd;
+  size_t smem_fwd, smem_bwd, scratch_bytes;
+};
+
+static int g_max_smem = 0;
+
+static int lstm_make_plan(int B, int H, int Tmax, LstmPlan* pl) {
+  if (g_max_smem == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return MMDA_ERR_CUDA;
+    if (cudaDeviceGetAttribute(&g_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) !=
+        cudaSuccess)
+      return MMDA_ERR_CUDA;
+  }
+  const int Kpad = (H + 3) & ~3;
+  // batch tile: large hidden sizes are shared-memory bound (W slice + h tile must fit), small
+  // ones want many CTAs
+  for (int C = 1; C <= 8; C *= 2) {
+    const int Hs = (H + C - 1) / C;
+    const int BT = (H > 128) ? 32 : 8;
+    const int BTP = BT + 4;
+    const int KS = (H > 128) ? 16 : 4;
+    const int RS = 32 / KS, R = (4 * Hs + RS - 1) / RS * RS;
+    const size_t misc = (size_t)(2 * BT + Tmax + 1) * 4;
+    const size_t fwd = (size_t)4 * Kpad * Hs * 4 + (size_t)Kpad * BTP * 4 + misc;
+    const size_t bwd = (size_t)R * Kpad * 4 + (size_t)R * BTP * 4 + misc;
+    if (fwd > (size_t)g_max_smem || bwd > (size_t)g_max_smem) continue;
+    const int UG = (Hs + 7) / 8, BG = BT / 8, K4 = Kpad / 4;
+    const int KG = (K4 + KS - 1) / KS;
+    const int wf = UG * BG, wb = (UG > KG ? UG : KG) * BG;
+    if (wf > 20 || wb > 20) continue;   // kernels are compiled for <= 640 threads
+    pl->C = C; pl->Hs = Hs; pl->Kpad = Kpad; pl->BT = BT; pl->KS = KS;
+    pl->n_tiles = (B + BT - 1) / BT;
+    pl->threads_fwd = wf * 32; pl->threads_bwd = wb * 32;
+    pl->smem_fwd = fwd; pl->smem_bwd = bwd;
+    pl->scratch_bytes = (size_t)2 * 2 * pl->n_tiles * C * BT * Kpad * sizeof(float);
+    return MMDA_OK;
+  }
+  mmda_set_error("lstm: hidden size %d does not fit the shared-memory resident W_hh plan", H);
+  return MMDA_ERR_UNSUPPORTED;
+}
+
+template <typename K>
+static int launch_cluster(K kern, const LstmArgs& a, const LstmPlan& pl, int threads, size_t smem,
+                          cudaStream_t st) {
+  MMDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(pl.C * pl.n_tiles, 2, 1);
+  cfg.blockDim = dim3(threads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = pl.C;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  MMDA_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
+  return MMDA_OK;
+}
+
+extern "C" {
+
+long long mmda_lstm_scratch_bytes(int B, int H) {
+  LstmPlan pl;
+  if (lstm_make_plan(B, H, 1, &pl) != MMDA_OK) return -1;
+  return (long long)pl.scratch_bytes;
+}
+
+// cluster size / units per CTA / batch tile the plan picks (for DESIGN.md, tests and the bench)
+int mmda_lstm_plan(int B, int H, int* out6) {
+  LstmPlan pl;
+  int rc = lstm_make_plan(B, H, 1, &pl);
+  if (rc != MMDA_OK) return rc;
+  out6[0] = pl.C; out6[1] = pl.Hs; out6[2] = pl.BT; out6[3] = pl.n_tiles;
+  out6[4] = (int)pl.smem_fwd; out6[5] = (int)pl.smem_bwd;
+  return MMDA_OK;
+}
+
+int mmda_lstm_forward(float* gates, const float* whh_f, const float* whh_r, float* y, float* c,
+                      const int* lens_sorted, const int* sorted_idx, const int* offsets,
+                      float* utt, int utt_ld, int utt_off_f, int utt_off_r, int B, int H, int Tmax,
+                      int save_for_backward, cudaStream_t stream) {
+  MMDA_REQUIRE(B > 0 && H > 0, "lstm_forward: bad sizes B=%d H=%d", B, H);
+  MMDA_REQUIRE(!save_for_backward || c != nullptr, "lstm_forward: c buffer required when saving");
+  LstmPlan pl;
+  int rc = lstm_make_plan(B, H, Tmax, &pl);
+  if (rc != MMDA_OK) return rc;
+  LstmArgs a = {};
+  a.Tmax = Tmax;
+  a.gates = gates; a.whh[0] = whh_f; a.whh[1] = whh_r; a.y = y; a.c = c;
+  a.lens = lens_sorted; a.sorted_idx = sorted_idx; a.offsets = offsets;
+  a.utt = utt; a.utt_ld = utt_ld; a.utt_off0 = utt_off_f; a.utt_off1 = utt_off_r;
+  a.B = B; a.H = H; a.Hs = pl.Hs; a.Kpad = pl.Kpad; a.C = pl.C; a.n_tiles = pl.n_tiles;
+  a.save = save_for_backward;
+  if (pl.BT == 32) return launch_cluster(lstm_fwd_kernel<32>, a, pl, pl.threads_fwd, pl.smem_fwd, stream);
+  return launch_cluster(lstm_fwd_kernel<8>, a, pl, pl.threads_fwd, pl.smem_fwd, stream);
+}
+
+int mmda_lstm_backward(float* gates, const float* whh_f, const float* whh_r, const float* c,
+                       const float* dy, const float* dutt, int utt_ld, int utt_off_f,
+                       int utt_off_r, const int* lens_sorted, const int* sorted_idx,
+                       const int* offsets, float* scratch, int B, int H, int Tmax,
+                       cudaStream_t stream) {
+  MMDA_REQUIRE(B > 0 && H > 0, "lstm_backward: bad sizes B=%d H=%d", B, H);
+  MMDA_REQUIRE(scratch != nullptr, "lstm_backward: scratch required (mmda_lstm_scratch_bytes)");
+  LstmPlan pl;
+  int rc = lstm_make_plan(B, H, Tmax, &pl);
+  if (rc != MMDA_OK) return rc;
+  LstmArgs a = {};
+  a.Tmax = Tmax;
+  a.gates = gates; a.whh[0] = whh_f; a.whh[1] = whh_r; a.c = const_cast<float*>(c);
+  a.dy = dy; a.dutt = dutt; a.utt_ld = utt_ld; a.utt_off0 = utt_off_f; a.utt_off1 = utt_off_r;
+  a.lens = lens_sorted; a.sorted_idx = sorted_idx; a.offsets = offsets; a.scratch = scratch;
+  a.B = B; a.H = H; a.Hs = pl.Hs; a.Kpad = pl.Kpad; a.C = pl.C; a.n_tiles = pl.n_tiles;
+  if (pl.BT == 32 && pl.KS == 16)
+    return launch_cluster(lstm_bwd_kernel<32, 16>, a, pl, pl.threads_bwd, pl.smem_bwd, stream);
+  return launch_cluster(lstm_bwd_kernel<8, 4>, a, pl, pl.threads_bwd, pl.smem_bwd, stream);
+}
+
+int mmda_lstm_shift_h(const float* y, float* hprev, const int* row_t, const int* row_j,
+                      const int* lens_sorted, const int* offsets, int N, int H,
+                      cudaStream_t stream) {
+  if (N <= 0) return MMDA_OK;
+  lstm_shift_kernel<<<N, 128, 0, stream>>>(y, hprev, row_t, row_j, lens_sorted, offsets, N, H);
+  MMDA_CHECK_LAUNCH();
+  return MMDA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,656 @@
+"""Host-side orchestration of the MISA forward / backward over libmmda_b200.so.
+
+``MisaEngine`` owns the device workspace (packed activations, saved gates, head buffers) and
+sequences the C-ABI kernels for one step.  It is used two ways:
+
+* level 1 (drop-in): ``MISA.forward`` wraps ``engine.forward`` in one ``torch.autograd.Function``
+  so the reference's own ``get_*_loss`` + ``loss.backward()`` (src/solver.py:163-183) work
+  unchanged; autograd hands the output gradients to ``engine.backward``.
+* level 2 (fused step): ``mmda_b200.trainer.FusedTrainer`` calls ``engine.forward``, the fused
+  loss kernels, ``engine.backward`` and the clip+Adam kernel with no autograd in the loop.
+
+PyTorch is used for device memory, streams and (in the trainer) ``torch.distributed`` only.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from ._lib import LIB, MmdaError
+from .config import ACTIVATIONS
+
+MODS = ("t", "v", "a")
+ENC = {"t": ("trnn1", "trnn2", "tlayer_norm"), "v": ("vrnn1", "vrnn2", "vlayer_norm"),
+       "a": ("arnn1", "arnn2", "alayer_norm")}
+PRIV_TAG = {"t": "1", "v": "1", "a": "3"}
+ACT_NONE, ACT_LEAKY, ACT_SIGMOID, ACT_RELU = 0, 1, 2, 3
+LN_EPS = 1e-5
+ATT_P = 0.1            # nn.TransformerEncoderLayer default dropout (reference src/models.py:160)
+NHEAD = 2
+TL = "transformer_encoder.layers.0."
+_DRYRUN = False       # tests only: exercise the host orchestration on CPU with a stubbed library
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+class Kernels:
+    """Thin typed wrappers: torch tensors in, C-ABI calls out (all on one stream)."""
+
+    def __init__(self):
+        self.stream = None
+        self.launches = 0
+
+    def bind_stream(self):
+        self.stream = 0 if _DRYRUN else torch.cuda.current_stream().cuda_stream
+
+    def _c(self, name, *args):
+        self.launches += 1
+        LIB.call(name, *args, self.stream)
+
+    # C = act(alpha * op(A) op(B) + beta*C + bias + bias2); A,B,C are 2-D views with unit inner stride
+    def gemm(self, A, B, C, ta=False, tb=False, alpha=1.0, beta=0.0, bias=None, bias2=None,
+             act=ACT_NONE, split_k=1):
+        M, N = C.shape
+        K = A.shape[0] if ta else A.shape[1]
+        assert A.stride(1) == 1 and B.stride(1) == 1 and C.stride(1) == 1
+        assert (A.shape[1] if ta else A.shape[0]) == M, (A.shape, C.shape, ta)
+        assert (B.shape[0] if tb else B.shape[1]) == N and (B.shape[1] if tb else B.shape[0]) == K, \
+            (A.shape, B.shape, C.shape, ta, tb)
+        self._c("mmda_sgemm", int(ta), int(tb), M, N, K, alpha, _ptr(A), A.stride(0), _ptr(B),
+                B.stride(0), beta, _ptr(C), C.stride(0), _ptr(bias), _ptr(bias2), act, split_k)
+
+    def linear(self, x, w, b, out, act=ACT_NONE, bias2=None):
+        self.gemm(x, w, out, tb=True, bias=b, bias2=bias2, act=act)
+
+    def linear_bwd(self, dy, x, w, dw, db, dx=None, dx_beta=0.0, db2=None):
+        """dy: grad of the linear output (pre-activation).  dw/db accumulate."""
+        self.gemm(dy, x, dw, ta=True, beta=1.0, split_k=0)
+        if db is not None:
+            self.colsum(dy, db, db2)
+        if dx is not None:
+            self.gemm(dy, w, dx, beta=dx_beta)
+
+    def colsum(self, x, out, out2=None):
+        self._c("mmda_colsum", _ptr(x), x.stride(0), x.shape[0], x.shape[1], _ptr(out), _ptr(out2))
+
+    def layernorm(self, x, res, g, b, y, mean, rstd):
+        self._c("mmda_layernorm_forward", _ptr(x), x.stride(0), _ptr(res),
+                0 if res is None else res.stride(0), _ptr(g), _ptr(b), _ptr(y), y.stride(0),
+                _ptr(mean), _ptr(rstd), x.shape[0], x.shape[1], LN_EPS)
+
+    def layernorm_bwd(self, dy, x, res, g, mean, rstd, dx, dg, db):
+        self._c("mmda_layernorm_backward", _ptr(dy), dy.stride(0), _ptr(x), x.stride(0), _ptr(res),
+                0 if res is None else res.stride(0), _ptr(g), _ptr(mean), _ptr(rstd), _ptr(dx),
+                dx.stride(0), _ptr(dg), _ptr(db), x.shape[0], x.shape[1])
+
+    def act(self, x, act):
+        self._c("mmda_act_forward", _ptr(x), x.stride(0), x.shape[0], x.shape[1], act)
+
+    def act_bwd(self, dy, y, act):
+        self._c("mmda_act_backward", _ptr(dy), dy.stride(0), _ptr(y), y.stride(0), dy.shape[0],
+                dy.shape[1], act)
+
+    def add(self, out, x, y=None, ax=1.0, ay=1.0):
+        self._c("mmda_add2d", _ptr(out), out.stride(0), _ptr(x), x.stride(0), ax, _ptr(y),
+                0 if y is None else y.stride(0), ay, out.shape[0], out.shape[1])
+
+    def dropout(self, x, out, p, seed, sid):
+        self._c("mmda_dropout", _ptr(x), _ptr(out), x.numel(), p, seed, sid)
+
+
+def _f32(*shape, device):
+    return torch.empty(*shape, dtype=torch.float32, device=device)
+
+
+class MisaEngine:
+    def __init__(self, model):
+        self.model = model
+        self.cfg = model.config
+        self.k = Kernels()
+        self.ws: Dict[str, torch.Tensor] = {}
+        self.act_id = ACTIVATIONS[model.act_name]
+        self.d = self.cfg.hidden_size
+        self.NC = self.cfg.num_classes
+        self.H = dict(zip(MODS, model.hidden_sizes))
+        self._pack_key = None
+        self._params = None
+        self._params_ver = None
+        self._dev = None
+        self.seed = 0x5EED
+        self.step_id = 0
+        if self.cfg.use_bert:
+            raise NotImplementedError(
+                "use_bert=True: the BERT text branch is the next scope row (SURVEY.md 8f N1); "
+                "this build covers the LSTM text encoder")
+
+    # ---------------------------------------------------------------- buffers -------------
+    def buf(self, name, *shape, dtype=torch.float32, zero=False):
+        dev = self._dev
+        t = self.ws.get(name)
+        n = 1
+        for s in shape:
+            n *= s
+        if t is None or t.numel() < n or t.dtype != dtype or t.device != dev:
+            t = torch.empty(max(n, 1), dtype=dtype, device=dev)
+            self.ws[name] = t
+        v = t[:n].view(*shape)
+        if zero:
+            v.zero_()
+        return v
+
+    @property
+    def device(self):
+        self.params()
+        return self._dev
+
+    def params(self) -> Dict[str, torch.Tensor]:
+        # re-read when the module's tensors were replaced (.to(), embed.weight.data = ...)
+        ver = tuple(p.data_ptr() for p in self.model.parameters())
+        if self._params_ver != ver:
+            self._dev = next(self.model.parameters()).device
+            self._params = {n: p.data for n, p in self.model.named_parameters()}
+            self._params_ver = ver
+            for n, p in self._params.items():
+                if not p.is_cuda and not _DRYRUN:
+                    raise MmdaError(f"parameter {n} is on {p.device}: the MISA hot path runs on a "
+                                    "B200 only (no CPU fallback); call model.to('cuda') first")
+                if p.dtype != torch.float32 or not p.is_contiguous():
+                    raise MmdaError(f"parameter {n} must be contiguous float32")
+        return self._params
+
+    # ---------------------------------------------------------------- packing -------------
+    def _pack(self, lengths_cpu: torch.Tensor):
+        """Same descending sort torch's pack_padded_sequence runs on the CPU lengths (so the
+        permutation is bit-identical), then device-side batch_sizes / offsets / row maps."""
+        if lengths_cpu.is_cuda:
+            raise MmdaError("lengths must stay on the CPU (reference src/solver.py:149)")
+        ln = lengths_cpu.to(torch.int64)
+        key = (ln.numel(), tuple(ln.tolist()))
+        if key == self._pack_key:
+            return self._pack_info
+        if ln.numel() == 0 or int(ln.min()) <= 0:
+            raise MmdaError("every sequence length must be >= 1 (pack_padded_sequence raises too)")
+        ls, si = torch.sort(ln, descending=True)
+        B, Tmax, N = ln.numel(), int(ls[0]), int(ln.sum())
+        host = torch.empty(2 * B, dtype=torch.int32)
+        if not _DRYRUN:
+            host = host.pin_memory()
+        host[:B] = ls.to(torch.int32)
+        host[B:] = si.to(torch.int32)
+        dev = self.buf("pack_in", 2 * B, dtype=torch.int32)
+        dev.copy_(host, non_blocking=True)
+        bs = self.buf("batch_sizes", Tmax, dtype=torch.int32)
+        off = self.buf("offsets", Tmax + 1, dtype=torch.int32)
+        row_t = self.buf("row_t", N, dtype=torch.int32)
+        row_j = self.buf("row_j", N, dtype=torch.int32)
+        self.k._c("mmda_pack_build", _ptr(dev[:B]), B, Tmax, N, _ptr(bs), _ptr(off), _ptr(row_t),
+                  _ptr(row_j))
+        self._host_keepalive = host
+        self._pack_info = dict(B=B, Tmax=Tmax, N=N, lens=dev[:B], sidx=dev[B:], bs=bs, off=off,
+                               row_t=row_t, row_j=row_j, sorted_idx_cpu=si, lens_sorted_cpu=ls)
+        self._pack_key = key
+        return self._pack_info
+
+    # ---------------------------------------------------------------- GEMM routing ---------
+    def big_gemm(self, *a, **kw):
+        """Hoisted LSTM GEMMs.  fp32 mode: exact fp32 SIMT path."""
+        self.k.gemm(*a, **kw)
+
+    # ---------------------------------------------------------------- forward --------------
+    def _encode(self, m, X, pk, train, P):
+        """reference src/models.py:163-180 + :203 for modality m on the packed rows X (N,I)."""
+        k, H = self.k, self.H[m]
+        r1, r2, ln = ENC[m]
+        N, B, Tmax = pk["N"], pk["B"], pk["Tmax"]
+        utt = self.buf(f"utt_{m}", B, 4 * H)
+        G1 = self.buf(f"G1_{m}", N, 8 * H)
+        Y1 = self.buf(f"Y1_{m}", N, 2 * H)
+        C1 = self.buf(f"C1_{m}", N, 2 * H)
+        Y1n = self.buf(f"Y1n_{m}", N, 2 * H)
+        G2 = self.buf(f"G2_{m}", N, 8 * H)
+        Y2 = self.buf(f"Y2_{m}", N, 2 * H)
+        C2 = self.buf(f"C2_{m}", N, 2 * H)
+        mu = self.buf(f"ln_mu_{m}", N)
+        rs = self.buf(f"ln_rs_{m}", N)
+        for G, Xin, r in ((G1, X, r1), (G2, Y1n, r2)):
+            if r == r2:
+                k.layernorm(Y1, None, P[f"{ln}.weight"], P[f"{ln}.bias"], Y1n, mu, rs)
+            for di, suf in enumerate(("", "_reverse")):
+                self.big_gemm(Xin, P[f"{r}.weight_ih_l0{suf}"], G[:, di * 4 * H:(di + 1) * 4 * H],
+                              tb=True, bias=P[f"{r}.bias_ih_l0{suf}"],
+                              bias2=P[f"{r}.bias_hh_l0{suf}"])
+            Y, C = (Y1, C1) if r == r1 else (Y2, C2)
+            o_f, o_r = (0, 2 * H) if r == r1 else (H, 3 * H)
+            k._c("mmda_lstm_forward", _ptr(G), _ptr(P[f"{r}.weight_hh_l0"]),
+                 _ptr(P[f"{r}.weight_hh_l0_reverse"]), _ptr(Y), _ptr(C), _ptr(pk["lens"]),
+                 _ptr(pk["sidx"]), _ptr(pk["off"]), _ptr(utt), 4 * H, o_f, o_r, B, H, Tmax,
+                 int(train))
+        return utt
+
+    def forward(self, sentences, visual, acoustic, lengths, train: bool, want_sp: bool = True,
+                dropout: Optional[bool] = None):
+        """Returns a dict of device tensors (views into the workspace, valid until the next call).
+        ``train`` keeps what the backward needs; ``dropout`` (default: = model.training) enables
+        the five Bernoulli sites."""
+        k, cfg, d, NC = self.k, self.cfg, self.d, self.NC
+        P = self.params()
+        k.bind_stream()
+        for name, t in (("sentences", sentences), ("visual", visual), ("acoustic", acoustic)):
+            if not t.is_cuda and not _DRYRUN:
+                raise MmdaError(f"{name} must be a CUDA tensor (reference moves it with to_gpu)")
+        pk = self._pack(lengths)
+        B, N, Tmax = pk["B"], pk["N"], pk["Tmax"]
+        if sentences.shape[0] < Tmax or sentences.shape[1] != B:
+            raise MmdaError(f"sentences {tuple(sentences.shape)} inconsistent with lengths")
+        drop = self.model.training if dropout is None else dropout
+        self.drop_on = bool(drop)
+        self.step_id += 1
+        seed = (self.seed * 1000003 + self.step_id) & 0xFFFFFFFFFFFFFFFF
+        self.cur_seed = seed
+        p_cls = float(cfg.dropout) if drop else 0.0
+        p_att = ATT_P if drop else 0.0
+        self.p_cls, self.p_att = p_cls, p_att
+
+        # ---- encoders on packed rows ----
+        sent = sentences.contiguous()
+        Xt = self.buf("X_t", N, self.H["t"])
+        V = P["embed.weight"].shape[0]
+        k._c("mmda_embedding_forward", _ptr(P["embed.weight"]), _ptr(sent), _ptr(Xt),
+             _ptr(pk["row_t"]), _ptr(pk["row_j"]), _ptr(pk["sidx"]), N, B, self.H["t"], V)
+        X = {"t": Xt}
+        for m, src in (("v", visual), ("a", acoustic)):
+            src = src.contiguous()
+            if src.dtype != torch.float32 or src.shape[1] != B or src.shape[2] != self.H[m]:
+                raise MmdaError(f"{m} input has shape {tuple(src.shape)} / {src.dtype}")
+            X[m] = self.buf(f"X_{m}", N, self.H[m])
+            k._c("mmda_gather_rows", _ptr(src), _ptr(X[m]), _ptr(pk["row_t"]), _ptr(pk["row_j"]),
+                 _ptr(pk["sidx"]), N, B, self.H[m])
+        self.saved = dict(pk=pk, sent=sent, X=X, train=train)
+        utt = {m: self._encode(m, X[m], pk, train, P) for m in MODS}
+
+        # ---- heads: project -> private/shared -> recon (src/models.py:254-279) ----
+        A = self.buf("A", 3, B, d)             # activation output (pre-LN)
+        O = self.buf("O", 3, B, d)             # utt_m_orig
+        X0 = self.buf("X0", B, 6, d)           # tokens [p_t,p_v,p_a,s_t,s_v,s_a]
+        SUM = self.buf("SUM", 3, B, d)         # utt_m = private + shared
+        R = self.buf("R", 3, B, d)             # utt_m_recon
+        pmu = self.buf("proj_mu", 3, B)
+        prs = self.buf("proj_rs", 3, B)
+        X0f = X0.view(B, 6 * d)
+        for i, m in enumerate(MODS):
+            k.linear(utt[m], P[f"project_{m}.project_{m}.weight"], P[f"project_{m}.project_{m}.bias"],
+                     A[i], act=self.act_id)
+            k.layernorm(A[i], None, P[f"project_{m}.project_{m}_layer_norm.weight"],
+                        P[f"project_{m}.project_{m}_layer_norm.bias"], O[i], pmu[i], prs[i])
+            tag = PRIV_TAG[m]
+            k.linear(O[i], P[f"private_{m}.private_{m}_{tag}.weight"],
+                     P[f"private_{m}.private_{m}_{tag}.bias"], X0f[:, i * d:(i + 1) * d],
+                     act=ACT_SIGMOID)
+            k.linear(O[i], P["shared.shared_1.weight"], P["shared.shared_1.bias"],
+                     X0f[:, (3 + i) * d:(4 + i) * d], act=ACT_SIGMOID)
+            k.add(SUM[i], X0f[:, i * d:(i + 1) * d], X0f[:, (3 + i) * d:(4 + i) * d])
+            k.linear(SUM[i], P[f"recon_{m}.recon_{m}_1.weight"], P[f"recon_{m}.recon_{m}_1.bias"],
+                     R[i])
+        out = {}
+        if want_sp:        # outputs no loss reads (src/models.py:234-237); kept for the contract
+            SP = self.buf("SP", 4, B, 4)
+            smean = self.buf("smean", B, d)
+            w, b = (P["sp_discriminator.sp_discriminator_layer_1.weight"],
+                    P["sp_discriminator.sp_discriminator_layer_1.bias"])
+            for i in range(3):
+                k.linear(X0f[:, i * d:(i + 1) * d], w, b, SP[i])
+            k.add(smean, X0f[:, 3 * d:4 * d], X0f[:, 4 * d:5 * d], 1.0 / 3.0, 1.0 / 3.0)
+            k.add(smean, smean, X0f[:, 5 * d:6 * d], 1.0, 1.0 / 3.0)
+            k.linear(smean, w, b, SP[3])
+            for i, m in enumerate(MODS):
+                out[f"shared_or_private_p_{m}"] = SP[i]
+            out["shared_or_private_s"] = SP[3]
+
+        # ---- fusion: post-norm encoder layer over the 6 tokens of each sample ----
+        rows = B * 6
+        Xr = X0.view(rows, d)
+        QKV = self.buf("QKV", rows, 3 * d)
+        PR = self.buf("PROBS", B, NHEAD, 6, 6)
+        CTX = self.buf("CTX", rows, d)
+        AO = self.buf("AO", rows, d)
+        X1 = self.buf("X1", rows, d)
+        F1 = self.buf("F1", rows, P[TL + "linear1.weight"].shape[0])
+        F2 = self.buf("F2", rows, d)
+        X2 = self.buf("X2", rows, d)
+        lnm = self.buf("enc_mu", 2, rows)
+        lnr = self.buf("enc_rs", 2, rows)
+        k.linear(Xr, P[TL + "self_attn.in_proj_weight"], P[TL + "self_attn.in_proj_bias"], QKV)
+        k._c("mmda_attention_forward", _ptr(QKV), _ptr(CTX), _ptr(PR), B, 6, NHEAD, d // NHEAD,
+             p_att, seed, 1)
+        k.linear(CTX, P[TL + "self_attn.out_proj.weight"], P[TL + "self_attn.out_proj.bias"], AO)
+        if p_att > 0:
+            k.dropout(AO, AO, p_att, seed, 2)
+        k.layernorm(Xr, AO, P[TL + "norm1.weight"], P[TL + "norm1.bias"], X1, lnm[0], lnr[0])
+        k.linear(X1, P[TL + "linear1.weight"], P[TL + "linear1.bias"], F1, act=ACT_RELU)
+        if p_att > 0:
+            k.dropout(F1, F1, p_att, seed, 3)
+        k.linear(F1, P[TL + "linear2.weight"], P[TL + "linear2.bias"], F2)
+        if p_att > 0:
+            k.dropout(F2, F2, p_att, seed, 4)
+        k.layernorm(X1, F2, P[TL + "norm2.weight"], P[TL + "norm2.bias"], X2, lnm[1], lnr[1])
+
+        # ---- confidence / classifier / labels (src/models.py:247-249) ----
+        Hf = X2.view(B, 6 * d)
+        TCP = self.buf("TCP", B, 6)
+        SC = self.buf("SCORES", B, NC)
+        LAB = self.buf("LABELS", B, NC)
+        k.linear(Hf, P["confidence.confidence_layer_1.weight"],
+                 P["confidence.confidence_layer_1.bias"], TCP, act=ACT_SIGMOID)
+        if p_cls > 0:
+            k.linear(Hf, P["classifier.classifier_layer.weight"],
+                     P["classifier.classifier_layer.bias"], SC)
+            k.dropout(SC, SC, p_cls, seed, 5)
+            k.act(SC, ACT_SIGMOID)
+        else:
+            k.linear(Hf, P["classifier.classifier_layer.weight"],
+                     P["classifier.classifier_layer.bias"], SC, act=ACT_SIGMOID)
+        k._c("mmda_threshold", _ptr(SC), _ptr(LAB), SC.numel(), float(cfg.threshold))
+
+        for i, m in enumerate(MODS):
+            out[f"utterance_{m}"] = utt[m]
+            out[f"utt_{m}_orig"] = O[i]
+            out[f"utt_private_{m}"] = X0[:, i, :]
+            out[f"utt_shared_{m}"] = X0[:, 3 + i, :]
+            out[f"utt_{m}"] = SUM[i]
+            out[f"utt_{m}_recon"] = R[i]
+        out.update(tcp=TCP, scores=SC, labels=LAB, tokens=X0, orig=O, recon=R, fused=Hf)
+        self.saved.update(utt=utt, B=B)
+        return out
+
+    # ---------------------------------------------------------------- backward -------------
+    def backward(self, G: Dict[str, torch.Tensor], d_scores=None, d_tcp=None, d_tokens=None,
+                 d_orig=None, d_recon=None, d_sp=None, on_ready=None):
+        """Accumulates parameter gradients into ``G[name]`` (tensors shaped like the parameters).
+
+        d_scores, d_tcp (B,NC); d_tokens (B,6,d) grad wrt [p_t,p_v,p_a,s_t,s_v,s_a]; d_orig,
+        d_recon (3,B,d); d_sp (4,B,4); any may be None.  ``on_ready(tag)`` is called after the
+        kernels producing the gradients of a parameter group have been enqueued (the
+        data-parallel trainer uses it to launch bucketed all-reduces)."""
+        k, d, NC = self.k, self.d, self.NC
+        P = self.params()
+        k.bind_stream()
+        sv = self.saved
+        if not sv.get("train"):
+            raise MmdaError("backward() needs a forward(train=True)")
+        B, pk = sv["B"], sv["pk"]
+        rows = B * 6
+        ws = self.ws
+        X0 = self.buf("X0", B, 6, d)
+        X0f, Xr = X0.view(B, 6 * d), X0.view(rows, d)
+        O, A, SUM = self.buf("O", 3, B, d), self.buf("A", 3, B, d), self.buf("SUM", 3, B, d)
+        QKV, PR = self.buf("QKV", rows, 3 * d), self.buf("PROBS", B, NHEAD, 6, 6)
+        CTX, AO, X1 = self.buf("CTX", rows, d), self.buf("AO", rows, d), self.buf("X1", rows, d)
+        FF = P[TL + "linear1.weight"].shape[0]
+        F1, F2, X2 = self.buf("F1", rows, FF), self.buf("F2", rows, d), self.buf("X2", rows, d)
+        lnm, lnr = self.buf("enc_mu", 2, rows), self.buf("enc_rs", 2, rows)
+        Hf = X2.view(B, 6 * d)
+        TCP, SC = self.buf("TCP", B, 6), self.buf("SCORES", B, NC)
+        seed, p_att, p_cls = self.cur_seed, self.p_att, self.p_cls
+        notify = on_ready or (lambda tag: None)
+
+        # ---- classifier / confidence ----
+        dHf = self.buf("dHf", B, 6 * d)
+        have = False
+        if d_scores is not None:
+            dl = self.buf("dLOGIT", B, NC)
+            k.add(dl, d_scores)
+            k.act_bwd(dl, SC, ACT_SIGMOID)
+            if p_cls > 0:
+                k.dropout(dl, dl, p_cls, seed, 5)
+            k.linear_bwd(dl, Hf, P["classifier.classifier_layer.weight"],
+                         G["classifier.classifier_layer.weight"],
+                         G["classifier.classifier_layer.bias"], dHf, 0.0)
+            have = True
+        if d_tcp is not None:
+            dt = self.buf("dTCPpre", B, 6)
+            k.add(dt, d_tcp)
+            k.act_bwd(dt, TCP, ACT_SIGMOID)
+            k.linear_bwd(dt, Hf, P["confidence.confidence_layer_1.weight"],
+                         G["confidence.confidence_layer_1.weight"],
+                         G["confidence.confidence_layer_1.bias"], dHf, 1.0 if have else 0.0)
+            have = True
+        dX0 = self.buf("dX0", B, 6, d)
+        dX0f, dXr = dX0.view(B, 6 * d), dX0.view(rows, d)
+        if have:
+            # ---- fusion layer backward ----
+            dS2 = self.buf("dS2", rows, d)
+            k.layernorm_bwd(dHf.view(rows, d), X1, F2, P[TL + "norm2.weight"], lnm[1], lnr[1], dS2,
+                            G[TL + "norm2.weight"], G[TL + "norm2.bias"])
+            dF2 = dS2
+            if p_att > 0:
+                dF2 = self.buf("dF2", rows, d)
+                k.dropout(dS2, dF2, p_att, seed, 4)
+            dF1 = self.buf("dF1", rows, FF)
+            k.linear_bwd(dF2, F1, P[TL + "linear2.weight"], G[TL + "linear2.weight"],
+                         G[TL + "linear2.bias"], dF1, 0.0)
+            if p_att > 0:
+                k.dropout(dF1, dF1, p_att, seed, 3)
+            k.act_bwd(dF1, F1, ACT_RELU)
+            # dX1 = dS2 + dF1 W1   (accumulate in place into dS2)
+            k.linear_bwd(dF1, X1, P[TL + "linear1.weight"], G[TL + "linear1.weight"],
+                         G[TL + "linear1.bias"], dS2, 1.0)
+            dS1 = self.buf("dS1", rows, d)
+            k.layernorm_bwd(dS2, Xr, AO, P[TL + "norm1.weight"], lnm[0], lnr[0], dS1,
+                            G[TL + "norm1.weight"], G[TL + "norm1.bias"])
+            dAO = dS1
+            if p_att > 0:
+                dAO = self.buf("dAO", rows, d)
+                k.dropout(dS1, dAO, p_att, seed, 2)
+            dCTX = self.buf("dCTX", rows, d)
+            k.linear_bwd(dAO, CTX, P[TL + "self_attn.out_proj.weight"],
+                         G[TL + "self_attn.out_proj.weight"], G[TL + "self_attn.out_proj.bias"],
+                         dCTX, 0.0)
+            dQKV = self.buf("dQKV", rows, 3 * d)
+            k._c("mmda_attention_backward", _ptr(QKV), _ptr(PR), _ptr(dCTX), _ptr(dQKV), B, 6,
+                 NHEAD, d // NHEAD, p_att, seed, 1)
+            # dX0 = dS1 + dQKV W_in
+            k.add(dXr, dS1)
+            k.linear_bwd(dQKV, Xr, P[TL + "self_attn.in_proj_weight"],
+                         G[TL + "self_attn.in_proj_weight"], G[TL + "self_attn.in_proj_bias"],
+                         dXr, 1.0)
+            if d_tokens is not None:
+                k.add(dXr, dXr, d_tokens.view(rows, d))
+        elif d_tokens is not None:
+            k.add(dXr, d_tokens.view(rows, d))
+        else:
+            dX0.zero_()
+        notify("fusion")
+
+        # ---- sp discriminator (only if somebody asked for its gradient) ----
+        if d_sp is not None:
+            w = P["sp_discriminator.sp_discriminator_layer_1.weight"]
+            gw, gb = (G["sp_discriminator.sp_discriminator_layer_1.weight"],
+                      G["sp_discriminator.sp_discriminator_layer_1.bias"])
+            smean = self.buf("smean", B, d)
+            dsm = self.buf("dsmean", B, d)
+            for i in range(3):
+                k.linear_bwd(d_sp[i], X0f[:, i * d:(i + 1) * d], w, gw, gb,
+                             dX0f[:, i * d:(i + 1) * d], 1.0)
+            k.linear_bwd(d_sp[3], smean, w, gw, gb, dsm, 0.0)
+            for i in range(3):
+                sl = dX0f[:, (3 + i) * d:(4 + i) * d]
+                k.add(sl, sl, dsm, 1.0, 1.0 / 3.0)
+
+        # ---- recon / private / shared / project ----
+        dO = self.buf("dO", 3, B, d)
+        dA = self.buf("dA", 3, B, d)
+        dutt = {}
+        for i, m in enumerate(MODS):
+            ps, ss = dX0f[:, i * d:(i + 1) * d], dX0f[:, (3 + i) * d:(4 + i) * d]
+            if d_recon is not None:
+                dsum = self.buf("dSUM", B, d)
+                k.linear_bwd(d_recon[i], SUM[i], P[f"recon_{m}.recon_{m}_1.weight"],
+                             G[f"recon_{m}.recon_{m}_1.weight"], G[f"recon_{m}.recon_{m}_1.bias"],
+                             dsum, 0.0)
+                k.add(ps, ps, dsum)
+                k.add(ss, ss, dsum)
+            k.act_bwd(ps, X0f[:, i * d:(i + 1) * d], ACT_SIGMOID)
+            k.act_bwd(ss, X0f[:, (3 + i) * d:(4 + i) * d], ACT_SIGMOID)
+            tag = PRIV_TAG[m]
+            has_do = d_orig is not None
+            if has_do:
+                k.add(dO[i], d_orig[i])
+            k.linear_bwd(ps, O[i], P[f"private_{m}.private_{m}_{tag}.weight"],
+                         G[f"private_{m}.private_{m}_{tag}.weight"],
+                         G[f"private_{m}.private_{m}_{tag}.bias"], dO[i], 1.0 if has_do else 0.0)
+            k.linear_bwd(ss, O[i], P["shared.shared_1.weight"], G["shared.shared_1.weight"],
+                         G["shared.shared_1.bias"], dO[i], 1.0)
+            pmu, prs = self.buf("proj_mu", 3, B), self.buf("proj_rs", 3, B)
+            k.layernorm_bwd(dO[i], A[i], None, P[f"project_{m}.project_{m}_layer_norm.weight"],
+                            pmu[i], prs[i], dA[i], G[f"project_{m}.project_{m}_layer_norm.weight"],
+                            G[f"project_{m}.project_{m}_layer_norm.bias"])
+            k.act_bwd(dA[i], A[i], self.act_id)
+            dutt[m] = self.buf(f"dutt_{m}", B, 4 * self.H[m])
+            k.linear_bwd(dA[i], sv["utt"][m], P[f"project_{m}.project_{m}.weight"],
+                         G[f"project_{m}.project_{m}.weight"], G[f"project_{m}.project_{m}.bias"],
+                         dutt[m], 0.0)
+        notify("heads")
+
+        # ---- encoders: BPTT + hoisted weight-gradient GEMMs ----
+        for m in ("v", "a", "t"):       # text last: its gradients are the biggest bucket
+            self._encode_backward(m, dutt[m], G, pk, P)
+            notify(f"enc_{m}")
+
+    def _encode_backward(self, m, dutt, G, pk, P):
+        k, H = self.k, self.H[m]
+        r1, r2, ln = ENC[m]
+        N, B, Tmax = pk["N"], pk["B"], pk["Tmax"]
+        X = self.saved["X"][m]
+        G1, G2 = self.buf(f"G1_{m}", N, 8 * H), self.buf(f"G2_{m}", N, 8 * H)
+        Y1, Y2 = self.buf(f"Y1_{m}", N, 2 * H), self.buf(f"Y2_{m}", N, 2 * H)
+        C1, C2 = self.buf(f"C1_{m}", N, 2 * H), self.buf(f"C2_{m}", N, 2 * H)
+        Y1n = self.buf(f"Y1n_{m}", N, 2 * H)
+        mu, rs = self.buf(f"ln_mu_{m}", N), self.buf(f"ln_rs_{m}", N)
+        nbytes = LIB.raw("mmda_lstm_scratch_bytes")(B, H)
+        if nbytes < 0:
+            raise MmdaError(LIB.raw("mmda_last_error")().decode())
+        scratch = self.buf("lstm_scratch", max(1, nbytes // 4))
+        HP = self.buf(f"HP_{m}", N, 2 * H)
+        dY1n = self.buf(f"dY1n_{m}", N, 2 * H)
+        dY1 = self.buf(f"dY1_{m}", N, 2 * H)
+        for r, Gt, Y, C, Xin, dy, (o_f, o_r) in ((r2, G2, Y2, C2, Y1n, None, (H, 3 * H)),
+                                                 (r1, G1, Y1, C1, X, dY1, (0, 2 * H))):
+            if r == r1:
+                k.layernorm_bwd(dY1n, Y1, None, P[f"{ln}.weight"], mu, rs, dY1, G[f"{ln}.weight"],
+                                G[f"{ln}.bias"])
+            k._c("mmda_lstm_backward", _ptr(Gt), _ptr(P[f"{r}.weight_hh_l0"]),
+                 _ptr(P[f"{r}.weight_hh_l0_reverse"]), _ptr(C), _ptr(dy), _ptr(dutt), 4 * H, o_f,
+                 o_r, _ptr(pk["lens"]), _ptr(pk["sidx"]), _ptr(pk["off"]), _ptr(scratch), B, H,
+                 Tmax)
+            k._c("mmda_lstm_shift_h", _ptr(Y), _ptr(HP), _ptr(pk["row_t"]), _ptr(pk["row_j"]),
+                 _ptr(pk["lens"]), _ptr(pk["off"]), N, H)
+            for di, suf in enumerate(("", "_reverse")):
+                dG = Gt[:, di * 4 * H:(di + 1) * 4 * H]
+                self.big_gemm(dG, Xin, G[f"{r}.weight_ih_l0{suf}"], ta=True, beta=1.0, split_k=0)
+                self.big_gemm(dG, HP[:, di * H:(di + 1) * H], G[f"{r}.weight_hh_l0{suf}"], ta=True,
+                              beta=1.0, split_k=0)
+                k.colsum(dG, G[f"{r}.bias_ih_l0{suf}"], G[f"{r}.bias_hh_l0{suf}"])
+            if r == r2 or m == "t":
+                dX = dY1n if r == r2 else self.buf("dX_t", N, H)
+                for di, suf in enumerate(("", "_reverse")):
+                    self.big_gemm(Gt[:, di * 4 * H:(di + 1) * 4 * H], P[f"{r}.weight_ih_l0{suf}"],
+                                  dX, beta=0.0 if di == 0 else 1.0)
+                if r == r1:
+                    V = P["embed.weight"].shape[0]
+                    k._c("mmda_embedding_backward", _ptr(G["embed.weight"]),
+                         _ptr(self.saved["sent"]), _ptr(dX), _ptr(pk["row_t"]), _ptr(pk["row_j"]),
+                         _ptr(pk["sidx"]), N, B, H, V)
+
+
+# ------------------------------------------------------------------------------------------
+# level 1: autograd bridge used by MISA.forward
+# ------------------------------------------------------------------------------------------
+_DIFF_OUT = ("scores", "tcp") + tuple(f"utt_private_{m}" for m in MODS) + \
+    tuple(f"utt_shared_{m}" for m in MODS) + tuple(f"utt_{m}_orig" for m in MODS) + \
+    tuple(f"utt_{m}_recon" for m in MODS) + tuple(f"utt_{m}" for m in MODS) + \
+    tuple(f"shared_or_private_p_{m}" for m in MODS) + ("shared_or_private_s",)
+
+
+class _MisaFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, sentences, visual, acoustic, lengths, names, *params):
+        eng = model.engine
+        out = eng.forward(sentences, visual, acoustic, lengths, train=True, want_sp=True)
+        ctx.model, ctx.names, ctx.fwd_step = model, names, eng.step_id
+        res = tuple(out[n].clone() for n in _DIFF_OUT) + (out["labels"].clone(),)
+        ctx.mark_non_differentiable(res[-1])
+        return res
+
+    @staticmethod
+    def backward(ctx, *g):
+        model, eng = ctx.model, ctx.model.engine
+        if eng.step_id != ctx.fwd_step:
+            raise MmdaError("backward() after a newer forward(): the engine keeps one step of "
+                            "saved activations")
+        gd = dict(zip(_DIFF_OUT, g[:-1]))
+        dev, d = eng.device, eng.d
+        B = eng.saved["B"]
+
+        def stack(keys, shape):
+            if all(gd[kk] is None for kk in keys):
+                return None
+            t = torch.zeros(shape, dtype=torch.float32, device=dev)
+            for i, kk in enumerate(keys):
+                if gd[kk] is not None:
+                    t[i].copy_(gd[kk])
+            return t
+
+        d_tok = stack([f"utt_private_{m}" for m in MODS] + [f"utt_shared_{m}" for m in MODS],
+                      (6, B, d))
+        # utt_m = private + shared feeds both tokens
+        for i, m in enumerate(MODS):
+            if gd[f"utt_{m}"] is not None:
+                if d_tok is None:
+                    d_tok = torch.zeros(6, B, d, dtype=torch.float32, device=dev)
+                d_tok[i] += gd[f"utt_{m}"]
+                d_tok[3 + i] += gd[f"utt_{m}"]
+        if d_tok is not None:
+            d_tok = d_tok.permute(1, 0, 2).contiguous()
+        d_orig = stack([f"utt_{m}_orig" for m in MODS], (3, B, d))
+        d_recon = stack([f"utt_{m}_recon" for m in MODS], (3, B, d))
+        d_sp = stack([f"shared_or_private_p_{m}" for m in MODS] + ["shared_or_private_s"],
+                     (4, B, 4))
+        ds = None if gd["scores"] is None else gd["scores"].contiguous()
+        dt = None if gd["tcp"] is None else gd["tcp"].contiguous()
+        P = eng.params()
+        sizes = [P[n].numel() for n in ctx.names]
+        arena = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        G, off = {}, 0
+        for n, sz in zip(ctx.names, sizes):
+            G[n] = arena[off:off + sz].view(P[n].shape)
+            off += sz
+        eng.backward(G, d_scores=ds, d_tcp=dt, d_tokens=d_tok, d_orig=d_orig, d_recon=d_recon,
+                     d_sp=d_sp)
+        untouched = set()
+        if d_sp is None:
+            untouched.add("sp_discriminator.")
+        if dt is None:
+            untouched.add("confidence.")
+        grads = tuple(None if any(n.startswith(u) for u in untouched) else G[n] for n in ctx.names)
+        return (None,) * 6 + grads
+
+
+def misa_apply(model, sentences, visual, acoustic, lengths, bert_sent, bert_sent_type,
+               bert_sent_mask):
+    eng = model.engine
+    named = list(model.named_parameters())
+    needs_grad = torch.is_grad_enabled() and any(p.requires_grad for _, p in named)
+    if needs_grad:
+        names = tuple(n for n, _ in named)
+        res = _MisaFunction.apply(model, sentences, visual, acoustic, lengths, names,
+                                  *[p for _, p in named])
+        out = dict(zip(_DIFF_OUT, res[:-1]))
+        out["labels"] = res[-1]
+        return out
+    o = eng.forward(sentences, visual, acoustic, lengths, train=False, want_sp=True)
+    out = {n: o[n].clone() for n in _DIFF_OUT}
+    out["labels"] = o["labels"].clone()
+    return out

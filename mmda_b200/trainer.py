@@ -1,0 +1,252 @@
+"""Level-2 fused training step: the reference's ``Solver.train`` inner loop
+(src/solver.py:139-193: zero_grad, forward, six losses, weighted sum, backward,
+clip_grad_value_, Adam.step) with no autograd, every stage a C-ABI kernel, parameters / gradients
+/ Adam moments in flat 16-byte aligned arenas, and -- when a process group is given -- batch-
+sharded data parallelism with exact global-batch semantics:
+
+* the three loss statistics segments are all-reduced between loss phases (SURVEY.md row D1:
+  DiffLoss, CMD and the conf loss are statistics over the batch axis and do not decompose);
+* parameter gradients are all-reduced per bucket (fusion+classifier | heads | visual | acoustic |
+  text encoder + embedding) as soon as the backward has produced them, overlapping the remaining
+  BPTT; buckets are contiguous ranges of the gradient arena.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from ._lib import MmdaError
+from . import engine as _engine
+from .engine import MODS, _ptr
+
+ALIGN = 64      # floats; every parameter starts on a 256-byte boundary of the arena
+DIFF_PAIRS = ((0, 3), (1, 4), (2, 5), (2, 0), (2, 1), (0, 1))   # solver.py:432-439, token ids
+LOSS_NAMES = ("cls", "diff", "sim", "recon", "conf", "total")
+
+
+def bucket_of(name: str) -> int:
+    """Gradient-ready order of the backward (engine.backward): 0 fusion+classifier, 1 heads,
+    2 visual encoder, 3 acoustic encoder, 4 text encoder + embedding, 5 never (no gradient)."""
+    if name.startswith(("transformer_encoder.", "classifier.", "confidence.")):
+        return 0
+    if name.startswith(("project_", "private_", "shared.", "recon_")):
+        return 1
+    if name.startswith(("vrnn", "vlayer_norm")):
+        return 2
+    if name.startswith(("arnn", "alayer_norm")):
+        return 3
+    if name.startswith(("trnn", "tlayer_norm", "embed.")):
+        return 4
+    if name.startswith("sp_discriminator."):
+        return 5
+    raise KeyError(name)
+
+
+def plan_arena(named_shapes: List[Tuple[str, Tuple[int, ...]]], use_confid: bool):
+    """-> (layout {name: (offset, numel)}, bucket ranges [(lo, hi)] for buckets 0..4, n_active,
+    n_total).  Pure function (unit-tested on CPU)."""
+    def bucket(n):
+        if n.startswith("confidence.") and not use_confid:
+            return 5
+        return bucket_of(n)
+    order = sorted(range(len(named_shapes)), key=lambda i: (bucket(named_shapes[i][0]), i))
+    layout, off = {}, 0
+    ranges, cur, lo = [], 0, 0
+    for i in order:
+        name, shape = named_shapes[i]
+        b = bucket(name)
+        while cur < b:
+            ranges.append((lo, off))
+            lo, cur = off, cur + 1
+        n = 1
+        for s in shape:
+            n *= s
+        layout[name] = (off, n)
+        off += (n + ALIGN - 1) // ALIGN * ALIGN
+    while cur < 5:
+        ranges.append((lo, off))
+        lo, cur = off, cur + 1
+    n_active = ranges[4][1]
+    return layout, ranges[:5], n_active, off
+
+
+class FusedTrainer:
+    def __init__(self, model, lr: Optional[float] = None, process_group=None,
+                 global_batch_stats: bool = True):
+        self.model = model
+        self.cfg = cfg = model.config
+        self.eng = model.engine
+        self.lr = float(cfg.learning_rate if lr is None else lr)
+        self.clip = float(cfg.clip)
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None:
+            import torch.distributed as dist
+            self.dist = dist
+            self.world = dist.get_world_size(process_group)
+        self.global_stats = global_batch_stats
+        self.use_confid = bool(getattr(cfg, "use_confidNet", False))
+        self.step_count = 0
+        self._build_arena()
+        self.m = torch.zeros_like(self.p_arena)
+        self.v = torch.zeros_like(self.p_arena)
+        self._pending = []
+
+    # ------------------------------------------------------------------ arenas -------------
+    def _build_arena(self):
+        named = [(n, p) for n, p in self.model.named_parameters()]
+        if not named[0][1].is_cuda and not _engine._DRYRUN:
+            raise MmdaError("FusedTrainer needs the model on a CUDA device (model.to('cuda'))")
+        dev = named[0][1].device
+        frozen = [n for n, p in named if not p.requires_grad]
+        if frozen:
+            raise MmdaError(f"frozen parameters are not supported by the fused step: {frozen[:3]}")
+        self.layout, self.ranges, self.n_active, n_total = plan_arena(
+            [(n, tuple(p.shape)) for n, p in named], self.use_confid)
+        self.p_arena = torch.zeros(n_total, dtype=torch.float32, device=dev)
+        self.g_arena = torch.zeros(n_total, dtype=torch.float32, device=dev)
+        self.G: Dict[str, torch.Tensor] = {}
+        for n, p in named:
+            off, sz = self.layout[n]
+            view = self.p_arena[off:off + sz].view(p.shape)
+            view.copy_(p.data)
+            p.data = view                       # the module's parameters now alias the arena
+            self.G[n] = self.g_arena[off:off + sz].view(p.shape)
+        self._alias_ver = tuple(p.data_ptr() for _, p in named)
+
+    def _check_alias(self):
+        ver = tuple(p.data_ptr() for p in self.model.parameters())
+        if ver != self._alias_ver:     # model.to(...) / embed.weight.data = ... after construction
+            m, v, step = self.m, self.v, self.step_count
+            old_layout = self.layout
+            self._build_arena()
+            if old_layout == self.layout and m.device == self.p_arena.device:
+                self.m, self.v = m, v
+            else:
+                self.m, self.v = torch.zeros_like(self.p_arena), torch.zeros_like(self.p_arena)
+            self.step_count = step
+
+    def attach_grads(self):
+        """Expose the arena gradients as ``param.grad`` (views; for inspection and tests).
+        Parameters the reference leaves at ``grad=None`` stay ``None``."""
+        skip = set(self.model.param_names_without_grad())
+        for n, p in self.model.named_parameters():
+            p.grad = None if n in skip else self.G[n]
+
+    # ------------------------------------------------------------------ collectives --------
+    def _allreduce(self, t, async_op=False):
+        if self.world > 1:
+            return self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.pg,
+                                        async_op=async_op)
+        return None
+
+    # ------------------------------------------------------------------ losses -------------
+    def _loss_buffers(self, B):
+        d, NC = self.eng.d, self.eng.NC
+        nA, nB, nC = 6 * d + 6 * NC + 3, 12 * d + 6 * d * d, 6 * d
+        pad = lambda n: (n + 3) // 4 * 4
+        tot = pad(nA) + pad(nB) + pad(nC) + 8 + 15 * d
+        st = self.eng.buf("loss_stats", tot)
+        o = 0
+        segA = st[o:o + nA]; o += pad(nA)
+        segB = st[o:o + nB]; o += pad(nB)
+        segC = st[o:o + nC]; o += pad(nC)
+        losses = st[o:o + 8]; o += 8
+        coef = st[o:o + 15 * d]
+        return st, segA, segB, segC, losses, coef
+
+    def loss_and_grads(self, out, labels, B):
+        """Fused losses forward + backward wrt the model outputs (csrc/loss.cu)."""
+        eng, k = self.eng, self.eng.k
+        d, NC, cfg = eng.d, eng.NC, self.cfg
+        Bg = float(B * self.world) if self.global_stats else float(B)
+        sync = self.global_stats and self.world > 1
+        st, segA, segB, segC, losses, coef = self._loss_buffers(B)
+        st.zero_()
+        X0, O, R = out["tokens"], out["orig"], out["recon"]
+        SC, TCP = out["scores"], out["tcp"]
+        y = labels
+        w_conf = float(cfg.conf_weight) if self.use_confid else 0.0
+        k._c("mmda_loss_phase1", _ptr(X0), _ptr(O), _ptr(R), _ptr(SC), _ptr(TCP), _ptr(y),
+             _ptr(segA), B, d, NC)
+        if sync:
+            self._allreduce(segA)
+        XN = eng.buf("XN", 6, B, d)
+        inv = eng.buf("inv_norm", 6, B)
+        k._c("mmda_loss_phase2", _ptr(X0), _ptr(segA), _ptr(XN), _ptr(inv), _ptr(segB), B, d, Bg)
+        Gm = segB[12 * d:].view(6, d, d)
+        for pi, (a, b) in enumerate(DIFF_PAIRS):
+            k.gemm(XN[a], XN[b], Gm[pi], ta=True)
+        if sync:
+            self._allreduce(segB)
+        k._c("mmda_loss_finalize", _ptr(segA), _ptr(segB), _ptr(losses), _ptr(coef), d, NC, Bg,
+             float(cfg.diff_weight), float(cfg.sim_weight), float(cfg.recon_weight), w_conf)
+        DXN = eng.buf("DXN", 6, B, d)
+        DXN.zero_()
+        alpha = float(cfg.diff_weight) * 2.0 / float(d * d)
+        for pi, (a, b) in enumerate(DIFF_PAIRS):
+            k.gemm(XN[b], Gm[pi], DXN[a], tb=True, alpha=alpha, beta=1.0)
+            k.gemm(XN[a], Gm[pi], DXN[b], alpha=alpha, beta=1.0)
+        k._c("mmda_loss_phase4a", _ptr(DXN), _ptr(inv), _ptr(segC), B, d)
+        if sync:
+            self._allreduce(segC)
+        dZ = eng.buf("dZ", B, 6, d)
+        k._c("mmda_loss_phase4b", _ptr(X0), _ptr(DXN), _ptr(segA), _ptr(segB), _ptr(segC),
+             _ptr(coef), _ptr(dZ), B, d, Bg, float(cfg.sim_weight), 0)
+        dSC, dTCP = eng.buf("dSCORES", B, NC), eng.buf("dTCP", B, NC)
+        dR, dO = eng.buf("dR", 3, B, d), eng.buf("dOrig", 3, B, d)
+        k._c("mmda_loss_grad_misc", _ptr(SC), _ptr(TCP), _ptr(y), _ptr(O), _ptr(R), _ptr(segA),
+             _ptr(dSC), _ptr(dTCP), _ptr(dR), _ptr(dO), B, d, NC, Bg, float(cfg.recon_weight),
+             w_conf)
+        return losses, dict(d_scores=dSC, d_tcp=dTCP if self.use_confid else None, d_tokens=dZ,
+                            d_orig=dO, d_recon=dR)
+
+    # ------------------------------------------------------------------ step ---------------
+    def _on_ready(self, tag):
+        if self.world == 1:
+            return
+        b = {"fusion": 0, "heads": 1, "enc_v": 2, "enc_a": 3, "enc_t": 4}[tag]
+        lo, hi = self.ranges[b]
+        if hi > lo:
+            self._pending.append(self._allreduce(self.g_arena[lo:hi], async_op=True))
+
+    def forward_backward(self, sentences, visual, acoustic, lengths, labels):
+        """zero_grad + forward + losses + backward (+ gradient all-reduce).  Returns the device
+        tensor of the six loss values [cls, diff, sim, recon, conf, total]."""
+        self._check_alias()
+        eng = self.eng
+        out = eng.forward(sentences, visual, acoustic, lengths, train=True, want_sp=False)
+        B = out["scores"].shape[0]
+        if labels.shape != (B, eng.NC) or labels.dtype != torch.float32 or \
+                not (labels.is_cuda or _engine._DRYRUN):
+            raise MmdaError("labels must be a CUDA float32 (B, num_classes) tensor")
+        self.g_arena[:self.n_active].zero_()
+        losses, grads = self.loss_and_grads(out, labels.contiguous(), B)
+        self._pending = []
+        eng.backward(self.G, on_ready=self._on_ready, **grads)
+        for w in self._pending:
+            w.wait()
+        self._pending = []
+        return losses
+
+    def optimizer_step(self):
+        self.step_count += 1
+        k = self.eng.k
+        k.bind_stream()
+        k._c("mmda_adam_clip_step", _ptr(self.p_arena), _ptr(self.g_arena), _ptr(self.m),
+             _ptr(self.v), self.n_active, self.step_count, self.lr, self.clip, 0.9, 0.999, 1e-8,
+             1.0)
+
+    def step(self, sentences, visual, acoustic, lengths, labels):
+        losses = self.forward_backward(sentences, visual, acoustic, lengths, labels)
+        self.optimizer_step()
+        return losses
+
+    def step_batch(self, batch, device=None):
+        """Public end-to-end call: a host ``Batch`` (pinned or pageable) -> one optimisation step.
+        Returns the loss tensor on the device; ``.tolist()`` it to read the values."""
+        dev = device or self.p_arena.device
+        to = lambda t: t.to(dev, non_blocking=True)
+        return self.step(to(batch.sentences), to(batch.visual), to(batch.acoustic), batch.lengths,
+                         to(batch.labels))

@@ -1,0 +1,340 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle.  Run with ``-m gpu`` on a B200.
+
+Tolerances (BASELINE.json north_star): logits, losses and gradients within 1e-5 relative in fp32
+mode; packing indices bit-exact.  "Relative" is scale-relative (max |a-b| / max |ref|) against
+an fp64 run of the oracle; where the fp32 oracle itself is further than 1e-5 from fp64 (long
+BPTT chains) the bound is 3x the fp32 oracle's own error.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN, load_small, max_rel, small_batch, small_cfg, state_from_npz
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+class Checks:
+    def __init__(self, tag):
+        self.tag, self.rows = tag, []
+
+    def add(self, name, got, ref, tol=TOL, ref32=None):
+        err = max_rel(got.detach().cpu() if torch.is_tensor(got) else got,
+                      ref.detach().cpu() if torch.is_tensor(ref) else ref)
+        bound = tol
+        if ref32 is not None:
+            bound = max(tol, 3.0 * max_rel(ref32.detach().cpu(), ref.detach().cpu()))
+        self.rows.append((name, err, bound, err <= bound))
+
+    def finish(self):
+        out = os.path.join(os.path.dirname(GOLDEN), "..", "gpurun_out")
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, f"parity_{self.tag}.txt"), "w") as f:
+            for n, e, b, ok in self.rows:
+                f.write(f"{'ok  ' if ok else 'FAIL'} {n:60s} err={e:.3e} bound={b:.1e}\n")
+        bad = [(n, e, b) for n, e, b, ok in self.rows if not ok]
+        assert not bad, "\n".join(f"{n}: err={e:.3e} > {b:.1e}" for n, e, b in bad[:40])
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a B200"
+    return torch.device("cuda:0")
+
+
+def _to(batch, dev):
+    return (batch.sentences.to(dev), batch.visual.to(dev), batch.acoustic.to(dev), batch.lengths)
+
+
+# ------------------------------------------------------------------------------------------
+# primitives
+# ------------------------------------------------------------------------------------------
+def test_sgemm_layouts(dev):
+    from mmda_b200.engine import Kernels
+    k = Kernels(); k.bind_stream()
+    g = torch.Generator(device="cpu").manual_seed(0)
+    C = Checks("sgemm")
+    for (M, N, K) in [(5, 7, 3), (64, 64, 64), (256, 128, 140), (1536, 2048, 128), (300, 1200, 1000),
+                      (1200, 300, 5000), (37, 129, 4099)]:
+        for ta in (False, True):
+            for tb in (False, True):
+                A = torch.randn((K, M) if ta else (M, K), generator=g).to(dev)
+                B = torch.randn((N, K) if tb else (K, N), generator=g).to(dev)
+                bias = torch.randn(N, generator=g).to(dev)
+                out = torch.full((M, N), 7.0, device=dev)
+                k.gemm(A, B, out, ta=ta, tb=tb, bias=bias)
+                ref = (A.double().t() if ta else A.double()) @ (B.double().t() if tb else B.double()) + bias.double()
+                C.add(f"gemm {M}x{N}x{K} ta={ta} tb={tb}", out, ref, 2e-6)
+        # split-K accumulate
+        A = torch.randn(K, M, generator=g).to(dev); B = torch.randn(K, N, generator=g).to(dev)
+        acc = torch.randn(M, N, generator=g).to(dev); ref = acc.double() + A.double().t() @ B.double()
+        k.gemm(A, B, acc, ta=True, beta=1.0, split_k=0)
+        C.add(f"gemm splitk auto {M}x{N}x{K}", acc, ref, 2e-6)
+    # strided C / A views and fused activation
+    X = torch.randn(256, 128, generator=g).to(dev); W = torch.randn(128, 128, generator=g).to(dev)
+    b = torch.randn(128, generator=g).to(dev)
+    tok = torch.zeros(256, 6, 128, device=dev)
+    k.linear(X, W, b, tok.view(256, 768)[:, 256:384], act=2)
+    C.add("linear sigmoid strided", tok[:, 2, :], torch.sigmoid(X.double() @ W.double().t() + b.double()), 2e-6)
+    assert float(tok[:, 1].abs().max()) == 0 and float(tok[:, 3].abs().max()) == 0
+    C.finish()
+
+
+def test_layernorm_attention_colsum(dev):
+    from mmda_b200.engine import Kernels, _ptr
+    k = Kernels(); k.bind_stream()
+    g = torch.Generator().manual_seed(1)
+    C = Checks("rowwise")
+    for rows, width in [(37, 70), (1536, 128), (999, 600), (8, 148)]:
+        x = torch.randn(rows, width, generator=g).to(dev); r = torch.randn(rows, width, generator=g).to(dev)
+        gam = (torch.rand(width, generator=g) + 0.5).to(dev); bet = torch.randn(width, generator=g).to(dev)
+        dy = torch.randn(rows, width, generator=g).to(dev)
+        for res in (None, r):
+            y = torch.empty_like(x); mu = torch.empty(rows, device=dev); rs = torch.empty(rows, device=dev)
+            k.layernorm(x, res, gam, bet, y, mu, rs)
+            xd = (x if res is None else x + res).double().requires_grad_(True)
+            gd, bd = gam.double().requires_grad_(True), bet.double().requires_grad_(True)
+            yr = torch.nn.functional.layer_norm(xd, (width,), gd, bd, 1e-5)
+            yr.backward(dy.double())
+            C.add(f"ln fwd {rows}x{width} res={res is not None}", y, yr, 2e-6)
+            dx = torch.empty_like(x); dg = torch.zeros(width, device=dev); db = torch.zeros(width, device=dev)
+            k.layernorm_bwd(dy, x, res, gam, mu, rs, dx, dg, db)
+            C.add(f"ln dx {rows}x{width}", dx, xd.grad, 5e-6)
+            C.add(f"ln dgamma {rows}x{width}", dg, gd.grad, 5e-6)
+            C.add(f"ln dbeta {rows}x{width}", db, bd.grad, 5e-6)
+        cs = torch.zeros(width, device=dev); cs2 = torch.ones(width, device=dev)
+        k.colsum(x, cs, cs2)
+        C.add(f"colsum {rows}x{width}", cs, x.double().sum(0), 5e-6)
+        C.add(f"colsum2 {rows}x{width}", cs2, x.double().sum(0) + 1, 5e-6)
+    # attention core vs torch MHA math (eval: no dropout)
+    for B, d in [(3, 16), (256, 128), (17, 64)]:
+        hd = d // 2
+        qkv = torch.randn(B * 6, 3 * d, generator=g).to(dev)
+        ctx = torch.empty(B * 6, d, device=dev); pr = torch.empty(B, 2, 6, 6, device=dev)
+        k._c("mmda_attention_forward", _ptr(qkv), _ptr(ctx), _ptr(pr), B, 6, 2, hd, 0.0, 1, 1)
+        q3 = qkv.double().view(B, 6, 3, 2, hd).requires_grad_(True)
+        q, kk, v = q3[:, :, 0], q3[:, :, 1], q3[:, :, 2]              # (B,6,2,hd)
+        s = torch.einsum("bihd,bjhd->bhij", q, kk) / hd ** 0.5
+        p = torch.softmax(s, -1)
+        o = torch.einsum("bhij,bjhd->bihd", p, v).reshape(B * 6, d)
+        C.add(f"attn fwd B={B} d={d}", ctx, o, 2e-6)
+        C.add(f"attn probs B={B} d={d}", pr, p, 2e-6)
+        do = torch.randn(B * 6, d, generator=g).to(dev)
+        o.backward(do.double())
+        dqkv = torch.empty_like(qkv)
+        k._c("mmda_attention_backward", _ptr(qkv), _ptr(pr), _ptr(do), _ptr(dqkv), B, 6, 2, hd, 0.0, 1, 1)
+        C.add(f"attn bwd B={B} d={d}", dqkv, q3.grad.reshape(B * 6, 3 * d), 5e-6)
+    C.finish()
+
+
+def test_pack_indices_bit_exact(dev):
+    from mmda_b200 import MISA, MisaConfig
+    from mmda_b200.engine import MisaEngine
+    cfg = MisaConfig(embedding_size=8, visual_size=4, acoustic_size=4, hidden_size=8, vocab_size=30)
+    eng = MISA(cfg).to(dev).engine
+    eng.params(); eng.k.bind_stream()
+    g = torch.Generator().manual_seed(5)
+    for B, T in [(1, 1), (7, 9), (40, 50), (256, 50), (300, 17)]:
+        for trial in range(3):
+            ln = torch.randint(1, T + 1, (B,), generator=g)
+            x = torch.randn(int(ln.max()), B, 3, generator=g)
+            ref = torch.nn.utils.rnn.pack_padded_sequence(x, ln, enforce_sorted=False)
+            pk = eng._pack(ln)
+            assert torch.equal(pk["bs"].cpu().long(), ref.batch_sizes)
+            assert torch.equal(pk["sidx"].cpu().long(), ref.sorted_indices)
+            off = torch.zeros(len(ref.batch_sizes) + 1, dtype=torch.long)
+            off[1:] = torch.cumsum(ref.batch_sizes, 0)
+            assert torch.equal(pk["off"].cpu().long(), off)
+            # the gather itself: packed rows == PackedSequence.data bit for bit
+            X = torch.empty(pk["N"], 3, device=dev)
+            from mmda_b200.engine import _ptr
+            eng.k._c("mmda_gather_rows", _ptr(x.to(dev)), _ptr(X), _ptr(pk["row_t"]), _ptr(pk["row_j"]),
+                     _ptr(pk["sidx"]), pk["N"], B, 3)
+            assert torch.equal(X.cpu(), ref.data)
+
+
+def test_adam_clip_matches_torch(dev):
+    from mmda_b200.engine import Kernels, _ptr
+    k = Kernels(); k.bind_stream()
+    g = torch.Generator().manual_seed(2)
+    n = 100003
+    p0 = torch.randn(n + 1, generator=g)[:n]
+    pt = p0.clone().double().requires_grad_(True)
+    opt = torch.optim.Adam([pt], lr=1e-3)
+    p = torch.zeros(n + 1, device=dev)[:n]; p.copy_(p0)
+    m = torch.zeros(n + 1, device=dev)[:n]; v = torch.zeros(n + 1, device=dev)[:n]
+    C = Checks("adam")
+    for step in range(1, 5):
+        gr = torch.randn(n, generator=g) * 2
+        pt.grad = gr.double().clone()
+        torch.nn.utils.clip_grad_value_([pt], 1.0)
+        opt.step()
+        gd = gr.to(dev)
+        k._c("mmda_adam_clip_step", _ptr(p), _ptr(gd), _ptr(m), _ptr(v), n, step, 1e-3, 1.0, 0.9, 0.999, 1e-8, 1.0)
+        C.add(f"adam step {step}", p, pt.detach(), 2e-6)
+    C.finish()
+
+
+# ------------------------------------------------------------------------------------------
+# whole model
+# ------------------------------------------------------------------------------------------
+def _oracle_pair(cfg, state, batch):
+    """fp32 and fp64 oracle runs (CPU) of one step: outputs, losses, grads-before-clip."""
+    from oracle.misa_oracle import OracleMISA, oracle_step
+    res = {}
+    for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+        m = OracleMISA(cfg)
+        m.load_state_dict(state)
+        m = m.to(dt).eval()
+        b = batch
+        if dt == torch.float64:
+            from mmda_b200.synthetic import Batch
+            b = Batch(batch.sentences, batch.visual.double(), batch.acoustic.double(),
+                      batch.labels.double(), batch.lengths, batch.bert_sent, batch.bert_sent_type,
+                      batch.bert_sent_mask)
+        out, L, grads = oracle_step(m, b, cfg, None)
+        res[tag] = (out, L, grads)
+    return res
+
+
+def _run_level1(model, batch, cfg, dev):
+    """The reference's own loss code shape (oracle_losses mirrors solver.get_*_loss) on the
+    drop-in model's autograd-connected attributes."""
+    from oracle.misa_oracle import oracle_losses
+    model.zero_grad()
+    scores, labels = model(*_to(batch, dev), None, None, None)
+    out = {k: getattr(model, k) for k in model.OUTPUT_ATTRS}
+    out["scores"], out["labels"] = scores, labels
+    L = oracle_losses(out, batch.labels.to(dev), cfg)
+    L["total"].backward()
+    return out, L
+
+
+ATTR_CHECK = ("utt_t_orig", "utt_v_orig", "utt_a_orig", "utt_private_t", "utt_private_v",
+              "utt_private_a", "utt_shared_t", "utt_shared_v", "utt_shared_a", "utt_t_recon",
+              "utt_v_recon", "utt_a_recon", "tcp", "shared_or_private_p_t", "shared_or_private_s")
+
+
+def _model_checks(tag, cfg, state, batch, dev, golden=None):
+    from mmda_b200 import MISA
+    from mmda_b200.trainer import FusedTrainer, LOSS_NAMES
+    orc = _oracle_pair(cfg, state, batch)
+    o32, L32, g32 = orc["f32"]
+    o64, L64, g64 = orc["f64"]
+    C = Checks(tag)
+    # ---- level 1: drop-in forward + autograd bridge ----
+    model = MISA(cfg)
+    model.load_state_dict(state)
+    model = model.to(dev).eval()
+    out, L = _run_level1(model, batch, cfg, dev)
+    C.add("L1 scores", out["scores"], o64["scores"], ref32=o32["scores"])
+    assert torch.equal(out["labels"].cpu(), o32["labels"]) or \
+        float((o64["scores"] - cfg.threshold).abs().min()) < 1e-5
+    for a in ATTR_CHECK:
+        C.add("L1 " + a, out[a], o64[a], ref32=o32[a])
+    for kk in ("cls", "diff", "recon", "sim", "conf", "total"):
+        C.add("L1 loss " + kk, L[kk], L64[kk], ref32=L32[kk])
+    none = set(model.param_names_without_grad())
+    for n, p in model.named_parameters():
+        if g64[n] is None:
+            assert p.grad is None, f"{n}: oracle leaves grad None"
+            assert n in none
+        else:
+            assert p.grad is not None, n
+            C.add("L1 grad " + n, p.grad, g64[n], ref32=g32[n])
+    # ---- level 2: fused losses + backward + clip + Adam ----
+    model2 = MISA(cfg)
+    model2.load_state_dict(state)
+    model2 = model2.to(dev).eval()
+    tr = FusedTrainer(model2)
+    s, v, a, ln = _to(batch, dev)
+    losses = tr.forward_backward(s, v, a, ln, batch.labels.to(dev))
+    lv = dict(zip(LOSS_NAMES, losses[:6].tolist()))
+    for kk in LOSS_NAMES:
+        C.add("L2 loss " + kk, torch.tensor(lv[kk]), L64[kk], ref32=L32[kk])
+    for n, p in model2.named_parameters():
+        if g64[n] is not None:
+            C.add("L2 grad " + n, tr.G[n], g64[n], ref32=g32[n])
+    tr.optimizer_step()
+    # oracle step in fp64 for the updated parameters
+    from oracle.misa_oracle import OracleMISA, oracle_optimizer, oracle_step
+    from mmda_b200.synthetic import Batch
+    m64 = OracleMISA(cfg); m64.load_state_dict(state); m64 = m64.double().eval()
+    b64 = Batch(batch.sentences, batch.visual.double(), batch.acoustic.double(), batch.labels.double(),
+                batch.lengths, batch.bert_sent, batch.bert_sent_type, batch.bert_sent_mask)
+    oracle_step(m64, b64, cfg, oracle_optimizer(m64, cfg))
+    after = dict(m64.named_parameters())
+    for n, p in model2.named_parameters():
+        if g64[n] is not None:
+            C.add("L2 param-after-step " + n, p.data, after[n].detach(), 2e-6)
+        else:
+            assert torch.equal(p.data.cpu(), state[n]), f"{n} must be untouched by the step"
+    if golden is not None:
+        for kk, vv in golden["losses"].items():
+            C.add("golden loss " + kk, torch.tensor(lv[kk]), torch.tensor(vv), 2e-5)
+        C.add("golden scores", out["scores"], torch.tensor(golden["scores"]), 2e-5)
+    C.finish()
+
+
+@pytest.mark.parametrize("name", ["small_ragged", "small_shuffled_confid"])
+def test_small_fixture(dev, name):
+    z, meta = load_small(name)
+    cfg = small_cfg(meta)
+    golden = {"losses": {k: float(z["loss/" + k]) for k in ("cls", "diff", "recon", "sim", "conf", "total")},
+              "scores": z["out/scores"].tolist()}
+    _model_checks(name, cfg, state_from_npz(z), small_batch(z), dev, golden)
+
+
+def _full(cfgname, recname, lengths, dev, **kw):
+    from mmda_b200 import config as Cfg
+    from mmda_b200.synthetic import batch_for
+    from oracle.misa_oracle import oracle_build
+    rec = json.load(open(os.path.join(GOLDEN, recname + ".json")))
+    cfg = getattr(Cfg, cfgname + "_config")(vocab_size=2000, **kw)
+    state = {k: v.clone() for k, v in oracle_build(cfg, rec["seed"]).state_dict().items()}
+    batch = batch_for(cfg, seed=rec["batch_seed"], lengths=lengths)
+    _model_checks(recname, cfg, state, batch, dev, rec["steps"][0])
+
+
+def test_c1_mosi_b64_ragged(dev):
+    _full("mosi", "c1_mosi_b64", "ragged", dev)
+
+
+def test_c2_mosei_b256_full(dev):
+    _full("mosei", "c2_mosei_b256", "full", dev)
+
+
+def test_c3_mosei_confid_ragged(dev):
+    _full("mosei", "c3_mosei_confid_b256", "ragged", dev, use_confidNet=True)
+
+
+def test_train_mode_dropout_statistics(dev):
+    """Train-mode dropout is checked statistically (SURVEY.md hard part 5): keep rate and the
+    0.5 score of dropped classifier logits (dropout sits before the sigmoid, models.py:150-153)."""
+    from mmda_b200 import MISA, mosei_config
+    from mmda_b200.synthetic import batch_for
+    cfg = mosei_config(vocab_size=500, dropout=0.5)
+    torch.manual_seed(0)
+    model = MISA(cfg).to(dev).train()
+    batch = batch_for(cfg, seed=3, lengths="ragged", seq_len=12)
+    with torch.no_grad():
+        scores, _ = model(*_to(batch, dev), None, None, None)
+    frac = float((scores == 0.5).float().mean())
+    assert 0.42 < frac < 0.58, frac
+    model.eval()
+    with torch.no_grad():
+        s1, _ = model(*_to(batch, dev), None, None, None)
+        s2, _ = model(*_to(batch, dev), None, None, None)
+    assert torch.equal(s1, s2) and float((s1 == 0.5).float().mean()) < 0.01
+
+
+def test_missing_library_fails_loudly(dev, monkeypatch):
+    import mmda_b200._lib as L
+    fresh = L._Lib()
+    monkeypatch.setattr(L, "LIB_PATH", "/nonexistent/libmmda_b200.so")
+    with pytest.raises(L.MmdaError):
+        fresh.load()
