@@ -580,6 +580,7 @@ class _MisaFunction(torch.autograd.Function):
         eng = model.engine
         out = eng.forward(sentences, visual, acoustic, lengths, train=True, want_sp=True)
         ctx.model, ctx.names, ctx.fwd_step = model, names, eng.step_id
+        ctx.set_materialize_grads(False)      # unused outputs arrive as None, not zeros
         res = tuple(out[n].clone() for n in _DIFF_OUT) + (out["labels"].clone(),)
         ctx.mark_non_differentiable(res[-1])
         return res
