@@ -63,9 +63,9 @@ __device__ __forceinline__ void reduce_scatter(float (&v)[N], int lane) {
 // forward
 // ------------------------------------------------------------------------------------------
 template <int BT>
-__global__ void __launch_bounds__(640, 1) lstm_fwd_kernel(const LstmArgs p) {
+__global__ void __launch_bounds__(BT == 40 ? 800 : 640, 1) lstm_fwd_kernel(const LstmArgs p) {
   extern __shared__ __align__(16) float smem[];
-  constexpr int BTP = BT + 4;
+  constexpr int BTP = BT + (BT % 32 == 0 ? 4 : 0);   // keep the 4 k-rows of a warp on distinct banks
   const int C = p.C, H = p.H, Hs = p.Hs, Kpad = p.Kpad;
   const int dir = blockIdx.y;
   const unsigned rank = cluster_ctarank();
@@ -118,11 +118,8 @@ __global__ void __launch_bounds__(640, 1) lstm_fwd_kernel(const LstmArgs p) {
   const int K4 = Kpad >> 2;
   float c0 = 0.f, c1 = 0.f;
 
-  // peers' h_s addresses for my (unit, batch pair)
-  uint32_t peer[8];
-#pragma unroll
-  for (int r = 0; r < 8; ++r)
-    peer[r] = dsmem_addr(h_s + min(u_glob, Kpad - 1) * BTP + bl0, r < C ? r : 0);
+  // my (unit, batch pair) slot of h_s; the same offset is pushed into every peer CTA
+  const float* h_slot = h_s + min(u_glob, Kpad - 1) * BTP + bl0;
 
   for (int s = 0; s < Lmax; ++s) {
     const int t = dir == 0 ? s : Lmax - 1 - s;
@@ -161,46 +158,53 @@ __global__ void __launch_bounds__(640, 1) lstm_fwd_kernel(const LstmArgs p) {
       }
       reduce_scatter<32, 8>(acc, lane);  // lane q now owns batch rows 2q, 2q+1 -> acc[0..8)
     }
-    cluster_arrive();  // A: this CTA is done reading h_{t-1}
+    cluster_arrive_relaxed();  // A: this CTA is done reading h_{t-1}
 
-    float hn0 = 0.f, hn1 = 0.f;
+    float hn0 = 0.f, hn1 = 0.f, s0[5], s1[5];
     if (a0) {
-      const float ig = sigmoidf_acc(acc[0] + x0[0]), fg = sigmoidf_acc(acc[1] + x0[1]);
-      const float gg = tanhf(acc[2] + x0[2]), og = sigmoidf_acc(acc[3] + x0[3]);
-      c0 = fg * c0 + ig * gg;
-      hn0 = og * tanhf(c0);
-      if (p.save) {
-        float* gp = p.gates + row0 * H8 + gcol;
-        gp[0] = ig; gp[H] = fg; gp[2 * H] = gg; gp[3 * H] = og;
-        p.c[row0 * H2 + ycol] = c0;
-      }
-      p.y[row0 * H2 + ycol] = hn0;
-      const bool fin = dir == 0 ? (t == len0 - 1) : (t == 0);
-      if (fin && p.utt) p.utt[(size_t)orig0 * p.utt_ld + utt_off + u_glob] = hn0;
+      s0[0] = sigmoidf_acc(acc[0] + x0[0]); s0[1] = sigmoidf_acc(acc[1] + x0[1]);
+      s0[2] = tanhf(acc[2] + x0[2]);        s0[3] = sigmoidf_acc(acc[3] + x0[3]);
+      c0 = s0[1] * c0 + s0[0] * s0[2];
+      s0[4] = c0;
+      hn0 = s0[3] * tanhf(c0);
     }
     if (a1) {
-      const float ig = sigmoidf_acc(acc[4] + x1[0]), fg = sigmoidf_acc(acc[5] + x1[1]);
-      const float gg = tanhf(acc[6] + x1[2]), og = sigmoidf_acc(acc[7] + x1[3]);
-      c1 = fg * c1 + ig * gg;
-      hn1 = og * tanhf(c1);
-      if (p.save) {
-        float* gp = p.gates + row1 * H8 + gcol;
-        gp[0] = ig; gp[H] = fg; gp[2 * H] = gg; gp[3 * H] = og;
-        p.c[row1 * H2 + ycol] = c1;
-      }
-      p.y[row1 * H2 + ycol] = hn1;
-      const bool fin = dir == 0 ? (t == len1 - 1) : (t == 0);
-      if (fin && p.utt) p.utt[(size_t)orig1 * p.utt_ld + utt_off + u_glob] = hn1;
+      s1[0] = sigmoidf_acc(acc[4] + x1[0]); s1[1] = sigmoidf_acc(acc[5] + x1[1]);
+      s1[2] = tanhf(acc[6] + x1[2]);        s1[3] = sigmoidf_acc(acc[7] + x1[3]);
+      c1 = s1[1] * c1 + s1[0] * s1[2];
+      s1[4] = c1;
+      hn1 = s1[3] * tanhf(c1);
     }
 
     cluster_wait();  // A: every CTA of the cluster is done reading h_{t-1}
     if (a0 || a1) {
 #pragma unroll
       for (int r = 0; r < 8; ++r)
-        if (r < C) dsmem_st_f2(peer[r], hn0, hn1);
+        if (r < C) dsmem_st_f2(dsmem_addr(h_slot, r), hn0, hn1);
     }
-    cluster_arrive();  // B: h_t pushed
-    cluster_wait();
+    cluster_arrive();  // B: h_t pushed (release)
+    // global stores drain while the barrier completes
+    if (a0) {
+      if (p.save) {
+        float* gp = p.gates + row0 * H8 + gcol;
+        gp[0] = s0[0]; gp[H] = s0[1]; gp[2 * H] = s0[2]; gp[3 * H] = s0[3];
+        p.c[row0 * H2 + ycol] = s0[4];
+      }
+      p.y[row0 * H2 + ycol] = hn0;
+      const bool fin = dir == 0 ? (t == len0 - 1) : (t == 0);
+      if (fin && p.utt) p.utt[(size_t)orig0 * p.utt_ld + utt_off + u_glob] = hn0;
+    }
+    if (a1) {
+      if (p.save) {
+        float* gp = p.gates + row1 * H8 + gcol;
+        gp[0] = s1[0]; gp[H] = s1[1]; gp[2 * H] = s1[2]; gp[3 * H] = s1[3];
+        p.c[row1 * H2 + ycol] = s1[4];
+      }
+      p.y[row1 * H2 + ycol] = hn1;
+      const bool fin = dir == 0 ? (t == len1 - 1) : (t == 0);
+      if (fin && p.utt) p.utt[(size_t)orig1 * p.utt_ld + utt_off + u_glob] = hn1;
+    }
+    cluster_wait();  // B
   }
 }
 
@@ -208,9 +212,9 @@ __global__ void __launch_bounds__(640, 1) lstm_fwd_kernel(const LstmArgs p) {
 // backward through time
 // ------------------------------------------------------------------------------------------
 template <int BT, int KS>
-__global__ void __launch_bounds__(640, 1) lstm_bwd_kernel(const LstmArgs p) {
+__global__ void __launch_bounds__(BT == 40 ? 800 : 640, 1) lstm_bwd_kernel(const LstmArgs p) {
   extern __shared__ __align__(16) float smem[];
-  constexpr int BTP = BT + 4;
+  constexpr int BTP = BT + (BT % 32 == 0 ? 4 : 0);
   constexpr int RS = 32 / KS;       // lanes that split the contraction over gate rows
   constexpr int NV = 32 / RS;       // outputs each lane owns after the reduce-scatter
   const int C = p.C, H = p.H, Hs = p.Hs, Kpad = p.Kpad;
@@ -419,6 +423,24 @@ struct LstmPlan {
 };
 
 static int g_max_smem = 0;
+static int g_max_clusters8 = 0;   // co-resident 8-CTA clusters of the big-H kernel (B200: 15)
+
+template <int BT> static int probe_clusters8(int threads, size_t smem) {
+  auto kern = lstm_fwd_kernel<BT>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(8 * 32, 2, 1);
+  cfg.blockDim = dim3(threads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 8; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
 
 static int lstm_make_plan(int B, int H, int Tmax, LstmPlan* pl) {
   if (g_max_smem == 0) {
@@ -433,24 +455,37 @@ static int lstm_make_plan(int B, int H, int Tmax, LstmPlan* pl) {
   // ones want many CTAs
   for (int C = 1; C <= 8; C *= 2) {
     const int Hs = (H + C - 1) / C;
-    const int BT = (H > 128) ? 32 : 8;
-    const int BTP = BT + 4;
     const int KS = (H > 128) ? 16 : 4;
     const int RS = 32 / KS, R = (4 * Hs + RS - 1) / RS * RS;
-    const size_t misc = (size_t)(2 * BT + Tmax + 1) * 4;
-    const size_t fwd = (size_t)4 * Kpad * Hs * 4 + (size_t)Kpad * BTP * 4 + misc;
-    const size_t bwd = (size_t)R * Kpad * 4 + (size_t)R * BTP * 4 + misc;
-    if (fwd > (size_t)g_max_smem || bwd > (size_t)g_max_smem) continue;
-    const int UG = (Hs + 7) / 8, BG = BT / 8, K4 = Kpad / 4;
-    const int KG = (K4 + KS - 1) / KS;
-    const int wf = UG * BG, wb = (UG > KG ? UG : KG) * BG;
-    if (wf > 20 || wb > 20) continue;   // kernels are compiled for <= 640 threads
-    pl->C = C; pl->Hs = Hs; pl->Kpad = Kpad; pl->BT = BT; pl->KS = KS;
-    pl->n_tiles = (B + BT - 1) / BT;
-    pl->threads_fwd = wf * 32; pl->threads_bwd = wb * 32;
-    pl->smem_fwd = fwd; pl->smem_bwd = bwd;
-    pl->scratch_bytes = (size_t)2 * 2 * pl->n_tiles * C * BT * Kpad * sizeof(float);
-    return MMDA_OK;
+    const int cand[3] = {40, 32, 8};
+    for (int ci = (H > 128 ? 0 : 2); ci < 3; ++ci) {
+      const int BT = cand[ci];
+      if (H > 128 && BT == 8) break;
+      const int BTP = BT + (BT % 32 == 0 ? 4 : 0);
+      const size_t misc = (size_t)(2 * BT + Tmax + 1) * 4;
+      const size_t fwd = (size_t)4 * Kpad * Hs * 4 + (size_t)Kpad * BTP * 4 + misc;
+      const size_t bwd = (size_t)R * Kpad * 4 + (size_t)R * BTP * 4 + misc;
+      if (fwd > (size_t)g_max_smem || bwd > (size_t)g_max_smem) continue;
+      const int UG = (Hs + 7) / 8, BG = BT / 8, K4 = Kpad / 4;
+      const int KG = (K4 + KS - 1) / KS;
+      const int wf = UG * BG, wb = (UG > KG ? UG : KG) * BG;
+      if (wf > (BT == 40 ? 25 : 20) || wb > (BT == 40 ? 25 : 20)) continue;
+      if (BT == 40) {
+        // the 40-row tile only pays when it lets the whole batch run as ONE wave of clusters
+        // (B200 co-schedules 15 clusters of 8 CTAs; 2 directions x ceil(B/32) tiles may not fit)
+        if (C == 8 && g_max_clusters8 == 0) g_max_clusters8 = probe_clusters8<40>(wf * 32, fwd);
+        const int t32 = (B + 31) / 32, t40 = (B + 39) / 40;
+        const int cap = C == 8 ? g_max_clusters8 : 1 << 30;
+        const int waves32 = (2 * t32 + cap - 1) / cap, waves40 = (2 * t40 + cap - 1) / cap;
+        if (cap <= 0 || waves40 * 40 >= waves32 * 32) continue;   // no gain: try BT = 32
+      }
+      pl->C = C; pl->Hs = Hs; pl->Kpad = Kpad; pl->BT = BT; pl->KS = KS;
+      pl->n_tiles = (B + BT - 1) / BT;
+      pl->threads_fwd = wf * 32; pl->threads_bwd = wb * 32;
+      pl->smem_fwd = fwd; pl->smem_bwd = bwd;
+      pl->scratch_bytes = (size_t)2 * 2 * pl->n_tiles * C * BT * Kpad * sizeof(float);
+      return MMDA_OK;
+    }
   }
   mmda_set_error("lstm: hidden size %d does not fit the shared-memory resident W_hh plan", H);
   return MMDA_ERR_UNSUPPORTED;
@@ -494,6 +529,33 @@ int mmda_lstm_plan(int B, int H, int* out6) {
   return MMDA_OK;
 }
 
+// probe: how many clusters of the text-size forward kernel can be co-resident (out[i] for
+// cluster sizes 1,2,4,8,16 with the given dynamic smem bytes and block size); -1 = not launchable
+int mmda_lstm_probe_clusters(int smem_bytes, int threads, int* out5) {
+  const int sizes[5] = {1, 2, 4, 8, 16};
+  auto kern = lstm_fwd_kernel<32>;
+  MMDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  for (int i = 0; i < 5; ++i) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(sizes[i] * 64, 2, 1);
+    cfg.blockDim = dim3(threads, 1, 1);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = sizes[i];
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int n = -1;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+    out5[i] = e == cudaSuccess ? n : -1;
+    if (e != cudaSuccess) cudaGetLastError();
+  }
+  return MMDA_OK;
+}
+
 int mmda_lstm_forward(float* gates, const float* whh_f, const float* whh_r, float* y, float* c,
                       const int* lens_sorted, const int* sorted_idx, const int* offsets,
                       float* utt, int utt_ld, int utt_off_f, int utt_off_r, int B, int H, int Tmax,
@@ -510,6 +572,7 @@ int mmda_lstm_forward(float* gates, const float* whh_f, const float* whh_r, floa
   a.utt = utt; a.utt_ld = utt_ld; a.utt_off0 = utt_off_f; a.utt_off1 = utt_off_r;
   a.B = B; a.H = H; a.Hs = pl.Hs; a.Kpad = pl.Kpad; a.C = pl.C; a.n_tiles = pl.n_tiles;
   a.save = save_for_backward;
+  if (pl.BT == 40) return launch_cluster(lstm_fwd_kernel<40>, a, pl, pl.threads_fwd, pl.smem_fwd, stream);
   if (pl.BT == 32) return launch_cluster(lstm_fwd_kernel<32>, a, pl, pl.threads_fwd, pl.smem_fwd, stream);
   return launch_cluster(lstm_fwd_kernel<8>, a, pl, pl.threads_fwd, pl.smem_fwd, stream);
 }
@@ -530,6 +593,8 @@ int mmda_lstm_backward(float* gates, const float* whh_f, const float* whh_r, con
   a.dy = dy; a.dutt = dutt; a.utt_ld = utt_ld; a.utt_off0 = utt_off_f; a.utt_off1 = utt_off_r;
   a.lens = lens_sorted; a.sorted_idx = sorted_idx; a.offsets = offsets; a.scratch = scratch;
   a.B = B; a.H = H; a.Hs = pl.Hs; a.Kpad = pl.Kpad; a.C = pl.C; a.n_tiles = pl.n_tiles;
+  if (pl.BT == 40 && pl.KS == 16)
+    return launch_cluster(lstm_bwd_kernel<40, 16>, a, pl, pl.threads_bwd, pl.smem_bwd, stream);
   if (pl.BT == 32 && pl.KS == 16)
     return launch_cluster(lstm_bwd_kernel<32, 16>, a, pl, pl.threads_bwd, pl.smem_bwd, stream);
   return launch_cluster(lstm_bwd_kernel<8, 4>, a, pl, pl.threads_bwd, pl.smem_bwd, stream);
