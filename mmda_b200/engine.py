@@ -136,6 +136,10 @@ class MisaEngine:
         # the operand pitches satisfy TMA's 16-byte rule, exact-fp32 SIMT path otherwise
         self.tc_kind = 0 if prec == "fp32" else 1
         self.use_tc = os.environ.get("MMDA_GEMM", "tc") != "simt"
+        # the visual / acoustic encoders run on side streams next to the text encoder (whose
+        # cluster kernel occupies 112 of the 148 SMs)
+        self.multi_stream = os.environ.get("MMDA_STREAMS", "1") != "0"
+        self._side = None
         if self.cfg.use_bert:
             raise NotImplementedError(
                 "use_bert=True: the BERT text branch is the next scope row (SURVEY.md 8f N1); "
@@ -213,6 +217,36 @@ class MisaEngine:
     def big_gemm(self, *a, **kw):
         """Hoisted LSTM GEMMs.  fp32 mode: exact fp32 SIMT path."""
         self.k.gemm(*a, **kw)
+
+    # ---------------------------------------------------------------- streams --------------
+    def _side_streams(self):
+        if self._side is None:
+            self._side = {m: torch.cuda.Stream(device=self._dev) for m in ("v", "a")}
+        return self._side
+
+    def _fork(self, fns):
+        """Run fns[m]() for m in v, a on side streams (after everything enqueued so far on the
+        current stream) and fns['t']() on the current stream; join before returning."""
+        if not self.multi_stream or _DRYRUN:
+            for m in ("v", "a", "t"):
+                fns[m]()
+            return
+        main = torch.cuda.current_stream()
+        start = torch.cuda.Event()
+        start.record(main)
+        done = []
+        for m, st in self._side_streams().items():
+            st.wait_event(start)
+            with torch.cuda.stream(st):
+                self.k.bind_stream()
+                fns[m]()
+                ev = torch.cuda.Event()
+                ev.record(st)
+                done.append(ev)
+        self.k.bind_stream()
+        fns["t"]()
+        for ev in done:
+            main.wait_event(ev)
 
     # ---------------------------------------------------------------- tensor-core operands --
     def _tc_ok(self, H, I):
@@ -313,22 +347,31 @@ class MisaEngine:
         p_att = ATT_P if drop else 0.0
         self.p_cls, self.p_att = p_cls, p_att
 
-        # ---- encoders on packed rows ----
+        # ---- encoders on packed rows (three modalities concurrently) ----
         sent = sentences.contiguous()
-        Xt = self.buf("X_t", N, self.H["t"])
         V = P["embed.weight"].shape[0]
-        k._c("mmda_embedding_forward", _ptr(P["embed.weight"]), _ptr(sent), _ptr(Xt),
-             _ptr(pk["row_t"]), _ptr(pk["row_j"]), _ptr(pk["sidx"]), N, B, self.H["t"], V)
-        X = {"t": Xt}
-        for m, src in (("v", visual), ("a", acoustic)):
-            src = src.contiguous()
+        X, utt = {}, {}
+        srcs = {"v": visual.contiguous(), "a": acoustic.contiguous()}
+        for m, src in srcs.items():
             if src.dtype != torch.float32 or src.shape[1] != B or src.shape[2] != self.H[m]:
                 raise MmdaError(f"{m} input has shape {tuple(src.shape)} / {src.dtype}")
             X[m] = self.buf(f"X_{m}", N, self.H[m])
-            k._c("mmda_gather_rows", _ptr(src), _ptr(X[m]), _ptr(pk["row_t"]), _ptr(pk["row_j"]),
-                 _ptr(pk["sidx"]), N, B, self.H[m])
-        self.saved = dict(pk=pk, sent=sent, X=X, train=train)
-        utt = {m: self._encode(m, X[m], pk, train, P) for m in MODS}
+        X["t"] = self.buf("X_t", N, self.H["t"])
+
+        def enc_text():
+            k._c("mmda_embedding_forward", _ptr(P["embed.weight"]), _ptr(sent), _ptr(X["t"]),
+                 _ptr(pk["row_t"]), _ptr(pk["row_j"]), _ptr(pk["sidx"]), N, B, self.H["t"], V)
+            utt["t"] = self._encode("t", X["t"], pk, train, P)
+
+        def enc_side(m):
+            def run():
+                k._c("mmda_gather_rows", _ptr(srcs[m]), _ptr(X[m]), _ptr(pk["row_t"]),
+                     _ptr(pk["row_j"]), _ptr(pk["sidx"]), N, B, self.H[m])
+                utt[m] = self._encode(m, X[m], pk, train, P)
+            return run
+
+        self.saved = dict(pk=pk, sent=sent, X=X, train=train, srcs=srcs)
+        self._fork({"t": enc_text, "v": enc_side("v"), "a": enc_side("a")})
 
         # ---- heads: project -> private/shared -> recon (src/models.py:254-279) ----
         A = self.buf("A", 3, B, d)             # activation output (pre-LN)
@@ -574,9 +617,13 @@ class MisaEngine:
         notify("heads")
 
         # ---- encoders: BPTT + hoisted weight-gradient GEMMs ----
-        for m in ("v", "a", "t"):       # text last: its gradients are the biggest bucket
-            self._encode_backward(m, dutt[m], G, pk, P)
-            notify(f"enc_{m}")
+        def enc_bwd(m):
+            def run():
+                self._encode_backward(m, dutt[m], G, pk, P)
+                notify(f"enc_{m}")       # on the stream that produced the gradients
+            return run
+
+        self._fork({m: enc_bwd(m) for m in MODS})
 
     def _encode_backward(self, m, dutt, G, pk, P):
         k, H = self.k, self.H[m]
@@ -591,7 +638,7 @@ class MisaEngine:
         nbytes = LIB.raw("mmda_lstm_scratch_bytes")(B, H)
         if nbytes < 0:
             raise MmdaError(LIB.raw("mmda_last_error")().decode())
-        scratch = self.buf("lstm_scratch", max(1, nbytes // 4))
+        scratch = self.buf(f"lstm_scratch_{m}", max(1, nbytes // 4))
         HP = self.buf(f"HP_{m}", N, 2 * H)
         dY1n = self.buf(f"dY1n_{m}", N, 2 * H)
         dY1 = self.buf(f"dY1_{m}", N, 2 * H)
