@@ -1,0 +1,79 @@
+"""Data-parallel parity on real GPUs (needs >= 2 GPUs; skipped otherwise): two ranks, each with
+half of the batch, must reproduce the single-GPU full-batch losses, gradients and post-step
+parameters (exact global-batch semantics through the statistics all-reduces)."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from mmda_b200 import MISA, mosei_config
+    from mmda_b200.synthetic import batch_for
+    from mmda_b200.trainer import FusedTrainer
+    cfg = mosei_config(vocab_size=500, batch_size=64, use_confidNet=True)
+    full = batch_for(cfg, seed=9, lengths="ragged", seq_len=20)
+
+    def make():
+        torch.manual_seed(3)
+        m = MISA(cfg)
+        for n, p in m.named_parameters():
+            if "weight_hh" in n:
+                torch.nn.init.orthogonal_(p)
+        return m.to(dev).eval()
+
+    def run(tr, b):
+        L = tr.forward_backward(b.sentences.to(dev), b.visual.to(dev), b.acoustic.to(dev), b.lengths,
+                                b.labels.to(dev))
+        return L[:6].clone()
+
+    per = 64 // world
+    tr_dp = FusedTrainer(make(), process_group=dist.group.WORLD)
+    L_dp = run(tr_dp, full.slice(rank * per, (rank + 1) * per))
+    tr_1 = FusedTrainer(make())
+    L_1 = run(tr_1, full)
+    na = tr_1.n_active
+    scale = float(tr_1.g_arena[:na].abs().max())
+    gerr = float((tr_dp.g_arena[:na] - tr_1.g_arena[:na]).abs().max()) / scale
+    lerr = float(((L_dp - L_1).abs() / L_1.abs().clamp_min(1e-6)).max())
+    tr_dp.optimizer_step(); tr_1.optimizer_step()
+    torch.cuda.synchronize()
+    q.put((rank, lerr, gerr))
+    dist.destroy_process_group()
+
+
+def test_two_rank_shards_equal_single_gpu_full_batch():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=300) for _ in range(2))
+    [p.join(60) for p in procs]
+    for rank, lerr, gerr in res:
+        assert lerr < 1e-5, (rank, lerr)
+        assert gerr < 2e-5, (rank, gerr)
