@@ -143,6 +143,9 @@ def run_reference(args, rank):
 # our arm
 # ------------------------------------------------------------------------------------------
 def run_ours(args):
+    # keep stdout clean for the single JSON line (NCCL / libraries may print banners to fd 1)
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     dist, pg, rank, local, world = dist_setup(args.gpus)
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
@@ -279,7 +282,8 @@ def run_ours(args):
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32},
             "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cb,
             "losses": dict(zip(LOSS_NAMES, last[:6])), "lib": os.path.basename(LIB.load()._name)}
-    print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if dist is not None:
         dist.destroy_process_group()
 
