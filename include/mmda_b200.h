@@ -99,6 +99,8 @@ int mmda_lstm_backward(float* gates, const float* whh_f, const float* whh_r, con
 long long mmda_lstm_scratch_bytes(int B, int H);
 /* out6 = {cluster size, units per CTA, batch tile, n batch tiles, smem fwd, smem bwd} */
 int mmda_lstm_plan(int B, int H, int* out6);
+/* diagnostic: per-step phase timestamps of CTA 0 of subsequent forward launches (NULL = off) */
+int mmda_lstm_set_debug_buffer(long long* dev_buf);
 /* diagnostic: co-resident clusters of the recurrent kernel for cluster sizes {1,2,4,8,16} */
 int mmda_lstm_probe_clusters(int smem_bytes, int threads, int* out5);
 /* h_{prev} operand for the hoisted dW_hh GEMM: [N][2H] */

@@ -60,6 +60,16 @@ __device__ __forceinline__ float act_grad_from_output(float y, int act) {
   }
 }
 
+// Fast gate nonlinearities for the recurrence: MUFU.EX2 + MUFU.RCP, absolute error ~2e-7 (the
+// libm expf/tanhf versions cost ~4x the instructions and sat on the per-step critical path).
+__device__ __forceinline__ float fast_sigmoid(float x) {
+  return __fdividef(1.0f, 1.0f + __expf(-x));
+}
+__device__ __forceinline__ float fast_tanh(float x) {
+  // 1 - 2/(1+e^{2x}); saturates cleanly: e^{2x} -> inf gives 1, -> 0 gives -1
+  return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -99,6 +109,40 @@ __device__ __forceinline__ uint32_t dsmem_addr(const void* smem_ptr, unsigned ra
 }
 __device__ __forceinline__ void dsmem_st_f2(uint32_t addr, float a, float b) {
   asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+}
+// ---- mbarrier + DSMEM bulk copy (TMA engine) ----
+__device__ __forceinline__ void mbar_init_cta(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait_parity(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "MBW_LOOP:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra MBW_DONE;\n\t"
+      "bra MBW_LOOP;\n\t"
+      "MBW_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+// generic-proxy shared-memory writes -> visible to the async proxy (bulk copy engine)
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// copy `bytes` (multiple of 16) from this CTA's smem to a peer CTA's smem; completion is
+// signalled as transaction bytes on the PEER's mbarrier
+__device__ __forceinline__ void dsmem_bulk_copy(uint32_t dst_cluster_addr, uint32_t src_cta_addr,
+                                                uint32_t bytes, uint32_t mbar_cluster_addr) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(dst_cluster_addr), "r"(src_cta_addr), "r"(bytes), "r"(mbar_cluster_addr)
+      : "memory");
 }
 // L2-coherent global load (bypasses L1): data another CTA wrote during this kernel
 __device__ __forceinline__ float ld_cg(const float* p) { return __ldcg(p); }

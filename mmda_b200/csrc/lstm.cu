@@ -36,6 +36,7 @@ struct LstmArgs {
   float* scratch;         // bwd: partial-sum exchange [2][n_clusters][C][BT][Kpad]
   int utt_ld, utt_off0, utt_off1;
   int B, H, Hs, Kpad, C, n_tiles, save, Tmax;
+  long long* dbg;         // optional per-step phase timestamps (profiling builds of the bench)
 };
 
 template <int N, int BITLO>
@@ -73,10 +74,11 @@ __global__ void __launch_bounds__(BT == 40 ? 800 : 640, 1) lstm_fwd_kernel(const
   const int b_base = tile * BT;
 
   float4* Ws = reinterpret_cast<float4*>(smem);   // [Kpad][Hs] of (i,f,g,o) rows of one unit
-  float* h_s = smem + 4 * Kpad * Hs;              // [Kpad][BTP]
-  int* lens_s = reinterpret_cast<int*>(h_s + Kpad * BTP);
+  float* h_s = smem + 4 * Kpad * Hs;              // [C*Hs][BTP]; CTA r owns rows [r*Hs, r*Hs+Hs)
+  const int HR = max(C * Hs, Kpad);               // rows past H stay zero
+  int* lens_s = reinterpret_cast<int*>(h_s + HR * BTP);
   int* orig_s = lens_s + BT;
-  int* offs_s = orig_s + BT;                      // [Tmax+1]
+  const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(orig_s + BT);   // 8-byte aligned
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = lane >> 3, usub = lane & 7;
@@ -96,16 +98,16 @@ __global__ void __launch_bounds__(BT == 40 ? 800 : 640, 1) lstm_fwd_kernel(const
       const float v = (k < H && ugl < H) ? W[(size_t)(g * H + ugl) * H + k] : 0.f;
       smem[(k * Hs + ul) * 4 + g] = v;
     }
-    for (int idx = tid; idx < Kpad * BTP; idx += blockDim.x) h_s[idx] = 0.f;
+    for (int idx = tid; idx < HR * BTP; idx += blockDim.x) h_s[idx] = 0.f;
     if (tid < BT) {
       const int b = b_base + tid;
       lens_s[tid] = b < p.B ? p.lens[b] : 0;
       orig_s[tid] = b < p.B ? p.sorted_idx[b] : 0;
     }
-    for (int idx = tid; idx <= p.Tmax; idx += blockDim.x) offs_s[idx] = p.offsets[idx];
+    if (tid == 0) mbar_init_cta(mbar, 1);
   }
   __syncthreads();
-  cluster_sync_all();  // every peer's h_s is zeroed before anyone pushes into it
+  cluster_sync_all();  // every peer's h_s is zeroed / mbarrier initialised before anyone pushes
 
   const int Lmax = lens_s[0];
   const int bl0 = bg * 8 + 2 * q;
@@ -118,13 +120,20 @@ __global__ void __launch_bounds__(BT == 40 ? 800 : 640, 1) lstm_fwd_kernel(const
   const int K4 = Kpad >> 2;
   float c0 = 0.f, c1 = 0.f;
 
-  // my (unit, batch pair) slot of h_s; the same offset is pushed into every peer CTA
-  const float* h_slot = h_s + min(u_glob, Kpad - 1) * BTP + bl0;
+  // my (unit, batch pair) slot in this CTA's own slice of h_s; the whole slice (Hs x BTP floats,
+  // contiguous) is then replicated into every peer with one DSMEM bulk copy per peer
+  float* h_slot = h_s + min(u_glob, HR - 1) * BTP + bl0;
+  const uint32_t slice_bytes = (uint32_t)(Hs * BTP * 4);
+  const uint32_t slice_addr = (uint32_t)__cvta_generic_to_shared(h_s + rank * Hs * BTP);
 
+  const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0;
+#define LSTM_TS(i) if (dbg_on) p.dbg[s * 8 + (i)] = clock64();
   for (int s = 0; s < Lmax; ++s) {
     const int t = dir == 0 ? s : Lmax - 1 - s;
+    LSTM_TS(0)
+    if (C > 1 && tid == 0) mbar_arrive_expect_tx(mbar, (C - 1) * slice_bytes);   // arm for h_t
     const bool a0 = u_ok && t < len0, a1 = u_ok && t < len1;
-    const int off_t = offs_s[t];
+    const int off_t = __ldg(p.offsets + t);
     const size_t row0 = (size_t)(off_t + b_base + bl0), row1 = row0 + 1;
     float x0[4] = {0.f, 0.f, 0.f, 0.f}, x1[4] = {0.f, 0.f, 0.f, 0.f};
     if (a0) {
@@ -158,31 +167,43 @@ __global__ void __launch_bounds__(BT == 40 ? 800 : 640, 1) lstm_fwd_kernel(const
       }
       reduce_scatter<32, 8>(acc, lane);  // lane q now owns batch rows 2q, 2q+1 -> acc[0..8)
     }
+    LSTM_TS(1)
     cluster_arrive_relaxed();  // A: this CTA is done reading h_{t-1}
 
     float hn0 = 0.f, hn1 = 0.f, s0[5], s1[5];
     if (a0) {
-      s0[0] = sigmoidf_acc(acc[0] + x0[0]); s0[1] = sigmoidf_acc(acc[1] + x0[1]);
-      s0[2] = tanhf(acc[2] + x0[2]);        s0[3] = sigmoidf_acc(acc[3] + x0[3]);
+      s0[0] = fast_sigmoid(acc[0] + x0[0]); s0[1] = fast_sigmoid(acc[1] + x0[1]);
+      s0[2] = fast_tanh(acc[2] + x0[2]);    s0[3] = fast_sigmoid(acc[3] + x0[3]);
       c0 = s0[1] * c0 + s0[0] * s0[2];
       s0[4] = c0;
-      hn0 = s0[3] * tanhf(c0);
+      hn0 = s0[3] * fast_tanh(c0);
     }
     if (a1) {
-      s1[0] = sigmoidf_acc(acc[4] + x1[0]); s1[1] = sigmoidf_acc(acc[5] + x1[1]);
-      s1[2] = tanhf(acc[6] + x1[2]);        s1[3] = sigmoidf_acc(acc[7] + x1[3]);
+      s1[0] = fast_sigmoid(acc[4] + x1[0]); s1[1] = fast_sigmoid(acc[5] + x1[1]);
+      s1[2] = fast_tanh(acc[6] + x1[2]);    s1[3] = fast_sigmoid(acc[7] + x1[3]);
       c1 = s1[1] * c1 + s1[0] * s1[2];
       s1[4] = c1;
-      hn1 = s1[3] * tanhf(c1);
+      hn1 = s1[3] * fast_tanh(c1);
     }
 
+    LSTM_TS(2)
     cluster_wait();  // A: every CTA of the cluster is done reading h_{t-1}
-    if (a0 || a1) {
-#pragma unroll
-      for (int r = 0; r < 8; ++r)
-        if (r < C) dsmem_st_f2(dsmem_addr(h_slot, r), hn0, hn1);
+    LSTM_TS(3)
+    if (a0 || a1) *reinterpret_cast<float2*>(h_slot) = make_float2(hn0, hn1);
+    if (C > 1) {
+      fence_proxy_async_smem();
+      __syncthreads();
+      if (tid == 0) {
+#pragma unroll 1
+        for (unsigned r = 0; r < (unsigned)C; ++r)
+          if (r != rank)
+            dsmem_bulk_copy(dsmem_addr(h_s + rank * Hs * BTP, r), slice_addr, slice_bytes,
+                            dsmem_addr(orig_s + BT, r));
+      }
+    } else {
+      __syncthreads();
     }
-    cluster_arrive();  // B: h_t pushed (release)
+    LSTM_TS(4)
     // global stores drain while the barrier completes
     if (a0) {
       if (p.save) {
@@ -204,8 +225,12 @@ __global__ void __launch_bounds__(BT == 40 ? 800 : 640, 1) lstm_fwd_kernel(const
       const bool fin = dir == 0 ? (t == len1 - 1) : (t == 0);
       if (fin && p.utt) p.utt[(size_t)orig1 * p.utt_ld + utt_off + u_glob] = hn1;
     }
-    cluster_wait();  // B
+    LSTM_TS(5)
+    if (C > 1) mbar_wait_parity(mbar, s & 1);   // the 7 peer slices of h_t have landed
+    LSTM_TS(6)
   }
+#undef LSTM_TS
+  cluster_sync_all();   // no CTA may exit while a peer's bulk copy still reads its shared memory
 }
 
 // ------------------------------------------------------------------------------------------
@@ -228,7 +253,6 @@ __global__ void __launch_bounds__(BT == 40 ? 800 : 640, 1) lstm_bwd_kernel(const
   float* dG_s = smem + R * Kpad;    // [R][BTP]
   int* lens_s = reinterpret_cast<int*>(dG_s + R * BTP);
   int* orig_s = lens_s + BT;
-  int* offs_s = orig_s + BT;        // [Tmax+1]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int BG = BT / 8;
@@ -257,7 +281,6 @@ __global__ void __launch_bounds__(BT == 40 ? 800 : 640, 1) lstm_bwd_kernel(const
       const int ugl = rank * Hs + ul;
       Wb[idx] = (k < H && ul < Hs && ugl < H) ? W[(size_t)(g * H + ugl) * H + k] : 0.f;
     }
-    for (int idx = tid; idx <= p.Tmax; idx += blockDim.x) offs_s[idx] = p.offsets[idx];
     for (int idx = tid; idx < R * BTP; idx += blockDim.x) dG_s[idx] = 0.f;
     if (tid < BT) {
       const int b = b_base + tid;
@@ -288,7 +311,7 @@ __global__ void __launch_bounds__(BT == 40 ? 800 : 640, 1) lstm_bwd_kernel(const
 
     // ---- prefetch everything the cell update needs (latency hidden behind the matvec) ----
     const bool a0 = u_ok && t < len0, a1 = u_ok && t < len1;
-    const int off_t = offs_s[t];
+    const int off_t = __ldg(p.offsets + t);
     const size_t row0 = (size_t)(off_t + b_base + ebl0), row1 = row0 + 1;
     // forward-order predecessor time (its c is c_{prev}); forward-order successor feeds dh_rec
     const int tp = dir == 0 ? t - 1 : t + 1;
@@ -299,7 +322,7 @@ __global__ void __launch_bounds__(BT == 40 ? 800 : 640, 1) lstm_bwd_kernel(const
       for (int g = 0; g < 4; ++g) g0[g] = p.gates[row0 * H8 + gcol + g * H];
       ct0 = p.c[row0 * H2 + ycol];
       const bool hp = dir == 0 ? (t >= 1) : (t + 1 < len0);
-      if (hp) cp0 = p.c[(size_t)(offs_s[tp] + b_base + ebl0) * H2 + ycol];
+      if (hp) cp0 = p.c[(size_t)(__ldg(p.offsets + tp) + b_base + ebl0) * H2 + ycol];
       if (p.dy) dh0 = p.dy[row0 * H2 + ycol];
       const bool fin = dir == 0 ? (t == len0 - 1) : (t == 0);
       if (fin && p.dutt) dh0 += p.dutt[(size_t)orig0 * p.utt_ld + utt_off + u_glob];
@@ -310,7 +333,7 @@ __global__ void __launch_bounds__(BT == 40 ? 800 : 640, 1) lstm_bwd_kernel(const
       for (int g = 0; g < 4; ++g) g1[g] = p.gates[row1 * H8 + gcol + g * H];
       ct1 = p.c[row1 * H2 + ycol];
       const bool hp = dir == 0 ? (t >= 1) : (t + 1 < len1);
-      if (hp) cp1 = p.c[(size_t)(offs_s[tp] + b_base + ebl0 + 1) * H2 + ycol];
+      if (hp) cp1 = p.c[(size_t)(__ldg(p.offsets + tp) + b_base + ebl0 + 1) * H2 + ycol];
       if (p.dy) dh1 = p.dy[row1 * H2 + ycol];
       const bool fin = dir == 0 ? (t == len1 - 1) : (t == 0);
       if (fin && p.dutt) dh1 += p.dutt[(size_t)orig1 * p.utt_ld + utt_off + u_glob];
@@ -361,7 +384,7 @@ __global__ void __launch_bounds__(BT == 40 ? 800 : 640, 1) lstm_bwd_kernel(const
         for (int r = 0; r < C; ++r) dh0 += ld_cg(src + (size_t)r * slab);
       }
       const float ig = g0[0], fg = g0[1], gg = g0[2], og = g0[3];
-      const float tc = tanhf(ct0);
+      const float tc = fast_tanh(ct0);
       const float dog = dh0 * tc * og * (1.f - og);
       const float dc = dc0 + dh0 * og * (1.f - tc * tc);
       const float dig = dc * gg * ig * (1.f - ig);
@@ -379,7 +402,7 @@ __global__ void __launch_bounds__(BT == 40 ? 800 : 640, 1) lstm_bwd_kernel(const
         for (int r = 0; r < C; ++r) dh1 += ld_cg(src + (size_t)r * slab);
       }
       const float ig = g1[0], fg = g1[1], gg = g1[2], og = g1[3];
-      const float tc = tanhf(ct1);
+      const float tc = fast_tanh(ct1);
       const float dog = dh1 * tc * og * (1.f - og);
       const float dc = dc1 + dh1 * og * (1.f - tc * tc);
       const float dig = dc * gg * ig * (1.f - ig);
@@ -462,8 +485,9 @@ static int lstm_make_plan(int B, int H, int Tmax, LstmPlan* pl) {
       const int BT = cand[ci];
       if (H > 128 && BT == 8) break;
       const int BTP = BT + (BT % 32 == 0 ? 4 : 0);
-      const size_t misc = (size_t)(2 * BT + Tmax + 1) * 4;
-      const size_t fwd = (size_t)4 * Kpad * Hs * 4 + (size_t)Kpad * BTP * 4 + misc;
+      const size_t misc = (size_t)(2 * BT) * 4 + 16;
+      const int HR = C * Hs > Kpad ? C * Hs : Kpad;
+      const size_t fwd = (size_t)4 * Kpad * Hs * 4 + (size_t)HR * BTP * 4 + misc;
       const size_t bwd = (size_t)R * Kpad * 4 + (size_t)R * BTP * 4 + misc;
       if (fwd > (size_t)g_max_smem || bwd > (size_t)g_max_smem) continue;
       const int UG = (Hs + 7) / 8, BG = BT / 8, K4 = Kpad / 4;
@@ -511,7 +535,16 @@ static int launch_cluster(K kern, const LstmArgs& a, const LstmPlan& pl, int thr
   return MMDA_OK;
 }
 
+static long long* g_lstm_dbg = nullptr;
+
 extern "C" {
+
+// profiling aid: when set (device buffer of >= 8*Tmax int64), CTA 0 of the NEXT forward launches
+// records clock64() at the phase boundaries of every step
+int mmda_lstm_set_debug_buffer(long long* dev_buf) {
+  g_lstm_dbg = dev_buf;
+  return MMDA_OK;
+}
 
 long long mmda_lstm_scratch_bytes(int B, int H) {
   LstmPlan pl;
@@ -572,6 +605,7 @@ int mmda_lstm_forward(float* gates, const float* whh_f, const float* whh_r, floa
   a.utt = utt; a.utt_ld = utt_ld; a.utt_off0 = utt_off_f; a.utt_off1 = utt_off_r;
   a.B = B; a.H = H; a.Hs = pl.Hs; a.Kpad = pl.Kpad; a.C = pl.C; a.n_tiles = pl.n_tiles;
   a.save = save_for_backward;
+  a.dbg = g_lstm_dbg;
   if (pl.BT == 40) return launch_cluster(lstm_fwd_kernel<40>, a, pl, pl.threads_fwd, pl.smem_fwd, stream);
   if (pl.BT == 32) return launch_cluster(lstm_fwd_kernel<32>, a, pl, pl.threads_fwd, pl.smem_fwd, stream);
   return launch_cluster(lstm_fwd_kernel<8>, a, pl, pl.threads_fwd, pl.smem_fwd, stream);

@@ -252,14 +252,15 @@ class MisaEngine:
     def _tc_ok(self, H, I):
         return self.use_tc and H % 4 == 0 and I % 4 == 0
 
-    def _prep(self, name, x, out=None, row0=0):
+    def _prep(self, name, x, out=None, row0=0, kind=None):
         """Tensor-core operand copy of the 2-D view x: (hi, lo) tf32 split or (bf16, None).
         Rows land at [row0, row0+rows) of the (possibly larger) buffer `out`."""
+        kind = self.tc_kind if kind is None else kind
         rows, cols = x.shape
         if out is None:
-            out = self._prep_buf(name, rows, cols)
+            out = self._prep_buf(name, rows, cols, kind)
         hi, lo = out
-        if self.tc_kind == 0:
+        if kind == 0:
             self.k._c("mmda_split_tf32", _ptr(x), x.stride(0), rows, cols, _ptr(hi[row0:]),
                       _ptr(lo[row0:]), hi.stride(0))
         else:
@@ -267,8 +268,9 @@ class MisaEngine:
                       hi.stride(0))
         return out
 
-    def _prep_buf(self, name, rows, cols):
-        if self.tc_kind == 0:
+    def _prep_buf(self, name, rows, cols, kind=None):
+        kind = self.tc_kind if kind is None else kind
+        if kind == 0:
             ld = (cols + 3) // 4 * 4
             hi = self.buf(name + "_hi", rows, ld)[:, :cols]
             lo = self.buf(name + "_lo", rows, ld)[:, :cols]
@@ -656,21 +658,21 @@ class MisaEngine:
             I = Xin.shape[1]
             tc = self._tc_ok(H, I)
             if tc:
-                kind = self.tc_kind
-                dGp = self._prep("tcdG", Gt)
-                Xp = self._prep_buf(f"tcX_{r}", N, I)          # written by the forward
-                Wst = self._prep_buf(f"tcW_{r}", 8 * H, I)
-                if kind == 0:
-                    HPp = self._prep("tcHP", HP)
-                    hp_cols = lambda di: self._cols(HPp, di * H, (di + 1) * H)
-                else:   # keep each direction's h_prev on a 16-byte aligned column offset
-                    Hp8 = (H + 7) // 8 * 8
-                    full = self.buf("tcHP_bf", N, 2 * Hp8, dtype=torch.bfloat16)
-                    for di in range(2):
-                        src = HP[:, di * H:(di + 1) * H]
-                        k._c("mmda_cast_bf16", _ptr(src), src.stride(0), N, H,
-                             _ptr(full[:, di * Hp8:]), full.stride(0))
-                    hp_cols = lambda di: (full[:, di * Hp8:di * Hp8 + H], None)
+                # Backward GEMMs are always 3xTF32: weight/activation gradients are sums with heavy
+                # cancellation, where bf16 operands cost several percent (measured 4-13 %); bf16
+                # mode covers the forward input projection only (BASELINE configs[2]).
+                kind = 0
+                dGp = self._prep("tcdG", Gt, kind=0)
+                if self.tc_kind == 0:      # operand splits written by the forward
+                    Xp = self._prep_buf(f"tcX_{r}", N, I, 0)
+                    Wst = self._prep_buf(f"tcW_{r}", 8 * H, I, 0)
+                else:
+                    Xp = self._prep(f"tcX_{r}", Xin, kind=0)
+                    Wst = self._prep_buf(f"tcW_{r}", 8 * H, I, 0)
+                    for di, suf in enumerate(("", "_reverse")):
+                        self._prep(None, P[f"{r}.weight_ih_l0{suf}"], out=Wst, row0=di * 4 * H, kind=0)
+                HPp = self._prep("tcHP", HP, kind=0)
+                hp_cols = lambda di: self._cols(HPp, di * H, (di + 1) * H)
             for di, suf in enumerate(("", "_reverse")):
                 dG = Gt[:, di * 4 * H:(di + 1) * 4 * H]
                 if tc:   # contract over tokens: both operands MN-major, auto split-K

@@ -440,3 +440,33 @@ def test_gemm_tc_tf32x3_and_bf16(dev):
                 ref = (Ad.t() if a_mn else Ad) @ (Bd if b_mn else Bd.t())
                 C.add(f"bf16 {M}x{N}x{K} a_mn={a_mn} b_mn={b_mn}", out, ref, 1e-5)
     C.finish()
+
+
+def test_c3_bf16_mode_within_2e2(dev):
+    """BASELINE configs[2]: ConfidNet branch + bf16 input-projection GEMMs (tcgen05 kind::f16,
+    fp32 accumulate).  Tolerance 2e-2 scale-relative on logits, losses and gradients."""
+    from mmda_b200 import MISA, config as Cfg
+    from mmda_b200.synthetic import batch_for
+    from mmda_b200.trainer import FusedTrainer, LOSS_NAMES
+    from oracle.misa_oracle import oracle_build, OracleMISA, oracle_step
+    rec = json.load(open(os.path.join(GOLDEN, "c3_mosei_confid_b256.json")))
+    cfg = Cfg.mosei_config(vocab_size=2000, use_confidNet=True)
+    state = {k: v.clone() for k, v in oracle_build(cfg, rec["seed"]).state_dict().items()}
+    batch = batch_for(cfg, seed=rec["batch_seed"], lengths="ragged")
+    ref = OracleMISA(cfg); ref.load_state_dict(state); ref.eval()
+    out, L, grads = oracle_step(ref, batch, cfg, None)
+    cfg16 = Cfg.mosei_config(vocab_size=2000, use_confidNet=True, precision="bf16")
+    model = MISA(cfg16); model.load_state_dict(state); model = model.to(dev).eval()
+    assert model.engine.tc_kind == 1
+    tr = FusedTrainer(model)
+    s, v, a, ln = _to(batch, dev)
+    losses = tr.forward_backward(s, v, a, ln, batch.labels.to(dev))
+    C = Checks("c3_bf16")
+    lv = dict(zip(LOSS_NAMES, losses[:6].tolist()))
+    for kk in LOSS_NAMES:
+        C.add("bf16 loss " + kk, torch.tensor(lv[kk]), L[kk].detach(), 2e-2)
+    C.add("bf16 scores", model.engine.ws["SCORES"][:256 * 6].view(256, 6), out["scores"].detach(), 2e-2)
+    for n, g in grads.items():
+        if g is not None:
+            C.add("bf16 grad " + n, tr.G[n], g, 2e-2)
+    C.finish()
