@@ -148,6 +148,13 @@ static int launch_sgemm(bool ta, bool tb, const float* A, const float* B, float*
   return MMDA_OK;
 }
 
+__global__ void zero2d_kernel(float* __restrict__ c, int ldc, int rows, int cols) {
+  const size_t n = (size_t)rows * cols;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x)
+    c[(i / cols) * ldc + (i % cols)] = 0.f;
+}
+
 extern "C" int mmda_sgemm(int transA, int transB, int M, int N, int K, float alpha,
                           const float* A, int lda, const float* B, int ldb, float beta, float* C,
                           int ldc, const float* bias, const float* bias2, int act, int split_k,
@@ -157,19 +164,31 @@ extern "C" int mmda_sgemm(int transA, int transB, int M, int N, int K, float alp
   MMDA_REQUIRE(split_k >= 0 && split_k <= 64, "sgemm: split_k=%d out of range", split_k);
   const long big_tiles = (long)((M + 127) / 128) * ((N + 127) / 128);
   const long med_tiles = (long)((M + 63) / 64) * ((N + 63) / 64);
-  if (split_k == 0) {   // auto: split only long-K problems that cannot fill the chip
+  const long small_tiles = (long)((M + 31) / 32) * ((N + 31) / 32);
+  // tile shape: the largest one that still fills the 148 SMs (possibly with the help of split-K)
+  int cfg = big_tiles >= 120 ? 2 : (med_tiles >= 32 ? 1 : 0);
+  if (split_k == 0) {   // auto: split long-K problems that cannot fill the chip
     split_k = 1;
-    if (beta == 1.f && act == ACT_NONE && K >= 2048) {
-      long tiles = big_tiles >= 148 ? big_tiles : med_tiles;
-      while (tiles * split_k < 296 && K / (split_k * 2) >= 512 && split_k < 32) split_k *= 2;
-    }
+    // auto split only where the result is accumulated anyway (gradients); plain forward
+    // products stay single-pass so the forward is bitwise reproducible run to run
+    const bool can_split = act == ACT_NONE && beta == 1.f;
+    const long tiles = cfg == 2 ? big_tiles : cfg == 1 ? med_tiles : small_tiles;
+    const long want = cfg == 0 ? 592 : 148;       // small tiles: 64-thread CTAs, want several per SM
+    if (can_split)
+      while (tiles * split_k < want && K / (split_k * 2) >= 256 && split_k < 32) split_k *= 2;
   }
-  MMDA_REQUIRE(split_k == 1 || (act == ACT_NONE && beta == 1.f),
-               "sgemm: split-K accumulates into C (needs beta=1, no activation)");
-  if (big_tiles >= 148)
+  MMDA_REQUIRE(split_k == 1 || (act == ACT_NONE && (beta == 1.f || beta == 0.f)),
+               "sgemm: split-K accumulates into C (needs beta 0/1, no activation)");
+  if (split_k > 1 && beta == 0.f) {   // split-K accumulates with atomics: start from zero
+    size_t n = (size_t)M * N, g = (n + 255) / 256;
+    zero2d_kernel<<<(int)(g > 1184 ? 1184 : g), 256, 0, stream>>>(C, ldc, M, N);
+    MMDA_CHECK_LAUNCH();
+    beta = 1.f;
+  }
+  if (cfg == 2)
     return launch_sgemm<128, 128, 16, 8, 8>(transA, transB, A, B, C, bias, bias2, M, N, K, lda, ldb, ldc,
                                             alpha, beta, act, split_k, stream);
-  if (med_tiles * split_k >= 148)
+  if (cfg == 1)
     return launch_sgemm<64, 64, 16, 4, 4>(transA, transB, A, B, C, bias, bias2, M, N, K, lda, ldb, ldc,
                                           alpha, beta, act, split_k, stream);
   return launch_sgemm<32, 32, 32, 4, 4>(transA, transB, A, B, C, bias, bias2, M, N, K, lda, ldb, ldc,

@@ -52,7 +52,7 @@ class Kernels:
 
     # C = act(alpha * op(A) op(B) + beta*C + bias + bias2); A,B,C are 2-D views with unit inner stride
     def gemm(self, A, B, C, ta=False, tb=False, alpha=1.0, beta=0.0, bias=None, bias2=None,
-             act=ACT_NONE, split_k=1):
+             act=ACT_NONE, split_k=0):
         M, N = C.shape
         K = A.shape[0] if ta else A.shape[1]
         assert A.stride(1) == 1 and B.stride(1) == 1 and C.stride(1) == 1
@@ -72,13 +72,14 @@ class Kernels:
     def linear(self, x, w, b, out, act=ACT_NONE, bias2=None):
         self.gemm(x, w, out, tb=True, bias=b, bias2=bias2, act=act)
 
-    def linear_bwd(self, dy, x, w, dw, db, dx=None, dx_beta=0.0, db2=None):
-        """dy: grad of the linear output (pre-activation).  dw/db accumulate."""
-        self.gemm(dy, x, dw, ta=True, beta=1.0, split_k=0)
+    def linear_bwd(self, dy, x, w, dw, db, dx=None, dx_beta=0.0, db2=None, dw_split=0):
+        """dy: grad of the linear output (pre-activation).  dw/db accumulate (dw_split >= 2
+        forces the atomic split-K path: needed when several streams accumulate into one dw)."""
+        self.gemm(dy, x, dw, ta=True, beta=1.0, split_k=dw_split)
         if db is not None:
             self.colsum(dy, db, db2)
         if dx is not None:
-            self.gemm(dy, w, dx, beta=dx_beta)
+            self.gemm(dy, w, dx, beta=dx_beta, split_k=1 if dx_beta not in (0.0, 1.0) else 0)
 
     def colsum(self, x, out, out2=None):
         self._c("mmda_colsum", _ptr(x), x.stride(0), x.shape[0], x.shape[1], _ptr(out), _ptr(out2))
@@ -223,6 +224,13 @@ class MisaEngine:
         if self._side is None:
             self._side = {m: torch.cuda.Stream(device=self._dev) for m in ("v", "a")}
         return self._side
+
+    def _wgrad_stream(self, m):
+        if not hasattr(self, "_wg"):
+            self._wg = {}
+        if m not in self._wg:
+            self._wg[m] = torch.cuda.Stream(device=self._dev)
+        return self._wg[m]
 
     def _fork(self, fns):
         """Run fns[m]() for m in v, a on side streams (after everything enqueued so far on the
@@ -384,20 +392,24 @@ class MisaEngine:
         pmu = self.buf("proj_mu", 3, B)
         prs = self.buf("proj_rs", 3, B)
         X0f = X0.view(B, 6 * d)
-        for i, m in enumerate(MODS):
-            k.linear(utt[m], P[f"project_{m}.project_{m}.weight"], P[f"project_{m}.project_{m}.bias"],
-                     A[i], act=self.act_id)
-            k.layernorm(A[i], None, P[f"project_{m}.project_{m}_layer_norm.weight"],
-                        P[f"project_{m}.project_{m}_layer_norm.bias"], O[i], pmu[i], prs[i])
-            tag = PRIV_TAG[m]
-            k.linear(O[i], P[f"private_{m}.private_{m}_{tag}.weight"],
-                     P[f"private_{m}.private_{m}_{tag}.bias"], X0f[:, i * d:(i + 1) * d],
-                     act=ACT_SIGMOID)
-            k.linear(O[i], P["shared.shared_1.weight"], P["shared.shared_1.bias"],
-                     X0f[:, (3 + i) * d:(4 + i) * d], act=ACT_SIGMOID)
-            k.add(SUM[i], X0f[:, i * d:(i + 1) * d], X0f[:, (3 + i) * d:(4 + i) * d])
-            k.linear(SUM[i], P[f"recon_{m}.recon_{m}_1.weight"], P[f"recon_{m}.recon_{m}_1.bias"],
-                     R[i])
+        def head_fwd(i, m):
+            def run():
+                k.linear(utt[m], P[f"project_{m}.project_{m}.weight"],
+                         P[f"project_{m}.project_{m}.bias"], A[i], act=self.act_id)
+                k.layernorm(A[i], None, P[f"project_{m}.project_{m}_layer_norm.weight"],
+                            P[f"project_{m}.project_{m}_layer_norm.bias"], O[i], pmu[i], prs[i])
+                tag = PRIV_TAG[m]
+                k.linear(O[i], P[f"private_{m}.private_{m}_{tag}.weight"],
+                         P[f"private_{m}.private_{m}_{tag}.bias"], X0f[:, i * d:(i + 1) * d],
+                         act=ACT_SIGMOID)
+                k.linear(O[i], P["shared.shared_1.weight"], P["shared.shared_1.bias"],
+                         X0f[:, (3 + i) * d:(4 + i) * d], act=ACT_SIGMOID)
+                k.add(SUM[i], X0f[:, i * d:(i + 1) * d], X0f[:, (3 + i) * d:(4 + i) * d])
+                k.linear(SUM[i], P[f"recon_{m}.recon_{m}_1.weight"],
+                         P[f"recon_{m}.recon_{m}_1.bias"], R[i])
+            return run
+
+        self._fork({m: head_fwd(i, m) for i, m in enumerate(MODS)})
         out = {}
         if want_sp:        # outputs no loss reads (src/models.py:234-237); kept for the contract
             SP = self.buf("SP", 4, B, 4)
@@ -586,36 +598,43 @@ class MisaEngine:
         # ---- recon / private / shared / project ----
         dO = self.buf("dO", 3, B, d)
         dA = self.buf("dA", 3, B, d)
-        dutt = {}
-        for i, m in enumerate(MODS):
-            ps, ss = dX0f[:, i * d:(i + 1) * d], dX0f[:, (3 + i) * d:(4 + i) * d]
-            if d_recon is not None:
-                dsum = self.buf("dSUM", B, d)
-                k.linear_bwd(d_recon[i], SUM[i], P[f"recon_{m}.recon_{m}_1.weight"],
-                             G[f"recon_{m}.recon_{m}_1.weight"], G[f"recon_{m}.recon_{m}_1.bias"],
-                             dsum, 0.0)
-                k.add(ps, ps, dsum)
-                k.add(ss, ss, dsum)
-            k.act_bwd(ps, X0f[:, i * d:(i + 1) * d], ACT_SIGMOID)
-            k.act_bwd(ss, X0f[:, (3 + i) * d:(4 + i) * d], ACT_SIGMOID)
-            tag = PRIV_TAG[m]
-            has_do = d_orig is not None
-            if has_do:
-                k.add(dO[i], d_orig[i])
-            k.linear_bwd(ps, O[i], P[f"private_{m}.private_{m}_{tag}.weight"],
-                         G[f"private_{m}.private_{m}_{tag}.weight"],
-                         G[f"private_{m}.private_{m}_{tag}.bias"], dO[i], 1.0 if has_do else 0.0)
-            k.linear_bwd(ss, O[i], P["shared.shared_1.weight"], G["shared.shared_1.weight"],
-                         G["shared.shared_1.bias"], dO[i], 1.0)
-            pmu, prs = self.buf("proj_mu", 3, B), self.buf("proj_rs", 3, B)
-            k.layernorm_bwd(dO[i], A[i], None, P[f"project_{m}.project_{m}_layer_norm.weight"],
-                            pmu[i], prs[i], dA[i], G[f"project_{m}.project_{m}_layer_norm.weight"],
-                            G[f"project_{m}.project_{m}_layer_norm.bias"])
-            k.act_bwd(dA[i], A[i], self.act_id)
-            dutt[m] = self.buf(f"dutt_{m}", B, 4 * self.H[m])
-            k.linear_bwd(dA[i], sv["utt"][m], P[f"project_{m}.project_{m}.weight"],
-                         G[f"project_{m}.project_{m}.weight"], G[f"project_{m}.project_{m}.bias"],
-                         dutt[m], 0.0)
+        dutt = {m: self.buf(f"dutt_{m}", B, 4 * self.H[m]) for m in MODS}
+        pmu, prs = self.buf("proj_mu", 3, B), self.buf("proj_rs", 3, B)
+
+        def head_bwd(i, m):
+            def run():
+                ps, ss = dX0f[:, i * d:(i + 1) * d], dX0f[:, (3 + i) * d:(4 + i) * d]
+                if d_recon is not None:
+                    dsum = self.buf(f"dSUM_{m}", B, d)
+                    k.linear_bwd(d_recon[i], SUM[i], P[f"recon_{m}.recon_{m}_1.weight"],
+                                 G[f"recon_{m}.recon_{m}_1.weight"],
+                                 G[f"recon_{m}.recon_{m}_1.bias"], dsum, 0.0)
+                    k.add(ps, ps, dsum)
+                    k.add(ss, ss, dsum)
+                k.act_bwd(ps, X0f[:, i * d:(i + 1) * d], ACT_SIGMOID)
+                k.act_bwd(ss, X0f[:, (3 + i) * d:(4 + i) * d], ACT_SIGMOID)
+                tag = PRIV_TAG[m]
+                has_do = d_orig is not None
+                if has_do:
+                    k.add(dO[i], d_orig[i])
+                k.linear_bwd(ps, O[i], P[f"private_{m}.private_{m}_{tag}.weight"],
+                             G[f"private_{m}.private_{m}_{tag}.weight"],
+                             G[f"private_{m}.private_{m}_{tag}.bias"], dO[i],
+                             1.0 if has_do else 0.0)
+                # the shared encoder's gradient is accumulated by all three modality streams
+                k.linear_bwd(ss, O[i], P["shared.shared_1.weight"], G["shared.shared_1.weight"],
+                             G["shared.shared_1.bias"], dO[i], 1.0, dw_split=2)
+                k.layernorm_bwd(dO[i], A[i], None, P[f"project_{m}.project_{m}_layer_norm.weight"],
+                                pmu[i], prs[i], dA[i],
+                                G[f"project_{m}.project_{m}_layer_norm.weight"],
+                                G[f"project_{m}.project_{m}_layer_norm.bias"])
+                k.act_bwd(dA[i], A[i], self.act_id)
+                k.linear_bwd(dA[i], sv["utt"][m], P[f"project_{m}.project_{m}.weight"],
+                             G[f"project_{m}.project_{m}.weight"],
+                             G[f"project_{m}.project_{m}.bias"], dutt[m], 0.0)
+            return run
+
+        self._fork({m: head_bwd(i, m) for i, m in enumerate(MODS)})
         notify("heads")
 
         # ---- encoders: BPTT + hoisted weight-gradient GEMMs ----
@@ -628,6 +647,10 @@ class MisaEngine:
         self._fork({m: enc_bwd(m) for m in MODS})
 
     def _encode_backward(self, m, dutt, G, pk, P):
+        """BPTT of both layers of modality m + the hoisted weight-gradient GEMMs.  The recurrence
+        and the dX GEMM form the critical path; the weight-gradient work of a layer (h_prev shift,
+        dW_ih, dW_hh, bias column sums) is pushed to a side stream so it overlaps the next BPTT
+        kernel (which leaves 36 of the 148 SMs free)."""
         k, H = self.k, self.H[m]
         r1, r2, ln = ENC[m]
         N, B, Tmax = pk["N"], pk["B"], pk["Tmax"]
@@ -641,9 +664,11 @@ class MisaEngine:
         if nbytes < 0:
             raise MmdaError(LIB.raw("mmda_last_error")().decode())
         scratch = self.buf(f"lstm_scratch_{m}", max(1, nbytes // 4))
-        HP = self.buf(f"HP_{m}", N, 2 * H)
         dY1n = self.buf(f"dY1n_{m}", N, 2 * H)
         dY1 = self.buf(f"dY1_{m}", N, 2 * H)
+        use_side = self.multi_stream and not _DRYRUN
+        cur = torch.cuda.current_stream() if use_side else None
+        side = self._wgrad_stream(m) if use_side else None
         for r, Gt, Y, C, Xin, dy, (o_f, o_r) in ((r2, G2, Y2, C2, Y1n, None, (H, 3 * H)),
                                                  (r1, G1, Y1, C1, X, dY1, (0, 2 * H))):
             if r == r1:
@@ -653,16 +678,13 @@ class MisaEngine:
                  _ptr(P[f"{r}.weight_hh_l0_reverse"]), _ptr(C), _ptr(dy), _ptr(dutt), 4 * H, o_f,
                  o_r, _ptr(pk["lens"]), _ptr(pk["sidx"]), _ptr(pk["off"]), _ptr(scratch), B, H,
                  Tmax)
-            k._c("mmda_lstm_shift_h", _ptr(Y), _ptr(HP), _ptr(pk["row_t"]), _ptr(pk["row_j"]),
-                 _ptr(pk["lens"]), _ptr(pk["off"]), N, H)
             I = Xin.shape[1]
             tc = self._tc_ok(H, I)
             if tc:
                 # Backward GEMMs are always 3xTF32: weight/activation gradients are sums with heavy
                 # cancellation, where bf16 operands cost several percent (measured 4-13 %); bf16
                 # mode covers the forward input projection only (BASELINE configs[2]).
-                kind = 0
-                dGp = self._prep("tcdG", Gt, kind=0)
+                dGp = self._prep(f"tcdG_{r}", Gt, kind=0)
                 if self.tc_kind == 0:      # operand splits written by the forward
                     Xp = self._prep_buf(f"tcX_{r}", N, I, 0)
                     Wst = self._prep_buf(f"tcW_{r}", 8 * H, I, 0)
@@ -671,25 +693,42 @@ class MisaEngine:
                     Wst = self._prep_buf(f"tcW_{r}", 8 * H, I, 0)
                     for di, suf in enumerate(("", "_reverse")):
                         self._prep(None, P[f"{r}.weight_ih_l0{suf}"], out=Wst, row0=di * 4 * H, kind=0)
-                HPp = self._prep("tcHP", HP, kind=0)
-                hp_cols = lambda di: self._cols(HPp, di * H, (di + 1) * H)
-            for di, suf in enumerate(("", "_reverse")):
-                dG = Gt[:, di * 4 * H:(di + 1) * 4 * H]
-                if tc:   # contract over tokens: both operands MN-major, auto split-K
-                    dGd = self._cols(dGp, di * 4 * H, (di + 1) * 4 * H)
-                    k.gemm_tc(kind, 1, 1, 4 * H, I, N, dGd, Xp, G[f"{r}.weight_ih_l0{suf}"], mode=1,
-                              split_k=0)
-                    k.gemm_tc(kind, 1, 1, 4 * H, H, N, dGd, hp_cols(di), G[f"{r}.weight_hh_l0{suf}"],
-                              mode=1, split_k=0)
-                else:
-                    self.big_gemm(dG, Xin, G[f"{r}.weight_ih_l0{suf}"], ta=True, beta=1.0, split_k=0)
-                    self.big_gemm(dG, HP[:, di * H:(di + 1) * H], G[f"{r}.weight_hh_l0{suf}"],
-                                  ta=True, beta=1.0, split_k=0)
-                k.colsum(dG, G[f"{r}.bias_ih_l0{suf}"], G[f"{r}.bias_hh_l0{suf}"])
+
+            def wgrad(r=r, Gt=Gt, Y=Y, Xin=Xin, tc=tc, I=I):
+                HP = self.buf(f"HP_{r}", N, 2 * H)
+                k._c("mmda_lstm_shift_h", _ptr(Y), _ptr(HP), _ptr(pk["row_t"]), _ptr(pk["row_j"]),
+                     _ptr(pk["lens"]), _ptr(pk["off"]), N, H)
+                if tc:
+                    HPp = self._prep(f"tcHP_{r}", HP, kind=0)
+                for di, suf in enumerate(("", "_reverse")):
+                    dG = Gt[:, di * 4 * H:(di + 1) * 4 * H]
+                    if tc:   # contract over tokens: both operands MN-major, auto split-K
+                        dGd = self._cols(dGp, di * 4 * H, (di + 1) * 4 * H)
+                        k.gemm_tc(0, 1, 1, 4 * H, I, N, dGd, Xp, G[f"{r}.weight_ih_l0{suf}"], mode=1,
+                                  split_k=0)
+                        k.gemm_tc(0, 1, 1, 4 * H, H, N, dGd, self._cols(HPp, di * H, (di + 1) * H),
+                                  G[f"{r}.weight_hh_l0{suf}"], mode=1, split_k=0)
+                    else:
+                        self.big_gemm(dG, Xin, G[f"{r}.weight_ih_l0{suf}"], ta=True, beta=1.0,
+                                      split_k=0)
+                        self.big_gemm(dG, HP[:, di * H:(di + 1) * H], G[f"{r}.weight_hh_l0{suf}"],
+                                      ta=True, beta=1.0, split_k=0)
+                    k.colsum(dG, G[f"{r}.bias_ih_l0{suf}"], G[f"{r}.bias_hh_l0{suf}"])
+
+            if use_side:
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                side.wait_event(ev)
+                with torch.cuda.stream(side):
+                    k.bind_stream()
+                    wgrad()
+                k.bind_stream()
+            else:
+                wgrad()
             if r == r2 or m == "t":
                 dX = dY1n if r == r2 else self.buf("dX_t", N, H)
                 if tc:   # dX = dG [N x 8H] * [W_ih ; W_ih_reverse] (stored [8H][I]: MN-major B)
-                    k.gemm_tc(kind, 0, 1, N, I, 8 * H, dGp, Wst, dX)
+                    k.gemm_tc(0, 0, 1, N, I, 8 * H, dGp, Wst, dX)
                 else:
                     for di, suf in enumerate(("", "_reverse")):
                         self.big_gemm(Gt[:, di * 4 * H:(di + 1) * 4 * H],
@@ -699,6 +738,10 @@ class MisaEngine:
                     k._c("mmda_embedding_backward", _ptr(G["embed.weight"]),
                          _ptr(self.saved["sent"]), _ptr(dX), _ptr(pk["row_t"]), _ptr(pk["row_j"]),
                          _ptr(pk["sidx"]), N, B, H, V)
+        if use_side:
+            done = torch.cuda.Event()
+            done.record(side)
+            cur.wait_event(done)
 
 
 # ------------------------------------------------------------------------------------------
