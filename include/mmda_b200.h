@@ -61,10 +61,12 @@ int mmda_embedding_backward(float* dE, const long long* sentences, const float* 
  * GEMMs of nn.LSTM (src/models.py:48-55).
  * C = act(alpha*op(A)*op(B) + beta*C + bias + bias2); op(A) = transA ? A[k*lda+m] : A[m*lda+k];
  * op(B) = transB ? B[n*ldb+k] : B[k*ldb+n].  split_k: 0 = auto, 1 = none, >1 = atomic split-K
- * (requires beta == 1 and no activation). */
+ * (requires beta == 1 and no activation).  c_row_interleave = H (else 0): logical row u*4+g of C
+ * is stored at row g*H+u -- un-does the gate-interleaved order of dG in the weight-gradient GEMMs. */
 int mmda_sgemm(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda,
                const float* B, int ldb, float beta, float* C, int ldc, const float* bias,
-               const float* bias2, int act, int split_k, mmda_stream_t stream);
+               const float* bias2, int act, int split_k, int c_row_interleave,
+               mmda_stream_t stream);
 
 /* Tensor-core path of the same contractions (tcgen05.mma + TMA + TMEM; csrc/gemm_tc.cu).
  * kind 0 = 3xTF32 (fp32-accurate; operands pre-split with mmda_split_tf32 into hi/lo fp32 arrays),
@@ -74,15 +76,16 @@ int mmda_sgemm(int transA, int transB, int M, int N, int K, float alpha, const f
 int mmda_gemm_tc(int kind, int a_mn, int b_mn, int M, int N, int K, const void* A_hi,
                  const void* A_lo, int lda, const void* B_hi, const void* B_lo, int ldb, float alpha,
                  float* C, int ldc, const float* bias, const float* bias2, int mode, int split_k,
-                 mmda_stream_t stream);
+                 int c_row_interleave, mmda_stream_t stream);
 int mmda_split_tf32(const float* x, int ldx, int rows, int cols, float* hi, float* lo, int ldo,
                     mmda_stream_t stream);
 int mmda_cast_bf16(const float* x, int ldx, int rows, int cols, void* out, int ldo,
                    mmda_stream_t stream);
 
 /* ---- bidirectional LSTM recurrence: nn.LSTM(bidirectional=True), src/models.py:48-55,167,176
- * gates [N][8H]: in = x*W_ih^T + b_ih + b_hh for (fwd | reverse); out (save_for_backward) =
- * activated gates.  y [N][2H], c [N][2H].  Final hidden states are scattered straight into the
+ * gates [N][2][H][4] (the i,f,g,o values of one unit adjacent): in = x*W_ih^T + b_ih + b_hh for
+ * (fwd | reverse), produced by a GEMM against mmda_lstm_pack_weights' permuted weight copy; out
+ * (save_for_backward) = activated gates.  y [N][2H], c [N][2H].  Final hidden states are scattered straight into the
  * utterance matrix utt (B, utt_ld) in ORIGINAL batch order at column offsets utt_off_f /
  * utt_off_r (src/models.py:203: [h1_fwd | h2_fwd | h1_bwd | h2_bwd]). */
 int mmda_lstm_forward(float* gates, const float* whh_f, const float* whh_r, float* y, float* c,
@@ -99,6 +102,12 @@ int mmda_lstm_backward(float* gates, const float* whh_f, const float* whh_r, con
 long long mmda_lstm_scratch_bytes(int B, int H);
 /* out6 = {cluster size, units per CTA, batch tile, n batch tiles, smem fwd, smem bwd} */
 int mmda_lstm_plan(int B, int H, int* out6);
+/* stacked gate-interleaved copy of W_ih (both directions) + bias stack for the hoisted GEMMs:
+ * row dir*4H+u*4+g <- row g*H+u.  mode 0 fp32 (out_a), 1 tf32 hi/lo (out_a,out_b), 2 bf16 (out_a). */
+int mmda_lstm_pack_weights(const float* w_ih_f, const float* w_ih_r, const float* b_ih_f,
+                           const float* b_hh_f, const float* b_ih_r, const float* b_hh_r, int H, int I,
+                           int mode, void* out_a, float* out_b, int ld, float* bias_out,
+                           mmda_stream_t stream);
 /* diagnostic: per-step phase timestamps of CTA 0 of subsequent forward launches (NULL = off) */
 int mmda_lstm_set_debug_buffer(long long* dev_buf);
 /* diagnostic: co-resident clusters of the recurrent kernel for cluster sizes {1,2,4,8,16} */
@@ -127,7 +136,7 @@ int mmda_add2d(float* out, int ldo, const float* x, int ldx, float ax, const flo
                float ay, int rows, int cols, mmda_stream_t stream);
 /* out[c] += sum_r x[r][c] (bias gradients; out2 optional second destination) */
 int mmda_colsum(const float* x, int ld, int rows, int cols, float* out, float* out2,
-                mmda_stream_t stream);
+                int out_interleave, mmda_stream_t stream);
 /* inverted dropout, mask = f(seed, stream_id, index): nn.Dropout at src/models.py:126,152,160 */
 int mmda_dropout(const float* x, float* out, long long n, float p, unsigned long long seed,
                  unsigned stream_id, mmda_stream_t stream);

@@ -144,7 +144,7 @@ __global__ void add2d_kernel(float* __restrict__ out, int ldo, const float* x, i
 // out[c] += sum_r x[r][c]  (and out2 if given): bias gradients
 __global__ void colsum_kernel(const float* __restrict__ x, int ld, int rows, int cols,
                               float* __restrict__ out, float* __restrict__ out2,
-                              int rows_per_block) {
+                              int rows_per_block, int ilv) {
   __shared__ float red[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   const int r_beg = blockIdx.y * rows_per_block, r_end = min(rows, r_beg + rows_per_block);
@@ -156,8 +156,9 @@ __global__ void colsum_kernel(const float* __restrict__ x, int ld, int rows, int
   if (threadIdx.y == 0 && c < cols) {
     float t = 0.f;
     for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
-    atomicAdd(out + c, t);
-    if (out2) atomicAdd(out2 + c, t);
+    const int co = ilv ? (c & 3) * ilv + (c >> 2) : c;   // gate-interleaved column -> g*H+u
+    atomicAdd(out + co, t);
+    if (out2) atomicAdd(out2 + co, t);
   }
 }
 // inverted dropout; the keep mask is a pure function of (seed, stream, index) so the backward
@@ -361,7 +362,7 @@ int mmda_add2d(float* out, int ldo, const float* x, int ldx, float ax, const flo
 }
 
 int mmda_colsum(const float* x, int ld, int rows, int cols, float* out, float* out2,
-                cudaStream_t stream) {
+                int out_interleave, cudaStream_t stream) {
   if (rows <= 0 || cols <= 0) return MMDA_OK;
   const int gx = (cols + 31) / 32;
   int gy = (296 + gx - 1) / gx;
@@ -369,7 +370,7 @@ int mmda_colsum(const float* x, int ld, int rows, int cols, float* out, float* o
   if (gy < 1) gy = 1;
   int rpb = (rows + gy - 1) / gy;
   gy = (rows + rpb - 1) / rpb;
-  colsum_kernel<<<dim3(gx, gy), dim3(32, 8), 0, stream>>>(x, ld, rows, cols, out, out2, rpb);
+  colsum_kernel<<<dim3(gx, gy), dim3(32, 8), 0, stream>>>(x, ld, rows, cols, out, out2, rpb, out_interleave);
   MMDA_CHECK_LAUNCH();
   return MMDA_OK;
 }

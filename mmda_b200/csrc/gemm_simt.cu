@@ -13,7 +13,8 @@ template <int BM, int BN, int BK, int TM, int TN, bool TA, bool TB>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 sgemm_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C,
              const float* __restrict__ bias, const float* __restrict__ bias2, int M, int N, int K,
-             int lda, int ldb, int ldc, float alpha, float beta, int act, int k_per_split) {
+             int lda, int ldb, int ldc, float alpha, float beta, int act, int k_per_split,
+             int c_ilv) {
   constexpr int NT = (BM / TM) * (BN / TN);
   constexpr int PAD = 4;
   constexpr int LA = (BM * BK) / NT, LB = (BN * BK) / NT;
@@ -111,7 +112,9 @@ sgemm_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __
       const int gn = n0 + tx * TN + j;
       if (gn >= N) continue;
       float v = alpha * acc[i][j];
-      float* cp = C + (size_t)gm * ldc + gn;
+      // c_ilv = H: logical row u*4+g of C is stored at row g*H+u (gate-interleaved dG operands)
+      const int gm_out = c_ilv ? (gm & 3) * c_ilv + (gm >> 2) : gm;
+      float* cp = C + (size_t)gm_out * ldc + gn;
       if (split) {
         if (blockIdx.z == 0) {
           if (bias != nullptr) v += bias[gn];
@@ -131,14 +134,16 @@ sgemm_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __
 template <int BM, int BN, int BK, int TM, int TN>
 static int launch_sgemm(bool ta, bool tb, const float* A, const float* B, float* C,
                         const float* bias, const float* bias2, int M, int N, int K, int lda, int ldb,
-                        int ldc, float alpha, float beta, int act, int split, cudaStream_t st) {
+                        int ldc, float alpha, float beta, int act, int split, int c_ilv,
+                        cudaStream_t st) {
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, split);
   dim3 block((BM / TM) * (BN / TN));
   int kps = (K + split - 1) / split;
   kps = (kps + BK - 1) / BK * BK;
 #define MMDA_SGEMM_GO(TA_, TB_)                                                             \
   sgemm_kernel<BM, BN, BK, TM, TN, TA_, TB_><<<grid, block, 0, st>>>(A, B, C, bias, bias2, M, N, K, \
-                                                                     lda, ldb, ldc, alpha, beta, act, kps)
+                                                                     lda, ldb, ldc, alpha, beta, act, kps, \
+                                                                     c_ilv)
   if (ta && tb) MMDA_SGEMM_GO(true, true);
   else if (ta) MMDA_SGEMM_GO(true, false);
   else if (tb) MMDA_SGEMM_GO(false, true);
@@ -158,7 +163,7 @@ __global__ void zero2d_kernel(float* __restrict__ c, int ldc, int rows, int cols
 extern "C" int mmda_sgemm(int transA, int transB, int M, int N, int K, float alpha,
                           const float* A, int lda, const float* B, int ldb, float beta, float* C,
                           int ldc, const float* bias, const float* bias2, int act, int split_k,
-                          cudaStream_t stream) {
+                          int c_row_interleave, cudaStream_t stream) {
   if (M <= 0 || N <= 0) return MMDA_OK;
   MMDA_REQUIRE(K >= 0 && A && B && C, "sgemm: bad arguments M=%d N=%d K=%d", M, N, K);
   MMDA_REQUIRE(split_k >= 0 && split_k <= 64, "sgemm: split_k=%d out of range", split_k);
@@ -187,10 +192,10 @@ extern "C" int mmda_sgemm(int transA, int transB, int M, int N, int K, float alp
   }
   if (cfg == 2)
     return launch_sgemm<128, 128, 16, 8, 8>(transA, transB, A, B, C, bias, bias2, M, N, K, lda, ldb, ldc,
-                                            alpha, beta, act, split_k, stream);
+                                            alpha, beta, act, split_k, c_row_interleave, stream);
   if (cfg == 1)
     return launch_sgemm<64, 64, 16, 4, 4>(transA, transB, A, B, C, bias, bias2, M, N, K, lda, ldb, ldc,
-                                          alpha, beta, act, split_k, stream);
+                                          alpha, beta, act, split_k, c_row_interleave, stream);
   return launch_sgemm<32, 32, 32, 4, 4>(transA, transB, A, B, C, bias, bias2, M, N, K, lda, ldb, ldc,
-                                        alpha, beta, act, split_k, stream);
+                                        alpha, beta, act, split_k, c_row_interleave, stream);
 }

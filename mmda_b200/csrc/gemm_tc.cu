@@ -106,6 +106,7 @@ struct TcArgs {
   float alpha;
   int mode;             // 0 store, 1 C += , 2 atomic add (split-K)
   int kb_per_split;     // K blocks per grid.z slice
+  int c_ilv;            // H: logical C row u*4+g is stored at row g*H+u; 0: identity
 };
 
 template <int KIND>
@@ -276,7 +277,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
       }
       const int nb = n0 + cc * 32;
       if (row < p.M && nb < p.N) {
-        float* crow = p.C + (size_t)row * p.ldc + nb;
+        const int row_out = p.c_ilv ? (row & 3) * p.c_ilv + (row >> 2) : row;
+        float* crow = p.C + (size_t)row_out * p.ldc + nb;
         const bool add_bias = (blockIdx.z == 0);
         if (vec_ok && nb + 32 <= p.N && p.mode != 2) {
 #pragma unroll
@@ -413,7 +415,7 @@ int mmda_cast_bf16(const float* x, int ldx, int rows, int cols, void* out, int l
 int mmda_gemm_tc(int kind, int a_mn, int b_mn, int M, int N, int K, const void* A_hi,
                  const void* A_lo, int lda, const void* B_hi, const void* B_lo, int ldb, float alpha,
                  float* C, int ldc, const float* bias, const float* bias2, int mode, int split_k,
-                 cudaStream_t stream) {
+                 int c_row_interleave, cudaStream_t stream) {
   if (M <= 0 || N <= 0) return MMDA_OK;
   MMDA_REQUIRE(kind == 0 || kind == 1, "gemm_tc: kind=%d", kind);
   MMDA_REQUIRE(K > 0 && A_hi && B_hi && C, "gemm_tc: bad arguments");
@@ -454,6 +456,7 @@ int mmda_gemm_tc(int kind, int a_mn, int b_mn, int M, int N, int K, const void* 
   a.a_mn = a_mn; a.b_mn = b_mn; a.alpha = alpha;
   a.mode = split_k > 1 ? 2 : mode;
   a.kb_per_split = (kb_total + split_k - 1) / split_k;
+  a.c_ilv = c_row_interleave;
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, split_k);
   if (kind == 0) {
     constexpr int smem = 3 * 4 * TILE_BYTES + 1024 + 256;

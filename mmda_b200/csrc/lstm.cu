@@ -7,7 +7,10 @@
 //
 // Layout.  Tokens live in torch's PackedSequence order (time-major inside the length-sorted
 // batch): packed row of (t, sorted position j) = offsets[t] + j.  Per layer:
-//   gates [N][2][4H]  in: x-projection + b_ih + b_hh;  out (training): sigma/tanh'ed gates;
+//   gates [N][2][H][4] in: x-projection + b_ih + b_hh, the i,f,g,o values of one unit adjacent
+//                     (one float4 per (token, direction, unit); the hoisted GEMMs use weight
+//                     rows permuted to match, see mmda_lstm_pack_weights);
+//                     out (training): sigma/tanh'ed gates;
 //                     after the backward kernel: d(pre-activation gates), the GEMM operand for
 //                     dW_ih / dW_hh / dX
 //   y     [N][2][H]   hidden states (fwd | bwd), c [N][2][H] cell states
@@ -21,6 +24,7 @@
 // per step.  The backward kernel keeps the same slice, produces partial dh_{t-1} over all H
 // columns, exchanges the partials through an L2-resident scratch and reduces its own columns.
 #include "common.cuh"
+#include <cuda_bf16.h>
 
 struct LstmArgs {
   float* gates;           // [N][8H]
@@ -114,7 +118,7 @@ __global__ void __launch_bounds__(BT == 40 ? 800 : 640, 1) lstm_fwd_kernel(const
   const int len0 = lens_s[bl0], len1 = lens_s[bl0 + 1], len_bg = lens_s[bg * 8];
   const int orig0 = orig_s[bl0], orig1 = orig_s[bl0 + 1];
   const int H2 = 2 * H, H8 = 8 * H;
-  const int gcol = dir * 4 * H + u_glob;   // + g*H
+  const int gcol = dir * 4 * H + u_glob * 4;   // float4 (i,f,g,o) of this unit
   const int ycol = dir * H + u_glob;
   const int utt_off = dir == 0 ? p.utt_off0 : p.utt_off1;
   const int K4 = Kpad >> 2;
@@ -137,12 +141,12 @@ __global__ void __launch_bounds__(BT == 40 ? 800 : 640, 1) lstm_fwd_kernel(const
     const size_t row0 = (size_t)(off_t + b_base + bl0), row1 = row0 + 1;
     float x0[4] = {0.f, 0.f, 0.f, 0.f}, x1[4] = {0.f, 0.f, 0.f, 0.f};
     if (a0) {
-#pragma unroll
-      for (int g = 0; g < 4; ++g) x0[g] = p.gates[row0 * H8 + gcol + g * H];
+      const float4 v = *reinterpret_cast<const float4*>(p.gates + row0 * H8 + gcol);
+      x0[0] = v.x; x0[1] = v.y; x0[2] = v.z; x0[3] = v.w;
     }
     if (a1) {
-#pragma unroll
-      for (int g = 0; g < 4; ++g) x1[g] = p.gates[row1 * H8 + gcol + g * H];
+      const float4 v = *reinterpret_cast<const float4*>(p.gates + row1 * H8 + gcol);
+      x1[0] = v.x; x1[1] = v.y; x1[2] = v.z; x1[3] = v.w;
     }
 
     float acc[32];
@@ -207,8 +211,7 @@ __global__ void __launch_bounds__(BT == 40 ? 800 : 640, 1) lstm_fwd_kernel(const
     // global stores drain while the barrier completes
     if (a0) {
       if (p.save) {
-        float* gp = p.gates + row0 * H8 + gcol;
-        gp[0] = s0[0]; gp[H] = s0[1]; gp[2 * H] = s0[2]; gp[3 * H] = s0[3];
+        *reinterpret_cast<float4*>(p.gates + row0 * H8 + gcol) = make_float4(s0[0], s0[1], s0[2], s0[3]);
         p.c[row0 * H2 + ycol] = s0[4];
       }
       p.y[row0 * H2 + ycol] = hn0;
@@ -217,8 +220,7 @@ __global__ void __launch_bounds__(BT == 40 ? 800 : 640, 1) lstm_fwd_kernel(const
     }
     if (a1) {
       if (p.save) {
-        float* gp = p.gates + row1 * H8 + gcol;
-        gp[0] = s1[0]; gp[H] = s1[1]; gp[2 * H] = s1[2]; gp[3 * H] = s1[3];
+        *reinterpret_cast<float4*>(p.gates + row1 * H8 + gcol) = make_float4(s1[0], s1[1], s1[2], s1[3]);
         p.c[row1 * H2 + ycol] = s1[4];
       }
       p.y[row1 * H2 + ycol] = hn1;
@@ -297,16 +299,19 @@ __global__ void __launch_bounds__(BT == 40 ? 800 : 640, 1) lstm_bwd_kernel(const
   const int orig0 = orig_s[ebl0], orig1 = orig_s[ebl0 + 1];
   const int len_mbg = mv_warp ? lens_s[mbg * 8] : 0;
   const int H2 = 2 * H, H8 = 8 * H;
-  const int gcol = dir * 4 * H + u_glob;
+  const int gcol = dir * 4 * H + u_glob * 4;
   const int ycol = dir * H + u_glob;
   const int utt_off = dir == 0 ? p.utt_off0 : p.utt_off1;
   const int cl_id = blockIdx.y * p.n_tiles + tile;
   const size_t slab = (size_t)BT * Kpad;   // one CTA's partial block
   float dc0 = 0.f, dc1 = 0.f;
 
+  const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0;
+#define LSTM_TS(i) if (dbg_on) p.dbg[s * 8 + (i)] = clock64();
   for (int s = 0; s < Lmax; ++s) {
     const int t = dir == 0 ? Lmax - 1 - s : s;
     const int par = s & 1;
+    LSTM_TS(0)
     float* scr = p.scratch + ((size_t)(par * 2 * p.n_tiles + cl_id) * C) * slab;
 
     // ---- prefetch everything the cell update needs (latency hidden behind the matvec) ----
@@ -318,8 +323,10 @@ __global__ void __launch_bounds__(BT == 40 ? 800 : 640, 1) lstm_bwd_kernel(const
     float g0[4], g1[4], ct0 = 0.f, ct1 = 0.f, cp0 = 0.f, cp1 = 0.f, dh0 = 0.f, dh1 = 0.f;
     bool rec0 = false, rec1 = false;
     if (a0) {
-#pragma unroll
-      for (int g = 0; g < 4; ++g) g0[g] = p.gates[row0 * H8 + gcol + g * H];
+      {
+        const float4 v = *reinterpret_cast<const float4*>(p.gates + row0 * H8 + gcol);
+        g0[0] = v.x; g0[1] = v.y; g0[2] = v.z; g0[3] = v.w;
+      }
       ct0 = p.c[row0 * H2 + ycol];
       const bool hp = dir == 0 ? (t >= 1) : (t + 1 < len0);
       if (hp) cp0 = p.c[(size_t)(__ldg(p.offsets + tp) + b_base + ebl0) * H2 + ycol];
@@ -329,8 +336,10 @@ __global__ void __launch_bounds__(BT == 40 ? 800 : 640, 1) lstm_bwd_kernel(const
       rec0 = dir == 0 ? (t + 1 < len0) : (t >= 1);
     }
     if (a1) {
-#pragma unroll
-      for (int g = 0; g < 4; ++g) g1[g] = p.gates[row1 * H8 + gcol + g * H];
+      {
+        const float4 v = *reinterpret_cast<const float4*>(p.gates + row1 * H8 + gcol);
+        g1[0] = v.x; g1[1] = v.y; g1[2] = v.z; g1[3] = v.w;
+      }
       ct1 = p.c[row1 * H2 + ycol];
       const bool hp = dir == 0 ? (t >= 1) : (t + 1 < len1);
       if (hp) cp1 = p.c[(size_t)(__ldg(p.offsets + tp) + b_base + ebl0 + 1) * H2 + ycol];
@@ -342,6 +351,7 @@ __global__ void __launch_bounds__(BT == 40 ? 800 : 640, 1) lstm_bwd_kernel(const
 
     // ---- partial dh over all H columns from this CTA's gate rows of the successor step ----
     // a batch group is needed iff one of its rows is active now AND had a successor step
+    LSTM_TS(1)
     const bool need = mv_warp && s > 0 && (dir == 0 ? (t + 1 < len_mbg) : (t < len_mbg));
     if (need) {
       float acc[32];
@@ -375,7 +385,9 @@ __global__ void __launch_bounds__(BT == 40 ? 800 : 640, 1) lstm_bwd_kernel(const
         }
       }
     }
+    LSTM_TS(2)
     cluster_sync_all();  // partials of every CTA visible (release/acquire at cluster scope)
+    LSTM_TS(3)
 
     // ---- reduce my columns, finish the cell backward, publish d(gates) ----
     if (a0) {
@@ -391,8 +403,7 @@ __global__ void __launch_bounds__(BT == 40 ? 800 : 640, 1) lstm_bwd_kernel(const
       const float dfg = dc * cp0 * fg * (1.f - fg);
       const float dgg = dc * ig * (1.f - gg * gg);
       dc0 = dc * fg;
-      float* gp = p.gates + row0 * H8 + gcol;
-      gp[0] = dig; gp[H] = dfg; gp[2 * H] = dgg; gp[3 * H] = dog;
+      *reinterpret_cast<float4*>(p.gates + row0 * H8 + gcol) = make_float4(dig, dfg, dgg, dog);
       float* sp = dG_s + (u * 4) * BTP + ebl0;
       sp[0] = dig; sp[BTP] = dfg; sp[2 * BTP] = dgg; sp[3 * BTP] = dog;
     }
@@ -409,13 +420,15 @@ __global__ void __launch_bounds__(BT == 40 ? 800 : 640, 1) lstm_bwd_kernel(const
       const float dfg = dc * cp1 * fg * (1.f - fg);
       const float dgg = dc * ig * (1.f - gg * gg);
       dc1 = dc * fg;
-      float* gp = p.gates + row1 * H8 + gcol;
-      gp[0] = dig; gp[H] = dfg; gp[2 * H] = dgg; gp[3 * H] = dog;
+      *reinterpret_cast<float4*>(p.gates + row1 * H8 + gcol) = make_float4(dig, dfg, dgg, dog);
       float* sp = dG_s + (u * 4) * BTP + ebl0 + 1;
       sp[0] = dig; sp[BTP] = dfg; sp[2 * BTP] = dgg; sp[3 * BTP] = dog;
     }
+    LSTM_TS(4)
     __syncthreads();  // dG_s complete before the next step's matvec
+    LSTM_TS(5)
   }
+#undef LSTM_TS
   cluster_sync_all();
 }
 
@@ -434,6 +447,41 @@ __global__ void lstm_shift_kernel(const float* __restrict__ y, float* __restrict
   for (int c = threadIdx.x; c < H2; c += blockDim.x) {
     const int src = c < H ? prev_f : prev_b;
     hp[(size_t)row * H2 + c] = src >= 0 ? y[(size_t)src * H2 + c] : 0.f;
+  }
+}
+
+// Stacked, gate-interleaved copy of the two directions' W_ih for the hoisted GEMMs:
+//   row (dir*4H + u*4 + g) of the copy = row (g*H + u) of weight_ih_l0{,_reverse}
+// so the GEMM writes / reads the [N][2][H][4] gate layout directly.  mode 0: fp32 copy (out_a);
+// mode 1: tf32 hi/lo split (out_a, out_b); mode 2: bf16 (out_a).  Also writes the matching bias
+// stack b_ih + b_hh (bias_out, nullable).
+__global__ void lstm_pack_weights_kernel(const float* __restrict__ wf, const float* __restrict__ wr,
+                                         const float* __restrict__ bif, const float* __restrict__ bhf,
+                                         const float* __restrict__ bir, const float* __restrict__ bhr,
+                                         int H, int I, int mode, void* __restrict__ out_a,
+                                         float* __restrict__ out_b, int ld, float* __restrict__ bias_out) {
+  const int H4 = 4 * H;
+  const size_t n = (size_t)2 * H4 * I;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % I);
+    const int r = (int)(i / I);              // source row in [0, 8H): dir*4H + g*H + u
+    const int dir = r / H4, rr = r % H4, g = rr / H, u = rr % H;
+    const float v = (dir ? wr : wf)[(size_t)rr * I + c];
+    const size_t o = (size_t)(dir * H4 + u * 4 + g) * ld + c;
+    if (mode == 0) {
+      reinterpret_cast<float*>(out_a)[o] = v;
+    } else if (mode == 1) {
+      uint32_t hb;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+      const float h = __uint_as_float(hb);
+      reinterpret_cast<float*>(out_a)[o] = h;
+      out_b[o] = v - h;
+    } else {
+      reinterpret_cast<__nv_bfloat16*>(out_a)[o] = __float2bfloat16(v);
+    }
+    if (bias_out != nullptr && c == 0)
+      bias_out[dir * H4 + u * 4 + g] = (dir ? bir : bif)[rr] + (dir ? bhr : bhf)[rr];
   }
 }
 
@@ -626,12 +674,27 @@ int mmda_lstm_backward(float* gates, const float* whh_f, const float* whh_r, con
   a.gates = gates; a.whh[0] = whh_f; a.whh[1] = whh_r; a.c = const_cast<float*>(c);
   a.dy = dy; a.dutt = dutt; a.utt_ld = utt_ld; a.utt_off0 = utt_off_f; a.utt_off1 = utt_off_r;
   a.lens = lens_sorted; a.sorted_idx = sorted_idx; a.offsets = offsets; a.scratch = scratch;
+  a.dbg = g_lstm_dbg;
   a.B = B; a.H = H; a.Hs = pl.Hs; a.Kpad = pl.Kpad; a.C = pl.C; a.n_tiles = pl.n_tiles;
   if (pl.BT == 40 && pl.KS == 16)
     return launch_cluster(lstm_bwd_kernel<40, 16>, a, pl, pl.threads_bwd, pl.smem_bwd, stream);
   if (pl.BT == 32 && pl.KS == 16)
     return launch_cluster(lstm_bwd_kernel<32, 16>, a, pl, pl.threads_bwd, pl.smem_bwd, stream);
   return launch_cluster(lstm_bwd_kernel<8, 4>, a, pl, pl.threads_bwd, pl.smem_bwd, stream);
+}
+
+int mmda_lstm_pack_weights(const float* w_ih_f, const float* w_ih_r, const float* b_ih_f,
+                           const float* b_hh_f, const float* b_ih_r, const float* b_hh_r, int H, int I,
+                           int mode, void* out_a, float* out_b, int ld, float* bias_out,
+                           cudaStream_t stream) {
+  MMDA_REQUIRE(mode >= 0 && mode <= 2 && H > 0 && I > 0 && ld >= I, "lstm_pack_weights: bad arguments");
+  MMDA_REQUIRE(mode != 1 || out_b != nullptr, "lstm_pack_weights: tf32 split needs out_b");
+  size_t n = (size_t)8 * H * I, g = (n + 255) / 256;
+  if (g > 1184) g = 1184;
+  lstm_pack_weights_kernel<<<(int)g, 256, 0, stream>>>(w_ih_f, w_ih_r, b_ih_f, b_hh_f, b_ih_r, b_hh_r,
+                                                       H, I, mode, out_a, out_b, ld, bias_out);
+  MMDA_CHECK_LAUNCH();
+  return MMDA_OK;
 }
 
 int mmda_lstm_shift_h(const float* y, float* hprev, const int* row_t, const int* row_j,

@@ -52,7 +52,7 @@ class Kernels:
 
     # C = act(alpha * op(A) op(B) + beta*C + bias + bias2); A,B,C are 2-D views with unit inner stride
     def gemm(self, A, B, C, ta=False, tb=False, alpha=1.0, beta=0.0, bias=None, bias2=None,
-             act=ACT_NONE, split_k=0):
+             act=ACT_NONE, split_k=0, c_ilv=0):
         M, N = C.shape
         K = A.shape[0] if ta else A.shape[1]
         assert A.stride(1) == 1 and B.stride(1) == 1 and C.stride(1) == 1
@@ -60,14 +60,15 @@ class Kernels:
         assert (B.shape[0] if tb else B.shape[1]) == N and (B.shape[1] if tb else B.shape[0]) == K, \
             (A.shape, B.shape, C.shape, ta, tb)
         self._c("mmda_sgemm", int(ta), int(tb), M, N, K, alpha, _ptr(A), A.stride(0), _ptr(B),
-                B.stride(0), beta, _ptr(C), C.stride(0), _ptr(bias), _ptr(bias2), act, split_k)
+                B.stride(0), beta, _ptr(C), C.stride(0), _ptr(bias), _ptr(bias2), act, split_k, c_ilv)
 
-    def gemm_tc(self, kind, a_mn, b_mn, M, N, K, A, B, C, alpha=1.0, bias=None, mode=0, split_k=1):
+    def gemm_tc(self, kind, a_mn, b_mn, M, N, K, A, B, C, alpha=1.0, bias=None, mode=0, split_k=1,
+                c_ilv=0):
         """Tensor-core GEMM.  A, B = (hi, lo_or_None) 2-D operand views (unit inner stride)."""
         (Ah, Al), (Bh, Bl) = A, B
         self._c("mmda_gemm_tc", kind, int(a_mn), int(b_mn), M, N, K, _ptr(Ah), _ptr(Al), Ah.stride(0),
                 _ptr(Bh), _ptr(Bl), Bh.stride(0), alpha, _ptr(C), C.stride(0), _ptr(bias), None, mode,
-                split_k)
+                split_k, c_ilv)
 
     def linear(self, x, w, b, out, act=ACT_NONE, bias2=None):
         self.gemm(x, w, out, tb=True, bias=b, bias2=bias2, act=act)
@@ -81,8 +82,9 @@ class Kernels:
         if dx is not None:
             self.gemm(dy, w, dx, beta=dx_beta, split_k=1 if dx_beta not in (0.0, 1.0) else 0)
 
-    def colsum(self, x, out, out2=None):
-        self._c("mmda_colsum", _ptr(x), x.stride(0), x.shape[0], x.shape[1], _ptr(out), _ptr(out2))
+    def colsum(self, x, out, out2=None, ilv=0):
+        self._c("mmda_colsum", _ptr(x), x.stride(0), x.shape[0], x.shape[1], _ptr(out), _ptr(out2),
+                ilv)
 
     def layernorm(self, x, res, g, b, y, mean, rstd):
         self._c("mmda_layernorm_forward", _ptr(x), x.stride(0), _ptr(res),
@@ -286,6 +288,22 @@ class MisaEngine:
         ld = (cols + 7) // 8 * 8
         return self.buf(name + "_bf", rows, ld, dtype=torch.bfloat16)[:, :cols], None
 
+    def _pack_weights(self, r, P, H, I, kind, want_bias=True):
+        """Stacked gate-interleaved copy of layer r's W_ih (both directions) for GEMM kind
+        `kind` (-1: plain fp32 for the SIMT path, 0: tf32 hi/lo, 1: bf16) + the bias stack."""
+        mode = {-1: 0, 0: 1, 1: 2}[kind]
+        if kind == -1:
+            W = (self.buf(f"Wst_{r}", 8 * H, I), None)
+        else:
+            W = self._prep_buf(f"tcW_{r}", 8 * H, I, kind)
+        bst = self.buf(f"bst_{r}", 8 * H) if want_bias else None
+        self.k._c("mmda_lstm_pack_weights", _ptr(P[f"{r}.weight_ih_l0"]),
+                  _ptr(P[f"{r}.weight_ih_l0_reverse"]), _ptr(P[f"{r}.bias_ih_l0"]),
+                  _ptr(P[f"{r}.bias_hh_l0"]), _ptr(P[f"{r}.bias_ih_l0_reverse"]),
+                  _ptr(P[f"{r}.bias_hh_l0_reverse"]), H, I, mode, _ptr(W[0]), _ptr(W[1]),
+                  W[0].stride(0), _ptr(bst))
+        return W, bst
+
     @staticmethod
     def _cols(op, lo, hi):
         return (op[0][:, lo:hi], None if op[1] is None else op[1][:, lo:hi])
@@ -310,21 +328,15 @@ class MisaEngine:
             if r == r2:
                 k.layernorm(Y1, None, P[f"{ln}.weight"], P[f"{ln}.bias"], Y1n, mu, rs)
             I = Xin.shape[1]
+            # both directions in ONE GEMM against the stacked, gate-interleaved weight copy:
+            # G[N][2][H][4] = Xin * Wst^T + (b_ih + b_hh)
             if self._tc_ok(H, I):
-                # both directions in one tcgen05 GEMM: G = Xin * [W_ih ; W_ih_reverse]^T + biases
-                Wst = self._prep_buf(f"tcW_{r}", 8 * H, I)
-                bst = self.buf(f"tcb_{r}", 1, 8 * H)
-                for di, suf in enumerate(("", "_reverse")):
-                    self._prep(None, P[f"{r}.weight_ih_l0{suf}"], out=Wst, row0=di * 4 * H)
-                    k.add(bst[:, di * 4 * H:(di + 1) * 4 * H], P[f"{r}.bias_ih_l0{suf}"].view(1, -1),
-                          P[f"{r}.bias_hh_l0{suf}"].view(1, -1))
+                Wst, bst = self._pack_weights(r, P, H, I, self.tc_kind)
                 Xp = self._prep(f"tcX_{r}", Xin)
                 k.gemm_tc(self.tc_kind, 0, 0, N, 8 * H, I, Xp, Wst, G, bias=bst)
             else:
-                for di, suf in enumerate(("", "_reverse")):
-                    self.big_gemm(Xin, P[f"{r}.weight_ih_l0{suf}"], G[:, di * 4 * H:(di + 1) * 4 * H],
-                                  tb=True, bias=P[f"{r}.bias_ih_l0{suf}"],
-                                  bias2=P[f"{r}.bias_hh_l0{suf}"])
+                Wst, bst = self._pack_weights(r, P, H, I, -1)
+                self.big_gemm(Xin, Wst[0], G, tb=True, bias=bst)
             Y, C = (Y1, C1) if r == r1 else (Y2, C2)
             o_f, o_r = (0, 2 * H) if r == r1 else (H, 3 * H)
             k._c("mmda_lstm_forward", _ptr(G), _ptr(P[f"{r}.weight_hh_l0"]),
@@ -690,9 +702,9 @@ class MisaEngine:
                     Wst = self._prep_buf(f"tcW_{r}", 8 * H, I, 0)
                 else:
                     Xp = self._prep(f"tcX_{r}", Xin, kind=0)
-                    Wst = self._prep_buf(f"tcW_{r}", 8 * H, I, 0)
-                    for di, suf in enumerate(("", "_reverse")):
-                        self._prep(None, P[f"{r}.weight_ih_l0{suf}"], out=Wst, row0=di * 4 * H, kind=0)
+                    Wst, _ = self._pack_weights(r, P, H, I, 0, want_bias=False)
+            else:
+                Wst = (self.buf(f"Wst_{r}", 8 * H, I), None)      # written by the forward
 
             def wgrad(r=r, Gt=Gt, Y=Y, Xin=Xin, tc=tc, I=I):
                 HP = self.buf(f"HP_{r}", N, 2 * H)
@@ -700,20 +712,21 @@ class MisaEngine:
                      _ptr(pk["lens"]), _ptr(pk["off"]), N, H)
                 if tc:
                     HPp = self._prep(f"tcHP_{r}", HP, kind=0)
+                # dG columns are gate-interleaved (u*4+g): c_ilv=H stores row u*4+g at g*H+u
                 for di, suf in enumerate(("", "_reverse")):
                     dG = Gt[:, di * 4 * H:(di + 1) * 4 * H]
                     if tc:   # contract over tokens: both operands MN-major, auto split-K
                         dGd = self._cols(dGp, di * 4 * H, (di + 1) * 4 * H)
                         k.gemm_tc(0, 1, 1, 4 * H, I, N, dGd, Xp, G[f"{r}.weight_ih_l0{suf}"], mode=1,
-                                  split_k=0)
+                                  split_k=0, c_ilv=H)
                         k.gemm_tc(0, 1, 1, 4 * H, H, N, dGd, self._cols(HPp, di * H, (di + 1) * H),
-                                  G[f"{r}.weight_hh_l0{suf}"], mode=1, split_k=0)
+                                  G[f"{r}.weight_hh_l0{suf}"], mode=1, split_k=0, c_ilv=H)
                     else:
                         self.big_gemm(dG, Xin, G[f"{r}.weight_ih_l0{suf}"], ta=True, beta=1.0,
-                                      split_k=0)
+                                      split_k=0, c_ilv=H)
                         self.big_gemm(dG, HP[:, di * H:(di + 1) * H], G[f"{r}.weight_hh_l0{suf}"],
-                                      ta=True, beta=1.0, split_k=0)
-                    k.colsum(dG, G[f"{r}.bias_ih_l0{suf}"], G[f"{r}.bias_hh_l0{suf}"])
+                                      ta=True, beta=1.0, split_k=0, c_ilv=H)
+                    k.colsum(dG, G[f"{r}.bias_ih_l0{suf}"], G[f"{r}.bias_hh_l0{suf}"], ilv=H)
 
             if use_side:
                 ev = torch.cuda.Event()
@@ -730,9 +743,7 @@ class MisaEngine:
                 if tc:   # dX = dG [N x 8H] * [W_ih ; W_ih_reverse] (stored [8H][I]: MN-major B)
                     k.gemm_tc(0, 0, 1, N, I, 8 * H, dGp, Wst, dX)
                 else:
-                    for di, suf in enumerate(("", "_reverse")):
-                        self.big_gemm(Gt[:, di * 4 * H:(di + 1) * 4 * H],
-                                      P[f"{r}.weight_ih_l0{suf}"], dX, beta=0.0 if di == 0 else 1.0)
+                    self.big_gemm(Gt, Wst[0], dX)
                 if r == r1:
                     V = P["embed.weight"].shape[0]
                     k._c("mmda_embedding_backward", _ptr(G["embed.weight"]),

@@ -411,7 +411,7 @@ def test_gemm_tc_tf32x3_and_bf16(dev):
                 Ah, Al = split(A); Bh, Bl = split(B)
                 out = torch.full((M, N), 3.0, device=dev)
                 k._c("mmda_gemm_tc", 0, a_mn, b_mn, M, N, K, _ptr(Ah), _ptr(Al), A.stride(0), _ptr(Bh),
-                     _ptr(Bl), B.stride(0), 1.0, _ptr(out), N, _ptr(bias), None, 0, 1)
+                     _ptr(Bl), B.stride(0), 1.0, _ptr(out), N, _ptr(bias), None, 0, 1, 0)
                 # one accumulation chain over K=12800 drifts to ~1e-5 (tensor-core fp32 adds truncate);
                 # the library's own callers use the auto split-K for such shapes (checked below)
                 C.add(f"tf32x3 {M}x{N}x{K} a_mn={a_mn} b_mn={b_mn}", out, ref + bias.double(),
@@ -420,7 +420,7 @@ def test_gemm_tc_tf32x3_and_bf16(dev):
                     acc = torch.randn(M, N, generator=g).to(dev)
                     ref2 = acc.double() + 0.5 * ref
                     k._c("mmda_gemm_tc", 0, a_mn, b_mn, M, N, K, _ptr(Ah), _ptr(Al), A.stride(0), _ptr(Bh),
-                         _ptr(Bl), B.stride(0), 0.5, _ptr(acc), N, None, None, 1, 0)
+                         _ptr(Bl), B.stride(0), 0.5, _ptr(acc), N, None, None, 1, 0, 0)
                     C.add(f"tf32x3 splitK {M}x{N}x{K} a_mn={a_mn} b_mn={b_mn}", acc, ref2, 1e-5)
     # bf16 (pitches padded to 8 elements)
     for (M, N, K) in [(256, 128, 64), (1000, 304, 304), (1200, 304, 4096)]:
@@ -435,7 +435,7 @@ def test_gemm_tc_tf32x3_and_bf16(dev):
                 assert torch.equal(Ab, A.bfloat16())
                 out = torch.empty(M, N, device=dev)
                 k._c("mmda_gemm_tc", 1, a_mn, b_mn, M, N, K, _ptr(Ab), None, Ab.stride(0), _ptr(Bb), None,
-                     Bb.stride(0), 1.0, _ptr(out), N, None, None, 0, 1)
+                     Bb.stride(0), 1.0, _ptr(out), N, None, None, 0, 1, 0)
                 Ad, Bd = Ab.double(), Bb.double()
                 ref = (Ad.t() if a_mn else Ad) @ (Bd if b_mn else Bd.t())
                 C.add(f"bf16 {M}x{N}x{K} a_mn={a_mn} b_mn={b_mn}", out, ref, 1e-5)

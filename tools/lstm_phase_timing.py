@@ -41,3 +41,25 @@ tot = d[1:, 0] - d[:-1, 0]
 print("text rnn2 (last text launch), clocks per step: mean total %.0f" % tot[5:].mean())
 for i, n in enumerate(names):
     print(f"  {n:24s} mean {ph[5:, i].mean():8.0f}  min {ph[5:, i].min():8.0f}  max {ph[5:, i].max():8.0f}")
+
+# ---- backward (text rnn1 = last text backward launch) ----
+from mmda_b200.trainer import FusedTrainer
+tr = FusedTrainer(m)
+lab = b.labels.to(dev)
+tr.forward_backward(*args, lab)
+dbg.zero_()
+G = tr.G
+du = eng.buf("dutt_t", 256, 1200)
+eng.k.bind_stream()
+LIB.call("mmda_lstm_set_debug_buffer", _ptr(dbg))
+eng.multi_stream = False
+eng._encode_backward("t", du, G, pk, eng.params())
+torch.cuda.synchronize()
+LIB.call("mmda_lstm_set_debug_buffer", None)
+d = dbg.cpu().view(64, 8)[:50].double()
+names = ["prefetch issue", "matvec+scratch write", "cluster sync", "reduce+gates+stores", "syncthreads"]
+ph = d[:, 1:6] - d[:, 0:5]
+tot = d[1:, 0] - d[:-1, 0]
+print("text BACKWARD (rnn1), clocks per step: mean total %.0f" % tot[5:].mean())
+for i, n in enumerate(names):
+    print(f"  {n:24s} mean {ph[5:, i].mean():8.0f}  min {ph[5:, i].min():8.0f}  max {ph[5:, i].max():8.0f}")
