@@ -255,6 +255,7 @@ __global__ void __launch_bounds__(BT == 40 ? 800 : 640, 1) lstm_bwd_kernel(const
   float* dG_s = smem + R * Kpad;    // [R][BTP]
   int* lens_s = reinterpret_cast<int*>(dG_s + R * BTP);
   int* orig_s = lens_s + BT;
+  int* offs_s = orig_s + BT;        // [Tmax+1]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int BG = BT / 8;
@@ -284,6 +285,7 @@ __global__ void __launch_bounds__(BT == 40 ? 800 : 640, 1) lstm_bwd_kernel(const
       Wb[idx] = (k < H && ul < Hs && ugl < H) ? W[(size_t)(g * H + ugl) * H + k] : 0.f;
     }
     for (int idx = tid; idx < R * BTP; idx += blockDim.x) dG_s[idx] = 0.f;
+    for (int idx = tid; idx <= p.Tmax; idx += blockDim.x) offs_s[idx] = p.offsets[idx];
     if (tid < BT) {
       const int b = b_base + tid;
       lens_s[tid] = b < p.B ? p.lens[b] : 0;
@@ -314,44 +316,8 @@ __global__ void __launch_bounds__(BT == 40 ? 800 : 640, 1) lstm_bwd_kernel(const
     LSTM_TS(0)
     float* scr = p.scratch + ((size_t)(par * 2 * p.n_tiles + cl_id) * C) * slab;
 
-    // ---- prefetch everything the cell update needs (latency hidden behind the matvec) ----
-    const bool a0 = u_ok && t < len0, a1 = u_ok && t < len1;
-    const int off_t = __ldg(p.offsets + t);
-    const size_t row0 = (size_t)(off_t + b_base + ebl0), row1 = row0 + 1;
-    // forward-order predecessor time (its c is c_{prev}); forward-order successor feeds dh_rec
-    const int tp = dir == 0 ? t - 1 : t + 1;
-    float g0[4], g1[4], ct0 = 0.f, ct1 = 0.f, cp0 = 0.f, cp1 = 0.f, dh0 = 0.f, dh1 = 0.f;
-    bool rec0 = false, rec1 = false;
-    if (a0) {
-      {
-        const float4 v = *reinterpret_cast<const float4*>(p.gates + row0 * H8 + gcol);
-        g0[0] = v.x; g0[1] = v.y; g0[2] = v.z; g0[3] = v.w;
-      }
-      ct0 = p.c[row0 * H2 + ycol];
-      const bool hp = dir == 0 ? (t >= 1) : (t + 1 < len0);
-      if (hp) cp0 = p.c[(size_t)(__ldg(p.offsets + tp) + b_base + ebl0) * H2 + ycol];
-      if (p.dy) dh0 = p.dy[row0 * H2 + ycol];
-      const bool fin = dir == 0 ? (t == len0 - 1) : (t == 0);
-      if (fin && p.dutt) dh0 += p.dutt[(size_t)orig0 * p.utt_ld + utt_off + u_glob];
-      rec0 = dir == 0 ? (t + 1 < len0) : (t >= 1);
-    }
-    if (a1) {
-      {
-        const float4 v = *reinterpret_cast<const float4*>(p.gates + row1 * H8 + gcol);
-        g1[0] = v.x; g1[1] = v.y; g1[2] = v.z; g1[3] = v.w;
-      }
-      ct1 = p.c[row1 * H2 + ycol];
-      const bool hp = dir == 0 ? (t >= 1) : (t + 1 < len1);
-      if (hp) cp1 = p.c[(size_t)(__ldg(p.offsets + tp) + b_base + ebl0 + 1) * H2 + ycol];
-      if (p.dy) dh1 = p.dy[row1 * H2 + ycol];
-      const bool fin = dir == 0 ? (t == len1 - 1) : (t == 0);
-      if (fin && p.dutt) dh1 += p.dutt[(size_t)orig1 * p.utt_ld + utt_off + u_glob];
-      rec1 = dir == 0 ? (t + 1 < len1) : (t >= 1);
-    }
-
     // ---- partial dh over all H columns from this CTA's gate rows of the successor step ----
     // a batch group is needed iff one of its rows is active now AND had a successor step
-    LSTM_TS(1)
     const bool need = mv_warp && s > 0 && (dir == 0 ? (t + 1 < len_mbg) : (t < len_mbg));
     if (need) {
       float acc[32];
@@ -376,25 +342,73 @@ __global__ void __launch_bounds__(BT == 40 ? 800 : 640, 1) lstm_bwd_kernel(const
       }
       reduce_scatter<32, KS>(acc, lane);
       if (kq_ok) {
-        // lane mq owns flat outputs [mq*NV, mq*NV+NV) of (b*4 + kk)
-        float* dst = scr + (size_t)rank * slab;
+        // lane mq owns flat outputs [mq*NV, mq*NV+NV) of (b*4 + kk): NV/4 rows x 4 consecutive k
+        float* dst = scr + (size_t)rank * slab + (size_t)(mbg * 8) * Kpad + kquad * 4;
 #pragma unroll
-        for (int j = 0; j < NV; ++j) {
-          const int o = mq * NV + j, b = o >> 2, kk = o & 3;
-          dst[(size_t)(mbg * 8 + b) * Kpad + kquad * 4 + kk] = acc[j];
+        for (int jb = 0; jb < NV / 4; ++jb) {
+          const int b = (mq * NV) / 4 + jb;
+          *reinterpret_cast<float4*>(dst + (size_t)b * Kpad) =
+              make_float4(acc[jb * 4], acc[jb * 4 + 1], acc[jb * 4 + 2], acc[jb * 4 + 3]);
         }
       }
     }
     LSTM_TS(2)
-    cluster_sync_all();  // partials of every CTA visible (release/acquire at cluster scope)
+    cluster_arrive();   // release: this CTA's partials are published
+    // ---- fetch everything the cell update needs while the cluster barrier completes ----
+    const bool a0 = u_ok && t < len0, a1 = u_ok && t < len1;
+    const int off_t = offs_s[t];
+    const size_t row0 = (size_t)(off_t + b_base + ebl0), row1 = row0 + 1;
+    // forward-order predecessor time (its c is c_{prev}); forward-order successor feeds dh_rec
+    const int tp = dir == 0 ? t - 1 : t + 1;
+    float g0[4], g1[4], ct0 = 0.f, ct1 = 0.f, cp0 = 0.f, cp1 = 0.f, dh0 = 0.f, dh1 = 0.f;
+    bool rec0 = false, rec1 = false;
+    if (a0) {
+      {
+        const float4 v = *reinterpret_cast<const float4*>(p.gates + row0 * H8 + gcol);
+        g0[0] = v.x; g0[1] = v.y; g0[2] = v.z; g0[3] = v.w;
+      }
+      ct0 = p.c[row0 * H2 + ycol];
+      const bool hp = dir == 0 ? (t >= 1) : (t + 1 < len0);
+      if (hp) cp0 = p.c[(size_t)(offs_s[tp] + b_base + ebl0) * H2 + ycol];
+      if (p.dy) dh0 = p.dy[row0 * H2 + ycol];
+      const bool fin = dir == 0 ? (t == len0 - 1) : (t == 0);
+      if (fin && p.dutt) dh0 += p.dutt[(size_t)orig0 * p.utt_ld + utt_off + u_glob];
+      rec0 = dir == 0 ? (t + 1 < len0) : (t >= 1);
+    }
+    if (a1) {
+      {
+        const float4 v = *reinterpret_cast<const float4*>(p.gates + row1 * H8 + gcol);
+        g1[0] = v.x; g1[1] = v.y; g1[2] = v.z; g1[3] = v.w;
+      }
+      ct1 = p.c[row1 * H2 + ycol];
+      const bool hp = dir == 0 ? (t >= 1) : (t + 1 < len1);
+      if (hp) cp1 = p.c[(size_t)(offs_s[tp] + b_base + ebl0 + 1) * H2 + ycol];
+      if (p.dy) dh1 = p.dy[row1 * H2 + ycol];
+      const bool fin = dir == 0 ? (t == len1 - 1) : (t == 0);
+      if (fin && p.dutt) dh1 += p.dutt[(size_t)orig1 * p.utt_ld + utt_off + u_glob];
+      rec1 = dir == 0 ? (t + 1 < len1) : (t >= 1);
+    }
+
+    LSTM_TS(1)
+    cluster_wait();     // acquire: partials of every CTA visible
     LSTM_TS(3)
+    // all 2*C partial loads in flight at once (they are L2 round trips), then summed
+    float rdh0 = 0.f, rdh1 = 0.f;
+    {
+      float v0[8], v1[8];
+      const float* src0 = scr + (size_t)ebl0 * Kpad + u_glob;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        v0[r] = (a0 && rec0 && r < C) ? ld_cg(src0 + (size_t)r * slab) : 0.f;
+        v1[r] = (a1 && rec1 && r < C) ? ld_cg(src0 + Kpad + (size_t)r * slab) : 0.f;
+      }
+#pragma unroll
+      for (int r = 0; r < 8; ++r) { rdh0 += v0[r]; rdh1 += v1[r]; }
+    }
 
     // ---- reduce my columns, finish the cell backward, publish d(gates) ----
     if (a0) {
-      if (rec0) {
-        const float* src = scr + (size_t)ebl0 * Kpad + u_glob;
-        for (int r = 0; r < C; ++r) dh0 += ld_cg(src + (size_t)r * slab);
-      }
+      dh0 += rdh0;
       const float ig = g0[0], fg = g0[1], gg = g0[2], og = g0[3];
       const float tc = fast_tanh(ct0);
       const float dog = dh0 * tc * og * (1.f - og);
@@ -408,10 +422,7 @@ __global__ void __launch_bounds__(BT == 40 ? 800 : 640, 1) lstm_bwd_kernel(const
       sp[0] = dig; sp[BTP] = dfg; sp[2 * BTP] = dgg; sp[3 * BTP] = dog;
     }
     if (a1) {
-      if (rec1) {
-        const float* src = scr + (size_t)(ebl0 + 1) * Kpad + u_glob;
-        for (int r = 0; r < C; ++r) dh1 += ld_cg(src + (size_t)r * slab);
-      }
+      dh1 += rdh1;
       const float ig = g1[0], fg = g1[1], gg = g1[2], og = g1[3];
       const float tc = fast_tanh(ct1);
       const float dog = dh1 * tc * og * (1.f - og);
@@ -536,7 +547,7 @@ static int lstm_make_plan(int B, int H, int Tmax, LstmPlan* pl) {
       const size_t misc = (size_t)(2 * BT) * 4 + 16;
       const int HR = C * Hs > Kpad ? C * Hs : Kpad;
       const size_t fwd = (size_t)4 * Kpad * Hs * 4 + (size_t)HR * BTP * 4 + misc;
-      const size_t bwd = (size_t)R * Kpad * 4 + (size_t)R * BTP * 4 + misc;
+      const size_t bwd = (size_t)R * Kpad * 4 + (size_t)R * BTP * 4 + misc + (size_t)(Tmax + 1) * 4;
       if (fwd > (size_t)g_max_smem || bwd > (size_t)g_max_smem) continue;
       const int UG = (Hs + 7) / 8, BG = BT / 8, K4 = Kpad / 4;
       const int KG = (K4 + KS - 1) / KS;

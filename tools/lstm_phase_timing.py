@@ -57,9 +57,10 @@ eng._encode_backward("t", du, G, pk, eng.params())
 torch.cuda.synchronize()
 LIB.call("mmda_lstm_set_debug_buffer", None)
 d = dbg.cpu().view(64, 8)[:50].double()
-names = ["prefetch issue", "matvec+scratch write", "cluster sync", "reduce+gates+stores", "syncthreads"]
-ph = d[:, 1:6] - d[:, 0:5]
 tot = d[1:, 0] - d[:-1, 0]
 print("text BACKWARD (rnn1), clocks per step: mean total %.0f" % tot[5:].mean())
-for i, n in enumerate(names):
-    print(f"  {n:24s} mean {ph[5:, i].mean():8.0f}  min {ph[5:, i].min():8.0f}  max {ph[5:, i].max():8.0f}")
+phases = {"matvec+scratch write": d[:, 2] - d[:, 0], "arrive + fetch issue": d[:, 1] - d[:, 2],
+          "cluster wait": d[:, 3] - d[:, 1], "reduce+gates+stores": d[:, 4] - d[:, 3],
+          "syncthreads": d[:, 5] - d[:, 4]}
+for n, v in phases.items():
+    print(f"  {n:24s} mean {v[5:].mean():8.0f}  min {v[5:].min():8.0f}  max {v[5:].max():8.0f}")
