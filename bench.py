@@ -256,14 +256,29 @@ def run_ours(args):
         alg_bytes = 2 * 10 * H * 4 * ntok          # both directions, 10H fp32 words per token
         flops = 2 * 2 * 4 * H * H * ntok           # recurrent MACs*2, both directions
         dur = kdur[kname] * 1e-3
-        sm_hz = (clk or {}).get("sm_mhz") or 1965.0
-        fma_peak = 148 * 128 * 2 * sm_hz * 1e6 / 1e12
+        sm_hz = ((clk or {}).get("sm_mhz") or 1965.0) * 1e6
+        fma_peak = 148 * 128 * 2 * sm_hz / 1e12
+        # operand bytes the mat-vec delivers from shared memory into registers per launch:
+        # per warp-iteration one float4 of W_hh + two float4 of h per lane (1536 B), x (K/4)
+        # iterations x warps x CTAs x steps (csrc/lstm.cu plan for H=300, B=256: 25 warps,
+        # 75 iterations, 112 CTAs, seq steps)
+        lds_bytes = 1536.0 * 75 * 25 * 112 * SEQ
+        smem_peak = 148 * 128 * sm_hz / 1e12       # TB/s
+        # DRAM traffic per launch from the committed ncu --set full capture of this kernel
+        traffic = {"mmda_lstm_forward": 127.62e6 + 148.93e6, "mmda_lstm_backward": 160.05e6 + 90.63e6}[kname]
         roof = {"kernel": kname + " (text encoder, H=300, both directions)", "bound": "hbm",
                 "achieved": alg_bytes / dur / 1e9, "peak": peak, "unit": "GB/s",
-                "frac": alg_bytes / dur / 1e9 / peak, "peak_source": peak_src, "traffic": None,
+                "frac": alg_bytes / dur / 1e9 / peak, "peak_source": peak_src,
+                "traffic": traffic, "traffic_source": "profiles/r01_ncu_full_lstm_text_bt40.txt "
+                                                       "(dram__bytes_read.sum + dram__bytes_write.sum, one launch)",
+                "algorithmic_bytes": alg_bytes,
                 "launch_ms": kdur[kname], "launch_ms_fwd": kdur["mmda_lstm_forward"],
                 "launch_ms_bwd": kdur["mmda_lstm_backward"],
-                "note": "the recurrence is fp32-FMA/latency bound, not HBM bound; see fp32_fma",
+                "note": "the recurrence is bound by shared-memory operand delivery and fp32 FMA issue "
+                        "(sequential dependence), not by HBM: see smem_operand and fp32_fma",
+                "smem_operand": {"achieved_tbs": lds_bytes / dur / 1e12, "peak_tbs": smem_peak,
+                                 "frac": lds_bytes / dur / 1e12 / smem_peak,
+                                 "peak_source": "148 SM x 128 B/clk x sampled SM clock"},
                 "fp32_fma": {"achieved_tflops": flops / dur / 1e12, "peak_tflops": fma_peak,
                              "frac": flops / dur / 1e12 / fma_peak,
                              "peak_source": "148 SM x 128 FMA/clk x 2 x sampled SM clock"}}

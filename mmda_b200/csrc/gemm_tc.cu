@@ -143,6 +143,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
   const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 1);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  // epilogue staging: 4 warps x (32 x 33) floats, after the barrier block
+  float* stage_base = reinterpret_cast<float*>(smem_raw + (bar_base + 256 - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
@@ -244,7 +246,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
     }
-    const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
 #pragma unroll 1
     for (int cc = 0; cc < BN / 32; ++cc) {
       uint32_t r[32];
@@ -275,39 +276,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
             r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(t[j]));
         }
       }
+      // Transpose the warp's 32x32 chunk through shared memory so that every store / atomic
+      // instruction covers 32 consecutive columns of ONE row (a single 128-byte line) instead
+      // of one column group of 32 different rows.
       const int nb = n0 + cc * 32;
-      if (row < p.M && nb < p.N) {
-        const int row_out = p.c_ilv ? (row & 3) * p.c_ilv + (row >> 2) : row;
-        float* crow = p.C + (size_t)row_out * p.ldc + nb;
-        const bool add_bias = (blockIdx.z == 0);
-        if (vec_ok && nb + 32 <= p.N && p.mode != 2) {
+      float* stage = stage_base + (warp - 2) * (32 * 33);
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 v;
-            v.x = p.alpha * __uint_as_float(r[j]);     v.y = p.alpha * __uint_as_float(r[j + 1]);
-            v.z = p.alpha * __uint_as_float(r[j + 2]); v.w = p.alpha * __uint_as_float(r[j + 3]);
-            if (p.bias) { v.x += p.bias[nb + j]; v.y += p.bias[nb + j + 1]; v.z += p.bias[nb + j + 2]; v.w += p.bias[nb + j + 3]; }
-            if (p.bias2) { v.x += p.bias2[nb + j]; v.y += p.bias2[nb + j + 1]; v.z += p.bias2[nb + j + 2]; v.w += p.bias2[nb + j + 3]; }
-            if (p.mode == 1) {
-              const float4 o = *reinterpret_cast<const float4*>(crow + j);
-              v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-            }
-            *reinterpret_cast<float4*>(crow + j) = v;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (nb + j < p.N) {
-              float v = p.alpha * __uint_as_float(r[j]);
-              if (add_bias && p.bias) v += p.bias[nb + j];
-              if (add_bias && p.bias2) v += p.bias2[nb + j];
-              if (p.mode == 2) atomicAdd(crow + j, v);
-              else if (p.mode == 1) crow[j] += v;
-              else crow[j] = v;
-            }
-          }
+      for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = __uint_as_float(r[j]);
+      __syncwarp();
+      const int col = nb + lane;
+      if (col < p.N) {
+        float bsum = 0.f;
+        if (blockIdx.z == 0) {
+          if (p.bias) bsum += p.bias[col];
+          if (p.bias2) bsum += p.bias2[col];
+        }
+        const int row_base = m0 + q * 32;
+#pragma unroll 4
+        for (int rr = 0; rr < 32; ++rr) {
+          const int grow = row_base + rr;
+          if (grow >= p.M) break;
+          const int row_out = p.c_ilv ? (grow & 3) * p.c_ilv + (grow >> 2) : grow;
+          float* cp = p.C + (size_t)row_out * p.ldc + col;
+          const float v = p.alpha * stage[rr * 33 + lane] + bsum;
+          if (p.mode == 2) atomicAdd(cp, v);
+          else if (p.mode == 1) *cp += v;
+          else *cp = v;
         }
       }
+      __syncwarp();
     }
   }
   tc_fence_before();
@@ -459,11 +456,11 @@ int mmda_gemm_tc(int kind, int a_mn, int b_mn, int M, int N, int K, const void* 
   a.c_ilv = c_row_interleave;
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, split_k);
   if (kind == 0) {
-    constexpr int smem = 3 * 4 * TILE_BYTES + 1024 + 256;
+    constexpr int smem = 3 * 4 * TILE_BYTES + 1024 + 256 + 4 * 32 * 33 * 4;
     MMDA_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     gemm_tc_kernel<0><<<grid, NUM_THREADS, smem, stream>>>(mAh, mAl, mBh, mBl, a);
   } else {
-    constexpr int smem = 6 * 2 * TILE_BYTES + 1024 + 256;
+    constexpr int smem = 6 * 2 * TILE_BYTES + 1024 + 256 + 4 * 32 * 33 * 4;
     MMDA_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     gemm_tc_kernel<1><<<grid, NUM_THREADS, smem, stream>>>(mAh, mAl, mBh, mBl, a);
   }
