@@ -137,20 +137,23 @@ int mmda_add2d(float* out, int ldo, const float* x, int ldx, float ax, const flo
 /* out[c] += sum_r x[r][c] (bias gradients; out2 optional second destination) */
 int mmda_colsum(const float* x, int ld, int rows, int cols, float* out, float* out2,
                 int out_interleave, mmda_stream_t stream);
-/* inverted dropout, mask = f(seed, stream_id, index): nn.Dropout at src/models.py:126,152,160 */
+/* inverted dropout, mask = f(seed [+ *seed_dev, the device step counter, if non-NULL], stream_id,
+ * index): nn.Dropout at src/models.py:126,152,160 */
 int mmda_dropout(const float* x, float* out, long long n, float p, unsigned long long seed,
-                 unsigned stream_id, mmda_stream_t stream);
+                 const unsigned long long* seed_dev, unsigned stream_id, mmda_stream_t stream);
 /* getBinaryTensor, src/utils/functions.py:112-115 */
 int mmda_threshold(const float* x, float* out, long long n, float thr, mmda_stream_t stream);
 
 /* ---- attention core of nn.TransformerEncoderLayer(d, nhead=2), src/models.py:160-161,243-245
  * qkv rows (b*seq + i) = [q | k | v]; probs (B, nhead, seq, seq) pre-dropout. */
 int mmda_attention_forward(const float* qkv, float* ctx, float* probs, int B, int seq, int nhead,
-                           int head_dim, float p_drop, unsigned long long seed, unsigned stream_id,
+                           int head_dim, float p_drop, unsigned long long seed,
+                           const unsigned long long* seed_dev, unsigned stream_id,
                            mmda_stream_t stream);
 int mmda_attention_backward(const float* qkv, const float* probs, const float* dctx, float* dqkv,
                             int B, int seq, int nhead, int head_dim, float p_drop,
-                            unsigned long long seed, unsigned stream_id, mmda_stream_t stream);
+                            unsigned long long seed, const unsigned long long* seed_dev,
+                            unsigned stream_id, mmda_stream_t stream);
 
 /* ---- fused losses forward + backward, src/solver.py:163-181,373-462 (see csrc/loss.cu) ------
  * X0 (B,6,d) tokens [p_t,p_v,p_a,s_t,s_v,s_a]; O,R (3,B,d); scores,tcp,y (B,NC).
@@ -179,7 +182,14 @@ int mmda_loss_grad_misc(const float* scores, const float* tcp, const float* y, c
  * gradient before clipping (1/world_size after a sum all-reduce, else 1). */
 int mmda_adam_clip_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
                         long long n, int step, float lr, float clip, float beta1, float beta2,
-                        float eps, float grad_scale, mmda_stream_t stream);
+                        float eps, float grad_scale, const void* state_dev, mmda_stream_t stream);
+/* Device-resident step state (32 bytes: step counter = dropout seed offset, beta^t products, the
+ * two Adam bias-correction scalars) so one captured CUDA graph replays step after step.  When
+ * state_dev is passed to mmda_adam_clip_step its scalars override `step`. */
+int mmda_step_state_init(void* state_dev, long long step, float beta1, float beta2,
+                         mmda_stream_t stream);
+int mmda_step_state_advance(void* state_dev, float lr, float beta1, float beta2,
+                            mmda_stream_t stream);
 
 #ifdef __cplusplus
 }

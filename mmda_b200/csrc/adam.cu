@@ -5,10 +5,31 @@
 // Restated in oracle/explicit.py::adam_clip_step.
 #include "common.cuh"
 
+// Per-step scalars kept on the device so a captured CUDA graph can be replayed step after step:
+// the step counter (also the dropout seed offset), beta^t running products and the two
+// bias-correction scalars of Adam.
+struct StepState {
+  unsigned long long counter;
+  double b1pow, b2pow;
+  float step_size, inv_sqrt_bc2;
+};
+
+__global__ void step_state_advance_kernel(StepState* st, double lr, double b1, double b2) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    st->counter += 1ULL;
+    st->b1pow *= b1;
+    st->b2pow *= b2;
+    st->step_size = (float)(lr / (1.0 - st->b1pow));
+    st->inv_sqrt_bc2 = (float)(1.0 / sqrt(1.0 - st->b2pow));
+  }
+}
+
 __global__ void __launch_bounds__(256)
 adam_clip_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                  float* __restrict__ v, size_t n, float clip, float step_size, float b1, float b2,
-                 float inv_sqrt_bc2, float eps, float grad_scale) {
+                 float inv_sqrt_bc2, float eps, float grad_scale,
+                 const StepState* __restrict__ state) {
+  if (state != nullptr) { step_size = state->step_size; inv_sqrt_bc2 = state->inv_sqrt_bc2; }
   const size_t n4 = n >> 2;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -44,9 +65,10 @@ adam_clip_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
 extern "C" int mmda_adam_clip_step(float* params, const float* grads, float* exp_avg,
                                    float* exp_avg_sq, long long n, int step, float lr, float clip,
                                    float beta1, float beta2, float eps, float grad_scale,
-                                   cudaStream_t stream) {
+                                   const void* state_dev, cudaStream_t stream) {
   if (n <= 0) return MMDA_OK;
-  MMDA_REQUIRE(step >= 1, "adam: step must be >= 1 (got %d)", step);
+  MMDA_REQUIRE(step >= 1 || state_dev != nullptr, "adam: step must be >= 1 (got %d)", step);
+  if (step < 1) step = 1;
   MMDA_REQUIRE((((uintptr_t)params | (uintptr_t)grads | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0,
                "adam: arena pointers must be 16-byte aligned");
   const double bc1 = 1.0 - pow((double)beta1, (double)step);
@@ -58,7 +80,30 @@ extern "C" int mmda_adam_clip_step(float* params, const float* grads, float* exp
   if (blocks < 1) blocks = 1;
   adam_clip_kernel<<<(int)blocks, 256, 0, stream>>>(params, grads, exp_avg, exp_avg_sq, (size_t)n,
                                                     clip, step_size, beta1, beta2, inv_sqrt_bc2, eps,
-                                                    grad_scale);
+                                                    grad_scale, reinterpret_cast<const StepState*>(state_dev));
   MMDA_CHECK_LAUNCH();
+  return MMDA_OK;
+}
+
+// state_dev: 32-byte device buffer, initialise with mmda_step_state_init; advance once per step
+// (inside the captured graph) before the dropout sites and the optimiser read it.
+extern "C" int mmda_step_state_advance(void* state_dev, float lr, float beta1, float beta2,
+                                       cudaStream_t stream) {
+  MMDA_REQUIRE(state_dev != nullptr, "step_state_advance: null state");
+  step_state_advance_kernel<<<1, 32, 0, stream>>>(reinterpret_cast<StepState*>(state_dev), lr, beta1, beta2);
+  MMDA_CHECK_LAUNCH();
+  return MMDA_OK;
+}
+
+extern "C" int mmda_step_state_init(void* state_dev, long long step, float beta1, float beta2,
+                                    cudaStream_t stream) {
+  StepState h;
+  h.counter = (unsigned long long)step;
+  h.b1pow = pow((double)beta1, (double)step);
+  h.b2pow = pow((double)beta2, (double)step);
+  h.step_size = 0.f;
+  h.inv_sqrt_bc2 = 0.f;
+  MMDA_CUDA(cudaMemcpyAsync(state_dev, &h, sizeof(h), cudaMemcpyHostToDevice, stream));
+  MMDA_CUDA(cudaStreamSynchronize(stream));
   return MMDA_OK;
 }

@@ -164,7 +164,9 @@ __global__ void colsum_kernel(const float* __restrict__ x, int ld, int rows, int
 // inverted dropout; the keep mask is a pure function of (seed, stream, index) so the backward
 // regenerates it instead of storing it
 __global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ out, size_t n,
-                               float p, float scale, unsigned long long seed, unsigned stream) {
+                               float p, float scale, unsigned long long seed,
+                               const unsigned long long* __restrict__ seed_dev, unsigned stream) {
+  if (seed_dev) seed += seed_dev[0] * 0x9E3779B97F4A7C15ULL;   // per-step device counter (graph replay)
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
        i += (size_t)gridDim.x * blockDim.x)
     out[i] = rng_uniform(seed, stream, (uint32_t)i) >= p ? x[i] * scale : 0.f;
@@ -183,7 +185,9 @@ constexpr int ATT_S = 6;
 template <int R>   // R = ceil(head_dim / 32) registers per lane
 __global__ void attn_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ ctx,
                                 float* __restrict__ probs, int B, int nhead, int HD, float scale,
-                                float p_drop, unsigned long long seed, unsigned stream) {
+                                float p_drop, unsigned long long seed,
+                                const unsigned long long* __restrict__ seed_dev, unsigned stream) {
+  if (seed_dev) seed += seed_dev[0] * 0x9E3779B97F4A7C15ULL;
   const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (w >= B * nhead) return;
@@ -238,7 +242,9 @@ template <int R>
 __global__ void attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ probs,
                                 const float* __restrict__ dctx, float* __restrict__ dqkv, int B,
                                 int nhead, int HD, float scale, float p_drop,
-                                unsigned long long seed, unsigned stream) {
+                                unsigned long long seed,
+                                const unsigned long long* __restrict__ seed_dev, unsigned stream) {
+  if (seed_dev) seed += seed_dev[0] * 0x9E3779B97F4A7C15ULL;
   const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (w >= B * nhead) return;
@@ -376,11 +382,11 @@ int mmda_colsum(const float* x, int ld, int rows, int cols, float* out, float* o
 }
 
 int mmda_dropout(const float* x, float* out, long long n, float p, unsigned long long seed,
-                 unsigned stream_id, cudaStream_t stream) {
+                 const unsigned long long* seed_dev, unsigned stream_id, cudaStream_t stream) {
   if (n <= 0) return MMDA_OK;
   MMDA_REQUIRE(p >= 0.f && p < 1.f, "dropout: p=%f", p);
   dropout_kernel<<<ew_grid((size_t)n), 256, 0, stream>>>(x, out, (size_t)n, p, 1.f / (1.f - p),
-                                                         seed, stream_id);
+                                                         seed, seed_dev, stream_id);
   MMDA_CHECK_LAUNCH();
   return MMDA_OK;
 }
@@ -393,18 +399,19 @@ int mmda_threshold(const float* x, float* out, long long n, float thr, cudaStrea
 }
 
 int mmda_attention_forward(const float* qkv, float* ctx, float* probs, int B, int seq, int nhead,
-                           int head_dim, float p_drop, unsigned long long seed, unsigned stream_id,
+                           int head_dim, float p_drop, unsigned long long seed,
+                           const unsigned long long* seed_dev, unsigned stream_id,
                            cudaStream_t stream) {
   MMDA_REQUIRE(seq == ATT_S, "attention: fusion sequence is 6 tokens (got %d)", seq);
   const int warps = B * nhead;
   const float scale = 1.0f / sqrtf((float)head_dim);
   const int grid = (warps + 3) / 4;
   if (head_dim <= 32)
-    attn_fwd_kernel<1><<<grid, 128, 0, stream>>>(qkv, ctx, probs, B, nhead, head_dim, scale, p_drop, seed, stream_id);
+    attn_fwd_kernel<1><<<grid, 128, 0, stream>>>(qkv, ctx, probs, B, nhead, head_dim, scale, p_drop, seed, seed_dev, stream_id);
   else if (head_dim <= 64)
-    attn_fwd_kernel<2><<<grid, 128, 0, stream>>>(qkv, ctx, probs, B, nhead, head_dim, scale, p_drop, seed, stream_id);
+    attn_fwd_kernel<2><<<grid, 128, 0, stream>>>(qkv, ctx, probs, B, nhead, head_dim, scale, p_drop, seed, seed_dev, stream_id);
   else if (head_dim <= 128)
-    attn_fwd_kernel<4><<<grid, 128, 0, stream>>>(qkv, ctx, probs, B, nhead, head_dim, scale, p_drop, seed, stream_id);
+    attn_fwd_kernel<4><<<grid, 128, 0, stream>>>(qkv, ctx, probs, B, nhead, head_dim, scale, p_drop, seed, seed_dev, stream_id);
   else {
     mmda_set_error("attention: head_dim=%d unsupported (<= 128)", head_dim);
     return MMDA_ERR_UNSUPPORTED;
@@ -415,17 +422,18 @@ int mmda_attention_forward(const float* qkv, float* ctx, float* probs, int B, in
 
 int mmda_attention_backward(const float* qkv, const float* probs, const float* dctx, float* dqkv,
                             int B, int seq, int nhead, int head_dim, float p_drop,
-                            unsigned long long seed, unsigned stream_id, cudaStream_t stream) {
+                            unsigned long long seed, const unsigned long long* seed_dev,
+                            unsigned stream_id, cudaStream_t stream) {
   MMDA_REQUIRE(seq == ATT_S, "attention: fusion sequence is 6 tokens (got %d)", seq);
   const int warps = B * nhead;
   const float scale = 1.0f / sqrtf((float)head_dim);
   const int grid = (warps + 3) / 4;
   if (head_dim <= 32)
-    attn_bwd_kernel<1><<<grid, 128, 0, stream>>>(qkv, probs, dctx, dqkv, B, nhead, head_dim, scale, p_drop, seed, stream_id);
+    attn_bwd_kernel<1><<<grid, 128, 0, stream>>>(qkv, probs, dctx, dqkv, B, nhead, head_dim, scale, p_drop, seed, seed_dev, stream_id);
   else if (head_dim <= 64)
-    attn_bwd_kernel<2><<<grid, 128, 0, stream>>>(qkv, probs, dctx, dqkv, B, nhead, head_dim, scale, p_drop, seed, stream_id);
+    attn_bwd_kernel<2><<<grid, 128, 0, stream>>>(qkv, probs, dctx, dqkv, B, nhead, head_dim, scale, p_drop, seed, seed_dev, stream_id);
   else if (head_dim <= 128)
-    attn_bwd_kernel<4><<<grid, 128, 0, stream>>>(qkv, probs, dctx, dqkv, B, nhead, head_dim, scale, p_drop, seed, stream_id);
+    attn_bwd_kernel<4><<<grid, 128, 0, stream>>>(qkv, probs, dctx, dqkv, B, nhead, head_dim, scale, p_drop, seed, seed_dev, stream_id);
   else {
     mmda_set_error("attention: head_dim=%d unsupported (<= 128)", head_dim);
     return MMDA_ERR_UNSUPPORTED;

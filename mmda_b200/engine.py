@@ -107,8 +107,8 @@ class Kernels:
         self._c("mmda_add2d", _ptr(out), out.stride(0), _ptr(x), x.stride(0), ax, _ptr(y),
                 0 if y is None else y.stride(0), ay, out.shape[0], out.shape[1])
 
-    def dropout(self, x, out, p, seed, sid):
-        self._c("mmda_dropout", _ptr(x), _ptr(out), x.numel(), p, seed, sid)
+    def dropout(self, x, out, p, seed, sid, seed_dev=None):
+        self._c("mmda_dropout", _ptr(x), _ptr(out), x.numel(), p, seed, _ptr(seed_dev), sid)
 
 
 def _f32(*shape, device):
@@ -121,6 +121,7 @@ class MisaEngine:
         self.cfg = model.config
         self.k = Kernels()
         self.ws: Dict[str, torch.Tensor] = {}
+        self.ws_version = 0
         self.act_id = ACTIVATIONS[model.act_name]
         self.d = self.cfg.hidden_size
         self.NC = self.cfg.num_classes
@@ -158,6 +159,7 @@ class MisaEngine:
         if t is None or t.numel() < n or t.dtype != dtype or t.device != dev:
             t = torch.empty(max(n, 1), dtype=dtype, device=dev)
             self.ws[name] = t
+            self.ws_version += 1        # captured CUDA graphs hold raw pointers into the workspace
         v = t[:n].view(*shape)
         if zero:
             v.zero_()
@@ -346,7 +348,7 @@ class MisaEngine:
         return utt
 
     def forward(self, sentences, visual, acoustic, lengths, train: bool, want_sp: bool = True,
-                dropout: Optional[bool] = None):
+                dropout: Optional[bool] = None, seed_dev: Optional[torch.Tensor] = None):
         """Returns a dict of device tensors (views into the workspace, valid until the next call).
         ``train`` keeps what the backward needs; ``dropout`` (default: = model.training) enables
         the five Bernoulli sites."""
@@ -363,8 +365,10 @@ class MisaEngine:
         drop = self.model.training if dropout is None else dropout
         self.drop_on = bool(drop)
         self.step_id += 1
-        seed = (self.seed * 1000003 + self.step_id) & 0xFFFFFFFFFFFFFFFF
-        self.cur_seed = seed
+        # dropout seed: host counter, or (graph-replayable) a constant plus the device step counter
+        seed = self.seed if seed_dev is not None else \
+            (self.seed * 1000003 + self.step_id) & 0xFFFFFFFFFFFFFFFF
+        self.cur_seed, self.seed_dev = seed, seed_dev
         p_cls = float(cfg.dropout) if drop else 0.0
         p_att = ATT_P if drop else 0.0
         self.p_cls, self.p_att = p_cls, p_att
@@ -452,17 +456,17 @@ class MisaEngine:
         lnr = self.buf("enc_rs", 2, rows)
         k.linear(Xr, P[TL + "self_attn.in_proj_weight"], P[TL + "self_attn.in_proj_bias"], QKV)
         k._c("mmda_attention_forward", _ptr(QKV), _ptr(CTX), _ptr(PR), B, 6, NHEAD, d // NHEAD,
-             p_att, seed, 1)
+             p_att, seed, _ptr(seed_dev), 1)
         k.linear(CTX, P[TL + "self_attn.out_proj.weight"], P[TL + "self_attn.out_proj.bias"], AO)
         if p_att > 0:
-            k.dropout(AO, AO, p_att, seed, 2)
+            k.dropout(AO, AO, p_att, seed, 2, seed_dev)
         k.layernorm(Xr, AO, P[TL + "norm1.weight"], P[TL + "norm1.bias"], X1, lnm[0], lnr[0])
         k.linear(X1, P[TL + "linear1.weight"], P[TL + "linear1.bias"], F1, act=ACT_RELU)
         if p_att > 0:
-            k.dropout(F1, F1, p_att, seed, 3)
+            k.dropout(F1, F1, p_att, seed, 3, seed_dev)
         k.linear(F1, P[TL + "linear2.weight"], P[TL + "linear2.bias"], F2)
         if p_att > 0:
-            k.dropout(F2, F2, p_att, seed, 4)
+            k.dropout(F2, F2, p_att, seed, 4, seed_dev)
         k.layernorm(X1, F2, P[TL + "norm2.weight"], P[TL + "norm2.bias"], X2, lnm[1], lnr[1])
 
         # ---- confidence / classifier / labels (src/models.py:247-249) ----
@@ -475,7 +479,7 @@ class MisaEngine:
         if p_cls > 0:
             k.linear(Hf, P["classifier.classifier_layer.weight"],
                      P["classifier.classifier_layer.bias"], SC)
-            k.dropout(SC, SC, p_cls, seed, 5)
+            k.dropout(SC, SC, p_cls, seed, 5, seed_dev)
             k.act(SC, ACT_SIGMOID)
         else:
             k.linear(Hf, P["classifier.classifier_layer.weight"],
@@ -521,7 +525,7 @@ class MisaEngine:
         lnm, lnr = self.buf("enc_mu", 2, rows), self.buf("enc_rs", 2, rows)
         Hf = X2.view(B, 6 * d)
         TCP, SC = self.buf("TCP", B, 6), self.buf("SCORES", B, NC)
-        seed, p_att, p_cls = self.cur_seed, self.p_att, self.p_cls
+        seed, p_att, p_cls, seed_dev = self.cur_seed, self.p_att, self.p_cls, self.seed_dev
         notify = on_ready or (lambda tag: None)
 
         # ---- classifier / confidence ----
@@ -532,7 +536,7 @@ class MisaEngine:
             k.add(dl, d_scores)
             k.act_bwd(dl, SC, ACT_SIGMOID)
             if p_cls > 0:
-                k.dropout(dl, dl, p_cls, seed, 5)
+                k.dropout(dl, dl, p_cls, seed, 5, seed_dev)
             k.linear_bwd(dl, Hf, P["classifier.classifier_layer.weight"],
                          G["classifier.classifier_layer.weight"],
                          G["classifier.classifier_layer.bias"], dHf, 0.0)
@@ -555,12 +559,12 @@ class MisaEngine:
             dF2 = dS2
             if p_att > 0:
                 dF2 = self.buf("dF2", rows, d)
-                k.dropout(dS2, dF2, p_att, seed, 4)
+                k.dropout(dS2, dF2, p_att, seed, 4, seed_dev)
             dF1 = self.buf("dF1", rows, FF)
             k.linear_bwd(dF2, F1, P[TL + "linear2.weight"], G[TL + "linear2.weight"],
                          G[TL + "linear2.bias"], dF1, 0.0)
             if p_att > 0:
-                k.dropout(dF1, dF1, p_att, seed, 3)
+                k.dropout(dF1, dF1, p_att, seed, 3, seed_dev)
             k.act_bwd(dF1, F1, ACT_RELU)
             # dX1 = dS2 + dF1 W1   (accumulate in place into dS2)
             k.linear_bwd(dF1, X1, P[TL + "linear1.weight"], G[TL + "linear1.weight"],
@@ -571,14 +575,14 @@ class MisaEngine:
             dAO = dS1
             if p_att > 0:
                 dAO = self.buf("dAO", rows, d)
-                k.dropout(dS1, dAO, p_att, seed, 2)
+                k.dropout(dS1, dAO, p_att, seed, 2, seed_dev)
             dCTX = self.buf("dCTX", rows, d)
             k.linear_bwd(dAO, CTX, P[TL + "self_attn.out_proj.weight"],
                          G[TL + "self_attn.out_proj.weight"], G[TL + "self_attn.out_proj.bias"],
                          dCTX, 0.0)
             dQKV = self.buf("dQKV", rows, 3 * d)
             k._c("mmda_attention_backward", _ptr(QKV), _ptr(PR), _ptr(dCTX), _ptr(dQKV), B, 6,
-                 NHEAD, d // NHEAD, p_att, seed, 1)
+                 NHEAD, d // NHEAD, p_att, seed, _ptr(seed_dev), 1)
             # dX0 = dS1 + dQKV W_in
             k.add(dXr, dS1)
             k.linear_bwd(dQKV, Xr, P[TL + "self_attn.in_proj_weight"],

@@ -73,7 +73,7 @@ def plan_arena(named_shapes: List[Tuple[str, Tuple[int, ...]]], use_confid: bool
 
 class FusedTrainer:
     def __init__(self, model, lr: Optional[float] = None, process_group=None,
-                 global_batch_stats: bool = True):
+                 global_batch_stats: bool = True, use_graph: Optional[bool] = None):
         self.model = model
         self.cfg = cfg = model.config
         self.eng = model.engine
@@ -92,6 +92,18 @@ class FusedTrainer:
         self.m = torch.zeros_like(self.p_arena)
         self.v = torch.zeros_like(self.p_arena)
         self._pending = []
+        # device-resident step state (step counter = dropout seed offset, Adam bias corrections)
+        self.state = torch.zeros(4, dtype=torch.float64, device=self.p_arena.device)
+        if not _engine._DRYRUN:
+            self.eng.k.bind_stream()
+            self.eng.k._c("mmda_step_state_init", _ptr(self.state), 0, 0.9, 0.999)
+        # CUDA-graph replay of the whole step (single GPU, repeated sequence-length pattern)
+        import os
+        self.use_graph = (use_graph if use_graph is not None else
+                          os.environ.get("MMDA_GRAPH", "1") != "0") and self.world == 1
+        self._graph = None
+        self._graph_seen = {}
+        self.launches_per_step = None
 
     # ------------------------------------------------------------------ arenas -------------
     def _build_arena(self):
@@ -216,7 +228,10 @@ class FusedTrainer:
         tensor of the six loss values [cls, diff, sim, recon, conf, total]."""
         self._check_alias()
         eng = self.eng
-        out = eng.forward(sentences, visual, acoustic, lengths, train=True, want_sp=False)
+        eng.k.bind_stream()
+        eng.k._c("mmda_step_state_advance", _ptr(self.state), self.lr, 0.9, 0.999)
+        out = eng.forward(sentences, visual, acoustic, lengths, train=True, want_sp=False,
+                          seed_dev=self.state)
         B = out["scores"].shape[0]
         if labels.shape != (B, eng.NC) or labels.dtype != torch.float32 or \
                 not (labels.is_cuda or _engine._DRYRUN):
@@ -236,11 +251,46 @@ class FusedTrainer:
         k.bind_stream()
         k._c("mmda_adam_clip_step", _ptr(self.p_arena), _ptr(self.g_arena), _ptr(self.m),
              _ptr(self.v), self.n_active, self.step_count, self.lr, self.clip, 0.9, 0.999, 1e-8,
-             1.0)
+             1.0, _ptr(self.state))
 
-    def step(self, sentences, visual, acoustic, lengths, labels):
+    def _eager_step(self, sentences, visual, acoustic, lengths, labels):
         losses = self.forward_backward(sentences, visual, acoustic, lengths, labels)
         self.optimizer_step()
+        return losses
+
+    def step(self, sentences, visual, acoustic, lengths, labels):
+        """One optimisation step.  With ``use_graph`` (default on one GPU) the kernel sequence of
+        a repeated (shapes, lengths) pattern is captured once into a CUDA graph -- multi-stream
+        forks included -- and replayed; per-step scalars live in ``self.state`` on the device."""
+        if not self.use_graph or _engine._DRYRUN:
+            return self._eager_step(sentences, visual, acoustic, lengths, labels)
+        key = (tuple(sentences.shape), tuple(visual.shape), tuple(acoustic.shape),
+               tuple(lengths.tolist()), self.model.training)
+        g = self._graph
+        if g is not None and g["key"] == key and g["ws"] == self.eng.ws_version and \
+                g["alias"] == self._alias_ver:
+            for dst, src in zip(g["inputs"], (sentences, visual, acoustic, labels)):
+                dst.copy_(src, non_blocking=True)
+            g["graph"].replay()
+            self.step_count += 1
+            return g["losses"]
+        seen = self._graph_seen.get(key, 0) + 1
+        self._graph_seen = {key: seen}
+        if seen < 3:                       # warm-up: allocates the workspace, builds the plans
+            return self._eager_step(sentences, visual, acoustic, lengths, labels)
+        self._check_alias()
+        inputs = [t.clone() for t in (sentences, visual, acoustic, labels)]
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        l0, count0 = self.eng.k.launches, self.step_count
+        with torch.cuda.graph(graph):
+            losses = self._eager_step(inputs[0], inputs[1], inputs[2], lengths, inputs[3])
+        self.launches_per_step = self.eng.k.launches - l0
+        self.step_count = count0           # capture enqueues nothing: the replay runs the step
+        self._graph = dict(key=key, graph=graph, inputs=inputs, losses=losses,
+                           ws=self.eng.ws_version, alias=self._alias_ver)
+        graph.replay()
+        self.step_count += 1
         return losses
 
     def step_batch(self, batch, device=None):

@@ -118,7 +118,7 @@ def test_layernorm_attention_colsum(dev):
         hd = d // 2
         qkv = torch.randn(B * 6, 3 * d, generator=g).to(dev)
         ctx = torch.empty(B * 6, d, device=dev); pr = torch.empty(B, 2, 6, 6, device=dev)
-        k._c("mmda_attention_forward", _ptr(qkv), _ptr(ctx), _ptr(pr), B, 6, 2, hd, 0.0, 1, 1)
+        k._c("mmda_attention_forward", _ptr(qkv), _ptr(ctx), _ptr(pr), B, 6, 2, hd, 0.0, 1, None, 1)
         q3 = qkv.double().view(B, 6, 3, 2, hd).requires_grad_(True)
         q, kk, v = q3[:, :, 0], q3[:, :, 1], q3[:, :, 2]              # (B,6,2,hd)
         s = torch.einsum("bihd,bjhd->bhij", q, kk) / hd ** 0.5
@@ -129,7 +129,7 @@ def test_layernorm_attention_colsum(dev):
         do = torch.randn(B * 6, d, generator=g).to(dev)
         o.backward(do.double())
         dqkv = torch.empty_like(qkv)
-        k._c("mmda_attention_backward", _ptr(qkv), _ptr(pr), _ptr(do), _ptr(dqkv), B, 6, 2, hd, 0.0, 1, 1)
+        k._c("mmda_attention_backward", _ptr(qkv), _ptr(pr), _ptr(do), _ptr(dqkv), B, 6, 2, hd, 0.0, 1, None, 1)
         C.add(f"attn bwd B={B} d={d}", dqkv, q3.grad.reshape(B * 6, 3 * d), 5e-6)
     C.finish()
 
@@ -177,7 +177,7 @@ def test_adam_clip_matches_torch(dev):
         torch.nn.utils.clip_grad_value_([pt], 1.0)
         opt.step()
         gd = gr.to(dev)
-        k._c("mmda_adam_clip_step", _ptr(p), _ptr(gd), _ptr(m), _ptr(v), n, step, 1e-3, 1.0, 0.9, 0.999, 1e-8, 1.0)
+        k._c("mmda_adam_clip_step", _ptr(p), _ptr(gd), _ptr(m), _ptr(v), n, step, 1e-3, 1.0, 0.9, 0.999, 1e-8, 1.0, None)
         C.add(f"adam step {step}", p, pt.detach(), 2e-6)
     C.finish()
 
@@ -498,4 +498,32 @@ def test_c3_bf16_mode_within_2e2(dev):
     for n in ("embed.weight", "trnn1.weight_ih_l0", "project_t.project_t.weight"):
         C.rows.append((f"sensitivity: oracle(bf16 operands) vs oracle(fp32) grad {n} = "
                        f"{max_rel(grads_r[n], grads[n]):.3e}", 0.0, 0.0, True))
+    C.finish()
+
+
+def test_cuda_graph_replay_equals_eager(dev):
+    """The captured CUDA graph of the fused step (multi-stream forks, device-resident step state)
+    must produce the same training trajectory as eager launches, including train-mode dropout
+    (same device seed counter) and varying inputs."""
+    from mmda_b200 import MISA, mosei_config
+    from mmda_b200.synthetic import batch_for
+    from mmda_b200.trainer import FusedTrainer
+    cfg = mosei_config(vocab_size=300, batch_size=48, use_confidNet=True)
+    batches = [batch_for(cfg, seed=40 + i, lengths="full", seq_len=12) for i in range(3)]
+    res = {}
+    for mode in (False, True):
+        torch.manual_seed(5)
+        model = MISA(cfg).to(dev).train()
+        tr = FusedTrainer(model, use_graph=mode)
+        Ls = []
+        for it in range(7):
+            b = batches[it % 3]
+            L = tr.step(b.sentences.to(dev), b.visual.to(dev), b.acoustic.to(dev), b.lengths, b.labels.to(dev))
+            Ls.append(L[:6].clone())
+        assert (tr._graph is not None) == mode
+        res[mode] = (torch.stack(Ls).cpu(), tr.p_arena[:tr.n_active].clone().cpu(), tr.step_count)
+    assert res[True][2] == res[False][2] == 7
+    C = Checks("graph")
+    C.add("losses over 7 steps", res[True][0], res[False][0], 1e-5)
+    C.add("parameters after 7 steps", res[True][1], res[False][1], 1e-5)
     C.finish()
