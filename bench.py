@@ -23,7 +23,7 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-SEQ, BATCH, VOCAB = 50, 256, 20000
+SEQ, BATCH, VOCAB = 50, 256, 20000     # BASELINE configs[1]; --seq / --batch override (configs[4] sweep)
 METRIC, UNIT = "train_samples_per_sec", "samples/s"
 
 
@@ -322,6 +322,7 @@ def run_ours(args):
 
 
 def main():
+    global SEQ
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -329,9 +330,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--lengths", default="full", choices=["full", "ragged"])
+    ap.add_argument("--seq", type=int, default=SEQ)
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    SEQ = args.seq
     if args.impl == "reference":
         run_reference(args, int(os.environ.get("RANK", "0")))
     else:

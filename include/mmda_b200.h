@@ -177,6 +177,13 @@ int mmda_loss_grad_misc(const float* scores, const float* tcp, const float* y, c
                         float* dO, int B, int d, int NC, float Bg, float w_recon, float w_conf,
                         mmda_stream_t stream);
 
+/* ---- evaluation metrics on the device: Solver.eval + get_accuracy / get_metrics,
+ * src/solver.py:311-370, src/utils/eval.py:14-65.  stats (4 + 3*NC floats, zero before a pass):
+ * [0] sum of per-sample |y&p|/max(|y|p|,1), [1] samples, [2] sum of per-batch cls losses,
+ * [3] batches, then TP[NC], FP[NC], FN[NC]. */
+int mmda_eval_accumulate(const float* scores, const float* pred_labels, const float* y,
+                         float* stats, int B, int NC, mmda_stream_t stream);
+
 /* ---- clip_grad_value_ + Adam.step, src/solver.py:185-186 ------------------------------------
  * flat arenas of n floats, 16-byte aligned; step is the 1-based count; grad_scale multiplies the
  * gradient before clipping (1/world_size after a sum all-reduce, else 1). */

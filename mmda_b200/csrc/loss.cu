@@ -372,3 +372,63 @@ int mmda_loss_grad_misc(const float* scores, const float* tcp, const float* y, c
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// Evaluation metrics on the device (reference src/solver.py:311-370 + src/utils/eval.py:14-65):
+// per batch accumulate, into a running stats vector that stays on the GPU for the whole dev/test
+// pass,   [0] sum_i |y_i & p_i| / max(|y_i | p_i|, 1)   (get_accuracy numerator)
+//         [1] samples      [2] sum over batches of the cls loss      [3] batches
+//         [4..4+NC) TP   [4+NC..) FP   [4+2NC..) FN   per class (precision / recall / F1)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+eval_accumulate_kernel(const float* __restrict__ scores, const float* __restrict__ pred,
+                       const float* __restrict__ y, float* __restrict__ stats, int B, int NC) {
+  __shared__ float red[8];
+  const int tid = threadIdx.x;
+  float jac = 0.f, bce = 0.f;
+  float tp[8], fp[8], fn[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) { tp[c] = 0.f; fp[c] = 0.f; fn[c] = 0.f; }
+  for (int b = tid; b < B; b += 256) {
+    int both = 0, any = 0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      if (c < NC) {
+        const bool t = y[b * NC + c] > 0.f, p = pred[b * NC + c] > 0.f;
+        both += (t && p); any += (t || p);
+        tp[c] += (t && p); fp[c] += (!t && p); fn[c] += (t && !p);
+        const float s = scores[b * NC + c], tt = y[b * NC + c];
+        bce -= tt * fmaxf(logf(s), -100.f) + (1.f - tt) * fmaxf(logf(1.f - s), -100.f);
+      }
+    }
+    jac += (float)both / (float)(any > 0 ? any : 1);
+  }
+  const float j = block_sum_256(jac, red);
+  const float l = block_sum_256(bce, red);
+  if (tid == 0) {
+    atomicAdd(stats + 0, j);
+    atomicAdd(stats + 1, (float)B);
+    atomicAdd(stats + 2, l / (float)B);      // sum_c mean_b BCE of this batch
+    atomicAdd(stats + 3, 1.f);
+  }
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    if (c < NC) {
+      const float a = block_sum_256(tp[c], red), b2 = block_sum_256(fp[c], red),
+                  c2 = block_sum_256(fn[c], red);
+      if (tid == 0) {
+        atomicAdd(stats + 4 + c, a);
+        atomicAdd(stats + 4 + NC + c, b2);
+        atomicAdd(stats + 4 + 2 * NC + c, c2);
+      }
+    }
+  }
+}
+
+extern "C" int mmda_eval_accumulate(const float* scores, const float* pred_labels, const float* y,
+                                    float* stats, int B, int NC, cudaStream_t stream) {
+  MMDA_REQUIRE(NC >= 1 && NC <= 8 && B > 0, "eval_accumulate: B=%d NC=%d", B, NC);
+  eval_accumulate_kernel<<<1, 256, 0, stream>>>(scores, pred_labels, y, stats, B, NC);
+  MMDA_CHECK_LAUNCH();
+  return MMDA_OK;
+}

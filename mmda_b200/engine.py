@@ -144,10 +144,13 @@ class MisaEngine:
         # cluster kernel occupies 112 of the 148 SMs)
         self.multi_stream = os.environ.get("MMDA_STREAMS", "1") != "0"
         self._side = None
-        if self.cfg.use_bert:
-            raise NotImplementedError(
-                "use_bert=True: the BERT text branch is the next scope row (SURVEY.md 8f N1); "
-                "this build covers the LSTM text encoder")
+        # use_bert=True: the BERT encoder itself stays the HF / PyTorch module
+        # (library kernels); its masked-mean output feeds the hand-written heads / fusion / losses
+        # through `utt_text`, and the gradient wrt that tensor is handed back to autograd.
+        self.use_bert = bool(self.cfg.use_bert)
+        self.utt_dim = {m: 4 * self.H[m] for m in MODS}
+        if self.use_bert:
+            self.utt_dim["t"] = 768
 
     # ---------------------------------------------------------------- buffers -------------
     def buf(self, name, *shape, dtype=torch.float32, zero=False):
@@ -175,7 +178,8 @@ class MisaEngine:
         ver = tuple(p.data_ptr() for p in self.model.parameters())
         if self._params_ver != ver:
             self._dev = next(self.model.parameters()).device
-            self._params = {n: p.data for n, p in self.model.named_parameters()}
+            self._params = {n: p.data for n, p in self.model.named_parameters()
+                            if not n.startswith("bertmodel.")}
             self._params_ver = ver
             for n, p in self._params.items():
                 if not p.is_cuda and not _DRYRUN:
@@ -348,19 +352,24 @@ class MisaEngine:
         return utt
 
     def forward(self, sentences, visual, acoustic, lengths, train: bool, want_sp: bool = True,
-                dropout: Optional[bool] = None, seed_dev: Optional[torch.Tensor] = None):
+                dropout: Optional[bool] = None, seed_dev: Optional[torch.Tensor] = None,
+                utt_text: Optional[torch.Tensor] = None):
         """Returns a dict of device tensors (views into the workspace, valid until the next call).
         ``train`` keeps what the backward needs; ``dropout`` (default: = model.training) enables
         the five Bernoulli sites."""
         k, cfg, d, NC = self.k, self.cfg, self.d, self.NC
         P = self.params()
         k.bind_stream()
+        if self.use_bert != (utt_text is not None):
+            raise MmdaError("utt_text (masked-mean BERT output) is required iff config.use_bert")
         for name, t in (("sentences", sentences), ("visual", visual), ("acoustic", acoustic)):
+            if name == "sentences" and self.use_bert:
+                continue
             if not t.is_cuda and not _DRYRUN:
                 raise MmdaError(f"{name} must be a CUDA tensor (reference moves it with to_gpu)")
         pk = self._pack(lengths)
         B, N, Tmax = pk["B"], pk["N"], pk["Tmax"]
-        if sentences.shape[0] < Tmax or sentences.shape[1] != B:
+        if not self.use_bert and (sentences.shape[0] < Tmax or sentences.shape[1] != B):
             raise MmdaError(f"sentences {tuple(sentences.shape)} inconsistent with lengths")
         drop = self.model.training if dropout is None else dropout
         self.drop_on = bool(drop)
@@ -374,17 +383,22 @@ class MisaEngine:
         self.p_cls, self.p_att = p_cls, p_att
 
         # ---- encoders on packed rows (three modalities concurrently) ----
-        sent = sentences.contiguous()
-        V = P["embed.weight"].shape[0]
+        sent = None if self.use_bert else sentences.contiguous()
+        V = 0 if self.use_bert else P["embed.weight"].shape[0]
         X, utt = {}, {}
         srcs = {"v": visual.contiguous(), "a": acoustic.contiguous()}
         for m, src in srcs.items():
             if src.dtype != torch.float32 or src.shape[1] != B or src.shape[2] != self.H[m]:
                 raise MmdaError(f"{m} input has shape {tuple(src.shape)} / {src.dtype}")
             X[m] = self.buf(f"X_{m}", N, self.H[m])
-        X["t"] = self.buf("X_t", N, self.H["t"])
+        if not self.use_bert:
+            X["t"] = self.buf("X_t", N, self.H["t"])
 
         def enc_text():
+            if self.use_bert:
+                utt["t"] = self.buf("utt_t", B, 768)
+                k.add(utt["t"], utt_text.detach().to(torch.float32).contiguous())
+                return
             k._c("mmda_embedding_forward", _ptr(P["embed.weight"]), _ptr(sent), _ptr(X["t"]),
                  _ptr(pk["row_t"]), _ptr(pk["row_j"]), _ptr(pk["sidx"]), N, B, self.H["t"], V)
             utt["t"] = self._encode("t", X["t"], pk, train, P)
@@ -614,7 +628,7 @@ class MisaEngine:
         # ---- recon / private / shared / project ----
         dO = self.buf("dO", 3, B, d)
         dA = self.buf("dA", 3, B, d)
-        dutt = {m: self.buf(f"dutt_{m}", B, 4 * self.H[m]) for m in MODS}
+        dutt = {m: self.buf(f"dutt_{m}", B, self.utt_dim[m]) for m in MODS}
         pmu, prs = self.buf("proj_mu", 3, B), self.buf("proj_rs", 3, B)
 
         def head_bwd(i, m):
@@ -656,11 +670,13 @@ class MisaEngine:
         # ---- encoders: BPTT + hoisted weight-gradient GEMMs ----
         def enc_bwd(m):
             def run():
-                self._encode_backward(m, dutt[m], G, pk, P)
+                if not (m == "t" and self.use_bert):
+                    self._encode_backward(m, dutt[m], G, pk, P)
                 notify(f"enc_{m}")       # on the stream that produced the gradients
             return run
 
         self._fork({m: enc_bwd(m) for m in MODS})
+        return dutt["t"] if self.use_bert else None
 
     def _encode_backward(self, m, dutt, G, pk, P):
         """BPTT of both layers of modality m + the hoisted weight-gradient GEMMs.  The recurrence
@@ -770,9 +786,10 @@ _DIFF_OUT = ("scores", "tcp") + tuple(f"utt_private_{m}" for m in MODS) + \
 
 class _MisaFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, model, sentences, visual, acoustic, lengths, names, *params):
+    def forward(ctx, model, sentences, visual, acoustic, lengths, names, utt_text, *params):
         eng = model.engine
-        out = eng.forward(sentences, visual, acoustic, lengths, train=True, want_sp=True)
+        out = eng.forward(sentences, visual, acoustic, lengths, train=True, want_sp=True,
+                          utt_text=utt_text)
         ctx.model, ctx.names, ctx.fwd_step = model, names, eng.step_id
         ctx.set_materialize_grads(False)      # unused outputs arrive as None, not zeros
         res = tuple(out[n].clone() for n in _DIFF_OUT) + (out["labels"].clone(),)
@@ -822,30 +839,49 @@ class _MisaFunction(torch.autograd.Function):
         for n, sz in zip(ctx.names, sizes):
             G[n] = arena[off:off + sz].view(P[n].shape)
             off += sz
-        eng.backward(G, d_scores=ds, d_tcp=dt, d_tokens=d_tok, d_orig=d_orig, d_recon=d_recon,
-                     d_sp=d_sp)
+        d_utt = eng.backward(G, d_scores=ds, d_tcp=dt, d_tokens=d_tok, d_orig=d_orig,
+                             d_recon=d_recon, d_sp=d_sp)
+        if d_utt is not None:
+            d_utt = d_utt.clone()
         untouched = set()
         if d_sp is None:
             untouched.add("sp_discriminator.")
         if dt is None:
             untouched.add("confidence.")
+        if eng.use_bert:
+            untouched.add("tlayer_norm.")     # exists in the module but no text LSTM runs
         grads = tuple(None if any(n.startswith(u) for u in untouched) else G[n] for n in ctx.names)
-        return (None,) * 6 + grads
+        return (None,) * 6 + (d_utt,) + grads
+
+
+def _bert_utterance(model, bert_sent, bert_sent_type, bert_sent_mask):
+    """reference src/models.py:186-198: BertModel -> masked mean over tokens (library kernels)."""
+    hid = model.bertmodel(input_ids=bert_sent, attention_mask=bert_sent_mask,
+                          token_type_ids=bert_sent_type)[0]
+    m = bert_sent_mask.unsqueeze(2)
+    return (m * hid).sum(1) / bert_sent_mask.sum(1, keepdim=True)
 
 
 def misa_apply(model, sentences, visual, acoustic, lengths, bert_sent, bert_sent_type,
                bert_sent_mask):
     eng = model.engine
-    named = list(model.named_parameters())
-    needs_grad = torch.is_grad_enabled() and any(p.requires_grad for _, p in named)
+    named = [(n, p) for n, p in model.named_parameters() if not n.startswith("bertmodel.")]
+    utt_text = None
+    if eng.use_bert:
+        if bert_sent is None:
+            raise MmdaError("use_bert=True needs bert_sent / bert_sent_type / bert_sent_mask")
+        utt_text = _bert_utterance(model, bert_sent, bert_sent_type, bert_sent_mask)
+    needs_grad = torch.is_grad_enabled() and (any(p.requires_grad for _, p in named) or
+                                              (utt_text is not None and utt_text.requires_grad))
     if needs_grad:
         names = tuple(n for n, _ in named)
-        res = _MisaFunction.apply(model, sentences, visual, acoustic, lengths, names,
+        res = _MisaFunction.apply(model, sentences, visual, acoustic, lengths, names, utt_text,
                                   *[p for _, p in named])
         out = dict(zip(_DIFF_OUT, res[:-1]))
         out["labels"] = res[-1]
         return out
-    o = eng.forward(sentences, visual, acoustic, lengths, train=False, want_sp=True)
+    o = eng.forward(sentences, visual, acoustic, lengths, train=False, want_sp=True,
+                    utt_text=utt_text)
     out = {n: o[n].clone() for n in _DIFF_OUT}
     out["labels"] = o["labels"].clone()
     return out

@@ -145,6 +145,8 @@ class MISA(nn.Module):
         skip = ["sp_discriminator."]
         if not getattr(self.config, "use_confidNet", False):
             skip.append("confidence.")
+        if getattr(self.config, "use_bert", False):
+            skip += ["tlayer_norm.", "bertmodel.pooler."]
         return [n for n, _ in self.named_parameters() if any(n.startswith(s) for s in skip)]
 
     # -- reference src/models.py:282-285 -----------------------------------------------------

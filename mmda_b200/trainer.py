@@ -76,6 +76,10 @@ class FusedTrainer:
                  global_batch_stats: bool = True, use_graph: Optional[bool] = None):
         self.model = model
         self.cfg = cfg = model.config
+        if getattr(cfg, "use_bert", False):
+            raise NotImplementedError(
+                "the fused level-2 step covers the LSTM text encoder; with use_bert=True use the "
+                "level-1 drop-in (model(...) + the reference Solver loop), SURVEY.md 8f N1")
         self.eng = model.engine
         self.lr = float(cfg.learning_rate if lr is None else lr)
         self.clip = float(cfg.clip)

@@ -159,3 +159,34 @@ def test_engine_kernel_sequence_level1_and_level2(dryrun):
     for n, p in model.named_parameters():
         off, sz = tr.layout[n]
         assert p.data_ptr() == tr.p_arena[off:].data_ptr()
+
+
+def test_metrics_from_stats_matches_reference_definitions():
+    """Host-side finalisation of the device metric counters vs the reference's formulas
+    (src/utils/eval.py:14-65: get_accuracy loop restated, sklearn precision/recall/F1)."""
+    import numpy as np
+    from sklearn import metrics as M
+    from mmda_b200.evaluate import metrics_from_stats
+    rng = np.random.default_rng(0)
+    y = (rng.random((300, 6)) < 0.3).astype(np.float32)
+    p = (rng.random((300, 6)) < 0.35).astype(np.float32)
+    y[:, 5] = 0                      # a class with no positives: zero-division paths
+    NC = 6
+    both, anyv = (y * p).sum(1), np.maximum(((y + p) > 0).sum(1), 1)
+    stats = [float((both / anyv).sum()), 300.0, 12.5, 5.0]
+    stats += [float(((y > 0) & (p > 0))[:, c].sum()) for c in range(NC)]
+    stats += [float(((y == 0) & (p > 0))[:, c].sum()) for c in range(NC)]
+    stats += [float(((y > 0) & (p == 0))[:, c].sum()) for c in range(NC)]
+    got = metrics_from_stats(stats, NC)
+    # reference get_accuracy
+    count = 0.0
+    for i in range(300):
+        t = sum(1 for j in range(6) if y[i][j] > 0 and p[i][j] > 0)
+        a = sum(1 for j in range(6) if y[i][j] > 0 or p[i][j] > 0) or 1
+        count += t / a
+    assert got["acc"] == round(count / 300, 4)
+    assert got["loss"] == 2.5
+    for avg, pre in (("macro", ""), ("micro", "micro_"), ("weighted", "weighted_")):
+        assert abs(got[pre + "f1"] - M.f1_score(y, p, average=avg, zero_division=0)) < 1e-9
+        assert abs(got[pre + "precision"] - M.precision_score(y, p, average=avg, zero_division=0)) < 1e-9
+        assert abs(got[pre + "recall"] - M.recall_score(y, p, average=avg, zero_division=0)) < 1e-9

@@ -527,3 +527,89 @@ def test_cuda_graph_replay_equals_eager(dev):
     C.add("losses over 7 steps", res[True][0], res[False][0], 1e-5)
     C.add("parameters after 7 steps", res[True][1], res[False][1], 1e-5)
     C.finish()
+
+
+def test_long_ragged_sequences_t130(dev):
+    """Sequence-length sweep (BASELINE configs[4]): T=130, ragged + shuffled lengths."""
+    from mmda_b200 import config as Cfg
+    from mmda_b200.synthetic import batch_for
+    from oracle.misa_oracle import oracle_build
+    cfg = Cfg.mosi_config(vocab_size=500, batch_size=24)
+    state = {k: v.clone() for k, v in oracle_build(cfg, 77).state_dict().items()}
+    batch = batch_for(cfg, seed=78, lengths="shuffled", seq_len=130)
+    _model_checks("t130_shuffled", cfg, state, batch, dev, None)
+
+
+def test_eval_pass_metrics_on_device(dev):
+    """Solver.eval (src/solver.py:311-370) on the device: forward-only, cls loss, metrics."""
+    import numpy as np
+    from mmda_b200 import MISA, mosei_config
+    from mmda_b200.evaluate import evaluate
+    from mmda_b200.synthetic import batch_for
+    from oracle.misa_oracle import OracleMISA, oracle_losses
+    cfg = mosei_config(vocab_size=400, batch_size=40, threshold=0.5)
+    torch.manual_seed(11)
+    model = MISA(cfg)
+    state = {k: v.clone() for k, v in model.state_dict().items()}
+    model = model.to(dev)
+    batches = [batch_for(cfg, seed=60 + i, lengths="ragged", seq_len=15) for i in range(3)]
+    got = evaluate(model, batches)
+    ref = OracleMISA(cfg); ref.load_state_dict(state); ref.eval()
+    ys, ps, losses = [], [], []
+    with torch.no_grad():
+        for b in batches:
+            out = ref(*b.model_args())
+            losses.append(float(oracle_losses(out, b.labels, cfg)["cls"]))
+            ys.append(b.labels.numpy()); ps.append(out["labels"].numpy())
+    y, p = np.concatenate(ys), np.concatenate(ps)
+    from sklearn import metrics as M
+    jac = np.mean((y * p).sum(1) / np.maximum(((y + p) > 0).sum(1), 1))
+    assert abs(got["loss"] - np.mean(losses)) < 1e-5 * np.mean(losses)
+    assert abs(got["acc"] - round(float(jac), 4)) <= 1e-4
+    assert abs(got["f1"] - M.f1_score(y, p, average="macro", zero_division=0)) < 1e-6
+    assert abs(got["micro_precision"] - M.precision_score(y, p, average="micro", zero_division=0)) < 1e-6
+    assert abs(got["weighted_recall"] - M.recall_score(y, p, average="weighted", zero_division=0)) < 1e-6
+
+
+def test_bert_text_branch_level1(dev):
+    """use_bert=True (BASELINE configs[3] / SURVEY 8f N1): HF BertModel (random-init bert-base,
+    library kernels) feeds the hand-written heads; level-1 contract incl. the gradient handed
+    back into BERT and the reference's layer freezing (solver.py:69-73)."""
+    from mmda_b200 import MISA, mosei_config
+    from mmda_b200.synthetic import batch_for
+    from oracle.misa_oracle import oracle_build, oracle_step
+    cfg = mosei_config(vocab_size=100, batch_size=6, use_bert=True)
+    ref = oracle_build(cfg, 21).eval()
+    state = {k: v.clone() for k, v in ref.state_dict().items()}
+    batch = batch_for(cfg, seed=22, lengths="ragged", seq_len=9)
+    out_r, L_r, g_r = oracle_step(ref, batch, cfg, None)
+    model = MISA(cfg)
+    model.load_state_dict(state)
+    for n, p in model.named_parameters():
+        if "bertmodel.encoder.layer" in n and int(n.split("encoder.layer.")[-1].split(".")[0]) <= 8:
+            p.requires_grad = False
+    model = model.to(dev).eval()
+    from oracle.misa_oracle import oracle_losses
+    scores, labels = model(batch.sentences.to(dev), batch.visual.to(dev), batch.acoustic.to(dev),
+                           batch.lengths, batch.bert_sent.to(dev), batch.bert_sent_type.to(dev),
+                           batch.bert_sent_mask.to(dev))
+    out = {k: getattr(model, k) for k in model.OUTPUT_ATTRS}
+    out["scores"], out["labels"] = scores, labels
+    L = oracle_losses(out, batch.labels.to(dev), cfg)
+    L["total"].backward()
+    C = Checks("bert_l1")
+    C.add("scores", scores, out_r["scores"].detach(), 2e-5)
+    for a in ("utt_t_orig", "utt_shared_t", "utt_private_a", "utt_t_recon", "tcp"):
+        C.add(a, out[a], out_r[a].detach(), 2e-5)
+    for kk in ("cls", "diff", "recon", "sim", "conf", "total"):
+        C.add("loss " + kk, L[kk], L_r[kk].detach(), 2e-5)
+    for n, p in model.named_parameters():
+        if g_r[n] is None:
+            C.flag("grad None " + n, p.grad is None)
+        elif n.startswith("bertmodel.") and (
+                "key.bias" in n      # exactly 0 in exact arithmetic (softmax shift invariance): pure noise
+                or not any(t in n for t in ("layer.11.", "layer.9.attention.self.query", "word_embeddings"))):
+            continue
+        else:
+            C.add("grad " + n, p.grad, g_r[n], 1e-4)
+    C.finish()
