@@ -613,3 +613,17 @@ def test_bert_text_branch_level1(dev):
         else:
             C.add("grad " + n, p.grad, g_r[n], 1e-4)
     C.finish()
+
+
+@pytest.mark.parametrize("sizes,B,T", [((160, 128, 200), 9, 6), ((96, 33, 260), 41, 5), ((300, 1, 2), 2, 3)])
+def test_other_recurrence_plans(dev, sizes, B, T):
+    """Hidden sizes that exercise the other cluster plans of the recurrence kernels (cluster of
+    2 / 4 CTAs, 8- and 32-row tiles, tcgen05 and SIMT GEMM routing, tiny batch; B=1 is degenerate in the reference itself: CMD of a single sample differentiates sqrt at 0)."""
+    from mmda_b200.config import MisaConfig
+    from mmda_b200.synthetic import batch_for
+    from oracle.misa_oracle import oracle_build
+    cfg = MisaConfig(embedding_size=sizes[0], visual_size=sizes[1], acoustic_size=sizes[2],
+                     hidden_size=32, vocab_size=60, batch_size=B, use_confidNet=True)
+    state = {k: v.clone() for k, v in oracle_build(cfg, 5).state_dict().items()}
+    batch = batch_for(cfg, seed=6, lengths="shuffled", seq_len=T)
+    _model_checks(f"plans_{sizes[0]}_{sizes[1]}_{sizes[2]}", cfg, state, batch, dev, None)
