@@ -157,7 +157,7 @@ int mmda_attention_backward(const float* qkv, const float* probs, const float* d
 
 /* ---- fused losses forward + backward, src/solver.py:163-181,373-462 (see csrc/loss.cu) ------
  * X0 (B,6,d) tokens [p_t,p_v,p_a,s_t,s_v,s_a]; O,R (3,B,d); scores,tcp,y (B,NC).
- * segA: 6*d + 6*NC + 3 floats; segB: 12*d + 6*d*d; segC: 6*d.  Bg = GLOBAL batch size. */
+ * segA: 6*d + 6*NC + 4 floats; segB: 12*d + 6*d*d; segC: 6*d.  Bg = GLOBAL batch size. */
 int mmda_loss_phase1(const float* X0, const float* O, const float* R, const float* scores,
                      const float* tcp, const float* y, float* segA, int B, int d, int NC,
                      mmda_stream_t stream);
@@ -166,7 +166,12 @@ int mmda_loss_phase2(const float* X0, const float* segA, float* XN, float* inv_n
 /* losses[6] = {cls, diff, sim, recon, conf, total}; coef (3,5,d) */
 int mmda_loss_finalize(const float* segA, const float* segB, float* losses, float* coef, int d,
                        int NC, float Bg, float w_diff, float w_sim, float w_recon, float w_conf,
-                       mmda_stream_t stream);
+                       int adversarial, mmda_stream_t stream);
+/* use_cmd_sim=False: domain cross-entropy of the adversarial discriminator, src/solver.py:388-407.
+ * domain_logits (3,B,3) = [pred_t; pred_v; pred_a]; writes the batch sum into segA[6d+6NC+3] (read by
+ * mmda_loss_finalize(adversarial=1)) and d(loss)/d(logits) scaled by w_sim/(3*Bg). */
+int mmda_loss_domain(const float* domain_logits, float* d_domain_logits, float* segA, int B, int d,
+                     int NC, float Bg, float w_sim, mmda_stream_t stream);
 int mmda_loss_phase4a(float* DXN, const float* inv_norm, float* colsum2, int B, int d,
                       mmda_stream_t stream);
 int mmda_loss_phase4b(const float* X0, const float* DXN, const float* segA, const float* segB,

@@ -148,7 +148,7 @@ loss_phase2_kernel(const float* __restrict__ X0, const float* __restrict__ segA,
 __global__ void __launch_bounds__(256)
 loss_finalize_kernel(const float* __restrict__ segA, const float* __restrict__ segB,
                      float* __restrict__ losses, float* __restrict__ coef, int d, int NC, float Bg,
-                     float w_diff, float w_sim, float w_recon, float w_conf) {
+                     float w_diff, float w_sim, float w_recon, float w_conf, int adversarial) {
   __shared__ float red[8];
   const int tid = threadIdx.x;
   const float* colsum = segA;
@@ -196,6 +196,9 @@ loss_finalize_kernel(const float* __restrict__ segA, const float* __restrict__ s
       l_conf += (-cls[2 * NC + c] + cls[3 * NC + c] * logf(cls[5 * NC + c])) / nnz;
     }
     const float recon = (cls[6 * NC + 0] + cls[6 * NC + 1] + cls[6 * NC + 2]) / (Bg * d) / 3.f;
+    // use_cmd_sim=False (solver.py:170-173): the similarity loss is the domain cross-entropy,
+    // whose batch sum loss_domain_kernel left in segA[6d + 6NC + 3]
+    if (adversarial) cmd = cls[6 * NC + 3] / (3.f * Bg);
     float total = l_cls + w_diff * diff + w_sim * cmd + w_recon * recon;
     if (w_conf != 0.f) total += w_conf * l_conf;
     losses[0] = l_cls; losses[1] = diff; losses[2] = cmd; losses[3] = recon; losses[4] = l_conf;
@@ -306,7 +309,40 @@ __global__ void loss_grad_misc_kernel(const float* __restrict__ scores,
   }
 }
 
+// Domain loss of the adversarial branch (solver.py:388-407): CrossEntropy over the 3B rows
+// [pred_t; pred_v; pred_a] with labels 0/1/2, mean reduction.  Writes the local batch SUM of the
+// row losses (all-reducible) and the gradient wrt the logits already scaled by w_sim/(3*Bg).
+__global__ void __launch_bounds__(256)
+loss_domain_kernel(const float* __restrict__ DL, float* __restrict__ dDL,
+                   float* __restrict__ dom_sum, int B, float Bg, float w_sim) {
+  __shared__ float red[8];
+  float acc = 0.f;
+  for (int idx = threadIdx.x; idx < 3 * B; idx += 256) {
+    const int m = idx / B;
+    const float* l = DL + (size_t)idx * 3;
+    const float mx = fmaxf(l[0], fmaxf(l[1], l[2]));
+    const float e0 = expf(l[0] - mx), e1 = expf(l[1] - mx), e2 = expf(l[2] - mx);
+    const float se = e0 + e1 + e2, lse = mx + logf(se);
+    acc += lse - l[m];
+    const float k = w_sim / (3.f * Bg);
+    float* g = dDL + (size_t)idx * 3;
+    g[0] = k * (e0 / se - (m == 0 ? 1.f : 0.f));
+    g[1] = k * (e1 / se - (m == 1 ? 1.f : 0.f));
+    g[2] = k * (e2 / se - (m == 2 ? 1.f : 0.f));
+  }
+  acc = block_sum_256(acc, red);
+  if (threadIdx.x == 0) *dom_sum = acc;
+}
+
 extern "C" {
+
+int mmda_loss_domain(const float* domain_logits, float* d_domain_logits, float* segA, int B, int d,
+                     int NC, float Bg, float w_sim, cudaStream_t stream) {
+  loss_domain_kernel<<<1, 256, 0, stream>>>(domain_logits, d_domain_logits,
+                                            segA + NTOK * d + 6 * NC + 3, B, Bg, w_sim);
+  MMDA_CHECK_LAUNCH();
+  return MMDA_OK;
+}
 
 int mmda_loss_phase1(const float* X0, const float* O, const float* R, const float* scores,
                      const float* tcp, const float* y, float* segA, int B, int d, int NC,
@@ -331,9 +367,9 @@ int mmda_loss_phase2(const float* X0, const float* segA, float* XN, float* inv_n
 
 int mmda_loss_finalize(const float* segA, const float* segB, float* losses, float* coef, int d,
                        int NC, float Bg, float w_diff, float w_sim, float w_recon, float w_conf,
-                       cudaStream_t stream) {
+                       int adversarial, cudaStream_t stream) {
   loss_finalize_kernel<<<1, 256, 0, stream>>>(segA, segB, losses, coef, d, NC, Bg, w_diff, w_sim,
-                                              w_recon, w_conf);
+                                              w_recon, w_conf, adversarial);
   MMDA_CHECK_LAUNCH();
   return MMDA_OK;
 }

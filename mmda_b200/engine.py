@@ -147,6 +147,9 @@ class MisaEngine:
         # use_bert=True: the BERT encoder itself stays the HF / PyTorch module
         # (library kernels); its masked-mean output feeds the hand-written heads / fusion / losses
         # through `utt_text`, and the gradient wrt that tensor is handed back to autograd.
+        self.adversarial = not bool(getattr(self.cfg, "use_cmd_sim", True))
+        self.diff_out = _DIFF_OUT + (tuple(f"domain_label_{m}" for m in MODS) if self.adversarial
+                                     else ())
         self.use_bert = bool(self.cfg.use_bert)
         self.utt_dim = {m: 4 * self.H[m] for m in MODS}
         if self.use_bert:
@@ -441,6 +444,24 @@ class MisaEngine:
 
         self._fork({m: head_fwd(i, m) for i, m in enumerate(MODS)})
         out = {}
+        if self.adversarial:
+            # models.py:219-227: domain_label_m = discriminator(GradReverse(utt_shared_m)); the
+            # reversal only matters in the backward
+            DHp = self.buf("DHpre", 3, B, d)      # activation output (pre-dropout)
+            DH = self.buf("DH", 3, B, d)
+            DL = self.buf("DL", 3, B, 3)
+            for i, m in enumerate(MODS):
+                k.linear(X0f[:, (3 + i) * d:(4 + i) * d],
+                         P["discriminator.discriminator_layer_1.weight"],
+                         P["discriminator.discriminator_layer_1.bias"], DHp[i], act=self.act_id)
+                if p_cls > 0:
+                    k.dropout(DHp[i], DH[i], p_cls, seed, 6 + i, seed_dev)
+                else:
+                    k.add(DH[i], DHp[i])
+                k.linear(DH[i], P["discriminator.discriminator_layer_2.weight"],
+                         P["discriminator.discriminator_layer_2.bias"], DL[i])
+                out[f"domain_label_{m}"] = DL[i]
+            out["domain"] = DL
         if want_sp:        # outputs no loss reads (src/models.py:234-237); kept for the contract
             SP = self.buf("SP", 4, B, 4)
             smean = self.buf("smean", B, d)
@@ -513,7 +534,7 @@ class MisaEngine:
 
     # ---------------------------------------------------------------- backward -------------
     def backward(self, G: Dict[str, torch.Tensor], d_scores=None, d_tcp=None, d_tokens=None,
-                 d_orig=None, d_recon=None, d_sp=None, on_ready=None):
+                 d_orig=None, d_recon=None, d_sp=None, d_domain=None, on_ready=None):
         """Accumulates parameter gradients into ``G[name]`` (tensors shaped like the parameters).
 
         d_scores, d_tcp (B,NC); d_tokens (B,6,d) grad wrt [p_t,p_v,p_a,s_t,s_v,s_a]; d_orig,
@@ -609,6 +630,26 @@ class MisaEngine:
         else:
             dX0.zero_()
         notify("fusion")
+
+        # ---- adversarial discriminator + gradient reversal (functions.py:9-21) ----
+        if d_domain is not None:
+            DHp, DH = self.buf("DHpre", 3, B, d), self.buf("DH", 3, B, d)
+            w1, w2 = (P["discriminator.discriminator_layer_1.weight"],
+                      P["discriminator.discriminator_layer_2.weight"])
+            lam = float(self.cfg.reverse_grad_weight)
+            for i in range(3):
+                dDH = self.buf("dDH", B, d)
+                k.linear_bwd(d_domain[i], DH[i], w2, G["discriminator.discriminator_layer_2.weight"],
+                             G["discriminator.discriminator_layer_2.bias"], dDH, 0.0)
+                if p_cls > 0:
+                    k.dropout(dDH, dDH, p_cls, seed, 6 + i, seed_dev)
+                k.act_bwd(dDH, DHp[i], self.act_id)
+                dS = self.buf("dSdom", B, d)
+                k.linear_bwd(dDH, X0f[:, (3 + i) * d:(4 + i) * d], w1,
+                             G["discriminator.discriminator_layer_1.weight"],
+                             G["discriminator.discriminator_layer_1.bias"], dS, 0.0)
+                sl = dX0f[:, (3 + i) * d:(4 + i) * d]
+                k.add(sl, sl, dS, 1.0, -lam)
 
         # ---- sp discriminator (only if somebody asked for its gradient) ----
         if d_sp is not None:
@@ -792,7 +833,7 @@ class _MisaFunction(torch.autograd.Function):
                           utt_text=utt_text)
         ctx.model, ctx.names, ctx.fwd_step = model, names, eng.step_id
         ctx.set_materialize_grads(False)      # unused outputs arrive as None, not zeros
-        res = tuple(out[n].clone() for n in _DIFF_OUT) + (out["labels"].clone(),)
+        res = tuple(out[n].clone() for n in eng.diff_out) + (out["labels"].clone(),)
         ctx.mark_non_differentiable(res[-1])
         return res
 
@@ -802,7 +843,7 @@ class _MisaFunction(torch.autograd.Function):
         if eng.step_id != ctx.fwd_step:
             raise MmdaError("backward() after a newer forward(): the engine keeps one step of "
                             "saved activations")
-        gd = dict(zip(_DIFF_OUT, g[:-1]))
+        gd = dict(zip(eng.diff_out, g[:-1]))
         dev, d = eng.device, eng.d
         B = eng.saved["B"]
 
@@ -839,8 +880,9 @@ class _MisaFunction(torch.autograd.Function):
         for n, sz in zip(ctx.names, sizes):
             G[n] = arena[off:off + sz].view(P[n].shape)
             off += sz
+        d_dom = stack([f"domain_label_{m}" for m in MODS], (3, B, 3)) if eng.adversarial else None
         d_utt = eng.backward(G, d_scores=ds, d_tcp=dt, d_tokens=d_tok, d_orig=d_orig,
-                             d_recon=d_recon, d_sp=d_sp)
+                             d_recon=d_recon, d_sp=d_sp, d_domain=d_dom)
         if d_utt is not None:
             d_utt = d_utt.clone()
         untouched = set()
@@ -850,6 +892,8 @@ class _MisaFunction(torch.autograd.Function):
             untouched.add("confidence.")
         if eng.use_bert:
             untouched.add("tlayer_norm.")     # exists in the module but no text LSTM runs
+        if eng.adversarial and d_dom is None:
+            untouched.add("discriminator.")
         grads = tuple(None if any(n.startswith(u) for u in untouched) else G[n] for n in ctx.names)
         return (None,) * 6 + (d_utt,) + grads
 
@@ -877,11 +921,11 @@ def misa_apply(model, sentences, visual, acoustic, lengths, bert_sent, bert_sent
         names = tuple(n for n, _ in named)
         res = _MisaFunction.apply(model, sentences, visual, acoustic, lengths, names, utt_text,
                                   *[p for _, p in named])
-        out = dict(zip(_DIFF_OUT, res[:-1]))
+        out = dict(zip(eng.diff_out, res[:-1]))
         out["labels"] = res[-1]
         return out
     o = eng.forward(sentences, visual, acoustic, lengths, train=False, want_sp=True,
                     utt_text=utt_text)
-    out = {n: o[n].clone() for n in _DIFF_OUT}
+    out = {n: o[n].clone() for n in eng.diff_out}
     out["labels"] = o["labels"].clone()
     return out

@@ -79,9 +79,6 @@ class MISA(nn.Module):
                                       "(src/models.py:33-36)")
         if getattr(config, "rnncell", "lstm") != "lstm":
             raise NotImplementedError("GRU cells are outside this round's scope (SURVEY.md 8f N4)")
-        if not getattr(config, "use_cmd_sim", True):
-            raise NotImplementedError("the adversarial discriminator branch (use_cmd_sim=False) is "
-                                      "outside this round's scope (SURVEY.md 8f N4)")
         if d % 2:
             raise ValueError("hidden_size must be even (2 attention heads)")
 
@@ -112,6 +109,12 @@ class MISA(nn.Module):
         self.shared = _named_seq(shared_1=nn.Linear(d, d), shared_activation_1=nn.Sigmoid())
         for m in MODS:
             setattr(self, f"recon_{m}", _named_seq(**{f"recon_{m}_1": nn.Linear(d, d)}))
+        if not getattr(config, "use_cmd_sim", True):      # adversarial branch, models.py:122-127
+            self.discriminator = _named_seq(
+                discriminator_layer_1=nn.Linear(d, d),
+                discriminator_layer_1_activation=act_mod,
+                discriminator_layer_1_dropout=nn.Dropout(config.dropout),
+                discriminator_layer_2=nn.Linear(d, len(self.hidden_sizes)))
         self.sp_discriminator = _named_seq(sp_discriminator_layer_1=nn.Linear(d, 4))
         self.confidence = _named_seq(confidence_layer_1=nn.Linear(6 * d, 6),
                                      confidence_layer_activation=nn.Sigmoid())
@@ -157,4 +160,6 @@ class MISA(nn.Module):
                          bert_sent_mask)
         for k in self.OUTPUT_ATTRS:
             object.__setattr__(self, k, out[k])
+        for m in MODS:      # models.py:219-231
+            object.__setattr__(self, f"domain_label_{m}", out.get(f"domain_label_{m}"))
         return out["scores"], out["labels"]

@@ -30,7 +30,7 @@ def bucket_of(name: str) -> int:
     2 visual encoder, 3 acoustic encoder, 4 text encoder + embedding, 5 never (no gradient)."""
     if name.startswith(("transformer_encoder.", "classifier.", "confidence.")):
         return 0
-    if name.startswith(("project_", "private_", "shared.", "recon_")):
+    if name.startswith(("project_", "private_", "shared.", "recon_", "discriminator.")):
         return 1
     if name.startswith(("vrnn", "vlayer_norm")):
         return 2
@@ -160,7 +160,7 @@ class FusedTrainer:
     # ------------------------------------------------------------------ losses -------------
     def _loss_buffers(self, B):
         d, NC = self.eng.d, self.eng.NC
-        nA, nB, nC = 6 * d + 6 * NC + 3, 12 * d + 6 * d * d, 6 * d
+        nA, nB, nC = 6 * d + 6 * NC + 4, 12 * d + 6 * d * d, 6 * d
         pad = lambda n: (n + 3) // 4 * 4
         tot = pad(nA) + pad(nB) + pad(nC) + 8 + 15 * d
         st = self.eng.buf("loss_stats", tot)
@@ -186,6 +186,13 @@ class FusedTrainer:
         w_conf = float(cfg.conf_weight) if self.use_confid else 0.0
         k._c("mmda_loss_phase1", _ptr(X0), _ptr(O), _ptr(R), _ptr(SC), _ptr(TCP), _ptr(y),
              _ptr(segA), B, d, NC)
+        adv = eng.adversarial
+        w_sim = 0.0 if adv else float(cfg.sim_weight)     # CMD part off in the adversarial variant
+        dDL = None
+        if adv:
+            dDL = eng.buf("dDL", 3, B, 3)
+            k._c("mmda_loss_domain", _ptr(out["domain"]), _ptr(dDL), _ptr(segA), B, d, NC, Bg,
+                 float(cfg.sim_weight))
         if sync:
             self._allreduce(segA)
         XN = eng.buf("XN", 6, B, d)
@@ -197,7 +204,8 @@ class FusedTrainer:
         if sync:
             self._allreduce(segB)
         k._c("mmda_loss_finalize", _ptr(segA), _ptr(segB), _ptr(losses), _ptr(coef), d, NC, Bg,
-             float(cfg.diff_weight), float(cfg.sim_weight), float(cfg.recon_weight), w_conf)
+             float(cfg.diff_weight), float(cfg.sim_weight), float(cfg.recon_weight), w_conf,
+             int(adv))
         DXN = eng.buf("DXN", 6, B, d)
         DXN.zero_()
         alpha = float(cfg.diff_weight) * 2.0 / float(d * d)
@@ -209,14 +217,14 @@ class FusedTrainer:
             self._allreduce(segC)
         dZ = eng.buf("dZ", B, 6, d)
         k._c("mmda_loss_phase4b", _ptr(X0), _ptr(DXN), _ptr(segA), _ptr(segB), _ptr(segC),
-             _ptr(coef), _ptr(dZ), B, d, Bg, float(cfg.sim_weight), 0)
+             _ptr(coef), _ptr(dZ), B, d, Bg, w_sim, 0)
         dSC, dTCP = eng.buf("dSCORES", B, NC), eng.buf("dTCP", B, NC)
         dR, dO = eng.buf("dR", 3, B, d), eng.buf("dOrig", 3, B, d)
         k._c("mmda_loss_grad_misc", _ptr(SC), _ptr(TCP), _ptr(y), _ptr(O), _ptr(R), _ptr(segA),
              _ptr(dSC), _ptr(dTCP), _ptr(dR), _ptr(dO), B, d, NC, Bg, float(cfg.recon_weight),
              w_conf)
         return losses, dict(d_scores=dSC, d_tcp=dTCP if self.use_confid else None, d_tokens=dZ,
-                            d_orig=dO, d_recon=dR)
+                            d_orig=dO, d_recon=dR, d_domain=dDL)
 
     # ------------------------------------------------------------------ step ---------------
     def _on_ready(self, tag):

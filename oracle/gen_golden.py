@@ -47,7 +47,8 @@ def build_reference(ref_solver, ref_config, cfg, seed):
     rc = ref_config.get_config(parse=False, use_bert=False, data=cfg.data,
                                use_confidNet=cfg.use_confidNet, batch_size=cfg.batch_size,
                                embedding_size=cfg.embedding_size, hidden_size=cfg.hidden_size,
-                               dropout=cfg.dropout, learning_rate=cfg.learning_rate)
+                               dropout=cfg.dropout, learning_rate=cfg.learning_rate,
+                               use_cmd_sim=cfg.use_cmd_sim)
     rc.visual_size, rc.acoustic_size = cfg.visual_size, cfg.acoustic_size
     rc.word2id = {i: i for i in range(cfg.vocab_size)}
     rc.pretrained_emb = None
@@ -77,7 +78,9 @@ def reference_step(s, rc, batch, do_step=True):
     scores, labels = m(*batch.model_args())
     y = batch.labels.type(torch.float)
     L = {"cls": s.get_cls_loss(scores, y), "diff": s.get_diff_loss(),
-         "recon": s.get_recon_loss(), "sim": s.get_cmd_loss(), "conf": s.get_conf_loss(scores, y)}
+         "recon": s.get_recon_loss(),
+         "sim": s.get_cmd_loss() if rc.use_cmd_sim else s.get_domain_loss(),   # solver.py:170-173
+         "conf": s.get_conf_loss(scores, y)}
     loss = L["cls"] + rc.diff_weight * L["diff"] + rc.sim_weight * L["sim"] + \
         rc.recon_weight * L["recon"]
     if rc.use_confidNet:
@@ -98,12 +101,13 @@ ATTRS = ["utt_t_orig", "utt_v_orig", "utt_a_orig", "utt_private_t", "utt_private
          "shared_or_private_p_a", "shared_or_private_s"]
 
 
-def gen_small(ref_solver, ref_config, name, seed, confid, lengths_mode):
+def gen_small(ref_solver, ref_config, name, seed, confid, lengths_mode, use_cmd_sim=True):
     import torch
     from mmda_b200.config import MisaConfig
     from mmda_b200.synthetic import batch_for
     cfg = MisaConfig(embedding_size=12, visual_size=5, acoustic_size=7, hidden_size=16,
-                     vocab_size=50, batch_size=6, use_confidNet=confid, dropout=0.1)
+                     vocab_size=50, batch_size=6, use_confidNet=confid, dropout=0.1,
+                     use_cmd_sim=use_cmd_sim)
     s, rc = build_reference(ref_solver, ref_config, cfg, seed)
     s.model.eval()                                   # deterministic parity mode
     batch = batch_for(cfg, seed=seed + 1, lengths=lengths_mode, seq_len=7)
@@ -119,7 +123,7 @@ def gen_small(ref_solver, ref_config, name, seed, confid, lengths_mode):
             arrs["grad/" + n] = g.numpy()
     for n, p in s.model.named_parameters():
         arrs["after/" + n] = p.detach().numpy()
-    for a in ATTRS:
+    for a in ATTRS + ([] if use_cmd_sim else ["domain_label_t", "domain_label_v", "domain_label_a"]):
         arrs["out/" + a] = getattr(s.model, a).detach().numpy()
     arrs["out/scores"] = scores.detach().numpy()
     arrs["out/labels"] = labels.detach().numpy()
@@ -131,7 +135,7 @@ def gen_small(ref_solver, ref_config, name, seed, confid, lengths_mode):
     arrs["pack/sorted_indices"] = packed.sorted_indices.numpy()
     arrs["pack/unsorted_indices"] = packed.unsorted_indices.numpy()
     arrs["pack/data"] = packed.data.numpy()
-    meta = {"seed": seed, "use_confidNet": confid, "lengths": lengths_mode,
+    meta = {"seed": seed, "use_confidNet": confid, "lengths": lengths_mode, "use_cmd_sim": use_cmd_sim,
             "none_grads": sorted(n for n, g in grads.items() if g is None),
             "cfg": {"embedding_size": 12, "visual_size": 5, "acoustic_size": 7,
                     "hidden_size": 16, "vocab_size": 50, "batch_size": 6, "seq_len": 7}}
@@ -170,8 +174,13 @@ def gen_summary(ref_solver, ref_config, name, cfg, seed, lengths_mode, steps=2):
 
 
 def main():
+    adv_only = "--adversarial-only" in sys.argv      # import_reference() sanitises argv
     ref_solver, ref_config = import_reference()
     from mmda_b200.config import mosi_config, mosei_config
+    if adv_only:
+        gen_small(ref_solver, ref_config, "small_adversarial", 31, False, "shuffled", use_cmd_sim=False)
+        return
+    gen_small(ref_solver, ref_config, "small_adversarial", 31, False, "shuffled", use_cmd_sim=False)
     gen_small(ref_solver, ref_config, "small_ragged", 11, False, "ragged")
     gen_small(ref_solver, ref_config, "small_shuffled_confid", 23, True, "shuffled")
     gen_summary(ref_solver, ref_config, "c1_mosi_b64", mosi_config(vocab_size=2000), 1234, "ragged")

@@ -209,7 +209,7 @@ def oracle_losses(out, y, cfg) -> Dict[str, torch.Tensor]:
     else:                                               # solver.py:388-407
         pred = torch.cat([out[f"domain_label_{m}"] for m in _MODS], 0)
         n = s.size(0)
-        true = torch.cat([torch.full((n,), i, dtype=torch.long) for i in range(3)], 0)
+        true = torch.cat([torch.full((n,), i, dtype=torch.long, device=pred.device) for i in range(3)], 0)
         L["sim"] = F.cross_entropy(pred, true)
     # solver.py:451-462 ; CrossEntropyLoss on 1-D float input+target == soft-label CE over batch axis
     tcp = out["tcp"]

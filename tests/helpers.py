@@ -19,7 +19,8 @@ def small_cfg(meta, **kw):
     from mmda_b200.config import MisaConfig
     c = dict(meta["cfg"])
     c.pop("seq_len")
-    return MisaConfig(use_confidNet=meta["use_confidNet"], **c, **kw)
+    return MisaConfig(use_confidNet=meta["use_confidNet"], use_cmd_sim=meta.get("use_cmd_sim", True),
+                      **c, **kw)
 
 
 def small_batch(z):

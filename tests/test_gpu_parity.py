@@ -218,6 +218,8 @@ def _oracle_pair(cfg, state, batch, masks=None):
                 lambda mod, i, o: align(o, masks["ffn"], "ffn-relu")))
             cnt = [0]
             def pre(mod, inp):
+                if cnt[0] >= 3:      # the same activation instance also serves the discriminator
+                    return None
                 i = cnt[0] % 3
                 cnt[0] += 1
                 return (align(inp[0], masks["proj"][i], f"proj-act[{i}]"),)
@@ -243,12 +245,15 @@ def _run_level1(model, batch, cfg, dev):
     model.zero_grad()
     scores, labels = model(*_to(batch, dev), None, None, None)
     out = {k: getattr(model, k) for k in model.OUTPUT_ATTRS}
+    if not cfg.use_cmd_sim:
+        out.update({a: getattr(model, a) for a in ("domain_label_t", "domain_label_v", "domain_label_a")})
     out["scores"], out["labels"] = scores, labels
     L = oracle_losses(out, batch.labels.to(dev), cfg)
     L["total"].backward()
     return out, L
 
 
+ADV_ATTRS = ("domain_label_t", "domain_label_v", "domain_label_a")
 ATTR_CHECK = ("utt_t_orig", "utt_v_orig", "utt_a_orig", "utt_private_t", "utt_private_v",
               "utt_private_a", "utt_shared_t", "utt_shared_v", "utt_shared_a", "utt_t_recon",
               "utt_v_recon", "utt_a_recon", "tcp", "shared_or_private_p_t", "shared_or_private_s")
@@ -274,7 +279,9 @@ def _model_checks(tag, cfg, state, batch, dev, golden=None):
     C.add("L1 scores", out["scores"], o64["scores"], ref32=o32["scores"])
     C.flag("L1 labels", torch.equal(out["labels"].cpu(), o32["labels"]) or
            float((o64["scores"] - cfg.threshold).abs().min()) < 1e-5)
-    for a in ATTR_CHECK:
+    if not cfg.use_cmd_sim:
+        out.update({a: getattr(model, a) for a in ADV_ATTRS})
+    for a in ATTR_CHECK + (() if cfg.use_cmd_sim else ADV_ATTRS):
         C.add("L1 " + a, out[a], o64[a], ref32=o32[a])
     for kk in ("cls", "diff", "recon", "sim", "conf", "total"):
         C.add("L1 loss " + kk, L[kk], L64[kk], ref32=L32[kk])
@@ -324,7 +331,7 @@ def _model_checks(tag, cfg, state, batch, dev, golden=None):
     C.finish()
 
 
-@pytest.mark.parametrize("name", ["small_ragged", "small_shuffled_confid"])
+@pytest.mark.parametrize("name", ["small_ragged", "small_shuffled_confid", "small_adversarial"])
 def test_small_fixture(dev, name):
     z, meta = load_small(name)
     cfg = small_cfg(meta)

@@ -12,7 +12,7 @@ from oracle.misa_oracle import (OracleMISA, oracle_build, oracle_losses, oracle_
                                 oracle_step)
 
 
-@pytest.mark.parametrize("name", ["small_ragged", "small_shuffled_confid"])
+@pytest.mark.parametrize("name", ["small_ragged", "small_shuffled_confid", "small_adversarial"])
 def test_small_fixture_full_tensors(name):
     z, meta = load_small(name)
     cfg = small_cfg(meta)
@@ -27,7 +27,7 @@ def test_small_fixture_full_tensors(name):
     np.testing.assert_allclose(out["scores"].detach().numpy(), z["out/scores"], rtol=0, atol=1e-6)
     np.testing.assert_array_equal(out["labels"].numpy(), z["out/labels"])
     for a in ("utt_t_orig", "utt_private_a", "utt_shared_v", "utt_a_recon", "tcp",
-              "shared_or_private_s"):
+              "shared_or_private_s") + (() if meta.get("use_cmd_sim", True) else ("domain_label_v",)):
         np.testing.assert_allclose(out[a].detach().numpy(), z["out/" + a], rtol=0, atol=1e-6)
     none = set(meta["none_grads"])
     for n, p in model.named_parameters():
