@@ -40,8 +40,8 @@ def test_config_activation_mapping_and_errors():
         activation_name(nn.PReLU)
     with pytest.raises(NotImplementedError):
         MISA(MisaConfig(vocab_size=10, rnncell="gru"))
-    with pytest.raises(NotImplementedError):
-        MISA(MisaConfig(vocab_size=10, use_cmd_sim=False))
+    adv = MISA(MisaConfig(vocab_size=10, use_cmd_sim=False))
+    assert "discriminator.discriminator_layer_2.weight" in adv.state_dict()
 
 
 def test_product_path_refuses_cpu():
