@@ -205,6 +205,26 @@ int mmda_step_state_init(void* state_dev, long long step, float beta1, float bet
 int mmda_step_state_advance(void* state_dev, float lr, float beta1, float beta2,
                             mmda_stream_t stream);
 
+/* ---- device-resident collate: collate_fn, src/data_loader.py:59-122, and the
+ * per-tensor to_gpu copies, src/utils/convert.py:4-11.  The split lives in HBM as ragged flat
+ * arrays (words (sumL,), visual (sumL,dv), acoustic (sumL,da), labels (n,n_label), offsets
+ * (n+1,)); `order` holds the batch's sample indices, already sorted by descending length on the
+ * host (the reference's stable sorted(..., reverse=True), data_loader.py:64); T = longest length.
+ * Outputs: sentences (T,B) padded with pad_id, visual (T,B,dv) / acoustic (T,B,da) zero padded,
+ * labels (B,), emo (B,6) = label[1:7] > 0, lengths (B,).  n_label must be 7 (the reference's
+ * collate raises for any other label width, data_loader.py:95-118). */
+int mmda_collate_batch(const long long* words, const float* visual, const float* acoustic,
+                       const float* labels, const long long* offsets, const long long* order,
+                       int B, int T, int dv, int da, int n_label, long long pad_id,
+                       long long* sentences, float* visual_out, float* acoustic_out,
+                       float* labels_out, float* emo_out, long long* lengths_out,
+                       mmda_stream_t stream);
+/* BERT fields from pre-tokenised word pieces (data_loader.py:84-85,113-115): per sample
+ * [cls] wp[:sent_len] [sep] pad..., token types 0, attention mask; all (B, sent_len+2) int64. */
+int mmda_collate_bert(const long long* wp_ids, const long long* wp_offsets, const long long* order,
+                      int B, int sent_len, long long cls_id, long long sep_id, long long pad_id,
+                      long long* ids, long long* types, long long* mask, mmda_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -3,6 +3,7 @@ TEST INFRASTRUCTURE.  Runs only in the build container (the GPU box has no /root
 the fixtures it writes are committed and are what the tests read.
 
     python oracle/gen_golden.py            # rewrites tests/golden/
+    python oracle/gen_golden.py --collate-only   # only tests/golden/collate_small.npz
 
 Recipe: put the reference on sys.path, sanitise argv, stub the packages
 that are absent offline (gensim, hypertune, mmsdk, wandb), neutralise the import-time
@@ -30,6 +31,7 @@ def import_reference():
     sys.path.insert(0, REF)
     for name in ("gensim", "hypertune", "mmsdk", "mmsdk.mmdatasdk", "wandb"):
         sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["mmsdk"].mmdatasdk = sys.modules["mmsdk.mmdatasdk"]
     sys.modules["hypertune"].HyperTune = lambda: None
     import transformers
     transformers.BertTokenizer.from_pretrained = classmethod(lambda cls, *a, **k: None)
@@ -173,9 +175,65 @@ def gen_summary(ref_solver, ref_config, name, cfg, seed, lengths_mode, steps=2):
         json.dump(rec, f)
 
 
+class _FakeTokenizer:
+    """Stand-in for bert-base-uncased's tokenizer (no network / vocab file offline): word pieces
+    from oracle.collate_oracle.wordpieces, then the encode_plus contract the reference relies on
+    (data_loader.py:84-85): specials added, truncated to max_length, padded to max_length."""
+
+    def encode_plus(self, text, max_length=None, add_special_tokens=True, pad_to_max_length=False):
+        from oracle.collate_oracle import BERT_PAD, CLS, SEP, wordpieces
+        wp = wordpieces(text.split(" "))[:max_length - 2]
+        ids = [CLS] + wp + [SEP]
+        n = len(ids)
+        ids = ids + [BERT_PAD] * (max_length - n)
+        return {"input_ids": ids, "token_type_ids": [0] * max_length,
+                "attention_mask": [1] * n + [0] * (max_length - n)}
+
+
+def gen_collate():
+    """Run the reference's own collate_fn (data_loader.py:59-122) on seeded ragged samples."""
+    import types as _types
+    import data_loader as ref_dl
+    from oracle.collate_oracle import make_samples
+    samples = make_samples(11, 5, 7, seed=77)
+
+    class FakeDataset:
+        def __init__(self, config):
+            self.data = samples
+        def __len__(self):
+            return len(self.data)
+
+    ref_dl.MSADataset = FakeDataset
+    ref_dl.DataLoader = lambda dataset, batch_size, shuffle, collate_fn: _types.SimpleNamespace(
+        collate_fn=collate_fn)
+    ref_dl.bert_tokenizer = _FakeTokenizer()
+    cfg = _types.SimpleNamespace(mode="train", batch_size=4)
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        loader = ref_dl.get_loader(cfg, shuffle=False)
+    arrs = {}
+    for bi, idx in enumerate([[0, 1, 2, 3, 4, 5, 6], [10, 3, 8, 7, 9, 2], [4]]):
+        out = loader.collate_fn([samples[i] for i in idx])
+        names = ["sentences", "visual", "acoustic", "labels", "emo_labels", "lengths",
+                 "bert_sentences", "bert_sentence_types", "bert_sentence_att_mask"]
+        arrs[f"b{bi}/index"] = np.array(idx, dtype=np.int64)
+        for n, t in zip(names, out[:9]):
+            arrs[f"b{bi}/{n}"] = t.numpy()
+        arrs[f"b{bi}/ids"] = np.array(out[9])
+    arrs["meta"] = np.frombuffer(json.dumps({"n": 11, "dv": 5, "da": 7, "seed": 77}).encode(),
+                                 dtype=np.uint8)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "collate_small.npz"), **arrs)
+    print("collate_small", {k: v.shape for k, v in arrs.items() if k.startswith("b1/")})
+
+
 def main():
     adv_only = "--adversarial-only" in sys.argv      # import_reference() sanitises argv
+    collate_only = "--collate-only" in sys.argv
     ref_solver, ref_config = import_reference()
+    if collate_only:
+        gen_collate()
+        return
     from mmda_b200.config import mosi_config, mosei_config
     if adv_only:
         gen_small(ref_solver, ref_config, "small_adversarial", 31, False, "shuffled", use_cmd_sim=False)
@@ -188,6 +246,7 @@ def main():
                 "full", steps=1)
     gen_summary(ref_solver, ref_config, "c3_mosei_confid_b256",
                 mosei_config(vocab_size=2000, use_confidNet=True), 4321, "ragged", steps=1)
+    gen_collate()
 
 
 if __name__ == "__main__":

@@ -74,3 +74,43 @@ def test_full_size_summary(name, cfgname, kw, lengths):
                 assert grads[n] is None, n
             else:
                 assert abs(float(grads[n].double().norm()) - g[2]) <= 1e-4 * max(g[2], 1e-12), n
+
+
+# ---- collate: oracle restatement vs the reference's own collate_fn -----------
+def test_collate_oracle_matches_reference_collate_fn():
+    from oracle.collate_oracle import collate, make_samples, wordpieces
+    z = np.load(os.path.join(GOLDEN, "collate_small.npz"), allow_pickle=False)
+    meta = json.loads(bytes(z["meta"]).decode())
+    samples = make_samples(meta["n"], meta["dv"], meta["da"], seed=meta["seed"])
+    for bi in range(3):
+        idx = z[f"b{bi}/index"]
+        out = collate([samples[i] for i in idx], wp_ids=lambda s: wordpieces(s[0][3]))
+        for k in ("sentences", "visual", "acoustic", "labels", "emo_labels", "lengths",
+                  "bert_sentences", "bert_sentence_types", "bert_sentence_att_mask"):
+            ref = z[f"b{bi}/{k}"]
+            assert out[k].shape == ref.shape and out[k].dtype == ref.dtype, (bi, k, out[k].dtype, ref.dtype)
+            assert np.array_equal(out[k], ref, equal_nan=True), (bi, k)
+        assert list(z[f"b{bi}/ids"]) == out["ids"]
+
+
+def test_collate_host_side_sort_flatten_and_errors():
+    from mmda_b200.collate import DeviceDataset, flatten_split
+    from oracle.collate_oracle import collate, make_samples
+    samples = make_samples(40, 3, 4, seed=5)
+    flat = flatten_split(samples)
+    assert flat["offsets"][-1] == flat["words"].shape[0] == flat["visual"].shape[0]
+    ds = DeviceDataset(samples, device="cpu")        # host logic only; collate() needs the GPU
+    idx = [7, 3, 11, 30, 2, 19, 5, 8, 21]
+    order = ds.sort_batch(idx)
+    ref = collate([samples[i] for i in idx])
+    assert [samples[i][2] for i in order] == ref["ids"]          # same stable descending sort
+    assert np.array_equal(ds.lengths[order], ref["lengths"])
+    with pytest.raises(ValueError):
+        ds.sort_batch([])
+    with pytest.raises(IndexError):
+        ds.sort_batch([0, 40])
+    mosi_like = [((s[0][0], s[0][1], s[0][2], s[0][3]), s[1][:, :1], s[2]) for s in samples]
+    with pytest.raises(TypeError):
+        DeviceDataset(mosi_like, device="cpu").collate([0, 1])
+    with pytest.raises(TypeError):
+        collate(mosi_like[:2])
