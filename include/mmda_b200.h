@@ -205,6 +205,28 @@ int mmda_step_state_init(void* state_dev, long long step, float beta1, float bet
 int mmda_step_state_advance(void* state_dev, float lr, float beta1, float beta2,
                             mmda_stream_t stream);
 
+/* ---- nn.GRU cells: rnn = nn.GRU when config.rnncell != 'lstm',
+ * src/models.py:39,168-169,177-178.  The recurrence kernels are shared with the LSTM: GRU
+ * parameters are expanded to a 4-slot layout -- W4_ih = [W_ir; W_iz; W_in; 0], W4_hh = [W_hr;
+ * W_hz; 0; W_hn], b4_ih = [b_ir; b_iz; b_in; 0], b4_hh = [b_hr; b_hz; 0; b_hn] -- so the hoisted
+ * GEMMs, mmda_lstm_pack_weights and the gate layout [N][2][H][4] apply unchanged, and the 4-slot
+ * gradients are folded back onto the (3H, .) parameters.  mmda_gru_backward takes the saved
+ * hidden states y where mmda_lstm_backward takes the cell states. */
+int mmda_gru_expand_weights(const float* w_ih, const float* w_hh, const float* b_ih,
+                            const float* b_hh, int H, int I, float* w4_ih, float* w4_hh,
+                            float* b4_ih, float* b4_hh, mmda_stream_t stream);
+int mmda_gru_fold_grads(const float* dw4_ih, const float* dw4_hh, const float* db4_ih,
+                        const float* db4_hh, int H, int I, float* dw_ih, float* dw_hh, float* db_ih,
+                        float* db_hh, mmda_stream_t stream);
+int mmda_gru_forward(float* gates, const float* whh4_f, const float* whh4_r, float* y,
+                     const int* lens_sorted, const int* sorted_idx, const int* offsets, float* utt,
+                     int utt_ld, int utt_off_f, int utt_off_r, int B, int H, int Tmax,
+                     int save_for_backward, mmda_stream_t stream);
+int mmda_gru_backward(float* gates, const float* whh4_f, const float* whh4_r, const float* y,
+                      const float* dy, const float* dutt, int utt_ld, int utt_off_f, int utt_off_r,
+                      const int* lens_sorted, const int* sorted_idx, const int* offsets,
+                      float* scratch, int B, int H, int Tmax, mmda_stream_t stream);
+
 /* ---- device-resident collate: collate_fn, src/data_loader.py:59-122, and the
  * per-tensor to_gpu copies, src/utils/convert.py:4-11.  The split lives in HBM as ragged flat
  * arrays (words (sumL,), visual (sumL,dv), acoustic (sumL,da), labels (n,n_label), offsets

@@ -70,7 +70,7 @@ __device__ __forceinline__ void reduce_scatter(float (&v)[N], int lane) {
 // ------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------
-template <int BT>
+template <int BT, int CELL>
 __global__ void __launch_bounds__(BT == 40 ? 800 : 640, 1) lstm_fwd_kernel(const LstmArgs p) {
   extern __shared__ __align__(16) float smem[];
   constexpr int BTP = BT + (BT % 32 == 0 ? 4 : 0);   // keep the 4 k-rows of a warp on distinct banks
@@ -178,19 +178,38 @@ __global__ void __launch_bounds__(BT == 40 ? 800 : 640, 1) lstm_fwd_kernel(const
     cluster_arrive_relaxed();  // A: this CTA is done reading h_{t-1}
 
     float hn0 = 0.f, hn1 = 0.f, s0[5], s1[5];
-    if (a0) {
-      s0[0] = fast_sigmoid(acc[0] + x0[0]); s0[1] = fast_sigmoid(acc[1] + x0[1]);
-      s0[2] = fast_tanh(acc[2] + x0[2]);    s0[3] = fast_sigmoid(acc[3] + x0[3]);
-      c0 = s0[1] * c0 + s0[0] * s0[2];
-      s0[4] = c0;
-      hn0 = s0[3] * fast_tanh(c0);
-    }
-    if (a1) {
-      s1[0] = fast_sigmoid(acc[4] + x1[0]); s1[1] = fast_sigmoid(acc[5] + x1[1]);
-      s1[2] = fast_tanh(acc[6] + x1[2]);    s1[3] = fast_sigmoid(acc[7] + x1[3]);
-      c1 = s1[1] * c1 + s1[0] * s1[2];
-      s1[4] = c1;
-      hn1 = s1[3] * fast_tanh(c1);
+    if (CELL == 0) {
+      if (a0) {
+        s0[0] = fast_sigmoid(acc[0] + x0[0]); s0[1] = fast_sigmoid(acc[1] + x0[1]);
+        s0[2] = fast_tanh(acc[2] + x0[2]);    s0[3] = fast_sigmoid(acc[3] + x0[3]);
+        c0 = s0[1] * c0 + s0[0] * s0[2];
+        s0[4] = c0;
+        hn0 = s0[3] * fast_tanh(c0);
+      }
+      if (a1) {
+        s1[0] = fast_sigmoid(acc[4] + x1[0]); s1[1] = fast_sigmoid(acc[5] + x1[1]);
+        s1[2] = fast_tanh(acc[6] + x1[2]);    s1[3] = fast_sigmoid(acc[7] + x1[3]);
+        c1 = s1[1] * c1 + s1[0] * s1[2];
+        s1[4] = c1;
+        hn1 = s1[3] * fast_tanh(c1);
+      }
+    } else {
+      // GRU (nn.GRU gate order r,z,n): slot 2 = W_in x + b_in (its W_hh rows are zero), slot 3 =
+      // W_hn h + b_hn (its W_ih rows are zero, b_hn arrives through the GEMM bias):
+      //   n = tanh(slot2 + r * slot3),  h' = (1 - z) n + z h.   Saved: (r, z, n, slot3).
+      const float2 hprev = (a0 || a1) ? *reinterpret_cast<const float2*>(h_slot) : make_float2(0.f, 0.f);
+      if (a0) {
+        s0[0] = fast_sigmoid(acc[0] + x0[0]); s0[1] = fast_sigmoid(acc[1] + x0[1]);
+        s0[3] = acc[3] + x0[3];
+        s0[2] = fast_tanh(acc[2] + x0[2] + s0[0] * s0[3]);
+        hn0 = (1.f - s0[1]) * s0[2] + s0[1] * hprev.x;
+      }
+      if (a1) {
+        s1[0] = fast_sigmoid(acc[4] + x1[0]); s1[1] = fast_sigmoid(acc[5] + x1[1]);
+        s1[3] = acc[7] + x1[3];
+        s1[2] = fast_tanh(acc[6] + x1[2] + s1[0] * s1[3]);
+        hn1 = (1.f - s1[1]) * s1[2] + s1[1] * hprev.y;
+      }
     }
 
     LSTM_TS(2)
@@ -215,7 +234,7 @@ __global__ void __launch_bounds__(BT == 40 ? 800 : 640, 1) lstm_fwd_kernel(const
     if (a0) {
       if (p.save) {
         *reinterpret_cast<float4*>(p.gates + row0 * H8 + gcol) = make_float4(s0[0], s0[1], s0[2], s0[3]);
-        p.c[row0 * H2 + ycol] = s0[4];
+        if (CELL == 0) p.c[row0 * H2 + ycol] = s0[4];
       }
       p.y[row0 * H2 + ycol] = hn0;
       const bool fin = dir == 0 ? (t == len0 - 1) : (t == 0);
@@ -224,7 +243,7 @@ __global__ void __launch_bounds__(BT == 40 ? 800 : 640, 1) lstm_fwd_kernel(const
     if (a1) {
       if (p.save) {
         *reinterpret_cast<float4*>(p.gates + row1 * H8 + gcol) = make_float4(s1[0], s1[1], s1[2], s1[3]);
-        p.c[row1 * H2 + ycol] = s1[4];
+        if (CELL == 0) p.c[row1 * H2 + ycol] = s1[4];
       }
       p.y[row1 * H2 + ycol] = hn1;
       const bool fin = dir == 0 ? (t == len1 - 1) : (t == 0);
@@ -413,7 +432,7 @@ __global__ void __launch_bounds__(512, 1) lstm_fwd2_kernel(const LstmArgs p) {
 // ------------------------------------------------------------------------------------------
 // backward through time
 // ------------------------------------------------------------------------------------------
-template <int BT, int KS>
+template <int BT, int KS, int CELL>
 __global__ void __launch_bounds__(BT == 40 ? 800 : 640, 1) lstm_bwd_kernel(const LstmArgs p) {
   extern __shared__ __align__(16) float smem[];
   constexpr int BTP = BT + (BT % 32 == 0 ? 4 : 0);
@@ -584,28 +603,53 @@ __global__ void __launch_bounds__(BT == 40 ? 800 : 640, 1) lstm_bwd_kernel(const
     // ---- reduce my columns, finish the cell backward, publish d(gates) ----
     if (a0) {
       dh0 += rdh0;
-      const float ig = g0[0], fg = g0[1], gg = g0[2], og = g0[3];
-      const float tc = fast_tanh(ct0);
-      const float dog = dh0 * tc * og * (1.f - og);
-      const float dc = dc0 + dh0 * og * (1.f - tc * tc);
-      const float dig = dc * gg * ig * (1.f - ig);
-      const float dfg = dc * cp0 * fg * (1.f - fg);
-      const float dgg = dc * ig * (1.f - gg * gg);
-      dc0 = dc * fg;
+      float dig, dfg, dgg, dog;
+      if (CELL == 0) {
+        const float ig = g0[0], fg = g0[1], gg = g0[2], og = g0[3];
+        const float tc = fast_tanh(ct0);
+        dog = dh0 * tc * og * (1.f - og);
+        const float dc = dc0 + dh0 * og * (1.f - tc * tc);
+        dig = dc * gg * ig * (1.f - ig);
+        dfg = dc * cp0 * fg * (1.f - fg);
+        dgg = dc * ig * (1.f - gg * gg);
+        dc0 = dc * fg;
+      } else {
+        // GRU: `c` carries y, so cp0 = h_{t-1}; dc0 carries the direct path dh * z
+        const float rg = g0[0], zg = g0[1], ng = g0[2], hn = g0[3];
+        dh0 += dc0;
+        const float dnp = dh0 * (1.f - zg) * (1.f - ng * ng);
+        dig = dnp * hn * rg * (1.f - rg);              // d r_pre
+        dfg = dh0 * (cp0 - ng) * zg * (1.f - zg);      // d z_pre
+        dgg = dnp;                                     // d n_pre   (x side)
+        dog = dnp * rg;                                // d (W_hn h + b_hn)
+        dc0 = dh0 * zg;
+      }
       *reinterpret_cast<float4*>(p.gates + row0 * H8 + gcol) = make_float4(dig, dfg, dgg, dog);
       float* sp = dG_s + (u * 4) * BTP + ebl0;
       sp[0] = dig; sp[BTP] = dfg; sp[2 * BTP] = dgg; sp[3 * BTP] = dog;
     }
     if (a1) {
       dh1 += rdh1;
-      const float ig = g1[0], fg = g1[1], gg = g1[2], og = g1[3];
-      const float tc = fast_tanh(ct1);
-      const float dog = dh1 * tc * og * (1.f - og);
-      const float dc = dc1 + dh1 * og * (1.f - tc * tc);
-      const float dig = dc * gg * ig * (1.f - ig);
-      const float dfg = dc * cp1 * fg * (1.f - fg);
-      const float dgg = dc * ig * (1.f - gg * gg);
-      dc1 = dc * fg;
+      float dig, dfg, dgg, dog;
+      if (CELL == 0) {
+        const float ig = g1[0], fg = g1[1], gg = g1[2], og = g1[3];
+        const float tc = fast_tanh(ct1);
+        dog = dh1 * tc * og * (1.f - og);
+        const float dc = dc1 + dh1 * og * (1.f - tc * tc);
+        dig = dc * gg * ig * (1.f - ig);
+        dfg = dc * cp1 * fg * (1.f - fg);
+        dgg = dc * ig * (1.f - gg * gg);
+        dc1 = dc * fg;
+      } else {
+        const float rg = g1[0], zg = g1[1], ng = g1[2], hn = g1[3];
+        dh1 += dc1;
+        const float dnp = dh1 * (1.f - zg) * (1.f - ng * ng);
+        dig = dnp * hn * rg * (1.f - rg);
+        dfg = dh1 * (cp1 - ng) * zg * (1.f - zg);
+        dgg = dnp;
+        dog = dnp * rg;
+        dc1 = dh1 * zg;
+      }
       *reinterpret_cast<float4*>(p.gates + row1 * H8 + gcol) = make_float4(dig, dfg, dgg, dog);
       float* sp = dG_s + (u * 4) * BTP + ebl0 + 1;
       sp[0] = dig; sp[BTP] = dfg; sp[2 * BTP] = dgg; sp[3 * BTP] = dog;
@@ -671,6 +715,58 @@ __global__ void lstm_pack_weights_kernel(const float* __restrict__ wf, const flo
   }
 }
 
+// nn.GRU parameters (gate rows r,z,n) <-> the 4-slot layout the recurrence kernels and the
+// hoisted GEMMs work in.  Flat index space: [4H x I | 4H x H | 4H | 4H].
+__global__ void gru_expand_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_hh,
+                                  const float* __restrict__ b_ih, const float* __restrict__ b_hh,
+                                  int H, int I, float* __restrict__ w4_ih, float* __restrict__ w4_hh,
+                                  float* __restrict__ b4_ih, float* __restrict__ b4_hh) {
+  const size_t nA = (size_t)4 * H * I, nB = (size_t)4 * H * H, nC = (size_t)4 * H;
+  const size_t n = nA + nB + 2 * nC;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    if (i < nA) {                     // x side: slots (r, z, n, 0)
+      const size_t r = i / I;
+      w4_ih[i] = r < (size_t)3 * H ? w_ih[i] : 0.f;
+    } else if (i < nA + nB) {         // h side: slots (r, z, 0, n)
+      const size_t j = i - nA, r = j / H, c = j % H;
+      const int slot = (int)(r / H);
+      w4_hh[j] = slot < 2 ? w_hh[j] : (slot == 2 ? 0.f : w_hh[(r - H) * H + c]);
+    } else if (i < nA + nB + nC) {
+      const size_t r = i - nA - nB;
+      b4_ih[r] = r < (size_t)3 * H ? b_ih[r] : 0.f;
+    } else {
+      const size_t r = i - nA - nB - nC;
+      const int slot = (int)(r / H);
+      b4_hh[r] = slot < 2 ? b_hh[r] : (slot == 2 ? 0.f : b_hh[r - H]);
+    }
+  }
+}
+
+// real grads += 4-slot grads.  Flat index space over the REAL shapes: [3H x I | 3H x H | 3H | 3H].
+__global__ void gru_fold_kernel(const float* __restrict__ dw4_ih, const float* __restrict__ dw4_hh,
+                                const float* __restrict__ db4_ih, const float* __restrict__ db4_hh,
+                                int H, int I, float* __restrict__ dw_ih, float* __restrict__ dw_hh,
+                                float* __restrict__ db_ih, float* __restrict__ db_hh) {
+  const size_t nA = (size_t)3 * H * I, nB = (size_t)3 * H * H, nC = (size_t)3 * H;
+  const size_t n = nA + nB + 2 * nC;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    if (i < nA) {
+      dw_ih[i] += dw4_ih[i];
+    } else if (i < nA + nB) {
+      const size_t j = i - nA, r = j / H, c = j % H;
+      dw_hh[j] += r < (size_t)2 * H ? dw4_hh[j] : dw4_hh[(r + H) * H + c];
+    } else if (i < nA + nB + nC) {
+      const size_t r = i - nA - nB;
+      db_ih[r] += db4_ih[r];
+    } else {
+      const size_t r = i - nA - nB - nC;
+      db_hh[r] += r < (size_t)2 * H ? db4_hh[r] : db4_hh[r + H];
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
@@ -684,7 +780,7 @@ static int g_lstm_tu = 1;   // units per thread in the forward mat-vec of the bi
 static int g_max_clusters8 = 0;   // co-resident 8-CTA clusters of the big-H kernel (B200: 15)
 
 template <int BT> static int probe_clusters8(int threads, size_t smem) {
-  auto kern = lstm_fwd_kernel<BT>;
+  auto kern = lstm_fwd_kernel<BT, 0>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return 0;
   cudaLaunchConfig_t cfg = {};
@@ -814,7 +910,7 @@ int mmda_lstm_plan(int B, int H, int* out6) {
 // cluster sizes 1,2,4,8,16 with the given dynamic smem bytes and block size); -1 = not launchable
 int mmda_lstm_probe_clusters(int smem_bytes, int threads, int* out5) {
   const int sizes[5] = {1, 2, 4, 8, 16};
-  auto kern = lstm_fwd_kernel<32>;
+  auto kern = lstm_fwd_kernel<32, 0>;
   MMDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   for (int i = 0; i < 5; ++i) {
@@ -837,14 +933,18 @@ int mmda_lstm_probe_clusters(int smem_bytes, int threads, int* out5) {
   return MMDA_OK;
 }
 
-int mmda_lstm_forward(float* gates, const float* whh_f, const float* whh_r, float* y, float* c,
-                      const int* lens_sorted, const int* sorted_idx, const int* offsets,
-                      float* utt, int utt_ld, int utt_off_f, int utt_off_r, int B, int H, int Tmax,
-                      int save_for_backward, cudaStream_t stream) {
-  MMDA_REQUIRE(B > 0 && H > 0, "lstm_forward: bad sizes B=%d H=%d", B, H);
-  MMDA_REQUIRE(!save_for_backward || c != nullptr, "lstm_forward: c buffer required when saving");
+static int rnn_forward(int cell, float* gates, const float* whh_f, const float* whh_r, float* y,
+                       float* c, const int* lens_sorted, const int* sorted_idx, const int* offsets,
+                       float* utt, int utt_ld, int utt_off_f, int utt_off_r, int B, int H, int Tmax,
+                       int save_for_backward, cudaStream_t stream) {
+  MMDA_REQUIRE(B > 0 && H > 0, "rnn_forward: bad sizes B=%d H=%d", B, H);
+  MMDA_REQUIRE(cell == 1 || !save_for_backward || c != nullptr,
+               "lstm_forward: c buffer required when saving");
   LstmPlan pl;
+  const int tu_saved = g_lstm_tu;
+  if (cell != 0) g_lstm_tu = 1;   // the two-unit variant implements the LSTM cell only
   int rc = lstm_make_plan(B, H, Tmax, &pl);
+  g_lstm_tu = tu_saved;
   if (rc != MMDA_OK) return rc;
   LstmArgs a = {};
   a.Tmax = Tmax;
@@ -856,17 +956,23 @@ int mmda_lstm_forward(float* gates, const float* whh_f, const float* whh_r, floa
   a.dbg = g_lstm_dbg;
   if (pl.tu == 2 && pl.BT == 40) return launch_cluster(lstm_fwd2_kernel<40>, a, pl, pl.threads_fwd, pl.smem_fwd, stream);
   if (pl.tu == 2 && pl.BT == 32) return launch_cluster(lstm_fwd2_kernel<32>, a, pl, pl.threads_fwd, pl.smem_fwd, stream);
-  if (pl.BT == 40) return launch_cluster(lstm_fwd_kernel<40>, a, pl, pl.threads_fwd, pl.smem_fwd, stream);
-  if (pl.BT == 32) return launch_cluster(lstm_fwd_kernel<32>, a, pl, pl.threads_fwd, pl.smem_fwd, stream);
-  return launch_cluster(lstm_fwd_kernel<8>, a, pl, pl.threads_fwd, pl.smem_fwd, stream);
+  if (cell != 0) {
+    if (pl.BT == 40) return launch_cluster(lstm_fwd_kernel<40, 1>, a, pl, pl.threads_fwd, pl.smem_fwd, stream);
+    if (pl.BT == 32) return launch_cluster(lstm_fwd_kernel<32, 1>, a, pl, pl.threads_fwd, pl.smem_fwd, stream);
+    return launch_cluster(lstm_fwd_kernel<8, 1>, a, pl, pl.threads_fwd, pl.smem_fwd, stream);
+  }
+  if (pl.BT == 40) return launch_cluster(lstm_fwd_kernel<40, 0>, a, pl, pl.threads_fwd, pl.smem_fwd, stream);
+  if (pl.BT == 32) return launch_cluster(lstm_fwd_kernel<32, 0>, a, pl, pl.threads_fwd, pl.smem_fwd, stream);
+  return launch_cluster(lstm_fwd_kernel<8, 0>, a, pl, pl.threads_fwd, pl.smem_fwd, stream);
 }
 
-int mmda_lstm_backward(float* gates, const float* whh_f, const float* whh_r, const float* c,
-                       const float* dy, const float* dutt, int utt_ld, int utt_off_f,
-                       int utt_off_r, const int* lens_sorted, const int* sorted_idx,
-                       const int* offsets, float* scratch, int B, int H, int Tmax,
-                       cudaStream_t stream) {
-  MMDA_REQUIRE(B > 0 && H > 0, "lstm_backward: bad sizes B=%d H=%d", B, H);
+static int rnn_backward(int cell, float* gates, const float* whh_f, const float* whh_r,
+                        const float* c, const float* dy, const float* dutt, int utt_ld,
+                        int utt_off_f, int utt_off_r, const int* lens_sorted,
+                        const int* sorted_idx, const int* offsets, float* scratch, int B, int H,
+                        int Tmax, cudaStream_t stream) {
+  MMDA_REQUIRE(B > 0 && H > 0, "rnn_backward: bad sizes B=%d H=%d", B, H);
+  MMDA_REQUIRE(c != nullptr, "rnn_backward: saved cell states (LSTM) / hidden states (GRU) required");
   MMDA_REQUIRE(scratch != nullptr, "lstm_backward: scratch required (mmda_lstm_scratch_bytes)");
   LstmPlan pl;
   int rc = lstm_make_plan(B, H, Tmax, &pl);
@@ -878,11 +984,80 @@ int mmda_lstm_backward(float* gates, const float* whh_f, const float* whh_r, con
   a.lens = lens_sorted; a.sorted_idx = sorted_idx; a.offsets = offsets; a.scratch = scratch;
   a.dbg = g_lstm_dbg;
   a.B = B; a.H = H; a.Hs = pl.Hs; a.Kpad = pl.Kpad; a.C = pl.C; a.n_tiles = pl.n_tiles;
+  if (cell != 0) {
+    if (pl.BT == 40 && pl.KS == 16)
+      return launch_cluster(lstm_bwd_kernel<40, 16, 1>, a, pl, pl.threads_bwd, pl.smem_bwd, stream);
+    if (pl.BT == 32 && pl.KS == 16)
+      return launch_cluster(lstm_bwd_kernel<32, 16, 1>, a, pl, pl.threads_bwd, pl.smem_bwd, stream);
+    return launch_cluster(lstm_bwd_kernel<8, 4, 1>, a, pl, pl.threads_bwd, pl.smem_bwd, stream);
+  }
   if (pl.BT == 40 && pl.KS == 16)
-    return launch_cluster(lstm_bwd_kernel<40, 16>, a, pl, pl.threads_bwd, pl.smem_bwd, stream);
+    return launch_cluster(lstm_bwd_kernel<40, 16, 0>, a, pl, pl.threads_bwd, pl.smem_bwd, stream);
   if (pl.BT == 32 && pl.KS == 16)
-    return launch_cluster(lstm_bwd_kernel<32, 16>, a, pl, pl.threads_bwd, pl.smem_bwd, stream);
-  return launch_cluster(lstm_bwd_kernel<8, 4>, a, pl, pl.threads_bwd, pl.smem_bwd, stream);
+    return launch_cluster(lstm_bwd_kernel<32, 16, 0>, a, pl, pl.threads_bwd, pl.smem_bwd, stream);
+  return launch_cluster(lstm_bwd_kernel<8, 4, 0>, a, pl, pl.threads_bwd, pl.smem_bwd, stream);
+}
+
+int mmda_lstm_forward(float* gates, const float* whh_f, const float* whh_r, float* y, float* c,
+                      const int* lens_sorted, const int* sorted_idx, const int* offsets,
+                      float* utt, int utt_ld, int utt_off_f, int utt_off_r, int B, int H, int Tmax,
+                      int save_for_backward, cudaStream_t stream) {
+  return rnn_forward(0, gates, whh_f, whh_r, y, c, lens_sorted, sorted_idx, offsets, utt, utt_ld,
+                     utt_off_f, utt_off_r, B, H, Tmax, save_for_backward, stream);
+}
+
+int mmda_lstm_backward(float* gates, const float* whh_f, const float* whh_r, const float* c,
+                       const float* dy, const float* dutt, int utt_ld, int utt_off_f,
+                       int utt_off_r, const int* lens_sorted, const int* sorted_idx,
+                       const int* offsets, float* scratch, int B, int H, int Tmax,
+                       cudaStream_t stream) {
+  return rnn_backward(0, gates, whh_f, whh_r, c, dy, dutt, utt_ld, utt_off_f, utt_off_r,
+                      lens_sorted, sorted_idx, offsets, scratch, B, H, Tmax, stream);
+}
+
+// nn.GRU variant (reference src/models.py:39,168-169,177-178).  Same kernels, 4-slot layout:
+// whh4 = [W_hr; W_hz; 0; W_hn], gates4 = x*[W_ir; W_iz; W_in; 0]^T + (b_ir+b_hr, b_iz+b_hz, b_in, b_hn)
+// (mmda_gru_expand_weights builds them); saved activations (r, z, n, W_hn h + b_hn).
+int mmda_gru_forward(float* gates, const float* whh4_f, const float* whh4_r, float* y,
+                     const int* lens_sorted, const int* sorted_idx, const int* offsets, float* utt,
+                     int utt_ld, int utt_off_f, int utt_off_r, int B, int H, int Tmax,
+                     int save_for_backward, cudaStream_t stream) {
+  return rnn_forward(1, gates, whh4_f, whh4_r, y, nullptr, lens_sorted, sorted_idx, offsets, utt,
+                     utt_ld, utt_off_f, utt_off_r, B, H, Tmax, save_for_backward, stream);
+}
+
+// After the call gates4 holds (d r_pre, d z_pre, d n_pre, d n_pre * r): slots 0,1,2 are the
+// x-side gate gradients, slots 0,1,3 the h-side ones.
+int mmda_gru_backward(float* gates, const float* whh4_f, const float* whh4_r, const float* y,
+                      const float* dy, const float* dutt, int utt_ld, int utt_off_f, int utt_off_r,
+                      const int* lens_sorted, const int* sorted_idx, const int* offsets,
+                      float* scratch, int B, int H, int Tmax, cudaStream_t stream) {
+  return rnn_backward(1, gates, whh4_f, whh4_r, y, dy, dutt, utt_ld, utt_off_f, utt_off_r,
+                      lens_sorted, sorted_idx, offsets, scratch, B, H, Tmax, stream);
+}
+
+int mmda_gru_expand_weights(const float* w_ih, const float* w_hh, const float* b_ih,
+                            const float* b_hh, int H, int I, float* w4_ih, float* w4_hh,
+                            float* b4_ih, float* b4_hh, cudaStream_t stream) {
+  MMDA_REQUIRE(H > 0 && I > 0, "gru_expand_weights: bad sizes H=%d I=%d", H, I);
+  const size_t n = (size_t)4 * H * (I + H + 2);
+  size_t g = (n + 255) / 256;
+  if (g > 1184) g = 1184;
+  gru_expand_kernel<<<(int)g, 256, 0, stream>>>(w_ih, w_hh, b_ih, b_hh, H, I, w4_ih, w4_hh, b4_ih, b4_hh);
+  MMDA_CHECK_LAUNCH();
+  return MMDA_OK;
+}
+
+int mmda_gru_fold_grads(const float* dw4_ih, const float* dw4_hh, const float* db4_ih,
+                        const float* db4_hh, int H, int I, float* dw_ih, float* dw_hh, float* db_ih,
+                        float* db_hh, cudaStream_t stream) {
+  MMDA_REQUIRE(H > 0 && I > 0, "gru_fold_grads: bad sizes H=%d I=%d", H, I);
+  const size_t n = (size_t)3 * H * (I + H + 2);
+  size_t g = (n + 255) / 256;
+  if (g > 1184) g = 1184;
+  gru_fold_kernel<<<(int)g, 256, 0, stream>>>(dw4_ih, dw4_hh, db4_ih, db4_hh, H, I, dw_ih, dw_hh, db_ih, db_hh);
+  MMDA_CHECK_LAUNCH();
+  return MMDA_OK;
 }
 
 int mmda_lstm_pack_weights(const float* w_ih_f, const float* w_ih_r, const float* b_ih_f,

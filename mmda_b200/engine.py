@@ -151,6 +151,7 @@ class MisaEngine:
         self.diff_out = _DIFF_OUT + (tuple(f"domain_label_{m}" for m in MODS) if self.adversarial
                                      else ())
         self.use_bert = bool(self.cfg.use_bert)
+        self.gru = getattr(model, "rnncell", "lstm") == "gru"        # models.py:39
         self.utt_dim = {m: 4 * self.H[m] for m in MODS}
         if self.use_bert:
             self.utt_dim["t"] = 768
@@ -313,6 +314,29 @@ class MisaEngine:
                   W[0].stride(0), _ptr(bst))
         return W, bst
 
+    _RNN_KEYS = ("weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0")
+
+    def _gru_overlay(self, m, P, what):
+        """nn.GRU cells (models.py:39): 4-slot stand-ins for modality m's (3H, .) GRU tensors so
+        the LSTM-shaped machinery (gate layout [N][2][H][4], stacked GEMMs) applies unchanged.
+        what = "expand": build the 4-slot weights from P; "weights": the same buffers, no launch;
+        "grads": zeroed 4-slot gradient buffers."""
+        H = self.H[m]
+        r1, r2, _ = ENC[m]
+        out = {}
+        for r, I in ((r1, H), (r2, 2 * H)):
+            for suf in ("", "_reverse"):
+                tag = "gruG" if what == "grads" else "gruW"
+                shapes = ((4 * H, I), (4 * H, H), (4 * H,), (4 * H,))
+                t = [self.buf(f"{tag}{i}_{r}{suf}", *sh) for i, sh in enumerate(shapes)]
+                if what == "expand":
+                    src = [P[f"{r}.{kk}{suf}"] for kk in self._RNN_KEYS]
+                    self.k._c("mmda_gru_expand_weights", *[_ptr(x) for x in src], H, I,
+                              *[_ptr(x) for x in t])
+                for kk, x in zip(self._RNN_KEYS, t):
+                    out[f"{r}.{kk}{suf}"] = x
+        return out
+
     @staticmethod
     def _cols(op, lo, hi):
         return (op[0][:, lo:hi], None if op[1] is None else op[1][:, lo:hi])
@@ -333,6 +357,8 @@ class MisaEngine:
         C2 = self.buf(f"C2_{m}", N, 2 * H)
         mu = self.buf(f"ln_mu_{m}", N)
         rs = self.buf(f"ln_rs_{m}", N)
+        if self.gru:
+            P = {**P, **self._gru_overlay(m, P, "expand")}
         for G, Xin, r in ((G1, X, r1), (G2, Y1n, r2)):
             if r == r2:
                 k.layernorm(Y1, None, P[f"{ln}.weight"], P[f"{ln}.bias"], Y1n, mu, rs)
@@ -348,6 +374,12 @@ class MisaEngine:
                 self.big_gemm(Xin, Wst[0], G, tb=True, bias=bst)
             Y, C = (Y1, C1) if r == r1 else (Y2, C2)
             o_f, o_r = (0, 2 * H) if r == r1 else (H, 3 * H)
+            if self.gru:
+                k._c("mmda_gru_forward", _ptr(G), _ptr(P[f"{r}.weight_hh_l0"]),
+                     _ptr(P[f"{r}.weight_hh_l0_reverse"]), _ptr(Y), _ptr(pk["lens"]),
+                     _ptr(pk["sidx"]), _ptr(pk["off"]), _ptr(utt), 4 * H, o_f, o_r, B, H, Tmax,
+                     int(train))
+                continue
             k._c("mmda_lstm_forward", _ptr(G), _ptr(P[f"{r}.weight_hh_l0"]),
                  _ptr(P[f"{r}.weight_hh_l0_reverse"]), _ptr(Y), _ptr(C), _ptr(pk["lens"]),
                  _ptr(pk["sidx"]), _ptr(pk["off"]), _ptr(utt), 4 * H, o_f, o_r, B, H, Tmax,
@@ -742,13 +774,18 @@ class MisaEngine:
         use_side = self.multi_stream and not _DRYRUN
         cur = torch.cuda.current_stream() if use_side else None
         side = self._wgrad_stream(m) if use_side else None
+        G_real = G
+        if self.gru:
+            P = {**P, **self._gru_overlay(m, P, "weights")}      # expanded by the forward
+            G = {**G, **self._gru_overlay(m, P, "grads")}
         for r, Gt, Y, C, Xin, dy, (o_f, o_r) in ((r2, G2, Y2, C2, Y1n, None, (H, 3 * H)),
                                                  (r1, G1, Y1, C1, X, dY1, (0, 2 * H))):
             if r == r1:
                 k.layernorm_bwd(dY1n, Y1, None, P[f"{ln}.weight"], mu, rs, dY1, G[f"{ln}.weight"],
                                 G[f"{ln}.bias"])
-            k._c("mmda_lstm_backward", _ptr(Gt), _ptr(P[f"{r}.weight_hh_l0"]),
-                 _ptr(P[f"{r}.weight_hh_l0_reverse"]), _ptr(C), _ptr(dy), _ptr(dutt), 4 * H, o_f,
+            k._c("mmda_gru_backward" if self.gru else "mmda_lstm_backward", _ptr(Gt),
+                 _ptr(P[f"{r}.weight_hh_l0"]), _ptr(P[f"{r}.weight_hh_l0_reverse"]),
+                 _ptr(Y if self.gru else C), _ptr(dy), _ptr(dutt), 4 * H, o_f,
                  o_r, _ptr(pk["lens"]), _ptr(pk["sidx"]), _ptr(pk["off"]), _ptr(scratch), B, H,
                  Tmax)
             I = Xin.shape[1]
@@ -768,6 +805,10 @@ class MisaEngine:
                 Wst = (self.buf(f"Wst_{r}", 8 * H, I), None)      # written by the forward
 
             def wgrad(r=r, Gt=Gt, Y=Y, Xin=Xin, tc=tc, I=I):
+                if self.gru:
+                    for suf in ("", "_reverse"):
+                        for kk in self._RNN_KEYS:
+                            G[f"{r}.{kk}{suf}"].zero_()
                 HP = self.buf(f"HP_{r}", N, 2 * H)
                 k._c("mmda_lstm_shift_h", _ptr(Y), _ptr(HP), _ptr(pk["row_t"]), _ptr(pk["row_j"]),
                      _ptr(pk["lens"]), _ptr(pk["off"]), N, H)
@@ -788,6 +829,9 @@ class MisaEngine:
                         self.big_gemm(dG, HP[:, di * H:(di + 1) * H], G[f"{r}.weight_hh_l0{suf}"],
                                       ta=True, beta=1.0, split_k=0, c_ilv=H)
                     k.colsum(dG, G[f"{r}.bias_ih_l0{suf}"], G[f"{r}.bias_hh_l0{suf}"], ilv=H)
+                    if self.gru:     # 4-slot gradients -> the (3H, .) parameters' gradients
+                        k._c("mmda_gru_fold_grads", *[_ptr(G[f"{r}.{kk}{suf}"]) for kk in self._RNN_KEYS],
+                             H, I, *[_ptr(G_real[f"{r}.{kk}{suf}"]) for kk in self._RNN_KEYS])
 
             if use_side:
                 ev = torch.cuda.Event()

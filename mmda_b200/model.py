@@ -25,18 +25,19 @@ _TORCH_ACT = {"leakyrelu": nn.LeakyReLU, "relu": nn.ReLU, "tanh": nn.Tanh, "sigm
 
 class BiLSTMParams(nn.Module):
     """Parameter container with ``nn.LSTM(input, hidden, bidirectional=True)``'s names, shapes,
-    registration order and U(-1/sqrt(H), 1/sqrt(H)) init (so RNG consumption matches)."""
+    registration order and U(-1/sqrt(H), 1/sqrt(H)) init (so RNG consumption matches).
+    ``gates=3`` gives ``nn.GRU``'s shapes (rows r,z,n) under the same names."""
 
-    def __init__(self, input_size: int, hidden_size: int):
+    def __init__(self, input_size: int, hidden_size: int, gates: int = 4):
         super().__init__()
-        self.input_size, self.hidden_size = input_size, hidden_size
+        self.input_size, self.hidden_size, self.gates = input_size, hidden_size, gates
         for suffix in ("", "_reverse"):
             self.register_parameter(f"weight_ih_l0{suffix}",
-                                    nn.Parameter(torch.empty(4 * hidden_size, input_size)))
+                                    nn.Parameter(torch.empty(gates * hidden_size, input_size)))
             self.register_parameter(f"weight_hh_l0{suffix}",
-                                    nn.Parameter(torch.empty(4 * hidden_size, hidden_size)))
-            self.register_parameter(f"bias_ih_l0{suffix}", nn.Parameter(torch.empty(4 * hidden_size)))
-            self.register_parameter(f"bias_hh_l0{suffix}", nn.Parameter(torch.empty(4 * hidden_size)))
+                                    nn.Parameter(torch.empty(gates * hidden_size, hidden_size)))
+            self.register_parameter(f"bias_ih_l0{suffix}", nn.Parameter(torch.empty(gates * hidden_size)))
+            self.register_parameter(f"bias_hh_l0{suffix}", nn.Parameter(torch.empty(gates * hidden_size)))
         stdv = 1.0 / math.sqrt(hidden_size) if hidden_size > 0 else 0
         for w in self.parameters():
             nn.init.uniform_(w, -stdv, stdv)
@@ -77,8 +78,8 @@ class MISA(nn.Module):
         if getattr(config, "extractor", "lstm") == "transformer":
             raise NotImplementedError("extractor='transformer' exits in the reference too "
                                       "(src/models.py:33-36)")
-        if getattr(config, "rnncell", "lstm") != "lstm":
-            raise NotImplementedError("GRU cells are outside this round's scope (SURVEY.md 8f N4)")
+        self.rnncell = "lstm" if getattr(config, "rnncell", "lstm") == "lstm" else "gru"   # models.py:39
+        ng = 4 if self.rnncell == "lstm" else 3
         if d % 2:
             raise ValueError("hidden_size must be even (2 attention heads)")
 
@@ -89,12 +90,12 @@ class MISA(nn.Module):
             self.bertmodel = BertModel(BertConfig(output_hidden_states=True))
         else:
             self.embed = nn.Embedding(len(config.word2id), sz["t"])
-            self.trnn1 = BiLSTMParams(sz["t"], sz["t"])
-            self.trnn2 = BiLSTMParams(2 * sz["t"], sz["t"])
-        self.vrnn1 = BiLSTMParams(sz["v"], sz["v"])
-        self.vrnn2 = BiLSTMParams(2 * sz["v"], sz["v"])
-        self.arnn1 = BiLSTMParams(sz["a"], sz["a"])
-        self.arnn2 = BiLSTMParams(2 * sz["a"], sz["a"])
+            self.trnn1 = BiLSTMParams(sz["t"], sz["t"], ng)
+            self.trnn2 = BiLSTMParams(2 * sz["t"], sz["t"], ng)
+        self.vrnn1 = BiLSTMParams(sz["v"], sz["v"], ng)
+        self.vrnn2 = BiLSTMParams(2 * sz["v"], sz["v"], ng)
+        self.arnn1 = BiLSTMParams(sz["a"], sz["a"], ng)
+        self.arnn2 = BiLSTMParams(2 * sz["a"], sz["a"], ng)
 
         for m in MODS:
             fan_in = 768 if (m == "t" and config.use_bert) else 4 * sz[m]

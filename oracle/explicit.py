@@ -72,6 +72,29 @@ def lstm_direction(x, lengths, w_ih, w_hh, b_ih, b_hh, reverse: bool):
     return y, hn, cn
 
 
+def gru_direction(x, lengths, w_ih, w_hh, b_ih, b_hh, reverse: bool):
+    """One nn.GRU direction (gate rows r,z,n; reference models.py:39 when rnncell != 'lstm'):
+    r = s(W_ir x + b_ir + W_hr h + b_hr), z likewise, n = tanh(W_in x + b_in + r*(W_hn h + b_hn)),
+    h' = (1-z) n + z h.  Returns y (T,B,H) and the final h (B,H)."""
+    T, B, _ = x.shape
+    H = w_hh.shape[1]
+    y = np.zeros((T, B, H), dtype=x.dtype)
+    hn = np.zeros((B, H), dtype=x.dtype)
+    for b in range(B):
+        h = np.zeros(H, dtype=x.dtype)
+        L = int(lengths[b])
+        for t in (range(L - 1, -1, -1) if reverse else range(L)):
+            gx = w_ih @ x[t, b] + b_ih
+            gh = w_hh @ h + b_hh
+            r = sigmoid(gx[:H] + gh[:H])
+            z = sigmoid(gx[H:2 * H] + gh[H:2 * H])
+            n = np.tanh(gx[2 * H:] + r * gh[2 * H:])
+            h = (1.0 - z) * n + z * h
+            y[t, b] = h
+        hn[b] = h
+    return y, hn
+
+
 def bilstm(x, lengths, p, prefix=""):
     """Bidirectional layer.  ``p`` maps torch's names (weight_ih_l0, ..._reverse) to arrays.
     Returns y (T,B,2H) = [fwd | bwd] and final h (2,B,H)."""

@@ -50,7 +50,7 @@ def build_reference(ref_solver, ref_config, cfg, seed):
                                use_confidNet=cfg.use_confidNet, batch_size=cfg.batch_size,
                                embedding_size=cfg.embedding_size, hidden_size=cfg.hidden_size,
                                dropout=cfg.dropout, learning_rate=cfg.learning_rate,
-                               use_cmd_sim=cfg.use_cmd_sim)
+                               use_cmd_sim=cfg.use_cmd_sim, rnncell=cfg.rnncell)
     rc.visual_size, rc.acoustic_size = cfg.visual_size, cfg.acoustic_size
     rc.word2id = {i: i for i in range(cfg.vocab_size)}
     rc.pretrained_emb = None
@@ -103,13 +103,14 @@ ATTRS = ["utt_t_orig", "utt_v_orig", "utt_a_orig", "utt_private_t", "utt_private
          "shared_or_private_p_a", "shared_or_private_s"]
 
 
-def gen_small(ref_solver, ref_config, name, seed, confid, lengths_mode, use_cmd_sim=True):
+def gen_small(ref_solver, ref_config, name, seed, confid, lengths_mode, use_cmd_sim=True,
+              rnncell="lstm"):
     import torch
     from mmda_b200.config import MisaConfig
     from mmda_b200.synthetic import batch_for
     cfg = MisaConfig(embedding_size=12, visual_size=5, acoustic_size=7, hidden_size=16,
                      vocab_size=50, batch_size=6, use_confidNet=confid, dropout=0.1,
-                     use_cmd_sim=use_cmd_sim)
+                     use_cmd_sim=use_cmd_sim, rnncell=rnncell)
     s, rc = build_reference(ref_solver, ref_config, cfg, seed)
     s.model.eval()                                   # deterministic parity mode
     batch = batch_for(cfg, seed=seed + 1, lengths=lengths_mode, seq_len=7)
@@ -138,6 +139,7 @@ def gen_small(ref_solver, ref_config, name, seed, confid, lengths_mode, use_cmd_
     arrs["pack/unsorted_indices"] = packed.unsorted_indices.numpy()
     arrs["pack/data"] = packed.data.numpy()
     meta = {"seed": seed, "use_confidNet": confid, "lengths": lengths_mode, "use_cmd_sim": use_cmd_sim,
+            "rnncell": rnncell,
             "none_grads": sorted(n for n, g in grads.items() if g is None),
             "cfg": {"embedding_size": 12, "visual_size": 5, "acoustic_size": 7,
                     "hidden_size": 16, "vocab_size": 50, "batch_size": 6, "seq_len": 7}}
@@ -230,15 +232,20 @@ def gen_collate():
 def main():
     adv_only = "--adversarial-only" in sys.argv      # import_reference() sanitises argv
     collate_only = "--collate-only" in sys.argv
+    gru_only = "--gru-only" in sys.argv
     ref_solver, ref_config = import_reference()
     if collate_only:
         gen_collate()
+        return
+    if gru_only:
+        gen_small(ref_solver, ref_config, "small_gru", 41, True, "shuffled", rnncell="gru")
         return
     from mmda_b200.config import mosi_config, mosei_config
     if adv_only:
         gen_small(ref_solver, ref_config, "small_adversarial", 31, False, "shuffled", use_cmd_sim=False)
         return
     gen_small(ref_solver, ref_config, "small_adversarial", 31, False, "shuffled", use_cmd_sim=False)
+    gen_small(ref_solver, ref_config, "small_gru", 41, True, "shuffled", rnncell="gru")
     gen_small(ref_solver, ref_config, "small_ragged", 11, False, "ragged")
     gen_small(ref_solver, ref_config, "small_shuffled_confid", 23, True, "shuffled")
     gen_summary(ref_solver, ref_config, "c1_mosi_b64", mosi_config(vocab_size=2000), 1234, "ragged")

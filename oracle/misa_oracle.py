@@ -59,19 +59,20 @@ class OracleMISA(nn.Module):
         sizes = {"t": cfg.embedding_size, "v": cfg.visual_size, "a": cfg.acoustic_size}
         self.sizes = sizes
         act = _act_module(cfg.activation)
-        if cfg.rnncell != "lstm" or cfg.extractor != "lstm":
-            raise NotImplementedError("oracle covers the LSTM extractor (SURVEY.md section 8f, N4)")
+        if cfg.extractor != "lstm":
+            raise NotImplementedError("extractor='transformer' exits in the reference (models.py:33-36)")
+        rnn = nn.LSTM if cfg.rnncell == "lstm" else nn.GRU          # models.py:39
         if cfg.use_bert:
             from transformers import BertConfig, BertModel
             # bert-base-uncased geometry == BertConfig() defaults; no network here.
             self.bertmodel = BertModel(BertConfig(output_hidden_states=True))
         else:
             self.embed = nn.Embedding(len(cfg.word2id), sizes["t"])
-            self.trnn1 = nn.LSTM(sizes["t"], sizes["t"], bidirectional=True)
-            self.trnn2 = nn.LSTM(2 * sizes["t"], sizes["t"], bidirectional=True)
+            self.trnn1 = rnn(sizes["t"], sizes["t"], bidirectional=True)
+            self.trnn2 = rnn(2 * sizes["t"], sizes["t"], bidirectional=True)
         for m in ("v", "a"):
-            setattr(self, f"{m}rnn1", nn.LSTM(sizes[m], sizes[m], bidirectional=True))
-            setattr(self, f"{m}rnn2", nn.LSTM(2 * sizes[m], sizes[m], bidirectional=True))
+            setattr(self, f"{m}rnn1", rnn(sizes[m], sizes[m], bidirectional=True))
+            setattr(self, f"{m}rnn2", rnn(2 * sizes[m], sizes[m], bidirectional=True))
         for m in _MODS:
             fan_in = 768 if (m == "t" and cfg.use_bert) else 4 * sizes[m]
             setattr(self, f"project_{m}", _seq(**{
@@ -110,9 +111,11 @@ class OracleMISA(nn.Module):
     @staticmethod
     def encode(seq, lengths, rnn1, rnn2, norm):
         B = lengths.size(0)
-        out1, (h1, _) = rnn1(pack_padded_sequence(seq, lengths, enforce_sorted=False))
+        out1, h1 = rnn1(pack_padded_sequence(seq, lengths, enforce_sorted=False))
+        h1 = h1[0] if isinstance(h1, tuple) else h1             # LSTM: (h, c); GRU: h  (models.py:166-169)
         padded, _ = pad_packed_sequence(out1)
-        _, (h2, _) = rnn2(pack_padded_sequence(norm(padded), lengths, enforce_sorted=False))
+        _, h2 = rnn2(pack_padded_sequence(norm(padded), lengths, enforce_sorted=False))
+        h2 = h2[0] if isinstance(h2, tuple) else h2
         # models.py:203 -> per sample [h1_fwd | h2_fwd | h1_bwd | h2_bwd]
         return torch.cat((h1, h2), dim=2).permute(1, 0, 2).contiguous().view(B, -1)
 

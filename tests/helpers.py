@@ -20,7 +20,7 @@ def small_cfg(meta, **kw):
     c = dict(meta["cfg"])
     c.pop("seq_len")
     return MisaConfig(use_confidNet=meta["use_confidNet"], use_cmd_sim=meta.get("use_cmd_sim", True),
-                      **c, **kw)
+                      rnncell=meta.get("rnncell", "lstm"), **c, **kw)
 
 
 def small_batch(z):

@@ -38,8 +38,8 @@ def test_config_activation_mapping_and_errors():
     assert activation_name("Tanh") == "tanh"
     with pytest.raises(ValueError):
         activation_name(nn.PReLU)
-    with pytest.raises(NotImplementedError):
-        MISA(MisaConfig(vocab_size=10, rnncell="gru"))
+    gru = MISA(MisaConfig(vocab_size=10, rnncell="gru", embedding_size=8)).state_dict()
+    assert gru["trnn2.weight_ih_l0_reverse"].shape == (24, 16) and gru["trnn1.bias_hh_l0"].shape == (24,)
     adv = MISA(MisaConfig(vocab_size=10, use_cmd_sim=False))
     assert "discriminator.discriminator_layer_2.weight" in adv.state_dict()
 

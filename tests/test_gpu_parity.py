@@ -331,7 +331,7 @@ def _model_checks(tag, cfg, state, batch, dev, golden=None):
     C.finish()
 
 
-@pytest.mark.parametrize("name", ["small_ragged", "small_shuffled_confid", "small_adversarial"])
+@pytest.mark.parametrize("name", ["small_ragged", "small_shuffled_confid", "small_adversarial", "small_gru"])
 def test_small_fixture(dev, name):
     z, meta = load_small(name)
     cfg = small_cfg(meta)
@@ -634,3 +634,18 @@ def test_other_recurrence_plans(dev, sizes, B, T):
     state = {k: v.clone() for k, v in oracle_build(cfg, 5).state_dict().items()}
     batch = batch_for(cfg, seed=6, lengths="shuffled", seq_len=T)
     _model_checks(f"plans_{sizes[0]}_{sizes[1]}_{sizes[2]}", cfg, state, batch, dev, None)
+
+
+@pytest.mark.parametrize("sizes,B,T", [((300, 35, 74), 64, 20), ((96, 33, 160), 41, 5)])
+def test_gru_cells(dev, sizes, B, T):
+    """rnncell='gru' (reference models.py:39,168-169,177-178) at MOSEI widths
+    (cluster of 8, tcgen05 GEMMs) and at sizes that take the smaller cluster plans."""
+    from mmda_b200.config import MisaConfig
+    from mmda_b200.synthetic import batch_for
+    from oracle.misa_oracle import oracle_build
+    cfg = MisaConfig(embedding_size=sizes[0], visual_size=sizes[1], acoustic_size=sizes[2],
+                     hidden_size=32 if sizes[0] < 300 else 128, vocab_size=200, batch_size=B,
+                     use_confidNet=True, rnncell="gru")
+    state = {k: v.clone() for k, v in oracle_build(cfg, 7).state_dict().items()}
+    batch = batch_for(cfg, seed=8, lengths="shuffled", seq_len=T)
+    _model_checks(f"gru_{sizes[0]}_{B}", cfg, state, batch, dev, None)

@@ -30,6 +30,25 @@ def test_bilstm_and_encoder_features():
     np.testing.assert_allclose(got, ref, rtol=0, atol=1e-12)
 
 
+def test_gru_direction_matches_torch():
+    """nn.GRU semantics (gate rows r,z,n; b_hn inside the r product) -- models.py:39 variant."""
+    from torch.nn.utils.rnn import pack_padded_sequence, pad_packed_sequence
+    torch.manual_seed(1)
+    T, B, I, H = 6, 5, 4, 3
+    lengths = torch.tensor([3, 6, 1, 6, 2])
+    x = torch.randn(T, B, I, dtype=torch.float64)
+    gru = nn.GRU(I, H, bidirectional=True).double()
+    out, hn = gru(pack_padded_sequence(x, lengths, enforce_sorted=False))
+    y_ref, _ = pad_packed_sequence(out, total_length=T)
+    p = _np(dict(gru.named_parameters()))
+    for d, suf in enumerate(("", "_reverse")):
+        y, h = E.gru_direction(x.numpy(), lengths.numpy(), p["weight_ih_l0" + suf],
+                               p["weight_hh_l0" + suf], p["bias_ih_l0" + suf],
+                               p["bias_hh_l0" + suf], reverse=bool(d))
+        np.testing.assert_allclose(y, y_ref[:, :, d * H:(d + 1) * H].detach().numpy(), atol=1e-12)
+        np.testing.assert_allclose(h, hn[d].detach().numpy(), atol=1e-12)
+
+
 def test_pack_indices_match_torch():
     g = torch.Generator().manual_seed(3)
     for B in (1, 7, 40):

@@ -12,7 +12,7 @@ from oracle.misa_oracle import (OracleMISA, oracle_build, oracle_losses, oracle_
                                 oracle_step)
 
 
-@pytest.mark.parametrize("name", ["small_ragged", "small_shuffled_confid", "small_adversarial"])
+@pytest.mark.parametrize("name", ["small_ragged", "small_shuffled_confid", "small_adversarial", "small_gru"])
 def test_small_fixture_full_tensors(name):
     z, meta = load_small(name)
     cfg = small_cfg(meta)
