@@ -227,6 +227,34 @@ int mmda_gru_backward(float* gates, const float* whh4_f, const float* whh4_r, co
                       const int* lens_sorted, const int* sorted_idx, const int* offsets,
                       float* scratch, int B, int H, int Tmax, mmda_stream_t stream);
 
+/* ---- BERT-base text encoder: BertModel(...)[0] + masked mean,
+ * src/models.py:41-45,186-198 (HF BertModel: embeddings, 12 x [self-attention, dense+LN, GELU
+ * FFN, dense+LN], LayerNorm eps 1e-12, dropout 0.1).  Dense layers run on mmda_gemm_tc, the
+ * LayerNorms / dropouts on mmda_layernorm_* / mmda_dropout; these are the remaining pieces.
+ * Tokens are batch-first: row m = b*S + s.  qkv rows = [q | k | v] (3*nhead*64 floats);
+ * probs [B][nhead][S][S] holds the post-softmax, pre-dropout probabilities for the backward. */
+int mmda_bert_embed_forward(const float* word, const float* pos, const float* typ,
+                            const long long* ids, const long long* types, int B, int S, int H,
+                            int V, int max_pos, float* out, mmda_stream_t stream);
+/* dword / dpos / dtyp accumulate (+=) and may be NULL; word row 0 (padding_idx) gets no gradient */
+int mmda_bert_embed_backward(const float* d, const long long* ids, const long long* types, int B,
+                             int S, int H, int V, float* dword, float* dpos, float* dtyp,
+                             mmda_stream_t stream);
+int mmda_gelu_forward(const float* x, float* y, long long n, mmda_stream_t stream);
+int mmda_gelu_backward(const float* dy, const float* x, float* dx, long long n, mmda_stream_t stream);
+int mmda_masked_mean_forward(const float* hid, const long long* mask, int B, int S, int H,
+                             float* utt, mmda_stream_t stream);
+int mmda_masked_mean_backward(const float* dutt, const long long* mask, int B, int S, int H,
+                              float* dhid, mmda_stream_t stream);
+int mmda_bert_attention_forward(const float* qkv, const long long* mask, float* ctx, float* probs,
+                                int B, int S, int nhead, int head_dim, float p_drop,
+                                unsigned long long seed, const unsigned long long* seed_dev,
+                                unsigned stream_id, mmda_stream_t stream);
+int mmda_bert_attention_backward(const float* qkv, const float* probs, const float* dctx,
+                                 float* dqkv, int B, int S, int nhead, int head_dim, float p_drop,
+                                 unsigned long long seed, const unsigned long long* seed_dev,
+                                 unsigned stream_id, mmda_stream_t stream);
+
 /* ---- device-resident collate: collate_fn, src/data_loader.py:59-122, and the
  * per-tensor to_gpu copies, src/utils/convert.py:4-11.  The split lives in HBM as ragged flat
  * arrays (words (sumL,), visual (sumL,dv), acoustic (sumL,da), labels (n,n_label), offsets

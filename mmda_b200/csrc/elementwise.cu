@@ -39,7 +39,8 @@ __global__ void layernorm_fwd_kernel(const float* __restrict__ x, int ldx,
 }
 
 // dx = rstd * (dy*g - mean(dy*g) - xhat * mean(dy*g*xhat));  dgamma += sum_r dy*xhat;  dbeta += sum_r dy
-constexpr int LN_MAXC = 20;   // width <= 640
+constexpr int LN_MAXC = 20;   // width <= 640 (every MISA norm); 32 -> width <= 1024 (BERT's 768)
+template <int LN_MAXC>
 __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ x, int ldx,
                      const float* __restrict__ res, int ldr, const float* __restrict__ gamma,
@@ -332,13 +333,17 @@ int mmda_layernorm_backward(const float* dy, int lddy, const float* x, int ldx, 
                             float* dx, int lddx, float* dgamma, float* dbeta, int rows, int width,
                             cudaStream_t stream) {
   if (rows <= 0) return MMDA_OK;
-  MMDA_REQUIRE(width > 0 && width <= 32 * LN_MAXC, "layernorm_backward: width=%d (max %d)", width,
-               32 * LN_MAXC);
+  MMDA_REQUIRE(width > 0 && width <= 1024, "layernorm_backward: width=%d (max 1024)", width);
   int rpb = (rows + 295) / 296;
   rpb = (rpb + 7) / 8 * 8;
   const int grid = (rows + rpb - 1) / rpb;
-  layernorm_bwd_kernel<<<grid, 256, 0, stream>>>(dy, lddy, x, ldx, res, ldr, gamma, mean, rstd, dx,
-                                                 lddx, dgamma, dbeta, rows, width, rpb);
+  if (width <= 32 * LN_MAXC)
+    layernorm_bwd_kernel<LN_MAXC><<<grid, 256, 0, stream>>>(dy, lddy, x, ldx, res, ldr, gamma, mean,
+                                                            rstd, dx, lddx, dgamma, dbeta, rows,
+                                                            width, rpb);
+  else
+    layernorm_bwd_kernel<32><<<grid, 256, 0, stream>>>(dy, lddy, x, ldx, res, ldr, gamma, mean, rstd,
+                                                       dx, lddx, dgamma, dbeta, rows, width, rpb);
   MMDA_CHECK_LAUNCH();
   return MMDA_OK;
 }

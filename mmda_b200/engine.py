@@ -144,9 +144,10 @@ class MisaEngine:
         # cluster kernel occupies 112 of the 148 SMs)
         self.multi_stream = os.environ.get("MMDA_STREAMS", "1") != "0"
         self._side = None
-        # use_bert=True: the BERT encoder itself stays the HF / PyTorch module
-        # (library kernels); its masked-mean output feeds the hand-written heads / fusion / losses
-        # through `utt_text`, and the gradient wrt that tensor is handed back to autograd.
+        # use_bert=True: the BERT encoder runs on the hand-written kernels too
+        # (mmda_b200/bert.py); its masked-mean output enters here as `utt_text` and backward()
+        # returns the gradient wrt it.
+        self._bert = None
         self.adversarial = not bool(getattr(self.cfg, "use_cmd_sim", True))
         self.diff_out = _DIFF_OUT + (tuple(f"domain_label_{m}" for m in MODS) if self.adversarial
                                      else ())
@@ -155,6 +156,13 @@ class MisaEngine:
         self.utt_dim = {m: 4 * self.H[m] for m in MODS}
         if self.use_bert:
             self.utt_dim["t"] = 768
+
+    @property
+    def bert(self):
+        if self._bert is None:
+            from .bert import BertEngine
+            self._bert = BertEngine(self)
+        return self._bert
 
     # ---------------------------------------------------------------- buffers -------------
     def buf(self, name, *shape, dtype=torch.float32, zero=False):
@@ -942,12 +950,32 @@ class _MisaFunction(torch.autograd.Function):
         return (None,) * 6 + (d_utt,) + grads
 
 
-def _bert_utterance(model, bert_sent, bert_sent_type, bert_sent_mask):
-    """reference src/models.py:186-198: BertModel -> masked mean over tokens (library kernels)."""
-    hid = model.bertmodel(input_ids=bert_sent, attention_mask=bert_sent_mask,
-                          token_type_ids=bert_sent_type)[0]
-    m = bert_sent_mask.unsqueeze(2)
-    return (m * hid).sum(1) / bert_sent_mask.sum(1, keepdim=True)
+class _BertFunction(torch.autograd.Function):
+    """reference src/models.py:186-198 (BertModel -> masked mean over tokens) on the hand-written
+    kernels (mmda_b200/bert.py), as one autograd node over the BERT parameters."""
+
+    @staticmethod
+    def forward(ctx, model, bert_sent, bert_sent_type, bert_sent_mask, names, *params):
+        eng = model.engine
+        be = eng.bert
+        be.calls = getattr(be, "calls", 0) + 1
+        seed = (eng.seed * 7919 + be.calls) & 0xFFFFFFFFFFFFFFFF
+        utt = be.forward(bert_sent, bert_sent_type, bert_sent_mask, train=True,
+                         drop=model.training, seed=seed)
+        ctx.model, ctx.names, ctx.call = model, names, be.calls
+        return utt.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        be = ctx.model.engine.bert
+        if be.calls != ctx.call:
+            raise MmdaError("backward() after a newer forward(): the engine keeps one step of "
+                            "saved activations")
+        P = be.params()
+        train = be.trainable()
+        G = {n: torch.zeros_like(P[n]) for n in ctx.names if n in train}
+        be.backward(G, g.contiguous())
+        return (None,) * 5 + tuple(G.get(n) for n in ctx.names)
 
 
 def misa_apply(model, sentences, visual, acoustic, lengths, bert_sent, bert_sent_type,
@@ -958,7 +986,13 @@ def misa_apply(model, sentences, visual, acoustic, lengths, bert_sent, bert_sent
     if eng.use_bert:
         if bert_sent is None:
             raise MmdaError("use_bert=True needs bert_sent / bert_sent_type / bert_sent_mask")
-        utt_text = _bert_utterance(model, bert_sent, bert_sent_type, bert_sent_mask)
+        bnamed = [("bertmodel." + n, p) for n, p in model.bertmodel.named_parameters()]
+        if torch.is_grad_enabled() and any(p.requires_grad for _, p in bnamed):
+            utt_text = _BertFunction.apply(model, bert_sent, bert_sent_type, bert_sent_mask,
+                                           tuple(n for n, _ in bnamed), *[p for _, p in bnamed])
+        else:
+            utt_text = eng.bert.forward(bert_sent, bert_sent_type, bert_sent_mask, train=False,
+                                        drop=False, seed=0).clone()
     needs_grad = torch.is_grad_enabled() and (any(p.requires_grad for _, p in named) or
                                               (utt_text is not None and utt_text.requires_grad))
     if needs_grad:

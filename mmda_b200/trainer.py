@@ -36,18 +36,23 @@ def bucket_of(name: str) -> int:
         return 2
     if name.startswith(("arnn", "alayer_norm")):
         return 3
-    if name.startswith(("trnn", "tlayer_norm", "embed.")):
+    if name.startswith("bertmodel.pooler."):          # never used, models.py:186-198
+        return 5
+    if name.startswith(("trnn", "tlayer_norm", "embed.", "bertmodel.")):
         return 4
     if name.startswith("sp_discriminator."):
         return 5
     raise KeyError(name)
 
 
-def plan_arena(named_shapes: List[Tuple[str, Tuple[int, ...]]], use_confid: bool):
+def plan_arena(named_shapes: List[Tuple[str, Tuple[int, ...]]], use_confid: bool, never=()):
     """-> (layout {name: (offset, numel)}, bucket ranges [(lo, hi)] for buckets 0..4, n_active,
-    n_total).  Pure function (unit-tested on CPU)."""
+    n_total).  ``never``: names that receive no gradient (frozen, or unused by this variant): they
+    live past ``n_active`` and the optimizer never touches them.  Pure function (CPU-tested)."""
+    never = set(never)
+
     def bucket(n):
-        if n.startswith("confidence.") and not use_confid:
+        if (n.startswith("confidence.") and not use_confid) or n in never:
             return 5
         return bucket_of(n)
     order = sorted(range(len(named_shapes)), key=lambda i: (bucket(named_shapes[i][0]), i))
@@ -76,10 +81,7 @@ class FusedTrainer:
                  global_batch_stats: bool = True, use_graph: Optional[bool] = None):
         self.model = model
         self.cfg = cfg = model.config
-        if getattr(cfg, "use_bert", False):
-            raise NotImplementedError(
-                "the fused level-2 step covers the LSTM text encoder; with use_bert=True use the "
-                "level-1 drop-in (model(...) + the reference Solver loop), SURVEY.md 8f N1")
+        self.use_bert = bool(getattr(cfg, "use_bert", False))
         self.eng = model.engine
         self.lr = float(cfg.learning_rate if lr is None else lr)
         self.clip = float(cfg.clip)
@@ -115,11 +117,14 @@ class FusedTrainer:
         if not named[0][1].is_cuda and not _engine._DRYRUN:
             raise MmdaError("FusedTrainer needs the model on a CUDA device (model.to('cuda'))")
         dev = named[0][1].device
-        frozen = [n for n, p in named if not p.requires_grad]
-        if frozen:
-            raise MmdaError(f"frozen parameters are not supported by the fused step: {frozen[:3]}")
+        # frozen tensors (src/solver.py:66-73 freezes BERT layers 0-8) and tensors the variant never
+        # differentiates sit past n_active: Adam skips them exactly as torch skips grad=None
+        never = [n for n, p in named if not p.requires_grad]
+        if self.use_bert:
+            never += [n for n, _ in named if n.startswith("tlayer_norm.")]
+        self.frozen = tuple(never)
         self.layout, self.ranges, self.n_active, n_total = plan_arena(
-            [(n, tuple(p.shape)) for n, p in named], self.use_confid)
+            [(n, tuple(p.shape)) for n, p in named], self.use_confid, never)
         self.p_arena = torch.zeros(n_total, dtype=torch.float32, device=dev)
         self.g_arena = torch.zeros(n_total, dtype=torch.float32, device=dev)
         self.G: Dict[str, torch.Tensor] = {}
@@ -129,10 +134,12 @@ class FusedTrainer:
             view.copy_(p.data)
             p.data = view                       # the module's parameters now alias the arena
             self.G[n] = self.g_arena[off:off + sz].view(p.shape)
-        self._alias_ver = tuple(p.data_ptr() for _, p in named)
+        self._alias_ver = tuple(p.data_ptr() for _, p in named) + \
+            tuple(p.requires_grad for _, p in named)
 
     def _check_alias(self):
-        ver = tuple(p.data_ptr() for p in self.model.parameters())
+        ver = tuple(p.data_ptr() for p in self.model.parameters()) + \
+            tuple(p.requires_grad for p in self.model.parameters())
         if ver != self._alias_ver:     # model.to(...) / embed.weight.data = ... after construction
             m, v, step = self.m, self.v, self.step_count
             old_layout = self.layout
@@ -228,22 +235,30 @@ class FusedTrainer:
 
     # ------------------------------------------------------------------ step ---------------
     def _on_ready(self, tag):
-        if self.world == 1:
+        if self.world == 1 or (tag == "enc_t" and self.use_bert and not self._bert_done):
             return
         b = {"fusion": 0, "heads": 1, "enc_v": 2, "enc_a": 3, "enc_t": 4}[tag]
         lo, hi = self.ranges[b]
         if hi > lo:
             self._pending.append(self._allreduce(self.g_arena[lo:hi], async_op=True))
 
-    def forward_backward(self, sentences, visual, acoustic, lengths, labels):
+    def forward_backward(self, sentences, visual, acoustic, lengths, labels, bert=None):
         """zero_grad + forward + losses + backward (+ gradient all-reduce).  Returns the device
-        tensor of the six loss values [cls, diff, sim, recon, conf, total]."""
+        tensor of the six loss values [cls, diff, sim, recon, conf, total].  ``bert`` =
+        (bert_sent, bert_sent_type, bert_sent_mask) when ``config.use_bert``."""
         self._check_alias()
         eng = self.eng
         eng.k.bind_stream()
         eng.k._c("mmda_step_state_advance", _ptr(self.state), self.lr, 0.9, 0.999)
+        utt_text = None
+        if self.use_bert:
+            if bert is None:
+                raise MmdaError("use_bert=True needs bert_sent / bert_sent_type / bert_sent_mask")
+            utt_text = eng.bert.forward(bert[0], bert[1], bert[2], train=True,
+                                        drop=self.model.training, seed=eng.seed ^ 0xB347,
+                                        seed_dev=self.state)
         out = eng.forward(sentences, visual, acoustic, lengths, train=True, want_sp=False,
-                          seed_dev=self.state)
+                          seed_dev=self.state, utt_text=utt_text)
         B = out["scores"].shape[0]
         if labels.shape != (B, eng.NC) or labels.dtype != torch.float32 or \
                 not (labels.is_cuda or _engine._DRYRUN):
@@ -251,7 +266,12 @@ class FusedTrainer:
         self.g_arena[:self.n_active].zero_()
         losses, grads = self.loss_and_grads(out, labels.contiguous(), B)
         self._pending = []
-        eng.backward(self.G, on_ready=self._on_ready, **grads)
+        self._bert_done = False
+        d_utt = eng.backward(self.G, on_ready=self._on_ready, **grads)
+        if self.use_bert:
+            eng.bert.backward(self.G, d_utt)
+            self._bert_done = True
+            self._on_ready("enc_t")
         for w in self._pending:
             w.wait()
         self._pending = []
@@ -265,15 +285,19 @@ class FusedTrainer:
              _ptr(self.v), self.n_active, self.step_count, self.lr, self.clip, 0.9, 0.999, 1e-8,
              1.0, _ptr(self.state))
 
-    def _eager_step(self, sentences, visual, acoustic, lengths, labels):
-        losses = self.forward_backward(sentences, visual, acoustic, lengths, labels)
+    def _eager_step(self, sentences, visual, acoustic, lengths, labels, bert=None):
+        losses = self.forward_backward(sentences, visual, acoustic, lengths, labels, bert)
         self.optimizer_step()
         return losses
 
-    def step(self, sentences, visual, acoustic, lengths, labels):
+    def step(self, sentences, visual, acoustic, lengths, labels, bert_sent=None,
+             bert_sent_type=None, bert_sent_mask=None):
         """One optimisation step.  With ``use_graph`` (default on one GPU) the kernel sequence of
         a repeated (shapes, lengths) pattern is captured once into a CUDA graph -- multi-stream
         forks included -- and replayed; per-step scalars live in ``self.state`` on the device."""
+        if self.use_bert:       # long step (12 transformer layers): launch overhead is noise
+            return self._eager_step(sentences, visual, acoustic, lengths, labels,
+                                    (bert_sent, bert_sent_type, bert_sent_mask))
         if not self.use_graph or _engine._DRYRUN:
             return self._eager_step(sentences, visual, acoustic, lengths, labels)
         key = (tuple(sentences.shape), tuple(visual.shape), tuple(acoustic.shape),
@@ -310,5 +334,9 @@ class FusedTrainer:
         Returns the loss tensor on the device; ``.tolist()`` it to read the values."""
         dev = device or self.p_arena.device
         to = lambda t: t.to(dev, non_blocking=True)
+        if self.use_bert:
+            return self.step(to(batch.sentences), to(batch.visual), to(batch.acoustic),
+                             batch.lengths, to(batch.labels), to(batch.bert_sent),
+                             to(batch.bert_sent_type), to(batch.bert_sent_mask))
         return self.step(to(batch.sentences), to(batch.visual), to(batch.acoustic), batch.lengths,
                          to(batch.labels))
