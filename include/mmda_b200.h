@@ -77,6 +77,9 @@ int mmda_gemm_tc(int kind, int a_mn, int b_mn, int M, int N, int K, const void* 
                  const void* A_lo, int lda, const void* B_hi, const void* B_lo, int ldb, float alpha,
                  float* C, int ldc, const float* bias, const float* bias2, int mode, int split_k,
                  int c_row_interleave, mmda_stream_t stream);
+/* A/B knob: 2 = persistent tile loop, dynamic tile scheduler, epilogue overlapped with the next
+ * tile's MMAs (default); 1 = one output tile per CTA. */
+int mmda_gemm_tc_set_version(int version);
 int mmda_split_tf32(const float* x, int ldx, int rows, int cols, float* hi, float* lo, int ldo,
                     mmda_stream_t stream);
 int mmda_cast_bf16(const float* x, int ldx, int rows, int cols, void* out, int ldo,

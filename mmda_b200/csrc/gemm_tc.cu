@@ -316,6 +316,292 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Persistent variant (default).  One CTA per SM pulls 128x128 output tiles (m fastest, so the
+// CTAs running side by side share B tiles in L2) from a global atomic counter -- dynamic, because
+// these GEMMs often run next to the 112-SM recurrence kernel and must be finished by whichever
+// SMs happen to be free.  The TMA ring and the MMA issue run ahead across tile boundaries; the
+// epilogue drains the TMEM accumulators of a tile into REGISTERS (sum of the 3xTF32 partial
+// accumulators: 128 values per thread), releases TMEM, and only then transposes / stores to
+// global memory, so the stores of tile i overlap the MMAs of tile i+1.  bf16 additionally
+// rotates over four TMEM accumulator buffers, so even the drain is hidden.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+struct TcArgs2 {
+  TcArgs a;
+  int tiles_m, tiles_n, split, total;
+  int* sched;          // [0] next tile, [1] finished CTAs (self-resetting)
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
+                const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl,
+                const TcArgs2 q2) {
+  const TcArgs& p = q2.a;
+  constexpr int ESZ = KIND == 0 ? 4 : 2;
+  constexpr int BK = 128 / ESZ;
+  constexpr int UK = 32 / ESZ;
+  constexpr int NPART = KIND == 0 ? 2 : 1;
+  constexpr int STAGES = KIND == 0 ? 3 : 6;
+  constexpr int STAGE_BYTES = 2 * NPART * TILE_BYTES;
+  constexpr int MN_CHUNK = 128 / ESZ;
+  constexpr int N_CHUNKS = 128 / MN_CHUNK;
+  constexpr int CHUNK_BYTES = BK * 128;
+  constexpr int NMAIN = KIND == 0 ? 3 : 1;
+  constexpr int NACC = KIND == 0 ? 4 : 1;
+  constexpr int NBUF = KIND == 0 ? 1 : 4;          // TMEM accumulator buffers
+  constexpr int BUF_COLS = NACC * 128;
+  constexpr int TMEM_COLS = 512;
+  constexpr int RING = 4;                          // tile-id ring depth
+  constexpr uint32_t MN_LAYOUT = KIND == 0 ? 1u : 2u;
+  constexpr uint32_t MN_SBO = KIND == 0 ? 512u : 1024u;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = base + STAGES * STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + NBUF + b); };
+  auto sfull_bar = [&](int r) { return bar_base + 8u * (2 * STAGES + 2 * NBUF + r); };
+  auto sempty_bar = [&](int r) { return bar_base + 8u * (2 * STAGES + 2 * NBUF + RING + r); };
+  constexpr int NBARS = 2 * STAGES + 2 * NBUF + 2 * RING;     // <= 28
+  const uint32_t tmem_slot = bar_base + 8u * NBARS;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  volatile int* tile_ring = reinterpret_cast<volatile int*>(smem_raw + (tmem_slot + 8 - smem_u32(smem_raw)));
+  float* stage_base = reinterpret_cast<float*>(smem_raw + (bar_base + 512 - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kb_total = (p.K + BK - 1) / BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int b = 0; b < NBUF; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4); }
+    for (int r = 0; r < RING; ++r) { mbar_init(sfull_bar(r), 1); mbar_init(sempty_bar(r), 5); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot_ptr;
+
+  // tile id -> (m0, n0, k-block range)
+  auto decode = [&](int tile, int& m0, int& n0, int& kb_beg, int& num_kb, int& z) {
+    const int mi = tile % q2.tiles_m;
+    const int rest = tile / q2.tiles_m;
+    const int ni = rest % q2.tiles_n;
+    z = rest / q2.tiles_n;
+    m0 = mi * BM; n0 = ni * BN;
+    kb_beg = z * p.kb_per_split;
+    const int kb_end = min(kb_total, kb_beg + p.kb_per_split);
+    num_kb = max(0, kb_end - kb_beg);
+  };
+
+  if (warp == 0) {
+    // ===================== scheduler + TMA producer =====================
+    if (lane == 0) {
+      int g = 0;                                   // k-blocks issued by this CTA so far
+      for (int tl = 0;; ++tl) {
+        const int r = tl % RING;
+        mbar_wait(sempty_bar(r), ((tl / RING) & 1) ^ 1);
+        const int tile = atomicAdd(q2.sched, 1);
+        tile_ring[r] = tile;
+        __threadfence_block();
+        mbar_arrive(sfull_bar(r));
+        if (tile >= q2.total) break;
+        int m0, n0, kb_beg, num_kb, z;
+        decode(tile, m0, n0, kb_beg, num_kb, z);
+        for (int i = 0; i < num_kb; ++i, ++g) {
+          const int s = g % STAGES, it = g / STAGES;
+          mbar_wait(empty_bar(s), (it & 1) ^ 1);
+          const uint32_t st = base + s * STAGE_BYTES;
+          mbar_expect_tx(full_bar(s), STAGE_BYTES);
+          const int k0 = (kb_beg + i) * BK;
+#pragma unroll
+          for (int part = 0; part < NPART; ++part) {
+            const CUtensorMap* mA = part == 0 ? &mapAh : &mapAl;
+            const CUtensorMap* mB = part == 0 ? &mapBh : &mapBl;
+            const uint32_t sa = st + part * TILE_BYTES;
+            const uint32_t sb = st + (NPART + part) * TILE_BYTES;
+            if (p.a_mn) {
+              for (int c = 0; c < N_CHUNKS; ++c)
+                tma_load_2d(sa + c * CHUNK_BYTES, mA, full_bar(s), m0 + c * MN_CHUNK, k0);
+            } else {
+              tma_load_2d(sa, mA, full_bar(s), k0, m0);
+            }
+            if (p.b_mn) {
+              for (int c = 0; c < N_CHUNKS; ++c)
+                tma_load_2d(sb + c * CHUNK_BYTES, mB, full_bar(s), n0 + c * MN_CHUNK, k0);
+            } else {
+              tma_load_2d(sb, mB, full_bar(s), k0, n0);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t fmt = KIND == 0 ? 2u : 1u;
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)p.a_mn << 15) |
+                             ((uint32_t)p.b_mn << 16) | ((uint32_t)(BN >> 3) << 17) |
+                             ((uint32_t)(BM >> 4) << 24);
+      int g = 0;
+      for (int tl = 0;; ++tl) {
+        const int r = tl % RING;
+        mbar_wait(sfull_bar(r), (tl / RING) & 1);
+        const int tile = tile_ring[r];
+        mbar_arrive(sempty_bar(r));
+        if (tile >= q2.total) break;
+        int m0, n0, kb_beg, num_kb, z;
+        decode(tile, m0, n0, kb_beg, num_kb, z);
+        const int buf = tl % NBUF;
+        mbar_wait(tempty_bar(buf), ((tl / NBUF) & 1) ^ 1);   // epilogue has drained this buffer
+        tc_fence_after();
+        const uint32_t acc0 = tmem_acc + buf * BUF_COLS;
+        for (int i = 0; i < num_kb; ++i, ++g) {
+          const int s = g % STAGES, it = g / STAGES;
+          mbar_wait(full_bar(s), it & 1);
+          tc_fence_after();
+          const uint32_t st = base + s * STAGE_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < BK / UK; ++ks) {
+            const uint32_t offA = p.a_mn ? ks * UK * 128 : ks * 32;
+            const uint32_t offB = p.b_mn ? ks * UK * 128 : ks * 32;
+            const uint32_t lboA = p.a_mn ? CHUNK_BYTES : 16, lboB = p.b_mn ? CHUNK_BYTES : 16;
+            const uint32_t sboA = p.a_mn ? MN_SBO : 1024u, sboB = p.b_mn ? MN_SBO : 1024u;
+            const uint32_t ltA = p.a_mn ? MN_LAYOUT : 2u, ltB = p.b_mn ? MN_LAYOUT : 2u;
+            const uint64_t dAh = make_desc(st + offA, lboA, sboA, ltA);
+            const uint64_t dBh = make_desc(st + NPART * TILE_BYTES + offB, lboB, sboB, ltB);
+            const int gk = i * (BK / UK) + ks;
+            if (KIND == 0) {
+              const uint64_t dAl = make_desc(st + TILE_BYTES + offA, lboA, sboA, ltA);
+              const uint64_t dBl = make_desc(st + 3 * TILE_BYTES + offB, lboB, sboB, ltB);
+              const uint32_t cross = acc0 + NMAIN * 128;
+              tc_mma<KIND>(cross, dAl, dBh, idesc, gk > 0 ? 1u : 0u);
+              tc_mma<KIND>(cross, dAh, dBl, idesc, 1u);
+              tc_mma<KIND>(acc0 + (gk % NMAIN) * 128, dAh, dBh, idesc, gk >= NMAIN ? 1u : 0u);
+            } else {
+              tc_mma<KIND>(acc0, dAh, dBh, idesc, gk > 0 ? 1u : 0u);
+            }
+          }
+          tc_commit(empty_bar(s));
+        }
+        tc_commit(tfull_bar(buf));
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int q = warp & 3;
+    float* stage = stage_base + (warp - 2) * (32 * 33);
+    for (int tl = 0;; ++tl) {
+      const int r = tl % RING;
+      mbar_wait(sfull_bar(r), (tl / RING) & 1);
+      const int tile = tile_ring[r];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sempty_bar(r));
+      if (tile >= q2.total) break;
+      int m0, n0, kb_beg, num_kb, z;
+      decode(tile, m0, n0, kb_beg, num_kb, z);
+      const int buf = tl % NBUF;
+      mbar_wait(tfull_bar(buf), (tl / NBUF) & 1);
+      tc_fence_after();
+      // ---- phase 1: TMEM -> registers (sum of the partial accumulators), then release TMEM ----
+      float acc[BN / 32][32];
+#pragma unroll
+      for (int cc = 0; cc < BN / 32; ++cc)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[cc][j] = 0.f;
+      if (num_kb > 0) {
+        const int ksteps = num_kb * (BK / UK);
+        const int n_used = KIND == 0 ? (ksteps < NMAIN ? ksteps : NMAIN) + 1 : 1;
+#pragma unroll
+        for (int cc = 0; cc < BN / 32; ++cc) {
+#pragma unroll 1
+          for (int a = 0; a < n_used; ++a) {
+            const int acc_id = (KIND == 0 && a == n_used - 1) ? NMAIN : a;
+            const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + buf * BUF_COLS +
+                                   acc_id * 128 + cc * 32;
+            uint32_t t[32];
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]),
+                  "=r"(t[7]), "=r"(t[8]), "=r"(t[9]), "=r"(t[10]), "=r"(t[11]), "=r"(t[12]), "=r"(t[13]),
+                  "=r"(t[14]), "=r"(t[15]), "=r"(t[16]), "=r"(t[17]), "=r"(t[18]), "=r"(t[19]),
+                  "=r"(t[20]), "=r"(t[21]), "=r"(t[22]), "=r"(t[23]), "=r"(t[24]), "=r"(t[25]),
+                  "=r"(t[26]), "=r"(t[27]), "=r"(t[28]), "=r"(t[29]), "=r"(t[30]), "=r"(t[31])
+                : "r"(taddr)
+                : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[cc][j] += __uint_as_float(t[j]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(buf));     // 4 epilogue warps -> buffer free
+      // ---- phase 2: transpose through shared memory, coalesced stores (overlaps the next tile) ----
+#pragma unroll
+      for (int cc = 0; cc < BN / 32; ++cc) {
+        const int nb = n0 + cc * 32;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = acc[cc][j];
+        __syncwarp();
+        const int col = nb + lane;
+        if (col < p.N) {
+          float bsum = 0.f;
+          if (z == 0) {
+            if (p.bias) bsum += p.bias[col];
+            if (p.bias2) bsum += p.bias2[col];
+          }
+          const int row_base = m0 + q * 32;
+#pragma unroll 4
+          for (int rr = 0; rr < 32; ++rr) {
+            const int grow = row_base + rr;
+            if (grow >= p.M) break;
+            const int row_out = p.c_ilv ? (grow & 3) * p.c_ilv + (grow >> 2) : grow;
+            float* cp = p.C + (size_t)row_out * p.ldc + col;
+            const float v = p.alpha * stage[rr * 33 + lane] + bsum;
+            if (p.mode == 2) atomicAdd(cp, v);
+            else if (p.mode == 1) *cp += v;
+            else *cp = v;
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc),
+                 "n"(TMEM_COLS)
+                 : "memory");
+  }
+  if (threadIdx.x == 0) {      // the last CTA re-arms the scheduler slot for the next launch
+    __threadfence();
+    const int done = atomicAdd(q2.sched + 1, 1);
+    if (done == (int)gridDim.x - 1) {
+      q2.sched[0] = 0;
+      q2.sched[1] = 0;
+      __threadfence();
+    }
+  }
+}
+
 // ---- elementwise operand preparation ----
 // hi = tf32(x) (round to nearest, ties away), lo = x - hi (exact in fp32)
 __global__ void split_tf32_kernel(const float* __restrict__ x, int ldx, int rows, int cols,
@@ -381,9 +667,31 @@ int encode_map(CUtensorMap* map, int kind, const void* ptr, long rows, long cols
   return MMDA_OK;
 }
 
+int g_tc_version = 2;          // 2 = persistent kernel (default), 1 = one tile per CTA
+int* g_sched = nullptr;        // ring of self-resetting scheduler slots (2 ints each)
+int g_sched_next = 0;
+constexpr int SCHED_SLOTS = 4096;
+
+int* next_sched_slot() {
+  if (g_sched == nullptr) {
+    if (cudaMalloc(&g_sched, SCHED_SLOTS * 2 * sizeof(int)) != cudaSuccess) return nullptr;
+    if (cudaMemset(g_sched, 0, SCHED_SLOTS * 2 * sizeof(int)) != cudaSuccess) return nullptr;
+  }
+  int* slot = g_sched + 2 * g_sched_next;
+  g_sched_next = (g_sched_next + 1) % SCHED_SLOTS;
+  return slot;
+}
+
 }  // namespace
 
 extern "C" {
+
+// A/B knob: 2 = persistent tile loop with overlapped epilogue (default), 1 = one tile per CTA
+int mmda_gemm_tc_set_version(int v) {
+  MMDA_REQUIRE(v == 1 || v == 2, "gemm_tc: version must be 1 or 2");
+  g_tc_version = v;
+  return MMDA_OK;
+}
 
 int mmda_split_tf32(const float* x, int ldx, int rows, int cols, float* hi, float* lo, int ldo,
                     cudaStream_t stream) {
@@ -454,6 +762,31 @@ int mmda_gemm_tc(int kind, int a_mn, int b_mn, int M, int N, int K, const void* 
   a.mode = split_k > 1 ? 2 : mode;
   a.kb_per_split = (kb_total + split_k - 1) / split_k;
   a.c_ilv = c_row_interleave;
+  if (g_tc_version == 2) {
+    TcArgs2 a2;
+    a2.a = a;
+    a2.tiles_m = (M + BM - 1) / BM; a2.tiles_n = (N + BN - 1) / BN; a2.split = split_k;
+    a2.total = a2.tiles_m * a2.tiles_n * split_k;
+    a2.sched = next_sched_slot();
+    MMDA_REQUIRE(a2.sched != nullptr, "gemm_tc: cannot allocate the tile scheduler slots");
+    static int n_sm = 0;
+    if (n_sm == 0) {
+      int dev = 0;
+      MMDA_CUDA(cudaGetDevice(&dev));
+      MMDA_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int ctas = a2.total < n_sm ? a2.total : n_sm;
+    constexpr int smem2 = 12 * TILE_BYTES + 1024 + 512 + 4 * 32 * 33 * 4;
+    if (kind == 0) {
+      MMDA_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+      gemm_tc2_kernel<0><<<ctas, NUM_THREADS, smem2, stream>>>(mAh, mAl, mBh, mBl, a2);
+    } else {
+      MMDA_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+      gemm_tc2_kernel<1><<<ctas, NUM_THREADS, smem2, stream>>>(mAh, mAl, mBh, mBl, a2);
+    }
+    MMDA_CHECK_LAUNCH();
+    return MMDA_OK;
+  }
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, split_k);
   if (kind == 0) {
     constexpr int smem = 3 * 4 * TILE_BYTES + 1024 + 256 + 4 * 32 * 33 * 4;

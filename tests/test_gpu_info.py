@@ -74,3 +74,44 @@ def test_info_oracle_on_cuda_vs_fused_step():
     with open(os.path.join(out, "info_oracle_cuda.json"), "w") as f:
         json.dump(info, f, indent=1)
     assert abs(first["ref"] - first["ours"]) <= 0.05 * abs(first["ref"])    # dropout masks differ
+
+
+def test_info_hf_bert_on_cuda_c4():
+    """Informational: the oracle's HF BertModel + torch modules on the same B200 at the C4 shape
+    (B=512, seq 50+2, layers 0-8 frozen, fp32, eager PyTorch) -- the library baseline the
+    hand-written BERT path (tools/bench_c4.py) is compared with."""
+    from mmda_b200.config import mosei_config
+    from mmda_b200.synthetic import batch_for
+    from oracle.misa_oracle import oracle_build, oracle_optimizer, oracle_step
+    dev = torch.device("cuda:0")
+    cfg = mosei_config(vocab_size=20000, batch_size=512, use_bert=True)
+    ref = oracle_build(cfg, seed=1234)
+    for n, p in ref.named_parameters():
+        if "bertmodel.encoder.layer" in n and int(n.split("encoder.layer.")[-1].split(".")[0]) <= 8:
+            p.requires_grad = False
+    ref = ref.to(dev).train()
+    opt = oracle_optimizer(ref, cfg)
+    b = batch_for(cfg, seed=1, lengths="full")
+    db = type(b)(b.sentences.to(dev), b.visual.to(dev), b.acoustic.to(dev), b.labels.to(dev),
+                 b.lengths, b.bert_sent.to(dev), b.bert_sent_type.to(dev), b.bert_sent_mask.to(dev))
+    res = {}
+    for tf32 in (False, True):
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        for _ in range(2):
+            oracle_step(ref, db, cfg, opt)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(4):
+            oracle_step(ref, db, cfg, opt)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 4
+        res["tf32_matmul" if tf32 else "fp32_matmul"] = {"ms_per_step": ms,
+                                                         "samples_per_s": 512 / ms * 1e3}
+    torch.backends.cuda.matmul.allow_tf32 = False
+    out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "info_hf_bert_cuda_c4.json"), "w") as f:
+        json.dump({"workload": "C4: oracle (HF BertModel + cuDNN LSTM, eager PyTorch) on cuda:0, "
+                               "B=512, seq 50+2, layers 0-8 frozen, train mode", **res}, f, indent=1)
