@@ -49,22 +49,34 @@ __global__ void bert_embed_bwd_kernel(const float* __restrict__ d, const long lo
 }
 
 // ---------------------------------------------------------------- GELU (erf form) ----------
-__global__ void gelu_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, size_t n) {
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
-       i += (size_t)gridDim.x * blockDim.x) {
-    const float v = x[i];
-    y[i] = 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
+__device__ __forceinline__ float gelu_f(float v) {
+  return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
+}
+__device__ __forceinline__ float gelu_grad_f(float v) {
+  const float cdf = 0.5f * (1.f + erff(v * 0.70710678118654752f));
+  const float pdf = 0.39894228040143268f * expf(-0.5f * v * v);
+  return cdf + v * pdf;
+}
+// n4 = n / 4 float4 groups (the host passes the scalar tail separately)
+__global__ void gelu_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, size_t n4,
+                                size_t n) {
+  const size_t t0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = t0; i < n4; i += stride) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    reinterpret_cast<float4*>(y)[i] = make_float4(gelu_f(v.x), gelu_f(v.y), gelu_f(v.z), gelu_f(v.w));
   }
+  for (size_t i = n4 * 4 + t0; i < n; i += stride) y[i] = gelu_f(x[i]);
 }
 __global__ void gelu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
-                                float* __restrict__ dx, size_t n) {
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
-       i += (size_t)gridDim.x * blockDim.x) {
-    const float v = x[i];
-    const float cdf = 0.5f * (1.f + erff(v * 0.70710678118654752f));
-    const float pdf = 0.39894228040143268f * expf(-0.5f * v * v);
-    dx[i] = dy[i] * (cdf + v * pdf);
+                                float* __restrict__ dx, size_t n4, size_t n) {
+  const size_t t0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = t0; i < n4; i += stride) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    const float4 d = reinterpret_cast<const float4*>(dy)[i];
+    reinterpret_cast<float4*>(dx)[i] = make_float4(d.x * gelu_grad_f(v.x), d.y * gelu_grad_f(v.y),
+                                                   d.z * gelu_grad_f(v.z), d.w * gelu_grad_f(v.w));
   }
+  for (size_t i = n4 * 4 + t0; i < n; i += stride) dx[i] = dy[i] * gelu_grad_f(x[i]);
 }
 
 // ---------------------------------------------------------------- masked mean --------------
@@ -95,134 +107,198 @@ __global__ void masked_mean_bwd_kernel(const float* __restrict__ dutt,
 
 // ---------------------------------------------------------------- self-attention -----------
 // One CTA per (sample, head); the whole S x S problem lives in shared memory (S <= ~100).
+// Every contraction is a register-tiled 4x4 outer product over "k-major" operands
+// (At[k][I], Bt[k][J], leading dimensions multiples of 4, zero padded): two LDS.128 feed 16 FMAs,
+// so the kernels are FMA-issue bound rather than shared-memory bound.
 constexpr int BHD = 64;          // head dim of bert-base
-constexpr int BHDP = BHD + 1;    // padded row pitch: conflict-free row-vs-row dot products
+constexpr int ATT_THREADS = 256;
 
 __device__ __forceinline__ float drop_scale(unsigned long long seed, unsigned stream, unsigned idx,
                                             float p, float inv_keep) {
   return (p > 0.f && rng_uniform(seed, stream, idx) < p) ? 0.f : inv_keep;
 }
 
-__global__ void __launch_bounds__(128)
+// acc[a][b] = sum_k At[k*lda + i0 + a] * Bt[k*ldb + j0 + b]
+__device__ __forceinline__ void mm_tile(const float* __restrict__ At, int lda,
+                                        const float* __restrict__ Bt, int ldb, int K, int i0, int j0,
+                                        float (&acc)[4][4]) {
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+  const float* ap = At + i0;
+  const float* bp = Bt + j0;
+#pragma unroll 4
+  for (int k = 0; k < K; ++k) {
+    const float4 av = *reinterpret_cast<const float4*>(ap + (size_t)k * lda);
+    const float4 bv = *reinterpret_cast<const float4*>(bp + (size_t)k * ldb);
+    const float a4[4] = {av.x, av.y, av.z, av.w}, b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(a4[a], b4[b], acc[a][b]);
+  }
+}
+
+__global__ void __launch_bounds__(ATT_THREADS)
 bert_attn_fwd_kernel(const float* __restrict__ qkv, const long long* __restrict__ mask,
                      float* __restrict__ ctx, float* __restrict__ probs, int S, int nhead,
                      float scale, float p_drop, unsigned long long seed,
                      const unsigned long long* __restrict__ seed_dev, unsigned stream) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   if (seed_dev) seed += seed_dev[0] * 0x9E3779B97F4A7C15ULL;
   const int b = blockIdx.x / nhead, h = blockIdx.x % nhead;
-  const int Hd = nhead * BHD, ld = 3 * Hd, SP = S + 1;
-  float* Qs = sm;
-  float* Ks = Qs + S * BHDP;
-  float* Vs = Ks + S * BHDP;
-  float* Ps = Vs + S * BHDP;     // [S][S+1]
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int idx = tid; idx < S * BHD; idx += blockDim.x) {
+  const int Hd = nhead * BHD, ld = 3 * Hd;
+  const int S4 = (S + 3) & ~3;
+  float* Qt = sm;                  // [64][S4]
+  float* Kt = Qt + BHD * S4;       // [64][S4]
+  float* Vs = Kt + BHD * S4;       // [S4][64]
+  float* Sc = Vs + S4 * BHD;       // [S4][S4] scores -> probabilities
+  float* Pt = Sc + S4 * S4;        // [S4][S4] dropped probabilities, transposed: Pt[j][i]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+  for (int idx = tid; idx < S4 * BHD; idx += blockDim.x) {
     const int s = idx / BHD, c = idx % BHD;
-    const float* r = qkv + (size_t)(b * S + s) * ld + h * BHD + c;
-    Qs[s * BHDP + c] = r[0];
-    Ks[s * BHDP + c] = r[Hd];
-    Vs[s * BHDP + c] = r[2 * Hd];
+    float q = 0.f, k = 0.f, v = 0.f;
+    if (s < S) {
+      const float* r = qkv + (size_t)(b * S + s) * ld + h * BHD + c;
+      q = r[0]; k = r[Hd]; v = r[2 * Hd];
+    }
+    Qt[c * S4 + s] = q;
+    Kt[c * S4 + s] = k;
+    Vs[s * BHD + c] = v;
   }
+  for (int idx = tid; idx < S4 * S4; idx += blockDim.x) Pt[idx] = 0.f;
   __syncthreads();
-  for (int idx = tid; idx < S * S; idx += blockDim.x) {
-    const int i = idx / S, j = idx % S;
-    float acc = 0.f;
-#pragma unroll 16
-    for (int c = 0; c < BHD; ++c) acc = fmaf(Qs[i * BHDP + c], Ks[j * BHDP + c], acc);
-    // HF adds finfo.min to masked keys: the softmax weight is exactly 0
-    Ps[i * SP + j] = mask[(size_t)b * S + j] != 0 ? acc * scale : -INFINITY;
+  const int nb = S4 >> 2;
+  for (int blk = tid; blk < nb * nb; blk += blockDim.x) {
+    const int i0 = (blk / nb) * 4, j0 = (blk % nb) * 4;
+    float acc[4][4];
+    mm_tile(Qt, S4, Kt, S4, BHD, i0, j0, acc);
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int j = j0 + c;
+        // HF adds finfo.min to masked keys: the softmax weight is exactly 0
+        Sc[(i0 + a) * S4 + j] = (j < S && mask[(size_t)b * S + j] != 0) ? acc[a][c] * scale : -INFINITY;
+      }
   }
   __syncthreads();
   const float inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
-  for (int i = warp; i < S; i += (blockDim.x >> 5)) {
+  for (int i = warp; i < S; i += nw) {
     float mx = -INFINITY;
-    for (int j = lane; j < S; j += 32) mx = fmaxf(mx, Ps[i * SP + j]);
+    for (int j = lane; j < S; j += 32) mx = fmaxf(mx, Sc[i * S4 + j]);
     mx = warp_max(mx);
     float sum = 0.f;
     for (int j = lane; j < S; j += 32) {
-      const float e = expf(Ps[i * SP + j] - mx);
-      Ps[i * SP + j] = e;
+      const float e = expf(Sc[i * S4 + j] - mx);
+      Sc[i * S4 + j] = e;
       sum += e;
     }
     sum = warp_sum(sum);
     const float inv = 1.f / sum;
     const unsigned base = (unsigned)(((b * nhead + h) * S + i) * S);
     for (int j = lane; j < S; j += 32) {
-      const float pr = Ps[i * SP + j] * inv;
+      const float pr = Sc[i * S4 + j] * inv;
       if (probs) probs[(size_t)base + j] = pr;
-      Ps[i * SP + j] = pr * drop_scale(seed, stream, base + j, p_drop, inv_keep);
+      Pt[j * S4 + i] = pr * drop_scale(seed, stream, base + j, p_drop, inv_keep);
     }
   }
   __syncthreads();
-  for (int idx = tid; idx < S * BHD; idx += blockDim.x) {
-    const int i = idx / BHD, c = idx % BHD;
-    float acc = 0.f;
-    for (int j = 0; j < S; ++j) acc = fmaf(Ps[i * SP + j], Vs[j * BHDP + c], acc);
-    ctx[(size_t)(b * S + i) * Hd + h * BHD + c] = acc;
+  for (int blk = tid; blk < nb * (BHD / 4); blk += blockDim.x) {
+    const int i0 = (blk / (BHD / 4)) * 4, c0 = (blk % (BHD / 4)) * 4;
+    float acc[4][4];
+    mm_tile(Pt, S4, Vs, BHD, S, i0, c0, acc);
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+      if (i0 + a < S)
+        *reinterpret_cast<float4*>(ctx + (size_t)(b * S + i0 + a) * Hd + h * BHD + c0) =
+            make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
   }
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(ATT_THREADS)
 bert_attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ probs,
                      const float* __restrict__ dctx, float* __restrict__ dqkv, int S, int nhead,
                      float scale, float p_drop, unsigned long long seed,
                      const unsigned long long* __restrict__ seed_dev, unsigned stream) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   if (seed_dev) seed += seed_dev[0] * 0x9E3779B97F4A7C15ULL;
   const int b = blockIdx.x / nhead, h = blockIdx.x % nhead;
-  const int Hd = nhead * BHD, ld = 3 * Hd, SP = S + 1;
-  float* Qs = sm;
-  float* Ks = Qs + S * BHDP;
-  float* Vs = Ks + S * BHDP;
-  float* Cs = Vs + S * BHDP;     // d(ctx)
-  float* Ps = Cs + S * BHDP;     // probabilities, later dropped probabilities
-  float* Ds = Ps + S * SP;       // d(dropped probs), later d(scores)
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int Hd = nhead * BHD, ld = 3 * Hd;
+  const int S4 = (S + 3) & ~3;
+  float* Qs = sm;                  // [S4][64]
+  float* Ks = Qs + S4 * BHD;       // [S4][64]
+  float* Vt = Ks + S4 * BHD;       // [64][S4]
+  float* Cs = Vt + BHD * S4;       // d(ctx) [S4][64]
+  float* Ct = Cs + S4 * BHD;       // d(ctx) transposed [64][S4]
+  float* Ps = Ct + BHD * S4;       // [S4][S4] probabilities -> dropped probabilities (row major)
+  float* Ds = Ps + S4 * S4;        // [S4][S4] d(probs) -> d(scores) (row major)
+  float* Dt = Ds + S4 * S4;        // d(scores) transposed
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
   const unsigned base0 = (unsigned)((b * nhead + h) * S * S);
-  for (int idx = tid; idx < S * BHD; idx += blockDim.x) {
+  for (int idx = tid; idx < S4 * BHD; idx += blockDim.x) {
     const int s = idx / BHD, c = idx % BHD;
-    const float* r = qkv + (size_t)(b * S + s) * ld + h * BHD + c;
-    Qs[s * BHDP + c] = r[0];
-    Ks[s * BHDP + c] = r[Hd];
-    Vs[s * BHDP + c] = r[2 * Hd];
-    Cs[s * BHDP + c] = dctx[(size_t)(b * S + s) * Hd + h * BHD + c];
+    float q = 0.f, k = 0.f, v = 0.f, dc = 0.f;
+    if (s < S) {
+      const float* r = qkv + (size_t)(b * S + s) * ld + h * BHD + c;
+      q = r[0]; k = r[Hd]; v = r[2 * Hd];
+      dc = dctx[(size_t)(b * S + s) * Hd + h * BHD + c];
+    }
+    Qs[s * BHD + c] = q;
+    Ks[s * BHD + c] = k;
+    Vt[c * S4 + s] = v;
+    Cs[s * BHD + c] = dc;
+    Ct[c * S4 + s] = dc;
   }
-  for (int idx = tid; idx < S * S; idx += blockDim.x)
-    Ps[(idx / S) * SP + idx % S] = probs[(size_t)base0 + idx];
+  for (int idx = tid; idx < S4 * S4; idx += blockDim.x) {
+    const int i = idx / S4, j = idx % S4;
+    Ps[idx] = (i < S && j < S) ? probs[(size_t)base0 + i * S + j] : 0.f;
+    Dt[idx] = 0.f;
+  }
   __syncthreads();
   const float inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
-  for (int idx = tid; idx < S * S; idx += blockDim.x) {   // d(dropped probs) -> d(probs)
-    const int i = idx / S, j = idx % S;
-    float acc = 0.f;
-#pragma unroll 16
-    for (int c = 0; c < BHD; ++c) acc = fmaf(Cs[i * BHDP + c], Vs[j * BHDP + c], acc);
-    Ds[i * SP + j] = acc * drop_scale(seed, stream, base0 + idx, p_drop, inv_keep);
+  const int nb = S4 >> 2;
+  for (int blk = tid; blk < nb * nb; blk += blockDim.x) {      // d(dropped probs) -> d(probs)
+    const int i0 = (blk / nb) * 4, j0 = (blk % nb) * 4;
+    float acc[4][4];
+    mm_tile(Ct, S4, Vt, S4, BHD, i0, j0, acc);
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int i = i0 + a, j = j0 + c;
+        Ds[i * S4 + j] = (i < S && j < S)
+            ? acc[a][c] * drop_scale(seed, stream, base0 + i * S + j, p_drop, inv_keep) : 0.f;
+      }
   }
   __syncthreads();
-  for (int i = warp; i < S; i += (blockDim.x >> 5)) {      // softmax backward, then dropout of P
+  for (int i = warp; i < S; i += nw) {      // softmax backward; probabilities -> dropped ones
     float r = 0.f;
-    for (int j = lane; j < S; j += 32) r += Ds[i * SP + j] * Ps[i * SP + j];
+    for (int j = lane; j < S; j += 32) r += Ds[i * S4 + j] * Ps[i * S4 + j];
     r = warp_sum(r);
     for (int j = lane; j < S; j += 32) {
-      const float pr = Ps[i * SP + j];
-      Ds[i * SP + j] = pr * (Ds[i * SP + j] - r) * scale;
-      Ps[i * SP + j] = pr * drop_scale(seed, stream, base0 + i * S + j, p_drop, inv_keep);
+      const float pr = Ps[i * S4 + j];
+      const float ds = pr * (Ds[i * S4 + j] - r) * scale;
+      Ds[i * S4 + j] = ds;
+      Dt[j * S4 + i] = ds;
+      Ps[i * S4 + j] = pr * drop_scale(seed, stream, base0 + i * S + j, p_drop, inv_keep);
     }
   }
   __syncthreads();
-  for (int idx = tid; idx < S * BHD; idx += blockDim.x) {
-    const int s = idx / BHD, c = idx % BHD;
-    float dq = 0.f, dk = 0.f, dv = 0.f;
-    for (int j = 0; j < S; ++j) {
-      dq = fmaf(Ds[s * SP + j], Ks[j * BHDP + c], dq);     // dQ[s] = sum_j dS[s][j] K[j]
-      dk = fmaf(Ds[j * SP + s], Qs[j * BHDP + c], dk);     // dK[s] = sum_i dS[i][s] Q[i]
-      dv = fmaf(Ps[j * SP + s], Cs[j * BHDP + c], dv);     // dV[s] = sum_i Pd[i][s] dC[i]
-    }
-    float* o = dqkv + (size_t)(b * S + s) * ld + h * BHD + c;
-    o[0] = dq;
-    o[Hd] = dk;
-    o[2 * Hd] = dv;
+  const int cb = BHD / 4;
+  for (int blk = tid; blk < 3 * nb * cb; blk += blockDim.x) {
+    const int which = blk / (nb * cb), rem = blk % (nb * cb);
+    const int s0 = (rem / cb) * 4, c0 = (rem % cb) * 4;
+    float acc[4][4];
+    if (which == 0) mm_tile(Dt, S4, Ks, BHD, S, s0, c0, acc);        // dQ[i] = sum_j dS[i][j] K[j]
+    else if (which == 1) mm_tile(Ds, S4, Qs, BHD, S, s0, c0, acc);   // dK[j] = sum_i dS[i][j] Q[i]
+    else mm_tile(Ps, S4, Cs, BHD, S, s0, c0, acc);                   // dV[j] = sum_i Pd[i][j] dC[i]
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+      if (s0 + a < S)
+        *reinterpret_cast<float4*>(dqkv + (size_t)(b * S + s0 + a) * ld + which * Hd + h * BHD + c0) =
+            make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
   }
 }
 
@@ -254,14 +330,18 @@ int mmda_bert_embed_backward(const float* d, const long long* ids, const long lo
 
 int mmda_gelu_forward(const float* x, float* y, long long n, cudaStream_t stream) {
   if (n <= 0) return MMDA_OK;
-  gelu_fwd_kernel<<<ew_grid_b((size_t)n), 256, 0, stream>>>(x, y, (size_t)n);
+  const bool v4 = (((uintptr_t)x | (uintptr_t)y) & 15) == 0;
+  const size_t n4 = v4 ? (size_t)n / 4 : 0;
+  gelu_fwd_kernel<<<ew_grid_b(v4 ? n4 + 1 : (size_t)n), 256, 0, stream>>>(x, y, n4, (size_t)n);
   MMDA_CHECK_LAUNCH();
   return MMDA_OK;
 }
 
 int mmda_gelu_backward(const float* dy, const float* x, float* dx, long long n, cudaStream_t stream) {
   if (n <= 0) return MMDA_OK;
-  gelu_bwd_kernel<<<ew_grid_b((size_t)n), 256, 0, stream>>>(dy, x, dx, (size_t)n);
+  const bool v4 = (((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dx) & 15) == 0;
+  const size_t n4 = v4 ? (size_t)n / 4 : 0;
+  gelu_bwd_kernel<<<ew_grid_b(v4 ? n4 + 1 : (size_t)n), 256, 0, stream>>>(dy, x, dx, n4, (size_t)n);
   MMDA_CHECK_LAUNCH();
   return MMDA_OK;
 }
@@ -283,7 +363,8 @@ int mmda_masked_mean_backward(const float* dutt, const long long* mask, int B, i
 }
 
 static int bert_attn_smem(int S, bool bwd) {
-  return (int)(((bwd ? 4 : 3) * S * BHDP + (bwd ? 2 : 1) * S * (S + 1)) * sizeof(float));
+  const int S4 = (S + 3) & ~3;
+  return (int)(((bwd ? 5 : 3) * S4 * BHD + (bwd ? 3 : 2) * S4 * S4) * sizeof(float));
 }
 
 int mmda_bert_attention_forward(const float* qkv, const long long* mask, float* ctx, float* probs,
@@ -295,7 +376,7 @@ int mmda_bert_attention_forward(const float* qkv, const long long* mask, float* 
   MMDA_REQUIRE(B > 0 && S > 0 && smem <= 200 * 1024,
                "bert_attention: sequence %d does not fit the shared-memory resident kernel", S);
   MMDA_CUDA(cudaFuncSetAttribute(bert_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  bert_attn_fwd_kernel<<<B * nhead, 128, smem, stream>>>(qkv, mask, ctx, probs, S, nhead,
+  bert_attn_fwd_kernel<<<B * nhead, ATT_THREADS, smem, stream>>>(qkv, mask, ctx, probs, S, nhead,
                                                          1.0f / sqrtf((float)head_dim), p_drop,
                                                          seed, seed_dev, stream_id);
   MMDA_CHECK_LAUNCH();
@@ -311,7 +392,7 @@ int mmda_bert_attention_backward(const float* qkv, const float* probs, const flo
   MMDA_REQUIRE(B > 0 && S > 0 && smem <= 200 * 1024,
                "bert_attention: sequence %d does not fit the shared-memory resident kernel", S);
   MMDA_CUDA(cudaFuncSetAttribute(bert_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  bert_attn_bwd_kernel<<<B * nhead, 128, smem, stream>>>(qkv, probs, dctx, dqkv, S, nhead,
+  bert_attn_bwd_kernel<<<B * nhead, ATT_THREADS, smem, stream>>>(qkv, probs, dctx, dqkv, S, nhead,
                                                          1.0f / sqrtf((float)head_dim), p_drop,
                                                          seed, seed_dev, stream_id);
   MMDA_CHECK_LAUNCH();

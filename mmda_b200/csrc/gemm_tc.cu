@@ -627,6 +627,41 @@ __global__ void cast_bf16_kernel(const float* __restrict__ x, int ldx, int rows,
     out[(size_t)r * ldo + c] = __float2bfloat16(x[(size_t)r * ldx + c]);
   }
 }
+// 4 elements per thread (16-byte loads / 16- or 8-byte stores): cols, pitches % 4 == 0, aligned bases
+__global__ void split_tf32_v4_kernel(const float* __restrict__ x, int ldx, int rows, int cols4,
+                                     float* __restrict__ hi, float* __restrict__ lo, int ldo) {
+  const size_t n = (size_t)rows * cols4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / cols4, c = (i % cols4) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(x + r * ldx + c);
+    const float in[4] = {v.x, v.y, v.z, v.w};
+    float h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t hb;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(in[j]));
+      h[j] = __uint_as_float(hb);
+      l[j] = in[j] - h[j];
+    }
+    *reinterpret_cast<float4*>(hi + r * ldo + c) = make_float4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<float4*>(lo + r * ldo + c) = make_float4(l[0], l[1], l[2], l[3]);
+  }
+}
+__global__ void cast_bf16_v4_kernel(const float* __restrict__ x, int ldx, int rows, int cols4,
+                                    __nv_bfloat16* __restrict__ out, int ldo) {
+  const size_t n = (size_t)rows * cols4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / cols4, c = (i % cols4) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(x + r * ldx + c);
+    const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<const uint32_t*>(&a);
+    pk.y = *reinterpret_cast<const uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(out + r * ldo + c) = pk;
+  }
+}
 
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                              const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
@@ -697,6 +732,15 @@ int mmda_split_tf32(const float* x, int ldx, int rows, int cols, float* hi, floa
                     cudaStream_t stream) {
   if (rows <= 0 || cols <= 0) return MMDA_OK;
   size_t n = (size_t)rows * cols, g = (n + 255) / 256;
+  if (cols % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0 &&
+      (((uintptr_t)x | (uintptr_t)hi | (uintptr_t)lo) & 15) == 0) {
+    g = (n / 4 + 255) / 256;
+    if (g > 148 * 16) g = 148 * 16;
+    if (g < 1) g = 1;
+    split_tf32_v4_kernel<<<(int)g, 256, 0, stream>>>(x, ldx, rows, cols / 4, hi, lo, ldo);
+    MMDA_CHECK_LAUNCH();
+    return MMDA_OK;
+  }
   if (g > 148 * 16) g = 148 * 16;
   split_tf32_kernel<<<(int)g, 256, 0, stream>>>(x, ldx, rows, cols, hi, lo, ldo);
   MMDA_CHECK_LAUNCH();
@@ -707,6 +751,16 @@ int mmda_cast_bf16(const float* x, int ldx, int rows, int cols, void* out, int l
                    cudaStream_t stream) {
   if (rows <= 0 || cols <= 0) return MMDA_OK;
   size_t n = (size_t)rows * cols, g = (n + 255) / 256;
+  if (cols % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0 && ((uintptr_t)x & 15) == 0 &&
+      ((uintptr_t)out & 7) == 0) {
+    g = (n / 4 + 255) / 256;
+    if (g > 148 * 16) g = 148 * 16;
+    if (g < 1) g = 1;
+    cast_bf16_v4_kernel<<<(int)g, 256, 0, stream>>>(x, ldx, rows, cols / 4,
+                                                    reinterpret_cast<__nv_bfloat16*>(out), ldo);
+    MMDA_CHECK_LAUNCH();
+    return MMDA_OK;
+  }
   if (g > 148 * 16) g = 148 * 16;
   cast_bf16_kernel<<<(int)g, 256, 0, stream>>>(x, ldx, rows, cols,
                                                reinterpret_cast<__nv_bfloat16*>(out), ldo);
