@@ -299,8 +299,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
           const int row_out = p.c_ilv ? (grow & 3) * p.c_ilv + (grow >> 2) : grow;
           float* cp = p.C + (size_t)row_out * p.ldc + col;
           const float v = p.alpha * stage[rr * 33 + lane] + bsum;
-          if (p.mode == 2) atomicAdd(cp, v);
-          else if (p.mode == 1) *cp += v;
+          if (p.mode != 0) atomicAdd(cp, v);   // RED, see the persistent kernel
           else *cp = v;
         }
       }
@@ -575,8 +574,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
             const int row_out = p.c_ilv ? (grow & 3) * p.c_ilv + (grow >> 2) : grow;
             float* cp = p.C + (size_t)row_out * p.ldc + col;
             const float v = p.alpha * stage[rr * 33 + lane] + bsum;
-            if (p.mode == 2) atomicAdd(cp, v);
-            else if (p.mode == 1) *cp += v;
+            // accumulate with RED (fire-and-forget) even without split-K: a load-add-store
+            // per element serialises the warp on global-load latency (measured 8x slower)
+            if (p.mode != 0) atomicAdd(cp, v);
             else *cp = v;
           }
         }
