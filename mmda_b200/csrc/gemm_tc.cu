@@ -335,8 +335,8 @@ struct TcArgs2 {
   int* sched;          // [0] next tile, [1] finished CTAs (self-resetting)
 };
 
-template <int KIND>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int KIND, int RAW>
+__global__ void __launch_bounds__(NUM_THREADS + RAW * 128, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
                 const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl,
                 const TcArgs2 q2) {
@@ -368,7 +368,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
   auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + NBUF + b); };
   auto sfull_bar = [&](int r) { return bar_base + 8u * (2 * STAGES + 2 * NBUF + r); };
   auto sempty_bar = [&](int r) { return bar_base + 8u * (2 * STAGES + 2 * NBUF + RING + r); };
-  constexpr int NBARS = 2 * STAGES + 2 * NBUF + 2 * RING;     // <= 28
+  auto conv_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 * NBUF + 2 * RING + s); };
+  constexpr int NBARS = 3 * STAGES + 2 * NBUF + 2 * RING;     // <= 34
+  // RAW: the operands arrive as plain fp32; TMA lands them in the hi slots and four converter
+  // warps split every stage in shared memory (hi = tf32(x) in place, lo = x - hi next to it) --
+  // half the L2->SM traffic of pre-split operands and no split pass over HBM.  The split is
+  // elementwise, so it is oblivious to the swizzled tile layout.
+  constexpr int TX_BYTES = RAW ? STAGE_BYTES / 2 : STAGE_BYTES;
+  constexpr int RING_READERS = RAW ? 9 : 5;
   const uint32_t tmem_slot = bar_base + 8u * NBARS;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   volatile int* tile_ring = reinterpret_cast<volatile int*>(smem_raw + (tmem_slot + 8 - smem_u32(smem_raw)));
@@ -380,7 +387,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int b = 0; b < NBUF; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4); }
-    for (int r = 0; r < RING; ++r) { mbar_init(sfull_bar(r), 1); mbar_init(sempty_bar(r), 5); }
+    for (int r = 0; r < RING; ++r) { mbar_init(sfull_bar(r), 1); mbar_init(sempty_bar(r), RING_READERS); }
+    for (int s = 0; s < STAGES; ++s) mbar_init(conv_bar(s), 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -424,10 +432,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
           const int s = g % STAGES, it = g / STAGES;
           mbar_wait(empty_bar(s), (it & 1) ^ 1);
           const uint32_t st = base + s * STAGE_BYTES;
-          mbar_expect_tx(full_bar(s), STAGE_BYTES);
+          mbar_expect_tx(full_bar(s), TX_BYTES);
           const int k0 = (kb_beg + i) * BK;
 #pragma unroll
-          for (int part = 0; part < NPART; ++part) {
+          for (int part = 0; part < (RAW ? 1 : NPART); ++part) {
             const CUtensorMap* mA = part == 0 ? &mapAh : &mapAl;
             const CUtensorMap* mB = part == 0 ? &mapBh : &mapBl;
             const uint32_t sa = st + part * TILE_BYTES;
@@ -470,7 +478,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
         const uint32_t acc0 = tmem_acc + buf * BUF_COLS;
         for (int i = 0; i < num_kb; ++i, ++g) {
           const int s = g % STAGES, it = g / STAGES;
-          mbar_wait(full_bar(s), it & 1);
+          mbar_wait(RAW ? conv_bar(s) : full_bar(s), it & 1);
           tc_fence_after();
           const uint32_t st = base + s * STAGE_BYTES;
 #pragma unroll
@@ -497,6 +505,49 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
           tc_commit(empty_bar(s));
         }
         tc_commit(tfull_bar(buf));
+      }
+    }
+  } else if (RAW && warp >= 6) {
+    // ===================== operand converter: fp32 -> (tf32 hi, lo) in shared memory ==========
+    const int ct = threadIdx.x - 6 * 32;           // 0..127
+    int g = 0;
+    for (int tl = 0;; ++tl) {
+      const int r = tl % RING;
+      mbar_wait(sfull_bar(r), (tl / RING) & 1);
+      const int tile = tile_ring[r];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sempty_bar(r));
+      if (tile >= q2.total) break;
+      int m0, n0, kb_beg, num_kb, z;
+      decode(tile, m0, n0, kb_beg, num_kb, z);
+      for (int i = 0; i < num_kb; ++i, ++g) {
+        const int s = g % STAGES, it = g / STAGES;
+        mbar_wait(full_bar(s), it & 1);
+        uint8_t* st = smem_raw + (base + s * STAGE_BYTES - smem_u32(smem_raw));
+#pragma unroll
+        for (int op = 0; op < 2; ++op) {           // A then B: hi slot at 2*op, lo slot at 2*op+1
+          float4* hi = reinterpret_cast<float4*>(st + (2 * op) * TILE_BYTES);
+          float4* lo = reinterpret_cast<float4*>(st + (2 * op + 1) * TILE_BYTES);
+#pragma unroll
+          for (int e = 0; e < TILE_BYTES / 16 / 128; ++e) {
+            const int idx = ct + e * 128;
+            const float4 v = hi[idx];
+            const float in[4] = {v.x, v.y, v.z, v.w};
+            float h[4], l[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint32_t hb;
+              asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(in[c]));
+              h[c] = __uint_as_float(hb);
+              l[c] = in[c] - h[c];
+            }
+            hi[idx] = make_float4(h[0], h[1], h[2], h[3]);
+            lo[idx] = make_float4(l[0], l[1], l[2], l[3]);
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> UMMA reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(conv_bar(s));
       }
     }
   } else {
@@ -776,6 +827,11 @@ int mmda_gemm_tc(int kind, int a_mn, int b_mn, int M, int N, int K, const void* 
                  float* C, int ldc, const float* bias, const float* bias2, int mode, int split_k,
                  int c_row_interleave, cudaStream_t stream) {
   if (M <= 0 || N <= 0) return MMDA_OK;
+  // kind 2: 3xTF32 from plain fp32 operands (A_hi / B_hi point at the fp32 data, the lo pointers
+  // are ignored); the hi/lo split happens in shared memory inside the kernel
+  const bool raw = kind == 2;
+  if (raw) { kind = 0; A_lo = A_hi; B_lo = B_hi; }
+  MMDA_REQUIRE(!raw || g_tc_version == 2, "gemm_tc: kind 2 needs the persistent kernel");
   MMDA_REQUIRE(kind == 0 || kind == 1, "gemm_tc: kind=%d", kind);
   MMDA_REQUIRE(K > 0 && A_hi && B_hi && C, "gemm_tc: bad arguments");
   MMDA_REQUIRE(kind == 1 || (A_lo && B_lo), "gemm_tc: 3xTF32 needs the lo parts");
@@ -831,12 +887,15 @@ int mmda_gemm_tc(int kind, int a_mn, int b_mn, int M, int N, int K, const void* 
     }
     const int ctas = a2.total < n_sm ? a2.total : n_sm;
     constexpr int smem2 = 12 * TILE_BYTES + 1024 + 512 + 4 * 32 * 33 * 4;
-    if (kind == 0) {
-      MMDA_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
-      gemm_tc2_kernel<0><<<ctas, NUM_THREADS, smem2, stream>>>(mAh, mAl, mBh, mBl, a2);
+    if (kind == 0 && raw) {
+      MMDA_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+      gemm_tc2_kernel<0, 1><<<ctas, NUM_THREADS + 128, smem2, stream>>>(mAh, mAl, mBh, mBl, a2);
+    } else if (kind == 0) {
+      MMDA_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+      gemm_tc2_kernel<0, 0><<<ctas, NUM_THREADS, smem2, stream>>>(mAh, mAl, mBh, mBl, a2);
     } else {
-      MMDA_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
-      gemm_tc2_kernel<1><<<ctas, NUM_THREADS, smem2, stream>>>(mAh, mAl, mBh, mBl, a2);
+      MMDA_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+      gemm_tc2_kernel<1, 0><<<ctas, NUM_THREADS, smem2, stream>>>(mAh, mAl, mBh, mBl, a2);
     }
     MMDA_CHECK_LAUNCH();
     return MMDA_OK;

@@ -66,6 +66,10 @@ class Kernels:
                 c_ilv=0):
         """Tensor-core GEMM.  A, B = (hi, lo_or_None) 2-D operand views (unit inner stride)."""
         (Ah, Al), (Bh, Bl) = A, B
+        if kind == 0 and Al is None and Bl is None:
+            kind = 2                     # plain fp32 operands, split in shared memory
+        elif kind == 0 and (Al is None or Bl is None):
+            raise MmdaError("gemm_tc: mixing pre-split and raw 3xTF32 operands")
         self._c("mmda_gemm_tc", kind, int(a_mn), int(b_mn), M, N, K, _ptr(Ah), _ptr(Al), Ah.stride(0),
                 _ptr(Bh), _ptr(Bl), Bh.stride(0), alpha, _ptr(C), C.stride(0), _ptr(bias), None, mode,
                 split_k, c_ilv)
@@ -139,6 +143,9 @@ class MisaEngine:
         # hoisted LSTM GEMMs: tcgen05 path (3xTF32 in fp32 mode, bf16 operands in bf16 mode) where
         # the operand pitches satisfy TMA's 16-byte rule, exact-fp32 SIMT path otherwise
         self.tc_kind = 0 if prec == "fp32" else 1
+        # 3xTF32 operands: plain fp32 tensors, split into tf32 hi/lo inside the GEMM kernel's
+        # shared-memory pipeline (MMDA_TF32_SPLIT=pre: separate split pass, hi/lo arrays in HBM)
+        self.tc_raw = os.environ.get("MMDA_TF32_SPLIT", "smem") != "pre"
         self.use_tc = os.environ.get("MMDA_GEMM", "tc") != "simt"
         # the visual / acoustic encoders run on side streams next to the text encoder (whose
         # cluster kernel occupies 112 of the 148 SMs)
@@ -285,6 +292,10 @@ class MisaEngine:
         Rows land at [row0, row0+rows) of the (possibly larger) buffer `out`."""
         kind = self.tc_kind if kind is None else kind
         rows, cols = x.shape
+        if kind == 0 and self.tc_raw:
+            if out is None and x.stride(1) == 1 and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0:
+                return x, None           # consumed as is
+            raise MmdaError(f"operand {name}: 3xTF32 operands must be 16-byte aligned fp32 views")
         if out is None:
             out = self._prep_buf(name, rows, cols, kind)
         hi, lo = out
@@ -301,6 +312,8 @@ class MisaEngine:
         if kind == 0:
             ld = (cols + 3) // 4 * 4
             hi = self.buf(name + "_hi", rows, ld)[:, :cols]
+            if self.tc_raw:
+                return hi, None
             lo = self.buf(name + "_lo", rows, ld)[:, :cols]
             return hi, lo
         ld = (cols + 7) // 8 * 8
@@ -309,7 +322,7 @@ class MisaEngine:
     def _pack_weights(self, r, P, H, I, kind, want_bias=True):
         """Stacked gate-interleaved copy of layer r's W_ih (both directions) for GEMM kind
         `kind` (-1: plain fp32 for the SIMT path, 0: tf32 hi/lo, 1: bf16) + the bias stack."""
-        mode = {-1: 0, 0: 1, 1: 2}[kind]
+        mode = {-1: 0, 0: 0 if self.tc_raw else 1, 1: 2}[kind]
         if kind == -1:
             W = (self.buf(f"Wst_{r}", 8 * H, I), None)
         else:
@@ -803,7 +816,10 @@ class MisaEngine:
                 # cancellation, where bf16 operands cost several percent (measured 4-13 %); bf16
                 # mode covers the forward input projection only (BASELINE configs[2]).
                 dGp = self._prep(f"tcdG_{r}", Gt, kind=0)
-                if self.tc_kind == 0:      # operand splits written by the forward
+                if self.tc_kind == 0 and self.tc_raw:
+                    Xp = self._prep(f"tcX_{r}", Xin, kind=0)          # the fp32 tensor itself
+                    Wst = self._prep_buf(f"tcW_{r}", 8 * H, I, 0)     # packed by the forward
+                elif self.tc_kind == 0:    # operand splits written by the forward
                     Xp = self._prep_buf(f"tcX_{r}", N, I, 0)
                     Wst = self._prep_buf(f"tcW_{r}", 8 * H, I, 0)
                 else:

@@ -439,6 +439,13 @@ def test_gemm_tc_tf32x3_and_bf16(dev):
                 # the library's own callers use the auto split-K for such shapes (checked below)
                 C.add(f"tf32x3 {M}x{N}x{K} a_mn={a_mn} b_mn={b_mn}", out, ref + bias.double(),
                       1e-5 if K <= 4096 else 3e-5)
+                # kind 2: the same contraction from the plain fp32 operands (hi/lo split inside
+                # the kernel's shared-memory pipeline) must give the same bits
+                out2 = torch.full((M, N), 5.0, device=dev)
+                k._c("mmda_gemm_tc", 2, a_mn, b_mn, M, N, K, _ptr(A), None, A.stride(0), _ptr(B),
+                     None, B.stride(0), 1.0, _ptr(out2), N, _ptr(bias), None, 0, 1, 0)
+                C.flag(f"tf32x3 raw == pre-split {M}x{N}x{K} a_mn={a_mn} b_mn={b_mn}",
+                       torch.equal(out, out2))
                 if K >= 1000:
                     acc = torch.randn(M, N, generator=g).to(dev)
                     ref2 = acc.double() + 0.5 * ref
