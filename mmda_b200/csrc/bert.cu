@@ -156,16 +156,20 @@ bert_attn_fwd_kernel(const float* __restrict__ qkv, const long long* __restrict_
   float* Sc = Vs + S4 * BHD;       // [S4][S4] scores -> probabilities
   float* Pt = Sc + S4 * S4;        // [S4][S4] dropped probabilities, transposed: Pt[j][i]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
-  for (int idx = tid; idx < S4 * BHD; idx += blockDim.x) {
-    const int s = idx / BHD, c = idx % BHD;
-    float q = 0.f, k = 0.f, v = 0.f;
+  // 16-byte global loads, several in flight per thread (the kernel is short: load latency matters)
+#pragma unroll 4
+  for (int idx = tid; idx < S4 * (BHD / 4); idx += blockDim.x) {
+    const int s = idx / (BHD / 4), c = (idx % (BHD / 4)) * 4;
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f), k = q, v = q;
     if (s < S) {
       const float* r = qkv + (size_t)(b * S + s) * ld + h * BHD + c;
-      q = r[0]; k = r[Hd]; v = r[2 * Hd];
+      q = *reinterpret_cast<const float4*>(r);
+      k = *reinterpret_cast<const float4*>(r + Hd);
+      v = *reinterpret_cast<const float4*>(r + 2 * Hd);
     }
-    Qt[c * S4 + s] = q;
-    Kt[c * S4 + s] = k;
-    Vs[s * BHD + c] = v;
+    Qt[(c + 0) * S4 + s] = q.x; Qt[(c + 1) * S4 + s] = q.y; Qt[(c + 2) * S4 + s] = q.z; Qt[(c + 3) * S4 + s] = q.w;
+    Kt[(c + 0) * S4 + s] = k.x; Kt[(c + 1) * S4 + s] = k.y; Kt[(c + 2) * S4 + s] = k.z; Kt[(c + 3) * S4 + s] = k.w;
+    *reinterpret_cast<float4*>(Vs + s * BHD + c) = v;
   }
   for (int idx = tid; idx < S4 * S4; idx += blockDim.x) Pt[idx] = 0.f;
   __syncthreads();
@@ -237,20 +241,24 @@ bert_attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ pr
   float* Dt = Ds + S4 * S4;        // d(scores) transposed
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
   const unsigned base0 = (unsigned)((b * nhead + h) * S * S);
-  for (int idx = tid; idx < S4 * BHD; idx += blockDim.x) {
-    const int s = idx / BHD, c = idx % BHD;
-    float q = 0.f, k = 0.f, v = 0.f, dc = 0.f;
+#pragma unroll 2
+  for (int idx = tid; idx < S4 * (BHD / 4); idx += blockDim.x) {
+    const int s = idx / (BHD / 4), c = (idx % (BHD / 4)) * 4;
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f), k = q, v = q, dc = q;
     if (s < S) {
       const float* r = qkv + (size_t)(b * S + s) * ld + h * BHD + c;
-      q = r[0]; k = r[Hd]; v = r[2 * Hd];
-      dc = dctx[(size_t)(b * S + s) * Hd + h * BHD + c];
+      q = *reinterpret_cast<const float4*>(r);
+      k = *reinterpret_cast<const float4*>(r + Hd);
+      v = *reinterpret_cast<const float4*>(r + 2 * Hd);
+      dc = *reinterpret_cast<const float4*>(dctx + (size_t)(b * S + s) * Hd + h * BHD + c);
     }
-    Qs[s * BHD + c] = q;
-    Ks[s * BHD + c] = k;
-    Vt[c * S4 + s] = v;
-    Cs[s * BHD + c] = dc;
-    Ct[c * S4 + s] = dc;
+    *reinterpret_cast<float4*>(Qs + s * BHD + c) = q;
+    *reinterpret_cast<float4*>(Ks + s * BHD + c) = k;
+    *reinterpret_cast<float4*>(Cs + s * BHD + c) = dc;
+    Vt[(c + 0) * S4 + s] = v.x; Vt[(c + 1) * S4 + s] = v.y; Vt[(c + 2) * S4 + s] = v.z; Vt[(c + 3) * S4 + s] = v.w;
+    Ct[(c + 0) * S4 + s] = dc.x; Ct[(c + 1) * S4 + s] = dc.y; Ct[(c + 2) * S4 + s] = dc.z; Ct[(c + 3) * S4 + s] = dc.w;
   }
+#pragma unroll 4
   for (int idx = tid; idx < S4 * S4; idx += blockDim.x) {
     const int i = idx / S4, j = idx % S4;
     Ps[idx] = (i < S && j < S) ? probs[(size_t)base0 + i * S + j] : 0.f;
