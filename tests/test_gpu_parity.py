@@ -531,14 +531,15 @@ def test_c3_bf16_mode_within_2e2(dev):
     C.finish()
 
 
-def test_cuda_graph_replay_equals_eager(dev):
+@pytest.mark.parametrize("rnncell", ["lstm", "gru"])
+def test_cuda_graph_replay_equals_eager(dev, rnncell):
     """The captured CUDA graph of the fused step (multi-stream forks, device-resident step state)
     must produce the same training trajectory as eager launches, including train-mode dropout
     (same device seed counter) and varying inputs."""
     from mmda_b200 import MISA, mosei_config
     from mmda_b200.synthetic import batch_for
     from mmda_b200.trainer import FusedTrainer
-    cfg = mosei_config(vocab_size=300, batch_size=48, use_confidNet=True)
+    cfg = mosei_config(vocab_size=300, batch_size=48, use_confidNet=True, rnncell=rnncell)
     batches = [batch_for(cfg, seed=40 + i, lengths="full", seq_len=12) for i in range(3)]
     res = {}
     for mode in (False, True):
@@ -553,7 +554,7 @@ def test_cuda_graph_replay_equals_eager(dev):
         assert (tr._graph is not None) == mode
         res[mode] = (torch.stack(Ls).cpu(), tr.p_arena[:tr.n_active].clone().cpu(), tr.step_count)
     assert res[True][2] == res[False][2] == 7
-    C = Checks("graph")
+    C = Checks("graph_" + rnncell)
     C.add("losses over 7 steps", res[True][0], res[False][0], 1e-5)
     C.add("parameters after 7 steps", res[True][1], res[False][1], 1e-5)
     C.finish()
