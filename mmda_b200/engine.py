@@ -30,6 +30,7 @@ ATT_P = 0.1            # nn.TransformerEncoderLayer default dropout (reference s
 NHEAD = 2
 TL = "transformer_encoder.layers.0."
 _DRYRUN = False       # tests only: exercise the host orchestration on CPU with a stubbed library
+_DRYRUN_SIMT_ONLY = False
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -358,6 +359,26 @@ class MisaEngine:
                     out[f"{r}.{kk}{suf}"] = x
         return out
 
+    # ---- dense layers big enough for the tensor-core path (the fusion layer's FFN) ----
+    def _tc_lin_ok(self, M, N, K):
+        return self.use_tc and not _DRYRUN_SIMT_ONLY and M >= 512 and N % 4 == 0 and K % 4 == 0
+
+    def tc_linear(self, tag, x, w, b, out):
+        """out = x w^T + b on tcgen05 (3xTF32: fp32-accurate in either precision mode)."""
+        M, K = x.shape
+        self.k.gemm_tc(0, 0, 0, M, w.shape[0], K, self._prep(tag + "_x", x, kind=0),
+                       self._prep(tag + "_w", w, kind=0), out, bias=b)
+
+    def tc_linear_bwd(self, tag, dy, x, w, dw, db, dx, dx_acc):
+        """dw += dy^T x, db += colsum(dy), dx (+)= dy w   (dy: [M][N], x: [M][K], w: [N][K])"""
+        M, N = dy.shape
+        K = x.shape[1]
+        dyo = self._prep(tag + "_dy", dy, kind=0)
+        self.k.gemm_tc(0, 1, 1, N, K, M, dyo, self._prep(tag + "_x", x, kind=0), dw, mode=1, split_k=0)
+        self.k.colsum(dy, db)
+        self.k.gemm_tc(0, 0, 1, M, K, N, dyo, self._prep(tag + "_w", w, kind=0), dx,
+                       mode=1 if dx_acc else 0, split_k=0 if dx_acc else 1)
+
     @staticmethod
     def _cols(op, lo, hi):
         return (op[0][:, lo:hi], None if op[1] is None else op[1][:, lo:hi])
@@ -549,10 +570,19 @@ class MisaEngine:
         if p_att > 0:
             k.dropout(AO, AO, p_att, seed, 2, seed_dev)
         k.layernorm(Xr, AO, P[TL + "norm1.weight"], P[TL + "norm1.bias"], X1, lnm[0], lnr[0])
-        k.linear(X1, P[TL + "linear1.weight"], P[TL + "linear1.bias"], F1, act=ACT_RELU)
+        FF = F1.shape[1]
+        ffn_tc = self._tc_lin_ok(rows, FF, d)
+        if ffn_tc:
+            self.tc_linear("ffn1", X1, P[TL + "linear1.weight"], P[TL + "linear1.bias"], F1)
+            k.act(F1, ACT_RELU)
+        else:
+            k.linear(X1, P[TL + "linear1.weight"], P[TL + "linear1.bias"], F1, act=ACT_RELU)
         if p_att > 0:
             k.dropout(F1, F1, p_att, seed, 3, seed_dev)
-        k.linear(F1, P[TL + "linear2.weight"], P[TL + "linear2.bias"], F2)
+        if ffn_tc:
+            self.tc_linear("ffn2", F1, P[TL + "linear2.weight"], P[TL + "linear2.bias"], F2)
+        else:
+            k.linear(F1, P[TL + "linear2.weight"], P[TL + "linear2.bias"], F2)
         if p_att > 0:
             k.dropout(F2, F2, p_att, seed, 4, seed_dev)
         k.layernorm(X1, F2, P[TL + "norm2.weight"], P[TL + "norm2.bias"], X2, lnm[1], lnr[1])
@@ -649,14 +679,23 @@ class MisaEngine:
                 dF2 = self.buf("dF2", rows, d)
                 k.dropout(dS2, dF2, p_att, seed, 4, seed_dev)
             dF1 = self.buf("dF1", rows, FF)
-            k.linear_bwd(dF2, F1, P[TL + "linear2.weight"], G[TL + "linear2.weight"],
-                         G[TL + "linear2.bias"], dF1, 0.0)
+            ffn_tc = self._tc_lin_ok(rows, FF, d)
+            if ffn_tc:
+                self.tc_linear_bwd("ffn2", dF2, F1, P[TL + "linear2.weight"], G[TL + "linear2.weight"],
+                                   G[TL + "linear2.bias"], dF1, False)
+            else:
+                k.linear_bwd(dF2, F1, P[TL + "linear2.weight"], G[TL + "linear2.weight"],
+                             G[TL + "linear2.bias"], dF1, 0.0)
             if p_att > 0:
                 k.dropout(dF1, dF1, p_att, seed, 3, seed_dev)
             k.act_bwd(dF1, F1, ACT_RELU)
             # dX1 = dS2 + dF1 W1   (accumulate in place into dS2)
-            k.linear_bwd(dF1, X1, P[TL + "linear1.weight"], G[TL + "linear1.weight"],
-                         G[TL + "linear1.bias"], dS2, 1.0)
+            if ffn_tc:
+                self.tc_linear_bwd("ffn1", dF1, X1, P[TL + "linear1.weight"], G[TL + "linear1.weight"],
+                                   G[TL + "linear1.bias"], dS2, True)
+            else:
+                k.linear_bwd(dF1, X1, P[TL + "linear1.weight"], G[TL + "linear1.weight"],
+                             G[TL + "linear1.bias"], dS2, 1.0)
             dS1 = self.buf("dS1", rows, d)
             k.layernorm_bwd(dS2, Xr, AO, P[TL + "norm1.weight"], lnm[0], lnr[0], dS1,
                             G[TL + "norm1.weight"], G[TL + "norm1.bias"])
