@@ -152,6 +152,8 @@ class MisaEngine:
         # cluster kernel occupies 112 of the 148 SMs)
         self.multi_stream = os.environ.get("MMDA_STREAMS", "1") != "0"
         self._side = None
+        self._text_stream = None
+        self.text_priority = os.environ.get("MMDA_TEXT_PRIORITY", "1") != "0"
         # use_bert=True: the BERT encoder runs on the hand-written kernels too
         # (mmda_b200/bert.py); its masked-mean output enters here as `utt_text` and backward()
         # returns the gradient wrt it.
@@ -279,8 +281,23 @@ class MisaEngine:
                 ev = torch.cuda.Event()
                 ev.record(st)
                 done.append(ev)
-        self.k.bind_stream()
-        fns["t"]()
+        # the text encoder is the critical path: it runs on a high-priority stream so its cluster
+        # kernels are placed ahead of the visual / acoustic CTAs competing for SMs
+        if self.text_priority:
+            if self._text_stream is None:
+                self._text_stream = torch.cuda.Stream(device=self._dev, priority=-1)
+            ts = self._text_stream
+            ts.wait_event(start)
+            with torch.cuda.stream(ts):
+                self.k.bind_stream()
+                fns["t"]()
+                ev = torch.cuda.Event()
+                ev.record(ts)
+                done.append(ev)
+            self.k.bind_stream()
+        else:
+            self.k.bind_stream()
+            fns["t"]()
         for ev in done:
             main.wait_event(ev)
 
