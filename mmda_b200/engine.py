@@ -153,6 +153,7 @@ class MisaEngine:
         self.multi_stream = os.environ.get("MMDA_STREAMS", "1") != "0"
         self._side = None
         self._text_stream = None
+        self.fork_log = None
         self.text_priority = os.environ.get("MMDA_TEXT_PRIORITY", "1") != "0"
         # use_bert=True: the BERT encoder runs on the hand-written kernels too
         # (mmda_b200/bert.py); its masked-mean output enters here as `utt_text` and backward()
@@ -270,17 +271,22 @@ class MisaEngine:
                 fns[m]()
             return
         main = torch.cuda.current_stream()
-        start = torch.cuda.Event()
+        timing = self.fork_log is not None      # profiling aid (tools/fork_timing.py)
+        start = torch.cuda.Event(enable_timing=timing)
         start.record(main)
         done = []
+        if timing:
+            self.fork_log.append(("start", start))
         for m, st in self._side_streams().items():
             st.wait_event(start)
             with torch.cuda.stream(st):
                 self.k.bind_stream()
                 fns[m]()
-                ev = torch.cuda.Event()
+                ev = torch.cuda.Event(enable_timing=timing)
                 ev.record(st)
                 done.append(ev)
+                if timing:
+                    self.fork_log.append((m, ev))
         # the text encoder is the critical path: it runs on a high-priority stream so its cluster
         # kernels are placed ahead of the visual / acoustic CTAs competing for SMs
         if self.text_priority:
@@ -291,9 +297,11 @@ class MisaEngine:
             with torch.cuda.stream(ts):
                 self.k.bind_stream()
                 fns["t"]()
-                ev = torch.cuda.Event()
+                ev = torch.cuda.Event(enable_timing=timing)
                 ev.record(ts)
                 done.append(ev)
+                if timing:
+                    self.fork_log.append(("t", ev))
             self.k.bind_stream()
         else:
             self.k.bind_stream()

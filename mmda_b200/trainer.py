@@ -329,14 +329,34 @@ class FusedTrainer:
         self.step_count += 1
         return losses
 
-    def step_batch(self, batch, device=None):
+    def step_batch(self, batch, device=None, prefetch=None):
         """Public end-to-end call: a host ``Batch`` (pinned or pageable) -> one optimisation step.
-        Returns the loss tensor on the device; ``.tolist()`` it to read the values."""
+        Returns the loss tensor on the device; ``.tolist()`` it to read the values.
+
+        ``prefetch``: the host ``Batch`` of the NEXT call.  Its host->device copies are issued on
+        a copy stream right after this step has been enqueued, so they overlap the step's
+        kernels; the next ``step_batch(prefetch_batch)`` picks the staged tensors up."""
         dev = device or self.p_arena.device
-        to = lambda t: t.to(dev, non_blocking=True)
-        if self.use_bert:
-            return self.step(to(batch.sentences), to(batch.visual), to(batch.acoustic),
-                             batch.lengths, to(batch.labels), to(batch.bert_sent),
-                             to(batch.bert_sent_type), to(batch.bert_sent_mask))
-        return self.step(to(batch.sentences), to(batch.visual), to(batch.acoustic), batch.lengths,
-                         to(batch.labels))
+        fields = ("sentences", "visual", "acoustic", "labels") + \
+            (("bert_sent", "bert_sent_type", "bert_sent_mask") if self.use_bert else ())
+        main = torch.cuda.current_stream()
+        staged = getattr(self, "_staged", None)
+        if staged is not None and staged[0] is batch:
+            main.wait_event(staged[2])
+            t = staged[1]
+        else:
+            t = {f: getattr(batch, f).to(dev, non_blocking=True) for f in fields}
+        self._staged = None
+        extra = [t[f] for f in fields[4:]]
+        out = self.step(t["sentences"], t["visual"], t["acoustic"], batch.lengths, t["labels"], *extra)
+        if prefetch is not None:
+            if not hasattr(self, "_copy_stream"):
+                self._copy_stream = torch.cuda.Stream(device=dev)
+            with torch.cuda.stream(self._copy_stream):
+                nt = {f: getattr(prefetch, f).to(dev, non_blocking=True) for f in fields}
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+            for v in nt.values():
+                v.record_stream(main)
+            self._staged = (prefetch, nt, ev)
+        return out
