@@ -258,6 +258,8 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e = world * args.batch * args.steps / (float(t) * 1e-3)
 
+    # captured CUDA graphs hold references to the NCCL communicator: drop them before teardown
+    tr.close()
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()

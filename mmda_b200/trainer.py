@@ -106,7 +106,8 @@ class FusedTrainer:
         # CUDA-graph replay of the whole step (single GPU, repeated sequence-length pattern)
         import os
         self.use_graph = (use_graph if use_graph is not None else
-                          os.environ.get("MMDA_GRAPH", "1") != "0") and self.world == 1
+                          os.environ.get("MMDA_GRAPH", "1") != "0") and \
+            (self.world == 1 or os.environ.get("MMDA_GRAPH_DP", "1") == "1")
         self._graph = None
         self._graph_seen = {}
         self.launches_per_step = None
@@ -328,6 +329,17 @@ class FusedTrainer:
         graph.replay()
         self.step_count += 1
         return losses
+
+    def close(self):
+        """Drop the captured CUDA graph.  Under data parallelism the graph references the NCCL
+        communicator: call this before ``dist.destroy_process_group()`` (which otherwise waits
+        for the graph's resources and hangs)."""
+        self._graph = None
+        self._graph_seen = {}
+        import gc
+        gc.collect()
+        if not _engine._DRYRUN:
+            torch.cuda.synchronize()
 
     def step_batch(self, batch, device=None, prefetch=None):
         """Public end-to-end call: a host ``Batch`` (pinned or pageable) -> one optimisation step.

@@ -59,7 +59,25 @@ def _worker(rank, world, port, q):
     lerr = float(((L_dp - L_1).abs() / L_1.abs().clamp_min(1e-6)).max())
     tr_dp.optimizer_step(); tr_1.optimizer_step()
     torch.cuda.synchronize()
-    q.put((rank, lerr, gerr))
+    # CUDA-graph replay of the whole step including the NCCL all-reduces == eager launches
+    shard = full.slice(rank * per, (rank + 1) * per)
+    args = (shard.sentences.to(dev), shard.visual.to(dev), shard.acoustic.to(dev), shard.lengths,
+            shard.labels.to(dev))
+    finals, traj = [], []
+    for mode in (True, False):
+        torch.manual_seed(3)
+        tr = FusedTrainer(make(), process_group=dist.group.WORLD, use_graph=mode)
+        traj.append(torch.stack([tr.step(*args)[:6].clone() for _ in range(6)]))
+        assert (tr._graph is not None) == mode
+        finals.append(tr.p_arena[:tr.n_active].clone())
+        tr.close()
+    # losses over the trajectory must agree tightly; parameters only up to Adam's noise floor
+    # (gradient elements at rounding level get +-lr updates whose sign is noise: <= 2*lr*steps)
+    perr = float(((traj[0] - traj[1]).abs() / traj[1].abs().clamp_min(1e-6)).max())
+    pabs = float((finals[0] - finals[1]).abs().max())
+    assert pabs <= 2 * 1e-4 * 6 + 1e-6, pabs
+    torch.cuda.synchronize()
+    q.put((rank, lerr, gerr, perr))
     dist.destroy_process_group()
 
 
@@ -74,6 +92,7 @@ def test_two_rank_shards_equal_single_gpu_full_batch():
     [p.start() for p in procs]
     res = sorted(q.get(timeout=300) for _ in range(2))
     [p.join(60) for p in procs]
-    for rank, lerr, gerr in res:
+    for rank, lerr, gerr, perr in res:
         assert lerr < 1e-5, (rank, lerr)
         assert gerr < 2e-5, (rank, gerr)
+        assert perr < 2e-5, (rank, perr)     # graph replay (incl. NCCL) == eager: 6-step loss trajectory
