@@ -263,6 +263,13 @@ class MisaEngine:
             self._wg[m] = torch.cuda.Stream(device=self._dev)
         return self._wg[m]
 
+    def _mark(self, tag):
+        """profiling aid: timestamp on the current stream (tools/fork_timing.py)"""
+        if self.fork_log is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(torch.cuda.current_stream())
+            self.fork_log.append((tag, ev))
+
     def _fork(self, fns):
         """Run fns[m]() for m in v, a on side streams (after everything enqueued so far on the
         current stream) and fns['t']() on the current stream; join before returning."""
@@ -441,6 +448,8 @@ class MisaEngine:
                 self.big_gemm(Xin, Wst[0], G, tb=True, bias=bst)
             Y, C = (Y1, C1) if r == r1 else (Y2, C2)
             o_f, o_r = (0, 2 * H) if r == r1 else (H, 3 * H)
+            if m == "t":
+                self._mark(f"  t.{r} in-proj GEMM enqueued-done")
             if self.gru:
                 k._c("mmda_gru_forward", _ptr(G), _ptr(P[f"{r}.weight_hh_l0"]),
                      _ptr(P[f"{r}.weight_hh_l0_reverse"]), _ptr(Y), _ptr(pk["lens"]),
@@ -451,6 +460,8 @@ class MisaEngine:
                  _ptr(P[f"{r}.weight_hh_l0_reverse"]), _ptr(Y), _ptr(C), _ptr(pk["lens"]),
                  _ptr(pk["sidx"]), _ptr(pk["off"]), _ptr(utt), 4 * H, o_f, o_r, B, H, Tmax,
                  int(train))
+            if m == "t":
+                self._mark(f"  t.{r} recurrence done")
         return utt
 
     def forward(self, sentences, visual, acoustic, lengths, train: bool, want_sp: bool = True,
@@ -873,6 +884,8 @@ class MisaEngine:
                  _ptr(Y if self.gru else C), _ptr(dy), _ptr(dutt), 4 * H, o_f,
                  o_r, _ptr(pk["lens"]), _ptr(pk["sidx"]), _ptr(pk["off"]), _ptr(scratch), B, H,
                  Tmax)
+            if m == "t":
+                self._mark(f"  t.{r} BPTT done")
             I = Xin.shape[1]
             tc = self._tc_ok(H, I)
             if tc:
@@ -928,6 +941,8 @@ class MisaEngine:
                 with torch.cuda.stream(side):
                     k.bind_stream()
                     wgrad()
+                    if m == "t":
+                        self._mark(f"  t.{r} wgrad (side stream) done")
                 k.bind_stream()
             else:
                 wgrad()
@@ -937,6 +952,8 @@ class MisaEngine:
                     k.gemm_tc(0, 0, 1, N, I, 8 * H, dGp, Wst, dX)
                 else:
                     self.big_gemm(Gt, Wst[0], dX)
+                if m == "t":
+                    self._mark(f"  t.{r} dX GEMM done")
                 if r == r1:
                     V = P["embed.weight"].shape[0]
                     k._c("mmda_embedding_backward", _ptr(G["embed.weight"]),

@@ -39,6 +39,8 @@ def main():
             region += 1
             start = ev
             print(f"{names[region % 4]}: fork at {t0.elapsed_time(ev):.3f} ms")
+        elif tag.startswith("  "):
+            print(f"      {tag.strip()}: +{start.elapsed_time(ev):.3f} ms")
         else:
             print(f"    {tag}: done +{start.elapsed_time(ev):.3f} ms")
 
