@@ -113,6 +113,8 @@ int mmda_lstm_pack_weights(const float* w_ih_f, const float* w_ih_r, const float
                            mmda_stream_t stream);
 /* tuning knob for A/B measurements: hidden units per thread (1 or 2) in the forward mat-vec */
 int mmda_lstm_set_units_per_thread(int tu);
+/* A/B knob: batch tile of the small-hidden-size plan (8 = many small CTAs, 32 = few large ones) */
+int mmda_lstm_set_small_tile(int bt);
 /* diagnostic: per-step phase timestamps of CTA 0 of subsequent forward launches (NULL = off) */
 int mmda_lstm_set_debug_buffer(long long* dev_buf);
 /* diagnostic: co-resident clusters of the recurrent kernel for cluster sizes {1,2,4,8,16} */

@@ -776,6 +776,8 @@ struct LstmPlan {
 };
 
 static int g_max_smem = 0;
+static int g_small_bt = 32; // batch tile of the small-H plan for B >= 64: few large CTAs leave the SMs next to the
+                            // text recurrence to the weight-gradient GEMMs (7.65 -> 7.59 ms); 8 = many small CTAs
 static int g_lstm_tu = 1;   // units per thread in the forward mat-vec of the big-H plan (2 measured 6 % slower)
 static int g_max_clusters8 = 0;   // co-resident 8-CTA clusters of the big-H kernel (B200: 15)
 
@@ -812,7 +814,7 @@ static int lstm_make_plan(int B, int H, int Tmax, LstmPlan* pl) {
     const int KS = (H > 128) ? 16 : 4;
     const int RS = 32 / KS, R = (4 * Hs + RS - 1) / RS * RS;
     const int cand[3] = {40, 32, 8};
-    for (int ci = (H > 128 ? 0 : 2); ci < 3; ++ci) {
+    for (int ci = (H > 128 ? 0 : (g_small_bt == 32 && B >= 64 ? 1 : 2)); ci < 3; ++ci) {
       const int BT = cand[ci];
       if (H > 128 && BT == 8) break;
       const int BTP = BT + (BT % 32 == 0 ? 4 : 0);
@@ -875,6 +877,13 @@ static int launch_cluster(K kern, const LstmArgs& a, const LstmPlan& pl, int thr
 static long long* g_lstm_dbg = nullptr;
 
 extern "C" {
+
+// tuning knob (A/B measurements): batch tile of the small-H plan (8 or 32)
+int mmda_lstm_set_small_tile(int bt) {
+  MMDA_REQUIRE(bt == 8 || bt == 32, "lstm: small-H batch tile must be 8 or 32");
+  g_small_bt = bt;
+  return MMDA_OK;
+}
 
 // tuning knob (A/B measurements): units per thread of the big-H forward mat-vec (1 or 2)
 int mmda_lstm_set_units_per_thread(int tu) {
@@ -989,12 +998,16 @@ static int rnn_backward(int cell, float* gates, const float* whh_f, const float*
       return launch_cluster(lstm_bwd_kernel<40, 16, 1>, a, pl, pl.threads_bwd, pl.smem_bwd, stream);
     if (pl.BT == 32 && pl.KS == 16)
       return launch_cluster(lstm_bwd_kernel<32, 16, 1>, a, pl, pl.threads_bwd, pl.smem_bwd, stream);
+    if (pl.BT == 32)
+      return launch_cluster(lstm_bwd_kernel<32, 4, 1>, a, pl, pl.threads_bwd, pl.smem_bwd, stream);
     return launch_cluster(lstm_bwd_kernel<8, 4, 1>, a, pl, pl.threads_bwd, pl.smem_bwd, stream);
   }
   if (pl.BT == 40 && pl.KS == 16)
     return launch_cluster(lstm_bwd_kernel<40, 16, 0>, a, pl, pl.threads_bwd, pl.smem_bwd, stream);
   if (pl.BT == 32 && pl.KS == 16)
     return launch_cluster(lstm_bwd_kernel<32, 16, 0>, a, pl, pl.threads_bwd, pl.smem_bwd, stream);
+  if (pl.BT == 32)
+    return launch_cluster(lstm_bwd_kernel<32, 4, 0>, a, pl, pl.threads_bwd, pl.smem_bwd, stream);
   return launch_cluster(lstm_bwd_kernel<8, 4, 0>, a, pl, pl.threads_bwd, pl.smem_bwd, stream);
 }
 

@@ -154,6 +154,8 @@ class MisaEngine:
         self._side = None
         self._text_stream = None
         self.fork_log = None
+        if "MMDA_LSTM_SMALL_TILE" in os.environ and not _DRYRUN:      # A/B knob
+            LIB.call("mmda_lstm_set_small_tile", int(os.environ["MMDA_LSTM_SMALL_TILE"]))
         self.text_priority = os.environ.get("MMDA_TEXT_PRIORITY", "1") != "0"
         # use_bert=True: the BERT encoder runs on the hand-written kernels too
         # (mmda_b200/bert.py); its masked-mean output enters here as `utt_text` and backward()
