@@ -77,7 +77,34 @@ def _worker(rank, world, port, q):
     pabs = float((finals[0] - finals[1]).abs().max())
     assert pabs <= 2 * 1e-4 * 6 + 1e-6, pabs
     torch.cuda.synchronize()
-    q.put((rank, lerr, gerr, perr))
+    # BERT text branch + frozen layers 0-8 under data parallelism (text bucket reduced after the
+    # BERT backward; frozen tensors sit outside the reduced range)
+    from transformers import BertConfig
+    bcfg = mosei_config(vocab_size=100, batch_size=8, use_bert=True)
+    bfull = batch_for(bcfg, seed=11, lengths="shuffled", seq_len=9)
+
+    def make_bert():
+        torch.manual_seed(4)
+        m = MISA(bcfg)
+        for n, p in m.named_parameters():
+            if "bertmodel.encoder.layer" in n and int(n.split("encoder.layer.")[-1].split(".")[0]) <= 8:
+                p.requires_grad = False
+        return m.to(dev).eval()
+
+    def run_bert(tr, b):
+        tr.forward_backward(b.sentences.to(dev), b.visual.to(dev), b.acoustic.to(dev), b.lengths,
+                            b.labels.to(dev), (b.bert_sent.to(dev), b.bert_sent_type.to(dev),
+                                               b.bert_sent_mask.to(dev)))
+
+    bper = 8 // world
+    tb_dp = FusedTrainer(make_bert(), process_group=dist.group.WORLD)
+    run_bert(tb_dp, bfull.slice(rank * bper, (rank + 1) * bper))
+    tb_1 = FusedTrainer(make_bert())
+    run_bert(tb_1, bfull)
+    nb = tb_1.n_active
+    berr = float((tb_dp.g_arena[:nb] - tb_1.g_arena[:nb]).abs().max() / tb_1.g_arena[:nb].abs().max())
+    torch.cuda.synchronize()
+    q.put((rank, lerr, gerr, perr, berr))
     dist.destroy_process_group()
 
 
@@ -92,7 +119,8 @@ def test_two_rank_shards_equal_single_gpu_full_batch():
     [p.start() for p in procs]
     res = sorted(q.get(timeout=300) for _ in range(2))
     [p.join(60) for p in procs]
-    for rank, lerr, gerr, perr in res:
+    for rank, lerr, gerr, perr, berr in res:
+        assert berr < 5e-5, (rank, berr)     # BERT branch: 2 x half batch == full batch gradients
         assert lerr < 1e-5, (rank, lerr)
         assert gerr < 2e-5, (rank, gerr)
         assert perr < 2e-5, (rank, perr)     # graph replay (incl. NCCL) == eager: 6-step loss trajectory
