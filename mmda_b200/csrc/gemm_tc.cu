@@ -603,35 +603,58 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(buf));     // 4 epilogue warps -> buffer free
-      // ---- phase 2: transpose through shared memory, coalesced stores (overlaps the next tile) ----
+      // ---- phase 2: stores (overlap the next tile's MMAs).  Each lane owns one output row and
+      // 32 consecutive columns per chunk: eight 16-byte stores (or vector REDs) per chunk, no
+      // shared-memory transpose.  Partial 32-byte sectors of neighbouring stores merge in L2. ----
+      {
+        const int grow = m0 + q * 32 + lane;
+        const bool row_ok = grow < p.M;
+        const int row_out = p.c_ilv ? (grow & 3) * p.c_ilv + (grow >> 2) : grow;
+        float* crow = p.C + (size_t)row_out * p.ldc;
+        const bool vec_ok = (p.ldc & 3) == 0 && ((uintptr_t)p.C & 15) == 0;
 #pragma unroll
-      for (int cc = 0; cc < BN / 32; ++cc) {
-        const int nb = n0 + cc * 32;
+        for (int cc = 0; cc < BN / 32; ++cc) {
+          const int nb = n0 + cc * 32;
+          if (!row_ok || nb >= p.N) continue;
+          if (vec_ok && nb + 32 <= p.N) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = acc[cc][j];
-        __syncwarp();
-        const int col = nb + lane;
-        if (col < p.N) {
-          float bsum = 0.f;
-          if (z == 0) {
-            if (p.bias) bsum += p.bias[col];
-            if (p.bias2) bsum += p.bias2[col];
-          }
-          const int row_base = m0 + q * 32;
-#pragma unroll 4
-          for (int rr = 0; rr < 32; ++rr) {
-            const int grow = row_base + rr;
-            if (grow >= p.M) break;
-            const int row_out = p.c_ilv ? (grow & 3) * p.c_ilv + (grow >> 2) : grow;
-            float* cp = p.C + (size_t)row_out * p.ldc + col;
-            const float v = p.alpha * stage[rr * 33 + lane] + bsum;
-            // accumulate with RED (fire-and-forget) even without split-K: a load-add-store
-            // per element serialises the warp on global-load latency (measured 8x slower)
-            if (p.mode != 0) atomicAdd(cp, v);
-            else *cp = v;
+            for (int j = 0; j < 32; j += 4) {
+              float4 v = make_float4(acc[cc][j], acc[cc][j + 1], acc[cc][j + 2], acc[cc][j + 3]);
+              v.x *= p.alpha; v.y *= p.alpha; v.z *= p.alpha; v.w *= p.alpha;
+              if (z == 0 && (p.bias || p.bias2)) {
+                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.bias) b4 = *reinterpret_cast<const float4*>(p.bias + nb + j);
+                if (p.bias2) {
+                  const float4 c4 = *reinterpret_cast<const float4*>(p.bias2 + nb + j);
+                  b4.x += c4.x; b4.y += c4.y; b4.z += c4.z; b4.w += c4.w;
+                }
+                v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+              }
+              float* cp = crow + nb + j;
+              if (p.mode != 0) {
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cp), "f"(v.x),
+                             "f"(v.y), "f"(v.z), "f"(v.w)
+                             : "memory");
+              } else {
+                *reinterpret_cast<float4*>(cp) = v;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {      // fully unrolled: acc stays in registers
+              const int col = nb + j;
+              if (col < p.N) {
+                float v = p.alpha * acc[cc][j];
+                if (z == 0) {
+                  if (p.bias) v += p.bias[col];
+                  if (p.bias2) v += p.bias2[col];
+                }
+                if (p.mode != 0) atomicAdd(crow + col, v);
+                else crow[col] = v;
+              }
+            }
           }
         }
-        __syncwarp();
       }
     }
   }
