@@ -245,8 +245,11 @@ int mmda_bert_embed_forward(const float* word, const float* pos, const float* ty
 int mmda_bert_embed_backward(const float* d, const long long* ids, const long long* types, int B,
                              int S, int H, int V, float* dword, float* dpos, float* dtyp,
                              mmda_stream_t stream);
-int mmda_gelu_forward(const float* x, float* y, long long n, mmda_stream_t stream);
-int mmda_gelu_backward(const float* dy, const float* x, float* dx, long long n, mmda_stream_t stream);
+/* y / dx (fp32) and y_bf16 / dx_bf16 (the tensor-core operand copy, contiguous like x) are each
+ * optional, at least one required: in bf16 mode the GELU output only feeds tcgen05 GEMMs. */
+int mmda_gelu_forward(const float* x, float* y, void* y_bf16, long long n, mmda_stream_t stream);
+int mmda_gelu_backward(const float* dy, const float* x, float* dx, void* dx_bf16, long long n,
+                       mmda_stream_t stream);
 int mmda_masked_mean_forward(const float* hid, const long long* mask, int B, int S, int H,
                              float* utt, mmda_stream_t stream);
 int mmda_masked_mean_backward(const float* dutt, const long long* mask, int B, int S, int H,

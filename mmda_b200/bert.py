@@ -76,6 +76,18 @@ class BertEngine:
         self.k.gemm_tc(self.eng.tc_kind, a_mn, b_mn, M, N, K, A, B, C, bias=bias,
                        mode=1 if acc else 0, split_k=0 if acc else 1)
 
+    def _gelu(self, l, pre, M):
+        """GELU of layer l's intermediate pre-activation -> tensor-core operand.  In bf16 mode the
+        activation only ever feeds tcgen05 GEMMs, so the kernel writes the bf16 copy directly."""
+        I = self.I
+        if self.eng.tc_kind == 1:
+            act_bf = self.eng.buf(f"bert_actbf_{l}", M, I, dtype=torch.bfloat16)
+            self.k._c("mmda_gelu_forward", _ptr(pre), None, _ptr(act_bf), M * I)
+            return act_bf, None
+        act = self.eng.buf(f"bert_act_{l}", M, I)
+        self.k._c("mmda_gelu_forward", _ptr(pre), _ptr(act), None, M * I)
+        return self._op("bert_opI", act)
+
     def _ln(self, x, res, g, b, y, mean, rstd):
         self.k._c("mmda_layernorm_forward", _ptr(x), x.stride(0), _ptr(res),
                   0 if res is None else res.stride(0), _ptr(g), _ptr(b), _ptr(y), y.stride(0),
@@ -137,10 +149,8 @@ class BertEngine:
             self._mm(0, 0, M, I, H, self._op("bert_opH", h1),
                      self._wop(P, Lp + "intermediate.dense.weight"), pre,
                      bias=P[Lp + "intermediate.dense.bias"])
-            act = buf(f"bert_act_{l}", M, I)
-            k._c("mmda_gelu_forward", _ptr(pre), _ptr(act), M * I)
             fo = buf(f"bert_fo_{l}", M, H)
-            self._mm(0, 0, M, H, I, self._op("bert_opI", act),
+            self._mm(0, 0, M, H, I, self._gelu(l, pre, M),
                      self._wop(P, Lp + "output.dense.weight"), fo, bias=P[Lp + "output.dense.bias"])
             if p_h > 0:
                 k.dropout(fo, fo, p_h, seed, 203 + 4 * l, seed_dev)
@@ -204,7 +214,8 @@ class BertEngine:
             QKV, ctx = buf(f"bert_qkv_{l}", M, 3 * H), buf(f"bert_ctx_{l}", M, H)
             probs = buf(f"bert_probs_{l}", B, nh, S, S)
             ao, h1 = buf(f"bert_ao_{l}", M, H), buf(f"bert_h1_{l}", M, H)
-            pre, act = buf(f"bert_pre_{l}", M, I), buf(f"bert_act_{l}", M, I)
+            pre = buf(f"bert_pre_{l}", M, I)
+            bf = eng.tc_kind == 1
             fo = buf(f"bert_fo_{l}", M, H)
             # ---- output LayerNorm(fo + h1) ----
             dsum = other
@@ -221,10 +232,18 @@ class BertEngine:
             dact = buf("bert_dI", M, I)
             self._mm(0, 1, M, I, H, dfo_op, self._wop(P, Lp + "output.dense.weight"), dact)
             if gw(Lp + "output.dense.weight") is not None:
-                wgrad(dfo_op, dfo, self._op("bert_opI", act), Lp + "output.dense.weight",
-                      Lp + "output.dense.bias", H, I)
-            k._c("mmda_gelu_backward", _ptr(dact), _ptr(pre), _ptr(dact), M * I)
-            dpre_op = self._op("bert_opI_d", dact)
+                act_op = (buf(f"bert_actbf_{l}", M, I, dtype=torch.bfloat16), None) if bf else \
+                    self._op("bert_opI", buf(f"bert_act_{l}", M, I))
+                wgrad(dfo_op, dfo, act_op, Lp + "output.dense.weight", Lp + "output.dense.bias", H, I)
+            if bf:     # d(pre) only feeds GEMMs (+ the bias column sum when that bias is trainable)
+                dpre_bf = buf("bert_dIbf", M, I, dtype=torch.bfloat16)
+                need32 = gw(Lp + "intermediate.dense.bias") is not None
+                k._c("mmda_gelu_backward", _ptr(dact), _ptr(pre), _ptr(dact) if need32 else None,
+                     _ptr(dpre_bf), M * I)
+                dpre_op = (dpre_bf, None)
+            else:
+                k._c("mmda_gelu_backward", _ptr(dact), _ptr(pre), _ptr(dact), None, M * I)
+                dpre_op = self._op("bert_opI_d", dact)
             # ---- intermediate.dense: h1 [M][H] -> pre [M][I]; dh1 = dsum + dpre W_i ----
             self._mm(0, 1, M, H, I, dpre_op, self._wop(P, Lp + "intermediate.dense.weight"), dsum,
                      acc=True)

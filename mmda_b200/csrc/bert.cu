@@ -8,6 +8,7 @@
 // Layout: tokens are batch-first, row m = b*S + s of [B*S][hidden]; QKV rows are
 // [q(hidden) | k(hidden) | v(hidden)]; probabilities [B][heads][S][S] (post-softmax, pre-dropout).
 #include "common.cuh"
+#include <cuda_bf16.h>
 
 // ---------------------------------------------------------------- embeddings ---------------
 // BertEmbeddings: word[ids] + position[s] + token_type[types]   (then LayerNorm + dropout)
@@ -57,26 +58,47 @@ __device__ __forceinline__ float gelu_grad_f(float v) {
   const float pdf = 0.39894228040143268f * expf(-0.5f * v * v);
   return cdf + v * pdf;
 }
-// n4 = n / 4 float4 groups (the host passes the scalar tail separately)
-__global__ void gelu_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, size_t n4,
+// n4 = n / 4 float4 groups.  y / dx may be NULL when only the bf16 operand copy (ybf / dxbf) is
+// wanted: in bf16 mode the GELU output and its gradient are consumed by tensor-core GEMMs only.
+__device__ __forceinline__ void st_bf16x4(__nv_bfloat16* p, float a, float b, float c, float d) {
+  const __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+  uint2 pk;
+  pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+  pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = pk;
+}
+__global__ void gelu_fwd_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                __nv_bfloat16* __restrict__ ybf, size_t n4, size_t n) {
+  const size_t t0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = t0; i < n4; i += stride) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    const float4 r = make_float4(gelu_f(v.x), gelu_f(v.y), gelu_f(v.z), gelu_f(v.w));
+    if (y) reinterpret_cast<float4*>(y)[i] = r;
+    if (ybf) st_bf16x4(ybf + i * 4, r.x, r.y, r.z, r.w);
+  }
+  for (size_t i = n4 * 4 + t0; i < n; i += stride) {
+    const float r = gelu_f(x[i]);
+    if (y) y[i] = r;
+    if (ybf) ybf[i] = __float2bfloat16(r);
+  }
+}
+__global__ void gelu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                float* __restrict__ dx, __nv_bfloat16* __restrict__ dxbf, size_t n4,
                                 size_t n) {
   const size_t t0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = t0; i < n4; i += stride) {
     const float4 v = reinterpret_cast<const float4*>(x)[i];
-    reinterpret_cast<float4*>(y)[i] = make_float4(gelu_f(v.x), gelu_f(v.y), gelu_f(v.z), gelu_f(v.w));
-  }
-  for (size_t i = n4 * 4 + t0; i < n; i += stride) y[i] = gelu_f(x[i]);
-}
-__global__ void gelu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
-                                float* __restrict__ dx, size_t n4, size_t n) {
-  const size_t t0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = t0; i < n4; i += stride) {
-    const float4 v = reinterpret_cast<const float4*>(x)[i];
     const float4 d = reinterpret_cast<const float4*>(dy)[i];
-    reinterpret_cast<float4*>(dx)[i] = make_float4(d.x * gelu_grad_f(v.x), d.y * gelu_grad_f(v.y),
-                                                   d.z * gelu_grad_f(v.z), d.w * gelu_grad_f(v.w));
+    const float4 r = make_float4(d.x * gelu_grad_f(v.x), d.y * gelu_grad_f(v.y),
+                                 d.z * gelu_grad_f(v.z), d.w * gelu_grad_f(v.w));
+    if (dx) reinterpret_cast<float4*>(dx)[i] = r;
+    if (dxbf) st_bf16x4(dxbf + i * 4, r.x, r.y, r.z, r.w);
   }
-  for (size_t i = n4 * 4 + t0; i < n; i += stride) dx[i] = dy[i] * gelu_grad_f(x[i]);
+  for (size_t i = n4 * 4 + t0; i < n; i += stride) {
+    const float r = dy[i] * gelu_grad_f(x[i]);
+    if (dx) dx[i] = r;
+    if (dxbf) dxbf[i] = __float2bfloat16(r);
+  }
 }
 
 // ---------------------------------------------------------------- masked mean --------------
@@ -336,20 +358,25 @@ int mmda_bert_embed_backward(const float* d, const long long* ids, const long lo
   return MMDA_OK;
 }
 
-int mmda_gelu_forward(const float* x, float* y, long long n, cudaStream_t stream) {
+int mmda_gelu_forward(const float* x, float* y, void* y_bf16, long long n, cudaStream_t stream) {
   if (n <= 0) return MMDA_OK;
-  const bool v4 = (((uintptr_t)x | (uintptr_t)y) & 15) == 0;
+  MMDA_REQUIRE(y != nullptr || y_bf16 != nullptr, "gelu_forward: no output");
+  const bool v4 = (((uintptr_t)x | (uintptr_t)y) & 15) == 0 && ((uintptr_t)y_bf16 & 7) == 0;
   const size_t n4 = v4 ? (size_t)n / 4 : 0;
-  gelu_fwd_kernel<<<ew_grid_b(v4 ? n4 + 1 : (size_t)n), 256, 0, stream>>>(x, y, n4, (size_t)n);
+  gelu_fwd_kernel<<<ew_grid_b(v4 ? n4 + 1 : (size_t)n), 256, 0, stream>>>(
+      x, y, reinterpret_cast<__nv_bfloat16*>(y_bf16), n4, (size_t)n);
   MMDA_CHECK_LAUNCH();
   return MMDA_OK;
 }
 
-int mmda_gelu_backward(const float* dy, const float* x, float* dx, long long n, cudaStream_t stream) {
+int mmda_gelu_backward(const float* dy, const float* x, float* dx, void* dx_bf16, long long n,
+                       cudaStream_t stream) {
   if (n <= 0) return MMDA_OK;
-  const bool v4 = (((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dx) & 15) == 0;
+  MMDA_REQUIRE(dx != nullptr || dx_bf16 != nullptr, "gelu_backward: no output");
+  const bool v4 = (((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dx) & 15) == 0 && ((uintptr_t)dx_bf16 & 7) == 0;
   const size_t n4 = v4 ? (size_t)n / 4 : 0;
-  gelu_bwd_kernel<<<ew_grid_b(v4 ? n4 + 1 : (size_t)n), 256, 0, stream>>>(dy, x, dx, n4, (size_t)n);
+  gelu_bwd_kernel<<<ew_grid_b(v4 ? n4 + 1 : (size_t)n), 256, 0, stream>>>(
+      dy, x, dx, reinterpret_cast<__nv_bfloat16*>(dx_bf16), n4, (size_t)n);
   MMDA_CHECK_LAUNCH();
   return MMDA_OK;
 }
