@@ -690,3 +690,39 @@ def test_gru_cells(dev, sizes, B, T):
     state = {k: v.clone() for k, v in oracle_build(cfg, 7).state_dict().items()}
     batch = batch_for(cfg, seed=8, lengths="shuffled", seq_len=T)
     _model_checks(f"gru_{sizes[0]}_{B}", cfg, state, batch, dev, None)
+
+
+def test_bert_bf16_mode_within_2e2(dev):
+    """precision='bf16' on the BERT branch (BASELINE configs[3]): every dense layer of the encoder
+    runs forward and backward with bf16 operands / fp32 accumulation.  Outputs and losses within
+    the 2e-2 bf16 bar of the fp32 oracle; gradients are checked for direction (cosine) because
+    bf16 operand rounding makes their element-wise error ill-conditioned (see the C3 test)."""
+    from mmda_b200 import MISA, FusedTrainer, mosei_config
+    from mmda_b200.synthetic import batch_for
+    from oracle.misa_oracle import oracle_build, oracle_step
+    cfg = mosei_config(vocab_size=100, batch_size=8, use_bert=True, precision="bf16")
+    ref = oracle_build(cfg, 51).eval()
+    state = {k: v.clone() for k, v in ref.state_dict().items()}
+    batch = batch_for(cfg, seed=52, lengths="shuffled", seq_len=11)
+    out_r, L_r, g_r = oracle_step(ref, batch, cfg, None)
+    model = MISA(cfg)
+    model.load_state_dict(state)
+    model = model.to(dev).eval()
+    tr = FusedTrainer(model)
+    L = tr.forward_backward(batch.sentences.to(dev), batch.visual.to(dev), batch.acoustic.to(dev),
+                            batch.lengths, batch.labels.to(dev),
+                            (batch.bert_sent.to(dev), batch.bert_sent_type.to(dev),
+                             batch.bert_sent_mask.to(dev))).cpu()
+    C = Checks("bert_bf16")
+    for i, kk in enumerate(("cls", "diff", "sim", "recon", "total")):
+        idx = {"cls": 0, "diff": 1, "sim": 2, "recon": 3, "total": 5}[kk]
+        C.add("loss " + kk, L[idx], L_r[kk].detach(), 2e-2)
+    C.add("utterance_text (BERT masked mean)", tr.eng.ws["bert_utt"][:8 * 768].view(8, 768),
+          out_r["utterance_t"].detach(), 2e-2)
+    for n in ("project_t.project_t.weight", "bertmodel.encoder.layer.11.output.dense.weight",
+              "bertmodel.encoder.layer.9.intermediate.dense.weight",
+              "bertmodel.embeddings.position_embeddings.weight"):
+        a, b = tr.G[n].detach().cpu().double().flatten(), g_r[n].double().flatten()
+        cos = float((a @ b) / (a.norm() * b.norm() + 1e-30))
+        C.flag(f"grad direction {n} cos={cos:.5f}", cos > 0.99)
+    C.finish()
