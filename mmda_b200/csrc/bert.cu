@@ -178,10 +178,12 @@ bert_attn_fwd_kernel(const float* __restrict__ qkv, const long long* __restrict_
   float* Sc = Vs + S4 * BHD;       // [S4][S4] scores -> probabilities
   float* Pt = Sc + S4 * S4;        // [S4][S4] dropped probabilities, transposed: Pt[j][i]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
-  // 16-byte global loads, several in flight per thread (the kernel is short: load latency matters)
+  // 16-byte global loads, several in flight per thread.  Lanes run over the token index so the
+  // transposed (k-major) stores are bank-conflict free; the 16-byte row segments each lane reads
+  // are served from L2.
 #pragma unroll 4
   for (int idx = tid; idx < S4 * (BHD / 4); idx += blockDim.x) {
-    const int s = idx / (BHD / 4), c = (idx % (BHD / 4)) * 4;
+    const int s = idx % S4, c = (idx / S4) * 4;
     float4 q = make_float4(0.f, 0.f, 0.f, 0.f), k = q, v = q;
     if (s < S) {
       const float* r = qkv + (size_t)(b * S + s) * ld + h * BHD + c;
@@ -200,14 +202,14 @@ bert_attn_fwd_kernel(const float* __restrict__ qkv, const long long* __restrict_
     const int i0 = (blk / nb) * 4, j0 = (blk % nb) * 4;
     float acc[4][4];
     mm_tile(Qt, S4, Kt, S4, BHD, i0, j0, acc);
+    bool keep[4];      // HF adds finfo.min to masked keys: the softmax weight is exactly 0
+#pragma unroll
+    for (int c = 0; c < 4; ++c) keep[c] = (j0 + c < S) && mask[(size_t)b * S + j0 + c] != 0;
 #pragma unroll
     for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int j = j0 + c;
-        // HF adds finfo.min to masked keys: the softmax weight is exactly 0
-        Sc[(i0 + a) * S4 + j] = (j < S && mask[(size_t)b * S + j] != 0) ? acc[a][c] * scale : -INFINITY;
-      }
+      *reinterpret_cast<float4*>(Sc + (i0 + a) * S4 + j0) =
+          make_float4(keep[0] ? acc[a][0] * scale : -INFINITY, keep[1] ? acc[a][1] * scale : -INFINITY,
+                      keep[2] ? acc[a][2] * scale : -INFINITY, keep[3] ? acc[a][3] * scale : -INFINITY);
   }
   __syncthreads();
   const float inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
@@ -265,7 +267,7 @@ bert_attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ pr
   const unsigned base0 = (unsigned)((b * nhead + h) * S * S);
 #pragma unroll 2
   for (int idx = tid; idx < S4 * (BHD / 4); idx += blockDim.x) {
-    const int s = idx / (BHD / 4), c = (idx % (BHD / 4)) * 4;
+    const int s = idx % S4, c = (idx / S4) * 4;      // lanes over tokens: conflict-free transposes
     float4 q = make_float4(0.f, 0.f, 0.f, 0.f), k = q, v = q, dc = q;
     if (s < S) {
       const float* r = qkv + (size_t)(b * S + s) * ld + h * BHD + c;
@@ -294,13 +296,17 @@ bert_attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ pr
     float acc[4][4];
     mm_tile(Ct, S4, Vt, S4, BHD, i0, j0, acc);
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < 4; ++a) {
+      const int i = i0 + a;
+      float o[4];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        const int i = i0 + a, j = j0 + c;
-        Ds[i * S4 + j] = (i < S && j < S)
+        const int j = j0 + c;
+        o[c] = (i < S && j < S)
             ? acc[a][c] * drop_scale(seed, stream, base0 + i * S + j, p_drop, inv_keep) : 0.f;
       }
+      *reinterpret_cast<float4*>(Ds + i * S4 + j0) = make_float4(o[0], o[1], o[2], o[3]);
+    }
   }
   __syncthreads();
   for (int i = warp; i < S; i += nw) {      // softmax backward; probabilities -> dropped ones

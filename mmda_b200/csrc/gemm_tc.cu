@@ -779,15 +779,41 @@ int encode_map(CUtensorMap* map, int kind, const void* ptr, long rows, long cols
 int g_tc_version = 2;          // 2 = persistent kernel (default), 1 = one tile per CTA
 int* g_sched = nullptr;        // ring of self-resetting scheduler slots (2 ints each)
 int g_sched_next = 0;
-constexpr int SCHED_SLOTS = 4096;
+// Scheduler slots: eager launches rotate through a ring (a slot is re-armed by its own kernel, and
+// 4096 launches never overlap in flight); launches recorded into a CUDA graph get slots of their
+// own that are never handed out again, because a graph may be replayed at any later time next to
+// eager launches on other streams.
+constexpr int SCHED_RING = 4096, SCHED_GRAPH = 28672, SCHED_SLOTS = SCHED_RING + SCHED_GRAPH;
+int g_sched_graph_next = 0;
 
-int* next_sched_slot() {
+int* next_sched_slot(cudaStream_t stream) {
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess) {
+    cudaGetLastError();
+    cap = cudaStreamCaptureStatusNone;
+  }
   if (g_sched == nullptr) {
-    if (cudaMalloc(&g_sched, SCHED_SLOTS * 2 * sizeof(int)) != cudaSuccess) return nullptr;
-    if (cudaMemset(g_sched, 0, SCHED_SLOTS * 2 * sizeof(int)) != cudaSuccess) return nullptr;
+    if (cap != cudaStreamCaptureStatusNone) {
+      mmda_set_error("gemm_tc: first use inside a CUDA graph capture (run one eager step first)");
+      return nullptr;
+    }
+    if (cudaMalloc(&g_sched, SCHED_SLOTS * 2 * sizeof(int)) != cudaSuccess ||
+        cudaMemset(g_sched, 0, SCHED_SLOTS * 2 * sizeof(int)) != cudaSuccess) {
+      cudaGetLastError();
+      g_sched = nullptr;
+      mmda_set_error("gemm_tc: cannot allocate the tile scheduler slots");
+      return nullptr;
+    }
+  }
+  if (cap != cudaStreamCaptureStatusNone) {
+    if (g_sched_graph_next >= SCHED_GRAPH) {
+      mmda_set_error("gemm_tc: out of scheduler slots for captured launches (%d used)", SCHED_GRAPH);
+      return nullptr;
+    }
+    return g_sched + 2 * (SCHED_RING + g_sched_graph_next++);
   }
   int* slot = g_sched + 2 * g_sched_next;
-  g_sched_next = (g_sched_next + 1) % SCHED_SLOTS;
+  g_sched_next = (g_sched_next + 1) % SCHED_RING;
   return slot;
 }
 
@@ -900,8 +926,8 @@ int mmda_gemm_tc(int kind, int a_mn, int b_mn, int M, int N, int K, const void* 
     a2.a = a;
     a2.tiles_m = (M + BM - 1) / BM; a2.tiles_n = (N + BN - 1) / BN; a2.split = split_k;
     a2.total = a2.tiles_m * a2.tiles_n * split_k;
-    a2.sched = next_sched_slot();
-    MMDA_REQUIRE(a2.sched != nullptr, "gemm_tc: cannot allocate the tile scheduler slots");
+    a2.sched = next_sched_slot(stream);
+    if (a2.sched == nullptr) return MMDA_ERR_CUDA;
     static int n_sm = 0;
     if (n_sm == 0) {
       int dev = 0;
