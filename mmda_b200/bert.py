@@ -49,7 +49,10 @@ class BertEngine:
         ps = list(self.eng.model.bertmodel.named_parameters())
         ver = tuple(p.data_ptr() for _, p in ps)
         if ver != self._pver:
+            from . import engine as _engine
             for n, p in ps:
+                if _engine._DRYRUN:
+                    continue
                 if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
                     raise MmdaError(f"bert parameter {n} must be a contiguous CUDA float32 tensor "
                                     "(no CPU fallback)")
@@ -103,8 +106,9 @@ class BertEngine:
         k.bind_stream()
         if ids.dim() != 2 or ids.shape != mask.shape or ids.shape != types.shape:
             raise MmdaError("bert: bert_sent / bert_sent_type / bert_sent_mask must be (B, S)")
+        from . import engine as _engine
         for t in (ids, types, mask):
-            if t.dtype != torch.int64 or not t.is_cuda:
+            if t.dtype != torch.int64 or not (t.is_cuda or _engine._DRYRUN):
                 raise MmdaError("bert: inputs must be CUDA int64 tensors")
         ids, types, mask = ids.contiguous(), types.contiguous(), mask.contiguous()
         B, S = ids.shape

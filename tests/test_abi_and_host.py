@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from mmda_b200 import MISA, MisaConfig, mosei_config
-from mmda_b200._lib import LIB, LIB_PATH, parse_header
+from mmda_b200._lib import LIB, LIB_PATH, MmdaError, parse_header
 
 
 def test_library_exports_every_declared_symbol():
@@ -190,3 +190,39 @@ def test_metrics_from_stats_matches_reference_definitions():
         assert abs(got[pre + "f1"] - M.f1_score(y, p, average=avg, zero_division=0)) < 1e-9
         assert abs(got[pre + "precision"] - M.precision_score(y, p, average=avg, zero_division=0)) < 1e-9
         assert abs(got[pre + "recall"] - M.recall_score(y, p, average=avg, zero_division=0)) < 1e-9
+
+
+def test_bert_branch_kernel_sequence_and_freeze_contract(dryrun):
+    """use_bert=True on the stubbed library: the hand-written BERT encoder issues 6 dense GEMMs per
+    layer forward, 6 data-gradient GEMMs per layer backward, and weight-gradient GEMMs only for
+    the layers the Solver leaves trainable (solver.py:66-73 freezes encoder layers 0-8)."""
+    from mmda_b200.synthetic import batch_for
+    from mmda_b200.trainer import FusedTrainer
+    cfg = mosei_config(vocab_size=50, batch_size=4, use_bert=True)
+    torch.manual_seed(0)
+    model = MISA(cfg).train()
+    for n, p in model.named_parameters():
+        if "bertmodel.encoder.layer" in n and int(n.split("encoder.layer.")[-1].split(".")[0]) <= 8:
+            p.requires_grad = False
+    b = batch_for(cfg, seed=1, lengths="ragged", seq_len=5)
+    tr = FusedTrainer(model)
+    # frozen tensors and the never-used pooler / tlayer_norm sit past the optimizer's range
+    for n, _ in model.named_parameters():
+        off, sz = tr.layout[n]
+        frozen = ("encoder.layer." in n and int(n.split("encoder.layer.")[-1].split(".")[0]) <= 8) \
+            or n.startswith(("bertmodel.pooler.", "tlayer_norm.", "sp_discriminator.", "confidence."))
+        assert (off >= tr.n_active) == frozen, n
+    tr.step(b.sentences, b.visual, b.acoustic, b.lengths, b.labels, b.bert_sent, b.bert_sent_type,
+            b.bert_sent_mask)
+    c = collections.Counter(dryrun.calls)
+    assert c["mmda_bert_attention_forward"] == 12 and c["mmda_bert_attention_backward"] == 12
+    assert c["mmda_gelu_forward"] == 12 and c["mmda_gelu_backward"] == 12
+    assert c["mmda_gemm_tc"] == 12 * 6 + 12 * 6 + 3 * 6        # fwd + dgrad + wgrad(layers 9-11)
+    assert c["mmda_bert_embed_forward"] == c["mmda_bert_embed_backward"] == 1
+    assert c["mmda_lstm_forward"] == 4                          # visual + acoustic only
+    seq = dryrun.calls
+    assert seq.index("mmda_bert_embed_forward") < seq.index("mmda_masked_mean_forward") \
+        < seq.index("mmda_loss_phase1") < seq.index("mmda_masked_mean_backward") \
+        < seq.index("mmda_bert_embed_backward") < seq.index("mmda_adam_clip_step")
+    with pytest.raises(MmdaError):
+        tr.step(b.sentences, b.visual, b.acoustic, b.lengths, b.labels)     # bert inputs missing
