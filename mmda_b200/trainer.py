@@ -253,7 +253,7 @@ class FusedTrainer:
         eng.k._c("mmda_step_state_advance", _ptr(self.state), self.lr, 0.9, 0.999)
         utt_text = None
         if self.use_bert:
-            if bert is None:
+            if bert is None or any(t is None for t in bert):
                 raise MmdaError("use_bert=True needs bert_sent / bert_sent_type / bert_sent_mask")
             utt_text = eng.bert.forward(bert[0], bert[1], bert[2], train=True,
                                         drop=self.model.training, seed=eng.seed ^ 0xB347,
