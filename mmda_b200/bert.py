@@ -72,7 +72,7 @@ class BertEngine:
     def _wop(self, P, name):
         ops = self._wops
         if name not in ops:
-            ops[name] = self.eng._prep("bertW_" + name, P[name])
+            ops[name] = self.eng._prep("bertW_" + name, P[name], split=True)
         return ops[name]
 
     def _mm(self, a_mn, b_mn, M, N, K, A, B, C, bias=None, acc=False):

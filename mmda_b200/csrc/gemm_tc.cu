@@ -336,7 +336,7 @@ struct TcArgs2 {
 };
 
 template <int KIND, int RAW>
-__global__ void __launch_bounds__(NUM_THREADS + RAW * 128, 1)
+__global__ void __launch_bounds__(NUM_THREADS + (RAW ? 128 : 0), 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
                 const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl,
                 const TcArgs2 q2) {
@@ -374,7 +374,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
   // warps split every stage in shared memory (hi = tf32(x) in place, lo = x - hi next to it) --
   // half the L2->SM traffic of pre-split operands and no split pass over HBM.  The split is
   // elementwise, so it is oblivious to the swizzled tile layout.
-  constexpr int TX_BYTES = RAW ? STAGE_BYTES / 2 : STAGE_BYTES;
+  // RAW = 1: both operands plain fp32; RAW = 2: A plain fp32, B pre-split (weights: split once per
+  // step, re-used by every tile, and the converter's shared-memory traffic halves)
+  constexpr int TX_BYTES = RAW == 1 ? STAGE_BYTES / 2 : (RAW == 2 ? 3 * STAGE_BYTES / 4 : STAGE_BYTES);
   constexpr int RING_READERS = RAW ? 9 : 5;
   const uint32_t tmem_slot = bar_base + 8u * NBARS;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
@@ -435,22 +437,26 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
           mbar_expect_tx(full_bar(s), TX_BYTES);
           const int k0 = (kb_beg + i) * BK;
 #pragma unroll
-          for (int part = 0; part < (RAW ? 1 : NPART); ++part) {
+          for (int part = 0; part < NPART; ++part) {
             const CUtensorMap* mA = part == 0 ? &mapAh : &mapAl;
             const CUtensorMap* mB = part == 0 ? &mapBh : &mapBl;
             const uint32_t sa = st + part * TILE_BYTES;
             const uint32_t sb = st + (NPART + part) * TILE_BYTES;
-            if (p.a_mn) {
-              for (int c = 0; c < N_CHUNKS; ++c)
-                tma_load_2d(sa + c * CHUNK_BYTES, mA, full_bar(s), m0 + c * MN_CHUNK, k0);
-            } else {
-              tma_load_2d(sa, mA, full_bar(s), k0, m0);
+            if (part == 0 || RAW == 0) {
+              if (p.a_mn) {
+                for (int c = 0; c < N_CHUNKS; ++c)
+                  tma_load_2d(sa + c * CHUNK_BYTES, mA, full_bar(s), m0 + c * MN_CHUNK, k0);
+              } else {
+                tma_load_2d(sa, mA, full_bar(s), k0, m0);
+              }
             }
-            if (p.b_mn) {
-              for (int c = 0; c < N_CHUNKS; ++c)
-                tma_load_2d(sb + c * CHUNK_BYTES, mB, full_bar(s), n0 + c * MN_CHUNK, k0);
-            } else {
-              tma_load_2d(sb, mB, full_bar(s), k0, n0);
+            if (part == 0 || RAW != 1) {
+              if (p.b_mn) {
+                for (int c = 0; c < N_CHUNKS; ++c)
+                  tma_load_2d(sb + c * CHUNK_BYTES, mB, full_bar(s), n0 + c * MN_CHUNK, k0);
+              } else {
+                tma_load_2d(sb, mB, full_bar(s), k0, n0);
+              }
             }
           }
         }
@@ -525,7 +531,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
         mbar_wait(full_bar(s), it & 1);
         uint8_t* st = smem_raw + (base + s * STAGE_BYTES - smem_u32(smem_raw));
 #pragma unroll
-        for (int op = 0; op < 2; ++op) {           // A then B: hi slot at 2*op, lo slot at 2*op+1
+        for (int op = 0; op < (RAW == 1 ? 2 : 1); ++op) {   // A (then B): hi slot 2*op, lo slot 2*op+1
           float4* hi = reinterpret_cast<float4*>(st + (2 * op) * TILE_BYTES);
           float4* lo = reinterpret_cast<float4*>(st + (2 * op + 1) * TILE_BYTES);
 #pragma unroll
@@ -879,7 +885,8 @@ int mmda_gemm_tc(int kind, int a_mn, int b_mn, int M, int N, int K, const void* 
   // kind 2: 3xTF32 from plain fp32 operands (A_hi / B_hi point at the fp32 data, the lo pointers
   // are ignored); the hi/lo split happens in shared memory inside the kernel
   const bool raw = kind == 2;
-  if (raw) { kind = 0; A_lo = A_hi; B_lo = B_hi; }
+  const int raw_mode = !raw ? 0 : (B_lo != nullptr ? 2 : 1);    // 2: B arrives pre-split
+  if (raw) { kind = 0; A_lo = A_hi; if (B_lo == nullptr) B_lo = B_hi; }
   MMDA_REQUIRE(!raw || g_tc_version == 2, "gemm_tc: kind 2 needs the persistent kernel");
   MMDA_REQUIRE(kind == 0 || kind == 1, "gemm_tc: kind=%d", kind);
   MMDA_REQUIRE(K > 0 && A_hi && B_hi && C, "gemm_tc: bad arguments");
@@ -936,9 +943,12 @@ int mmda_gemm_tc(int kind, int a_mn, int b_mn, int M, int N, int K, const void* 
     }
     const int ctas = a2.total < n_sm ? a2.total : n_sm;
     constexpr int smem2 = 12 * TILE_BYTES + 1024 + 512 + 4 * 32 * 33 * 4;
-    if (kind == 0 && raw) {
+    if (kind == 0 && raw_mode == 1) {
       MMDA_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
       gemm_tc2_kernel<0, 1><<<ctas, NUM_THREADS + 128, smem2, stream>>>(mAh, mAl, mBh, mBl, a2);
+    } else if (kind == 0 && raw_mode == 2) {
+      MMDA_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+      gemm_tc2_kernel<0, 2><<<ctas, NUM_THREADS + 128, smem2, stream>>>(mAh, mAl, mBh, mBl, a2);
     } else if (kind == 0) {
       MMDA_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
       gemm_tc2_kernel<0, 0><<<ctas, NUM_THREADS, smem2, stream>>>(mAh, mAl, mBh, mBl, a2);

@@ -67,10 +67,10 @@ class Kernels:
                 c_ilv=0):
         """Tensor-core GEMM.  A, B = (hi, lo_or_None) 2-D operand views (unit inner stride)."""
         (Ah, Al), (Bh, Bl) = A, B
-        if kind == 0 and Al is None and Bl is None:
-            kind = 2                     # plain fp32 operands, split in shared memory
-        elif kind == 0 and (Al is None or Bl is None):
-            raise MmdaError("gemm_tc: mixing pre-split and raw 3xTF32 operands")
+        if kind == 0 and Al is None:
+            kind = 2     # A plain fp32 (split in shared memory); B plain (Bl None) or pre-split
+        elif kind == 0 and Bl is None:
+            raise MmdaError("gemm_tc: a pre-split A operand needs a pre-split B operand")
         self._c("mmda_gemm_tc", kind, int(a_mn), int(b_mn), M, N, K, _ptr(Ah), _ptr(Al), Ah.stride(0),
                 _ptr(Bh), _ptr(Bl), Bh.stride(0), alpha, _ptr(C), C.stride(0), _ptr(bias), None, mode,
                 split_k, c_ilv)
@@ -322,11 +322,20 @@ class MisaEngine:
     def _tc_ok(self, H, I):
         return self.use_tc and H % 4 == 0 and I % 4 == 0
 
-    def _prep(self, name, x, out=None, row0=0, kind=None):
+    def _prep(self, name, x, out=None, row0=0, kind=None, split=False):
         """Tensor-core operand copy of the 2-D view x: (hi, lo) tf32 split or (bf16, None).
-        Rows land at [row0, row0+rows) of the (possibly larger) buffer `out`."""
+        Rows land at [row0, row0+rows) of the (possibly larger) buffer `out`.  In the default
+        3xTF32 mode activations are consumed as plain fp32 (returned as is); ``split=True`` forces
+        the ahead-of-time split -- used for weights (B operands), which every tile re-reads."""
         kind = self.tc_kind if kind is None else kind
         rows, cols = x.shape
+        if kind == 0 and self.tc_raw and split:
+            ld = (cols + 3) // 4 * 4
+            hi = self.buf(name + "_hi", rows, ld)[:, :cols]
+            lo = self.buf(name + "_lo", rows, ld)[:, :cols]
+            self.k._c("mmda_split_tf32", _ptr(x), x.stride(0), rows, cols, _ptr(hi), _ptr(lo),
+                      hi.stride(0))
+            return hi, lo
         if kind == 0 and self.tc_raw:
             if out is None and x.stride(1) == 1 and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0:
                 return x, None           # consumed as is
@@ -342,12 +351,12 @@ class MisaEngine:
                       hi.stride(0))
         return out
 
-    def _prep_buf(self, name, rows, cols, kind=None):
+    def _prep_buf(self, name, rows, cols, kind=None, split=False):
         kind = self.tc_kind if kind is None else kind
         if kind == 0:
             ld = (cols + 3) // 4 * 4
             hi = self.buf(name + "_hi", rows, ld)[:, :cols]
-            if self.tc_raw:
+            if self.tc_raw and not split:
                 return hi, None
             lo = self.buf(name + "_lo", rows, ld)[:, :cols]
             return hi, lo
@@ -357,11 +366,11 @@ class MisaEngine:
     def _pack_weights(self, r, P, H, I, kind, want_bias=True):
         """Stacked gate-interleaved copy of layer r's W_ih (both directions) for GEMM kind
         `kind` (-1: plain fp32 for the SIMT path, 0: tf32 hi/lo, 1: bf16) + the bias stack."""
-        mode = {-1: 0, 0: 0 if self.tc_raw else 1, 1: 2}[kind]
+        mode = {-1: 0, 0: 1, 1: 2}[kind]
         if kind == -1:
             W = (self.buf(f"Wst_{r}", 8 * H, I), None)
         else:
-            W = self._prep_buf(f"tcW_{r}", 8 * H, I, kind)
+            W = self._prep_buf(f"tcW_{r}", 8 * H, I, kind, split=True)
         bst = self.buf(f"bst_{r}", 8 * H) if want_bias else None
         self.k._c("mmda_lstm_pack_weights", _ptr(P[f"{r}.weight_ih_l0"]),
                   _ptr(P[f"{r}.weight_ih_l0_reverse"]), _ptr(P[f"{r}.bias_ih_l0"]),
@@ -401,7 +410,7 @@ class MisaEngine:
         """out = x w^T + b on tcgen05 (3xTF32: fp32-accurate in either precision mode)."""
         M, K = x.shape
         self.k.gemm_tc(0, 0, 0, M, w.shape[0], K, self._prep(tag + "_x", x, kind=0),
-                       self._prep(tag + "_w", w, kind=0), out, bias=b)
+                       self._prep(tag + "_w", w, kind=0, split=True), out, bias=b)
 
     def tc_linear_bwd(self, tag, dy, x, w, dw, db, dx, dx_acc):
         """dw += dy^T x, db += colsum(dy), dx (+)= dy w   (dy: [M][N], x: [M][K], w: [N][K])"""
@@ -410,7 +419,7 @@ class MisaEngine:
         dyo = self._prep(tag + "_dy", dy, kind=0)
         self.k.gemm_tc(0, 1, 1, N, K, M, dyo, self._prep(tag + "_x", x, kind=0), dw, mode=1, split_k=0)
         self.k.colsum(dy, db)
-        self.k.gemm_tc(0, 0, 1, M, K, N, dyo, self._prep(tag + "_w", w, kind=0), dx,
+        self.k.gemm_tc(0, 0, 1, M, K, N, dyo, self._prep(tag + "_w", w, kind=0, split=True), dx,
                        mode=1 if dx_acc else 0, split_k=0 if dx_acc else 1)
 
     @staticmethod
@@ -897,7 +906,7 @@ class MisaEngine:
                 dGp = self._prep(f"tcdG_{r}", Gt, kind=0)
                 if self.tc_kind == 0 and self.tc_raw:
                     Xp = self._prep(f"tcX_{r}", Xin, kind=0)          # the fp32 tensor itself
-                    Wst = self._prep_buf(f"tcW_{r}", 8 * H, I, 0)     # packed by the forward
+                    Wst = self._prep_buf(f"tcW_{r}", 8 * H, I, 0, split=True)   # packed by the forward
                 elif self.tc_kind == 0:    # operand splits written by the forward
                     Xp = self._prep_buf(f"tcX_{r}", N, I, 0)
                     Wst = self._prep_buf(f"tcW_{r}", 8 * H, I, 0)

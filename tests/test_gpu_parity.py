@@ -446,6 +446,12 @@ def test_gemm_tc_tf32x3_and_bf16(dev):
                      None, B.stride(0), 1.0, _ptr(out2), N, _ptr(bias), None, 0, 1, 0)
                 C.flag(f"tf32x3 raw == pre-split {M}x{N}x{K} a_mn={a_mn} b_mn={b_mn}",
                        torch.equal(out, out2))
+                # mixed: A plain fp32, B pre-split (how weights are fed)
+                out3 = torch.full((M, N), 6.0, device=dev)
+                k._c("mmda_gemm_tc", 2, a_mn, b_mn, M, N, K, _ptr(A), None, A.stride(0), _ptr(Bh),
+                     _ptr(Bl), B.stride(0), 1.0, _ptr(out3), N, _ptr(bias), None, 0, 1, 0)
+                C.flag(f"tf32x3 raw-A/split-B == pre-split {M}x{N}x{K} a_mn={a_mn} b_mn={b_mn}",
+                       torch.equal(out, out3))
                 if K >= 1000:
                     acc = torch.randn(M, N, generator=g).to(dev)
                     ref2 = acc.double() + 0.5 * ref
