@@ -562,7 +562,12 @@ def test_cuda_graph_replay_equals_eager(dev, rnncell):
     assert res[True][2] == res[False][2] == 7
     C = Checks("graph_" + rnncell)
     C.add("losses over 7 steps", res[True][0], res[False][0], 1e-5)
-    C.add("parameters after 7 steps", res[True][1], res[False][1], 1e-5)
+    # parameters: atomics (split-K, RED epilogues) make rounding-level gradient elements differ
+    # between two runs, and Adam turns such an element into a +-lr update whose sign is noise:
+    # the bound is Adam's noise floor 2*lr*steps, the trajectory check above is the tight one
+    dp = float((res[True][1] - res[False][1]).abs().max())
+    C.rows.append((f"parameters after 7 steps: max |delta| = {dp:.3e} <= 2*lr*steps", dp,
+                   2 * cfg.learning_rate * 7, dp <= 2 * cfg.learning_rate * 7))
     C.finish()
 
 
