@@ -70,9 +70,14 @@ int mmda_sgemm(int transA, int transB, int M, int N, int K, float alpha, const f
 
 /* Tensor-core path of the same contractions (tcgen05.mma + TMA + TMEM; csrc/gemm_tc.cu).
  * kind 0 = 3xTF32 (fp32-accurate; operands pre-split with mmda_split_tf32 into hi/lo fp32 arrays),
- * kind 1 = bf16 operands (mmda_cast_bf16), fp32 accumulate.  a_mn/b_mn: 0 = operand stored
- * [MN][K] (K contiguous), 1 = stored [K][MN].  Row pitches must be multiples of 16 bytes.
- * mode 0: C = alpha*A*B^T + bias + bias2; mode 1: C += ...; split_k (0 = auto) needs mode 1. */
+ * kind 1 = bf16 operands (mmda_cast_bf16), fp32 accumulate,
+ * kind 2 = 3xTF32 with A given as plain fp32 (A_hi = the fp32 data, A_lo ignored): the kernel's
+ *          converter warps split every A stage into tf32 hi/lo in shared memory; B is plain fp32
+ *          too when B_lo == NULL, else pre-split (weights).  Bit-identical to kind 0.
+ * a_mn/b_mn: 0 = operand stored [MN][K] (K contiguous), 1 = stored [K][MN].  Base pointers must be
+ * 16-byte aligned and row pitches multiples of 16 bytes.
+ * mode 0: C = alpha*A*B^T + bias + bias2; mode 1: C += ... (vector RED); split_k (0 = auto) needs
+ * mode 1.  c_row_interleave as in mmda_sgemm. */
 int mmda_gemm_tc(int kind, int a_mn, int b_mn, int M, int N, int K, const void* A_hi,
                  const void* A_lo, int lda, const void* B_hi, const void* B_lo, int ldb, float alpha,
                  float* C, int ldc, const float* bias, const float* bias2, int mode, int split_k,
