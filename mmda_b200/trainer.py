@@ -76,6 +76,28 @@ def plan_arena(named_shapes: List[Tuple[str, Tuple[int, ...]]], use_confid: bool
     return layout, ranges[:5], n_active, off
 
 
+_LIVE_DP_TRAINERS = None     # weak set of data-parallel trainers that may hold captured graphs
+
+
+def _register_dp_trainer(tr):
+    """Captured CUDA graphs reference the NCCL communicator; ``destroy_process_group`` waits on
+    them forever.  Wrap it once so that every live data-parallel trainer drops its graph first."""
+    global _LIVE_DP_TRAINERS
+    import weakref
+    import torch.distributed as dist
+    if _LIVE_DP_TRAINERS is None:
+        _LIVE_DP_TRAINERS = weakref.WeakSet()
+        original = dist.destroy_process_group
+
+        def destroy_process_group(*args, **kwargs):
+            for t in list(_LIVE_DP_TRAINERS):
+                t.close()
+            return original(*args, **kwargs)
+
+        dist.destroy_process_group = destroy_process_group
+    _LIVE_DP_TRAINERS.add(tr)
+
+
 class FusedTrainer:
     def __init__(self, model, lr: Optional[float] = None, process_group=None,
                  global_batch_stats: bool = True, use_graph: Optional[bool] = None):
@@ -111,6 +133,8 @@ class FusedTrainer:
         self._graph = None
         self._graph_seen = {}
         self.launches_per_step = None
+        if self.world > 1 and self.use_graph:
+            _register_dp_trainer(self)
 
     # ------------------------------------------------------------------ arenas -------------
     def _build_arena(self):
@@ -332,8 +356,10 @@ class FusedTrainer:
 
     def close(self):
         """Drop the captured CUDA graph.  Under data parallelism the graph references the NCCL
-        communicator: call this before ``dist.destroy_process_group()`` (which otherwise waits
-        for the graph's resources and hangs)."""
+        communicator and must be gone before ``dist.destroy_process_group()`` (which otherwise
+        waits for the graph's resources and hangs); ``torch.distributed.destroy_process_group``
+        is wrapped to do this for every live data-parallel trainer, calling it explicitly is
+        still fine."""
         self._graph = None
         self._graph_seen = {}
         import gc

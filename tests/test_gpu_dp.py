@@ -70,7 +70,10 @@ def _worker(rank, world, port, q):
         traj.append(torch.stack([tr.step(*args)[:6].clone() for _ in range(6)]))
         assert (tr._graph is not None) == mode
         finals.append(tr.p_arena[:tr.n_active].clone())
-        tr.close()
+        if not mode:
+            tr.close()       # the graph-holding trainer is closed by the wrapped destroy_process_group
+        else:
+            keep_alive = tr
     # losses over the trajectory must agree tightly; parameters only up to Adam's noise floor
     # (gradient elements at rounding level get +-lr updates whose sign is noise: <= 2*lr*steps)
     perr = float(((traj[0] - traj[1]).abs() / traj[1].abs().clamp_min(1e-6)).max())
