@@ -129,6 +129,29 @@ int mmda_lstm_shift_h(const float* y, float* hprev, const int* row_t, const int*
                       const int* lens_sorted, const int* offsets, int N, int H,
                       mmda_stream_t stream);
 
+/* ---- tensor-core recurrence for large hidden sizes (text encoder, H = 300): same contract and
+ * buffers as mmda_lstm_forward / mmda_lstm_backward (nn.LSTM, src/models.py:48-55,167,176), the
+ * per-step h * W_hh^T product runs on tcgen05 with every operand split into three bf16 terms
+ * (fp32-accurate, 6 MMAs per K step), W_hh resident in TMEM + shared memory, h_t exchanged between
+ * the CTAs of a batch tile through an L2-resident workspace `ws`.  ws[0] (int) is set to 1 if a
+ * peer CTA never showed up (the launch then ends with garbage instead of hanging). */
+long long mmda_lstm_tc_workspace_bytes(int B, int H, int Tmax);   /* -1: hidden size not covered */
+/* out8 = {slices, groups, batch tile, n tiles, padded K, smem fwd, smem bwd, CTAs} */
+int mmda_lstm_tc_plan(int B, int H, int Tmax, int* out8);
+int mmda_lstm_tc_forward(float* gates, const float* whh_f, const float* whh_r, float* y, float* c,
+                         const int* lens_sorted, const int* sorted_idx, const int* offsets,
+                         float* utt, int utt_ld, int utt_off_f, int utt_off_r, int B, int H,
+                         int Tmax, int save_for_backward, void* ws, mmda_stream_t stream);
+int mmda_lstm_tc_backward(float* gates, const float* whh_f, const float* whh_r, const float* c,
+                          const float* dy, const float* dutt, int utt_ld, int utt_off_f,
+                          int utt_off_r, const int* lens_sorted, const int* sorted_idx,
+                          const int* offsets, int B, int H, int Tmax, void* ws,
+                          mmda_stream_t stream);
+/* A/B knob: SMs one launch may occupy (default 120: the rest serve the concurrent encoders) */
+int mmda_lstm_tc_set_max_ctas(int n);
+/* diagnostic: per-step phase timestamps of CTA 0 (NULL = off) */
+int mmda_lstm_tc_set_debug_buffer(long long* dev_buf);
+
 /* ---- nn.LayerNorm, src/models.py:65-80,155-157,172 and the two norms of the fusion layer ----
  * y = LN(x + res) (res may be NULL); mean/rstd saved per row for the backward. */
 int mmda_layernorm_forward(const float* x, int ldx, const float* res, int ldr, const float* gamma,

@@ -1,0 +1,778 @@
+// Tensor-core persistent bidirectional LSTM recurrence for sm_100a (forward and BPTT), the
+// large-hidden-size path (text encoder, H = 300) of nn.LSTM at reference src/models.py:48-55,
+// 167,176.  Same contract, buffers and layouts as lstm.cu (gates [N][2][H][4], y / c [N][2][H],
+// PackedSequence row order, h0 = c0 = 0, reverse direction runs t = L_b-1..0, rows past a
+// sample's length are never touched); semantics restated in oracle/explicit.py::lstm_direction.
+//
+// Why tensor cores.  The fp32 SIMT recurrence is bound by shared-memory operand delivery
+// (1 536 B of operands per 32 FFMA per warp).  tcgen05 reads its operands straight
+// from TMEM / shared memory.  fp32 accuracy is kept by splitting every operand into THREE bf16
+// terms (x = x1 + x2 + x3 exactly to fp32 rounding) and issuing the six products whose weight is
+// >= 2^-16:  W1h1 | W1h2 + W2h1 | W1h3 + W2h2 + W3h1  (the dropped terms are <= 2^-24 relative).
+// The tensor core accumulates in fp32 with truncation, so the dominant W1h1 chain alternates
+// over two TMEM accumulators and the small terms get their own; the three are added in
+// round-to-nearest fp32 by the cell-update threads.
+//
+// Work split.  One CTA per SM, no clusters: CTA (direction, group, slice r) keeps the 4 gate
+// rows of hidden units [32r, 32r+32) -- 128 rows = one M=128 MMA -- resident for the whole
+// sequence: W1, W2 in TMEM (the A operand is read from TMEM), W3 in shared memory.  A group of
+// S = ceil(H/32) CTAs shares one batch tile of <= 48 length-sorted samples (the MMA N).  Every
+// step each CTA computes  gates^T[128 x N] = W_slice[128 x K] * h_{t-1}^T[K x N],  finishes the
+// cell update of its own units in registers (4x4 shuffle transposes bring the i,f,g,o values of
+// one cell into one thread) and publishes its 32 columns of h_t to an L2-resident exchange
+// buffer; a release/acquire counter per tile replaces the cluster barrier.  The backward kernel
+// keeps W^T (three M-tiles over the H output columns, K = its 128 gate rows), multiplies it with
+// its own d(gates) of the successor step, and exchanges the partial dh through an L2 scratch.
+#include "common.cuh"
+#include "tcgen05.cuh"
+
+namespace {
+
+using namespace tc5;
+
+constexpr int TCL_THREADS = 256;
+constexpr int TCL_N = 48;                     // batch rows per tile = widest MMA N used
+constexpr int TCL_UNITS = 32;                 // hidden units per CTA (x4 gates = 128 MMA rows)
+constexpr int A_ATOM = 128 * 128;             // bytes: 128 rows x 64 bf16 (one 128B-swizzle K atom)
+constexpr int B_ATOM = TCL_N * 128;           // bytes: 48 rows x 64 bf16
+constexpr int HS_LD = 33;                     // h_t staging pitch (floats)
+constexpr int MISC_FIXED = 64 + TCL_N * HS_LD * 4 + 2 * TCL_N * 4;   // barriers, staging, lens, orig
+constexpr long long SPIN_LIMIT = 1LL << 31;   // clock64 ticks (~1 s): a lost peer ends the launch, not the box
+
+struct TclArgs {
+  float* gates;           // [N][8H]
+  const float* whh[2];    // per direction [4H][H]
+  float* y;               // [N][2H]
+  float* c;               // [N][2H]
+  const int* lens;        // [B] sorted (descending) lengths
+  const int* sorted_idx;  // [B]
+  const int* offsets;     // [Tmax+1]
+  float* utt;             // fwd: final hidden states, (B, utt_ld), original batch order
+  const float* dutt;      // bwd
+  const float* dy;        // bwd: grad wrt y [N][2H] (nullable)
+  int utt_ld, utt_off0, utt_off1;
+  int B, H, Kp, S, G, BT, NT, MT, save, Tmax;
+  float* xch;             // fwd: h exchange [2][NT][2][48][S*32]; bwd: partials [2][2][NT][S][48][S*32]
+  unsigned* flags;        // [2][NT] step counters (zeroed before the launch)
+  int* err;               // set to 1 when a peer never showed up
+  long long* dbg;
+};
+
+// wait until *flag >= target (thread 0 only); returns false after SPIN_LIMIT ticks or when another
+// CTA already gave up
+__device__ __forceinline__ bool spin_until(const unsigned* flag, unsigned target, int* err) {
+  if (ld_acquire(flag) >= target) return true;
+  const long long t0 = clock64();
+  unsigned it = 0;
+  while (ld_acquire(flag) < target) {
+    if ((++it & 255u) == 0) {
+      if (clock64() - t0 > SPIN_LIMIT || *reinterpret_cast<volatile int*>(err) != 0) {
+        *reinterpret_cast<volatile int*>(err) = 1;
+        return false;
+      }
+    }
+  }
+  return true;
+}
+
+// byte offset of the 16-byte chunk (row n, k-chunk ck of 8 bf16) inside a K-major 128B-swizzled
+// operand whose 64-element K atoms are `atom_bytes` apart
+__device__ __forceinline__ uint32_t swz_chunk(int n, int ck, int atom_bytes) {
+  return (uint32_t)((ck >> 3) * atom_bytes + (n >> 3) * 1024 + (n & 7) * 128 + (((ck & 7) ^ (n & 7)) << 4));
+}
+
+// 4x4 transpose across the 4 lanes that hold the i,f,g,o rows of one unit: on entry lane g holds
+// a[j] = gate g of column j; on exit lane g holds a[j] = gate j of column g.
+__device__ __forceinline__ void transpose4(float (&a)[4], int g) {
+  const bool o1 = (g & 1) != 0, o2 = (g & 2) != 0;
+  // stage 1 (partner g^1): even lanes keep columns {0,2}, odd lanes keep {1,3}
+  const float s0 = o1 ? a[0] : a[1], s1 = o1 ? a[2] : a[3];
+  const float r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+  // (lo column: gates 2*(g/2), 2*(g/2)+1), (hi column = lo + 2: same gates)
+  const float lo_e = o1 ? r0 : a[0], lo_o = o1 ? a[1] : r0;
+  const float hi_e = o1 ? r1 : a[2], hi_o = o1 ? a[3] : r1;
+  // stage 2 (partner g^2): lanes 0,1 keep the lo column, lanes 2,3 keep the hi column
+  const float t0 = o2 ? lo_e : hi_e, t1 = o2 ? lo_o : hi_o;
+  const float u0 = __shfl_xor_sync(0xffffffffu, t0, 2), u1 = __shfl_xor_sync(0xffffffffu, t1, 2);
+  a[0] = o2 ? u0 : lo_e;
+  a[1] = o2 ? u1 : lo_o;
+  a[2] = o2 ? hi_e : u0;
+  a[3] = o2 ? hi_o : u1;
+}
+
+// ------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TCL_THREADS, 1) lstm_tc_fwd_kernel(const TclArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sptr = smem_raw + (sbase - smem_u32(smem_raw));
+  const int H = p.H, Kp = p.Kp, S = p.S;
+  const int KA = (Kp + 63) >> 6;              // K atoms
+  const int KC = Kp >> 3;                     // 16-byte chunks per operand row
+  const uint32_t W3_off = 0;
+  const uint32_t hB_off = (uint32_t)KA * A_ATOM;
+  const uint32_t hB_split = (uint32_t)KA * B_ATOM;
+  const uint32_t misc_off = hB_off + 3 * hB_split;
+  const uint32_t mma_bar = sbase + misc_off;
+  const uint32_t tmem_slot = sbase + misc_off + 8;
+  volatile int* abort_s = reinterpret_cast<volatile int*>(sptr + misc_off + 16);
+  float* hs = reinterpret_cast<float*>(sptr + misc_off + 64);     // [48][HS_LD]
+  int* lens_s = reinterpret_cast<int*>(hs + TCL_N * HS_LD);
+  int* orig_s = lens_s + TCL_N;
+  int* cnt_s = orig_s + TCL_N;                                    // [Tmax] rows alive at time t
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, hc = warp >> 2;
+  const int r = blockIdx.x % S;
+  const int grp = (blockIdx.x / S) % p.G;
+  const int dir = blockIdx.x / (S * p.G);
+  const int XLD = S * TCL_UNITS;              // exchange row pitch (floats)
+
+  if (tid == 0) {
+    mbar_init(mma_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    *abort_s = 0;
+  }
+  if (warp == 0) tmem_alloc512(tmem_slot);
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tm = *reinterpret_cast<uint32_t*>(sptr + misc_off + 8);
+  const uint32_t tmW1 = tm, tmW2 = tm + (Kp >> 1);
+  const uint32_t tmD = tm + 2 * (Kp >> 1);    // main0 | main1 | cross, TCL_N columns each
+  const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+
+  {  // resident weights: row rho = 4*ul + g of the slice = W_hh[g*H + 32r + ul][:]
+    const int rho = q * 32 + lane, ul = rho >> 2, g = rho & 3, u = r * TCL_UNITS + ul;
+    const float* __restrict__ src = p.whh[dir] + (size_t)(g * H + min(u, H - 1)) * H;
+    const bool row_ok = u < H;
+    const bool vec = (H & 3) == 0;
+    const int c_beg = hc == 0 ? 0 : (KC + 1) / 2, c_end = hc == 0 ? (KC + 1) / 2 : KC;
+    for (int ck = c_beg; ck < c_end; ++ck) {
+      float x[8];
+      const int k0 = ck * 8;
+      if (row_ok && vec && k0 + 8 <= H) {
+        const float4 a = *reinterpret_cast<const float4*>(src + k0);
+        const float4 b = *reinterpret_cast<const float4*>(src + k0 + 4);
+        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = (row_ok && k0 + i < H) ? src[k0 + i] : 0.f;
+      }
+      uint4 w1, w2, w3;
+      split3x8(x, w1, w2, w3);
+      tmem_st4(tmW1 + lane_sel + ck * 4, w1.x, w1.y, w1.z, w1.w);
+      tmem_st4(tmW2 + lane_sel + ck * 4, w2.x, w2.y, w2.z, w2.w);
+      *reinterpret_cast<uint4*>(sptr + W3_off + swz_chunk(rho, ck, A_ATOM)) = w3;
+    }
+    tmem_wait_st();
+  }
+  fence_async_smem();
+  fence_before();
+  __syncthreads();
+
+  // my cells: unit ul = 8q + lane/4, batch columns b_i = 24*hc + 4*i + (lane & 3), i < 6
+  const int g4 = lane & 3;
+  const int ul = 8 * q + (lane >> 2);
+  const int u = r * TCL_UNITS + ul;
+  const bool u_ok = u < H;
+  const int H2 = 2 * H, H8 = 8 * H;
+  const int gcol = dir * 4 * H + u * 4;
+  const int ycol = dir * H + u;
+  const int utt_off = dir == 0 ? p.utt_off0 : p.utt_off1;
+  uint32_t mma_phase = 0;
+  const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0 && tid == 0;
+#define TCL_TS(i) if (dbg_on && tile == grp) p.dbg[s * 8 + (i)] = clock64();
+
+  for (int tile = grp; tile < p.NT; tile += p.G) {
+    const int b_base = tile * p.BT;
+    const int rows = min(p.BT, p.B - b_base);
+    __syncthreads();   // previous tile fully done with lens_s / cnt_s / hs
+    if (tid < TCL_N) {
+      lens_s[tid] = tid < rows ? p.lens[b_base + tid] : 0;
+      orig_s[tid] = tid < rows ? p.sorted_idx[b_base + tid] : 0;
+    }
+    __syncthreads();
+    const int L = lens_s[0];
+    for (int t = tid; t < L; t += TCL_THREADS) {
+      int n = 0;
+      for (int j = 0; j < rows; ++j) n += lens_s[j] > t;
+      cnt_s[t] = n;
+    }
+    __syncthreads();
+    unsigned* flag = p.flags + dir * p.NT + tile;
+    float* xbuf = p.xch + (size_t)(dir * p.NT + tile) * 2 * TCL_N * XLD;
+    float cst[6];
+    int len_c[6], orig_c[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      cst[i] = 0.f;
+      const int b = 24 * hc + 4 * i + g4;
+      len_c[i] = u_ok ? lens_s[b] : 0;
+      orig_c[i] = orig_s[b];
+    }
+
+    for (int s = 0; s < L; ++s) {
+      const int t = dir == 0 ? s : L - 1 - s;
+      const int tprev = dir == 0 ? t - 1 : t + 1;
+      TCL_TS(0)
+      const int off_t = __ldg(p.offsets + t);
+      // x-projection of my cells (independent of h: in flight during the exchange + MMAs)
+      float4 xg[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const int b = 24 * hc + 4 * i + g4;
+        xg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t < len_c[i])
+          xg[i] = __ldcs(reinterpret_cast<const float4*>(p.gates + (size_t)(off_t + b_base + b) * H8 + gcol));
+      }
+      float acc[6][4];
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+      if (s > 0) {
+        const int n_act = cnt_s[t];
+        const int Nmma = (n_act + 15) & ~15;
+        if (tid == 0 && !*abort_s) {
+          if (!spin_until(flag, (unsigned)(S * s), p.err)) *abort_s = 1;
+        }
+        __syncthreads();
+        TCL_TS(1)
+        // ---- h_{t-1} tile: fp32 from L2 -> three bf16 terms -> swizzled K-major B operand ----
+        const float* xsrc = xbuf + (size_t)((s - 1) & 1) * TCL_N * XLD;
+        const int items = Nmma * KC;
+        for (int id = tid; id < items; id += TCL_THREADS) {
+          const int n = id / KC, ck = id - n * KC;
+          float x[8];
+          if (tprev < lens_s[n]) {      // row n had a predecessor step (else h_{t-1} = h0 = 0)
+            const float4 a = __ldcg(reinterpret_cast<const float4*>(xsrc + (size_t)n * XLD + ck * 8));
+            const float4 b = __ldcg(reinterpret_cast<const float4*>(xsrc + (size_t)n * XLD + ck * 8 + 4));
+            x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = 0.f;
+          }
+          uint4 h1, h2, h3;
+          split3x8(x, h1, h2, h3);
+          const uint32_t o = hB_off + swz_chunk(n, ck, B_ATOM);
+          *reinterpret_cast<uint4*>(sptr + o) = h1;
+          *reinterpret_cast<uint4*>(sptr + o + hB_split) = h2;
+          *reinterpret_cast<uint4*>(sptr + o + 2 * hB_split) = h3;
+        }
+        fence_async_smem();
+        fence_before();
+        __syncthreads();
+        TCL_TS(2)
+        if (tid == 0) {
+          fence_after();
+          const uint32_t idesc = idesc_bf16(128, Nmma);
+          const uint32_t d_m0 = tmD, d_m1 = tmD + TCL_N, d_x = tmD + 2 * TCL_N;
+          const int KS = Kp >> 4;
+          for (int ks = 0; ks < KS; ++ks) {
+            const uint32_t bo = sbase + hB_off + (uint32_t)(ks >> 2) * B_ATOM + (uint32_t)(ks & 3) * 32;
+            const uint64_t b1 = make_desc(bo, 16, 1024), b2 = make_desc(bo + hB_split, 16, 1024),
+                           b3 = make_desc(bo + 2 * hB_split, 16, 1024);
+            const uint64_t a3 = make_desc(sbase + W3_off + (uint32_t)(ks >> 2) * A_ATOM + (uint32_t)(ks & 3) * 32, 16, 1024);
+            const uint32_t a1 = tmW1 + ks * 8, a2 = tmW2 + ks * 8;
+            mma_ts(d_x, a1, b3, idesc, ks > 0 ? 1u : 0u);   // 2^-16 terms first
+            mma_ss(d_x, a3, b1, idesc, 1u);
+            mma_ts(d_x, a2, b2, idesc, 1u);
+            mma_ts(d_x, a1, b2, idesc, 1u);                 // 2^-8 terms
+            mma_ts(d_x, a2, b1, idesc, 1u);
+            mma_ts((ks & 1) ? d_m1 : d_m0, a1, b1, idesc, ks >= 2 ? 1u : 0u);
+          }
+          commit(mma_bar);
+        }
+        mbar_wait(mma_bar, mma_phase);
+        mma_phase ^= 1;
+        fence_after();
+        TCL_TS(3)
+        // ---- D -> registers: my row (gate g4 of unit ul), 24 batch columns ----
+        const int KSn = Kp >> 4;
+#pragma unroll
+        for (int cb = 0; cb < 3; ++cb) {
+          uint32_t m0[8], m1[8], xx[8];
+          const uint32_t col = (uint32_t)(24 * hc + 8 * cb);
+          tmem_ld8(tmD + lane_sel + col, m0);
+          tmem_ld8(tmD + lane_sel + 2 * TCL_N + col, xx);
+          if (KSn > 1) tmem_ld8(tmD + lane_sel + TCL_N + col, m1);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float v = __uint_as_float(m0[j]);
+            if (KSn > 1) v += __uint_as_float(m1[j]);
+            acc[cb * 2 + (j >> 2)][j & 3] = v + __uint_as_float(xx[j]);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) transpose4(acc[i], g4);
+      }
+
+      // ---- cell update (acc[i][0..3] = W_hh h of gates i,f,g,o of cell (ul, b_i)) ----
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const int b = 24 * hc + 4 * i + g4;
+        float hn = 0.f;
+        if (t < len_c[i]) {
+          const float ig = fast_sigmoid(acc[i][0] + xg[i].x);
+          const float fg = fast_sigmoid(acc[i][1] + xg[i].y);
+          const float gg = fast_tanh(acc[i][2] + xg[i].z);
+          const float og = fast_sigmoid(acc[i][3] + xg[i].w);
+          cst[i] = fg * cst[i] + ig * gg;
+          hn = og * fast_tanh(cst[i]);
+          const size_t row = (size_t)(off_t + b_base + b);
+          if (p.save) {
+            *reinterpret_cast<float4*>(p.gates + row * H8 + gcol) = make_float4(ig, fg, gg, og);
+            p.c[row * H2 + ycol] = cst[i];
+          }
+          p.y[row * H2 + ycol] = hn;
+          const bool fin = dir == 0 ? (t == len_c[i] - 1) : (t == 0);
+          if (fin && p.utt) p.utt[(size_t)orig_c[i] * p.utt_ld + utt_off + u] = hn;
+        }
+        hs[b * HS_LD + ul] = hn;
+      }
+      TCL_TS(4)
+      if (s + 1 < L) {
+        fence_before();        // my TMEM reads are done before the next step's MMAs overwrite D
+        __syncthreads();
+        // ---- publish my 32 columns of h_t ----
+        float* xdst = xbuf + (size_t)(s & 1) * TCL_N * XLD + r * TCL_UNITS;
+        for (int id = tid; id < rows * 8; id += TCL_THREADS) {
+          const int n = id >> 3, c4 = (id & 7) * 4;
+          const float* hp = hs + n * HS_LD + c4;
+          __stcg(reinterpret_cast<float4*>(xdst + (size_t)n * XLD + c4), make_float4(hp[0], hp[1], hp[2], hp[3]));
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) red_release_add(flag, 1u);
+      }
+      TCL_TS(5)
+    }
+  }
+#undef TCL_TS
+  fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc512(tm);
+}
+
+// ------------------------------------------------------------------------------------------
+// backward through time
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TCL_THREADS, 1) lstm_tc_bwd_kernel(const TclArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sptr = smem_raw + (sbase - smem_u32(smem_raw));
+  const int H = p.H, S = p.S, MT = p.MT;
+  // W^T slice as the A operand: M = output column j (MT tiles of 128), K = my 128 gate rows (2
+  // atoms).  Term 1 lives in TMEM; terms 2 and 3 in shared memory.  The last M tile only stores
+  // its `rows_last` real rows (the MMA still reads 128 rows: whatever follows in shared memory
+  // lands in output rows nobody reads), so its blocks come first.
+  const int rows_last = ((H - 128 * (MT - 1)) + 7) & ~7;
+  const uint32_t PB = (uint32_t)rows_last * 128;
+  const uint32_t full_off = 4 * PB;                               // [split 2][atom 2] partial blocks
+  const uint32_t dG_off = full_off + (uint32_t)(2 * (MT - 1) * 2) * A_ATOM;
+  const uint32_t dG_split = 2 * B_ATOM;
+  const uint32_t misc_off = dG_off + 3 * dG_split;
+  auto wt_block = [&](int sp, int mt, int a) -> uint32_t {      // sp: 0 = term 2, 1 = term 3
+    return mt == MT - 1 ? (uint32_t)(sp * 2 + a) * PB
+                        : full_off + (uint32_t)((sp * (MT - 1) + mt) * 2 + a) * A_ATOM;
+  };
+  const uint32_t mma_bar = sbase + misc_off;
+  const uint32_t tmem_slot = sbase + misc_off + 8;
+  volatile int* abort_s = reinterpret_cast<volatile int*>(sptr + misc_off + 16);
+  int* lens_s = reinterpret_cast<int*>(sptr + misc_off + 64);
+  int* orig_s = lens_s + TCL_N;
+  int* cnt_s = orig_s + TCL_N;               // [Tmax]
+  int* offs_s = cnt_s + p.Tmax;              // [Tmax+1]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, hc = warp >> 2;
+  const int r = blockIdx.x % S;
+  const int grp = (blockIdx.x / S) % p.G;
+  const int dir = blockIdx.x / (S * p.G);
+  const int XLD = S * TCL_UNITS;
+
+  if (tid == 0) {
+    mbar_init(mma_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    *abort_s = 0;
+  }
+  if (warp == 0) tmem_alloc512(tmem_slot);
+  for (int i = tid; i <= p.Tmax; i += TCL_THREADS) offs_s[i] = p.offsets[i];
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tm = *reinterpret_cast<uint32_t*>(sptr + misc_off + 8);
+  const uint32_t tmD = tm + MT * 64;          // per M tile: main | cross, TCL_N columns each
+  const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+
+  {  // A[j][rho] = W_hh[(rho&3)*H + 32r + (rho>>2)][j]
+    const float* __restrict__ W = p.whh[dir];
+    for (int mt = 0; mt < MT; ++mt) {
+      const int jl = q * 32 + lane, j = mt * 128 + jl;
+      const bool j_ok = j < H;
+      const bool st_ok = mt < MT - 1 || jl < rows_last;
+      for (int ck = hc * 8; ck < hc * 8 + 8; ++ck) {
+        float x[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rho = ck * 8 + i, uu = r * TCL_UNITS + (rho >> 2);
+          x[i] = (j_ok && uu < H) ? __ldg(W + (size_t)((rho & 3) * H + uu) * H + j) : 0.f;
+        }
+        uint4 w1, w2, w3;
+        split3x8(x, w1, w2, w3);
+        tmem_st4(tm + lane_sel + mt * 64 + ck * 4, w1.x, w1.y, w1.z, w1.w);
+        if (st_ok) {
+          const uint32_t o = (uint32_t)((jl >> 3) * 1024 + (jl & 7) * 128 + (((ck & 7) ^ (jl & 7)) << 4));
+          *reinterpret_cast<uint4*>(sptr + wt_block(0, mt, ck >> 3) + o) = w2;
+          *reinterpret_cast<uint4*>(sptr + wt_block(1, mt, ck >> 3) + o) = w3;
+        }
+      }
+    }
+    tmem_wait_st();
+  }
+  fence_async_smem();
+  fence_before();
+  __syncthreads();
+
+  // cell role: lane = local unit, warp w owns batch rows w, w+8, ..., w+40
+  const int ul = lane, u = r * TCL_UNITS + ul;
+  const bool u_ok = u < H;
+  const int H2 = 2 * H, H8 = 8 * H;
+  const int gcol = dir * 4 * H + u * 4;
+  const int ycol = dir * H + u;
+  const int utt_off = dir == 0 ? p.utt_off0 : p.utt_off1;
+  uint32_t mma_phase = 0;
+  const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0 && tid == 0;
+#define TCL_TS(i) if (dbg_on && tile == grp) p.dbg[s * 8 + (i)] = clock64();
+
+  for (int tile = grp; tile < p.NT; tile += p.G) {
+    const int b_base = tile * p.BT;
+    const int rows = min(p.BT, p.B - b_base);
+    __syncthreads();
+    if (tid < TCL_N) {
+      lens_s[tid] = tid < rows ? p.lens[b_base + tid] : 0;
+      orig_s[tid] = tid < rows ? p.sorted_idx[b_base + tid] : 0;
+    }
+    __syncthreads();
+    const int L = lens_s[0];
+    for (int t = tid; t < L; t += TCL_THREADS) {
+      int n = 0;
+      for (int j = 0; j < rows; ++j) n += lens_s[j] > t;
+      cnt_s[t] = n;
+    }
+    __syncthreads();
+    unsigned* flag = p.flags + dir * p.NT + tile;
+    const size_t slab = (size_t)TCL_N * XLD;                     // one CTA's partial block
+    float* part = p.xch + (size_t)((dir * p.NT + tile) * 2) * S * slab;   // [par][S][48][XLD]
+    float dcst[6];
+    int len_c[6], orig_c[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      dcst[i] = 0.f;
+      const int b = warp + 8 * i;
+      len_c[i] = u_ok ? lens_s[b] : 0;
+      orig_c[i] = orig_s[b];
+    }
+    int n_prev = 0;     // rows whose d(gates) fed the MMAs in flight
+
+    for (int s = 0; s < L; ++s) {
+      const int t = dir == 0 ? L - 1 - s : s;
+      const int par = s & 1;
+      TCL_TS(0)
+      if (s > 0) {
+        // ---- partial dh^T[j][b] of the successor step: TMEM -> my block of the L2 scratch ----
+        mbar_wait(mma_bar, mma_phase);
+        mma_phase ^= 1;
+        fence_after();
+        float* dst = part + ((size_t)par * S + r) * slab;
+        for (int mt = 0; mt < MT; ++mt) {
+          const int j = mt * 128 + q * 32 + lane;
+#pragma unroll
+          for (int cb = 0; cb < 3; ++cb) {
+            const int col = 24 * hc + 8 * cb;
+            if (col < n_prev) {     // warp-uniform
+              uint32_t m[8], x[8];
+              tmem_ld8(tmD + lane_sel + mt * 2 * TCL_N + col, m);
+              tmem_ld8(tmD + lane_sel + mt * 2 * TCL_N + TCL_N + col, x);
+              tmem_wait_ld();
+              if (j < H) {
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj)
+                  if (col + jj < n_prev)
+                    __stcg(dst + (size_t)(col + jj) * XLD + j, __uint_as_float(m[jj]) + __uint_as_float(x[jj]));
+              }
+            }
+          }
+        }
+        __threadfence();
+        fence_before();
+        __syncthreads();
+        if (tid == 0) red_release_add(flag, 1u);
+      }
+      TCL_TS(1)
+      // ---- everything the cell backward needs that does not depend on the exchange ----
+      const int off_t = offs_s[t];
+      const int tp = dir == 0 ? t - 1 : t + 1;      // forward-order predecessor (its c is c_prev)
+      float4 gt[6];
+      float ct[6], cp[6], dh[6];
+      bool act[6], rec[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const int b = warp + 8 * i;
+        act[i] = t < len_c[i];
+        rec[i] = false;
+        ct[i] = 0.f; cp[i] = 0.f; dh[i] = 0.f;
+        gt[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (act[i]) {
+          const size_t row = (size_t)(off_t + b_base + b);
+          gt[i] = *reinterpret_cast<const float4*>(p.gates + row * H8 + gcol);
+          ct[i] = p.c[row * H2 + ycol];
+          const bool hp = dir == 0 ? (t >= 1) : (t + 1 < len_c[i]);
+          if (hp) cp[i] = p.c[(size_t)(offs_s[tp] + b_base + b) * H2 + ycol];
+          if (p.dy) dh[i] = p.dy[row * H2 + ycol];
+          const bool fin = dir == 0 ? (t == len_c[i] - 1) : (t == 0);
+          if (fin && p.dutt) dh[i] += p.dutt[(size_t)orig_c[i] * p.utt_ld + utt_off + u];
+          rec[i] = dir == 0 ? (t + 1 < len_c[i]) : (t >= 1);
+        }
+      }
+      if (s > 0) {
+        if (tid == 0 && !*abort_s) {
+          if (!spin_until(flag, (unsigned)(S * s), p.err)) *abort_s = 1;
+        }
+        __syncthreads();
+      }
+      TCL_TS(2)
+      // ---- reduce my columns over the S partial blocks ----
+      if (s > 0) {
+        const float* src = part + (size_t)par * S * slab + u;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          if (act[i] && rec[i]) {
+            const int b = warp + 8 * i;
+            float v[12];
+#pragma unroll
+            for (int rr = 0; rr < 12; ++rr)
+              v[rr] = rr < S ? __ldcg(src + (size_t)rr * slab + (size_t)b * XLD) : 0.f;
+            float sum = 0.f;
+#pragma unroll
+            for (int rr = 0; rr < 12; ++rr) sum += v[rr];
+            dh[i] += sum;
+          }
+        }
+      }
+      TCL_TS(3)
+      // ---- cell backward; d(gates) -> global (GEMM operand) and -> my B operand (3 bf16 terms) ----
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const int b = warp + 8 * i;
+        float dig = 0.f, dfg = 0.f, dgg = 0.f, dog = 0.f;
+        if (act[i]) {
+          const float ig = gt[i].x, fg = gt[i].y, gg = gt[i].z, og = gt[i].w;
+          const float tc = fast_tanh(ct[i]);
+          dog = dh[i] * tc * og * (1.f - og);
+          const float dc = dcst[i] + dh[i] * og * (1.f - tc * tc);
+          dig = dc * gg * ig * (1.f - ig);
+          dfg = dc * cp[i] * fg * (1.f - fg);
+          dgg = dc * ig * (1.f - gg * gg);
+          dcst[i] = dc * fg;
+          *reinterpret_cast<float4*>(p.gates + (size_t)(off_t + b_base + b) * H8 + gcol) =
+              make_float4(dig, dfg, dgg, dog);
+        }
+        uint32_t a[4], bb[4], cc[4];
+        split3(dig, a[0], bb[0], cc[0]);
+        split3(dfg, a[1], bb[1], cc[1]);
+        split3(dgg, a[2], bb[2], cc[2]);
+        split3(dog, a[3], bb[3], cc[3]);
+        // row b of the K-major operand, k = 4*ul .. 4*ul+3
+        const uint32_t o = dG_off + (uint32_t)(ul >> 4) * B_ATOM + (uint32_t)(b >> 3) * 1024 +
+                           (uint32_t)(b & 7) * 128 + (uint32_t)((((ul & 15) >> 1) ^ (b & 7)) << 4) +
+                           (uint32_t)(ul & 1) * 8;
+        *reinterpret_cast<uint2*>(sptr + o) = make_uint2(a[0] | (a[1] << 16), a[2] | (a[3] << 16));
+        *reinterpret_cast<uint2*>(sptr + o + dG_split) = make_uint2(bb[0] | (bb[1] << 16), bb[2] | (bb[3] << 16));
+        *reinterpret_cast<uint2*>(sptr + o + 2 * dG_split) = make_uint2(cc[0] | (cc[1] << 16), cc[2] | (cc[3] << 16));
+      }
+      TCL_TS(4)
+      if (s + 1 < L) {
+        fence_async_smem();
+        fence_before();
+        __syncthreads();
+        n_prev = cnt_s[t];
+        if (tid == 0) {
+          fence_after();
+          const int Nmma = (n_prev + 15) & ~15;
+          const uint32_t idesc = idesc_bf16(128, Nmma);
+          for (int mt = 0; mt < MT; ++mt) {
+            const uint32_t d_m = tmD + mt * 2 * TCL_N, d_x = d_m + TCL_N;
+            for (int ks = 0; ks < 8; ++ks) {
+              const int a = ks >> 2;
+              const uint32_t ko = (uint32_t)(ks & 3) * 32;
+              const uint32_t bo = sbase + dG_off + (uint32_t)a * B_ATOM + ko;
+              const uint64_t b1 = make_desc(bo, 16, 1024), b2 = make_desc(bo + dG_split, 16, 1024),
+                             b3 = make_desc(bo + 2 * dG_split, 16, 1024);
+              const uint32_t a1 = tm + mt * 64 + ks * 8;
+              const uint64_t a2 = make_desc(sbase + wt_block(0, mt, a) + ko, 16, 1024);
+              const uint64_t a3 = make_desc(sbase + wt_block(1, mt, a) + ko, 16, 1024);
+              mma_ts(d_x, a1, b3, idesc, ks > 0 ? 1u : 0u);
+              mma_ss(d_x, a3, b1, idesc, 1u);
+              mma_ss(d_x, a2, b2, idesc, 1u);
+              mma_ts(d_x, a1, b2, idesc, 1u);
+              mma_ss(d_x, a2, b1, idesc, 1u);
+              mma_ts(d_m, a1, b1, idesc, ks > 0 ? 1u : 0u);
+            }
+          }
+          commit(mma_bar);
+        }
+      }
+      TCL_TS(5)
+    }
+  }
+#undef TCL_TS
+  fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc512(tm);
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+struct TclPlan {
+  int S, G, BT, NT, Kp, MT;
+  size_t smem_fwd, smem_bwd, flag_off, xch_off, total;
+};
+
+int g_tcl_max_ctas = 120;   // leaves 28 SMs to the visual / acoustic encoders and the GEMMs running next to it
+
+int tcl_make_plan(int B, int H, int Tmax, TclPlan* pl) {
+  if (H <= 128 || H > 352 || B <= 0) return MMDA_ERR_UNSUPPORTED;
+  const int S = (H + TCL_UNITS - 1) / TCL_UNITS;
+  const int Kp = (H + 15) & ~15;
+  const int MT = (H + 127) / 128;
+  const int KA = (Kp + 63) / 64;
+  int Gmax = g_tcl_max_ctas / (2 * S);
+  if (Gmax < 1) Gmax = 1;
+  const int nt_min = (B + TCL_N - 1) / TCL_N;
+  int NT;
+  if (nt_min >= Gmax) NT = nt_min;
+  else {
+    NT = (B + 15) / 16;
+    if (NT > Gmax) NT = Gmax;
+    if (NT < nt_min) NT = nt_min;
+  }
+  const int BT = (B + NT - 1) / NT;
+  NT = (B + BT - 1) / BT;
+  pl->S = S; pl->Kp = Kp; pl->MT = MT; pl->NT = NT; pl->BT = BT;
+  pl->G = NT < Gmax ? NT : Gmax;
+  const size_t misc = MISC_FIXED + (size_t)(2 * Tmax + 2) * 4;
+  pl->smem_fwd = 1024 + (size_t)KA * A_ATOM + (size_t)3 * KA * B_ATOM + misc;
+  const int rows_last = ((H - 128 * (MT - 1)) + 7) & ~7;
+  pl->smem_bwd = 1024 + (size_t)4 * rows_last * 128 + (size_t)(2 * (MT - 1) * 2) * A_ATOM +
+                 (size_t)3 * 2 * B_ATOM + misc;
+  if (pl->smem_fwd > 232448 || pl->smem_bwd > 232448) return MMDA_ERR_UNSUPPORTED;
+  // workspace: [err (256 B)] [flags fwd+bwd 2*2*NT u32, padded] [exchange / partial scratch]
+  pl->flag_off = 256;
+  const size_t flag_bytes = ((size_t)2 * NT * 4 + 255) & ~(size_t)255;
+  pl->xch_off = pl->flag_off + flag_bytes;
+  const size_t XLD = (size_t)S * TCL_UNITS;
+  const size_t fwd_x = (size_t)2 * NT * 2 * TCL_N * XLD * 4;
+  const size_t bwd_x = (size_t)2 * NT * 2 * S * TCL_N * XLD * 4;
+  pl->total = pl->xch_off + (fwd_x > bwd_x ? fwd_x : bwd_x);
+  return MMDA_OK;
+}
+
+long long* g_tcl_dbg = nullptr;
+
+}  // namespace
+
+extern "C" {
+
+// bytes of the workspace mmda_lstm_tc_forward / _backward need for (B, H), or -1 when the
+// tensor-core recurrence does not cover this hidden size (the caller then uses mmda_lstm_forward)
+long long mmda_lstm_tc_workspace_bytes(int B, int H, int Tmax) {
+  TclPlan pl;
+  if (tcl_make_plan(B, H, Tmax, &pl) != MMDA_OK) return -1;
+  return (long long)pl.total;
+}
+
+// {slices S, groups G, batch tile BT, tiles NT, Kp, smem fwd, smem bwd, CTAs}
+int mmda_lstm_tc_plan(int B, int H, int Tmax, int* out8) {
+  TclPlan pl;
+  int rc = tcl_make_plan(B, H, Tmax, &pl);
+  if (rc != MMDA_OK) {
+    mmda_set_error("lstm_tc: hidden size %d not covered (128 < H <= 352)", H);
+    return rc;
+  }
+  out8[0] = pl.S; out8[1] = pl.G; out8[2] = pl.BT; out8[3] = pl.NT; out8[4] = pl.Kp;
+  out8[5] = (int)pl.smem_fwd; out8[6] = (int)pl.smem_bwd; out8[7] = 2 * pl.S * pl.G;
+  return MMDA_OK;
+}
+
+// upper bound on the CTAs (= SMs) one launch may occupy
+int mmda_lstm_tc_set_max_ctas(int n) {
+  MMDA_REQUIRE(n >= 2 && n <= 1024, "lstm_tc: max CTAs must be in [2, 1024]");
+  g_tcl_max_ctas = n;
+  return MMDA_OK;
+}
+
+int mmda_lstm_tc_set_debug_buffer(long long* dev_buf) {
+  g_tcl_dbg = dev_buf;
+  return MMDA_OK;
+}
+
+static int tcl_launch(bool bwd, TclArgs& a, int B, int H, int Tmax, void* ws, cudaStream_t stream) {
+  MMDA_REQUIRE(B > 0 && H > 0 && Tmax > 0, "lstm_tc: bad sizes B=%d H=%d Tmax=%d", B, H, Tmax);
+  MMDA_REQUIRE(ws != nullptr, "lstm_tc: workspace required (mmda_lstm_tc_workspace_bytes)");
+  TclPlan pl;
+  int rc = tcl_make_plan(B, H, Tmax, &pl);
+  if (rc != MMDA_OK) {
+    mmda_set_error("lstm_tc: hidden size %d not covered (128 < H <= 352)", H);
+    return rc;
+  }
+  uint8_t* w = static_cast<uint8_t*>(ws);
+  a.err = reinterpret_cast<int*>(w);
+  a.flags = reinterpret_cast<unsigned*>(w + pl.flag_off);
+  a.xch = reinterpret_cast<float*>(w + pl.xch_off);
+  a.B = B; a.H = H; a.Kp = pl.Kp; a.S = pl.S; a.G = pl.G; a.BT = pl.BT; a.NT = pl.NT; a.MT = pl.MT;
+  a.Tmax = Tmax;
+  a.dbg = g_tcl_dbg;
+  MMDA_CUDA(cudaMemsetAsync(a.flags, 0, (size_t)2 * pl.NT * 4, stream));
+  const size_t smem = bwd ? pl.smem_bwd : pl.smem_fwd;
+  auto kern = bwd ? lstm_tc_bwd_kernel : lstm_tc_fwd_kernel;
+  MMDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<2 * pl.S * pl.G, TCL_THREADS, smem, stream>>>(a);
+  MMDA_CHECK_LAUNCH();
+  return MMDA_OK;
+}
+
+// Same contract as mmda_lstm_forward (reference src/models.py:167,176) + the workspace.
+int mmda_lstm_tc_forward(float* gates, const float* whh_f, const float* whh_r, float* y, float* c,
+                         const int* lens_sorted, const int* sorted_idx, const int* offsets,
+                         float* utt, int utt_ld, int utt_off_f, int utt_off_r, int B, int H,
+                         int Tmax, int save_for_backward, void* ws, cudaStream_t stream) {
+  MMDA_REQUIRE(!save_for_backward || c != nullptr, "lstm_tc_forward: c buffer required when saving");
+  TclArgs a = {};
+  a.gates = gates; a.whh[0] = whh_f; a.whh[1] = whh_r; a.y = y; a.c = c;
+  a.lens = lens_sorted; a.sorted_idx = sorted_idx; a.offsets = offsets;
+  a.utt = utt; a.utt_ld = utt_ld; a.utt_off0 = utt_off_f; a.utt_off1 = utt_off_r;
+  a.save = save_for_backward;
+  return tcl_launch(false, a, B, H, Tmax, ws, stream);
+}
+
+// Same contract as mmda_lstm_backward (BPTT of the recurrence above) + the workspace.
+int mmda_lstm_tc_backward(float* gates, const float* whh_f, const float* whh_r, const float* c,
+                          const float* dy, const float* dutt, int utt_ld, int utt_off_f,
+                          int utt_off_r, const int* lens_sorted, const int* sorted_idx,
+                          const int* offsets, int B, int H, int Tmax, void* ws,
+                          cudaStream_t stream) {
+  MMDA_REQUIRE(c != nullptr, "lstm_tc_backward: saved cell states required");
+  TclArgs a = {};
+  a.gates = gates; a.whh[0] = whh_f; a.whh[1] = whh_r; a.c = const_cast<float*>(c);
+  a.dy = dy; a.dutt = dutt; a.utt_ld = utt_ld; a.utt_off0 = utt_off_f; a.utt_off1 = utt_off_r;
+  a.lens = lens_sorted; a.sorted_idx = sorted_idx; a.offsets = offsets;
+  return tcl_launch(true, a, B, H, Tmax, ws, stream);
+}
+
+}  // extern "C"
