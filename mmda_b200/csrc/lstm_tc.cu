@@ -6,23 +6,30 @@
 //
 // Why tensor cores.  The fp32 SIMT recurrence is bound by shared-memory operand delivery
 // (1 536 B of operands per 32 FFMA per warp).  tcgen05 reads its operands straight
-// from TMEM / shared memory.  fp32 accuracy is kept by splitting every operand into THREE bf16
-// terms (x = x1 + x2 + x3 exactly to fp32 rounding) and issuing the six products whose weight is
-// >= 2^-16:  W1h1 | W1h2 + W2h1 | W1h3 + W2h2 + W3h1  (the dropped terms are <= 2^-24 relative).
-// The tensor core accumulates in fp32 with truncation, so the dominant W1h1 chain alternates
-// over two TMEM accumulators and the small terms get their own; the three are added in
-// round-to-nearest fp32 by the cell-update threads.
+// from TMEM / shared memory.  fp32 accuracy is kept by operand splitting:
+//   forward:  x = x1 + 2^-11 x2 with x1, x2 fp16 (22 significant bits + the scale keeps x2 out of
+//             the fp16 subnormals); products W1h1 | W1h2 + W2h1, the second group accumulated at
+//             scale 2^11 in its own TMEM accumulator (the dropped W2h2 is 2^-24 relative);
+//   backward: d(gates) spans too many binades for fp16, so both operands are split into three
+//             bf16 terms and the six products of weight >= 2^-16 are issued.
+// The tensor core accumulates in fp32 with truncation, so the dominant term alternates over two
+// accumulators (forward) / stays a short K = 128 chain (backward) and the small terms get their
+// own accumulator; the cell-update threads add them in round-to-nearest fp32.
 //
-// Work split.  One CTA per SM, no clusters: CTA (direction, group, slice r) keeps the 4 gate
-// rows of hidden units [32r, 32r+32) -- 128 rows = one M=128 MMA -- resident for the whole
-// sequence: W1, W2 in TMEM (the A operand is read from TMEM), W3 in shared memory.  A group of
-// S = ceil(H/32) CTAs shares one batch tile of <= 48 length-sorted samples (the MMA N).  Every
-// step each CTA computes  gates^T[128 x N] = W_slice[128 x K] * h_{t-1}^T[K x N],  finishes the
-// cell update of its own units in registers (4x4 shuffle transposes bring the i,f,g,o values of
-// one cell into one thread) and publishes its 32 columns of h_t to an L2-resident exchange
-// buffer; a release/acquire counter per tile replaces the cluster barrier.  The backward kernel
-// keeps W^T (three M-tiles over the H output columns, K = its 128 gate rows), multiplies it with
-// its own d(gates) of the successor step, and exchanges the partial dh through an L2 scratch.
+// Work split.  One CTA per SM, no clusters: CTA (direction, group, slice r) owns the 4 gate rows
+// of hidden units [32r, 32r+32) -- 128 rows = one M=128 MMA -- for the whole sequence; its W_hh
+// slice lives in TMEM (the MMA's A operand is read from TMEM).  A group of S = ceil(H/32) CTAs
+// shares one batch tile of <= 48 length-sorted samples (the MMA N).  Every step each CTA computes
+//   gates^T[128 x N] = W_slice[128 x K] * h_{t-1}^T[K x N],
+// finishes the cell update of its own units in registers (4x4 shuffle transposes bring the
+// i,f,g,o values of one cell into one thread) and publishes its 32 columns of h_t -- already split
+// and already in the swizzled K-major operand layout -- into an L2-resident image that every CTA
+// of the group pulls into shared memory with one bulk copy (TMA engine).  A release/acquire
+// counter per tile replaces the cluster barrier.  Warp-specialised: 8 cell warps + 1 control warp
+// (flag wait, bulk copy, MMA issue); no CTA-wide barrier inside the time loop.
+// The backward kernel keeps W^T (three M tiles over the H output columns, K = its 128 gate rows:
+// term 1 in TMEM, terms 2 and 3 in shared memory), multiplies it with its own d(gates) of the
+// successor step and reduce-scatters the partial dh through an L2 scratch.
 #include "common.cuh"
 #include "tcgen05.cuh"
 
@@ -30,13 +37,15 @@ namespace {
 
 using namespace tc5;
 
-constexpr int TCL_THREADS = 256;
+constexpr int TCL_CELL_WARPS = 8;
+constexpr int TCL_FWD_THREADS = 32 * (TCL_CELL_WARPS + 1);   // + the control warp
+constexpr int TCL_BWD_THREADS = 32 * TCL_CELL_WARPS;
 constexpr int TCL_N = 48;                     // batch rows per tile = widest MMA N used
 constexpr int TCL_UNITS = 32;                 // hidden units per CTA (x4 gates = 128 MMA rows)
-constexpr int A_ATOM = 128 * 128;             // bytes: 128 rows x 64 bf16 (one 128B-swizzle K atom)
-constexpr int B_ATOM = TCL_N * 128;           // bytes: 48 rows x 64 bf16
-constexpr int HS_LD = 33;                     // h_t staging pitch (floats)
-constexpr int MISC_FIXED = 64 + TCL_N * HS_LD * 4 + 2 * TCL_N * 4;   // barriers, staging, lens, orig
+constexpr int A_ATOM = 128 * 128;             // bytes: 128 rows x 64 16-bit elements (one 128B-swizzle K atom)
+constexpr int B_ATOM = TCL_N * 128;           // bytes: 48 rows x 64 elements
+constexpr int MAX_KA = 6;
+constexpr int MISC_FIXED = 128 + 2 * TCL_N * 4;   // barriers + tmem slot, lens, orig
 constexpr long long SPIN_LIMIT = 1LL << 31;   // clock64 ticks (~1 s): a lost peer ends the launch, not the box
 
 struct TclArgs {
@@ -52,13 +61,13 @@ struct TclArgs {
   const float* dy;        // bwd: grad wrt y [N][2H] (nullable)
   int utt_ld, utt_off0, utt_off1;
   int B, H, Kp, S, G, BT, NT, MT, save, Tmax;
-  float* xch;             // fwd: h exchange [2][NT][2][48][S*32]; bwd: partials [2][2][NT][S][48][S*32]
-  unsigned* flags;        // [2][NT] step counters (zeroed before the launch)
+  uint8_t* xch;           // fwd: h operand images [2][NT][2][2*KA*B_ATOM]; bwd: partials [2][NT][2][S][48][S*32] f32
+  unsigned* flags;        // [2][NT] counters (zeroed before the launch): one tick per cell warp and step
   int* err;               // set to 1 when a peer never showed up
   long long* dbg;
 };
 
-// wait until *flag >= target (thread 0 only); returns false after SPIN_LIMIT ticks or when another
+// wait until *flag >= target (one thread); returns false after SPIN_LIMIT ticks or when another
 // CTA already gave up
 __device__ __forceinline__ bool spin_until(const unsigned* flag, unsigned target, int* err) {
   if (ld_acquire(flag) >= target) return true;
@@ -75,8 +84,8 @@ __device__ __forceinline__ bool spin_until(const unsigned* flag, unsigned target
   return true;
 }
 
-// byte offset of the 16-byte chunk (row n, k-chunk ck of 8 bf16) inside a K-major 128B-swizzled
-// operand whose 64-element K atoms are `atom_bytes` apart
+// byte offset of the 16-byte chunk (row n, k-chunk ck of 8 elements) inside a K-major
+// 128B-swizzled operand whose 64-element K atoms are `atom_bytes` apart
 __device__ __forceinline__ uint32_t swz_chunk(int n, int ck, int atom_bytes) {
   return (uint32_t)((ck >> 3) * atom_bytes + (n >> 3) * 1024 + (n & 7) * 128 + (((ck & 7) ^ (n & 7)) << 4));
 }
@@ -100,50 +109,56 @@ __device__ __forceinline__ void transpose4(float (&a)[4], int g) {
   a[3] = o2 ? hi_o : u1;
 }
 
+// a cell warp publishes "my global writes of this step are done": one tick on the tile counter
+__device__ __forceinline__ void warp_publish(unsigned* flag, int lane) {
+  fence_before();            // my TMEM reads retire before a peer-triggered MMA overwrites D
+  fence_proxy_async_all();   // my generic-proxy global writes vs the peers' bulk copies
+  __threadfence();
+  __syncwarp();
+  if (lane == 0) red_release_add(flag, 1u);
+}
+
 // ------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TCL_THREADS, 1) lstm_tc_fwd_kernel(const TclArgs p) {
+__global__ void __launch_bounds__(TCL_FWD_THREADS, 1) lstm_tc_fwd_kernel(const TclArgs p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sptr = smem_raw + (sbase - smem_u32(smem_raw));
   const int H = p.H, Kp = p.Kp, S = p.S;
   const int KA = (Kp + 63) >> 6;              // K atoms
   const int KC = Kp >> 3;                     // 16-byte chunks per operand row
-  const uint32_t W3_off = 0;
-  const uint32_t hB_off = (uint32_t)KA * A_ATOM;
-  const uint32_t hB_split = (uint32_t)KA * B_ATOM;
-  const uint32_t misc_off = hB_off + 3 * hB_split;
+  const uint32_t SPL = (uint32_t)KA * B_ATOM; // one split term of the h operand
+  const uint32_t IMG = 2 * SPL;               // h1 | h2 image
+  const uint32_t misc_off = IMG;
   const uint32_t mma_bar = sbase + misc_off;
-  const uint32_t tmem_slot = sbase + misc_off + 8;
-  volatile int* abort_s = reinterpret_cast<volatile int*>(sptr + misc_off + 16);
-  float* hs = reinterpret_cast<float*>(sptr + misc_off + 64);     // [48][HS_LD]
-  int* lens_s = reinterpret_cast<int*>(hs + TCL_N * HS_LD);
+  auto copy_bar = [&](int a) { return sbase + misc_off + 8u + 8u * (uint32_t)a; };
+  const uint32_t tmem_slot = sbase + misc_off + 8 + 8 * MAX_KA;
+  int* lens_s = reinterpret_cast<int*>(sptr + misc_off + 128);
   int* orig_s = lens_s + TCL_N;
   int* cnt_s = orig_s + TCL_N;                                    // [Tmax] rows alive at time t
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q = warp & 3, hc = warp >> 2;
+  const int q = warp & 3, hc = (warp >> 2) & 1;
   const int r = blockIdx.x % S;
   const int grp = (blockIdx.x / S) % p.G;
   const int dir = blockIdx.x / (S * p.G);
-  const int XLD = S * TCL_UNITS;              // exchange row pitch (floats)
 
   if (tid == 0) {
-    mbar_init(mma_bar, 1);
+    mbar_init(mma_bar, 4);                    // four issuing warps commit
+    for (int a = 0; a < KA; ++a) mbar_init(copy_bar(a), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    *abort_s = 0;
   }
   if (warp == 0) tmem_alloc512(tmem_slot);
   fence_before();
   __syncthreads();
   fence_after();
-  const uint32_t tm = *reinterpret_cast<uint32_t*>(sptr + misc_off + 8);
+  const uint32_t tm = *reinterpret_cast<uint32_t*>(sptr + misc_off + 8 + 8 * MAX_KA);
   const uint32_t tmW1 = tm, tmW2 = tm + (Kp >> 1);
-  const uint32_t tmD = tm + 2 * (Kp >> 1);    // main0 | main1 | cross, TCL_N columns each
+  const uint32_t tmD = tm + 2 * (Kp >> 1);    // main0 | main1 | cross a | cross b (x 2^11), TCL_N columns each
   const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
 
-  {  // resident weights: row rho = 4*ul + g of the slice = W_hh[g*H + 32r + ul][:]
+  if (warp < TCL_CELL_WARPS) {  // resident weights: row rho = 4*ul + g of the slice = W_hh[g*H + 32r + ul][:]
     const int rho = q * 32 + lane, ul = rho >> 2, g = rho & 3, u = r * TCL_UNITS + ul;
     const float* __restrict__ src = p.whh[dir] + (size_t)(g * H + min(u, H - 1)) * H;
     const bool row_ok = u < H;
@@ -160,15 +175,13 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) lstm_tc_fwd_kernel(const TclAr
 #pragma unroll
         for (int i = 0; i < 8; ++i) x[i] = (row_ok && k0 + i < H) ? src[k0 + i] : 0.f;
       }
-      uint4 w1, w2, w3;
-      split3x8(x, w1, w2, w3);
+      uint4 w1, w2;
+      split2hx8(x, w1, w2);
       tmem_st4(tmW1 + lane_sel + ck * 4, w1.x, w1.y, w1.z, w1.w);
       tmem_st4(tmW2 + lane_sel + ck * 4, w2.x, w2.y, w2.z, w2.w);
-      *reinterpret_cast<uint4*>(sptr + W3_off + swz_chunk(rho, ck, A_ATOM)) = w3;
     }
     tmem_wait_st();
   }
-  fence_async_smem();
   fence_before();
   __syncthreads();
 
@@ -181,42 +194,73 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) lstm_tc_fwd_kernel(const TclAr
   const int gcol = dir * 4 * H + u * 4;
   const int ycol = dir * H + u;
   const int utt_off = dir == 0 ? p.utt_off0 : p.utt_off1;
-  uint32_t mma_phase = 0;
-  const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0 && tid == 0;
-#define TCL_TS(i) if (dbg_on && tile == grp) p.dbg[s * 8 + (i)] = clock64();
+  const int KS = Kp >> 4;
+  uint32_t n_mma = 0;        // MMA batches issued / consumed so far (every thread keeps its own count)
+  const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0;
+#define TCL_TS(i) if (dbg_on && tile == grp) p.dbg[s * 16 + (i)] = clock64();
 
   for (int tile = grp; tile < p.NT; tile += p.G) {
     const int b_base = tile * p.BT;
     const int rows = min(p.BT, p.B - b_base);
-    __syncthreads();   // previous tile fully done with lens_s / cnt_s / hs
+    __syncthreads();   // previous tile fully done with lens_s / cnt_s
     if (tid < TCL_N) {
       lens_s[tid] = tid < rows ? p.lens[b_base + tid] : 0;
       orig_s[tid] = tid < rows ? p.sorted_idx[b_base + tid] : 0;
     }
     __syncthreads();
     const int L = lens_s[0];
-    for (int t = tid; t < L; t += TCL_THREADS) {
+    for (int t = tid; t < L; t += TCL_FWD_THREADS) {
       int n = 0;
       for (int j = 0; j < rows; ++j) n += lens_s[j] > t;
       cnt_s[t] = n;
     }
     __syncthreads();
     unsigned* flag = p.flags + dir * p.NT + tile;
-    float* xbuf = p.xch + (size_t)(dir * p.NT + tile) * 2 * TCL_N * XLD;
+    uint8_t* img = p.xch + (size_t)(dir * p.NT + tile) * 2 * IMG;     // [parity][IMG]
+
+    if (warp == TCL_CELL_WARPS) {
+      // ===================== control: flag wait, bulk copies of h_{t-1} (one barrier per K atom) ====
+      if (lane == 0) {
+        bool aborted = false;
+        for (int s = 1; s < L; ++s) {
+          const int t = dir == 0 ? s : L - 1 - s;
+          const uint32_t rb = (uint32_t)cnt_s[t] * 128;        // live rows of every atom block
+          if (!aborted && !spin_until(flag, (unsigned)(S * TCL_CELL_WARPS * s), p.err)) aborted = true;
+          TCL_TS(1)
+          if (n_mma > 0) mbar_wait(mma_bar, (n_mma - 1) & 1);   // previous MMAs are done reading the image
+          fence_proxy_async_all();
+          const uint8_t* src = img + (size_t)((s - 1) & 1) * IMG;
+          for (int a = 0; a < KA; ++a) {
+            mbar_expect_tx(copy_bar(a), 2 * rb);
+            const uint32_t o = (uint32_t)a * B_ATOM;
+            bulk_g2s(sbase + o, src + o, rb, copy_bar(a));
+            bulk_g2s(sbase + SPL + o, src + SPL + o, rb, copy_bar(a));
+          }
+          ++n_mma;
+          TCL_TS(2)
+        }
+      }
+      __syncwarp();
+      n_mma = __shfl_sync(0xffffffffu, n_mma, 0);
+      continue;
+    }
+
+    // ===================== cell warps (warps 0..3 also issue the MMAs) =====================
     float cst[6];
     int len_c[6], orig_c[6];
+    uint32_t img_off[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
       cst[i] = 0.f;
       const int b = 24 * hc + 4 * i + g4;
       len_c[i] = u_ok ? lens_s[b] : 0;
       orig_c[i] = orig_s[b];
+      img_off[i] = swz_chunk(b, u >> 3, B_ATOM) + (uint32_t)(u & 7) * 2;
     }
 
     for (int s = 0; s < L; ++s) {
       const int t = dir == 0 ? s : L - 1 - s;
-      const int tprev = dir == 0 ? t - 1 : t + 1;
-      TCL_TS(0)
+      if (tid == 0) { TCL_TS(0) }
       const int off_t = __ldg(p.offsets + t);
       // x-projection of my cells (independent of h: in flight during the exchange + MMAs)
       float4 xg[6];
@@ -234,122 +278,105 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) lstm_tc_fwd_kernel(const TclAr
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
       if (s > 0) {
-        const int n_act = cnt_s[t];
-        const int Nmma = (n_act + 15) & ~15;
-        if (tid == 0 && !*abort_s) {
-          if (!spin_until(flag, (unsigned)(S * s), p.err)) *abort_s = 1;
-        }
-        __syncthreads();
-        TCL_TS(1)
-        // ---- h_{t-1} tile: fp32 from L2 -> three bf16 terms -> swizzled K-major B operand ----
-        const float* xsrc = xbuf + (size_t)((s - 1) & 1) * TCL_N * XLD;
-        const int items = Nmma * KC;
-        for (int id = tid; id < items; id += TCL_THREADS) {
-          const int n = id / KC, ck = id - n * KC;
-          float x[8];
-          if (tprev < lens_s[n]) {      // row n had a predecessor step (else h_{t-1} = h0 = 0)
-            const float4 a = __ldcg(reinterpret_cast<const float4*>(xsrc + (size_t)n * XLD + ck * 8));
-            const float4 b = __ldcg(reinterpret_cast<const float4*>(xsrc + (size_t)n * XLD + ck * 8 + 4));
-            x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) x[i] = 0.f;
-          }
-          uint4 h1, h2, h3;
-          split3x8(x, h1, h2, h3);
-          const uint32_t o = hB_off + swz_chunk(n, ck, B_ATOM);
-          *reinterpret_cast<uint4*>(sptr + o) = h1;
-          *reinterpret_cast<uint4*>(sptr + o + hB_split) = h2;
-          *reinterpret_cast<uint4*>(sptr + o + 2 * hB_split) = h3;
-        }
-        fence_async_smem();
-        fence_before();
-        __syncthreads();
-        TCL_TS(2)
-        if (tid == 0) {
+        if (warp < 4) {
+          // ---- issue my accumulator's MMAs, K atom by K atom as the bulk copies land ----
+          // warp 0: W1h1 even k-steps -> main0; warp 1: odd -> main1; warp 2: W1h2 -> cross a;
+          // warp 3: W2h1 -> cross b.  One accumulator per issuing warp keeps the summation
+          // order (hence the bits) deterministic.
+          const int Nmma = (cnt_s[t] + 15) & ~15;
+          const uint32_t idesc = idesc_f16(128, Nmma);
+          const uint32_t d_acc = tmD + warp * TCL_N;
+          const uint32_t a_base = warp == 3 ? tmW2 : tmW1;
+          const uint64_t b_0 = make_desc(sbase + (warp == 2 ? SPL : 0u), 16, 1024);
           fence_after();
-          const uint32_t idesc = idesc_bf16(128, Nmma);
-          const uint32_t d_m0 = tmD, d_m1 = tmD + TCL_N, d_x = tmD + 2 * TCL_N;
-          const int KS = Kp >> 4;
-          for (int ks = 0; ks < KS; ++ks) {
-            const uint32_t bo = sbase + hB_off + (uint32_t)(ks >> 2) * B_ATOM + (uint32_t)(ks & 3) * 32;
-            const uint64_t b1 = make_desc(bo, 16, 1024), b2 = make_desc(bo + hB_split, 16, 1024),
-                           b3 = make_desc(bo + 2 * hB_split, 16, 1024);
-            const uint64_t a3 = make_desc(sbase + W3_off + (uint32_t)(ks >> 2) * A_ATOM + (uint32_t)(ks & 3) * 32, 16, 1024);
-            const uint32_t a1 = tmW1 + ks * 8, a2 = tmW2 + ks * 8;
-            mma_ts(d_x, a1, b3, idesc, ks > 0 ? 1u : 0u);   // 2^-16 terms first
-            mma_ss(d_x, a3, b1, idesc, 1u);
-            mma_ts(d_x, a2, b2, idesc, 1u);
-            mma_ts(d_x, a1, b2, idesc, 1u);                 // 2^-8 terms
-            mma_ts(d_x, a2, b1, idesc, 1u);
-            mma_ts((ks & 1) ? d_m1 : d_m0, a1, b1, idesc, ks >= 2 ? 1u : 0u);
+          for (int a = 0; a < KA; ++a) {
+            mbar_wait(copy_bar(a), n_mma & 1);
+            fence_after();
+            const uint64_t ba = b_0 + (uint64_t)((a * B_ATOM) >> 4);
+            if (elect_one()) {
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                const int ks = a * 4 + kk;
+                if (ks < KS) {
+                  if (warp >= 2) mma_ts(d_acc, a_base + ks * 8, ba + 2 * kk, idesc, ks > 0 ? 1u : 0u);
+                  else if ((ks & 1) == warp) mma_ts(d_acc, a_base + ks * 8, ba + 2 * kk, idesc, ks >= 2 ? 1u : 0u);
+                }
+              }
+            }
+            __syncwarp();
           }
-          commit(mma_bar);
+          if (elect_one()) commit(mma_bar);
+          __syncwarp();
         }
-        mbar_wait(mma_bar, mma_phase);
-        mma_phase ^= 1;
+        if (tid == 0) { TCL_TS(3) }
+        mbar_wait(mma_bar, n_mma & 1);
+        ++n_mma;
         fence_after();
-        TCL_TS(3)
+        if (tid == 0) { TCL_TS(4) }
         // ---- D -> registers: my row (gate g4 of unit ul), 24 batch columns ----
-        const int KSn = Kp >> 4;
 #pragma unroll
         for (int cb = 0; cb < 3; ++cb) {
-          uint32_t m0[8], m1[8], xx[8];
+          uint32_t m0[8], m1[8], xa[8], xb[8];
           const uint32_t col = (uint32_t)(24 * hc + 8 * cb);
           tmem_ld8(tmD + lane_sel + col, m0);
-          tmem_ld8(tmD + lane_sel + 2 * TCL_N + col, xx);
-          if (KSn > 1) tmem_ld8(tmD + lane_sel + TCL_N + col, m1);
+          tmem_ld8(tmD + lane_sel + 2 * TCL_N + col, xa);
+          tmem_ld8(tmD + lane_sel + 3 * TCL_N + col, xb);
+          if (KS > 1) tmem_ld8(tmD + lane_sel + TCL_N + col, m1);
           tmem_wait_ld();
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float v = __uint_as_float(m0[j]);
-            if (KSn > 1) v += __uint_as_float(m1[j]);
-            acc[cb * 2 + (j >> 2)][j & 3] = v + __uint_as_float(xx[j]);
+            if (KS > 1) v += __uint_as_float(m1[j]);
+            acc[cb * 2 + (j >> 2)][j & 3] =
+                fmaf(__uint_as_float(xa[j]) + __uint_as_float(xb[j]), 1.f / 2048.f, v);
           }
         }
 #pragma unroll
         for (int i = 0; i < 6; ++i) transpose4(acc[i], g4);
+        if (tid == 0) { TCL_TS(8) }
       }
 
       // ---- cell update (acc[i][0..3] = W_hh h of gates i,f,g,o of cell (ul, b_i)) ----
+      float4 ga[6];
+      float hn[6];
+      uint8_t* dst = img + (size_t)(s & 1) * IMG;
 #pragma unroll
       for (int i = 0; i < 6; ++i) {
-        const int b = 24 * hc + 4 * i + g4;
-        float hn = 0.f;
+        hn[i] = 0.f;
         if (t < len_c[i]) {
-          const float ig = fast_sigmoid(acc[i][0] + xg[i].x);
-          const float fg = fast_sigmoid(acc[i][1] + xg[i].y);
-          const float gg = fast_tanh(acc[i][2] + xg[i].z);
-          const float og = fast_sigmoid(acc[i][3] + xg[i].w);
-          cst[i] = fg * cst[i] + ig * gg;
-          hn = og * fast_tanh(cst[i]);
+          ga[i].x = fast_sigmoid(acc[i][0] + xg[i].x);
+          ga[i].y = fast_sigmoid(acc[i][1] + xg[i].y);
+          ga[i].z = fast_tanh(acc[i][2] + xg[i].z);
+          ga[i].w = fast_sigmoid(acc[i][3] + xg[i].w);
+          cst[i] = ga[i].y * cst[i] + ga[i].x * ga[i].z;
+          hn[i] = ga[i].w * fast_tanh(cst[i]);
+        }
+        if (s + 1 < L) {      // my element of the next step's B operand (zeros keep h0 = 0 rows clean)
+          uint32_t h1, h2;
+          split2h(hn[i], h1, h2);
+          *reinterpret_cast<unsigned short*>(dst + img_off[i]) = (unsigned short)h1;
+          *reinterpret_cast<unsigned short*>(dst + SPL + img_off[i]) = (unsigned short)h2;
+        }
+      }
+      if (tid == 0) { TCL_TS(9) }
+      if (s + 1 < L) warp_publish(flag, lane);
+      if (tid == 0) { TCL_TS(5) }
+      // ---- outputs nobody waits for inside this launch ----
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        if (t < len_c[i]) {
+          const int b = 24 * hc + 4 * i + g4;
           const size_t row = (size_t)(off_t + b_base + b);
           if (p.save) {
-            *reinterpret_cast<float4*>(p.gates + row * H8 + gcol) = make_float4(ig, fg, gg, og);
+            *reinterpret_cast<float4*>(p.gates + row * H8 + gcol) = ga[i];
             p.c[row * H2 + ycol] = cst[i];
           }
-          p.y[row * H2 + ycol] = hn;
+          p.y[row * H2 + ycol] = hn[i];
           const bool fin = dir == 0 ? (t == len_c[i] - 1) : (t == 0);
-          if (fin && p.utt) p.utt[(size_t)orig_c[i] * p.utt_ld + utt_off + u] = hn;
+          if (fin && p.utt) p.utt[(size_t)orig_c[i] * p.utt_ld + utt_off + u] = hn[i];
         }
-        hs[b * HS_LD + ul] = hn;
       }
-      TCL_TS(4)
-      if (s + 1 < L) {
-        fence_before();        // my TMEM reads are done before the next step's MMAs overwrite D
-        __syncthreads();
-        // ---- publish my 32 columns of h_t ----
-        float* xdst = xbuf + (size_t)(s & 1) * TCL_N * XLD + r * TCL_UNITS;
-        for (int id = tid; id < rows * 8; id += TCL_THREADS) {
-          const int n = id >> 3, c4 = (id & 7) * 4;
-          const float* hp = hs + n * HS_LD + c4;
-          __stcg(reinterpret_cast<float4*>(xdst + (size_t)n * XLD + c4), make_float4(hp[0], hp[1], hp[2], hp[3]));
-        }
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) red_release_add(flag, 1u);
-      }
-      TCL_TS(5)
+      if (tid == 0) { TCL_TS(6) }
     }
   }
 #undef TCL_TS
@@ -361,7 +388,7 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) lstm_tc_fwd_kernel(const TclAr
 // ------------------------------------------------------------------------------------------
 // backward through time
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TCL_THREADS, 1) lstm_tc_bwd_kernel(const TclArgs p) {
+__global__ void __launch_bounds__(TCL_BWD_THREADS, 1) lstm_tc_bwd_kernel(const TclArgs p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sptr = smem_raw + (sbase - smem_u32(smem_raw));
@@ -380,32 +407,32 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) lstm_tc_bwd_kernel(const TclAr
     return mt == MT - 1 ? (uint32_t)(sp * 2 + a) * PB
                         : full_off + (uint32_t)((sp * (MT - 1) + mt) * 2 + a) * A_ATOM;
   };
-  const uint32_t mma_bar = sbase + misc_off;
-  const uint32_t tmem_slot = sbase + misc_off + 8;
-  volatile int* abort_s = reinterpret_cast<volatile int*>(sptr + misc_off + 16);
-  int* lens_s = reinterpret_cast<int*>(sptr + misc_off + 64);
+  const uint32_t mma_bar = sbase + misc_off, dg_bar = sbase + misc_off + 8;
+  const uint32_t tmem_slot = sbase + misc_off + 16;
+  int* lens_s = reinterpret_cast<int*>(sptr + misc_off + 128);
   int* orig_s = lens_s + TCL_N;
   int* cnt_s = orig_s + TCL_N;               // [Tmax]
   int* offs_s = cnt_s + p.Tmax;              // [Tmax+1]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q = warp & 3, hc = warp >> 2;
+  const int q = warp & 3, hc = (warp >> 2) & 1;
   const int r = blockIdx.x % S;
   const int grp = (blockIdx.x / S) % p.G;
   const int dir = blockIdx.x / (S * p.G);
   const int XLD = S * TCL_UNITS;
+  const int n_issuers = 2 * MT;              // warp w < 2*MT issues (tile w/2, main | cross)
 
   if (tid == 0) {
-    mbar_init(mma_bar, 1);
+    mbar_init(mma_bar, n_issuers);
+    mbar_init(dg_bar, TCL_CELL_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    *abort_s = 0;
   }
   if (warp == 0) tmem_alloc512(tmem_slot);
-  for (int i = tid; i <= p.Tmax; i += TCL_THREADS) offs_s[i] = p.offsets[i];
+  for (int i = tid; i <= p.Tmax; i += TCL_BWD_THREADS) offs_s[i] = p.offsets[i];
   fence_before();
   __syncthreads();
   fence_after();
-  const uint32_t tm = *reinterpret_cast<uint32_t*>(sptr + misc_off + 8);
+  const uint32_t tm = *reinterpret_cast<uint32_t*>(sptr + misc_off + 16);
   const uint32_t tmD = tm + MT * 64;          // per M tile: main | cross, TCL_N columns each
   const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
 
@@ -445,9 +472,10 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) lstm_tc_bwd_kernel(const TclAr
   const int gcol = dir * 4 * H + u * 4;
   const int ycol = dir * H + u;
   const int utt_off = dir == 0 ? p.utt_off0 : p.utt_off1;
-  uint32_t mma_phase = 0;
+  uint32_t n_mma = 0, n_dg = 0;
+  bool aborted = false;
   const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0 && tid == 0;
-#define TCL_TS(i) if (dbg_on && tile == grp) p.dbg[s * 8 + (i)] = clock64();
+#define TCL_TS(i) if (dbg_on && tile == grp) p.dbg[s * 16 + (i)] = clock64();
 
   for (int tile = grp; tile < p.NT; tile += p.G) {
     const int b_base = tile * p.BT;
@@ -459,7 +487,7 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) lstm_tc_bwd_kernel(const TclAr
     }
     __syncthreads();
     const int L = lens_s[0];
-    for (int t = tid; t < L; t += TCL_THREADS) {
+    for (int t = tid; t < L; t += TCL_BWD_THREADS) {
       int n = 0;
       for (int j = 0; j < rows; ++j) n += lens_s[j] > t;
       cnt_s[t] = n;
@@ -467,7 +495,8 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) lstm_tc_bwd_kernel(const TclAr
     __syncthreads();
     unsigned* flag = p.flags + dir * p.NT + tile;
     const size_t slab = (size_t)TCL_N * XLD;                     // one CTA's partial block
-    float* part = p.xch + (size_t)((dir * p.NT + tile) * 2) * S * slab;   // [par][S][48][XLD]
+    float* part = reinterpret_cast<float*>(p.xch) + (size_t)((dir * p.NT + tile) * 2) * S * slab;   // [par][S][48][XLD]
+
     float dcst[6];
     int len_c[6], orig_c[6];
 #pragma unroll
@@ -477,7 +506,6 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) lstm_tc_bwd_kernel(const TclAr
       len_c[i] = u_ok ? lens_s[b] : 0;
       orig_c[i] = orig_s[b];
     }
-    int n_prev = 0;     // rows whose d(gates) fed the MMAs in flight
 
     for (int s = 0; s < L; ++s) {
       const int t = dir == 0 ? L - 1 - s : s;
@@ -485,9 +513,11 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) lstm_tc_bwd_kernel(const TclAr
       TCL_TS(0)
       if (s > 0) {
         // ---- partial dh^T[j][b] of the successor step: TMEM -> my block of the L2 scratch ----
-        mbar_wait(mma_bar, mma_phase);
-        mma_phase ^= 1;
+        const int n_prev = cnt_s[dir == 0 ? t + 1 : t - 1];     // rows whose d(gates) fed these MMAs
+        mbar_wait(mma_bar, n_mma & 1);
+        ++n_mma;
         fence_after();
+        TCL_TS(1)
         float* dst = part + ((size_t)par * S + r) * slab;
         for (int mt = 0; mt < MT; ++mt) {
           const int j = mt * 128 + q * 32 + lane;
@@ -508,12 +538,10 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) lstm_tc_bwd_kernel(const TclAr
             }
           }
         }
-        __threadfence();
-        fence_before();
-        __syncthreads();
-        if (tid == 0) red_release_add(flag, 1u);
+        TCL_TS(8)
+        warp_publish(flag, lane);
       }
-      TCL_TS(1)
+      TCL_TS(2)
       // ---- everything the cell backward needs that does not depend on the exchange ----
       const int off_t = offs_s[t];
       const int tp = dir == 0 ? t - 1 : t + 1;      // forward-order predecessor (its c is c_prev)
@@ -540,32 +568,31 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) lstm_tc_bwd_kernel(const TclAr
         }
       }
       if (s > 0) {
-        if (tid == 0 && !*abort_s) {
-          if (!spin_until(flag, (unsigned)(S * s), p.err)) *abort_s = 1;
-        }
-        __syncthreads();
-      }
-      TCL_TS(2)
-      // ---- reduce my columns over the S partial blocks ----
-      if (s > 0) {
+        // every cell warp of every CTA of the group has published its partials of this step
+        if (lane == 0 && !aborted && !spin_until(flag, (unsigned)(S * TCL_CELL_WARPS * s), p.err)) aborted = true;
+        __syncwarp();
+        TCL_TS(3)
+        // ---- reduce my columns over the S partial blocks (every load in flight at once) ----
         const float* src = part + (size_t)par * S * slab + u;
+        float v[6][12];
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
-          if (act[i] && rec[i]) {
-            const int b = warp + 8 * i;
-            float v[12];
+          const int b = warp + 8 * i;
 #pragma unroll
-            for (int rr = 0; rr < 12; ++rr)
-              v[rr] = rr < S ? __ldcg(src + (size_t)rr * slab + (size_t)b * XLD) : 0.f;
-            float sum = 0.f;
+          for (int rr = 0; rr < 12; ++rr)
+            v[i][rr] = (act[i] && rec[i] && rr < S) ? __ldcg(src + (size_t)rr * slab + (size_t)b * XLD) : 0.f;
+        }
 #pragma unroll
-            for (int rr = 0; rr < 12; ++rr) sum += v[rr];
-            dh[i] += sum;
-          }
+        for (int i = 0; i < 6; ++i) {
+          float sum = 0.f;
+#pragma unroll
+          for (int rr = 0; rr < 12; ++rr) sum += v[i][rr];
+          dh[i] += sum;
         }
       }
-      TCL_TS(3)
+      TCL_TS(4)
       // ---- cell backward; d(gates) -> global (GEMM operand) and -> my B operand (3 bf16 terms) ----
+      float4 dgv[6];
 #pragma unroll
       for (int i = 0; i < 6; ++i) {
         const int b = warp + 8 * i;
@@ -579,55 +606,72 @@ __global__ void __launch_bounds__(TCL_THREADS, 1) lstm_tc_bwd_kernel(const TclAr
           dfg = dc * cp[i] * fg * (1.f - fg);
           dgg = dc * ig * (1.f - gg * gg);
           dcst[i] = dc * fg;
-          *reinterpret_cast<float4*>(p.gates + (size_t)(off_t + b_base + b) * H8 + gcol) =
-              make_float4(dig, dfg, dgg, dog);
         }
-        uint32_t a[4], bb[4], cc[4];
-        split3(dig, a[0], bb[0], cc[0]);
-        split3(dfg, a[1], bb[1], cc[1]);
-        split3(dgg, a[2], bb[2], cc[2]);
-        split3(dog, a[3], bb[3], cc[3]);
-        // row b of the K-major operand, k = 4*ul .. 4*ul+3
-        const uint32_t o = dG_off + (uint32_t)(ul >> 4) * B_ATOM + (uint32_t)(b >> 3) * 1024 +
-                           (uint32_t)(b & 7) * 128 + (uint32_t)((((ul & 15) >> 1) ^ (b & 7)) << 4) +
-                           (uint32_t)(ul & 1) * 8;
-        *reinterpret_cast<uint2*>(sptr + o) = make_uint2(a[0] | (a[1] << 16), a[2] | (a[3] << 16));
-        *reinterpret_cast<uint2*>(sptr + o + dG_split) = make_uint2(bb[0] | (bb[1] << 16), bb[2] | (bb[3] << 16));
-        *reinterpret_cast<uint2*>(sptr + o + 2 * dG_split) = make_uint2(cc[0] | (cc[1] << 16), cc[2] | (cc[3] << 16));
+        dgv[i] = make_float4(dig, dfg, dgg, dog);
+        if (s + 1 < L) {
+          uint32_t a[4], bb[4], cc[4];
+          split3(dig, a[0], bb[0], cc[0]);
+          split3(dfg, a[1], bb[1], cc[1]);
+          split3(dgg, a[2], bb[2], cc[2]);
+          split3(dog, a[3], bb[3], cc[3]);
+          // row b of the K-major operand, k = 4*ul .. 4*ul+3
+          const uint32_t o = dG_off + (uint32_t)(ul >> 4) * B_ATOM + (uint32_t)(b >> 3) * 1024 +
+                             (uint32_t)(b & 7) * 128 + (uint32_t)((((ul & 15) >> 1) ^ (b & 7)) << 4) +
+                             (uint32_t)(ul & 1) * 8;
+          *reinterpret_cast<uint2*>(sptr + o) = make_uint2(a[0] | (a[1] << 16), a[2] | (a[3] << 16));
+          *reinterpret_cast<uint2*>(sptr + o + dG_split) = make_uint2(bb[0] | (bb[1] << 16), bb[2] | (bb[3] << 16));
+          *reinterpret_cast<uint2*>(sptr + o + 2 * dG_split) = make_uint2(cc[0] | (cc[1] << 16), cc[2] | (cc[3] << 16));
+        }
       }
-      TCL_TS(4)
       if (s + 1 < L) {
         fence_async_smem();
-        fence_before();
-        __syncthreads();
-        n_prev = cnt_s[t];
-        if (tid == 0) {
-          fence_after();
-          const int Nmma = (n_prev + 15) & ~15;
-          const uint32_t idesc = idesc_bf16(128, Nmma);
-          for (int mt = 0; mt < MT; ++mt) {
-            const uint32_t d_m = tmD + mt * 2 * TCL_N, d_x = d_m + TCL_N;
-            for (int ks = 0; ks < 8; ++ks) {
-              const int a = ks >> 2;
-              const uint32_t ko = (uint32_t)(ks & 3) * 32;
-              const uint32_t bo = sbase + dG_off + (uint32_t)a * B_ATOM + ko;
-              const uint64_t b1 = make_desc(bo, 16, 1024), b2 = make_desc(bo + dG_split, 16, 1024),
-                             b3 = make_desc(bo + 2 * dG_split, 16, 1024);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(dg_bar);
+      }
+      TCL_TS(5)
+      // the GEMM operand copy of d(gates): nobody inside this launch waits for it
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+        if (act[i])
+          *reinterpret_cast<float4*>(p.gates + (size_t)(off_t + b_base + warp + 8 * i) * H8 + gcol) = dgv[i];
+      if (s + 1 < L && warp < n_issuers) {
+        // ---- issue the MMAs of my accumulator: (M tile warp/2, main | cross) ----
+        mbar_wait(dg_bar, n_dg & 1);          // all eight warps' d(gates) are in shared memory
+        fence_after();
+        const int mt = warp >> 1;
+        const bool cross = (warp & 1) != 0;
+        const int Nmma = (cnt_s[t] + 15) & ~15;
+        const uint32_t idesc = idesc_bf16(128, Nmma);
+        const uint32_t d_acc = tmD + mt * 2 * TCL_N + (cross ? TCL_N : 0);
+        const uint64_t b_0 = make_desc(sbase + dG_off, 16, 1024);
+        if (elect_one()) {
+#pragma unroll
+          for (int a = 0; a < 2; ++a) {
+            const uint64_t b1a = b_0 + (uint64_t)((a * B_ATOM) >> 4);
+            const uint64_t b2a = b1a + (uint64_t)(dG_split >> 4), b3a = b2a + (uint64_t)(dG_split >> 4);
+            const uint64_t a2a = make_desc(sbase + wt_block(0, mt, a), 16, 1024);
+            const uint64_t a3a = make_desc(sbase + wt_block(1, mt, a), 16, 1024);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const int ks = a * 4 + kk;
               const uint32_t a1 = tm + mt * 64 + ks * 8;
-              const uint64_t a2 = make_desc(sbase + wt_block(0, mt, a) + ko, 16, 1024);
-              const uint64_t a3 = make_desc(sbase + wt_block(1, mt, a) + ko, 16, 1024);
-              mma_ts(d_x, a1, b3, idesc, ks > 0 ? 1u : 0u);
-              mma_ss(d_x, a3, b1, idesc, 1u);
-              mma_ss(d_x, a2, b2, idesc, 1u);
-              mma_ts(d_x, a1, b2, idesc, 1u);
-              mma_ss(d_x, a2, b1, idesc, 1u);
-              mma_ts(d_m, a1, b1, idesc, ks > 0 ? 1u : 0u);
+              if (cross) {
+                mma_ts(d_acc, a1, b3a + 2 * kk, idesc, ks > 0 ? 1u : 0u);    // 2^-16 terms first
+                mma_ss(d_acc, a3a + 2 * kk, b1a + 2 * kk, idesc, 1u);
+                mma_ss(d_acc, a2a + 2 * kk, b2a + 2 * kk, idesc, 1u);
+                mma_ts(d_acc, a1, b2a + 2 * kk, idesc, 1u);                  // 2^-8 terms
+                mma_ss(d_acc, a2a + 2 * kk, b1a + 2 * kk, idesc, 1u);
+              } else {
+                mma_ts(d_acc, a1, b1a + 2 * kk, idesc, ks > 0 ? 1u : 0u);
+              }
             }
           }
           commit(mma_bar);
         }
+        __syncwarp();
       }
-      TCL_TS(5)
+      if (s + 1 < L) ++n_dg;
+      TCL_TS(6)
     }
   }
 #undef TCL_TS
@@ -647,7 +691,7 @@ struct TclPlan {
 int g_tcl_max_ctas = 120;   // leaves 28 SMs to the visual / acoustic encoders and the GEMMs running next to it
 
 int tcl_make_plan(int B, int H, int Tmax, TclPlan* pl) {
-  if (H <= 128 || H > 352 || B <= 0) return MMDA_ERR_UNSUPPORTED;
+  if (H <= 128 || H > 320 || B <= 0) return MMDA_ERR_UNSUPPORTED;
   const int S = (H + TCL_UNITS - 1) / TCL_UNITS;
   const int Kp = (H + 15) & ~15;
   const int MT = (H + 127) / 128;
@@ -667,7 +711,7 @@ int tcl_make_plan(int B, int H, int Tmax, TclPlan* pl) {
   pl->S = S; pl->Kp = Kp; pl->MT = MT; pl->NT = NT; pl->BT = BT;
   pl->G = NT < Gmax ? NT : Gmax;
   const size_t misc = MISC_FIXED + (size_t)(2 * Tmax + 2) * 4;
-  pl->smem_fwd = 1024 + (size_t)KA * A_ATOM + (size_t)3 * KA * B_ATOM + misc;
+  pl->smem_fwd = 1024 + (size_t)2 * KA * B_ATOM + misc;
   const int rows_last = ((H - 128 * (MT - 1)) + 7) & ~7;
   pl->smem_bwd = 1024 + (size_t)4 * rows_last * 128 + (size_t)(2 * (MT - 1) * 2) * A_ATOM +
                  (size_t)3 * 2 * B_ATOM + misc;
@@ -677,7 +721,7 @@ int tcl_make_plan(int B, int H, int Tmax, TclPlan* pl) {
   const size_t flag_bytes = ((size_t)2 * NT * 4 + 255) & ~(size_t)255;
   pl->xch_off = pl->flag_off + flag_bytes;
   const size_t XLD = (size_t)S * TCL_UNITS;
-  const size_t fwd_x = (size_t)2 * NT * 2 * TCL_N * XLD * 4;
+  const size_t fwd_x = (size_t)2 * NT * 2 * (2 * KA * B_ATOM);
   const size_t bwd_x = (size_t)2 * NT * 2 * S * TCL_N * XLD * 4;
   pl->total = pl->xch_off + (fwd_x > bwd_x ? fwd_x : bwd_x);
   return MMDA_OK;
@@ -702,7 +746,7 @@ int mmda_lstm_tc_plan(int B, int H, int Tmax, int* out8) {
   TclPlan pl;
   int rc = tcl_make_plan(B, H, Tmax, &pl);
   if (rc != MMDA_OK) {
-    mmda_set_error("lstm_tc: hidden size %d not covered (128 < H <= 352)", H);
+    mmda_set_error("lstm_tc: hidden size %d not covered (128 < H <= 320)", H);
     return rc;
   }
   out8[0] = pl.S; out8[1] = pl.G; out8[2] = pl.BT; out8[3] = pl.NT; out8[4] = pl.Kp;
@@ -728,13 +772,13 @@ static int tcl_launch(bool bwd, TclArgs& a, int B, int H, int Tmax, void* ws, cu
   TclPlan pl;
   int rc = tcl_make_plan(B, H, Tmax, &pl);
   if (rc != MMDA_OK) {
-    mmda_set_error("lstm_tc: hidden size %d not covered (128 < H <= 352)", H);
+    mmda_set_error("lstm_tc: hidden size %d not covered (128 < H <= 320)", H);
     return rc;
   }
   uint8_t* w = static_cast<uint8_t*>(ws);
   a.err = reinterpret_cast<int*>(w);
   a.flags = reinterpret_cast<unsigned*>(w + pl.flag_off);
-  a.xch = reinterpret_cast<float*>(w + pl.xch_off);
+  a.xch = w + pl.xch_off;
   a.B = B; a.H = H; a.Kp = pl.Kp; a.S = pl.S; a.G = pl.G; a.BT = pl.BT; a.NT = pl.NT; a.MT = pl.MT;
   a.Tmax = Tmax;
   a.dbg = g_tcl_dbg;
@@ -742,7 +786,7 @@ static int tcl_launch(bool bwd, TclArgs& a, int B, int H, int Tmax, void* ws, cu
   const size_t smem = bwd ? pl.smem_bwd : pl.smem_fwd;
   auto kern = bwd ? lstm_tc_bwd_kernel : lstm_tc_fwd_kernel;
   MMDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<2 * pl.S * pl.G, TCL_THREADS, smem, stream>>>(a);
+  kern<<<2 * pl.S * pl.G, bwd ? TCL_BWD_THREADS : TCL_FWD_THREADS, smem, stream>>>(a);
   MMDA_CHECK_LAUNCH();
   return MMDA_OK;
 }

@@ -2,6 +2,7 @@
 // tensor-core recurrence (lstm_tc.cu).  gemm_tc.cu keeps its own private copies.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstdint>
 
 namespace tc5 {
@@ -102,6 +103,55 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
 }
 __device__ __forceinline__ void tmem_wait_ld() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// true in exactly one lane of the (converged) warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+// bulk copy global -> this CTA's shared memory on the TMA engine; completion = transaction bytes
+// on `bar`.  dst, src 16-byte aligned, bytes % 16 == 0.
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+// orders generic-proxy accesses (st.global by any CTA, made visible by a release/acquire chain)
+// against this thread's later async-proxy accesses (bulk copies), and vice versa
+__device__ __forceinline__ void fence_proxy_async_all() {
+  asm volatile("fence.proxy.async;" ::: "memory");
+}
+// instruction descriptor for kind::f16 with fp16 A/B (format 0), fp32 accumulate, K-major operands
+__device__ __forceinline__ uint32_t idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// x = a + 2^-11 * b with a, b fp16: a = fp16(x), b = fp16(2^11 (x - a)); |x - a - 2^-11 b| <= 2^-24 |x|
+// (for |x| < 65504; tiny x: absolute error <= 2^-36)
+__device__ __forceinline__ void split2h(float x, uint32_t& a, uint32_t& b) {
+  const __half h1 = __float2half_rn(x);
+  const float r = x - __half2float(h1);
+  const __half h2 = __float2half_rn(r * 2048.f);
+  a = (uint32_t)__half_as_ushort(h1);
+  b = (uint32_t)__half_as_ushort(h2);
+}
+__device__ __forceinline__ void split2hx8(const float (&x)[8], uint4& o1, uint4& o2) {
+  uint32_t a[8], b[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) split2h(x[i], a[i], b[i]);
+  o1 = make_uint4(a[0] | (a[1] << 16), a[2] | (a[3] << 16), a[4] | (a[5] << 16), a[6] | (a[7] << 16));
+  o2 = make_uint4(b[0] | (b[1] << 16), b[2] | (b[3] << 16), b[4] | (b[5] << 16), b[6] | (b[7] << 16));
 }
 
 // x = a + b + c with a, b, c bf16 (24 significant bits: exact to fp32 rounding)

@@ -245,26 +245,22 @@ def main():
         "fwd_tc": timeit(f_tc) - t_copy, "fwd_simt": timeit(f_simt) - t_copy,
         "bwd_tc": timeit(b_tc) - t_copy, "bwd_simt": timeit(b_simt) - t_copy, "copy": t_copy}), flush=True)
 
-    # ---- per-step phase stamps of CTA 0 ----
-    dbg = torch.zeros(8 * (c["Tmax"] + 1), dtype=torch.int64, device=dev)
+    # ---- per-step phase stamps of CTA 0 (16 slots per step; see TCL_TS in lstm_tc.cu) ----
+    dbg = torch.zeros(16 * (c["Tmax"] + 1), dtype=torch.int64, device=dev)
     LIB.call("mmda_lstm_tc_set_debug_buffer", P(dbg))
-    f_tc(); torch.cuda.synchronize()
-    d = dbg.view(-1, 8)[: c["Tmax"]].cpu()
-    mid = d[5:c["Tmax"] - 1]
-    if len(mid) > 1:
-        ph = (mid[:, 1:6] - mid[:, 0:5]).double().mean(0).tolist()
-        step = (d[6:c["Tmax"] - 1, 0] - d[5:c["Tmax"] - 2, 0]).double().mean().item()
-        print("fwd phases clk [wait-flag, load+split, sync, mma, ld+cell, publish]:",
-              [round(x) for x in ph], "step", round(step), flush=True)
-    dbg.zero_()
-    b_tc(); torch.cuda.synchronize()
-    d = dbg.view(-1, 8)[: c["Tmax"]].cpu()
-    mid = d[5:c["Tmax"] - 1]
-    if len(mid) > 1:
-        ph = (mid[:, 1:6] - mid[:, 0:5]).double().mean(0).tolist()
-        step = (d[6:c["Tmax"] - 1, 0] - d[5:c["Tmax"] - 2, 0]).double().mean().item()
-        print("bwd phases clk [mma-wait+partials, prefetch, wait-flag, reduce, cell, issue]:",
-              [round(x) for x in ph], "step", round(step), flush=True)
+    for name, fn in (("fwd", f_tc), ("bwd", b_tc)):
+        dbg.zero_()
+        fn(); torch.cuda.synchronize()
+        d = dbg.view(-1, 16)[: c["Tmax"]].cpu().double()
+        lo, hi = 5, c["Tmax"] - 2
+        if hi - lo < 2:
+            continue
+        rel0 = (d[lo:hi] - d[lo:hi, 0:1])
+        rel0[d[lo:hi] == 0] = float("nan")
+        means = rel0.nanmean(0).tolist()
+        step = (d[lo + 1:hi + 1, 0] - d[lo:hi, 0]).mean().item()
+        print(name, "stamps (clk after step start):",
+              {i: round(v) for i, v in enumerate(means) if v == v and i > 0}, "step", round(step), flush=True)
     LIB.call("mmda_lstm_tc_set_debug_buffer", None)
 
 
