@@ -121,22 +121,40 @@ __device__ __forceinline__ void warp_publish(unsigned* flag, int lane) {
 // ------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TCL_FWD_THREADS, 1) lstm_tc_fwd_kernel(const TclArgs p) {
+// A batch tile (<= 48 rows) is processed as up to three 16-row SUB-TILES that move through the
+// roles below like a software pipeline: while the cell warps update sub-tile k, the h_t of
+// sub-tile k-1 is on its way through L2 and the MMAs of sub-tile k+1 run.  Every role walks the
+// items (sub-tile k, step s) in the same order; mbarriers hand an item from role to role:
+//   publisher warp : staged h_t (smem) -> the sub-tile's L2 image, fence, tick the flag
+//   control warp   : flag wait (all S CTAs of the group ticked) -> one bulk copy image -> smem
+//   MMA warp       : copy landed -> 3 MMAs per K step (N = 16) -> commit   (issuing from two warps
+//                    at once measured 1.7x slower per MMA)
+//   8 cell warps   : MMA done -> TMEM -> registers -> gates/cell update -> stage h_t, store outputs
+constexpr int SUB = 16;                        // rows of a sub-tile = MMA N
+constexpr int MAXSUB = TCL_N / SUB;
+constexpr int SUB_ATOM = SUB * 128;            // bytes of one K atom of a sub-tile operand
+constexpr int STAGE_BYTES = 2 * SUB * 64;      // h1 | h2 of this CTA's 32 units, 16 rows
+constexpr int TCL_FWD_WARPS = TCL_CELL_WARPS + 5;
+constexpr int TCL_FWD_THREADS4 = 32 * TCL_FWD_WARPS;
+
+__global__ void __launch_bounds__(TCL_FWD_THREADS4, 1) lstm_tc_fwd_kernel(const TclArgs p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sptr = smem_raw + (sbase - smem_u32(smem_raw));
   const int H = p.H, Kp = p.Kp, S = p.S;
   const int KA = (Kp + 63) >> 6;              // K atoms
   const int KC = Kp >> 3;                     // 16-byte chunks per operand row
-  const uint32_t SPL = (uint32_t)KA * B_ATOM; // one split term of the h operand
-  const uint32_t IMG = 2 * SPL;               // h1 | h2 image
-  const uint32_t misc_off = IMG;
-  const uint32_t mma_bar = sbase + misc_off;
-  auto copy_bar = [&](int a) { return sbase + misc_off + 8u + 8u * (uint32_t)a; };
-  const uint32_t tmem_slot = sbase + misc_off + 8 + 8 * MAX_KA;
+  const int KS = Kp >> 4;                     // K steps
+  const uint32_t SPLS = (uint32_t)KA * SUB_ATOM;   // one split term of a sub-tile image
+  const uint32_t IMGS = 2 * SPLS;                  // h1 | h2
+  const uint32_t stage_off = MAXSUB * IMGS;
+  const uint32_t misc_off = stage_off + MAXSUB * STAGE_BYTES;
+  auto copy_bar = [&](int k) { return sbase + misc_off + 8u * (uint32_t)k; };
+  auto mma_bar = [&](int k) { return sbase + misc_off + 24u + 8u * (uint32_t)k; };
+  auto stage_bar = [&](int k) { return sbase + misc_off + 48u + 8u * (uint32_t)k; };
+  const uint32_t tmem_slot = sbase + misc_off + 72;
   int* lens_s = reinterpret_cast<int*>(sptr + misc_off + 128);
   int* orig_s = lens_s + TCL_N;
-  int* cnt_s = orig_s + TCL_N;                                    // [Tmax] rows alive at time t
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3, hc = (warp >> 2) & 1;
@@ -145,17 +163,20 @@ __global__ void __launch_bounds__(TCL_FWD_THREADS, 1) lstm_tc_fwd_kernel(const T
   const int dir = blockIdx.x / (S * p.G);
 
   if (tid == 0) {
-    mbar_init(mma_bar, 4);                    // four issuing warps commit
-    for (int a = 0; a < KA; ++a) mbar_init(copy_bar(a), 1);
+    for (int k = 0; k < MAXSUB; ++k) {
+      mbar_init(copy_bar(k), 1);
+      mbar_init(mma_bar(k), 1);
+      mbar_init(stage_bar(k), TCL_CELL_WARPS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) tmem_alloc512(tmem_slot);
   fence_before();
   __syncthreads();
   fence_after();
-  const uint32_t tm = *reinterpret_cast<uint32_t*>(sptr + misc_off + 8 + 8 * MAX_KA);
+  const uint32_t tm = *reinterpret_cast<uint32_t*>(sptr + misc_off + 72);
   const uint32_t tmW1 = tm, tmW2 = tm + (Kp >> 1);
-  const uint32_t tmD = tm + 2 * (Kp >> 1);    // main0 | main1 | cross a | cross b (x 2^11), TCL_N columns each
+  const uint32_t tmD = tm + 2 * (Kp >> 1);    // [sub-tile][main0 | main1 | cross a | cross b (x 2^11)][16 columns]
   const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
 
   if (warp < TCL_CELL_WARPS) {  // resident weights: row rho = 4*ul + g of the slice = W_hh[g*H + 32r + ul][:]
@@ -185,7 +206,7 @@ __global__ void __launch_bounds__(TCL_FWD_THREADS, 1) lstm_tc_fwd_kernel(const T
   fence_before();
   __syncthreads();
 
-  // my cells: unit ul = 8q + lane/4, batch columns b_i = 24*hc + 4*i + (lane & 3), i < 6
+  // my cells of sub-tile k: unit ul = 8q + lane/4, rows n_i = 8*hc + 4*i + (lane & 3), i < 2
   const int g4 = lane & 3;
   const int ul = 8 * q + (lane >> 2);
   const int u = r * TCL_UNITS + ul;
@@ -194,190 +215,221 @@ __global__ void __launch_bounds__(TCL_FWD_THREADS, 1) lstm_tc_fwd_kernel(const T
   const int gcol = dir * 4 * H + u * 4;
   const int ycol = dir * H + u;
   const int utt_off = dir == 0 ? p.utt_off0 : p.utt_off1;
-  const int KS = Kp >> 4;
-  uint32_t n_mma = 0;        // MMA batches issued / consumed so far (every thread keeps its own count)
+  uint32_t n_done[MAXSUB] = {0, 0, 0};     // completed phases of "my" barrier of each sub-tile
   const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0;
-#define TCL_TS(i) if (dbg_on && tile == grp) p.dbg[s * 16 + (i)] = clock64();
+#define TCL_TS(i) if (dbg_on && tile == grp && k == 0) p.dbg[s * 16 + (i)] = clock64();
 
   for (int tile = grp; tile < p.NT; tile += p.G) {
     const int b_base = tile * p.BT;
     const int rows = min(p.BT, p.B - b_base);
-    __syncthreads();   // previous tile fully done with lens_s / cnt_s
+    const int nsub = (rows + SUB - 1) / SUB;
+    __syncthreads();   // previous tile fully done with lens_s
     if (tid < TCL_N) {
       lens_s[tid] = tid < rows ? p.lens[b_base + tid] : 0;
       orig_s[tid] = tid < rows ? p.sorted_idx[b_base + tid] : 0;
     }
     __syncthreads();
-    const int L = lens_s[0];
-    for (int t = tid; t < L; t += TCL_FWD_THREADS) {
-      int n = 0;
-      for (int j = 0; j < rows; ++j) n += lens_s[j] > t;
-      cnt_s[t] = n;
-    }
-    __syncthreads();
-    unsigned* flag = p.flags + dir * p.NT + tile;
-    uint8_t* img = p.xch + (size_t)(dir * p.NT + tile) * 2 * IMG;     // [parity][IMG]
+    int Lk[MAXSUB];
+#pragma unroll
+    for (int k = 0; k < MAXSUB; ++k) Lk[k] = k < nsub ? lens_s[k * SUB] : 0;
+    const int L0 = Lk[0];
+    unsigned* flags = p.flags + (size_t)(dir * p.NT + tile) * MAXSUB;
+    uint8_t* img_g = p.xch + (size_t)(dir * p.NT + tile) * MAXSUB * 2 * IMGS;   // [k][parity][IMGS]
 
     if (warp == TCL_CELL_WARPS) {
-      // ===================== control: flag wait, bulk copies of h_{t-1} (one barrier per K atom) ====
+      // ===================== control: flag wait -> bulk copy of the sub-tile's h_{t-1} image =========
       if (lane == 0) {
         bool aborted = false;
-        for (int s = 1; s < L; ++s) {
-          const int t = dir == 0 ? s : L - 1 - s;
-          const uint32_t rb = (uint32_t)cnt_s[t] * 128;        // live rows of every atom block
-          if (!aborted && !spin_until(flag, (unsigned)(S * TCL_CELL_WARPS * s), p.err)) aborted = true;
-          TCL_TS(1)
-          if (n_mma > 0) mbar_wait(mma_bar, (n_mma - 1) & 1);   // previous MMAs are done reading the image
-          fence_proxy_async_all();
-          const uint8_t* src = img + (size_t)((s - 1) & 1) * IMG;
-          for (int a = 0; a < KA; ++a) {
-            mbar_expect_tx(copy_bar(a), 2 * rb);
-            const uint32_t o = (uint32_t)a * B_ATOM;
-            bulk_g2s(sbase + o, src + o, rb, copy_bar(a));
-            bulk_g2s(sbase + SPL + o, src + SPL + o, rb, copy_bar(a));
+        for (int s = 1; s < L0; ++s)
+#pragma unroll
+          for (int k = 0; k < MAXSUB; ++k) {
+            if (s >= Lk[k]) continue;
+            if (!aborted && !spin_until(flags + k, (unsigned)(S * s), p.err)) aborted = true;
+            TCL_TS(1)
+            fence_proxy_async_global();
+            mbar_expect_tx(copy_bar(k), IMGS);
+            bulk_g2s(sbase + (uint32_t)k * IMGS, img_g + ((size_t)k * 2 + ((s - 1) & 1)) * IMGS, IMGS,
+                     copy_bar(k));
           }
-          ++n_mma;
-          TCL_TS(2)
-        }
       }
       __syncwarp();
-      n_mma = __shfl_sync(0xffffffffu, n_mma, 0);
       continue;
     }
-
-    // ===================== cell warps (warps 0..3 also issue the MMAs) =====================
-    float cst[6];
-    int len_c[6], orig_c[6];
-    uint32_t img_off[6];
+    if (warp == TCL_CELL_WARPS + 1) {
+      // ===================== MMA issue =====================
+      for (int s = 1; s < L0; ++s)
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      cst[i] = 0.f;
-      const int b = 24 * hc + 4 * i + g4;
-      len_c[i] = u_ok ? lens_s[b] : 0;
-      orig_c[i] = orig_s[b];
-      img_off[i] = swz_chunk(b, u >> 3, B_ATOM) + (uint32_t)(u & 7) * 2;
-    }
-
-    for (int s = 0; s < L; ++s) {
-      const int t = dir == 0 ? s : L - 1 - s;
-      if (tid == 0) { TCL_TS(0) }
-      const int off_t = __ldg(p.offsets + t);
-      // x-projection of my cells (independent of h: in flight during the exchange + MMAs)
-      float4 xg[6];
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        const int b = 24 * hc + 4 * i + g4;
-        xg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (t < len_c[i])
-          xg[i] = __ldcs(reinterpret_cast<const float4*>(p.gates + (size_t)(off_t + b_base + b) * H8 + gcol));
-      }
-      float acc[6][4];
-#pragma unroll
-      for (int i = 0; i < 6; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-
-      if (s > 0) {
-        if (warp < 4) {
-          // ---- issue my accumulator's MMAs, K atom by K atom as the bulk copies land ----
-          // warp 0: W1h1 even k-steps -> main0; warp 1: odd -> main1; warp 2: W1h2 -> cross a;
-          // warp 3: W2h1 -> cross b.  One accumulator per issuing warp keeps the summation
-          // order (hence the bits) deterministic.
-          const int Nmma = (cnt_s[t] + 15) & ~15;
-          const uint32_t idesc = idesc_f16(128, Nmma);
-          const uint32_t d_acc = tmD + warp * TCL_N;
-          const uint32_t a_base = warp == 3 ? tmW2 : tmW1;
-          const uint64_t b_0 = make_desc(sbase + (warp == 2 ? SPL : 0u), 16, 1024);
+        for (int k = 0; k < MAXSUB; ++k) {
+          if (s >= Lk[k]) continue;
+          mbar_wait(copy_bar(k), n_done[k] & 1);
+          ++n_done[k];
           fence_after();
-          for (int a = 0; a < KA; ++a) {
-            mbar_wait(copy_bar(a), n_mma & 1);
-            fence_after();
-            const uint64_t ba = b_0 + (uint64_t)((a * B_ATOM) >> 4);
-            if (elect_one()) {
+          if (lane == 0) { TCL_TS(2) }
+          const uint32_t idesc = idesc_f16(128, SUB);
+          // consecutive MMAs never hit the same accumulator (a dependent MMA waits ~48 clk)
+          const uint32_t d_m0 = tmD + (uint32_t)k * 4 * SUB, d_m1 = d_m0 + SUB, d_xa = d_m0 + 2 * SUB,
+                         d_xb = d_m0 + 3 * SUB;
+          const uint64_t b1_0 = make_desc(sbase + (uint32_t)k * IMGS, 16, 1024);
+          const uint64_t b2_0 = make_desc(sbase + (uint32_t)k * IMGS + SPLS, 16, 1024);
+          if (elect_one()) {
+            for (int a = 0; a < KA; ++a) {
+              const uint64_t b1a = b1_0 + (uint64_t)((a * SUB_ATOM) >> 4), b2a = b2_0 + (uint64_t)((a * SUB_ATOM) >> 4);
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk) {
                 const int ks = a * 4 + kk;
                 if (ks < KS) {
-                  if (warp >= 2) mma_ts(d_acc, a_base + ks * 8, ba + 2 * kk, idesc, ks > 0 ? 1u : 0u);
-                  else if ((ks & 1) == warp) mma_ts(d_acc, a_base + ks * 8, ba + 2 * kk, idesc, ks >= 2 ? 1u : 0u);
+                  const uint32_t a1 = tmW1 + ks * 8, a2 = tmW2 + ks * 8;
+                  mma_ts(d_xa, a1, b2a + 2 * kk, idesc, ks > 0 ? 1u : 0u);
+                  mma_ts(d_xb, a2, b1a + 2 * kk, idesc, ks > 0 ? 1u : 0u);
+                  mma_ts((ks & 1) ? d_m1 : d_m0, a1, b1a + 2 * kk, idesc, ks >= 2 ? 1u : 0u);
                 }
               }
             }
-            __syncwarp();
+            commit(mma_bar(k));
           }
-          if (elect_one()) commit(mma_bar);
           __syncwarp();
+          if (lane == 0) { TCL_TS(3) }
         }
-        if (tid == 0) { TCL_TS(3) }
-        mbar_wait(mma_bar, n_mma & 1);
-        ++n_mma;
-        fence_after();
-        if (tid == 0) { TCL_TS(4) }
-        // ---- D -> registers: my row (gate g4 of unit ul), 24 batch columns ----
+      continue;
+    }
+    if (warp >= TCL_CELL_WARPS + 2) {
+      // ===================== publishers (one warp per sub-tile): staged h_t -> L2 image, tick ====
+      const int k = warp - (TCL_CELL_WARPS + 2);
+      for (int s = 0; s + 1 < L0; ++s)
+        {
+          if (s + 1 >= Lk[k]) continue;
+          mbar_wait(stage_bar(k), n_done[k] & 1);
+          ++n_done[k];
+          if (lane == 0) { TCL_TS(7) }
+          uint8_t* dst = img_g + ((size_t)k * 2 + (s & 1)) * IMGS;
+          const uint8_t* st = sptr + stage_off + k * STAGE_BYTES;
 #pragma unroll
-        for (int cb = 0; cb < 3; ++cb) {
+          for (int i = 0; i < 4; ++i) {
+            const int id = lane + 32 * i;                      // 128 chunks of 16 B
+            const int sp = id >> 6, n = (id >> 2) & 15, c = id & 3;
+            const uint4 v = *reinterpret_cast<const uint4*>(st + sp * (SUB * 64) + n * 64 + c * 16);
+            *reinterpret_cast<uint4*>(dst + sp * SPLS + swz_chunk(n, 4 * r + c, SUB_ATOM)) = v;
+          }
+          if (lane == 0) { TCL_TS(9) }
+          fence_proxy_async_global();     // my generic-proxy writes vs the peers' bulk copies
+          __syncwarp();                   // orders the 32 lanes' stores before lane 0's release (cumulative)
+          if (lane == 0) red_release_add(flags + k, 1u);
+          if (lane == 0) { TCL_TS(8) }
+        }
+      continue;
+    }
+
+    // ===================== cell warps =====================
+    float cst[MAXSUB][2];
+    float4 xg[MAXSUB][2];      // x-projection of my cells, fetched one step ahead (HBM latency)
+    int len_c[MAXSUB][2], orig_c[MAXSUB][2];
+#pragma unroll
+    for (int k = 0; k < MAXSUB; ++k)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        cst[k][i] = 0.f;
+        const int b = k * SUB + 8 * hc + 4 * i + g4;
+        len_c[k][i] = u_ok ? lens_s[b] : 0;
+        orig_c[k][i] = orig_s[b];
+        xg[k][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int t0 = dir == 0 ? 0 : Lk[k] - 1;
+        if (k < nsub && t0 < len_c[k][i])
+          xg[k][i] = __ldcs(reinterpret_cast<const float4*>(
+              p.gates + (size_t)(__ldg(p.offsets + t0) + b_base + b) * H8 + gcol));
+      }
+
+    for (int s = 0; s < L0; ++s)
+#pragma unroll
+      for (int k = 0; k < MAXSUB; ++k) {
+        if (s >= Lk[k]) continue;
+        const int t = dir == 0 ? s : Lk[k] - 1 - s;
+        if (tid == 0) { TCL_TS(0) }
+        const int off_t = __ldg(p.offsets + t);
+        const float4 xg0 = xg[k][0], xg1 = xg[k][1];
+        if (s + 1 < Lk[k]) {   // next step's x-projection of these two cells
+          const int tn = dir == 0 ? t + 1 : t - 1;
+          const int off_n = __ldg(p.offsets + tn);
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int b = k * SUB + 8 * hc + 4 * i + g4;
+            if (tn < len_c[k][i])
+              xg[k][i] = __ldcs(reinterpret_cast<const float4*>(p.gates + (size_t)(off_n + b_base + b) * H8 + gcol));
+          }
+        }
+        float acc[2][4];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        if (s > 0) {
+          mbar_wait(mma_bar(k), n_done[k] & 1);
+          ++n_done[k];
+          fence_after();
+          if (tid == 0) { TCL_TS(4) }
           uint32_t m0[8], m1[8], xa[8], xb[8];
-          const uint32_t col = (uint32_t)(24 * hc + 8 * cb);
+          const uint32_t col = (uint32_t)(k * 4 * SUB + 8 * hc);
           tmem_ld8(tmD + lane_sel + col, m0);
-          tmem_ld8(tmD + lane_sel + 2 * TCL_N + col, xa);
-          tmem_ld8(tmD + lane_sel + 3 * TCL_N + col, xb);
-          if (KS > 1) tmem_ld8(tmD + lane_sel + TCL_N + col, m1);
+          tmem_ld8(tmD + lane_sel + 2 * SUB + col, xa);
+          tmem_ld8(tmD + lane_sel + 3 * SUB + col, xb);
+          if (KS > 1) tmem_ld8(tmD + lane_sel + SUB + col, m1);
           tmem_wait_ld();
+          fence_before();
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float v = __uint_as_float(m0[j]);
             if (KS > 1) v += __uint_as_float(m1[j]);
-            acc[cb * 2 + (j >> 2)][j & 3] =
-                fmaf(__uint_as_float(xa[j]) + __uint_as_float(xb[j]), 1.f / 2048.f, v);
+            acc[j >> 2][j & 3] = fmaf(__uint_as_float(xa[j]) + __uint_as_float(xb[j]), 1.f / 2048.f, v);
+          }
+          transpose4(acc[0], g4);
+          transpose4(acc[1], g4);
+        }
+        // ---- cell update ----
+        float4 ga[2];
+        float hn[2];
+        const bool more = s + 1 < Lk[k];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          hn[i] = 0.f;
+          if (t < len_c[k][i]) {
+            const float4 xv = i == 0 ? xg0 : xg1;
+            ga[i].x = fast_sigmoid(acc[i][0] + xv.x);
+            ga[i].y = fast_sigmoid(acc[i][1] + xv.y);
+            ga[i].z = fast_tanh(acc[i][2] + xv.z);
+            ga[i].w = fast_sigmoid(acc[i][3] + xv.w);
+            cst[k][i] = ga[i].y * cst[k][i] + ga[i].x * ga[i].z;
+            hn[i] = ga[i].w * fast_tanh(cst[k][i]);
+          }
+          if (more) {        // stage my element of the next step's B operand (zeros keep h0 = 0 rows clean)
+            uint32_t h1, h2;
+            split2h(hn[i], h1, h2);
+            const int n = 8 * hc + 4 * i + g4;
+            unsigned short* st = reinterpret_cast<unsigned short*>(sptr + stage_off + k * STAGE_BYTES) + n * 32 + ul;
+            st[0] = (unsigned short)h1;
+            st[SUB * 32] = (unsigned short)h2;
           }
         }
-#pragma unroll
-        for (int i = 0; i < 6; ++i) transpose4(acc[i], g4);
-        if (tid == 0) { TCL_TS(8) }
-      }
-
-      // ---- cell update (acc[i][0..3] = W_hh h of gates i,f,g,o of cell (ul, b_i)) ----
-      float4 ga[6];
-      float hn[6];
-      uint8_t* dst = img + (size_t)(s & 1) * IMG;
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        hn[i] = 0.f;
-        if (t < len_c[i]) {
-          ga[i].x = fast_sigmoid(acc[i][0] + xg[i].x);
-          ga[i].y = fast_sigmoid(acc[i][1] + xg[i].y);
-          ga[i].z = fast_tanh(acc[i][2] + xg[i].z);
-          ga[i].w = fast_sigmoid(acc[i][3] + xg[i].w);
-          cst[i] = ga[i].y * cst[i] + ga[i].x * ga[i].z;
-          hn[i] = ga[i].w * fast_tanh(cst[i]);
+        if (more) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(stage_bar(k));
         }
-        if (s + 1 < L) {      // my element of the next step's B operand (zeros keep h0 = 0 rows clean)
-          uint32_t h1, h2;
-          split2h(hn[i], h1, h2);
-          *reinterpret_cast<unsigned short*>(dst + img_off[i]) = (unsigned short)h1;
-          *reinterpret_cast<unsigned short*>(dst + SPL + img_off[i]) = (unsigned short)h2;
-        }
-      }
-      if (tid == 0) { TCL_TS(9) }
-      if (s + 1 < L) warp_publish(flag, lane);
-      if (tid == 0) { TCL_TS(5) }
-      // ---- outputs nobody waits for inside this launch ----
+        if (tid == 0) { TCL_TS(5) }
+        // ---- outputs nobody waits for inside this launch ----
 #pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        if (t < len_c[i]) {
-          const int b = 24 * hc + 4 * i + g4;
-          const size_t row = (size_t)(off_t + b_base + b);
-          if (p.save) {
-            *reinterpret_cast<float4*>(p.gates + row * H8 + gcol) = ga[i];
-            p.c[row * H2 + ycol] = cst[i];
+        for (int i = 0; i < 2; ++i) {
+          if (t < len_c[k][i]) {
+            const int b = k * SUB + 8 * hc + 4 * i + g4;
+            const size_t row = (size_t)(off_t + b_base + b);
+            if (p.save) {
+              *reinterpret_cast<float4*>(p.gates + row * H8 + gcol) = ga[i];
+              p.c[row * H2 + ycol] = cst[k][i];
+            }
+            p.y[row * H2 + ycol] = hn[i];
+            const bool fin = dir == 0 ? (t == len_c[k][i] - 1) : (t == 0);
+            if (fin && p.utt) p.utt[(size_t)orig_c[k][i] * p.utt_ld + utt_off + u] = hn[i];
           }
-          p.y[row * H2 + ycol] = hn[i];
-          const bool fin = dir == 0 ? (t == len_c[i] - 1) : (t == 0);
-          if (fin && p.utt) p.utt[(size_t)orig_c[i] * p.utt_ld + utt_off + u] = hn[i];
         }
+        if (tid == 0) { TCL_TS(6) }
       }
-      if (tid == 0) { TCL_TS(6) }
-    }
   }
 #undef TCL_TS
   fence_before();
@@ -711,17 +763,17 @@ int tcl_make_plan(int B, int H, int Tmax, TclPlan* pl) {
   pl->S = S; pl->Kp = Kp; pl->MT = MT; pl->NT = NT; pl->BT = BT;
   pl->G = NT < Gmax ? NT : Gmax;
   const size_t misc = MISC_FIXED + (size_t)(2 * Tmax + 2) * 4;
-  pl->smem_fwd = 1024 + (size_t)2 * KA * B_ATOM + misc;
+  pl->smem_fwd = 1024 + (size_t)MAXSUB * (2 * KA * SUB_ATOM + STAGE_BYTES) + misc;
   const int rows_last = ((H - 128 * (MT - 1)) + 7) & ~7;
   pl->smem_bwd = 1024 + (size_t)4 * rows_last * 128 + (size_t)(2 * (MT - 1) * 2) * A_ATOM +
                  (size_t)3 * 2 * B_ATOM + misc;
   if (pl->smem_fwd > 232448 || pl->smem_bwd > 232448) return MMDA_ERR_UNSUPPORTED;
   // workspace: [err (256 B)] [flags fwd+bwd 2*2*NT u32, padded] [exchange / partial scratch]
   pl->flag_off = 256;
-  const size_t flag_bytes = ((size_t)2 * NT * 4 + 255) & ~(size_t)255;
+  const size_t flag_bytes = ((size_t)2 * NT * MAXSUB * 4 + 255) & ~(size_t)255;
   pl->xch_off = pl->flag_off + flag_bytes;
   const size_t XLD = (size_t)S * TCL_UNITS;
-  const size_t fwd_x = (size_t)2 * NT * 2 * (2 * KA * B_ATOM);
+  const size_t fwd_x = (size_t)2 * NT * MAXSUB * 2 * (2 * KA * SUB_ATOM);
   const size_t bwd_x = (size_t)2 * NT * 2 * S * TCL_N * XLD * 4;
   pl->total = pl->xch_off + (fwd_x > bwd_x ? fwd_x : bwd_x);
   return MMDA_OK;
@@ -782,11 +834,11 @@ static int tcl_launch(bool bwd, TclArgs& a, int B, int H, int Tmax, void* ws, cu
   a.B = B; a.H = H; a.Kp = pl.Kp; a.S = pl.S; a.G = pl.G; a.BT = pl.BT; a.NT = pl.NT; a.MT = pl.MT;
   a.Tmax = Tmax;
   a.dbg = g_tcl_dbg;
-  MMDA_CUDA(cudaMemsetAsync(a.flags, 0, (size_t)2 * pl.NT * 4, stream));
+  MMDA_CUDA(cudaMemsetAsync(a.flags, 0, (size_t)2 * pl.NT * MAXSUB * 4, stream));
   const size_t smem = bwd ? pl.smem_bwd : pl.smem_fwd;
   auto kern = bwd ? lstm_tc_bwd_kernel : lstm_tc_fwd_kernel;
   MMDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<2 * pl.S * pl.G, bwd ? TCL_BWD_THREADS : TCL_FWD_THREADS, smem, stream>>>(a);
+  kern<<<2 * pl.S * pl.G, bwd ? TCL_BWD_THREADS : TCL_FWD_THREADS4, smem, stream>>>(a);
   MMDA_CHECK_LAUNCH();
   return MMDA_OK;
 }

@@ -133,6 +133,10 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
 __device__ __forceinline__ void fence_proxy_async_all() {
   asm volatile("fence.proxy.async;" ::: "memory");
 }
+// the same, restricted to the global state space (does not wait on shared-memory async traffic)
+__device__ __forceinline__ void fence_proxy_async_global() {
+  asm volatile("fence.proxy.async.global;" ::: "memory");
+}
 // instruction descriptor for kind::f16 with fp16 A/B (format 0), fp32 accumulate, K-major operands
 __device__ __forceinline__ uint32_t idesc_f16(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);

@@ -157,6 +157,11 @@ class MisaEngine:
         if "MMDA_LSTM_SMALL_TILE" in os.environ and not _DRYRUN:      # A/B knob
             LIB.call("mmda_lstm_set_small_tile", int(os.environ["MMDA_LSTM_SMALL_TILE"]))
         self.text_priority = os.environ.get("MMDA_TEXT_PRIORITY", "1") != "0"
+        # large hidden sizes (text, H = 300): tensor-core recurrence (csrc/lstm_tc.cu) instead of
+        # the SIMT cluster kernel; MMDA_LSTM_TC=0 keeps the SIMT path (A/B measurements)
+        self.lstm_tc = os.environ.get("MMDA_LSTM_TC", "1") != "0"
+        if "MMDA_LSTM_TC_CTAS" in os.environ and not _DRYRUN:
+            LIB.call("mmda_lstm_tc_set_max_ctas", int(os.environ["MMDA_LSTM_TC_CTAS"]))
         # use_bert=True: the BERT encoder runs on the hand-written kernels too
         # (mmda_b200/bert.py); its masked-mean output enters here as `utt_text` and backward()
         # returns the gradient wrt it.
@@ -426,6 +431,27 @@ class MisaEngine:
     def _cols(op, lo, hi):
         return (op[0][:, lo:hi], None if op[1] is None else op[1][:, lo:hi])
 
+    def _lstm_tc_ws(self, m, B, H, Tmax):
+        """Workspace of the tensor-core recurrence for modality m, or None when that path does
+        not cover (B, H) -- small hidden sizes and GRU cells stay on the SIMT kernels."""
+        if not self.lstm_tc or self.gru or _DRYRUN:
+            return None
+        nbytes = LIB.raw("mmda_lstm_tc_workspace_bytes")(B, H, Tmax)
+        if nbytes <= 0:
+            return None
+        name, n = f"lstm_tc_ws_{m}", (nbytes + 3) // 4
+        old = self.ws.get(name)
+        ws = self.buf(name, n, dtype=torch.int32)
+        if old is None or old.data_ptr() != ws.data_ptr():
+            ws[:64].zero_()      # ws[0] = sticky "a peer CTA never showed up" flag
+        return ws
+
+    def lstm_tc_check(self):
+        """Raise if a tensor-core recurrence launch gave up waiting for a peer CTA (ws[0] != 0)."""
+        for name, t in self.ws.items():
+            if name.startswith("lstm_tc_ws_") and int(t[0]) != 0:
+                raise MmdaError(f"{name}: a tensor-core recurrence launch timed out waiting for a peer CTA")
+
     # ---------------------------------------------------------------- forward --------------
     def _encode(self, m, X, pk, train, P):
         """reference src/models.py:163-180 + :203 for modality m on the packed rows X (N,I)."""
@@ -467,10 +493,17 @@ class MisaEngine:
                      _ptr(pk["sidx"]), _ptr(pk["off"]), _ptr(utt), 4 * H, o_f, o_r, B, H, Tmax,
                      int(train))
                 continue
-            k._c("mmda_lstm_forward", _ptr(G), _ptr(P[f"{r}.weight_hh_l0"]),
-                 _ptr(P[f"{r}.weight_hh_l0_reverse"]), _ptr(Y), _ptr(C), _ptr(pk["lens"]),
-                 _ptr(pk["sidx"]), _ptr(pk["off"]), _ptr(utt), 4 * H, o_f, o_r, B, H, Tmax,
-                 int(train))
+            tcws = self._lstm_tc_ws(m, B, H, Tmax)
+            if tcws is not None:
+                k._c("mmda_lstm_tc_forward", _ptr(G), _ptr(P[f"{r}.weight_hh_l0"]),
+                     _ptr(P[f"{r}.weight_hh_l0_reverse"]), _ptr(Y), _ptr(C), _ptr(pk["lens"]),
+                     _ptr(pk["sidx"]), _ptr(pk["off"]), _ptr(utt), 4 * H, o_f, o_r, B, H, Tmax,
+                     int(train), _ptr(tcws))
+            else:
+                k._c("mmda_lstm_forward", _ptr(G), _ptr(P[f"{r}.weight_hh_l0"]),
+                     _ptr(P[f"{r}.weight_hh_l0_reverse"]), _ptr(Y), _ptr(C), _ptr(pk["lens"]),
+                     _ptr(pk["sidx"]), _ptr(pk["off"]), _ptr(utt), 4 * H, o_f, o_r, B, H, Tmax,
+                     int(train))
             if m == "t":
                 self._mark(f"  t.{r} recurrence done")
         return utt
@@ -890,11 +923,18 @@ class MisaEngine:
             if r == r1:
                 k.layernorm_bwd(dY1n, Y1, None, P[f"{ln}.weight"], mu, rs, dY1, G[f"{ln}.weight"],
                                 G[f"{ln}.bias"])
-            k._c("mmda_gru_backward" if self.gru else "mmda_lstm_backward", _ptr(Gt),
-                 _ptr(P[f"{r}.weight_hh_l0"]), _ptr(P[f"{r}.weight_hh_l0_reverse"]),
-                 _ptr(Y if self.gru else C), _ptr(dy), _ptr(dutt), 4 * H, o_f,
-                 o_r, _ptr(pk["lens"]), _ptr(pk["sidx"]), _ptr(pk["off"]), _ptr(scratch), B, H,
-                 Tmax)
+            tcws = self._lstm_tc_ws(m, B, H, Tmax)
+            if tcws is not None:
+                k._c("mmda_lstm_tc_backward", _ptr(Gt), _ptr(P[f"{r}.weight_hh_l0"]),
+                     _ptr(P[f"{r}.weight_hh_l0_reverse"]), _ptr(C), _ptr(dy), _ptr(dutt), 4 * H, o_f,
+                     o_r, _ptr(pk["lens"]), _ptr(pk["sidx"]), _ptr(pk["off"]), B, H, Tmax,
+                     _ptr(tcws))
+            else:
+                k._c("mmda_gru_backward" if self.gru else "mmda_lstm_backward", _ptr(Gt),
+                     _ptr(P[f"{r}.weight_hh_l0"]), _ptr(P[f"{r}.weight_hh_l0_reverse"]),
+                     _ptr(Y if self.gru else C), _ptr(dy), _ptr(dutt), 4 * H, o_f,
+                     o_r, _ptr(pk["lens"]), _ptr(pk["sidx"]), _ptr(pk["off"]), _ptr(scratch), B, H,
+                     Tmax)
             if m == "t":
                 self._mark(f"  t.{r} BPTT done")
             I = Xin.shape[1]
