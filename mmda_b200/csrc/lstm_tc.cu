@@ -440,7 +440,27 @@ __global__ void __launch_bounds__(TCL_FWD_THREADS4, 1) lstm_tc_fwd_kernel(const 
 // ------------------------------------------------------------------------------------------
 // backward through time
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TCL_BWD_THREADS, 1) lstm_tc_bwd_kernel(const TclArgs p) {
+// Same sub-tile pipeline as the forward, with two 24-row sub-tiles (MMA N = 32): the backward needs
+// 6 MMAs per K step and M tile, half of them with the A operand in shared memory (~45 clk each
+// whatever N is), so fewer, wider MMAs win.  One TMEM accumulator per (sub-tile, M tile): the terms
+// are issued smallest first (2^-16 group, 2^-8 group, main), so the truncating fp32 accumulation
+// only sees the 8 main adds at full magnitude.  Roles (every role walks the items (k, s) in the
+// same order):
+//   8 cell warps  : [partials of this step reduced over the S CTAs] -> cell backward -> d(gates)
+//                   as three bf16 terms into the sub-tile's B operand (+ fp32 to global)
+//   MMA warp      : d(gates) staged -> partial dh^T[j][b] = W^T_slice * d(gates)^T for the three
+//                   M tiles (6 MMAs per K step and tile) -> commit
+//   4 writer warps: MMA done -> TMEM -> this CTA's block of the L2 partial scratch -> tick
+//   control warp  : flag wait (every writer warp of the S CTAs ticked) -> release the cell warps
+constexpr int TCL_BWD_WARPS4 = TCL_CELL_WARPS + 6;
+constexpr int TCL_BWD_THREADS4 = 32 * TCL_BWD_WARPS4;
+constexpr int BWD_WRITERS = 4;
+constexpr int BSUB = 24;                       // rows of a backward sub-tile
+constexpr int BN = 32;                         // its MMA N (rows 24..31 of the B operand stay zero)
+constexpr int BMAXSUB = TCL_N / BSUB;
+constexpr int BSUB_ATOM = BN * 128;
+
+__global__ void __launch_bounds__(TCL_BWD_THREADS4, 1) lstm_tc_bwd_kernel(const TclArgs p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sptr = smem_raw + (sbase - smem_u32(smem_raw));
@@ -453,17 +473,20 @@ __global__ void __launch_bounds__(TCL_BWD_THREADS, 1) lstm_tc_bwd_kernel(const T
   const uint32_t PB = (uint32_t)rows_last * 128;
   const uint32_t full_off = 4 * PB;                               // [split 2][atom 2] partial blocks
   const uint32_t dG_off = full_off + (uint32_t)(2 * (MT - 1) * 2) * A_ATOM;
-  const uint32_t dG_split = 2 * B_ATOM;
-  const uint32_t misc_off = dG_off + 3 * dG_split;
+  const uint32_t dG_split = 2 * BSUB_ATOM;                         // one bf16 term of one sub-tile (2 K atoms)
+  const uint32_t dG_sub = 3 * dG_split;
+  const uint32_t misc_off = dG_off + BMAXSUB * dG_sub;
   auto wt_block = [&](int sp, int mt, int a) -> uint32_t {      // sp: 0 = term 2, 1 = term 3
     return mt == MT - 1 ? (uint32_t)(sp * 2 + a) * PB
                         : full_off + (uint32_t)((sp * (MT - 1) + mt) * 2 + a) * A_ATOM;
   };
-  const uint32_t mma_bar = sbase + misc_off, dg_bar = sbase + misc_off + 8;
-  const uint32_t tmem_slot = sbase + misc_off + 16;
+  auto mma_bar = [&](int k) { return sbase + misc_off + 8u * (uint32_t)k; };
+  auto dg_bar = [&](int k) { return sbase + misc_off + 24u + 8u * (uint32_t)k; };
+  auto part_bar = [&](int k) { return sbase + misc_off + 48u + 8u * (uint32_t)k; };
+  const uint32_t tmem_slot = sbase + misc_off + 72;
   int* lens_s = reinterpret_cast<int*>(sptr + misc_off + 128);
   int* orig_s = lens_s + TCL_N;
-  int* cnt_s = orig_s + TCL_N;               // [Tmax]
+  int* cnt_s = orig_s + TCL_N;               // [Tmax]: rows of the TILE alive at time t
   int* offs_s = cnt_s + p.Tmax;              // [Tmax+1]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -472,23 +495,25 @@ __global__ void __launch_bounds__(TCL_BWD_THREADS, 1) lstm_tc_bwd_kernel(const T
   const int grp = (blockIdx.x / S) % p.G;
   const int dir = blockIdx.x / (S * p.G);
   const int XLD = S * TCL_UNITS;
-  const int n_issuers = 2 * MT;              // warp w < 2*MT issues (tile w/2, main | cross)
 
   if (tid == 0) {
-    mbar_init(mma_bar, n_issuers);
-    mbar_init(dg_bar, TCL_CELL_WARPS);
+    for (int k = 0; k < BMAXSUB; ++k) {
+      mbar_init(mma_bar(k), 1);
+      mbar_init(dg_bar(k), TCL_CELL_WARPS);
+      mbar_init(part_bar(k), 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) tmem_alloc512(tmem_slot);
-  for (int i = tid; i <= p.Tmax; i += TCL_BWD_THREADS) offs_s[i] = p.offsets[i];
+  for (int i = tid; i <= p.Tmax; i += TCL_BWD_THREADS4) offs_s[i] = p.offsets[i];
   fence_before();
   __syncthreads();
   fence_after();
-  const uint32_t tm = *reinterpret_cast<uint32_t*>(sptr + misc_off + 16);
-  const uint32_t tmD = tm + MT * 64;          // per M tile: main | cross, TCL_N columns each
+  const uint32_t tm = *reinterpret_cast<uint32_t*>(sptr + misc_off + 72);
+  const uint32_t tmD = tm + MT * 64;          // [sub-tile][M tile][32 columns]
   const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
 
-  {  // A[j][rho] = W_hh[(rho&3)*H + 32r + (rho>>2)][j]
+  if (warp < TCL_CELL_WARPS) {  // A[j][rho] = W_hh[(rho&3)*H + 32r + (rho>>2)][j]
     const float* __restrict__ W = p.whh[dir];
     for (int mt = 0; mt < MT; ++mt) {
       const int jl = q * 32 + lane, j = mt * 128 + jl;
@@ -513,218 +538,268 @@ __global__ void __launch_bounds__(TCL_BWD_THREADS, 1) lstm_tc_bwd_kernel(const T
     }
     tmem_wait_st();
   }
+  for (uint32_t i = tid; i < BMAXSUB * dG_sub / 16; i += TCL_BWD_THREADS4)   // pad rows of the B operands
+    reinterpret_cast<uint4*>(sptr + dG_off)[i] = make_uint4(0u, 0u, 0u, 0u);
   fence_async_smem();
   fence_before();
   __syncthreads();
 
-  // cell role: lane = local unit, warp w owns batch rows w, w+8, ..., w+40
-  const int ul = lane, u = r * TCL_UNITS + ul;
-  const bool u_ok = u < H;
   const int H2 = 2 * H, H8 = 8 * H;
-  const int gcol = dir * 4 * H + u * 4;
-  const int ycol = dir * H + u;
-  const int utt_off = dir == 0 ? p.utt_off0 : p.utt_off1;
-  uint32_t n_mma = 0, n_dg = 0;
-  bool aborted = false;
-  const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0 && tid == 0;
-#define TCL_TS(i) if (dbg_on && tile == grp) p.dbg[s * 16 + (i)] = clock64();
+  uint32_t n_done[BMAXSUB] = {0, 0};       // completed phases of "my" barrier of each sub-tile
+  const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0;
+#define TCL_TS(i) if (dbg_on && tile == grp && k == 0) p.dbg[s * 16 + (i)] = clock64();
 
   for (int tile = grp; tile < p.NT; tile += p.G) {
     const int b_base = tile * p.BT;
     const int rows = min(p.BT, p.B - b_base);
+    const int nsub = (rows + BSUB - 1) / BSUB;
     __syncthreads();
     if (tid < TCL_N) {
       lens_s[tid] = tid < rows ? p.lens[b_base + tid] : 0;
       orig_s[tid] = tid < rows ? p.sorted_idx[b_base + tid] : 0;
     }
     __syncthreads();
-    const int L = lens_s[0];
-    for (int t = tid; t < L; t += TCL_BWD_THREADS) {
+    int Lk[BMAXSUB];
+#pragma unroll
+    for (int k = 0; k < BMAXSUB; ++k) Lk[k] = k < nsub ? lens_s[k * BSUB] : 0;
+    const int L0 = Lk[0];
+    for (int t = tid; t < L0; t += TCL_BWD_THREADS4) {
       int n = 0;
       for (int j = 0; j < rows; ++j) n += lens_s[j] > t;
       cnt_s[t] = n;
     }
     __syncthreads();
-    unsigned* flag = p.flags + dir * p.NT + tile;
-    const size_t slab = (size_t)TCL_N * XLD;                     // one CTA's partial block
-    float* part = reinterpret_cast<float*>(p.xch) + (size_t)((dir * p.NT + tile) * 2) * S * slab;   // [par][S][48][XLD]
+    unsigned* flags = p.flags + (size_t)(dir * p.NT + tile) * BMAXSUB;
+    const size_t slab = (size_t)BSUB * XLD;                      // one CTA's partial block of a sub-tile
+    // partial scratch of this tile: [k][parity][S][24][XLD]
+    float* part = reinterpret_cast<float*>(p.xch) + (size_t)(dir * p.NT + tile) * BMAXSUB * 2 * S * slab;
 
-    float dcst[6];
-    int len_c[6], orig_c[6];
+    if (warp == TCL_CELL_WARPS + 5) {
+      // ===================== control: every writer warp of the group has published =============
+      if (lane == 0) {
+        bool aborted = false;
+        for (int s = 1; s < L0; ++s)
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      dcst[i] = 0.f;
-      const int b = warp + 8 * i;
-      len_c[i] = u_ok ? lens_s[b] : 0;
-      orig_c[i] = orig_s[b];
+          for (int k = 0; k < BMAXSUB; ++k) {
+            if (s >= Lk[k]) continue;
+            if (!aborted && !spin_until(flags + k, (unsigned)(S * BWD_WRITERS * s), p.err)) aborted = true;
+            TCL_TS(1)
+            mbar_arrive(part_bar(k));
+          }
+      }
+      __syncwarp();
+      continue;
     }
-
-    for (int s = 0; s < L; ++s) {
-      const int t = dir == 0 ? L - 1 - s : s;
-      const int par = s & 1;
-      TCL_TS(0)
-      if (s > 0) {
-        // ---- partial dh^T[j][b] of the successor step: TMEM -> my block of the L2 scratch ----
-        const int n_prev = cnt_s[dir == 0 ? t + 1 : t - 1];     // rows whose d(gates) fed these MMAs
-        mbar_wait(mma_bar, n_mma & 1);
-        ++n_mma;
-        fence_after();
-        TCL_TS(1)
-        float* dst = part + ((size_t)par * S + r) * slab;
-        for (int mt = 0; mt < MT; ++mt) {
-          const int j = mt * 128 + q * 32 + lane;
+    if (warp == TCL_CELL_WARPS + 4) {
+      // ===================== MMA issue =====================
+      for (int s = 0; s + 1 < L0; ++s)
 #pragma unroll
-          for (int cb = 0; cb < 3; ++cb) {
-            const int col = 24 * hc + 8 * cb;
-            if (col < n_prev) {     // warp-uniform
-              uint32_t m[8], x[8];
-              tmem_ld8(tmD + lane_sel + mt * 2 * TCL_N + col, m);
-              tmem_ld8(tmD + lane_sel + mt * 2 * TCL_N + TCL_N + col, x);
-              tmem_wait_ld();
-              if (j < H) {
+        for (int k = 0; k < BMAXSUB; ++k) {
+          if (s + 1 >= Lk[k]) continue;
+          mbar_wait(dg_bar(k), n_done[k] & 1);       // all eight cell warps staged d(gates) of (k, s)
+          ++n_done[k];
+          fence_after();
+          if (lane == 0) { TCL_TS(2) }
+          const uint32_t idesc = idesc_bf16(128, BN);
+          const uint64_t b1_0 = make_desc(sbase + dG_off + (uint32_t)k * dG_sub, 16, 1024);
+          const uint64_t b2_0 = b1_0 + (uint64_t)(dG_split >> 4), b3_0 = b2_0 + (uint64_t)(dG_split >> 4);
+          if (elect_one()) {
+            for (int mt = 0; mt < MT; ++mt) {
+              const uint32_t d = tmD + (uint32_t)(k * MT + mt) * BN;
+              const uint32_t a1_0 = tm + mt * 64;
+              uint64_t a2_[2], a3_[2];
 #pragma unroll
-                for (int jj = 0; jj < 8; ++jj)
-                  if (col + jj < n_prev)
-                    __stcg(dst + (size_t)(col + jj) * XLD + j, __uint_as_float(m[jj]) + __uint_as_float(x[jj]));
+              for (int a = 0; a < 2; ++a) {
+                a2_[a] = make_desc(sbase + wt_block(0, mt, a), 16, 1024);
+                a3_[a] = make_desc(sbase + wt_block(1, mt, a), 16, 1024);
+              }
+              // smallest terms first: 2^-16 group, 2^-8 group, main
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks) {
+                const int a = ks >> 2;
+                const uint64_t ko = (uint64_t)((a * BSUB_ATOM) >> 4) + 2 * (ks & 3), ka = 2 * (ks & 3);
+                mma_ts(d, a1_0 + ks * 8, b3_0 + ko, idesc, ks > 0 ? 1u : 0u);
+                mma_ss(d, a3_[a] + ka, b1_0 + ko, idesc, 1u);
+                mma_ss(d, a2_[a] + ka, b2_0 + ko, idesc, 1u);
+              }
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks) {
+                const int a = ks >> 2;
+                const uint64_t ko = (uint64_t)((a * BSUB_ATOM) >> 4) + 2 * (ks & 3), ka = 2 * (ks & 3);
+                mma_ts(d, a1_0 + ks * 8, b2_0 + ko, idesc, 1u);
+                mma_ss(d, a2_[a] + ka, b1_0 + ko, idesc, 1u);
+              }
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks) {
+                const uint64_t ko = (uint64_t)(((ks >> 2) * BSUB_ATOM) >> 4) + 2 * (ks & 3);
+                mma_ts(d, a1_0 + ks * 8, b1_0 + ko, idesc, 1u);
+              }
+            }
+            commit(mma_bar(k));
+          }
+          __syncwarp();
+          if (lane == 0) { TCL_TS(3) }
+        }
+      continue;
+    }
+    if (warp >= TCL_CELL_WARPS) {
+      // ===================== writers: partial dh^T of the successor step -> L2 scratch, tick =======
+      // (warps 8..11: TMEM lane quarter = warp & 3)
+      for (int s = 1; s < L0; ++s)
+#pragma unroll
+        for (int k = 0; k < BMAXSUB; ++k) {
+          if (s >= Lk[k]) continue;
+          const int t = dir == 0 ? Lk[k] - 1 - s : s;
+          const int tprev = dir == 0 ? t + 1 : t - 1;            // the step whose d(gates) fed these MMAs
+          // rows of THIS sub-tile alive at tprev (the tile is length-sorted)
+          const int n_prev = min(BSUB, max(0, cnt_s[tprev] - k * BSUB));
+          mbar_wait(mma_bar(k), n_done[k] & 1);
+          ++n_done[k];
+          fence_after();
+          if (lane == 0 && q == 0) { TCL_TS(4) }
+          float* dst = part + (((size_t)k * 2 + (s & 1)) * S + r) * slab;
+          for (int mt = 0; mt < MT; ++mt) {
+            const int j = mt * 128 + q * 32 + lane;
+            uint32_t v0[8], v1[8], v2[8];
+            const uint32_t col = (uint32_t)(k * MT + mt) * BN;
+            tmem_ld8(tmD + lane_sel + col, v0);
+            tmem_ld8(tmD + lane_sel + col + 8, v1);
+            tmem_ld8(tmD + lane_sel + col + 16, v2);
+            tmem_wait_ld();
+            if (j < H) {
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj) {
+                if (jj < n_prev) __stcg(dst + (size_t)jj * XLD + j, __uint_as_float(v0[jj]));
+                if (jj + 8 < n_prev) __stcg(dst + (size_t)(jj + 8) * XLD + j, __uint_as_float(v1[jj]));
+                if (jj + 16 < n_prev) __stcg(dst + (size_t)(jj + 16) * XLD + j, __uint_as_float(v2[jj]));
               }
             }
           }
+          if (lane == 0 && q == 0) { TCL_TS(8) }
+          fence_before();
+          __syncwarp();
+          if (lane == 0) red_release_add(flags + k, 1u);
+          if (lane == 0 && q == 0) { TCL_TS(5) }
         }
-        TCL_TS(8)
-        warp_publish(flag, lane);
-      }
-      TCL_TS(2)
-      // ---- everything the cell backward needs that does not depend on the exchange ----
-      const int off_t = offs_s[t];
-      const int tp = dir == 0 ? t - 1 : t + 1;      // forward-order predecessor (its c is c_prev)
-      float4 gt[6];
-      float ct[6], cp[6], dh[6];
-      bool act[6], rec[6];
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        const int b = warp + 8 * i;
-        act[i] = t < len_c[i];
-        rec[i] = false;
-        ct[i] = 0.f; cp[i] = 0.f; dh[i] = 0.f;
-        gt[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (act[i]) {
-          const size_t row = (size_t)(off_t + b_base + b);
-          gt[i] = *reinterpret_cast<const float4*>(p.gates + row * H8 + gcol);
-          ct[i] = p.c[row * H2 + ycol];
-          const bool hp = dir == 0 ? (t >= 1) : (t + 1 < len_c[i]);
-          if (hp) cp[i] = p.c[(size_t)(offs_s[tp] + b_base + b) * H2 + ycol];
-          if (p.dy) dh[i] = p.dy[row * H2 + ycol];
-          const bool fin = dir == 0 ? (t == len_c[i] - 1) : (t == 0);
-          if (fin && p.dutt) dh[i] += p.dutt[(size_t)orig_c[i] * p.utt_ld + utt_off + u];
-          rec[i] = dir == 0 ? (t + 1 < len_c[i]) : (t >= 1);
-        }
-      }
-      if (s > 0) {
-        // every cell warp of every CTA of the group has published its partials of this step
-        if (lane == 0 && !aborted && !spin_until(flag, (unsigned)(S * TCL_CELL_WARPS * s), p.err)) aborted = true;
-        __syncwarp();
-        TCL_TS(3)
-        // ---- reduce my columns over the S partial blocks (every load in flight at once) ----
-        const float* src = part + (size_t)par * S * slab + u;
-        float v[6][12];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-          const int b = warp + 8 * i;
-#pragma unroll
-          for (int rr = 0; rr < 12; ++rr)
-            v[i][rr] = (act[i] && rec[i] && rr < S) ? __ldcg(src + (size_t)rr * slab + (size_t)b * XLD) : 0.f;
-        }
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-          float sum = 0.f;
-#pragma unroll
-          for (int rr = 0; rr < 12; ++rr) sum += v[i][rr];
-          dh[i] += sum;
-        }
-      }
-      TCL_TS(4)
-      // ---- cell backward; d(gates) -> global (GEMM operand) and -> my B operand (3 bf16 terms) ----
-      float4 dgv[6];
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        const int b = warp + 8 * i;
-        float dig = 0.f, dfg = 0.f, dgg = 0.f, dog = 0.f;
-        if (act[i]) {
-          const float ig = gt[i].x, fg = gt[i].y, gg = gt[i].z, og = gt[i].w;
-          const float tc = fast_tanh(ct[i]);
-          dog = dh[i] * tc * og * (1.f - og);
-          const float dc = dcst[i] + dh[i] * og * (1.f - tc * tc);
-          dig = dc * gg * ig * (1.f - ig);
-          dfg = dc * cp[i] * fg * (1.f - fg);
-          dgg = dc * ig * (1.f - gg * gg);
-          dcst[i] = dc * fg;
-        }
-        dgv[i] = make_float4(dig, dfg, dgg, dog);
-        if (s + 1 < L) {
-          uint32_t a[4], bb[4], cc[4];
-          split3(dig, a[0], bb[0], cc[0]);
-          split3(dfg, a[1], bb[1], cc[1]);
-          split3(dgg, a[2], bb[2], cc[2]);
-          split3(dog, a[3], bb[3], cc[3]);
-          // row b of the K-major operand, k = 4*ul .. 4*ul+3
-          const uint32_t o = dG_off + (uint32_t)(ul >> 4) * B_ATOM + (uint32_t)(b >> 3) * 1024 +
-                             (uint32_t)(b & 7) * 128 + (uint32_t)((((ul & 15) >> 1) ^ (b & 7)) << 4) +
-                             (uint32_t)(ul & 1) * 8;
-          *reinterpret_cast<uint2*>(sptr + o) = make_uint2(a[0] | (a[1] << 16), a[2] | (a[3] << 16));
-          *reinterpret_cast<uint2*>(sptr + o + dG_split) = make_uint2(bb[0] | (bb[1] << 16), bb[2] | (bb[3] << 16));
-          *reinterpret_cast<uint2*>(sptr + o + 2 * dG_split) = make_uint2(cc[0] | (cc[1] << 16), cc[2] | (cc[3] << 16));
-        }
-      }
-      if (s + 1 < L) {
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(dg_bar);
-      }
-      TCL_TS(5)
-      // the GEMM operand copy of d(gates): nobody inside this launch waits for it
-#pragma unroll
-      for (int i = 0; i < 6; ++i)
-        if (act[i])
-          *reinterpret_cast<float4*>(p.gates + (size_t)(off_t + b_base + warp + 8 * i) * H8 + gcol) = dgv[i];
-      if (s + 1 < L && warp < n_issuers) {
-        // ---- issue the MMAs of my accumulator: (M tile warp/2, main | cross) ----
-        mbar_wait(dg_bar, n_dg & 1);          // all eight warps' d(gates) are in shared memory
-        fence_after();
-        const int mt = warp >> 1;
-        const bool cross = (warp & 1) != 0;
-        const int Nmma = (cnt_s[t] + 15) & ~15;
-        const uint32_t idesc = idesc_bf16(128, Nmma);
-        const uint32_t d_acc = tmD + mt * 2 * TCL_N + (cross ? TCL_N : 0);
-        const uint64_t b_0 = make_desc(sbase + dG_off, 16, 1024);
-        if (elect_one()) {
-#pragma unroll
-          for (int a = 0; a < 2; ++a) {
-            const uint64_t b1a = b_0 + (uint64_t)((a * B_ATOM) >> 4);
-            const uint64_t b2a = b1a + (uint64_t)(dG_split >> 4), b3a = b2a + (uint64_t)(dG_split >> 4);
-            const uint64_t a2a = make_desc(sbase + wt_block(0, mt, a), 16, 1024);
-            const uint64_t a3a = make_desc(sbase + wt_block(1, mt, a), 16, 1024);
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              const int ks = a * 4 + kk;
-              const uint32_t a1 = tm + mt * 64 + ks * 8;
-              if (cross) {
-                mma_ts(d_acc, a1, b3a + 2 * kk, idesc, ks > 0 ? 1u : 0u);    // 2^-16 terms first
-                mma_ss(d_acc, a3a + 2 * kk, b1a + 2 * kk, idesc, 1u);
-                mma_ss(d_acc, a2a + 2 * kk, b2a + 2 * kk, idesc, 1u);
-                mma_ts(d_acc, a1, b2a + 2 * kk, idesc, 1u);                  // 2^-8 terms
-                mma_ss(d_acc, a2a + 2 * kk, b1a + 2 * kk, idesc, 1u);
-              } else {
-                mma_ts(d_acc, a1, b1a + 2 * kk, idesc, ks > 0 ? 1u : 0u);
-              }
-            }
-          }
-          commit(mma_bar);
-        }
-        __syncwarp();
-      }
-      if (s + 1 < L) ++n_dg;
-      TCL_TS(6)
+      continue;
     }
+
+    // ===================== cell warps: lane = local unit, warp w owns rows w, w + 8, w + 16 of a sub-tile ====
+    const int ul = lane, u = r * TCL_UNITS + ul;
+    const bool u_ok = u < H;
+    const int gcol = dir * 4 * H + u * 4;
+    const int ycol = dir * H + u;
+    const int utt_off = dir == 0 ? p.utt_off0 : p.utt_off1;
+    float dcst[BMAXSUB][3];
+    int len_c[BMAXSUB][3], orig_c[BMAXSUB][3];
+#pragma unroll
+    for (int k = 0; k < BMAXSUB; ++k)
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        dcst[k][i] = 0.f;
+        const int b = k * BSUB + warp + 8 * i;
+        len_c[k][i] = u_ok ? lens_s[b] : 0;
+        orig_c[k][i] = orig_s[b];
+      }
+
+    for (int s = 0; s < L0; ++s)
+#pragma unroll
+      for (int k = 0; k < BMAXSUB; ++k) {
+        if (s >= Lk[k]) continue;
+        const int t = dir == 0 ? Lk[k] - 1 - s : s;
+        if (tid == 0) { TCL_TS(0) }
+        // ---- everything the cell backward needs that does not depend on the exchange ----
+        const int off_t = offs_s[t];
+        const int tp = dir == 0 ? t - 1 : t + 1;      // forward-order predecessor (its c is c_prev)
+        float4 gt[3];
+        float ct[3], cp[3], dh[3];
+        bool act[3], rec[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const int b = k * BSUB + warp + 8 * i;
+          act[i] = t < len_c[k][i];
+          rec[i] = false;
+          ct[i] = 0.f; cp[i] = 0.f; dh[i] = 0.f;
+          gt[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (act[i]) {
+            const size_t row = (size_t)(off_t + b_base + b);
+            gt[i] = *reinterpret_cast<const float4*>(p.gates + row * H8 + gcol);
+            ct[i] = p.c[row * H2 + ycol];
+            const bool hp = dir == 0 ? (t >= 1) : (t + 1 < len_c[k][i]);
+            if (hp) cp[i] = p.c[(size_t)(offs_s[tp] + b_base + b) * H2 + ycol];
+            if (p.dy) dh[i] = p.dy[row * H2 + ycol];
+            const bool fin = dir == 0 ? (t == len_c[k][i] - 1) : (t == 0);
+            if (fin && p.dutt) dh[i] += p.dutt[(size_t)orig_c[k][i] * p.utt_ld + utt_off + u];
+            rec[i] = dir == 0 ? (t + 1 < len_c[k][i]) : (t >= 1);
+          }
+        }
+        if (s > 0) {
+          mbar_wait(part_bar(k), n_done[k] & 1);   // every CTA's partials of (k, s) are in L2
+          ++n_done[k];
+          if (tid == 0) { TCL_TS(6) }
+          // ---- reduce my columns over the S partial blocks (all loads in flight at once) ----
+          const float* src = part + ((size_t)k * 2 + (s & 1)) * S * slab + u;
+          float v[3][12];
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const int n = warp + 8 * i;
+#pragma unroll
+            for (int rr = 0; rr < 12; ++rr)
+              v[i][rr] = (act[i] && rec[i] && rr < S) ? __ldcg(src + (size_t)rr * slab + (size_t)n * XLD) : 0.f;
+          }
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            float sum = 0.f;
+#pragma unroll
+            for (int rr = 0; rr < 12; ++rr) sum += v[i][rr];
+            dh[i] += sum;
+          }
+        }
+        // ---- cell backward; d(gates) -> my rows of the sub-tile's B operand (3 bf16 terms) ----
+        const bool more = s + 1 < Lk[k];
+        float4 dgv[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const int n = warp + 8 * i;
+          float dig = 0.f, dfg = 0.f, dgg = 0.f, dog = 0.f;
+          if (act[i]) {
+            const float ig = gt[i].x, fg = gt[i].y, gg = gt[i].z, og = gt[i].w;
+            const float tc = fast_tanh(ct[i]);
+            dog = dh[i] * tc * og * (1.f - og);
+            const float dc = dcst[k][i] + dh[i] * og * (1.f - tc * tc);
+            dig = dc * gg * ig * (1.f - ig);
+            dfg = dc * cp[i] * fg * (1.f - fg);
+            dgg = dc * ig * (1.f - gg * gg);
+            dcst[k][i] = dc * fg;
+          }
+          dgv[i] = make_float4(dig, dfg, dgg, dog);
+          if (more) {
+            uint32_t a[4], bb[4], cc[4];
+            split3(dig, a[0], bb[0], cc[0]);
+            split3(dfg, a[1], bb[1], cc[1]);
+            split3(dgg, a[2], bb[2], cc[2]);
+            split3(dog, a[3], bb[3], cc[3]);
+            // row n of the K-major operand, k = 4*ul .. 4*ul+3
+            const uint32_t o = dG_off + (uint32_t)k * dG_sub + (uint32_t)(ul >> 4) * BSUB_ATOM +
+                               (uint32_t)(n >> 3) * 1024 + (uint32_t)(n & 7) * 128 +
+                               (uint32_t)((((ul & 15) >> 1) ^ (n & 7)) << 4) + (uint32_t)(ul & 1) * 8;
+            *reinterpret_cast<uint2*>(sptr + o) = make_uint2(a[0] | (a[1] << 16), a[2] | (a[3] << 16));
+            *reinterpret_cast<uint2*>(sptr + o + dG_split) = make_uint2(bb[0] | (bb[1] << 16), bb[2] | (bb[3] << 16));
+            *reinterpret_cast<uint2*>(sptr + o + 2 * dG_split) = make_uint2(cc[0] | (cc[1] << 16), cc[2] | (cc[3] << 16));
+          }
+        }
+        if (more) {
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(dg_bar(k));
+        }
+        if (tid == 0) { TCL_TS(7) }
+        // the GEMM operand copy of d(gates): nobody inside this launch waits for it
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+          if (act[i])
+            *reinterpret_cast<float4*>(p.gates + (size_t)(off_t + b_base + k * BSUB + warp + 8 * i) * H8 + gcol) = dgv[i];
+      }
   }
 #undef TCL_TS
   fence_before();
@@ -766,7 +841,7 @@ int tcl_make_plan(int B, int H, int Tmax, TclPlan* pl) {
   pl->smem_fwd = 1024 + (size_t)MAXSUB * (2 * KA * SUB_ATOM + STAGE_BYTES) + misc;
   const int rows_last = ((H - 128 * (MT - 1)) + 7) & ~7;
   pl->smem_bwd = 1024 + (size_t)4 * rows_last * 128 + (size_t)(2 * (MT - 1) * 2) * A_ATOM +
-                 (size_t)3 * 2 * B_ATOM + misc;
+                 (size_t)BMAXSUB * 3 * 2 * BSUB_ATOM + misc;
   if (pl->smem_fwd > 232448 || pl->smem_bwd > 232448) return MMDA_ERR_UNSUPPORTED;
   // workspace: [err (256 B)] [flags fwd+bwd 2*2*NT u32, padded] [exchange / partial scratch]
   pl->flag_off = 256;
@@ -774,7 +849,7 @@ int tcl_make_plan(int B, int H, int Tmax, TclPlan* pl) {
   pl->xch_off = pl->flag_off + flag_bytes;
   const size_t XLD = (size_t)S * TCL_UNITS;
   const size_t fwd_x = (size_t)2 * NT * MAXSUB * 2 * (2 * KA * SUB_ATOM);
-  const size_t bwd_x = (size_t)2 * NT * 2 * S * TCL_N * XLD * 4;
+  const size_t bwd_x = (size_t)2 * NT * BMAXSUB * 2 * S * BSUB * XLD * 4;
   pl->total = pl->xch_off + (fwd_x > bwd_x ? fwd_x : bwd_x);
   return MMDA_OK;
 }
@@ -838,7 +913,7 @@ static int tcl_launch(bool bwd, TclArgs& a, int B, int H, int Tmax, void* ws, cu
   const size_t smem = bwd ? pl.smem_bwd : pl.smem_fwd;
   auto kern = bwd ? lstm_tc_bwd_kernel : lstm_tc_fwd_kernel;
   MMDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<2 * pl.S * pl.G, bwd ? TCL_BWD_THREADS : TCL_FWD_THREADS4, smem, stream>>>(a);
+  kern<<<2 * pl.S * pl.G, bwd ? TCL_BWD_THREADS4 : TCL_FWD_THREADS4, smem, stream>>>(a);
   MMDA_CHECK_LAUNCH();
   return MMDA_OK;
 }
