@@ -27,6 +27,13 @@ SEQ, BATCH, VOCAB = 50, 256, 20000     # BASELINE configs[1]; --seq / --batch ov
 METRIC, UNIT = "train_samples_per_sec", "samples/s"
 
 
+def workload(batch, lengths):
+    """One string for both arms (the driver compares the arms' `config`)."""
+    return (f"MOSEI-shape synthetic (BASELINE configs[1]): 300/35/74-d, seq {SEQ}, batch {batch}/GPU, "
+            f"vocab {VOCAB}, lengths={lengths}, train mode (dropout on), fused step: fwd + 6 losses + "
+            "bwd + clip + Adam")
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -94,7 +101,9 @@ def dist_setup(n_gpus):
 # ------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference's PyTorch CPU path, all host threads
 # ------------------------------------------------------------------------------------------
-def cpu_steps(steps, warmup, budget_s=150.0, batch=BATCH):
+def cpu_steps(steps, warmup, budget_s=150.0, batch=BATCH, lengths="full"):
+    """The oracle port of the reference's PyTorch CPU path on all host threads, on the SAME batch
+    size as the GPU arm.  A slow host shortens the sample (fewer steps), never the workload."""
     from mmda_b200.config import mosei_config
     from mmda_b200.synthetic import batch_for
     from oracle.misa_oracle import oracle_build, oracle_optimizer, oracle_step
@@ -103,13 +112,14 @@ def cpu_steps(steps, warmup, budget_s=150.0, batch=BATCH):
     cfg = mosei_config(vocab_size=VOCAB, batch_size=batch)
     model = oracle_build(cfg, 1234).train()
     opt = oracle_optimizer(model, cfg)
-    b = batch_for(cfg, seed=1234, lengths="full", seq_len=SEQ)
+    b = batch_for(cfg, seed=1234, lengths=lengths, seq_len=SEQ)
     t0 = time.perf_counter()
-    oracle_step(model, b, cfg, opt)
+    oracle_step(model, b, cfg, opt)              # first step = warm-up no. 1
     first = time.perf_counter() - t0
-    sample = f"{steps} steps of the batch-{batch} seq-{SEQ} step after {warmup} warm-up"
-    if first * (steps + warmup) > budget_s and batch > 32:
-        return cpu_steps(steps, warmup, budget_s, batch // 4)
+    want = steps
+    if first * (steps + warmup) > budget_s:
+        warmup = 1
+        steps = max(1, int(budget_s / max(first, 1e-9)) - 1)
     for _ in range(max(0, warmup - 1)):
         oracle_step(model, b, cfg, opt)
     ts = []
@@ -118,25 +128,161 @@ def cpu_steps(steps, warmup, budget_s=150.0, batch=BATCH):
         oracle_step(model, b, cfg, opt)
         ts.append(time.perf_counter() - t0)
     tot = sum(ts)
+    sample = f"{steps} steps of the batch-{batch} seq-{SEQ} step after {max(1, warmup)} warm-up"
+    if steps != want:
+        sample += f" ({want} requested; shortened to fit {budget_s:.0f} s of CPU time)"
     return {"value": batch * steps / tot, "unit": UNIT, "cores": torch.get_num_threads(),
-            "kind": "port", "sample": sample, "ms_per_step": 1e3 * tot / steps, "batch": batch}
+            "kind": "port", "sample": sample, "ms_per_step": 1e3 * tot / steps, "batch": batch,
+            "steps": steps}
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    cb = cpu_steps(args.steps, args.warmup)
+    cb = cpu_steps(args.steps, args.warmup, batch=args.batch, lengths=args.lengths)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT,
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "n_gpus": args.gpus, "steps": cb["steps"], "warmup": args.warmup,
             "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"MOSEI-shape synthetic 300/35/74-d seq {SEQ} batch {cb['batch']} "
-                                   "(reference PyTorch CPU path via the oracle port; /root/reference "
-                                   "is not on the GPU box)"},
+            "config": {"workload": workload(args.batch, args.lengths),
+                       "global_batch": args.batch, "parallelism": "cpu",
+                       "note": "reference PyTorch CPU path via the oracle port (the Python reference "
+                               "cannot travel to the GPU box); one process, all host threads"},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def roofline_block(cfg, batch0, kdur, clk, args):
+    """Roofline of the text-encoder recurrence launch that takes longest (forward or BPTT).
+    Everything is derived from the live plan and the live timing; DRAM traffic comes from the
+    committed ncu capture when one exists for this exact shape (else null)."""
+    import ctypes
+    from mmda_b200._lib import LIB
+    timed = {k: v for k, v in kdur.items() if v}
+    if not timed:
+        return None
+    kname = max(timed, key=timed.get)
+    tc = "_tc_" in kname
+    bwd = kname.endswith("backward")
+    H = cfg.embedding_size
+    ntok = int(batch0.lengths.sum())
+    Tmax = int(batch0.lengths.max())
+    dur = timed[kname] * 1e-3
+    peak, peak_src, pk = peaks()
+    sm_hz = ((clk or {}).get("sm_mhz") or 1965.0) * 1e6
+    fma_peak = 148 * 128 * 2 * sm_hz / 1e12
+    tensor_peak = pk.get("bf16_tflops_sustained", 1403.9)
+    alg_bytes = 2 * 10 * H * 4 * ntok              # both directions, 10H fp32 words per token (M3)
+    flops = 2 * 2 * 4 * H * H * ntok               # recurrent MACs * 2, both directions (M3)
+    bounds_us = {"hbm": alg_bytes / (peak * 1e9) * 1e6, "fp32_fma": flops / (fma_peak * 1e12) * 1e6}
+    plan = {}
+    if tc:
+        arr = (ctypes.c_int * 8)()
+        LIB.call("mmda_lstm_tc_plan", args.batch, H, Tmax, arr)
+        plan = dict(zip(("slices", "groups", "batch_tile", "tiles", "k_padded", "smem_fwd", "smem_bwd",
+                         "ctas"), list(arr)))
+        terms = 6 if bwd else 3                    # bf16x3 (6 products) backward, fp16x2 (3) forward
+        issued = flops * terms
+        bounds_us["tensor"] = issued / (tensor_peak * 1e12) * 1e6
+    else:
+        arr = (ctypes.c_int * 6)()
+        LIB.call("mmda_lstm_plan", args.batch, H, arr)
+        plan = dict(zip(("cluster", "units_per_cta", "batch_tile", "tiles", "smem_fwd", "smem_bwd"), list(arr)))
+        plan["ctas"] = 2 * plan["cluster"] * plan["tiles"]
+        warps = (plan["units_per_cta"] + 7) // 8 * (plan["batch_tile"] // 8)
+        lds = 1536.0 * ((H + 3) // 4) * warps * plan["ctas"] * Tmax   # operand bytes smem -> registers
+        bounds_us["smem"] = lds / (148 * 128 * sm_hz) * 1e6
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp):
+        key = f"{kname}:B{args.batch}:T{Tmax}:H{H}:{args.lengths}"
+        ent = json.load(open(tp)).get(key)
+        if ent:
+            traffic, traffic_src = ent["dram_bytes"], ent["source"]
+    m2 = max(bounds_us, key=bounds_us.get)         # the roofline that bounds this launch (M2 ii: the max)
+    out = {"kernel": kname + f" (text encoder, H={H}, both directions, {ntok} tokens)",
+           "bound": "tensor" if tc else "hbm",
+           "achieved": (flops / dur / 1e12) if tc else (alg_bytes / dur / 1e9),
+           "peak": tensor_peak if tc else peak, "unit": "TFLOP/s" if tc else "GB/s",
+           "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if tc else peak_src,
+           "traffic": traffic, "traffic_source": traffic_src,
+           "algorithmic_bytes": alg_bytes, "algorithmic_flops": flops,
+           "launch_ms": timed[kname], "launch_ms_all": timed, "plan": plan,
+           "roofline_time_us": bounds_us, "binding_roofline": m2,
+           "frac_of_binding_roofline": bounds_us[m2] * 1e-6 / dur,
+           "hbm": {"achieved_gbs": alg_bytes / dur / 1e9, "peak_gbs": peak,
+                   "frac": alg_bytes / dur / 1e9 / peak, "peak_source": peak_src},
+           "fp32_fma": {"achieved_tflops": flops / dur / 1e12, "peak_tflops": fma_peak,
+                        "frac": flops / dur / 1e12 / fma_peak,
+                        "peak_source": "148 SM x 128 FMA/clk x 2 x sampled SM clock"}}
+    out["frac"] = out["achieved"] / out["peak"]
+    if tc:
+        out["tensor_issued"] = {"achieved_tflops": flops * terms / dur / 1e12, "peak_tflops": tensor_peak,
+                                "frac": flops * terms / dur / 1e12 / tensor_peak,
+                                "terms_per_product": terms}
+        out["note"] = ("tensor-core recurrence: fp32-accurate operand splits (3 MMAs per product forward, "
+                       "6 backward); a time step is a serial chain of MMA -> cell update -> L2 exchange, so "
+                       "the launch is latency-bound: `frac` (algorithmic flops vs the tensor peak) is small by "
+                       "construction, `fp32_fma.frac` compares with the best a SIMT fp32 kernel could do "
+                       "(SURVEY M2 ii), and frac_of_binding_roofline with the largest of the rooflines")
+    else:
+        out["note"] = "SIMT recurrence: bound by shared-memory operand delivery and fp32 FMA issue, not HBM"
+    return out
+
+
+def dp_check(dist, pg, rank, world, dev):
+    """Data-parallel parity evidence for the driver (the 2-GPU pytest is skipped on 1-GPU boxes):
+    one eval-mode step of a small global batch sharded over all ranks vs the same batch on rank 0
+    alone (kernel path) and vs the CPU oracle (losses)."""
+    from mmda_b200 import MISA, mosei_config
+    from mmda_b200.synthetic import batch_for
+    from mmda_b200.trainer import FusedTrainer, LOSS_NAMES
+    per = 32
+    cfg = mosei_config(vocab_size=500, batch_size=per * world, use_confidNet=True)
+    full = batch_for(cfg, seed=77, lengths="ragged", seq_len=20)
+
+    def make():
+        torch.manual_seed(5)
+        m = MISA(cfg)
+        for n, p in m.named_parameters():
+            if "weight_hh" in n:
+                torch.nn.init.orthogonal_(p)
+        return m
+
+    def run(tr, b):
+        L = tr.forward_backward(b.sentences.to(dev), b.visual.to(dev), b.acoustic.to(dev), b.lengths,
+                                b.labels.to(dev))
+        torch.cuda.synchronize()
+        return L[:6].clone()
+
+    tr_dp = FusedTrainer(make().to(dev).eval(), process_group=pg, use_graph=False)
+    L_dp = run(tr_dp, full.slice(rank * per, (rank + 1) * per))
+    out = None
+    if rank == 0:
+        tr_1 = FusedTrainer(make().to(dev).eval(), use_graph=False)
+        L_1 = run(tr_1, full)
+        na = tr_1.n_active
+        g1, gd = tr_1.g_arena[:na], tr_dp.g_arena[:na]
+        out = {"global_batch": per * world, "ranks": world,
+               "loss_max_rel_vs_single_gpu": float(((L_dp - L_1).abs() / L_1.abs().clamp_min(1e-6)).max()),
+               "grad_max_err_over_max_vs_single_gpu": float((gd - g1).abs().max() / g1.abs().max()),
+               "grad_norm_dp": float(gd.norm()), "grad_norm_single_gpu": float(g1.norm())}
+        try:
+            from oracle.misa_oracle import OracleMISA, oracle_step
+            ref = OracleMISA(cfg)
+            ref.load_state_dict({k: v.detach().cpu() for k, v in make().state_dict().items()})
+            ref.eval()
+            _, L, grads = oracle_step(ref, full, cfg, None)
+            lo = torch.tensor([float(L[k]) for k in LOSS_NAMES[:6]])
+            out["loss_max_rel_vs_cpu_oracle"] = float(((L_dp.cpu() - lo).abs() / lo.abs().clamp_min(1e-6)).max())
+            gn = torch.sqrt(sum((g.double() ** 2).sum() for g in grads.values() if g is not None))
+            out["grad_norm_cpu_oracle"] = float(gn)
+        except Exception as e:      # the oracle is a checker: report, do not fail the bench
+            out["oracle_error"] = repr(e)[:200]
+    tr_dp.close()
+    return out
 
 
 # ------------------------------------------------------------------------------------------
@@ -179,6 +325,8 @@ def run_ours(args):
             dist.barrier(device_ids=[local])
         torch.cuda.synchronize()
 
+    dp = dp_check(dist, pg, rank, world, dev) if world > 1 else None
+
     # ---- warm-up (also captures the CUDA graph of the step on a single GPU) ----
     for i in range(max(3, args.warmup) + 2):
         tr.step(*devb[i % nb])
@@ -216,19 +364,17 @@ def run_ours(args):
 
     # ---- per-launch timing of the dominant kernel (text-encoder LSTM recurrence), live, with
     # CUDA events on the launching stream; eager launches (a graph replay hides the launches) ----
-    kt = {"mmda_lstm_forward": [], "mmda_lstm_backward": []}
+    H_POS = {"mmda_lstm_forward": -3, "mmda_lstm_backward": -2,          # (.., B, H, Tmax[, save])
+             "mmda_lstm_tc_forward": -4, "mmda_lstm_tc_backward": -3}     # (.., B, H, Tmax[, save], ws)
+    kt = {k: [] for k in H_POS}
     orig_c = eng.k._c
 
     def timed_c(name, *a):
-        if name not in kt:
+        if name not in kt or a[H_POS[name]] != cfg.embedding_size:       # text encoder only
             return orig_c(name, *a)
-        h_arg = a[-3] if name == "mmda_lstm_forward" else a[-2]   # (.., B, H, Tmax[, save])
-        if h_arg == cfg.embedding_size:                            # text encoder only
-            e_a, e_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e_a.record(); orig_c(name, *a); e_b.record()
-            kt[name].append((e_a, e_b))
-        else:
-            orig_c(name, *a)
+        e_a, e_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e_a.record(); orig_c(name, *a); e_b.record()
+        kt[name].append((e_a, e_b))
 
     eng.k._c = timed_c
     tr.use_graph = False
@@ -238,6 +384,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     tr.use_graph = graph_on
     eng.k._c = orig_c
+    eng.lstm_tc_check()
     kdur = {k: (sum(a.elapsed_time(b) for a, b in v) / len(v) if v else None) for k, v in kt.items()}
 
     # ---- e2e: public API with host buffers, H2D + D2H inside the timed region ----
@@ -264,59 +411,23 @@ def run_ours(args):
         if dist is not None:
             dist.destroy_process_group()
         return
-    # ---- roofline of the dominant kernel (SURVEY.md section 8d, M3) ----
-    H = cfg.embedding_size
-    ntok = int(host[0].lengths.sum())
-    peak, peak_src, pk = peaks()
-    roof = None
-    kname = max((k for k in kdur if kdur[k]), key=lambda k: kdur[k], default=None)
-    if kname:
-        alg_bytes = 2 * 10 * H * 4 * ntok          # both directions, 10H fp32 words per token
-        flops = 2 * 2 * 4 * H * H * ntok           # recurrent MACs*2, both directions
-        dur = kdur[kname] * 1e-3
-        sm_hz = ((clk or {}).get("sm_mhz") or 1965.0) * 1e6
-        fma_peak = 148 * 128 * 2 * sm_hz / 1e12
-        # operand bytes the mat-vec delivers from shared memory into registers per launch:
-        # per warp-iteration one float4 of W_hh + two float4 of h per lane (1536 B), x (K/4)
-        # iterations x warps x CTAs x steps (csrc/lstm.cu plan for H=300, B=256: 25 warps,
-        # 75 iterations, 112 CTAs, seq steps)
-        lds_bytes = 1536.0 * 75 * 25 * 112 * SEQ
-        smem_peak = 148 * 128 * sm_hz / 1e12       # TB/s
-        # DRAM traffic per launch from the committed ncu --set full capture of this kernel
-        traffic = {"mmda_lstm_forward": 127.62e6 + 148.93e6, "mmda_lstm_backward": 160.05e6 + 90.63e6}[kname]
-        roof = {"kernel": kname + " (text encoder, H=300, both directions)", "bound": "hbm",
-                "achieved": alg_bytes / dur / 1e9, "peak": peak, "unit": "GB/s",
-                "frac": alg_bytes / dur / 1e9 / peak, "peak_source": peak_src,
-                "traffic": traffic, "traffic_source": "profiles/r01_ncu_full_lstm_text_bt40.txt "
-                                                       "(dram__bytes_read.sum + dram__bytes_write.sum, one launch)",
-                "algorithmic_bytes": alg_bytes,
-                "launch_ms": kdur[kname], "launch_ms_fwd": kdur["mmda_lstm_forward"],
-                "launch_ms_bwd": kdur["mmda_lstm_backward"],
-                "note": "the recurrence is bound by shared-memory operand delivery and fp32 FMA issue "
-                        "(sequential dependence), not by HBM: see smem_operand and fp32_fma",
-                "smem_operand": {"achieved_tbs": lds_bytes / dur / 1e12, "peak_tbs": smem_peak,
-                                 "frac": lds_bytes / dur / 1e12 / smem_peak,
-                                 "peak_source": "148 SM x 128 B/clk x sampled SM clock"},
-                "fp32_fma": {"achieved_tflops": flops / dur / 1e12, "peak_tflops": fma_peak,
-                             "frac": flops / dur / 1e12 / fma_peak,
-                             "peak_source": "148 SM x 128 FMA/clk x 2 x sampled SM clock"}}
+    # ---- roofline of the dominant kernel (SURVEY.md section 8d, M2/M3) ----
+    roof = roofline_block(cfg, host[0], kdur, clk, args)
     cb = None
     if world == 1 and not args.no_cpu:
-        cb = cpu_steps(3, 1, budget_s=40.0)
+        cb = cpu_steps(3, 1, budget_s=40.0, batch=args.batch, lengths=args.lengths)
         cb = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "bf16",
             "data": "synthetic",
-            "config": {"workload": f"MOSEI-shape synthetic (BASELINE configs[1]): 300/35/74-d, seq {SEQ}, "
-                                   f"batch {args.batch}/GPU, vocab {VOCAB}, lengths={args.lengths}, train mode "
-                                   "(dropout on), fused step: fwd + 6 losses + bwd + clip + Adam",
+            "config": {"workload": workload(args.batch, args.lengths),
                        "global_batch": world * args.batch, "parallelism": f"dp{world}",
                        "l2": "256 MiB memset between steps inside the timed region; per-step working "
                              "set (~0.6 GB of activations) also exceeds the 126 MB L2"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32},
             "gpu_launches": launches, "cuda_graph": graph_on, "host_enqueue_ms_per_step": host_ms,
-            "clocks": clk, "roofline": roof, "cpu_baseline": cb,
+            "clocks": clk, "roofline": roof, "cpu_baseline": cb, "dp_check": dp,
             "losses": dict(zip(LOSS_NAMES, last[:6])), "lib": os.path.basename(LIB.load()._name)}
     sys.stdout.flush()
     os.write(real_stdout, (json.dumps(line) + "\n").encode())

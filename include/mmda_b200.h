@@ -85,6 +85,10 @@ int mmda_gemm_tc(int kind, int a_mn, int b_mn, int M, int N, int K, const void* 
 /* A/B knob: 2 = persistent tile loop, dynamic tile scheduler, epilogue overlapped with the next
  * tile's MMAs (default); 1 = one output tile per CTA. */
 int mmda_gemm_tc_set_version(int version);
+/* tile-scheduler slots owned by launches recorded into CUDA graphs: returns the number in use;
+ * release_to >= 0 first hands back the slots [release_to, in use) (the graphs recorded since that
+ * mark must be destroyed).  release_to = -1 only queries. */
+int mmda_gemm_tc_graph_slots(int release_to);
 int mmda_split_tf32(const float* x, int ldx, int rows, int cols, float* hi, float* lo, int ldo,
                     mmda_stream_t stream);
 int mmda_cast_bf16(const float* x, int ldx, int rows, int cols, void* out, int ldo,

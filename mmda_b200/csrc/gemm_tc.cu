@@ -827,6 +827,14 @@ int* next_sched_slot(cudaStream_t stream) {
 
 extern "C" {
 
+// Scheduler slots handed to launches recorded into CUDA graphs: returns how many are in use.  With
+// release_to >= 0 the slots [release_to, in use) are handed back first -- the caller guarantees that
+// every graph recorded since its mark (= the value returned before its capture) is destroyed.
+int mmda_gemm_tc_graph_slots(int release_to) {
+  if (release_to >= 0 && release_to <= g_sched_graph_next) g_sched_graph_next = release_to;
+  return g_sched_graph_next;
+}
+
 // A/B knob: 2 = persistent tile loop with overlapped epilogue (default), 1 = one tile per CTA
 int mmda_gemm_tc_set_version(int v) {
   MMDA_REQUIRE(v == 1 || v == 2, "gemm_tc: version must be 1 or 2");

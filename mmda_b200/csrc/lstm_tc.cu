@@ -913,7 +913,20 @@ static int tcl_launch(bool bwd, TclArgs& a, int B, int H, int Tmax, void* ws, cu
   const size_t smem = bwd ? pl.smem_bwd : pl.smem_fwd;
   auto kern = bwd ? lstm_tc_bwd_kernel : lstm_tc_fwd_kernel;
   MMDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<2 * pl.S * pl.G, bwd ? TCL_BWD_THREADS4 : TCL_FWD_THREADS4, smem, stream>>>(a);
+  // The CTAs of a group wait on one another (flags in L2), so every CTA of the grid must be
+  // resident at the same time: a cooperative launch makes the driver guarantee exactly that (it
+  // refuses the launch otherwise) instead of relying on the grid being smaller than the chip.
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pl.S * pl.G, 1, 1);
+  cfg.blockDim = dim3(bwd ? TCL_BWD_THREADS4 : TCL_FWD_THREADS4, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  MMDA_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
   MMDA_CHECK_LAUNCH();
   return MMDA_OK;
 }

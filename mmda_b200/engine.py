@@ -190,9 +190,13 @@ class MisaEngine:
         for s in shape:
             n *= s
         if t is None or t.numel() < n or t.dtype != dtype or t.device != dev:
+            if t is not None:
+                # a captured CUDA graph may hold this buffer's raw pointer: replacing it (growth,
+                # dtype, device) invalidates the graph; a buffer under a NEW name cannot be
+                # referenced by any existing graph
+                self.ws_version += 1
             t = torch.empty(max(n, 1), dtype=dtype, device=dev)
             self.ws[name] = t
-            self.ws_version += 1        # captured CUDA graphs hold raw pointers into the workspace
         v = t[:n].view(*shape)
         if zero:
             v.zero_()
@@ -913,7 +917,7 @@ class MisaEngine:
         dY1 = self.buf(f"dY1_{m}", N, 2 * H)
         use_side = self.multi_stream and not _DRYRUN
         cur = torch.cuda.current_stream() if use_side else None
-        side = self._wgrad_stream(m) if use_side else None
+        side_used = []
         G_real = G
         if self.gru:
             P = {**P, **self._gru_overlay(m, P, "weights")}      # expanded by the forward
@@ -956,7 +960,9 @@ class MisaEngine:
             else:
                 Wst = (self.buf(f"Wst_{r}", 8 * H, I), None)      # written by the forward
 
-            def wgrad(r=r, Gt=Gt, Y=Y, Xin=Xin, tc=tc, I=I):
+            hp_box = {}
+
+            def wgrad_common(r=r, Y=Y, tc=tc):
                 if self.gru:
                     for suf in ("", "_reverse"):
                         for kk in self._RNN_KEYS:
@@ -964,39 +970,57 @@ class MisaEngine:
                 HP = self.buf(f"HP_{r}", N, 2 * H)
                 k._c("mmda_lstm_shift_h", _ptr(Y), _ptr(HP), _ptr(pk["row_t"]), _ptr(pk["row_j"]),
                      _ptr(pk["lens"]), _ptr(pk["off"]), N, H)
+                hp_box["HP"] = HP
                 if tc:
-                    HPp = self._prep(f"tcHP_{r}", HP, kind=0)
+                    hp_box["HPp"] = self._prep(f"tcHP_{r}", HP, kind=0)
+
+            def wgrad_dir(di, r=r, Gt=Gt, Xin=Xin, tc=tc, I=I):
                 # dG columns are gate-interleaved (u*4+g): c_ilv=H stores row u*4+g at g*H+u
-                for di, suf in enumerate(("", "_reverse")):
-                    dG = Gt[:, di * 4 * H:(di + 1) * 4 * H]
-                    if tc:   # contract over tokens: both operands MN-major, auto split-K
-                        dGd = self._cols(dGp, di * 4 * H, (di + 1) * 4 * H)
-                        k.gemm_tc(0, 1, 1, 4 * H, I, N, dGd, Xp, G[f"{r}.weight_ih_l0{suf}"], mode=1,
+                suf = ("", "_reverse")[di]
+                HP = hp_box["HP"]
+                dG = Gt[:, di * 4 * H:(di + 1) * 4 * H]
+                if tc:   # contract over tokens: both operands MN-major, auto split-K
+                    dGd = self._cols(dGp, di * 4 * H, (di + 1) * 4 * H)
+                    k.gemm_tc(0, 1, 1, 4 * H, I, N, dGd, Xp, G[f"{r}.weight_ih_l0{suf}"], mode=1,
+                              split_k=0, c_ilv=H)
+                    k.gemm_tc(0, 1, 1, 4 * H, H, N, dGd, self._cols(hp_box["HPp"], di * H, (di + 1) * H),
+                              G[f"{r}.weight_hh_l0{suf}"], mode=1, split_k=0, c_ilv=H)
+                else:
+                    self.big_gemm(dG, Xin, G[f"{r}.weight_ih_l0{suf}"], ta=True, beta=1.0,
                                   split_k=0, c_ilv=H)
-                        k.gemm_tc(0, 1, 1, 4 * H, H, N, dGd, self._cols(HPp, di * H, (di + 1) * H),
-                                  G[f"{r}.weight_hh_l0{suf}"], mode=1, split_k=0, c_ilv=H)
-                    else:
-                        self.big_gemm(dG, Xin, G[f"{r}.weight_ih_l0{suf}"], ta=True, beta=1.0,
-                                      split_k=0, c_ilv=H)
-                        self.big_gemm(dG, HP[:, di * H:(di + 1) * H], G[f"{r}.weight_hh_l0{suf}"],
-                                      ta=True, beta=1.0, split_k=0, c_ilv=H)
-                    k.colsum(dG, G[f"{r}.bias_ih_l0{suf}"], G[f"{r}.bias_hh_l0{suf}"], ilv=H)
-                    if self.gru:     # 4-slot gradients -> the (3H, .) parameters' gradients
-                        k._c("mmda_gru_fold_grads", *[_ptr(G[f"{r}.{kk}{suf}"]) for kk in self._RNN_KEYS],
-                             H, I, *[_ptr(G_real[f"{r}.{kk}{suf}"]) for kk in self._RNN_KEYS])
+                    self.big_gemm(dG, HP[:, di * H:(di + 1) * H], G[f"{r}.weight_hh_l0{suf}"],
+                                  ta=True, beta=1.0, split_k=0, c_ilv=H)
+                k.colsum(dG, G[f"{r}.bias_ih_l0{suf}"], G[f"{r}.bias_hh_l0{suf}"], ilv=H)
+                if self.gru:     # 4-slot gradients -> the (3H, .) parameters' gradients
+                    k._c("mmda_gru_fold_grads", *[_ptr(G[f"{r}.{kk}{suf}"]) for kk in self._RNN_KEYS],
+                         H, I, *[_ptr(G_real[f"{r}.{kk}{suf}"]) for kk in self._RNN_KEYS])
 
             if use_side:
+                # one side stream per (layer, direction): the weight-gradient GEMMs of the second
+                # layer must not queue in front of the first layer's (they overlap the next BPTT
+                # launch and only get the SMs it leaves free)
+                sA, sB = self._wgrad_stream((m, r, 0)), self._wgrad_stream((m, r, 1))
                 ev = torch.cuda.Event()
                 ev.record(cur)
-                side.wait_event(ev)
-                with torch.cuda.stream(side):
+                sA.wait_event(ev)
+                with torch.cuda.stream(sA):
                     k.bind_stream()
-                    wgrad()
+                    wgrad_common()
+                    evc = torch.cuda.Event()
+                    evc.record(sA)
+                    wgrad_dir(0)
+                sB.wait_event(evc)
+                with torch.cuda.stream(sB):
+                    k.bind_stream()
+                    wgrad_dir(1)
                     if m == "t":
                         self._mark(f"  t.{r} wgrad (side stream) done")
                 k.bind_stream()
+                side_used += [sA, sB]
             else:
-                wgrad()
+                wgrad_common()
+                wgrad_dir(0)
+                wgrad_dir(1)
             if r == r2 or m == "t":
                 dX = dY1n if r == r2 else self.buf("dX_t", N, H)
                 if tc:   # dX = dG [N x 8H] * [W_ih ; W_ih_reverse] (stored [8H][I]: MN-major B)
@@ -1010,9 +1034,9 @@ class MisaEngine:
                     k._c("mmda_embedding_backward", _ptr(G["embed.weight"]),
                          _ptr(self.saved["sent"]), _ptr(dX), _ptr(pk["row_t"]), _ptr(pk["row_j"]),
                          _ptr(pk["sidx"]), N, B, H, V)
-        if use_side:
+        for st in side_used:
             done = torch.cuda.Event()
-            done.record(side)
+            done.record(st)
             cur.wait_event(done)
 
 

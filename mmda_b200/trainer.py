@@ -16,7 +16,7 @@ from typing import Dict, List, Optional, Tuple
 
 import torch
 
-from ._lib import MmdaError
+from ._lib import LIB, MmdaError
 from . import engine as _engine
 from .engine import MODS, _ptr
 
@@ -308,7 +308,12 @@ class FusedTrainer:
         k.bind_stream()
         k._c("mmda_adam_clip_step", _ptr(self.p_arena), _ptr(self.g_arena), _ptr(self.m),
              _ptr(self.v), self.n_active, self.step_count, self.lr, self.clip, 0.9, 0.999, 1e-8,
-             1.0, _ptr(self.state))
+             self._grad_scale(), _ptr(self.state))
+
+    def _grad_scale(self):
+        """Per-shard losses (global_batch_stats=False) are normalised by the LOCAL batch, so the
+        summed gradients are world x the data-parallel average (DDP semantics: divide)."""
+        return 1.0 if (self.global_stats or self.world == 1) else 1.0 / self.world
 
     def _eager_step(self, sentences, visual, acoustic, lengths, labels, bert=None):
         losses = self.forward_backward(sentences, visual, acoustic, lengths, labels, bert)
@@ -326,33 +331,57 @@ class FusedTrainer:
         if not self.use_graph or _engine._DRYRUN:
             return self._eager_step(sentences, visual, acoustic, lengths, labels)
         key = (tuple(sentences.shape), tuple(visual.shape), tuple(acoustic.shape),
-               tuple(lengths.tolist()), self.model.training)
+               tuple(lengths.tolist()), self.model.training, float(self.lr))
+        alias = tuple(p.data_ptr() for p in self.model.parameters()) + \
+            tuple(p.requires_grad for p in self.model.parameters())
         g = self._graph
-        if g is not None and g["key"] == key and g["ws"] == self.eng.ws_version and \
-                g["alias"] == self._alias_ver:
-            for dst, src in zip(g["inputs"], (sentences, visual, acoustic, labels)):
-                dst.copy_(src, non_blocking=True)
-            g["graph"].replay()
-            self.step_count += 1
-            return g["losses"]
+        if g is not None and (g["ws"] != self.eng.ws_version or g["alias"] != alias):
+            self._drop_graph()          # raw pointers inside the graph are stale: eager warm-up first
+            g = None
+        if g is not None and g["key"] == key:
+            # the graph reads the pack buffers (lens / sorted idx / offsets / row maps) by pointer;
+            # any other forward on this engine (evaluate(), a level-1 forward, an eager step with
+            # other lengths) has overwritten them: rebuild them for these lengths before the replay
+            self.eng._pack(lengths)
+            if g["ws"] == self.eng.ws_version:
+                for dst, src in zip(g["inputs"], (sentences, visual, acoustic, labels)):
+                    dst.copy_(src, non_blocking=True)
+                g["graph"].replay()
+                self.step_count += 1
+                return g["losses"]
+            self._drop_graph()
         seen = self._graph_seen.get(key, 0) + 1
         self._graph_seen = {key: seen}
         if seen < 3:                       # warm-up: allocates the workspace, builds the plans
             return self._eager_step(sentences, visual, acoustic, lengths, labels)
         self._check_alias()
+        self._drop_graph()
         inputs = [t.clone() for t in (sentences, visual, acoustic, labels)]
+        self.eng._pack(lengths)            # outside the capture: its H2D copy must not be recorded
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         l0, count0 = self.eng.k.launches, self.step_count
+        slots0 = LIB.raw("mmda_gemm_tc_graph_slots")(-1)
         with torch.cuda.graph(graph):
             losses = self._eager_step(inputs[0], inputs[1], inputs[2], lengths, inputs[3])
         self.launches_per_step = self.eng.k.launches - l0
         self.step_count = count0           # capture enqueues nothing: the replay runs the step
         self._graph = dict(key=key, graph=graph, inputs=inputs, losses=losses,
-                           ws=self.eng.ws_version, alias=self._alias_ver)
+                           ws=self.eng.ws_version, alias=self._alias_ver, slots=slots0)
         graph.replay()
         self.step_count += 1
         return losses
+
+    def _drop_graph(self):
+        """Forget the captured graph (stale pointers, new shapes, close()) and hand its GEMM
+        tile-scheduler slots back when it was the most recent capture."""
+        g, self._graph = self._graph, None
+        if g is not None:
+            g["graph"] = None
+            if not _engine._DRYRUN:
+                torch.cuda.synchronize()
+                LIB.raw("mmda_gemm_tc_graph_slots")(int(g.get("slots", -1)))
+            self._graph_seen = {}
 
     def close(self):
         """Drop the captured CUDA graph.  Under data parallelism the graph references the NCCL
@@ -360,7 +389,7 @@ class FusedTrainer:
         waits for the graph's resources and hangs); ``torch.distributed.destroy_process_group``
         is wrapped to do this for every live data-parallel trainer, calling it explicitly is
         still fine."""
-        self._graph = None
+        self._drop_graph()
         self._graph_seen = {}
         import gc
         gc.collect()

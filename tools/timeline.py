@@ -1,0 +1,50 @@
+"""Kernel timeline of one C2 training step under CUDA-graph replay (torch.profiler / CUPTI):
+which stream runs what, when, and where the critical path has gaps.
+
+    python tools/timeline.py [out.txt]
+"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    from torch.profiler import ProfilerActivity, profile
+    from mmda_b200 import MISA, FusedTrainer, mosei_config
+    from mmda_b200.synthetic import batch_for
+    dev = torch.device("cuda:0")
+    cfg = mosei_config(vocab_size=20000, batch_size=256)
+    torch.manual_seed(0)
+    tr = FusedTrainer(MISA(cfg).to(dev).train())
+    b = batch_for(cfg, seed=1, lengths=os.environ.get("LENGTHS", "full"))
+    args = [b.sentences.to(dev), b.visual.to(dev), b.acoustic.to(dev), b.lengths, b.labels.to(dev)]
+    for _ in range(6):
+        tr.step(*args)
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        tr.step(*args)
+        torch.cuda.synchronize()
+    evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+    ks = []
+    for e in evs:
+        tr_ = e.time_range
+        ks.append((tr_.start, tr_.end, e.name, getattr(e, "device_resource_id", -1)))
+    ks.sort()
+    if not ks:
+        print("no CUDA events captured")
+        return
+    t0 = ks[0][0]
+    streams = sorted({k[3] for k in ks})
+    sid = {s: i for i, s in enumerate(streams)}
+    out = open(sys.argv[1], "w") if len(sys.argv) > 1 else sys.stdout
+    print(f"kernels: {len(ks)}  streams: {len(streams)}  span: {(max(k[1] for k in ks) - t0) / 1e3:.3f} ms", file=out)
+    for s, e, n, st in ks:
+        short = n.replace("void ", "").replace("(anonymous namespace)::", "")[:60]
+        print(f"{(s - t0) / 1e3:8.3f} {(e - s) / 1e3:7.3f}  s{sid[st]:<2d} {short}", file=out)
+
+
+if __name__ == "__main__":
+    main()
