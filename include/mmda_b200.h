@@ -206,6 +206,16 @@ int mmda_loss_phase2(const float* X0, const float* segA, float* XN, float* inv_n
 int mmda_loss_finalize(const float* segA, const float* segB, float* losses, float* coef, int d,
                        int NC, float Bg, float w_diff, float w_sim, float w_recon, float w_conf,
                        int adversarial, mmda_stream_t stream);
+/* DiffLoss Gram matrices and their backward, batched over the six pairs of src/solver.py:432-439
+ * (src/utils/functions.py:49-78): Gm[p] = XN[a_p]^T XN[b_p]  (XN [6][B][d], Gm [6][d][d]);
+ * DXN[x] = alpha * (sum_{a_p = x} XN[b_p] Gm[p]^T + sum_{b_p = x} XN[a_p] Gm[p])  (overwrites). */
+int mmda_loss_gram(const float* XN, float* Gm, int B, int d, mmda_stream_t stream);
+int mmda_loss_dxn(const float* XN, const float* Gm, float* DXN, int B, int d, float alpha,
+                  mmda_stream_t stream);
+/* y = act(x W^T + b) with N <= 8 output columns: classifier / confidence heads,
+ * src/models.py:138-153,247-248 (Linear(6*hidden -> num_classes)). */
+int mmda_linear_skinny(const float* x, int ldx, const float* w, const float* bias, float* y, int ldy,
+                       int M, int N, int K, int act, mmda_stream_t stream);
 /* use_cmd_sim=False: domain cross-entropy of the adversarial discriminator, src/solver.py:388-407.
  * domain_logits (3,B,3) = [pred_t; pred_v; pred_a]; writes the batch sum into segA[6d+6NC+3] (read by
  * mmda_loss_finalize(adversarial=1)) and d(loss)/d(logits) scaled by w_sim/(3*Bg). */

@@ -468,3 +468,139 @@ extern "C" int mmda_eval_accumulate(const float* scores, const float* pred_label
   MMDA_CHECK_LAUNCH();
   return MMDA_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// DiffLoss Gram matrices and their backward as two batched launches (reference
+// src/utils/functions.py:49-78 through src/solver.py:422-441; the six (private, shared) /
+// (private, private) pairs).  They replace 6 + 12 separate small GEMM launches.
+//   XN [6][B][d]: centred, row-normalised tokens;  Gm [6][d][d]: Gm[p] = XN[a_p]^T XN[b_p]
+//   DXN[x] = alpha * ( sum_{p: a_p = x} XN[b_p] Gm[p]^T  +  sum_{p: b_p = x} XN[a_p] Gm[p] )
+// The pair table is the reference's (solver.py:432-439): (p_t,s_t) (p_v,s_v) (p_a,s_a) (p_a,p_t)
+// (p_a,p_v) (p_t,p_v) in token ids [p_t,p_v,p_a,s_t,s_v,s_a].
+// ------------------------------------------------------------------------------------------
+__constant__ int c_pair_a[6] = {0, 1, 2, 2, 2, 0};
+__constant__ int c_pair_b[6] = {3, 4, 5, 0, 1, 1};
+
+__global__ void __launch_bounds__(256) loss_gram_kernel(const float* __restrict__ XN, float* __restrict__ Gm,
+                                                        int B, int d) {
+  __shared__ float As[32][33], Bs[32][33];
+  const int p = blockIdx.z, i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+  const float* A = XN + (size_t)c_pair_a[p] * B * d;
+  const float* Bm = XN + (size_t)c_pair_b[p] * B * d;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k0 = 0; k0 < B; k0 += 32) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int k = k0 + ty * 4 + r;
+      As[ty * 4 + r][tx] = (k < B && i0 + tx < d) ? A[(size_t)k * d + i0 + tx] : 0.f;
+      Bs[ty * 4 + r][tx] = (k < B && j0 + tx < d) ? Bm[(size_t)k * d + j0 + tx] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const float bv = Bs[k][tx];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[r] = fmaf(As[k][ty * 4 + r], bv, acc[r]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int i = i0 + ty * 4 + r, j = j0 + tx;
+    if (i < d && j < d) Gm[((size_t)p * d + i) * d + j] = acc[r];
+  }
+}
+
+__global__ void __launch_bounds__(256) loss_dxn_kernel(const float* __restrict__ XN, const float* __restrict__ Gm,
+                                                       float* __restrict__ DXN, int B, int d, float alpha) {
+  __shared__ float Xs[32][33], Gs[32][33];
+  const int x = blockIdx.z, b0 = blockIdx.y * 32, i0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int p = 0; p < 6; ++p) {
+    const bool is_a = c_pair_a[p] == x, is_b = c_pair_b[p] == x;
+    if (!is_a && !is_b) continue;                              // block-uniform
+    const float* X = XN + (size_t)(is_a ? c_pair_b[p] : c_pair_a[p]) * B * d;
+    const float* G = Gm + (size_t)p * d * d;
+    for (int j0 = 0; j0 < d; j0 += 32) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int rr = ty * 4 + r;
+        Xs[rr][tx] = (b0 + rr < B && j0 + tx < d) ? X[(size_t)(b0 + rr) * d + j0 + tx] : 0.f;
+        // Gs[j][i] = coefficient of X[.][j0+j] in output column i0+i
+        if (is_a)   // out[b][i] += sum_j X[b][j] * G[i][j]
+          Gs[tx][rr] = (i0 + rr < d && j0 + tx < d) ? G[(size_t)(i0 + rr) * d + j0 + tx] : 0.f;
+        else        // out[b][i] += sum_j X[b][j] * G[j][i]
+          Gs[rr][tx] = (j0 + rr < d && i0 + tx < d) ? G[(size_t)(j0 + rr) * d + i0 + tx] : 0.f;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float gv = Gs[j][tx];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[r] = fmaf(Xs[ty * 4 + r][j], gv, acc[r]);
+      }
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int b = b0 + ty * 4 + r, i = i0 + tx;
+    if (b < B && i < d) DXN[((size_t)x * B + b) * d + i] = alpha * acc[r];
+  }
+}
+
+extern "C" int mmda_loss_gram(const float* XN, float* Gm, int B, int d, cudaStream_t stream) {
+  MMDA_REQUIRE(B > 0 && d > 0, "loss_gram: B=%d d=%d", B, d);
+  dim3 grid((d + 31) / 32, (d + 31) / 32, 6);
+  loss_gram_kernel<<<grid, 256, 0, stream>>>(XN, Gm, B, d);
+  MMDA_CHECK_LAUNCH();
+  return MMDA_OK;
+}
+
+extern "C" int mmda_loss_dxn(const float* XN, const float* Gm, float* DXN, int B, int d, float alpha,
+                             cudaStream_t stream) {
+  MMDA_REQUIRE(B > 0 && d > 0, "loss_dxn: B=%d d=%d", B, d);
+  dim3 grid((d + 31) / 32, (B + 31) / 32, 6);
+  loss_dxn_kernel<<<grid, 256, 0, stream>>>(XN, Gm, DXN, B, d, alpha);
+  MMDA_CHECK_LAUNCH();
+  return MMDA_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// y = act(x W^T + b) for a handful of output columns (classifier / confidence heads,
+// reference src/models.py:138-153: Linear(6*hidden -> num_classes)): one warp per row.
+// ------------------------------------------------------------------------------------------
+template <int NMAX>
+__global__ void __launch_bounds__(256) linear_skinny_kernel(const float* __restrict__ x, int ldx,
+                                                            const float* __restrict__ w,
+                                                            const float* __restrict__ bias,
+                                                            float* __restrict__ y, int ldy, int M,
+                                                            int N, int K, int act) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= M) return;
+  float acc[NMAX];
+#pragma unroll
+  for (int n = 0; n < NMAX; ++n) acc[n] = 0.f;
+  const float* xr = x + (size_t)row * ldx;
+  for (int k = lane; k < K; k += 32) {
+    const float xv = xr[k];
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n)
+      if (n < N) acc[n] = fmaf(xv, __ldg(w + (size_t)n * K + k), acc[n]);
+  }
+#pragma unroll
+  for (int n = 0; n < NMAX; ++n) {
+    const float s = warp_sum(acc[n]);
+    if (n < N && lane == 0) y[(size_t)row * ldy + n] = apply_act(s + (bias ? bias[n] : 0.f), act);
+  }
+}
+
+extern "C" int mmda_linear_skinny(const float* x, int ldx, const float* w, const float* bias, float* y,
+                                  int ldy, int M, int N, int K, int act, cudaStream_t stream) {
+  MMDA_REQUIRE(M > 0 && K > 0 && N >= 1 && N <= 8, "linear_skinny: M=%d N=%d K=%d (N <= 8)", M, N, K);
+  linear_skinny_kernel<8><<<(M + 7) / 8, 256, 0, stream>>>(x, ldx, w, bias, y, ldy, M, N, K, act);
+  MMDA_CHECK_LAUNCH();
+  return MMDA_OK;
+}

@@ -676,16 +676,22 @@ class MisaEngine:
         TCP = self.buf("TCP", B, 6)
         SC = self.buf("SCORES", B, NC)
         LAB = self.buf("LABELS", B, NC)
-        k.linear(Hf, P["confidence.confidence_layer_1.weight"],
-                 P["confidence.confidence_layer_1.bias"], TCP, act=ACT_SIGMOID)
+        def head(w, b, out, act):     # Linear(6d -> num_classes): one warp per row
+            if out.shape[1] <= 8:
+                k._c("mmda_linear_skinny", _ptr(Hf), Hf.stride(0), _ptr(P[w]), _ptr(P[b]), _ptr(out),
+                     out.stride(0), B, out.shape[1], Hf.shape[1], act)
+            else:
+                k.linear(Hf, P[w], P[b], out, act=act)
+
+        head("confidence.confidence_layer_1.weight", "confidence.confidence_layer_1.bias", TCP,
+             ACT_SIGMOID)
         if p_cls > 0:
-            k.linear(Hf, P["classifier.classifier_layer.weight"],
-                     P["classifier.classifier_layer.bias"], SC)
+            head("classifier.classifier_layer.weight", "classifier.classifier_layer.bias", SC, ACT_NONE)
             k.dropout(SC, SC, p_cls, seed, 5, seed_dev)
             k.act(SC, ACT_SIGMOID)
         else:
-            k.linear(Hf, P["classifier.classifier_layer.weight"],
-                     P["classifier.classifier_layer.bias"], SC, act=ACT_SIGMOID)
+            head("classifier.classifier_layer.weight", "classifier.classifier_layer.bias", SC,
+                 ACT_SIGMOID)
         k._c("mmda_threshold", _ptr(SC), _ptr(LAB), SC.numel(), float(cfg.threshold))
 
         for i, m in enumerate(MODS):

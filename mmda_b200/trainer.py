@@ -231,19 +231,15 @@ class FusedTrainer:
         inv = eng.buf("inv_norm", 6, B)
         k._c("mmda_loss_phase2", _ptr(X0), _ptr(segA), _ptr(XN), _ptr(inv), _ptr(segB), B, d, Bg)
         Gm = segB[12 * d:].view(6, d, d)
-        for pi, (a, b) in enumerate(DIFF_PAIRS):
-            k.gemm(XN[a], XN[b], Gm[pi], ta=True)
+        k._c("mmda_loss_gram", _ptr(XN), _ptr(Gm), B, d)     # the six pairs in one launch
         if sync:
             self._allreduce(segB)
         k._c("mmda_loss_finalize", _ptr(segA), _ptr(segB), _ptr(losses), _ptr(coef), d, NC, Bg,
              float(cfg.diff_weight), float(cfg.sim_weight), float(cfg.recon_weight), w_conf,
              int(adv))
         DXN = eng.buf("DXN", 6, B, d)
-        DXN.zero_()
         alpha = float(cfg.diff_weight) * 2.0 / float(d * d)
-        for pi, (a, b) in enumerate(DIFF_PAIRS):
-            k.gemm(XN[b], Gm[pi], DXN[a], tb=True, alpha=alpha, beta=1.0)
-            k.gemm(XN[a], Gm[pi], DXN[b], alpha=alpha, beta=1.0)
+        k._c("mmda_loss_dxn", _ptr(XN), _ptr(Gm), _ptr(DXN), B, d, alpha)
         k._c("mmda_loss_phase4a", _ptr(DXN), _ptr(inv), _ptr(segC), B, d)
         if sync:
             self._allreduce(segC)
