@@ -45,8 +45,9 @@ int mmda_device_info(int* out5);
  * Writes batch_sizes[Tmax], offsets[Tmax+1] and the (t, j) coordinates of each of the N rows. */
 int mmda_pack_build(const int* lens_sorted, int B, int Tmax, int N, int* batch_sizes, int* offsets,
                     int* row_t, int* row_j, mmda_stream_t stream);
-/* X[row] = src[t][sorted_idx[j]] for a time-major padded (T,B,D) input (visual / acoustic). */
-int mmda_gather_rows(const float* src, float* X, const int* row_t, const int* row_j,
+/* X[row] = src[t][sorted_idx[j]] for a time-major padded (T,B,D) input (visual / acoustic); ldx =
+ * row pitch of X in floats (>= D: a pitch that is a multiple of 4 keeps X a legal TMA operand). */
+int mmda_gather_rows(const float* src, float* X, int ldx, const int* row_t, const int* row_j,
                      const int* sorted_idx, int N, int B, int D, mmda_stream_t stream);
 
 /* ---- nn.Embedding, src/models.py:47,201 (forward fused with the pack; dense backward) ------ */
@@ -128,9 +129,9 @@ int mmda_lstm_set_small_tile(int bt);
 int mmda_lstm_set_debug_buffer(long long* dev_buf);
 /* diagnostic: co-resident clusters of the recurrent kernel for cluster sizes {1,2,4,8,16} */
 int mmda_lstm_probe_clusters(int smem_bytes, int threads, int* out5);
-/* h_{prev} operand for the hoisted dW_hh GEMM: [N][2H] */
+/* h_{prev} operand for the hoisted dW_hh GEMM: [N][2][Hp] (Hp >= H: direction pitch) */
 int mmda_lstm_shift_h(const float* y, float* hprev, const int* row_t, const int* row_j,
-                      const int* lens_sorted, const int* offsets, int N, int H,
+                      const int* lens_sorted, const int* offsets, int N, int H, int Hp,
                       mmda_stream_t stream);
 
 /* ---- tensor-core recurrence for large hidden sizes (text encoder, H = 300): same contract and

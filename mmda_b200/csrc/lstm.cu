@@ -662,12 +662,13 @@ __global__ void __launch_bounds__(BT == 40 ? 800 : 640, 1) lstm_bwd_kernel(const
   cluster_sync_all();
 }
 
-// h_{prev} operand of the hoisted dW_hh GEMM: hp[row][dir*H+u] = y at the forward-order
-// predecessor step of `row` in that direction, or 0 at the start of the sequence.
+// h_{prev} operand of the hoisted dW_hh GEMM: hp[row][dir][u] (direction pitch Hp >= H, so both
+// direction slices start 16-byte aligned when Hp % 4 == 0) = y at the forward-order predecessor
+// step of `row` in that direction, or 0 at the start of the sequence.
 __global__ void lstm_shift_kernel(const float* __restrict__ y, float* __restrict__ hp,
                                   const int* __restrict__ row_t, const int* __restrict__ row_j,
                                   const int* __restrict__ lens, const int* __restrict__ offsets,
-                                  int N, int H) {
+                                  int N, int H, int Hp) {
   const int row = blockIdx.x;
   if (row >= N) return;
   const int t = row_t[row], j = row_j[row], L = lens[j];
@@ -675,8 +676,8 @@ __global__ void lstm_shift_kernel(const float* __restrict__ y, float* __restrict
   const int prev_b = (t + 1 < L) ? offsets[t + 1] + j : -1;
   const int H2 = 2 * H;
   for (int c = threadIdx.x; c < H2; c += blockDim.x) {
-    const int src = c < H ? prev_f : prev_b;
-    hp[(size_t)row * H2 + c] = src >= 0 ? y[(size_t)src * H2 + c] : 0.f;
+    const int dir = c >= H, src = dir ? prev_b : prev_f;
+    hp[((size_t)row * 2 + dir) * Hp + (c - dir * H)] = src >= 0 ? y[(size_t)src * H2 + c] : 0.f;
   }
 }
 
@@ -1088,10 +1089,11 @@ int mmda_lstm_pack_weights(const float* w_ih_f, const float* w_ih_r, const float
 }
 
 int mmda_lstm_shift_h(const float* y, float* hprev, const int* row_t, const int* row_j,
-                      const int* lens_sorted, const int* offsets, int N, int H,
+                      const int* lens_sorted, const int* offsets, int N, int H, int Hp,
                       cudaStream_t stream) {
   if (N <= 0) return MMDA_OK;
-  lstm_shift_kernel<<<N, 128, 0, stream>>>(y, hprev, row_t, row_j, lens_sorted, offsets, N, H);
+  MMDA_REQUIRE(Hp >= H, "lstm_shift_h: Hp=%d < H=%d", Hp, H);
+  lstm_shift_kernel<<<N, 128, 0, stream>>>(y, hprev, row_t, row_j, lens_sorted, offsets, N, H, Hp);
   MMDA_CHECK_LAUNCH();
   return MMDA_OK;
 }

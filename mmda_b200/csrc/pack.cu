@@ -45,11 +45,11 @@ __global__ void pack_rows_kernel(const int* __restrict__ batch_sizes,
 // X[row][:] = src[t][sorted_idx[j]][:]    (src is the time-major padded (T,B,D) input)
 __global__ void gather_rows_kernel(const float* __restrict__ src, float* __restrict__ X,
                                    const int* __restrict__ row_t, const int* __restrict__ row_j,
-                                   const int* __restrict__ sorted_idx, int N, int B, int D) {
+                                   const int* __restrict__ sorted_idx, int N, int B, int D, int ldx) {
   const int row = blockIdx.x * blockDim.y + threadIdx.y;
   if (row >= N) return;
   const float* s = src + ((size_t)row_t[row] * B + sorted_idx[row_j[row]]) * D;
-  float* d = X + (size_t)row * D;
+  float* d = X + (size_t)row * ldx;
   for (int c = threadIdx.x; c < D; c += blockDim.x) d[c] = s[c];
 }
 
@@ -97,11 +97,12 @@ int mmda_pack_build(const int* lens_sorted, int B, int Tmax, int N, int* batch_s
   return MMDA_OK;
 }
 
-int mmda_gather_rows(const float* src, float* X, const int* row_t, const int* row_j,
+int mmda_gather_rows(const float* src, float* X, int ldx, const int* row_t, const int* row_j,
                      const int* sorted_idx, int N, int B, int D, cudaStream_t stream) {
   if (N <= 0) return MMDA_OK;
+  MMDA_REQUIRE(ldx >= D, "gather_rows: ldx=%d < D=%d", ldx, D);
   dim3 block(32, 8);
-  gather_rows_kernel<<<(N + 7) / 8, block, 0, stream>>>(src, X, row_t, row_j, sorted_idx, N, B, D);
+  gather_rows_kernel<<<(N + 7) / 8, block, 0, stream>>>(src, X, row_t, row_j, sorted_idx, N, B, D, ldx);
   MMDA_CHECK_LAUNCH();
   return MMDA_OK;
 }

@@ -143,11 +143,17 @@ class MisaEngine:
             raise ValueError(f"precision must be 'fp32' or 'bf16', got {prec!r}")
         # hoisted LSTM GEMMs: tcgen05 path (3xTF32 in fp32 mode, bf16 operands in bf16 mode) where
         # the operand pitches satisfy TMA's 16-byte rule, exact-fp32 SIMT path otherwise
+        # precision="bf16" selects bf16 operands for the BERT text encoder's GEMMs only (C4).  The
+        # hoisted LSTM GEMMs always run 3xTF32 (fp32-accurate): a bf16 input projection moved this
+        # model's text-encoder gradients by 5-15 % (measured round 1) and gained nothing once the
+        # recurrence itself ran on tensor cores, so that mode was removed.
         self.tc_kind = 0 if prec == "fp32" else 1
+        self.lstm_kind = 0
         # 3xTF32 operands: plain fp32 tensors, split into tf32 hi/lo inside the GEMM kernel's
         # shared-memory pipeline (MMDA_TF32_SPLIT=pre: separate split pass, hi/lo arrays in HBM)
         self.tc_raw = os.environ.get("MMDA_TF32_SPLIT", "smem") != "pre"
         self.use_tc = os.environ.get("MMDA_GEMM", "tc") != "simt"
+        self.tc_small = os.environ.get("MMDA_GEMM_SMALL", "tc") != "simt"
         # the visual / acoustic encoders run on side streams next to the text encoder (whose
         # cluster kernel occupies 112 of the 148 SMs)
         self.multi_stream = os.environ.get("MMDA_STREAMS", "1") != "0"
@@ -329,7 +335,16 @@ class MisaEngine:
 
     # ---------------------------------------------------------------- tensor-core operands --
     def _tc_ok(self, H, I):
-        return self.use_tc and H % 4 == 0 and I % 4 == 0
+        """The hoisted LSTM GEMMs run on tcgen05 for every hidden size: operands whose natural
+        pitch breaks TMA's 16-byte rule (visual 35 / 70, acoustic 74 floats) live in buffers with
+        the pitch rounded up to 4 floats (`pbuf`); the pad columns are never read (the tensor
+        maps carry the true extents).  MMDA_GEMM_SMALL=simt keeps the old SIMT routing."""
+        return self.use_tc and (self.tc_small or (H % 4 == 0 and I % 4 == 0))
+
+    def pbuf(self, name, rows, cols):
+        """(rows, cols) view of a workspace buffer whose row pitch is cols rounded up to 4 floats."""
+        ld = (cols + 3) // 4 * 4
+        return self.buf(name, rows, ld)[:, :cols]
 
     def _prep(self, name, x, out=None, row0=0, kind=None, split=False):
         """Tensor-core operand copy of the 2-D view x: (hi, lo) tf32 split or (bf16, None).
@@ -466,7 +481,7 @@ class MisaEngine:
         G1 = self.buf(f"G1_{m}", N, 8 * H)
         Y1 = self.buf(f"Y1_{m}", N, 2 * H)
         C1 = self.buf(f"C1_{m}", N, 2 * H)
-        Y1n = self.buf(f"Y1n_{m}", N, 2 * H)
+        Y1n = self.pbuf(f"Y1n_{m}", N, 2 * H)
         G2 = self.buf(f"G2_{m}", N, 8 * H)
         Y2 = self.buf(f"Y2_{m}", N, 2 * H)
         C2 = self.buf(f"C2_{m}", N, 2 * H)
@@ -481,9 +496,9 @@ class MisaEngine:
             # both directions in ONE GEMM against the stacked, gate-interleaved weight copy:
             # G[N][2][H][4] = Xin * Wst^T + (b_ih + b_hh)
             if self._tc_ok(H, I):
-                Wst, bst = self._pack_weights(r, P, H, I, self.tc_kind)
-                Xp = self._prep(f"tcX_{r}", Xin)
-                k.gemm_tc(self.tc_kind, 0, 0, N, 8 * H, I, Xp, Wst, G, bias=bst)
+                Wst, bst = self._pack_weights(r, P, H, I, self.lstm_kind)
+                Xp = self._prep(f"tcX_{r}", Xin, kind=self.lstm_kind)
+                k.gemm_tc(self.lstm_kind, 0, 0, N, 8 * H, I, Xp, Wst, G, bias=bst)
             else:
                 Wst, bst = self._pack_weights(r, P, H, I, -1)
                 self.big_gemm(Xin, Wst[0], G, tb=True, bias=bst)
@@ -551,7 +566,7 @@ class MisaEngine:
         for m, src in srcs.items():
             if src.dtype != torch.float32 or src.shape[1] != B or src.shape[2] != self.H[m]:
                 raise MmdaError(f"{m} input has shape {tuple(src.shape)} / {src.dtype}")
-            X[m] = self.buf(f"X_{m}", N, self.H[m])
+            X[m] = self.pbuf(f"X_{m}", N, self.H[m])
         if not self.use_bert:
             X["t"] = self.buf("X_t", N, self.H["t"])
 
@@ -566,7 +581,7 @@ class MisaEngine:
 
         def enc_side(m):
             def run():
-                k._c("mmda_gather_rows", _ptr(srcs[m]), _ptr(X[m]), _ptr(pk["row_t"]),
+                k._c("mmda_gather_rows", _ptr(srcs[m]), _ptr(X[m]), X[m].stride(0), _ptr(pk["row_t"]),
                      _ptr(pk["row_j"]), _ptr(pk["sidx"]), N, B, self.H[m])
                 utt[m] = self._encode(m, X[m], pk, train, P)
             return run
@@ -913,13 +928,13 @@ class MisaEngine:
         G1, G2 = self.buf(f"G1_{m}", N, 8 * H), self.buf(f"G2_{m}", N, 8 * H)
         Y1, Y2 = self.buf(f"Y1_{m}", N, 2 * H), self.buf(f"Y2_{m}", N, 2 * H)
         C1, C2 = self.buf(f"C1_{m}", N, 2 * H), self.buf(f"C2_{m}", N, 2 * H)
-        Y1n = self.buf(f"Y1n_{m}", N, 2 * H)
+        Y1n = self.pbuf(f"Y1n_{m}", N, 2 * H)
         mu, rs = self.buf(f"ln_mu_{m}", N), self.buf(f"ln_rs_{m}", N)
         nbytes = LIB.raw("mmda_lstm_scratch_bytes")(B, H)
         if nbytes < 0:
             raise MmdaError(LIB.raw("mmda_last_error")().decode())
         scratch = self.buf(f"lstm_scratch_{m}", max(1, nbytes // 4))
-        dY1n = self.buf(f"dY1n_{m}", N, 2 * H)
+        dY1n = self.pbuf(f"dY1n_{m}", N, 2 * H)
         dY1 = self.buf(f"dY1_{m}", N, 2 * H)
         use_side = self.multi_stream and not _DRYRUN
         cur = torch.cuda.current_stream() if use_side else None
@@ -954,10 +969,10 @@ class MisaEngine:
                 # cancellation, where bf16 operands cost several percent (measured 4-13 %); bf16
                 # mode covers the forward input projection only (BASELINE configs[2]).
                 dGp = self._prep(f"tcdG_{r}", Gt, kind=0)
-                if self.tc_kind == 0 and self.tc_raw:
+                if self.lstm_kind == 0 and self.tc_raw:
                     Xp = self._prep(f"tcX_{r}", Xin, kind=0)          # the fp32 tensor itself
                     Wst = self._prep_buf(f"tcW_{r}", 8 * H, I, 0, split=True)   # packed by the forward
-                elif self.tc_kind == 0:    # operand splits written by the forward
+                elif self.lstm_kind == 0:    # operand splits written by the forward
                     Xp = self._prep_buf(f"tcX_{r}", N, I, 0)
                     Wst = self._prep_buf(f"tcW_{r}", 8 * H, I, 0)
                 else:
@@ -973,12 +988,13 @@ class MisaEngine:
                     for suf in ("", "_reverse"):
                         for kk in self._RNN_KEYS:
                             G[f"{r}.{kk}{suf}"].zero_()
-                HP = self.buf(f"HP_{r}", N, 2 * H)
+                Hp = (H + 3) // 4 * 4                 # direction pitch: both slices 16-byte aligned
+                HP = self.buf(f"HP_{r}", N, 2 * Hp)
                 k._c("mmda_lstm_shift_h", _ptr(Y), _ptr(HP), _ptr(pk["row_t"]), _ptr(pk["row_j"]),
-                     _ptr(pk["lens"]), _ptr(pk["off"]), N, H)
-                hp_box["HP"] = HP
+                     _ptr(pk["lens"]), _ptr(pk["off"]), N, H, Hp)
+                hp_box["HP"] = [HP[:, di * Hp:di * Hp + H] for di in (0, 1)]
                 if tc:
-                    hp_box["HPp"] = self._prep(f"tcHP_{r}", HP, kind=0)
+                    hp_box["HPp"] = [self._prep(f"tcHP_{r}_{di}", hp_box["HP"][di], kind=0) for di in (0, 1)]
 
             def wgrad_dir(di, r=r, Gt=Gt, Xin=Xin, tc=tc, I=I):
                 # dG columns are gate-interleaved (u*4+g): c_ilv=H stores row u*4+g at g*H+u
@@ -989,12 +1005,12 @@ class MisaEngine:
                     dGd = self._cols(dGp, di * 4 * H, (di + 1) * 4 * H)
                     k.gemm_tc(0, 1, 1, 4 * H, I, N, dGd, Xp, G[f"{r}.weight_ih_l0{suf}"], mode=1,
                               split_k=0, c_ilv=H)
-                    k.gemm_tc(0, 1, 1, 4 * H, H, N, dGd, self._cols(hp_box["HPp"], di * H, (di + 1) * H),
+                    k.gemm_tc(0, 1, 1, 4 * H, H, N, dGd, hp_box["HPp"][di],
                               G[f"{r}.weight_hh_l0{suf}"], mode=1, split_k=0, c_ilv=H)
                 else:
                     self.big_gemm(dG, Xin, G[f"{r}.weight_ih_l0{suf}"], ta=True, beta=1.0,
                                   split_k=0, c_ilv=H)
-                    self.big_gemm(dG, HP[:, di * H:(di + 1) * H], G[f"{r}.weight_hh_l0{suf}"],
+                    self.big_gemm(dG, HP[di], G[f"{r}.weight_hh_l0{suf}"],
                                   ta=True, beta=1.0, split_k=0, c_ilv=H)
                 k.colsum(dG, G[f"{r}.bias_ih_l0{suf}"], G[f"{r}.bias_hh_l0{suf}"], ilv=H)
                 if self.gru:     # 4-slot gradients -> the (3H, .) parameters' gradients
