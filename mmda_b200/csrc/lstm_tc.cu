@@ -40,7 +40,7 @@ using namespace tc5;
 constexpr int TCL_CELL_WARPS = 8;
 constexpr int TCL_FWD_THREADS = 32 * (TCL_CELL_WARPS + 1);   // + the control warp
 constexpr int TCL_BWD_THREADS = 32 * TCL_CELL_WARPS;
-constexpr int TCL_N = 48;                     // batch rows per tile = widest MMA N used
+constexpr int TCL_N = 64;                     // batch rows per tile
 constexpr int TCL_UNITS = 32;                 // hidden units per CTA (x4 gates = 128 MMA rows)
 constexpr int A_ATOM = 128 * 128;             // bytes: 128 rows x 64 16-bit elements (one 128B-swizzle K atom)
 constexpr int B_ATOM = TCL_N * 128;           // bytes: 48 rows x 64 elements
@@ -121,7 +121,7 @@ __device__ __forceinline__ void warp_publish(unsigned* flag, int lane) {
 // ------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------
-// A batch tile (<= 48 rows) is processed as up to three 16-row SUB-TILES that move through the
+// A batch tile (<= 64 rows) is processed as up to four 16-row SUB-TILES that move through the
 // roles below like a software pipeline: while the cell warps update sub-tile k, the h_t of
 // sub-tile k-1 is on its way through L2 and the MMAs of sub-tile k+1 run.  Every role walks the
 // items (sub-tile k, step s) in the same order; mbarriers hand an item from role to role:
@@ -134,7 +134,7 @@ constexpr int SUB = 16;                        // rows of a sub-tile = MMA N
 constexpr int MAXSUB = TCL_N / SUB;
 constexpr int SUB_ATOM = SUB * 128;            // bytes of one K atom of a sub-tile operand
 constexpr int STAGE_BYTES = 2 * SUB * 64;      // h1 | h2 of this CTA's 32 units, 16 rows
-constexpr int TCL_FWD_WARPS = TCL_CELL_WARPS + 5;
+constexpr int TCL_FWD_WARPS = TCL_CELL_WARPS + 2 + MAXSUB;   // control, MMA, one publisher per sub-tile
 constexpr int TCL_FWD_THREADS4 = 32 * TCL_FWD_WARPS;
 
 __global__ void __launch_bounds__(TCL_FWD_THREADS4, 1) lstm_tc_fwd_kernel(const TclArgs p) {
@@ -150,9 +150,9 @@ __global__ void __launch_bounds__(TCL_FWD_THREADS4, 1) lstm_tc_fwd_kernel(const 
   const uint32_t stage_off = MAXSUB * IMGS;
   const uint32_t misc_off = stage_off + MAXSUB * STAGE_BYTES;
   auto copy_bar = [&](int k) { return sbase + misc_off + 8u * (uint32_t)k; };
-  auto mma_bar = [&](int k) { return sbase + misc_off + 24u + 8u * (uint32_t)k; };
-  auto stage_bar = [&](int k) { return sbase + misc_off + 48u + 8u * (uint32_t)k; };
-  const uint32_t tmem_slot = sbase + misc_off + 72;
+  auto mma_bar = [&](int k) { return sbase + misc_off + 32u + 8u * (uint32_t)k; };
+  auto stage_bar = [&](int k) { return sbase + misc_off + 64u + 8u * (uint32_t)k; };
+  const uint32_t tmem_slot = sbase + misc_off + 96;
   int* lens_s = reinterpret_cast<int*>(sptr + misc_off + 128);
   int* orig_s = lens_s + TCL_N;
 
@@ -174,9 +174,9 @@ __global__ void __launch_bounds__(TCL_FWD_THREADS4, 1) lstm_tc_fwd_kernel(const 
   fence_before();
   __syncthreads();
   fence_after();
-  const uint32_t tm = *reinterpret_cast<uint32_t*>(sptr + misc_off + 72);
+  const uint32_t tm = *reinterpret_cast<uint32_t*>(sptr + misc_off + 96);
   const uint32_t tmW1 = tm, tmW2 = tm + (Kp >> 1);
-  const uint32_t tmD = tm + 2 * (Kp >> 1);    // [sub-tile][main0 | main1 | cross a | cross b (x 2^11)][16 columns]
+  const uint32_t tmD = tm + 2 * (Kp >> 1);    // [sub-tile][main0 | main1 | cross (x 2^11)][16 columns]
   const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
 
   if (warp < TCL_CELL_WARPS) {  // resident weights: row rho = 4*ul + g of the slice = W_hh[g*H + 32r + ul][:]
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(TCL_FWD_THREADS4, 1) lstm_tc_fwd_kernel(const 
   const int gcol = dir * 4 * H + u * 4;
   const int ycol = dir * H + u;
   const int utt_off = dir == 0 ? p.utt_off0 : p.utt_off1;
-  uint32_t n_done[MAXSUB] = {0, 0, 0};     // completed phases of "my" barrier of each sub-tile
+  uint32_t n_done[MAXSUB] = {0, 0, 0, 0};  // completed phases of "my" barrier of each sub-tile
   const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0;
 #define TCL_TS(i) if (dbg_on && tile == grp && k == 0) p.dbg[s * 16 + (i)] = clock64();
 
@@ -266,9 +266,7 @@ __global__ void __launch_bounds__(TCL_FWD_THREADS4, 1) lstm_tc_fwd_kernel(const 
           fence_after();
           if (lane == 0) { TCL_TS(2) }
           const uint32_t idesc = idesc_f16(128, SUB);
-          // consecutive MMAs never hit the same accumulator (a dependent MMA waits ~48 clk)
-          const uint32_t d_m0 = tmD + (uint32_t)k * 4 * SUB, d_m1 = d_m0 + SUB, d_xa = d_m0 + 2 * SUB,
-                         d_xb = d_m0 + 3 * SUB;
+          const uint32_t d_m0 = tmD + (uint32_t)k * 3 * SUB, d_m1 = d_m0 + SUB, d_x = d_m0 + 2 * SUB;
           const uint64_t b1_0 = make_desc(sbase + (uint32_t)k * IMGS, 16, 1024);
           const uint64_t b2_0 = make_desc(sbase + (uint32_t)k * IMGS + SPLS, 16, 1024);
           if (elect_one()) {
@@ -279,8 +277,8 @@ __global__ void __launch_bounds__(TCL_FWD_THREADS4, 1) lstm_tc_fwd_kernel(const 
                 const int ks = a * 4 + kk;
                 if (ks < KS) {
                   const uint32_t a1 = tmW1 + ks * 8, a2 = tmW2 + ks * 8;
-                  mma_ts(d_xa, a1, b2a + 2 * kk, idesc, ks > 0 ? 1u : 0u);
-                  mma_ts(d_xb, a2, b1a + 2 * kk, idesc, ks > 0 ? 1u : 0u);
+                  mma_ts(d_x, a1, b2a + 2 * kk, idesc, ks > 0 ? 1u : 0u);
+                  mma_ts(d_x, a2, b1a + 2 * kk, idesc, 1u);
                   mma_ts((ks & 1) ? d_m1 : d_m0, a1, b1a + 2 * kk, idesc, ks >= 2 ? 1u : 0u);
                 }
               }
@@ -366,11 +364,10 @@ __global__ void __launch_bounds__(TCL_FWD_THREADS4, 1) lstm_tc_fwd_kernel(const 
           ++n_done[k];
           fence_after();
           if (tid == 0) { TCL_TS(4) }
-          uint32_t m0[8], m1[8], xa[8], xb[8];
-          const uint32_t col = (uint32_t)(k * 4 * SUB + 8 * hc);
+          uint32_t m0[8], m1[8], xx[8];
+          const uint32_t col = (uint32_t)(k * 3 * SUB + 8 * hc);
           tmem_ld8(tmD + lane_sel + col, m0);
-          tmem_ld8(tmD + lane_sel + 2 * SUB + col, xa);
-          tmem_ld8(tmD + lane_sel + 3 * SUB + col, xb);
+          tmem_ld8(tmD + lane_sel + 2 * SUB + col, xx);
           if (KS > 1) tmem_ld8(tmD + lane_sel + SUB + col, m1);
           tmem_wait_ld();
           fence_before();
@@ -378,7 +375,7 @@ __global__ void __launch_bounds__(TCL_FWD_THREADS4, 1) lstm_tc_fwd_kernel(const 
           for (int j = 0; j < 8; ++j) {
             float v = __uint_as_float(m0[j]);
             if (KS > 1) v += __uint_as_float(m1[j]);
-            acc[j >> 2][j & 3] = fmaf(__uint_as_float(xa[j]) + __uint_as_float(xb[j]), 1.f / 2048.f, v);
+            acc[j >> 2][j & 3] = fmaf(__uint_as_float(xx[j]), 1.f / 2048.f, v);
           }
           transpose4(acc[0], g4);
           transpose4(acc[1], g4);
@@ -440,7 +437,7 @@ __global__ void __launch_bounds__(TCL_FWD_THREADS4, 1) lstm_tc_fwd_kernel(const 
 // ------------------------------------------------------------------------------------------
 // backward through time
 // ------------------------------------------------------------------------------------------
-// Same sub-tile pipeline as the forward, with two 24-row sub-tiles (MMA N = 32): the backward needs
+// Same sub-tile pipeline as the forward, with two 32-row sub-tiles (MMA N = 32): the backward needs
 // 6 MMAs per K step and M tile, half of them with the A operand in shared memory (~45 clk each
 // whatever N is), so fewer, wider MMAs win.  One TMEM accumulator per (sub-tile, M tile): the terms
 // are issued smallest first (2^-16 group, 2^-8 group, main), so the truncating fp32 accumulation
@@ -455,8 +452,8 @@ __global__ void __launch_bounds__(TCL_FWD_THREADS4, 1) lstm_tc_fwd_kernel(const 
 constexpr int TCL_BWD_WARPS4 = TCL_CELL_WARPS + 6;
 constexpr int TCL_BWD_THREADS4 = 32 * TCL_BWD_WARPS4;
 constexpr int BWD_WRITERS = 4;
-constexpr int BSUB = 24;                       // rows of a backward sub-tile
-constexpr int BN = 32;                         // its MMA N (rows 24..31 of the B operand stay zero)
+constexpr int BSUB = 32;                       // rows of a backward sub-tile
+constexpr int BN = 32;                         // its MMA N
 constexpr int BMAXSUB = TCL_N / BSUB;
 constexpr int BSUB_ATOM = BN * 128;
 
@@ -571,7 +568,7 @@ __global__ void __launch_bounds__(TCL_BWD_THREADS4, 1) lstm_tc_bwd_kernel(const 
     __syncthreads();
     unsigned* flags = p.flags + (size_t)(dir * p.NT + tile) * BMAXSUB;
     const size_t slab = (size_t)BSUB * XLD;                      // one CTA's partial block of a sub-tile
-    // partial scratch of this tile: [k][parity][S][24][XLD]
+    // partial scratch of this tile: [k][parity][S][32][XLD]
     float* part = reinterpret_cast<float*>(p.xch) + (size_t)(dir * p.NT + tile) * BMAXSUB * 2 * S * slab;
 
     if (warp == TCL_CELL_WARPS + 5) {
@@ -660,11 +657,12 @@ __global__ void __launch_bounds__(TCL_BWD_THREADS4, 1) lstm_tc_bwd_kernel(const 
           float* dst = part + (((size_t)k * 2 + (s & 1)) * S + r) * slab;
           for (int mt = 0; mt < MT; ++mt) {
             const int j = mt * 128 + q * 32 + lane;
-            uint32_t v0[8], v1[8], v2[8];
+            uint32_t v0[8], v1[8], v2[8], v3[8];
             const uint32_t col = (uint32_t)(k * MT + mt) * BN;
             tmem_ld8(tmD + lane_sel + col, v0);
             tmem_ld8(tmD + lane_sel + col + 8, v1);
             tmem_ld8(tmD + lane_sel + col + 16, v2);
+            tmem_ld8(tmD + lane_sel + col + 24, v3);
             tmem_wait_ld();
             if (j < H) {
 #pragma unroll
@@ -672,6 +670,7 @@ __global__ void __launch_bounds__(TCL_BWD_THREADS4, 1) lstm_tc_bwd_kernel(const 
                 if (jj < n_prev) __stcg(dst + (size_t)jj * XLD + j, __uint_as_float(v0[jj]));
                 if (jj + 8 < n_prev) __stcg(dst + (size_t)(jj + 8) * XLD + j, __uint_as_float(v1[jj]));
                 if (jj + 16 < n_prev) __stcg(dst + (size_t)(jj + 16) * XLD + j, __uint_as_float(v2[jj]));
+                if (jj + 24 < n_prev) __stcg(dst + (size_t)(jj + 24) * XLD + j, __uint_as_float(v3[jj]));
               }
             }
           }
@@ -684,18 +683,18 @@ __global__ void __launch_bounds__(TCL_BWD_THREADS4, 1) lstm_tc_bwd_kernel(const 
       continue;
     }
 
-    // ===================== cell warps: lane = local unit, warp w owns rows w, w + 8, w + 16 of a sub-tile ====
+    // ===================== cell warps: lane = local unit, warp w owns rows w, w + 8, w + 16, w + 24 of a sub-tile ====
     const int ul = lane, u = r * TCL_UNITS + ul;
     const bool u_ok = u < H;
     const int gcol = dir * 4 * H + u * 4;
     const int ycol = dir * H + u;
     const int utt_off = dir == 0 ? p.utt_off0 : p.utt_off1;
-    float dcst[BMAXSUB][3];
-    int len_c[BMAXSUB][3], orig_c[BMAXSUB][3];
+    float dcst[BMAXSUB][4];
+    int len_c[BMAXSUB][4], orig_c[BMAXSUB][4];
 #pragma unroll
     for (int k = 0; k < BMAXSUB; ++k)
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
+      for (int i = 0; i < 4; ++i) {
         dcst[k][i] = 0.f;
         const int b = k * BSUB + warp + 8 * i;
         len_c[k][i] = u_ok ? lens_s[b] : 0;
@@ -711,11 +710,11 @@ __global__ void __launch_bounds__(TCL_BWD_THREADS4, 1) lstm_tc_bwd_kernel(const 
         // ---- everything the cell backward needs that does not depend on the exchange ----
         const int off_t = offs_s[t];
         const int tp = dir == 0 ? t - 1 : t + 1;      // forward-order predecessor (its c is c_prev)
-        float4 gt[3];
-        float ct[3], cp[3], dh[3];
-        bool act[3], rec[3];
+        float4 gt[4];
+        float ct[4], cp[4], dh[4];
+        bool act[4], rec[4];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
+        for (int i = 0; i < 4; ++i) {
           const int b = k * BSUB + warp + 8 * i;
           act[i] = t < len_c[k][i];
           rec[i] = false;
@@ -739,27 +738,30 @@ __global__ void __launch_bounds__(TCL_BWD_THREADS4, 1) lstm_tc_bwd_kernel(const 
           if (tid == 0) { TCL_TS(6) }
           // ---- reduce my columns over the S partial blocks (all loads in flight at once) ----
           const float* src = part + ((size_t)k * 2 + (s & 1)) * S * slab + u;
-          float v[3][12];
 #pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            const int n = warp + 8 * i;
+          for (int h2 = 0; h2 < 2; ++h2) {        // two cells (24 loads) in flight at a time
+            float v[2][12];
 #pragma unroll
-            for (int rr = 0; rr < 12; ++rr)
-              v[i][rr] = (act[i] && rec[i] && rr < S) ? __ldcg(src + (size_t)rr * slab + (size_t)n * XLD) : 0.f;
-          }
+            for (int ii = 0; ii < 2; ++ii) {
+              const int i = h2 * 2 + ii, n = warp + 8 * i;
 #pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            float sum = 0.f;
+              for (int rr = 0; rr < 12; ++rr)
+                v[ii][rr] = (act[i] && rec[i] && rr < S) ? __ldcg(src + (size_t)rr * slab + (size_t)n * XLD) : 0.f;
+            }
 #pragma unroll
-            for (int rr = 0; rr < 12; ++rr) sum += v[i][rr];
-            dh[i] += sum;
+            for (int ii = 0; ii < 2; ++ii) {
+              float sum = 0.f;
+#pragma unroll
+              for (int rr = 0; rr < 12; ++rr) sum += v[ii][rr];
+              dh[h2 * 2 + ii] += sum;
+            }
           }
         }
         // ---- cell backward; d(gates) -> my rows of the sub-tile's B operand (3 bf16 terms) ----
         const bool more = s + 1 < Lk[k];
-        float4 dgv[3];
+        float4 dgv[4];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
+        for (int i = 0; i < 4; ++i) {
           const int n = warp + 8 * i;
           float dig = 0.f, dfg = 0.f, dgg = 0.f, dog = 0.f;
           if (act[i]) {
@@ -796,7 +798,7 @@ __global__ void __launch_bounds__(TCL_BWD_THREADS4, 1) lstm_tc_bwd_kernel(const 
         if (tid == 0) { TCL_TS(7) }
         // the GEMM operand copy of d(gates): nobody inside this launch waits for it
 #pragma unroll
-        for (int i = 0; i < 3; ++i)
+        for (int i = 0; i < 4; ++i)
           if (act[i])
             *reinterpret_cast<float4*>(p.gates + (size_t)(off_t + b_base + k * BSUB + warp + 8 * i) * H8 + gcol) = dgv[i];
       }
@@ -825,18 +827,16 @@ int tcl_make_plan(int B, int H, int Tmax, TclPlan* pl) {
   const int KA = (Kp + 63) / 64;
   int Gmax = g_tcl_max_ctas / (2 * S);
   if (Gmax < 1) Gmax = 1;
+  // A time step is a latency chain (MMA -> cell update -> L2 exchange), not SM-bound work: more,
+  // smaller tiles do not shorten it, they only take SMs away from the kernels running next to
+  // this one.  So: the fewest tiles that cover the batch, spread evenly over the rounds.
   const int nt_min = (B + TCL_N - 1) / TCL_N;
-  int NT;
-  if (nt_min >= Gmax) NT = nt_min;
-  else {
-    NT = (B + 15) / 16;
-    if (NT > Gmax) NT = Gmax;
-    if (NT < nt_min) NT = nt_min;
-  }
+  int NT = nt_min;
   const int BT = (B + NT - 1) / NT;
   NT = (B + BT - 1) / BT;
+  const int rounds = (NT + Gmax - 1) / Gmax;
   pl->S = S; pl->Kp = Kp; pl->MT = MT; pl->NT = NT; pl->BT = BT;
-  pl->G = NT < Gmax ? NT : Gmax;
+  pl->G = (NT + rounds - 1) / rounds;
   const size_t misc = MISC_FIXED + (size_t)(2 * Tmax + 2) * 4;
   pl->smem_fwd = 1024 + (size_t)MAXSUB * (2 * KA * SUB_ATOM + STAGE_BYTES) + misc;
   const int rows_last = ((H - 128 * (MT - 1)) + 7) & ~7;

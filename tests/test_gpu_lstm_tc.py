@@ -43,7 +43,7 @@ def test_tc_plan_and_unsupported_sizes():
     arr = (ctypes.c_int * 8)()
     LIB.call("mmda_lstm_tc_plan", 256, 300, 50, arr)
     S, G, BT, NT, Kp, smf, smb, ctas = list(arr)
-    assert S == 10 and Kp == 304 and BT * NT >= 256 and BT <= 48 and ctas == 2 * S * G <= 148
+    assert S == 10 and Kp == 304 and BT * NT >= 256 and BT <= 64 and ctas == 2 * S * G <= 148
     assert max(smf, smb) <= 232448
     assert LIB.raw("mmda_lstm_tc_workspace_bytes")(256, 74, 50) == -1      # small H: SIMT kernels
     assert LIB.raw("mmda_lstm_tc_workspace_bytes")(256, 400, 50) == -1
