@@ -180,10 +180,12 @@ def roofline_block(cfg, batch0, kdur, clk, args):
     plan = {}
     if tc:
         arr = (ctypes.c_int * 8)()
+        LIB.call("mmda_lstm_tc_plan_select", int(bwd))
         LIB.call("mmda_lstm_tc_plan", args.batch, H, Tmax, arr)
-        plan = dict(zip(("slices", "groups", "batch_tile", "tiles", "k_padded", "smem_fwd", "smem_bwd",
-                         "ctas"), list(arr)))
-        terms = 6 if bwd else 3                    # bf16x3 (6 products) backward, fp16x2 (3) forward
+        LIB.call("mmda_lstm_tc_plan_select", 0)
+        plan = dict(zip(("slices", "groups", "batch_tile", "tiles", "units_per_cta" if bwd else "k_padded",
+                         "smem_fwd", "smem_bwd", "ctas"), list(arr)))
+        terms = 3                                  # two fp16 terms per operand: 3 MMAs per product
         issued = flops * terms
         bounds_us["tensor"] = issued / (tensor_peak * 1e12) * 1e6
     else:
@@ -222,8 +224,8 @@ def roofline_block(cfg, batch0, kdur, clk, args):
         out["tensor_issued"] = {"achieved_tflops": flops * terms / dur / 1e12, "peak_tflops": tensor_peak,
                                 "frac": flops * terms / dur / 1e12 / tensor_peak,
                                 "terms_per_product": terms}
-        out["note"] = ("tensor-core recurrence: fp32-accurate operand splits (3 MMAs per product forward, "
-                       "6 backward); a time step is a serial chain of MMA -> cell update -> L2 exchange, so "
+        out["note"] = ("tensor-core recurrence: fp32-accurate operand splits (two fp16 terms per operand, 3 MMAs "
+                       "per product); a time step is a serial chain of MMA -> cell update -> L2 exchange, so "
                        "the launch is latency-bound: `frac` (algorithmic flops vs the tensor peak) is small by "
                        "construction, `fp32_fma.frac` compares with the best a SIMT fp32 kernel could do "
                        "(SURVEY M2 ii), and frac_of_binding_roofline with the largest of the rooflines")

@@ -143,6 +143,9 @@ int mmda_lstm_shift_h(const float* y, float* hprev, const int* row_t, const int*
 long long mmda_lstm_tc_workspace_bytes(int B, int H, int Tmax);   /* -1: hidden size not covered */
 /* out8 = {slices, groups, batch tile, n tiles, padded K, smem fwd, smem bwd, CTAs} */
 int mmda_lstm_tc_plan(int B, int H, int Tmax, int* out8);
+/* 0 (default): mmda_lstm_tc_plan reports the forward decomposition; 1: the backward one, with
+ * out8[4] = hidden units per CTA instead of the padded K */
+int mmda_lstm_tc_plan_select(int backward);
 int mmda_lstm_tc_forward(float* gates, const float* whh_f, const float* whh_r, float* y, float* c,
                          const int* lens_sorted, const int* sorted_idx, const int* offsets,
                          float* utt, int utt_ld, int utt_off_f, int utt_off_r, int B, int H,
@@ -156,6 +159,8 @@ int mmda_lstm_tc_backward(float* gates, const float* whh_f, const float* whh_r, 
 int mmda_lstm_tc_set_max_ctas(int n);
 /* diagnostic: per-step phase timestamps of CTA 0 (NULL = off) */
 int mmda_lstm_tc_set_debug_buffer(long long* dev_buf);
+/* diagnostic, timing experiments only (results become wrong): backward kernel skips parts of a step */
+int mmda_lstm_tc_set_debug_flags(int flags);
 
 /* ---- nn.LayerNorm, src/models.py:65-80,155-157,172 and the two norms of the fusion layer ----
  * y = LN(x + res) (res may be NULL); mean/rstd saved per row for the backward. */

@@ -60,7 +60,7 @@ struct TclArgs {
   const float* dutt;      // bwd
   const float* dy;        // bwd: grad wrt y [N][2H] (nullable)
   int utt_ld, utt_off0, utt_off1;
-  int B, H, Kp, S, G, BT, NT, MT, save, Tmax;
+  int B, H, Kp, S, G, BT, NT, MT, U, save, Tmax;
   uint8_t* xch;           // fwd: h operand images [2][NT][2][2*KA*B_ATOM]; bwd: partials [2][NT][2][S][48][S*32] f32
   unsigned* flags;        // [2][NT] counters (zeroed before the launch): one tick per cell warp and step
   int* err;               // set to 1 when a peer never showed up
@@ -68,20 +68,24 @@ struct TclArgs {
 };
 
 // wait until *flag >= target (one thread); returns false after SPIN_LIMIT ticks or when another
-// CTA already gave up
+// CTA already gave up.  The flag is polled with relaxed loads + a short sleep.
 __device__ __forceinline__ bool spin_until(const unsigned* flag, unsigned target, int* err) {
-  if (ld_acquire(flag) >= target) return true;
-  const long long t0 = clock64();
-  unsigned it = 0;
-  while (ld_acquire(flag) < target) {
-    if ((++it & 255u) == 0) {
-      if (clock64() - t0 > SPIN_LIMIT || *reinterpret_cast<volatile int*>(err) != 0) {
-        *reinterpret_cast<volatile int*>(err) = 1;
-        return false;
+  bool ok = true;
+  if (ld_relaxed(flag) < target) {
+    const long long t0 = clock64();
+    unsigned it = 0;
+    while (ld_relaxed(flag) < target) {
+      if ((++it & 255u) == 0) {
+        if (clock64() - t0 > SPIN_LIMIT || *reinterpret_cast<volatile int*>(err) != 0) {
+          *reinterpret_cast<volatile int*>(err) = 1;
+          ok = false;
+          break;
+        }
       }
     }
   }
-  return true;
+  acquire_fence_gpu();     // one acquire for the whole wait (see ld_relaxed)
+  return ok;
 }
 
 // byte offset of the 16-byte chunk (row n, k-chunk ck of 8 elements) inside a K-major
@@ -239,6 +243,7 @@ __global__ void __launch_bounds__(TCL_FWD_THREADS4, 1) lstm_tc_fwd_kernel(const 
     if (warp == TCL_CELL_WARPS) {
       // ===================== control: flag wait -> bulk copy of the sub-tile's h_{t-1} image =========
       if (lane == 0) {
+        // served in item order: polling the sub-tiles' flags out of order was measured 40 % slower
         bool aborted = false;
         for (int s = 1; s < L0; ++s)
 #pragma unroll
@@ -437,50 +442,54 @@ __global__ void __launch_bounds__(TCL_FWD_THREADS4, 1) lstm_tc_fwd_kernel(const 
 // ------------------------------------------------------------------------------------------
 // backward through time
 // ------------------------------------------------------------------------------------------
-// Same sub-tile pipeline as the forward, with two 32-row sub-tiles (MMA N = 32): the backward needs
-// 6 MMAs per K step and M tile, half of them with the A operand in shared memory (~45 clk each
-// whatever N is), so fewer, wider MMAs win.  One TMEM accumulator per (sub-tile, M tile): the terms
-// are issued smallest first (2^-16 group, 2^-8 group, main), so the truncating fp32 accumulation
-// only sees the 8 main adds at full magnitude.  Roles (every role walks the items (k, s) in the
-// same order):
-//   8 cell warps  : [partials of this step reduced over the S CTAs] -> cell backward -> d(gates)
-//                   as three bf16 terms into the sub-tile's B operand (+ fp32 to global)
-//   MMA warp      : d(gates) staged -> partial dh^T[j][b] = W^T_slice * d(gates)^T for the three
-//                   M tiles (6 MMAs per K step and tile) -> commit
-//   4 writer warps: MMA done -> TMEM -> this CTA's block of the L2 partial scratch -> tick
+// Same sub-tile pipeline as the forward (three 16-row sub-tiles of a 48-row tile).  CTA r owns the
+// gate rows of U (= 30 for H = 300) hidden units and multiplies W^T_slice [H x 4U] (three M tiles
+// over the H output columns, K = its 4U gate rows) with its own d(gates) of the successor step;
+// the partial dh of the S CTAs is reduce-scattered through an L2 scratch.
+//
+// Operand splits.  d(gates) spans many binades, so every (CTA, sub-tile, step) first scales its
+// d(gates) block by a power of two s that puts the block maximum into [4, 8) (exact), then splits
+// x s = b1 + 2^-11 b2 into two fp16 terms like the forward; W^T likewise (a1 + 2^-11 a2).  The three
+// products a1 b2 + a2 b1 + a1 (2^11 b1) all carry the factor 2^11 s, so ONE TMEM accumulator per
+// (sub-tile, M tile) takes them -- cross terms first, the eight main terms last, which keeps the
+// truncating fp32 accumulation at 8 full-magnitude adds -- and the writer warps undo the factor
+// exactly.  Entries below 2^-35 of the block maximum are lost (absolute error <= 2^-38 of it).
+// With two terms per operand the whole W^T slice fits in TMEM (6 blocks of 2U columns), every MMA
+// reads its A operand from TMEM (the shared-memory A operand of the previous version cost ~45 clk
+// per MMA whatever N was) and shared memory only holds the three fp16 planes of d(gates).
+//
+// Roles (every role walks the items (k, s) in the same order):
+//   8 cell warps  : [partials of this step reduced over the S CTAs] -> cell backward -> block max
+//                   -> scaled fp16 planes of d(gates) into the sub-tile's B operand (+ fp32 to global)
+//   MMA warp      : planes staged -> 3 MMAs per K step and M tile (N = 16) -> commit
+//   4 writer warps: MMA done -> TMEM -> unscale -> this CTA's block of the L2 partial scratch -> tick
 //   control warp  : flag wait (every writer warp of the S CTAs ticked) -> release the cell warps
 constexpr int TCL_BWD_WARPS4 = TCL_CELL_WARPS + 6;
 constexpr int TCL_BWD_THREADS4 = 32 * TCL_BWD_WARPS4;
 constexpr int BWD_WRITERS = 4;
-constexpr int BSUB = 32;                       // rows of a backward sub-tile
-constexpr int BN = 32;                         // its MMA N
-constexpr int BMAXSUB = TCL_N / BSUB;
-constexpr int BSUB_ATOM = BN * 128;
+constexpr int BSUB = 16;                       // rows of a backward sub-tile = MMA N
+constexpr int BMAXSUB = 3;
+constexpr int TCL_NB = BSUB * BMAXSUB;         // rows of a backward tile
+constexpr int BSUB_ATOM = BSUB * 128;
+constexpr int BWD_PLANE = 2 * BSUB_ATOM;       // one fp16 plane of one sub-tile (K = 128: 2 atoms)
+constexpr int BWD_SUB_BYTES = 3 * BWD_PLANE;   // b1 | 2^11 b1 | b2
+constexpr int BWD_CELLS = BMAXSUB * 2 * 32 * TCL_CELL_WARPS;      // cell slots: [sub-tile][i][cell thread]
+constexpr int BWD_PRE_BYTES = BWD_CELLS * (16 + 3 * 4);          // gates float4 | c_t | c_prev | dy
 
 __global__ void __launch_bounds__(TCL_BWD_THREADS4, 1) lstm_tc_bwd_kernel(const TclArgs p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sptr = smem_raw + (sbase - smem_u32(smem_raw));
-  const int H = p.H, S = p.S, MT = p.MT;
-  // W^T slice as the A operand: M = output column j (MT tiles of 128), K = my 128 gate rows (2
-  // atoms).  Term 1 lives in TMEM; terms 2 and 3 in shared memory.  The last M tile only stores
-  // its `rows_last` real rows (the MMA still reads 128 rows: whatever follows in shared memory
-  // lands in output rows nobody reads), so its blocks come first.
-  const int rows_last = ((H - 128 * (MT - 1)) + 7) & ~7;
-  const uint32_t PB = (uint32_t)rows_last * 128;
-  const uint32_t full_off = 4 * PB;                               // [split 2][atom 2] partial blocks
-  const uint32_t dG_off = full_off + (uint32_t)(2 * (MT - 1) * 2) * A_ATOM;
-  const uint32_t dG_split = 2 * BSUB_ATOM;                         // one bf16 term of one sub-tile (2 K atoms)
-  const uint32_t dG_sub = 3 * dG_split;
-  const uint32_t misc_off = dG_off + BMAXSUB * dG_sub;
-  auto wt_block = [&](int sp, int mt, int a) -> uint32_t {      // sp: 0 = term 2, 1 = term 3
-    return mt == MT - 1 ? (uint32_t)(sp * 2 + a) * PB
-                        : full_off + (uint32_t)((sp * (MT - 1) + mt) * 2 + a) * A_ATOM;
-  };
+  const int H = p.H, S = p.S, MT = p.MT, U = p.U;
+  const int Kc = 2 * U;                                            // TMEM columns of one W^T block
+  // per-thread staging of the next step's cell inputs (cp.async, one step ahead: HBM latency)
+  const uint32_t pre_off = BMAXSUB * BWD_SUB_BYTES;
+  const uint32_t misc_off = pre_off + BWD_PRE_BYTES;
   auto mma_bar = [&](int k) { return sbase + misc_off + 8u * (uint32_t)k; };
-  auto dg_bar = [&](int k) { return sbase + misc_off + 24u + 8u * (uint32_t)k; };
-  auto part_bar = [&](int k) { return sbase + misc_off + 48u + 8u * (uint32_t)k; };
-  const uint32_t tmem_slot = sbase + misc_off + 72;
+  auto dg_bar = [&](int k) { return sbase + misc_off + 32u + 8u * (uint32_t)k; };
+  auto part_bar = [&](int k) { return sbase + misc_off + 64u + 8u * (uint32_t)k; };
+  const uint32_t tmem_slot = sbase + misc_off + 96;
+  unsigned* smax = reinterpret_cast<unsigned*>(sptr + misc_off + 100);   // [2][BMAXSUB] block maxima (float bits)
   int* lens_s = reinterpret_cast<int*>(sptr + misc_off + 128);
   int* orig_s = lens_s + TCL_N;
   int* cnt_s = orig_s + TCL_N;               // [Tmax]: rows of the TILE alive at time t
@@ -499,6 +508,7 @@ __global__ void __launch_bounds__(TCL_BWD_THREADS4, 1) lstm_tc_bwd_kernel(const 
       mbar_init(dg_bar(k), TCL_CELL_WARPS);
       mbar_init(part_bar(k), 1);
     }
+    for (int i = 0; i < 2 * BMAXSUB; ++i) smax[i] = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) tmem_alloc512(tmem_slot);
@@ -506,43 +516,43 @@ __global__ void __launch_bounds__(TCL_BWD_THREADS4, 1) lstm_tc_bwd_kernel(const 
   fence_before();
   __syncthreads();
   fence_after();
-  const uint32_t tm = *reinterpret_cast<uint32_t*>(sptr + misc_off + 72);
-  const uint32_t tmD = tm + MT * 64;          // [sub-tile][M tile][32 columns]
+  const uint32_t tm = *reinterpret_cast<uint32_t*>(sptr + misc_off + 96);
+  auto w_blk = [&](int mt, int term) { return tm + (uint32_t)((mt * 2 + term) * Kc); };
+  const uint32_t tmD = tm + (uint32_t)((MT * 2 * Kc + 4 + 15) & ~15);   // [sub-tile][M tile][16 columns]
   const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
 
-  if (warp < TCL_CELL_WARPS) {  // A[j][rho] = W_hh[(rho&3)*H + 32r + (rho>>2)][j]
+  if (warp < TCL_CELL_WARPS) {  // A[j][rho] = W_hh[(rho&3)*H + r*U + (rho>>2)][j], rho < 4U
     const float* __restrict__ W = p.whh[dir];
+    const int nck = Kc >> 2;                          // 8-element chunks of one block row
     for (int mt = 0; mt < MT; ++mt) {
-      const int jl = q * 32 + lane, j = mt * 128 + jl;
+      const int j = mt * 128 + q * 32 + lane;
       const bool j_ok = j < H;
-      const bool st_ok = mt < MT - 1 || jl < rows_last;
-      for (int ck = hc * 8; ck < hc * 8 + 8; ++ck) {
+      for (int ck = hc; ck < nck; ck += 2) {
         float x[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int rho = ck * 8 + i, uu = r * TCL_UNITS + (rho >> 2);
+          const int rho = ck * 8 + i, uu = r * U + (rho >> 2);
           x[i] = (j_ok && uu < H) ? __ldg(W + (size_t)((rho & 3) * H + uu) * H + j) : 0.f;
         }
-        uint4 w1, w2, w3;
-        split3x8(x, w1, w2, w3);
-        tmem_st4(tm + lane_sel + mt * 64 + ck * 4, w1.x, w1.y, w1.z, w1.w);
-        if (st_ok) {
-          const uint32_t o = (uint32_t)((jl >> 3) * 1024 + (jl & 7) * 128 + (((ck & 7) ^ (jl & 7)) << 4));
-          *reinterpret_cast<uint4*>(sptr + wt_block(0, mt, ck >> 3) + o) = w2;
-          *reinterpret_cast<uint4*>(sptr + wt_block(1, mt, ck >> 3) + o) = w3;
-        }
+        uint4 w1, w2;
+        split2hx8(x, w1, w2);
+        tmem_st4(w_blk(mt, 0) + lane_sel + ck * 4, w1.x, w1.y, w1.z, w1.w);
+        tmem_st4(w_blk(mt, 1) + lane_sel + ck * 4, w2.x, w2.y, w2.z, w2.w);
       }
     }
+    // the last K step of a block may read 4 columns past it: W of the next block (finite, times
+    // the zero rows of the B operand) -- and these zero columns after the last block
+    if (hc == 0) tmem_st4(tm + lane_sel + (uint32_t)(MT * 2 * Kc), 0u, 0u, 0u, 0u);
     tmem_wait_st();
   }
-  for (uint32_t i = tid; i < BMAXSUB * dG_sub / 16; i += TCL_BWD_THREADS4)   // pad rows of the B operands
-    reinterpret_cast<uint4*>(sptr + dG_off)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (uint32_t i = tid; i < BMAXSUB * BWD_SUB_BYTES / 16; i += TCL_BWD_THREADS4)
+    reinterpret_cast<uint4*>(sptr)[i] = make_uint4(0u, 0u, 0u, 0u);
   fence_async_smem();
   fence_before();
   __syncthreads();
 
   const int H2 = 2 * H, H8 = 8 * H;
-  uint32_t n_done[BMAXSUB] = {0, 0};       // completed phases of "my" barrier of each sub-tile
+  uint32_t n_done[BMAXSUB] = {0, 0, 0};      // completed phases of "my" barrier of each sub-tile
   const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0;
 #define TCL_TS(i) if (dbg_on && tile == grp && k == 0) p.dbg[s * 16 + (i)] = clock64();
 
@@ -568,7 +578,7 @@ __global__ void __launch_bounds__(TCL_BWD_THREADS4, 1) lstm_tc_bwd_kernel(const 
     __syncthreads();
     unsigned* flags = p.flags + (size_t)(dir * p.NT + tile) * BMAXSUB;
     const size_t slab = (size_t)BSUB * XLD;                      // one CTA's partial block of a sub-tile
-    // partial scratch of this tile: [k][parity][S][32][XLD]
+    // partial scratch of this tile: [k][parity][S][16][XLD]
     float* part = reinterpret_cast<float*>(p.xch) + (size_t)(dir * p.NT + tile) * BMAXSUB * 2 * S * slab;
 
     if (warp == TCL_CELL_WARPS + 5) {
@@ -597,39 +607,23 @@ __global__ void __launch_bounds__(TCL_BWD_THREADS4, 1) lstm_tc_bwd_kernel(const 
           ++n_done[k];
           fence_after();
           if (lane == 0) { TCL_TS(2) }
-          const uint32_t idesc = idesc_bf16(128, BN);
-          const uint64_t b1_0 = make_desc(sbase + dG_off + (uint32_t)k * dG_sub, 16, 1024);
-          const uint64_t b2_0 = b1_0 + (uint64_t)(dG_split >> 4), b3_0 = b2_0 + (uint64_t)(dG_split >> 4);
+          const uint32_t idesc = idesc_f16(128, BSUB);
+          const uint64_t b1_0 = make_desc(sbase + (uint32_t)k * BWD_SUB_BYTES, 16, 1024);
+          const uint64_t B1_0 = b1_0 + (uint64_t)(BWD_PLANE >> 4), b2_0 = B1_0 + (uint64_t)(BWD_PLANE >> 4);
           if (elect_one()) {
             for (int mt = 0; mt < MT; ++mt) {
-              const uint32_t d = tmD + (uint32_t)(k * MT + mt) * BN;
-              const uint32_t a1_0 = tm + mt * 64;
-              uint64_t a2_[2], a3_[2];
+              const uint32_t d = tmD + (uint32_t)(k * MT + mt) * BSUB;
+              const uint32_t a1 = w_blk(mt, 0), a2 = w_blk(mt, 1);
 #pragma unroll
-              for (int a = 0; a < 2; ++a) {
-                a2_[a] = make_desc(sbase + wt_block(0, mt, a), 16, 1024);
-                a3_[a] = make_desc(sbase + wt_block(1, mt, a), 16, 1024);
-              }
-              // smallest terms first: 2^-16 group, 2^-8 group, main
-#pragma unroll
-              for (int ks = 0; ks < 8; ++ks) {
-                const int a = ks >> 2;
-                const uint64_t ko = (uint64_t)((a * BSUB_ATOM) >> 4) + 2 * (ks & 3), ka = 2 * (ks & 3);
-                mma_ts(d, a1_0 + ks * 8, b3_0 + ko, idesc, ks > 0 ? 1u : 0u);
-                mma_ss(d, a3_[a] + ka, b1_0 + ko, idesc, 1u);
-                mma_ss(d, a2_[a] + ka, b2_0 + ko, idesc, 1u);
-              }
-#pragma unroll
-              for (int ks = 0; ks < 8; ++ks) {
-                const int a = ks >> 2;
-                const uint64_t ko = (uint64_t)((a * BSUB_ATOM) >> 4) + 2 * (ks & 3), ka = 2 * (ks & 3);
-                mma_ts(d, a1_0 + ks * 8, b2_0 + ko, idesc, 1u);
-                mma_ss(d, a2_[a] + ka, b1_0 + ko, idesc, 1u);
-              }
-#pragma unroll
-              for (int ks = 0; ks < 8; ++ks) {
+              for (int ks = 0; ks < 8; ++ks) {        // cross terms (scale 2^11 s)
                 const uint64_t ko = (uint64_t)(((ks >> 2) * BSUB_ATOM) >> 4) + 2 * (ks & 3);
-                mma_ts(d, a1_0 + ks * 8, b1_0 + ko, idesc, 1u);
+                mma_ts(d, a1 + ks * 8, b2_0 + ko, idesc, ks > 0 ? 1u : 0u);
+                mma_ts(d, a2 + ks * 8, b1_0 + ko, idesc, 1u);
+              }
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks) {        // main term against 2^11 b1
+                const uint64_t ko = (uint64_t)(((ks >> 2) * BSUB_ATOM) >> 4) + 2 * (ks & 3);
+                mma_ts(d, a1 + ks * 8, B1_0 + ko, idesc, 1u);
               }
             }
             commit(mma_bar(k));
@@ -654,24 +648,30 @@ __global__ void __launch_bounds__(TCL_BWD_THREADS4, 1) lstm_tc_bwd_kernel(const 
           ++n_done[k];
           fence_after();
           if (lane == 0 && q == 0) { TCL_TS(4) }
+          // undo 2^11 * s of the block of step s-1 (same exponent arithmetic as the cell warps)
+          const unsigned mxb = *reinterpret_cast<volatile unsigned*>(smax + ((s - 1) & 1) * BMAXSUB + k);
+          const int e = mxb == 0u ? 0 : min(120, max(-120, 129 - (int)((mxb >> 23) & 0xffu)));
+          const float unscale = ldexpf(1.f, -11 - e);
           float* dst = part + (((size_t)k * 2 + (s & 1)) * S + r) * slab;
           for (int mt = 0; mt < MT; ++mt) {
             const int j = mt * 128 + q * 32 + lane;
-            uint32_t v0[8], v1[8], v2[8], v3[8];
-            const uint32_t col = (uint32_t)(k * MT + mt) * BN;
-            tmem_ld8(tmD + lane_sel + col, v0);
-            tmem_ld8(tmD + lane_sel + col + 8, v1);
-            tmem_ld8(tmD + lane_sel + col + 16, v2);
-            tmem_ld8(tmD + lane_sel + col + 24, v3);
-            tmem_wait_ld();
-            if (j < H) {
+            uint32_t v0[8], v1[8];
+            const uint32_t col = (uint32_t)(k * MT + mt) * BSUB;
+            if (!(p.save & 2)) {
+              tmem_ld8(tmD + lane_sel + col, v0);
+              tmem_ld8(tmD + lane_sel + col + 8, v1);
+              tmem_wait_ld();
+            } else {
 #pragma unroll
-              for (int jj = 0; jj < 8; ++jj) {
-                if (jj < n_prev) __stcg(dst + (size_t)jj * XLD + j, __uint_as_float(v0[jj]));
-                if (jj + 8 < n_prev) __stcg(dst + (size_t)(jj + 8) * XLD + j, __uint_as_float(v1[jj]));
-                if (jj + 16 < n_prev) __stcg(dst + (size_t)(jj + 16) * XLD + j, __uint_as_float(v2[jj]));
-                if (jj + 24 < n_prev) __stcg(dst + (size_t)(jj + 24) * XLD + j, __uint_as_float(v3[jj]));
-              }
+              for (int jj = 0; jj < 8; ++jj) { v0[jj] = 0u; v1[jj] = 0u; }
+            }
+            // plain (weak) stores: the release of the tick below publishes them
+            float* dj = dst + min(j, H - 1);
+            const bool ok = j < H && !(p.save & 1);
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+              if (ok && jj < n_prev) dj[(size_t)jj * XLD] = __uint_as_float(v0[jj]) * unscale;
+              if (ok && jj + 8 < n_prev) dj[(size_t)(jj + 8) * XLD] = __uint_as_float(v1[jj]) * unscale;
             }
           }
           if (lane == 0 && q == 0) { TCL_TS(8) }
@@ -683,23 +683,43 @@ __global__ void __launch_bounds__(TCL_BWD_THREADS4, 1) lstm_tc_bwd_kernel(const 
       continue;
     }
 
-    // ===================== cell warps: lane = local unit, warp w owns rows w, w + 8, w + 16, w + 24 of a sub-tile ====
-    const int ul = lane, u = r * TCL_UNITS + ul;
-    const bool u_ok = u < H;
+    // ===================== cell warps: lane = local unit, warp w owns rows w and w + 8 of a sub-tile ====
+    const int ul = lane, u = r * U + ul;
+    const bool u_ok = ul < U && u < H;
     const int gcol = dir * 4 * H + u * 4;
     const int ycol = dir * H + u;
     const int utt_off = dir == 0 ? p.utt_off0 : p.utt_off1;
-    float dcst[BMAXSUB][4];
-    int len_c[BMAXSUB][4], orig_c[BMAXSUB][4];
+    float dcst[BMAXSUB][2];
+    int len_c[BMAXSUB][2], orig_c[BMAXSUB][2];
 #pragma unroll
     for (int k = 0; k < BMAXSUB; ++k)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < 2; ++i) {
         dcst[k][i] = 0.f;
         const int b = k * BSUB + warp + 8 * i;
         len_c[k][i] = u_ok ? lens_s[b] : 0;
         orig_c[k][i] = orig_s[b];
       }
+    float4* pre_g = reinterpret_cast<float4*>(sptr + pre_off);
+    float* pre_f = reinterpret_cast<float*>(sptr + pre_off + BWD_CELLS * 16);
+    auto prefetch_cells = [&](int k, int tn) {      // stage the inputs of sub-tile k's cells at time tn
+      const int off_n = offs_s[tn];
+      const int tpn = dir == 0 ? tn - 1 : tn + 1;   // forward-order predecessor of tn
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        if (tn >= len_c[k][i]) continue;
+        const int b = k * BSUB + warp + 8 * i, slot = (k * 2 + i) * 256 + tid;
+        const size_t row = (size_t)(off_n + b_base + b);
+        cp_async16(pre_g + slot, p.gates + row * H8 + gcol);
+        cp_async4(pre_f + slot, p.c + row * H2 + ycol);
+        const bool hp = dir == 0 ? (tn >= 1) : (tn + 1 < len_c[k][i]);
+        if (hp) cp_async4(pre_f + BWD_CELLS + slot, p.c + (size_t)(offs_s[tpn] + b_base + b) * H2 + ycol);
+        if (p.dy) cp_async4(pre_f + 2 * BWD_CELLS + slot, p.dy + row * H2 + ycol);
+      }
+    };
+#pragma unroll
+    for (int k = 0; k < BMAXSUB; ++k)
+      if (k < nsub) prefetch_cells(k, dir == 0 ? Lk[k] - 1 : 0);
 
     for (int s = 0; s < L0; ++s)
 #pragma unroll
@@ -707,62 +727,65 @@ __global__ void __launch_bounds__(TCL_BWD_THREADS4, 1) lstm_tc_bwd_kernel(const 
         if (s >= Lk[k]) continue;
         const int t = dir == 0 ? Lk[k] - 1 - s : s;
         if (tid == 0) { TCL_TS(0) }
-        // ---- everything the cell backward needs that does not depend on the exchange ----
+        // ---- everything the cell backward needs that does not depend on the exchange: staged in
+        // shared memory by this thread's own cp.async of the previous step (or the tile prologue) ----
         const int off_t = offs_s[t];
-        const int tp = dir == 0 ? t - 1 : t + 1;      // forward-order predecessor (its c is c_prev)
-        float4 gt[4];
-        float ct[4], cp[4], dh[4];
-        bool act[4], rec[4];
+        float4 gt[2];
+        float ct[2], cp[2], dh[2];
+        bool act[2], rec[2];
+        cp_async_wait_all();
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int b = k * BSUB + warp + 8 * i;
+        for (int i = 0; i < 2; ++i) {
+          const int slot = (k * 2 + i) * 256 + tid;
           act[i] = t < len_c[k][i];
           rec[i] = false;
           ct[i] = 0.f; cp[i] = 0.f; dh[i] = 0.f;
           gt[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (act[i]) {
-            const size_t row = (size_t)(off_t + b_base + b);
-            gt[i] = *reinterpret_cast<const float4*>(p.gates + row * H8 + gcol);
-            ct[i] = p.c[row * H2 + ycol];
+          if (act[i] && !(p.save & 16)) {
+            gt[i] = pre_g[slot];
+            ct[i] = pre_f[slot];
             const bool hp = dir == 0 ? (t >= 1) : (t + 1 < len_c[k][i]);
-            if (hp) cp[i] = p.c[(size_t)(offs_s[tp] + b_base + b) * H2 + ycol];
-            if (p.dy) dh[i] = p.dy[row * H2 + ycol];
+            if (hp) cp[i] = pre_f[BWD_CELLS + slot];
+            if (p.dy) dh[i] = pre_f[2 * BWD_CELLS + slot];
             const bool fin = dir == 0 ? (t == len_c[k][i] - 1) : (t == 0);
             if (fin && p.dutt) dh[i] += p.dutt[(size_t)orig_c[k][i] * p.utt_ld + utt_off + u];
             rec[i] = dir == 0 ? (t + 1 < len_c[k][i]) : (t >= 1);
+          } else if (act[i]) {
+            rec[i] = dir == 0 ? (t + 1 < len_c[k][i]) : (t >= 1);
           }
         }
+        if (s + 1 < Lk[k]) prefetch_cells(k, dir == 0 ? t - 1 : t + 1);     // inputs of (k, s+1)
         if (s > 0) {
           mbar_wait(part_bar(k), n_done[k] & 1);   // every CTA's partials of (k, s) are in L2
           ++n_done[k];
           if (tid == 0) { TCL_TS(6) }
           // ---- reduce my columns over the S partial blocks (all loads in flight at once) ----
           const float* src = part + ((size_t)k * 2 + (s & 1)) * S * slab + u;
+          float v[2][12];
 #pragma unroll
-          for (int h2 = 0; h2 < 2; ++h2) {        // two cells (24 loads) in flight at a time
-            float v[2][12];
+          for (int i = 0; i < 2; ++i) {
+            const int n = warp + 8 * i;
 #pragma unroll
-            for (int ii = 0; ii < 2; ++ii) {
-              const int i = h2 * 2 + ii, n = warp + 8 * i;
+            for (int rr = 0; rr < 12; ++rr)
+              v[i][rr] = (act[i] && rec[i] && rr < S && !(p.save & 4)) ? __ldcg(src + (size_t)rr * slab + (size_t)n * XLD) : 0.f;
+          }
 #pragma unroll
-              for (int rr = 0; rr < 12; ++rr)
-                v[ii][rr] = (act[i] && rec[i] && rr < S) ? __ldcg(src + (size_t)rr * slab + (size_t)n * XLD) : 0.f;
-            }
+          for (int i = 0; i < 2; ++i) {
+            float sum = 0.f;
 #pragma unroll
-            for (int ii = 0; ii < 2; ++ii) {
-              float sum = 0.f;
-#pragma unroll
-              for (int rr = 0; rr < 12; ++rr) sum += v[ii][rr];
-              dh[h2 * 2 + ii] += sum;
-            }
+            for (int rr = 0; rr < 12; ++rr) sum += v[i][rr];
+            dh[i] += sum;
           }
         }
-        // ---- cell backward; d(gates) -> my rows of the sub-tile's B operand (3 bf16 terms) ----
+        if (tid == 0) { TCL_TS(10) }
+        // every cell warp is past item (k, s-1): the slot of the NEXT step can be cleared
+        if (tid == 0) smax[((s + 1) & 1) * BMAXSUB + k] = 0u;
+        // ---- cell backward ----
         const bool more = s + 1 < Lk[k];
-        float4 dgv[4];
+        float4 dgv[2];
+        float mx = 0.f;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int n = warp + 8 * i;
+        for (int i = 0; i < 2; ++i) {
           float dig = 0.f, dfg = 0.f, dgg = 0.f, dog = 0.f;
           if (act[i]) {
             const float ig = gt[i].x, fg = gt[i].y, gg = gt[i].z, og = gt[i].w;
@@ -775,22 +798,38 @@ __global__ void __launch_bounds__(TCL_BWD_THREADS4, 1) lstm_tc_bwd_kernel(const 
             dcst[k][i] = dc * fg;
           }
           dgv[i] = make_float4(dig, dfg, dgg, dog);
-          if (more) {
-            uint32_t a[4], bb[4], cc[4];
-            split3(dig, a[0], bb[0], cc[0]);
-            split3(dfg, a[1], bb[1], cc[1]);
-            split3(dgg, a[2], bb[2], cc[2]);
-            split3(dog, a[3], bb[3], cc[3]);
-            // row n of the K-major operand, k = 4*ul .. 4*ul+3
-            const uint32_t o = dG_off + (uint32_t)k * dG_sub + (uint32_t)(ul >> 4) * BSUB_ATOM +
-                               (uint32_t)(n >> 3) * 1024 + (uint32_t)(n & 7) * 128 +
-                               (uint32_t)((((ul & 15) >> 1) ^ (n & 7)) << 4) + (uint32_t)(ul & 1) * 8;
-            *reinterpret_cast<uint2*>(sptr + o) = make_uint2(a[0] | (a[1] << 16), a[2] | (a[3] << 16));
-            *reinterpret_cast<uint2*>(sptr + o + dG_split) = make_uint2(bb[0] | (bb[1] << 16), bb[2] | (bb[3] << 16));
-            *reinterpret_cast<uint2*>(sptr + o + 2 * dG_split) = make_uint2(cc[0] | (cc[1] << 16), cc[2] | (cc[3] << 16));
-          }
+          mx = fmaxf(mx, fmaxf(fmaxf(fabsf(dig), fabsf(dfg)), fmaxf(fabsf(dgg), fabsf(dog))));
         }
         if (more) {
+          // ---- block maximum over the 8 cell warps -> power-of-two scale s.t. max in [4, 8) ----
+          mx = warp_max(mx);
+          if (!(mx < 3.0e38f)) mx = 3.0e38f;                    // inf / nan guard: keep the exponent finite
+          if (lane == 0) atomicMax(smax + (s & 1) * BMAXSUB + k, __float_as_uint(mx));
+          if (tid == 0) { TCL_TS(11) }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (tid == 0) { TCL_TS(12) }
+          const unsigned mxb = *reinterpret_cast<volatile unsigned*>(smax + (s & 1) * BMAXSUB + k);
+          const int e = mxb == 0u ? 0 : min(120, max(-120, 129 - (int)((mxb >> 23) & 0xffu)));
+          const float sc = ldexpf(1.f, e);
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int n = warp + 8 * i;
+            const float x[4] = {dgv[i].x * sc, dgv[i].y * sc, dgv[i].z * sc, dgv[i].w * sc};
+            uint32_t b1[4], b2[4], B1[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              split2h(x[g], b1[g], b2[g]);
+              const float hi = __half2float(__ushort_as_half((unsigned short)b1[g]));
+              B1[g] = (uint32_t)__half_as_ushort(__float2half_rn(hi * 2048.f));   // exact: |hi| < 8
+            }
+            // row n of the K-major operand, k = 4*ul .. 4*ul+3
+            const uint32_t o = (uint32_t)k * BWD_SUB_BYTES + (uint32_t)(ul >> 4) * BSUB_ATOM +
+                               (uint32_t)(n >> 3) * 1024 + (uint32_t)(n & 7) * 128 +
+                               (uint32_t)((((ul & 15) >> 1) ^ (n & 7)) << 4) + (uint32_t)(ul & 1) * 8;
+            *reinterpret_cast<uint2*>(sptr + o) = make_uint2(b1[0] | (b1[1] << 16), b1[2] | (b1[3] << 16));
+            *reinterpret_cast<uint2*>(sptr + o + BWD_PLANE) = make_uint2(B1[0] | (B1[1] << 16), B1[2] | (B1[3] << 16));
+            *reinterpret_cast<uint2*>(sptr + o + 2 * BWD_PLANE) = make_uint2(b2[0] | (b2[1] << 16), b2[2] | (b2[3] << 16));
+          }
           fence_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(dg_bar(k));
@@ -798,8 +837,8 @@ __global__ void __launch_bounds__(TCL_BWD_THREADS4, 1) lstm_tc_bwd_kernel(const 
         if (tid == 0) { TCL_TS(7) }
         // the GEMM operand copy of d(gates): nobody inside this launch waits for it
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (act[i])
+        for (int i = 0; i < 2; ++i)
+          if (act[i] && !(p.save & 8))
             *reinterpret_cast<float4*>(p.gates + (size_t)(off_t + b_base + k * BSUB + warp + 8 * i) * H8 + gcol) = dgv[i];
       }
   }
@@ -813,48 +852,61 @@ __global__ void __launch_bounds__(TCL_BWD_THREADS4, 1) lstm_tc_bwd_kernel(const 
 // host side
 // ------------------------------------------------------------------------------------------
 struct TclPlan {
-  int S, G, BT, NT, Kp, MT;
+  int Kp, MT;
+  int S, G, BT, NT;            // forward: slices of 32 units, groups, batch tile (<= 64), tiles
+  int Sb, Gb, BTb, NTb, Ub;    // backward: slices of Ub units, groups, batch tile (<= 48), tiles
   size_t smem_fwd, smem_bwd, flag_off, xch_off, total;
 };
 
-int g_tcl_max_ctas = 120;   // leaves 28 SMs to the visual / acoustic encoders and the GEMMs running next to it
+int g_tcl_max_ctas = 120;   // upper bound on the SMs one launch occupies
 
 int tcl_make_plan(int B, int H, int Tmax, TclPlan* pl) {
   if (H <= 128 || H > 320 || B <= 0) return MMDA_ERR_UNSUPPORTED;
-  const int S = (H + TCL_UNITS - 1) / TCL_UNITS;
   const int Kp = (H + 15) & ~15;
   const int MT = (H + 127) / 128;
   const int KA = (Kp + 63) / 64;
-  int Gmax = g_tcl_max_ctas / (2 * S);
-  if (Gmax < 1) Gmax = 1;
-  // A time step is a latency chain (MMA -> cell update -> L2 exchange), not SM-bound work: more,
-  // smaller tiles do not shorten it, they only take SMs away from the kernels running next to
-  // this one.  So: the fewest tiles that cover the batch, spread evenly over the rounds.
-  const int nt_min = (B + TCL_N - 1) / TCL_N;
-  int NT = nt_min;
-  const int BT = (B + NT - 1) / NT;
-  NT = (B + BT - 1) / BT;
-  const int rounds = (NT + Gmax - 1) / Gmax;
-  pl->S = S; pl->Kp = Kp; pl->MT = MT; pl->NT = NT; pl->BT = BT;
-  pl->G = (NT + rounds - 1) / rounds;
+  pl->Kp = Kp; pl->MT = MT;
+  // A time step is a latency chain (MMA -> cell update -> L2 exchange), not SM-bound work: the
+  // fewest tiles that cover the batch, spread evenly over the rounds.
+  auto tiles = [&](int rows_max, int S, int* BT, int* NT, int* G) {
+    int Gmax = g_tcl_max_ctas / (2 * S);
+    if (Gmax < 1) Gmax = 1;
+    int nt = (B + rows_max - 1) / rows_max;
+    *BT = (B + nt - 1) / nt;
+    *NT = (B + *BT - 1) / *BT;
+    const int rounds = (*NT + Gmax - 1) / Gmax;
+    *G = (*NT + rounds - 1) / rounds;
+  };
+  pl->S = (H + TCL_UNITS - 1) / TCL_UNITS;
+  tiles(TCL_N, pl->S, &pl->BT, &pl->NT, &pl->G);
+  // backward: the whole W^T slice (two fp16 terms, MT tiles of 2U columns) + the accumulators
+  // (3 sub-tiles x MT tiles x 16 columns) must fit the 512 TMEM columns; U even
+  int Sb = pl->S, Ub = 0;
+  for (;; ++Sb) {
+    Ub = ((H + Sb - 1) / Sb + 1) & ~1;
+    if (((MT * 2 * 2 * Ub + 4 + 15) & ~15) + BMAXSUB * MT * BSUB <= 512 && Ub <= TCL_UNITS) break;
+    if (Sb > 64) return MMDA_ERR_UNSUPPORTED;
+  }
+  pl->Sb = Sb; pl->Ub = Ub;
+  tiles(TCL_NB, Sb, &pl->BTb, &pl->NTb, &pl->Gb);
   const size_t misc = MISC_FIXED + (size_t)(2 * Tmax + 2) * 4;
   pl->smem_fwd = 1024 + (size_t)MAXSUB * (2 * KA * SUB_ATOM + STAGE_BYTES) + misc;
-  const int rows_last = ((H - 128 * (MT - 1)) + 7) & ~7;
-  pl->smem_bwd = 1024 + (size_t)4 * rows_last * 128 + (size_t)(2 * (MT - 1) * 2) * A_ATOM +
-                 (size_t)BMAXSUB * 3 * 2 * BSUB_ATOM + misc;
+  pl->smem_bwd = 1024 + (size_t)BMAXSUB * BWD_SUB_BYTES + BWD_PRE_BYTES + misc;
   if (pl->smem_fwd > 232448 || pl->smem_bwd > 232448) return MMDA_ERR_UNSUPPORTED;
-  // workspace: [err (256 B)] [flags fwd+bwd 2*2*NT u32, padded] [exchange / partial scratch]
+  // workspace: [err (256 B)] [flags, padded] [exchange images (forward) / partial scratch (backward)]
   pl->flag_off = 256;
-  const size_t flag_bytes = ((size_t)2 * NT * MAXSUB * 4 + 255) & ~(size_t)255;
+  const int nt_max = pl->NT > pl->NTb ? pl->NT : pl->NTb;
+  const size_t flag_bytes = ((size_t)2 * nt_max * MAXSUB * 4 + 255) & ~(size_t)255;
   pl->xch_off = pl->flag_off + flag_bytes;
-  const size_t XLD = (size_t)S * TCL_UNITS;
-  const size_t fwd_x = (size_t)2 * NT * MAXSUB * 2 * (2 * KA * SUB_ATOM);
-  const size_t bwd_x = (size_t)2 * NT * BMAXSUB * 2 * S * BSUB * XLD * 4;
+  const size_t fwd_x = (size_t)2 * pl->NT * MAXSUB * 2 * (2 * KA * SUB_ATOM);
+  const size_t bwd_x = (size_t)2 * pl->NTb * BMAXSUB * 2 * Sb * BSUB * (Sb * TCL_UNITS) * 4;
   pl->total = pl->xch_off + (fwd_x > bwd_x ? fwd_x : bwd_x);
   return MMDA_OK;
 }
 
 long long* g_tcl_dbg = nullptr;
+int g_tcl_dbg_flags = 0;    // timing experiments only (results become wrong): see mmda_lstm_tc_set_debug_flags
+int g_tcl_plan_bwd = 0;     // mmda_lstm_tc_plan reports the backward decomposition when set
 
 }  // namespace
 
@@ -878,6 +930,17 @@ int mmda_lstm_tc_plan(int B, int H, int Tmax, int* out8) {
   }
   out8[0] = pl.S; out8[1] = pl.G; out8[2] = pl.BT; out8[3] = pl.NT; out8[4] = pl.Kp;
   out8[5] = (int)pl.smem_fwd; out8[6] = (int)pl.smem_bwd; out8[7] = 2 * pl.S * pl.G;
+  if (g_tcl_plan_bwd) {
+    out8[0] = pl.Sb; out8[1] = pl.Gb; out8[2] = pl.BTb; out8[3] = pl.NTb; out8[4] = pl.Ub;
+    out8[7] = 2 * pl.Sb * pl.Gb;
+  }
+  return MMDA_OK;
+}
+
+// which decomposition mmda_lstm_tc_plan reports: 0 = forward (default), 1 = backward
+// ({slices, groups, batch tile, tiles, units per CTA, smem fwd, smem bwd, CTAs})
+int mmda_lstm_tc_plan_select(int backward) {
+  g_tcl_plan_bwd = backward != 0;
   return MMDA_OK;
 }
 
@@ -885,6 +948,13 @@ int mmda_lstm_tc_plan(int B, int H, int Tmax, int* out8) {
 int mmda_lstm_tc_set_max_ctas(int n) {
   MMDA_REQUIRE(n >= 2 && n <= 1024, "lstm_tc: max CTAs must be in [2, 1024]");
   g_tcl_max_ctas = n;
+  return MMDA_OK;
+}
+
+// timing experiments on the backward kernel (the results become WRONG): bit 0 = writers skip their
+// stores, bit 1 = writers skip the TMEM loads, bit 2 = cells skip the partial loads
+int mmda_lstm_tc_set_debug_flags(int flags) {
+  g_tcl_dbg_flags = flags;
   return MMDA_OK;
 }
 
@@ -906,10 +976,12 @@ static int tcl_launch(bool bwd, TclArgs& a, int B, int H, int Tmax, void* ws, cu
   a.err = reinterpret_cast<int*>(w);
   a.flags = reinterpret_cast<unsigned*>(w + pl.flag_off);
   a.xch = w + pl.xch_off;
-  a.B = B; a.H = H; a.Kp = pl.Kp; a.S = pl.S; a.G = pl.G; a.BT = pl.BT; a.NT = pl.NT; a.MT = pl.MT;
+  a.B = B; a.H = H; a.Kp = pl.Kp; a.MT = pl.MT;
+  if (bwd) { a.S = pl.Sb; a.G = pl.Gb; a.BT = pl.BTb; a.NT = pl.NTb; a.U = pl.Ub; }
+  else { a.S = pl.S; a.G = pl.G; a.BT = pl.BT; a.NT = pl.NT; a.U = TCL_UNITS; }
   a.Tmax = Tmax;
   a.dbg = g_tcl_dbg;
-  MMDA_CUDA(cudaMemsetAsync(a.flags, 0, (size_t)2 * pl.NT * MAXSUB * 4, stream));
+  MMDA_CUDA(cudaMemsetAsync(a.flags, 0, (size_t)2 * a.NT * MAXSUB * 4, stream));
   const size_t smem = bwd ? pl.smem_bwd : pl.smem_fwd;
   auto kern = bwd ? lstm_tc_bwd_kernel : lstm_tc_fwd_kernel;
   MMDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -917,7 +989,7 @@ static int tcl_launch(bool bwd, TclArgs& a, int B, int H, int Tmax, void* ws, cu
   // resident at the same time: a cooperative launch makes the driver guarantee exactly that (it
   // refuses the launch otherwise) instead of relying on the grid being smaller than the chip.
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(2 * pl.S * pl.G, 1, 1);
+  cfg.gridDim = dim3(2 * a.S * a.G, 1, 1);
   cfg.blockDim = dim3(bwd ? TCL_BWD_THREADS4 : TCL_FWD_THREADS4, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
@@ -956,6 +1028,7 @@ int mmda_lstm_tc_backward(float* gates, const float* whh_f, const float* whh_r, 
   a.gates = gates; a.whh[0] = whh_f; a.whh[1] = whh_r; a.c = const_cast<float*>(c);
   a.dy = dy; a.dutt = dutt; a.utt_ld = utt_ld; a.utt_off0 = utt_off_f; a.utt_off1 = utt_off_r;
   a.lens = lens_sorted; a.sorted_idx = sorted_idx; a.offsets = offsets;
+  a.save = g_tcl_dbg_flags;
   return tcl_launch(true, a, B, H, Tmax, ws, stream);
 }
 

@@ -287,11 +287,13 @@ class MisaEngine:
             ev.record(torch.cuda.current_stream())
             self.fork_log.append((tag, ev))
 
-    def _fork(self, fns):
+    def _fork(self, fns, text_first=False):
         """Run fns[m]() for m in v, a on side streams (after everything enqueued so far on the
-        current stream) and fns['t']() on the current stream; join before returning."""
+        current stream) and fns['t']() on the text stream; join before returning.  With
+        ``text_first`` the text function is enqueued first, so the side streams can wait on events
+        it recorded (`_order_events`)."""
         if not self.multi_stream or _DRYRUN:
-            for m in ("v", "a", "t"):
+            for m in (("t", "v", "a") if text_first else ("v", "a", "t")):
                 fns[m]()
             return
         main = torch.cuda.current_stream()
@@ -301,35 +303,47 @@ class MisaEngine:
         done = []
         if timing:
             self.fork_log.append(("start", start))
-        for m, st in self._side_streams().items():
-            st.wait_event(start)
-            with torch.cuda.stream(st):
+
+        def run_side():
+            for m, st in self._side_streams().items():
+                st.wait_event(start)
+                with torch.cuda.stream(st):
+                    self.k.bind_stream()
+                    fns[m]()
+                    ev = torch.cuda.Event(enable_timing=timing)
+                    ev.record(st)
+                    done.append(ev)
+                    if timing:
+                        self.fork_log.append((m, ev))
+
+        def run_text():
+            # the text encoder is the critical path: it runs on a high-priority stream so its
+            # kernels are placed ahead of the visual / acoustic CTAs competing for SMs
+            if self.text_priority:
+                if self._text_stream is None:
+                    self._text_stream = torch.cuda.Stream(device=self._dev, priority=-1)
+                ts = self._text_stream
+                ts.wait_event(start)
+                with torch.cuda.stream(ts):
+                    self.k.bind_stream()
+                    fns["t"]()
+                    ev = torch.cuda.Event(enable_timing=timing)
+                    ev.record(ts)
+                    done.append(ev)
+                    if timing:
+                        self.fork_log.append(("t", ev))
                 self.k.bind_stream()
-                fns[m]()
-                ev = torch.cuda.Event(enable_timing=timing)
-                ev.record(st)
-                done.append(ev)
-                if timing:
-                    self.fork_log.append((m, ev))
-        # the text encoder is the critical path: it runs on a high-priority stream so its cluster
-        # kernels are placed ahead of the visual / acoustic CTAs competing for SMs
-        if self.text_priority:
-            if self._text_stream is None:
-                self._text_stream = torch.cuda.Stream(device=self._dev, priority=-1)
-            ts = self._text_stream
-            ts.wait_event(start)
-            with torch.cuda.stream(ts):
+            else:
                 self.k.bind_stream()
                 fns["t"]()
-                ev = torch.cuda.Event(enable_timing=timing)
-                ev.record(ts)
-                done.append(ev)
-                if timing:
-                    self.fork_log.append(("t", ev))
+
+        if text_first:
+            run_text()
+            run_side()
             self.k.bind_stream()
         else:
-            self.k.bind_stream()
-            fns["t"]()
+            run_side()
+            run_text()
         for ev in done:
             main.wait_event(ev)
 
@@ -913,7 +927,15 @@ class MisaEngine:
                 notify(f"enc_{m}")       # on the stream that produced the gradients
             return run
 
-        self._fork({m: enc_bwd(m) for m in MODS})
+        # The text BPTT launches cooperatively on ~120 SMs: if the small visual / acoustic BPTT
+        # kernels get there first it has to wait for them to drain (0.3 ms, measured).  The side
+        # encoders have slack in this region, so the text stream is enqueued first and the side
+        # streams hold their layer-2 BPTT until the text layer-2 BPTT is done, and their layer-1
+        # BPTT until the text stream has reached its own layer-1 launch (both launches then become
+        # eligible together and the text stream's priority decides).
+        self._order_events = {}
+        self._fork({m: enc_bwd(m) for m in MODS}, text_first=self.lstm_tc and not self.gru)
+        self._order_events = {}
         return dutt["t"] if self.use_bert else None
 
     def _encode_backward(self, m, dutt, G, pk, P):
@@ -949,11 +971,22 @@ class MisaEngine:
                 k.layernorm_bwd(dY1n, Y1, None, P[f"{ln}.weight"], mu, rs, dY1, G[f"{ln}.weight"],
                                 G[f"{ln}.bias"])
             tcws = self._lstm_tc_ws(m, B, H, Tmax)
+            layer = 2 if r == r2 else 1
+            if use_side and m != "t" and layer in getattr(self, "_order_events", {}):
+                cur.wait_event(self._order_events[layer])
+            if use_side and m == "t" and tcws is not None and layer == 1 and hasattr(self, "_order_events"):
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                self._order_events[1] = ev
             if tcws is not None:
                 k._c("mmda_lstm_tc_backward", _ptr(Gt), _ptr(P[f"{r}.weight_hh_l0"]),
                      _ptr(P[f"{r}.weight_hh_l0_reverse"]), _ptr(C), _ptr(dy), _ptr(dutt), 4 * H, o_f,
                      o_r, _ptr(pk["lens"]), _ptr(pk["sidx"]), _ptr(pk["off"]), B, H, Tmax,
                      _ptr(tcws))
+                if use_side and m == "t" and layer == 2 and hasattr(self, "_order_events"):
+                    ev = torch.cuda.Event()
+                    ev.record(cur)
+                    self._order_events[2] = ev
             else:
                 k._c("mmda_gru_backward" if self.gru else "mmda_lstm_backward", _ptr(Gt),
                      _ptr(P[f"{r}.weight_hh_l0"]), _ptr(P[f"{r}.weight_hh_l0_reverse"]),
