@@ -121,8 +121,6 @@ int mmda_lstm_pack_weights(const float* w_ih_f, const float* w_ih_r, const float
                            const float* b_hh_f, const float* b_ih_r, const float* b_hh_r, int H, int I,
                            int mode, void* out_a, float* out_b, int ld, float* bias_out,
                            mmda_stream_t stream);
-/* tuning knob for A/B measurements: hidden units per thread (1 or 2) in the forward mat-vec */
-int mmda_lstm_set_units_per_thread(int tu);
 /* A/B knob: batch tile of the small-hidden-size plan (8 = many small CTAs, 32 = few large ones) */
 int mmda_lstm_set_small_tile(int bt);
 /* diagnostic: per-step phase timestamps of CTA 0 of subsequent forward launches (NULL = off) */

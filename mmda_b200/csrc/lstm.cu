@@ -258,178 +258,6 @@ __global__ void __launch_bounds__(BT == 40 ? 800 : 640, 1) lstm_fwd_kernel(const
 }
 
 // ------------------------------------------------------------------------------------------
-// forward, two hidden units per thread (8 batch rows x 8 gate rows = 64 accumulators).
-// The mat-vec of the one-unit kernel above is bound by operand DELIVERY from shared memory: per
-// 32 FFMA every lane receives 12 floats (one float4 of W_hh, two of h) = 12 cycles of the
-// 128 B/clk SM->RF path against 8 FFMA issue cycles.  With two units per thread a lane receives
-// 16 floats per 64 FFMA (16 vs 16 cycles).  15 warps instead of 25 (the 19 unit pairs of a
-// 38-unit slice fill 3 groups of 8 lanes: 21 % idle lanes) but no register-file pressure
-// (480 threads -> up to 136 registers).
-// ------------------------------------------------------------------------------------------
-template <int BT>
-__global__ void __launch_bounds__(512, 1) lstm_fwd2_kernel(const LstmArgs p) {
-  extern __shared__ __align__(16) float smem[];
-  constexpr int BTP = BT + (BT % 32 == 0 ? 4 : 0);
-  const int C = p.C, H = p.H, Hs = p.Hs, Kpad = p.Kpad;
-  const int dir = blockIdx.y;
-  const unsigned rank = cluster_ctarank();
-  const int tile = blockIdx.x / C;
-  const int b_base = tile * BT;
-
-  float4* Ws = reinterpret_cast<float4*>(smem);
-  float* h_s = smem + 4 * Kpad * Hs;
-  const int HR = max(C * Hs, Kpad);
-  int* lens_s = reinterpret_cast<int*>(h_s + HR * BTP);
-  int* orig_s = lens_s + BT;
-  const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(orig_s + BT);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q = lane >> 3, psub = lane & 7;
-  const int NP = (Hs + 1) >> 1;              // unit pairs in this slice
-  const int PG = (NP + 7) >> 3;
-  const int pg = warp % PG, bg = warp / PG;
-  const int u0 = 2 * (pg * 8 + psub);        // local units u0, u0+1
-  const int ug0 = rank * Hs + u0;
-  bool uok[2];
-  uok[0] = (u0 < Hs) && (ug0 < H);
-  uok[1] = (u0 + 1 < Hs) && (ug0 + 1 < H);
-  const int uc0 = min(u0, Hs - 1), uc1 = min(u0 + 1, Hs - 1);
-
-  {
-    const float* __restrict__ W = p.whh[dir];
-    const int total = 4 * Hs * Kpad;
-    for (int idx = tid; idx < total; idx += blockDim.x) {
-      const int k = idx % Kpad, r = idx / Kpad, g = r & 3, ul = r >> 2;
-      const int ugl = rank * Hs + ul;
-      const float v = (k < H && ugl < H) ? W[(size_t)(g * H + ugl) * H + k] : 0.f;
-      smem[(k * Hs + ul) * 4 + g] = v;
-    }
-    for (int idx = tid; idx < HR * BTP; idx += blockDim.x) h_s[idx] = 0.f;
-    if (tid < BT) {
-      const int b = b_base + tid;
-      lens_s[tid] = b < p.B ? p.lens[b] : 0;
-      orig_s[tid] = b < p.B ? p.sorted_idx[b] : 0;
-    }
-    if (tid == 0) mbar_init_cta(mbar, 1);
-  }
-  __syncthreads();
-  cluster_sync_all();
-
-  const int Lmax = lens_s[0];
-  const int bl0 = bg * 8 + 2 * q;
-  const int len[2] = {lens_s[bl0], lens_s[bl0 + 1]};
-  const int orig[2] = {orig_s[bl0], orig_s[bl0 + 1]};
-  const int len_bg = lens_s[bg * 8];
-  const int H2 = 2 * H, H8 = 8 * H;
-  const int utt_off = dir == 0 ? p.utt_off0 : p.utt_off1;
-  const int K4 = Kpad >> 2;
-  float cst[2][2] = {{0.f, 0.f}, {0.f, 0.f}};       // [batch row][unit]
-  const uint32_t slice_bytes = (uint32_t)(Hs * BTP * 4);
-  const uint32_t slice_addr = (uint32_t)__cvta_generic_to_shared(h_s + rank * Hs * BTP);
-
-  for (int s = 0; s < Lmax; ++s) {
-    const int t = dir == 0 ? s : Lmax - 1 - s;
-    if (C > 1 && tid == 0) mbar_arrive_expect_tx(mbar, (C - 1) * slice_bytes);
-    const int off_t = __ldg(p.offsets + t);
-    bool act[2][2];
-    float4 x[2][2];
-#pragma unroll
-    for (int bb = 0; bb < 2; ++bb)
-#pragma unroll
-      for (int uu = 0; uu < 2; ++uu) {
-        act[bb][uu] = uok[uu] && t < len[bb];
-        x[bb][uu] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (act[bb][uu])
-          x[bb][uu] = *reinterpret_cast<const float4*>(
-              p.gates + (size_t)(off_t + b_base + bl0 + bb) * H8 + dir * 4 * H + (ug0 + uu) * 4);
-      }
-
-    float acc[64];
-#pragma unroll
-    for (int i = 0; i < 64; ++i) acc[i] = 0.f;
-    if (t < len_bg) {
-      const float4* wp0 = Ws + q * Hs + uc0;
-      const float4* wp1 = Ws + q * Hs + uc1;
-      const float* hp = h_s + q * BTP + bg * 8;
-#pragma unroll 2
-      for (int i = 0; i < K4; ++i) {
-        const float4 w0 = wp0[(size_t)i * 4 * Hs];
-        const float4 w1 = wp1[(size_t)i * 4 * Hs];
-        const float4 ha = *reinterpret_cast<const float4*>(hp + i * 4 * BTP);
-        const float4 hb = *reinterpret_cast<const float4*>(hp + i * 4 * BTP + 4);
-        const float hv[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
-#pragma unroll
-        for (int b = 0; b < 8; ++b) {
-          acc[b * 8 + 0] = fmaf(w0.x, hv[b], acc[b * 8 + 0]);
-          acc[b * 8 + 1] = fmaf(w0.y, hv[b], acc[b * 8 + 1]);
-          acc[b * 8 + 2] = fmaf(w0.z, hv[b], acc[b * 8 + 2]);
-          acc[b * 8 + 3] = fmaf(w0.w, hv[b], acc[b * 8 + 3]);
-          acc[b * 8 + 4] = fmaf(w1.x, hv[b], acc[b * 8 + 4]);
-          acc[b * 8 + 5] = fmaf(w1.y, hv[b], acc[b * 8 + 5]);
-          acc[b * 8 + 6] = fmaf(w1.z, hv[b], acc[b * 8 + 6]);
-          acc[b * 8 + 7] = fmaf(w1.w, hv[b], acc[b * 8 + 7]);
-        }
-      }
-      reduce_scatter<64, 8>(acc, lane);   // lane q: batch rows 2q, 2q+1 x 8 gate rows -> acc[0..16)
-    }
-    cluster_arrive_relaxed();
-
-    float hn[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-    float4 gsv[2][2];
-#pragma unroll
-    for (int bb = 0; bb < 2; ++bb)
-#pragma unroll
-      for (int uu = 0; uu < 2; ++uu) {
-        if (act[bb][uu]) {
-          const float* a = acc + bb * 8 + uu * 4;
-          const float ig = fast_sigmoid(a[0] + x[bb][uu].x), fg = fast_sigmoid(a[1] + x[bb][uu].y);
-          const float gg = fast_tanh(a[2] + x[bb][uu].z), og = fast_sigmoid(a[3] + x[bb][uu].w);
-          cst[bb][uu] = fg * cst[bb][uu] + ig * gg;
-          hn[bb][uu] = og * fast_tanh(cst[bb][uu]);
-          gsv[bb][uu] = make_float4(ig, fg, gg, og);
-        }
-      }
-
-    cluster_wait();
-#pragma unroll
-    for (int uu = 0; uu < 2; ++uu)
-      if (act[0][uu] || act[1][uu])
-        *reinterpret_cast<float2*>(h_s + (size_t)(ug0 + uu) * BTP + bl0) = make_float2(hn[0][uu], hn[1][uu]);
-    if (C > 1) {
-      fence_proxy_async_smem();
-      __syncthreads();
-      if (tid == 0) {
-#pragma unroll 1
-        for (unsigned r = 0; r < (unsigned)C; ++r)
-          if (r != rank)
-            dsmem_bulk_copy(dsmem_addr(h_s + rank * Hs * BTP, r), slice_addr, slice_bytes,
-                            dsmem_addr(orig_s + BT, r));
-      }
-    } else {
-      __syncthreads();
-    }
-#pragma unroll
-    for (int bb = 0; bb < 2; ++bb)
-#pragma unroll
-      for (int uu = 0; uu < 2; ++uu) {
-        if (act[bb][uu]) {
-          const size_t row = (size_t)(off_t + b_base + bl0 + bb);
-          const int ug = ug0 + uu;
-          if (p.save) {
-            *reinterpret_cast<float4*>(p.gates + row * H8 + dir * 4 * H + ug * 4) = gsv[bb][uu];
-            p.c[row * H2 + dir * H + ug] = cst[bb][uu];
-          }
-          p.y[row * H2 + dir * H + ug] = hn[bb][uu];
-          const bool fin = dir == 0 ? (t == len[bb] - 1) : (t == 0);
-          if (fin && p.utt) p.utt[(size_t)orig[bb] * p.utt_ld + utt_off + ug] = hn[bb][uu];
-        }
-      }
-    if (C > 1) mbar_wait_parity(mbar, s & 1);
-  }
-  cluster_sync_all();
-}
-
-// ------------------------------------------------------------------------------------------
 // backward through time
 // ------------------------------------------------------------------------------------------
 template <int BT, int KS, int CELL>
@@ -772,14 +600,13 @@ __global__ void gru_fold_kernel(const float* __restrict__ dw4_ih, const float* _
 // host side
 // ------------------------------------------------------------------------------------------
 struct LstmPlan {
-  int C, Hs, Kpad, BT, KS, n_tiles, threads_fwd, threads_bwd, tu;
+  int C, Hs, Kpad, BT, KS, n_tiles, threads_fwd, threads_bwd;
   size_t smem_fwd, smem_bwd, scratch_bytes;
 };
 
 static int g_max_smem = 0;
 static int g_small_bt = 32; // batch tile of the small-H plan for B >= 64: few large CTAs leave the SMs next to the
                             // text recurrence to the weight-gradient GEMMs (7.65 -> 7.59 ms); 8 = many small CTAs
-static int g_lstm_tu = 1;   // units per thread in the forward mat-vec of the big-H plan (2 measured 6 % slower)
 static int g_max_clusters8 = 0;   // co-resident 8-CTA clusters of the big-H kernel (B200: 15)
 
 template <int BT> static int probe_clusters8(int threads, size_t smem) {
@@ -840,12 +667,6 @@ static int lstm_make_plan(int B, int H, int Tmax, LstmPlan* pl) {
       pl->C = C; pl->Hs = Hs; pl->Kpad = Kpad; pl->BT = BT; pl->KS = KS;
       pl->n_tiles = (B + BT - 1) / BT;
       pl->threads_fwd = wf * 32; pl->threads_bwd = wb * 32;
-      // two-units-per-thread forward variant for the big-H plan (MMDA_LSTM_TU=1 selects the old one)
-      pl->tu = 1;
-      if (BT >= 32 && g_lstm_tu == 2) {
-        const int PG = ((Hs + 1) / 2 + 7) / 8;
-        if (PG * BG <= 16) { pl->tu = 2; pl->threads_fwd = PG * BG * 32; }
-      }
       pl->smem_fwd = fwd; pl->smem_bwd = bwd;
       pl->scratch_bytes = (size_t)2 * 2 * pl->n_tiles * C * BT * Kpad * sizeof(float);
       return MMDA_OK;
@@ -883,13 +704,6 @@ extern "C" {
 int mmda_lstm_set_small_tile(int bt) {
   MMDA_REQUIRE(bt == 8 || bt == 32, "lstm: small-H batch tile must be 8 or 32");
   g_small_bt = bt;
-  return MMDA_OK;
-}
-
-// tuning knob (A/B measurements): units per thread of the big-H forward mat-vec (1 or 2)
-int mmda_lstm_set_units_per_thread(int tu) {
-  MMDA_REQUIRE(tu == 1 || tu == 2, "lstm: units per thread must be 1 or 2");
-  g_lstm_tu = tu;
   return MMDA_OK;
 }
 
@@ -951,10 +765,7 @@ static int rnn_forward(int cell, float* gates, const float* whh_f, const float* 
   MMDA_REQUIRE(cell == 1 || !save_for_backward || c != nullptr,
                "lstm_forward: c buffer required when saving");
   LstmPlan pl;
-  const int tu_saved = g_lstm_tu;
-  if (cell != 0) g_lstm_tu = 1;   // the two-unit variant implements the LSTM cell only
   int rc = lstm_make_plan(B, H, Tmax, &pl);
-  g_lstm_tu = tu_saved;
   if (rc != MMDA_OK) return rc;
   LstmArgs a = {};
   a.Tmax = Tmax;
@@ -964,8 +775,6 @@ static int rnn_forward(int cell, float* gates, const float* whh_f, const float* 
   a.B = B; a.H = H; a.Hs = pl.Hs; a.Kpad = pl.Kpad; a.C = pl.C; a.n_tiles = pl.n_tiles;
   a.save = save_for_backward;
   a.dbg = g_lstm_dbg;
-  if (pl.tu == 2 && pl.BT == 40) return launch_cluster(lstm_fwd2_kernel<40>, a, pl, pl.threads_fwd, pl.smem_fwd, stream);
-  if (pl.tu == 2 && pl.BT == 32) return launch_cluster(lstm_fwd2_kernel<32>, a, pl, pl.threads_fwd, pl.smem_fwd, stream);
   if (cell != 0) {
     if (pl.BT == 40) return launch_cluster(lstm_fwd_kernel<40, 1>, a, pl, pl.threads_fwd, pl.smem_fwd, stream);
     if (pl.BT == 32) return launch_cluster(lstm_fwd_kernel<32, 1>, a, pl, pl.threads_fwd, pl.smem_fwd, stream);

@@ -149,9 +149,8 @@ class MisaEngine:
         # recurrence itself ran on tensor cores, so that mode was removed.
         self.tc_kind = 0 if prec == "fp32" else 1
         self.lstm_kind = 0
-        # 3xTF32 operands: plain fp32 tensors, split into tf32 hi/lo inside the GEMM kernel's
-        # shared-memory pipeline (MMDA_TF32_SPLIT=pre: separate split pass, hi/lo arrays in HBM)
-        self.tc_raw = os.environ.get("MMDA_TF32_SPLIT", "smem") != "pre"
+        # 3xTF32 operands: activations are plain fp32 tensors, split into tf32 hi/lo inside the
+        # GEMM kernel's shared-memory pipeline; weights (re-read by every tile) are split once
         self.use_tc = os.environ.get("MMDA_GEMM", "tc") != "simt"
         self.tc_small = os.environ.get("MMDA_GEMM_SMALL", "tc") != "simt"
         # the visual / acoustic encoders run on side streams next to the text encoder (whose
@@ -264,7 +263,8 @@ class MisaEngine:
 
     # ---------------------------------------------------------------- GEMM routing ---------
     def big_gemm(self, *a, **kw):
-        """Hoisted LSTM GEMMs.  fp32 mode: exact fp32 SIMT path."""
+        """Hoisted LSTM GEMMs on the exact-fp32 SIMT kernel (MMDA_GEMM=simt / MMDA_GEMM_SMALL=simt
+        A/B runs; the default routes them to the tcgen05 3xTF32 kernel)."""
         self.k.gemm(*a, **kw)
 
     # ---------------------------------------------------------------- streams --------------
@@ -361,32 +361,26 @@ class MisaEngine:
         return self.buf(name, rows, ld)[:, :cols]
 
     def _prep(self, name, x, out=None, row0=0, kind=None, split=False):
-        """Tensor-core operand copy of the 2-D view x: (hi, lo) tf32 split or (bf16, None).
-        Rows land at [row0, row0+rows) of the (possibly larger) buffer `out`.  In the default
-        3xTF32 mode activations are consumed as plain fp32 (returned as is); ``split=True`` forces
-        the ahead-of-time split -- used for weights (B operands), which every tile re-reads."""
+        """Tensor-core operand of the 2-D view x.  3xTF32 (kind 0): activations are consumed as
+        plain fp32 (returned as is, the kernel splits them in shared memory); ``split=True`` makes
+        the ahead-of-time (hi, lo) tf32 split -- used for weights (B operands), which every tile
+        re-reads.  bf16 (kind 1, BERT encoder): a bf16 copy; rows land at [row0, row0+rows) of
+        the (possibly larger) buffer `out`."""
         kind = self.tc_kind if kind is None else kind
         rows, cols = x.shape
-        if kind == 0 and self.tc_raw and split:
-            ld = (cols + 3) // 4 * 4
-            hi = self.buf(name + "_hi", rows, ld)[:, :cols]
-            lo = self.buf(name + "_lo", rows, ld)[:, :cols]
+        if kind == 0 and split:
+            hi, lo = self._prep_buf(name, rows, cols, 0, split=True)
             self.k._c("mmda_split_tf32", _ptr(x), x.stride(0), rows, cols, _ptr(hi), _ptr(lo),
                       hi.stride(0))
             return hi, lo
-        if kind == 0 and self.tc_raw:
+        if kind == 0:
             if out is None and x.stride(1) == 1 and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0:
                 return x, None           # consumed as is
             raise MmdaError(f"operand {name}: 3xTF32 operands must be 16-byte aligned fp32 views")
         if out is None:
             out = self._prep_buf(name, rows, cols, kind)
         hi, lo = out
-        if kind == 0:
-            self.k._c("mmda_split_tf32", _ptr(x), x.stride(0), rows, cols, _ptr(hi[row0:]),
-                      _ptr(lo[row0:]), hi.stride(0))
-        else:
-            self.k._c("mmda_cast_bf16", _ptr(x), x.stride(0), rows, cols, _ptr(hi[row0:]),
-                      hi.stride(0))
+        self.k._c("mmda_cast_bf16", _ptr(x), x.stride(0), rows, cols, _ptr(hi[row0:]), hi.stride(0))
         return out
 
     def _prep_buf(self, name, rows, cols, kind=None, split=False):
@@ -394,7 +388,7 @@ class MisaEngine:
         if kind == 0:
             ld = (cols + 3) // 4 * 4
             hi = self.buf(name + "_hi", rows, ld)[:, :cols]
-            if self.tc_raw and not split:
+            if not split:
                 return hi, None
             lo = self.buf(name + "_lo", rows, ld)[:, :cols]
             return hi, lo
@@ -923,7 +917,7 @@ class MisaEngine:
         def enc_bwd(m):
             def run():
                 if not (m == "t" and self.use_bert):
-                    self._encode_backward(m, dutt[m], G, pk, P)
+                    self._encode_backward(m, dutt[m], G, pk, P, notify)
                 notify(f"enc_{m}")       # on the stream that produced the gradients
             return run
 
@@ -938,7 +932,7 @@ class MisaEngine:
         self._order_events = {}
         return dutt["t"] if self.use_bert else None
 
-    def _encode_backward(self, m, dutt, G, pk, P):
+    def _encode_backward(self, m, dutt, G, pk, P, notify=None):
         """BPTT of both layers of modality m + the hoisted weight-gradient GEMMs.  The recurrence
         and the dX GEMM form the critical path; the weight-gradient work of a layer (h_prev shift,
         dW_ih, dW_hh, bias column sums) is pushed to a side stream so it overlaps the next BPTT
@@ -998,19 +992,11 @@ class MisaEngine:
             I = Xin.shape[1]
             tc = self._tc_ok(H, I)
             if tc:
-                # Backward GEMMs are always 3xTF32: weight/activation gradients are sums with heavy
-                # cancellation, where bf16 operands cost several percent (measured 4-13 %); bf16
-                # mode covers the forward input projection only (BASELINE configs[2]).
+                # 3xTF32 like the forward: weight / activation gradients are sums with heavy
+                # cancellation, where bf16 operands cost several percent (measured 4-13 %)
                 dGp = self._prep(f"tcdG_{r}", Gt, kind=0)
-                if self.lstm_kind == 0 and self.tc_raw:
-                    Xp = self._prep(f"tcX_{r}", Xin, kind=0)          # the fp32 tensor itself
-                    Wst = self._prep_buf(f"tcW_{r}", 8 * H, I, 0, split=True)   # packed by the forward
-                elif self.lstm_kind == 0:    # operand splits written by the forward
-                    Xp = self._prep_buf(f"tcX_{r}", N, I, 0)
-                    Wst = self._prep_buf(f"tcW_{r}", 8 * H, I, 0)
-                else:
-                    Xp = self._prep(f"tcX_{r}", Xin, kind=0)
-                    Wst, _ = self._pack_weights(r, P, H, I, 0, want_bias=False)
+                Xp = self._prep(f"tcX_{r}", Xin, kind=0)          # the fp32 tensor itself
+                Wst = self._prep_buf(f"tcW_{r}", 8 * H, I, 0, split=True)   # packed by the forward
             else:
                 Wst = (self.buf(f"Wst_{r}", 8 * H, I), None)      # written by the forward
 
@@ -1070,6 +1056,13 @@ class MisaEngine:
                     wgrad_dir(1)
                     if m == "t":
                         self._mark(f"  t.{r} wgrad (side stream) done")
+                    if m == "t" and r == r2 and notify is not None:
+                        # rnn2's gradients are complete once both directions' streams are: let the
+                        # data-parallel trainer reduce them under the layer-1 BPTT
+                        eva = torch.cuda.Event()
+                        eva.record(sA)
+                        sB.wait_event(eva)
+                        notify("enc_t_l2")
                 k.bind_stream()
                 side_used += [sA, sB]
             else:

@@ -25,9 +25,15 @@ DIFF_PAIRS = ((0, 3), (1, 4), (2, 5), (2, 0), (2, 1), (0, 1))   # solver.py:432-
 LOSS_NAMES = ("cls", "diff", "sim", "recon", "conf", "total")
 
 
+N_BUCKETS = 7      # gradient buckets 0..6 (all-reduced); N_BUCKETS = parameters without a gradient
+
+
 def bucket_of(name: str) -> int:
     """Gradient-ready order of the backward (engine.backward): 0 fusion+classifier, 1 heads,
-    2 visual encoder, 3 acoustic encoder, 4 text encoder + embedding, 5 never (no gradient)."""
+    2 visual encoder, 3 acoustic encoder, 4 text rnn2, 5 text LayerNorm + rnn1, 6 embedding (+ the
+    BERT encoder), 7 never (no gradient).  The text encoder is split so that the all-reduce of
+    rnn2's 8.6 MB runs under the layer-1 BPTT and the dense 24 MB embedding gradient -- ready only
+    after the very last backward kernel -- is not held back by anything else."""
     if name.startswith(("transformer_encoder.", "classifier.", "confidence.")):
         return 0
     if name.startswith(("project_", "private_", "shared.", "recon_", "discriminator.")):
@@ -37,23 +43,28 @@ def bucket_of(name: str) -> int:
     if name.startswith(("arnn", "alayer_norm")):
         return 3
     if name.startswith("bertmodel.pooler."):          # never used, models.py:186-198
-        return 5
-    if name.startswith(("trnn", "tlayer_norm", "embed.", "bertmodel.")):
+        return N_BUCKETS
+    if name.startswith("trnn2"):
         return 4
-    if name.startswith("sp_discriminator."):
+    if name.startswith(("trnn1", "tlayer_norm")):
         return 5
+    if name.startswith(("embed.", "bertmodel.")):
+        return 6
+    if name.startswith("sp_discriminator."):
+        return N_BUCKETS
     raise KeyError(name)
 
 
 def plan_arena(named_shapes: List[Tuple[str, Tuple[int, ...]]], use_confid: bool, never=()):
-    """-> (layout {name: (offset, numel)}, bucket ranges [(lo, hi)] for buckets 0..4, n_active,
-    n_total).  ``never``: names that receive no gradient (frozen, or unused by this variant): they
-    live past ``n_active`` and the optimizer never touches them.  Pure function (CPU-tested)."""
+    """-> (layout {name: (offset, numel)}, bucket ranges [(lo, hi)] for the N_BUCKETS gradient
+    buckets, n_active, n_total).  ``never``: names that receive no gradient (frozen, or unused by
+    this variant): they live past ``n_active`` and the optimizer never touches them.  Pure
+    function (CPU-tested)."""
     never = set(never)
 
     def bucket(n):
         if (n.startswith("confidence.") and not use_confid) or n in never:
-            return 5
+            return N_BUCKETS
         return bucket_of(n)
     order = sorted(range(len(named_shapes)), key=lambda i: (bucket(named_shapes[i][0]), i))
     layout, off = {}, 0
@@ -69,11 +80,11 @@ def plan_arena(named_shapes: List[Tuple[str, Tuple[int, ...]]], use_confid: bool
             n *= s
         layout[name] = (off, n)
         off += (n + ALIGN - 1) // ALIGN * ALIGN
-    while cur < 5:
+    while cur < N_BUCKETS:
         ranges.append((lo, off))
         lo, cur = off, cur + 1
-    n_active = ranges[4][1]
-    return layout, ranges[:5], n_active, off
+    n_active = ranges[N_BUCKETS - 1][1]
+    return layout, ranges[:N_BUCKETS], n_active, off
 
 
 _LIVE_DP_TRAINERS = None     # weak set of data-parallel trainers that may hold captured graphs
@@ -120,6 +131,7 @@ class FusedTrainer:
         self.m = torch.zeros_like(self.p_arena)
         self.v = torch.zeros_like(self.p_arena)
         self._pending = []
+        self._reduced = set()
         # device-resident step state (step counter = dropout seed offset, Adam bias corrections)
         self.state = torch.zeros(4, dtype=torch.float64, device=self.p_arena.device)
         if not _engine._DRYRUN:
@@ -258,10 +270,17 @@ class FusedTrainer:
     def _on_ready(self, tag):
         if self.world == 1 or (tag == "enc_t" and self.use_bert and not self._bert_done):
             return
-        b = {"fusion": 0, "heads": 1, "enc_v": 2, "enc_a": 3, "enc_t": 4}[tag]
-        lo, hi = self.ranges[b]
-        if hi > lo:
-            self._pending.append(self._allreduce(self.g_arena[lo:hi], async_op=True))
+        # enc_t_l2: the text rnn2 gradients are complete (issued from the weight-gradient stream,
+        # long before the rest of the text encoder); enc_t: everything else of the text encoder
+        buckets = {"fusion": (0,), "heads": (1,), "enc_v": (2,), "enc_a": (3,), "enc_t_l2": (4,),
+                   "enc_t": (5, 6)}[tag]
+        if tag == "enc_t" and 4 not in self._reduced:
+            buckets = (4,) + buckets          # e.g. BERT text branch: no rnn2 notification
+        for b in buckets:
+            lo, hi = self.ranges[b]
+            self._reduced.add(b)
+            if hi > lo:
+                self._pending.append(self._allreduce(self.g_arena[lo:hi], async_op=True))
 
     def forward_backward(self, sentences, visual, acoustic, lengths, labels, bert=None):
         """zero_grad + forward + losses + backward (+ gradient all-reduce).  Returns the device
@@ -287,6 +306,7 @@ class FusedTrainer:
         self.g_arena[:self.n_active].zero_()
         losses, grads = self.loss_and_grads(out, labels.contiguous(), B)
         self._pending = []
+        self._reduced = set()
         self._bert_done = False
         d_utt = eng.backward(self.G, on_ready=self._on_ready, **grads)
         if self.use_bert:

@@ -91,7 +91,7 @@ def test_arena_plan_buckets_are_contiguous_and_ordered():
     shapes = [(n, tuple(p.shape)) for n, p in m.named_parameters()]
     for confid in (False, True):
         layout, ranges, n_active, n_total = plan_arena(shapes, confid)
-        assert len(ranges) == 5 and ranges[0][0] == 0 and ranges[-1][1] == n_active <= n_total
+        assert len(ranges) == 7 and ranges[0][0] == 0 and ranges[-1][1] == n_active <= n_total
         for (lo, hi), (lo2, _hi2) in zip(ranges, ranges[1:]):
             assert hi == lo2 and lo <= hi
         for n, (off, sz) in layout.items():
