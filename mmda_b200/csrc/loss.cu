@@ -584,11 +584,38 @@ __global__ void __launch_bounds__(256) linear_skinny_kernel(const float* __restr
 #pragma unroll
   for (int n = 0; n < NMAX; ++n) acc[n] = 0.f;
   const float* xr = x + (size_t)row * ldx;
-  for (int k = lane; k < K; k += 32) {
-    const float xv = xr[k];
+  if ((K & 3) == 0 && (ldx & 3) == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0) {
+    // 16-byte loads, 8 k-quads of the row in flight per lane
+    const int K4 = K >> 2;
+    const float4* x4 = reinterpret_cast<const float4*>(xr);
+    const float4* w4 = reinterpret_cast<const float4*>(w);
+    for (int k0 = 0; k0 < K4; k0 += 32 * 8) {
+      float4 xv[8];
 #pragma unroll
-    for (int n = 0; n < NMAX; ++n)
-      if (n < N) acc[n] = fmaf(xv, __ldg(w + (size_t)n * K + k), acc[n]);
+      for (int j = 0; j < 8; ++j) {
+        const int k = k0 + lane + 32 * j;
+        xv[j] = k < K4 ? x4[k] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int k = k0 + lane + 32 * j;
+        if (k < K4) {
+#pragma unroll
+          for (int n = 0; n < NMAX; ++n)
+            if (n < N) {
+              const float4 wv = __ldg(w4 + (size_t)n * K4 + k);
+              acc[n] = fmaf(xv[j].x, wv.x, fmaf(xv[j].y, wv.y, fmaf(xv[j].z, wv.z, fmaf(xv[j].w, wv.w, acc[n]))));
+            }
+        }
+      }
+    }
+  } else {
+    for (int k = lane; k < K; k += 32) {
+      const float xv = xr[k];
+#pragma unroll
+      for (int n = 0; n < NMAX; ++n)
+        if (n < N) acc[n] = fmaf(xv, __ldg(w + (size_t)n * K + k), acc[n]);
+    }
   }
 #pragma unroll
   for (int n = 0; n < NMAX; ++n) {

@@ -360,8 +360,12 @@ class FusedTrainer:
             # other lengths) has overwritten them: rebuild them for these lengths before the replay
             self.eng._pack(lengths)
             if g["ws"] == self.eng.ws_version:
-                for dst, src in zip(g["inputs"], (sentences, visual, acoustic, labels)):
-                    dst.copy_(src, non_blocking=True)
+                srcs = [sentences, visual, acoustic, labels]
+                if all(d.dtype == s_.dtype and d.device == s_.device for d, s_ in zip(g["inputs"], srcs)):
+                    torch._foreach_copy_(g["inputs"], srcs)      # one launch per dtype group
+                else:
+                    for dst, src in zip(g["inputs"], srcs):
+                        dst.copy_(src, non_blocking=True)
                 g["graph"].replay()
                 self.step_count += 1
                 return g["losses"]

@@ -668,6 +668,22 @@ def test_bert_fused_step_level2(dev):
     _model_checks("bert_l2", cfg, state, batch, dev, None, frozen=frozen)
 
 
+def test_bert_c4_sequence_length(dev):
+    """The C4 sequence shape (BASELINE configs[3]: seq 50 + [CLS]/[SEP] = 52 BERT positions, the
+    attention kernels' S = 52 tile) through both levels with the full parity harness against the
+    fp64 HF oracle; batch 16 keeps the CPU oracle to seconds (C4's batch 512 only adds rows)."""
+    from mmda_b200 import mosei_config
+    from mmda_b200.synthetic import batch_for
+    from oracle.misa_oracle import oracle_build
+    cfg = mosei_config(vocab_size=100, batch_size=16, use_bert=True, use_confidNet=True)
+    state = {k: v.clone() for k, v in oracle_build(cfg, 41).state_dict().items()}
+    batch = batch_for(cfg, seed=42, lengths="ragged", seq_len=50)
+    assert batch.bert_sent.shape[1] == 52
+    frozen = lambda n: "bertmodel.encoder.layer" in n and \
+        int(n.split("encoder.layer.")[-1].split(".")[0]) <= 8
+    _model_checks("bert_c4_s52", cfg, state, batch, dev, None, frozen=frozen)
+
+
 @pytest.mark.parametrize("sizes,B,T", [((160, 128, 200), 9, 6), ((96, 33, 260), 41, 5), ((300, 1, 2), 2, 3)])
 def test_other_recurrence_plans(dev, sizes, B, T):
     """Hidden sizes that exercise the other cluster plans of the recurrence kernels (cluster of
