@@ -416,6 +416,15 @@ class FusedTrainer:
         if not _engine._DRYRUN:
             torch.cuda.synchronize()
 
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        """``with FusedTrainer(model, process_group=pg) as tr: ...`` drops the captured graph on the
+        way out -- the explicit alternative to the wrapped ``destroy_process_group``."""
+        self.close()
+        return False
+
     def step_batch(self, batch, device=None, prefetch=None):
         """Public end-to-end call: a host ``Batch`` (pinned or pageable) -> one optimisation step.
         Returns the loss tensor on the device; ``.tolist()`` it to read the values.
