@@ -45,6 +45,18 @@ int mmda_device_info(int* out5);
  * Writes batch_sizes[Tmax], offsets[Tmax+1] and the (t, j) coordinates of each of the N rows. */
 int mmda_pack_build(const int* lens_sorted, int B, int Tmax, int N, int* batch_sizes, int* offsets,
                     int* row_t, int* row_j, mmda_stream_t stream);
+/* Same, for a launch padded to Np >= N packed rows (one captured CUDA graph serves every length
+ * pattern whose row count rounds to the same Np; Tmax is then the padded time extent of the input
+ * tensors, batch_sizes[t] = 0 past the longest sequence): rows [N, Np) of the row maps point at
+ * token (0, 0), so row-wise kernels launched over Np rows read valid memory.  The reference packs
+ * exactly (pack_padded_sequence, src/models.py:164); the padding rows never reach a valid row's
+ * result -- GEMM rows are independent and the backward zeroes them (mmda_zero_tail_rows) before
+ * any reduction over rows. */
+int mmda_pack_build_padded(const int* lens_sorted, int B, int Tmax, int N, int Np, int* batch_sizes,
+                           int* offsets, int* row_t, int* row_j, mmda_stream_t stream);
+/* rows [*n_rows_dev, Np) of the fp32 matrix A (row pitch ld floats, ld % 4 == 0) := 0; the row
+ * count is read on the device (offsets[Tmax] of the pack), so the call is graph-replay safe. */
+int mmda_zero_tail_rows(float* A, int ld, const int* n_rows_dev, int Np, mmda_stream_t stream);
 /* X[row] = src[t][sorted_idx[j]] for a time-major padded (T,B,D) input (visual / acoustic); ldx =
  * row pitch of X in floats (>= D: a pitch that is a multiple of 4 keeps X a legal TMA operand). */
 int mmda_gather_rows(const float* src, float* X, int ldx, const int* row_t, const int* row_j,

@@ -43,6 +43,24 @@ __global__ void pack_rows_kernel(const int* __restrict__ batch_sizes,
 }
 
 // X[row][:] = src[t][sorted_idx[j]][:]    (src is the time-major padded (T,B,D) input)
+// padded launches (one captured graph for many length patterns): rows [N, Np) of the row maps
+// point at token (t=0, j=0), so row-wise kernels that run over Np rows read valid memory there
+__global__ void pack_tail_kernel(int N, int Np, int* __restrict__ row_t, int* __restrict__ row_j) {
+  const int r = N + blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < Np) { row_t[r] = 0; row_j[r] = 0; }
+}
+
+// rows [*n_rows, Np) of a [Np][ld] fp32 matrix := 0  (n_rows is read on the device, so a captured
+// graph zeroes the right tail for whatever lengths the replay was packed for)
+__global__ void zero_tail_rows_kernel(float* __restrict__ A, int ld4, const int* __restrict__ n_rows,
+                                      int Np) {
+  const int N = *n_rows;
+  float4* A4 = reinterpret_cast<float4*>(A);
+  for (int r = N + blockIdx.x; r < Np; r += gridDim.x)
+    for (int c = threadIdx.x; c < ld4; c += blockDim.x)
+      A4[(size_t)r * ld4 + c] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
 __global__ void gather_rows_kernel(const float* __restrict__ src, float* __restrict__ X,
                                    const int* __restrict__ row_t, const int* __restrict__ row_j,
                                    const int* __restrict__ sorted_idx, int N, int B, int D, int ldx) {
@@ -93,6 +111,25 @@ int mmda_pack_build(const int* lens_sorted, int B, int Tmax, int N, int* batch_s
                                                                   batch_sizes, offsets);
   MMDA_CHECK_LAUNCH();
   pack_rows_kernel<<<Tmax, 128, 0, stream>>>(batch_sizes, offsets, Tmax, row_t, row_j);
+  MMDA_CHECK_LAUNCH();
+  return MMDA_OK;
+}
+
+int mmda_pack_build_padded(const int* lens_sorted, int B, int Tmax, int N, int Np, int* batch_sizes,
+                           int* offsets, int* row_t, int* row_j, cudaStream_t stream) {
+  MMDA_REQUIRE(Np >= N, "pack_build_padded: Np=%d < N=%d", Np, N);
+  int rc = mmda_pack_build(lens_sorted, B, Tmax, N, batch_sizes, offsets, row_t, row_j, stream);
+  if (rc != MMDA_OK || Np == N) return rc;
+  pack_tail_kernel<<<(Np - N + 255) / 256, 256, 0, stream>>>(N, Np, row_t, row_j);
+  MMDA_CHECK_LAUNCH();
+  return MMDA_OK;
+}
+
+int mmda_zero_tail_rows(float* A, int ld, const int* n_rows_dev, int Np, cudaStream_t stream) {
+  MMDA_REQUIRE(ld % 4 == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0,
+               "zero_tail_rows: ld=%d / base not 16-byte aligned", ld);
+  if (Np <= 0) return MMDA_OK;
+  zero_tail_rows_kernel<<<296, 256, 0, stream>>>(A, ld / 4, n_rows_dev, Np);
   MMDA_CHECK_LAUNCH();
   return MMDA_OK;
 }

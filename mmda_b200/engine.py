@@ -13,6 +13,7 @@ PyTorch is used for device memory, streams and (in the trainer) ``torch.distribu
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional
 
 import torch
@@ -29,6 +30,9 @@ LN_EPS = 1e-5
 ATT_P = 0.1            # nn.TransformerEncoderLayer default dropout (reference src/models.py:160)
 NHEAD = 2
 TL = "transformer_encoder.layers.0."
+# stream priorities (text chain, visual/acoustic chains, weight-gradient leaves); lower = sooner
+_PRIO = tuple(int(x) for x in os.environ.get("MMDA_PRIO", "-2,-1,0").split(","))
+_ORDER = os.environ.get("MMDA_ORDER", "done,pre").split(",")   # side BPTT layer 2 / layer 1 gate
 _DRYRUN = False       # tests only: exercise the host orchestration on CPU with a stubbed library
 _DRYRUN_SIMT_ONLY = False
 
@@ -132,6 +136,7 @@ class MisaEngine:
         self.NC = self.cfg.num_classes
         self.H = dict(zip(MODS, model.hidden_sizes))
         self._pack_key = None
+        self.pad = None                 # (T_pad, Np) while FusedTrainer runs a padded (graph) step
         self._params = None
         self._params_ver = None
         self._dev = None
@@ -200,7 +205,9 @@ class MisaEngine:
                 # dtype, device) invalidates the graph; a buffer under a NEW name cannot be
                 # referenced by any existing graph
                 self.ws_version += 1
-            t = torch.empty(max(n, 1), dtype=dtype, device=dev)
+            # zero-filled: a padded launch (self.pad) runs row-wise kernels over rows no kernel
+            # ever wrote, and those must at least hold finite values
+            t = torch.zeros(max(n, 1), dtype=dtype, device=dev)
             self.ws[name] = t
         v = t[:n].view(*shape)
         if zero:
@@ -235,13 +242,23 @@ class MisaEngine:
         if lengths_cpu.is_cuda:
             raise MmdaError("lengths must stay on the CPU (reference src/solver.py:149)")
         ln = lengths_cpu.to(torch.int64)
-        key = (ln.numel(), tuple(ln.tolist()))
+        pad = self.pad
+        key = (ln.numel(), tuple(ln.tolist()), pad)
         if key == self._pack_key:
             return self._pack_info
         if ln.numel() == 0 or int(ln.min()) <= 0:
             raise MmdaError("every sequence length must be >= 1 (pack_padded_sequence raises too)")
         ls, si = torch.sort(ln, descending=True)
         B, Tmax, N = ln.numel(), int(ls[0]), int(ln.sum())
+        Np = N
+        if pad is not None:
+            # (T_pad, Np): every kernel of the step is launched over Np >= N packed rows and a
+            # time extent of T_pad >= Tmax, so one captured graph serves all length patterns that
+            # round to the same Np (FusedTrainer.step); the device-side lens / offsets / row maps
+            # carry the real lengths
+            if pad[0] < Tmax or pad[1] < N:
+                raise MmdaError(f"pad {pad} smaller than the batch (Tmax={Tmax}, N={N})")
+            Tmax, Np = pad
         host = torch.empty(2 * B, dtype=torch.int32)
         if not _DRYRUN:
             host = host.pin_memory()
@@ -251,12 +268,14 @@ class MisaEngine:
         dev.copy_(host, non_blocking=True)
         bs = self.buf("batch_sizes", Tmax, dtype=torch.int32)
         off = self.buf("offsets", Tmax + 1, dtype=torch.int32)
-        row_t = self.buf("row_t", N, dtype=torch.int32)
-        row_j = self.buf("row_j", N, dtype=torch.int32)
-        self.k._c("mmda_pack_build", _ptr(dev[:B]), B, Tmax, N, _ptr(bs), _ptr(off), _ptr(row_t),
-                  _ptr(row_j))
+        row_t = self.buf("row_t", Np, dtype=torch.int32)
+        row_j = self.buf("row_j", Np, dtype=torch.int32)
+        self.k._c("mmda_pack_build_padded", _ptr(dev[:B]), B, Tmax, N, Np, _ptr(bs), _ptr(off),
+                  _ptr(row_t), _ptr(row_j))
         self._host_keepalive = host
-        self._pack_info = dict(B=B, Tmax=Tmax, N=N, lens=dev[:B], sidx=dev[B:], bs=bs, off=off,
+        # N is the LAUNCH row count (= the real one unless padded); n_dev the real one, on the device
+        self._pack_info = dict(B=B, Tmax=Tmax, N=Np, N_true=N, padded=Np != N, n_dev=off[Tmax:],
+                               lens=dev[:B], sidx=dev[B:], bs=bs, off=off,
                                row_t=row_t, row_j=row_j, sorted_idx_cpu=si, lens_sorted_cpu=ls)
         self._pack_key = key
         return self._pack_info
@@ -270,14 +289,14 @@ class MisaEngine:
     # ---------------------------------------------------------------- streams --------------
     def _side_streams(self):
         if self._side is None:
-            self._side = {m: torch.cuda.Stream(device=self._dev) for m in ("v", "a")}
+            self._side = {m: torch.cuda.Stream(device=self._dev, priority=_PRIO[1]) for m in ("v", "a")}
         return self._side
 
     def _wgrad_stream(self, m):
         if not hasattr(self, "_wg"):
             self._wg = {}
         if m not in self._wg:
-            self._wg[m] = torch.cuda.Stream(device=self._dev)
+            self._wg[m] = torch.cuda.Stream(device=self._dev, priority=_PRIO[2])
         return self._wg[m]
 
     def _mark(self, tag):
@@ -321,7 +340,7 @@ class MisaEngine:
             # kernels are placed ahead of the visual / acoustic CTAs competing for SMs
             if self.text_priority:
                 if self._text_stream is None:
-                    self._text_stream = torch.cuda.Stream(device=self._dev, priority=-1)
+                    self._text_stream = torch.cuda.Stream(device=self._dev, priority=_PRIO[0])
                 ts = self._text_stream
                 ts.wait_event(start)
                 with torch.cuda.stream(ts):
@@ -968,25 +987,30 @@ class MisaEngine:
             layer = 2 if r == r2 else 1
             if use_side and m != "t" and layer in getattr(self, "_order_events", {}):
                 cur.wait_event(self._order_events[layer])
-            if use_side and m == "t" and tcws is not None and layer == 1 and hasattr(self, "_order_events"):
+            gate = _ORDER[2 - layer]        # "pre": the launch point, "done": completion, "none"
+            if use_side and m == "t" and tcws is not None and gate == "pre" and hasattr(self, "_order_events"):
                 ev = torch.cuda.Event()
                 ev.record(cur)
-                self._order_events[1] = ev
+                self._order_events[layer] = ev
             if tcws is not None:
                 k._c("mmda_lstm_tc_backward", _ptr(Gt), _ptr(P[f"{r}.weight_hh_l0"]),
                      _ptr(P[f"{r}.weight_hh_l0_reverse"]), _ptr(C), _ptr(dy), _ptr(dutt), 4 * H, o_f,
                      o_r, _ptr(pk["lens"]), _ptr(pk["sidx"]), _ptr(pk["off"]), B, H, Tmax,
                      _ptr(tcws))
-                if use_side and m == "t" and layer == 2 and hasattr(self, "_order_events"):
+                if use_side and m == "t" and gate == "done" and hasattr(self, "_order_events"):
                     ev = torch.cuda.Event()
                     ev.record(cur)
-                    self._order_events[2] = ev
+                    self._order_events[layer] = ev
             else:
                 k._c("mmda_gru_backward" if self.gru else "mmda_lstm_backward", _ptr(Gt),
                      _ptr(P[f"{r}.weight_hh_l0"]), _ptr(P[f"{r}.weight_hh_l0_reverse"]),
                      _ptr(Y if self.gru else C), _ptr(dy), _ptr(dutt), 4 * H, o_f,
                      o_r, _ptr(pk["lens"]), _ptr(pk["sidx"]), _ptr(pk["off"]), _ptr(scratch), B, H,
                      Tmax)
+            if pk["padded"]:
+                # padding rows of d(gates) still hold the forward GEMM's values: zero them before
+                # the weight-gradient / dX GEMMs and bias column sums reduce over all N rows
+                k._c("mmda_zero_tail_rows", _ptr(Gt), 8 * H, _ptr(pk["n_dev"]), N)
             if m == "t":
                 self._mark(f"  t.{r} BPTT done")
             I = Xin.shape[1]

@@ -25,6 +25,8 @@ DIFF_PAIRS = ((0, 3), (1, 4), (2, 5), (2, 0), (2, 1), (0, 1))   # solver.py:432-
 LOSS_NAMES = ("cls", "diff", "sim", "recon", "conf", "total")
 
 
+ROW_GRANULE = 512  # packed-row bucket of the captured step graphs (FusedTrainer.step)
+MAX_GRAPHS = 24    # live step graphs per trainer before the cache is flushed
 N_BUCKETS = 7      # gradient buckets 0..6 (all-reduced); N_BUCKETS = parameters without a gradient
 
 
@@ -109,6 +111,26 @@ def _register_dp_trainer(tr):
     _LIVE_DP_TRAINERS.add(tr)
 
 
+class LossFuture:
+    """Losses of one step on their way to the host (FusedTrainer.step_batch(fetch=True)): a
+    non-blocking device->pinned-host copy issued right behind the step, read with result()."""
+    _RING = 4
+
+    def __init__(self, trainer, losses_dev):
+        ring = trainer.__dict__.setdefault("_loss_ring", [])
+        if len(ring) < self._RING:
+            ring.append(torch.empty(losses_dev.numel(), dtype=losses_dev.dtype).pin_memory())
+        slot = trainer.__dict__["_loss_slot"] = (trainer.__dict__.get("_loss_slot", -1) + 1) % self._RING
+        self.host = ring[min(slot, len(ring) - 1)]
+        self.host.copy_(losses_dev.detach().reshape(-1), non_blocking=True)
+        self.event = torch.cuda.Event()
+        self.event.record()
+
+    def result(self):
+        self.event.synchronize()
+        return self.host.tolist()
+
+
 class FusedTrainer:
     def __init__(self, model, lr: Optional[float] = None, process_group=None,
                  global_batch_stats: bool = True, use_graph: Optional[bool] = None):
@@ -142,7 +164,9 @@ class FusedTrainer:
         self.use_graph = (use_graph if use_graph is not None else
                           os.environ.get("MMDA_GRAPH", "1") != "0") and \
             (self.world == 1 or os.environ.get("MMDA_GRAPH_DP", "1") == "1")
-        self._graph = None
+        self._graphs = {}               # key -> captured step (see step())
+        self._graphs_ws = self._graphs_alias = None
+        self._graphs_slots = -1
         self._graph_seen = {}
         self.launches_per_step = None
         if self.world > 1 and self.use_graph:
@@ -346,62 +370,98 @@ class FusedTrainer:
                                     (bert_sent, bert_sent_type, bert_sent_mask))
         if not self.use_graph or _engine._DRYRUN:
             return self._eager_step(sentences, visual, acoustic, lengths, labels)
-        key = (tuple(sentences.shape), tuple(visual.shape), tuple(acoustic.shape),
-               tuple(lengths.tolist()), self.model.training, float(self.lr))
+        # Every kernel of the step runs over Np >= N packed rows and the full time extent T of the
+        # input tensors (engine._pack, pad mode); the real lengths reach the kernels through the
+        # device-side pack buffers, rebuilt before each replay.  So the graph key carries Np --
+        # N rounded up to ROW_GRANULE, capped at B*T -- and not the lengths: a ragged data stream
+        # needs one graph per row bucket (about ten for MOSEI-like length spreads), not one per
+        # batch.  Batches with N == Np (full lengths: the C2 bench) get their own graph without
+        # the tail-zeroing launches.
+        T, B = int(sentences.shape[0]), int(sentences.shape[1])
+        N = int(lengths.sum())
+        cap = B * T
+        Np = min(cap, -(-N // ROW_GRANULE) * ROW_GRANULE)
+        if visual.shape[0] != T or acoustic.shape[0] != T or int(lengths.max()) > T:
+            return self._eager_step(sentences, visual, acoustic, lengths, labels)
+        key = (tuple(sentences.shape), tuple(visual.shape), tuple(acoustic.shape), Np, N == Np,
+               self.model.training, float(self.lr))
         alias = tuple(p.data_ptr() for p in self.model.parameters()) + \
             tuple(p.requires_grad for p in self.model.parameters())
-        g = self._graph
-        if g is not None and (g["ws"] != self.eng.ws_version or g["alias"] != alias):
-            self._drop_graph()          # raw pointers inside the graph are stale: eager warm-up first
-            g = None
-        if g is not None and g["key"] == key:
-            # the graph reads the pack buffers (lens / sorted idx / offsets / row maps) by pointer;
-            # any other forward on this engine (evaluate(), a level-1 forward, an eager step with
-            # other lengths) has overwritten them: rebuild them for these lengths before the replay
-            self.eng._pack(lengths)
-            if g["ws"] == self.eng.ws_version:
-                srcs = [sentences, visual, acoustic, labels]
-                if all(d.dtype == s_.dtype and d.device == s_.device for d, s_ in zip(g["inputs"], srcs)):
-                    torch._foreach_copy_(g["inputs"], srcs)      # one launch per dtype group
-                else:
-                    for dst, src in zip(g["inputs"], srcs):
-                        dst.copy_(src, non_blocking=True)
-                g["graph"].replay()
-                self.step_count += 1
-                return g["losses"]
-            self._drop_graph()
-        seen = self._graph_seen.get(key, 0) + 1
-        self._graph_seen = {key: seen}
-        if seen < 3:                       # warm-up: allocates the workspace, builds the plans
-            return self._eager_step(sentences, visual, acoustic, lengths, labels)
-        self._check_alias()
-        self._drop_graph()
-        inputs = [t.clone() for t in (sentences, visual, acoustic, labels)]
-        self.eng._pack(lengths)            # outside the capture: its H2D copy must not be recorded
-        torch.cuda.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        l0, count0 = self.eng.k.launches, self.step_count
-        slots0 = LIB.raw("mmda_gemm_tc_graph_slots")(-1)
-        with torch.cuda.graph(graph):
-            losses = self._eager_step(inputs[0], inputs[1], inputs[2], lengths, inputs[3])
-        self.launches_per_step = self.eng.k.launches - l0
-        self.step_count = count0           # capture enqueues nothing: the replay runs the step
-        self._graph = dict(key=key, graph=graph, inputs=inputs, losses=losses,
-                           ws=self.eng.ws_version, alias=self._alias_ver, slots=slots0)
-        graph.replay()
-        self.step_count += 1
-        return losses
+        if self._graphs and (self._graphs_ws != self.eng.ws_version or self._graphs_alias != alias):
+            self._drop_graph()          # raw pointers inside the graphs are stale: eager warm-up first
+        g = self._graphs.get(key)
+        eng = self.eng
+        try:
+            eng.pad = (T, Np)
+            if g is not None:
+                # the graph reads the pack buffers (lens / sorted idx / offsets / row maps) by
+                # pointer: rebuild them for these lengths (a no-op when nothing else ran on this
+                # engine since the same lengths were packed)
+                eng._pack(lengths)
+                if self._graphs_ws == eng.ws_version:
+                    srcs = [sentences, visual, acoustic, labels]
+                    if all(d.dtype == s_.dtype and d.device == s_.device for d, s_ in zip(g["inputs"], srcs)):
+                        torch._foreach_copy_(g["inputs"], srcs)      # one launch per dtype group
+                    else:
+                        for dst, src in zip(g["inputs"], srcs):
+                            dst.copy_(src, non_blocking=True)
+                    g["graph"].replay()
+                    self.step_count += 1
+                    self.launches_per_step = g["launches"]
+                    return g["losses"]
+                self._drop_graph()
+            seen = self._graph_seen.get(key, 0) + 1
+            self._graph_seen[key] = seen
+            warm = 3 if not self._graphs else 2
+            if seen < warm:
+                # warm-up: allocates the workspace, builds the GEMM plans.  The very first ones
+                # run at the largest row count this (B, T) can produce so that later, smaller
+                # buckets never grow a buffer (growth would invalidate every captured graph)
+                if not self._graphs:
+                    eng.pad = (T, cap)
+                return self._eager_step(sentences, visual, acoustic, lengths, labels)
+            self._check_alias()
+            if len(self._graphs) >= MAX_GRAPHS:
+                self._drop_graph()
+            inputs = [t.clone() for t in (sentences, visual, acoustic, labels)]
+            eng._pack(lengths)             # outside the capture: its H2D copy must not be recorded
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            l0, count0 = eng.k.launches, self.step_count
+            if not self._graphs:
+                self._graphs_slots = LIB.raw("mmda_gemm_tc_graph_slots")(-1)
+            with torch.cuda.graph(graph):
+                losses = self._eager_step(inputs[0], inputs[1], inputs[2], lengths, inputs[3])
+            self.launches_per_step = eng.k.launches - l0
+            self.step_count = count0       # capture enqueues nothing: the replay runs the step
+            if self._graphs and (self._graphs_ws != eng.ws_version):
+                self._drop_graph()         # the capture grew a buffer older graphs point into
+            self._graphs[key] = dict(graph=graph, inputs=inputs, losses=losses, key=key,
+                                     launches=self.launches_per_step)
+            self._graphs_ws, self._graphs_alias = eng.ws_version, alias
+            graph.replay()
+            self.step_count += 1
+            return losses
+        finally:
+            eng.pad = None
+
+    @property
+    def _graph(self):
+        """the most recently captured graph (introspection / tests)"""
+        return next(reversed(self._graphs.values())) if self._graphs else None
 
     def _drop_graph(self):
-        """Forget the captured graph (stale pointers, new shapes, close()) and hand its GEMM
-        tile-scheduler slots back when it was the most recent capture."""
-        g, self._graph = self._graph, None
-        if g is not None:
-            g["graph"] = None
+        """Forget every captured graph (stale pointers, close()) and hand their GEMM
+        tile-scheduler slots back."""
+        gs, self._graphs = self._graphs, {}
+        self._graph_seen = {}
+        if gs:
+            for g in gs.values():
+                g["graph"] = None
+            gs.clear()
             if not _engine._DRYRUN:
                 torch.cuda.synchronize()
-                LIB.raw("mmda_gemm_tc_graph_slots")(int(g.get("slots", -1)))
-            self._graph_seen = {}
+                LIB.raw("mmda_gemm_tc_graph_slots")(int(self._graphs_slots))
 
     def close(self):
         """Drop the captured CUDA graph.  Under data parallelism the graph references the NCCL
@@ -425,9 +485,13 @@ class FusedTrainer:
         self.close()
         return False
 
-    def step_batch(self, batch, device=None, prefetch=None):
+    def step_batch(self, batch, device=None, prefetch=None, fetch=False):
         """Public end-to-end call: a host ``Batch`` (pinned or pageable) -> one optimisation step.
-        Returns the loss tensor on the device; ``.tolist()`` it to read the values.
+        Returns the loss tensor on the device; ``.tolist()`` it to read the values.  With
+        ``fetch=True`` it returns a ``LossFuture`` instead: the losses are copied to pinned host
+        memory right behind the step, and ``.result()`` waits for that copy only -- a training loop
+        that reads step i's losses after enqueueing step i+1 keeps the device busy back to back
+        (the reference's loop blocks on ``loss.item()`` every step, solver.py:233-240).
 
         ``prefetch``: the host ``Batch`` of the NEXT call.  Its host->device copies are issued on
         a copy stream right after this step has been enqueued, so they overlap the step's
@@ -445,6 +509,8 @@ class FusedTrainer:
         self._staged = None
         extra = [t[f] for f in fields[4:]]
         out = self.step(t["sentences"], t["visual"], t["acoustic"], batch.lengths, t["labels"], *extra)
+        if fetch:
+            out = LossFuture(self, out)
         if prefetch is not None:
             if not hasattr(self, "_copy_stream"):
                 self._copy_stream = torch.cuda.Stream(device=dev)

@@ -557,12 +557,81 @@ def test_graph_replay_after_other_forwards(dev):
                 continue
             L.append(tr.step(*args(item))[:6].clone())
         if mode:
-            assert tr._graph is not None and tr._graph["key"][3] == tuple(b1.lengths.tolist())
+            # one graph for both length patterns: the key carries the padded row count only
+            assert len(tr._graphs) == 1 and tr._graph["key"][3] in (512, 48 * 14)
         outs[mode] = (torch.stack(L), tr.p_arena[:tr.n_active].clone())
         tr.close()
     lerr = float(((outs[True][0] - outs[False][0]).abs() / outs[False][0].abs().clamp_min(1e-6)).max())
     assert lerr < 2e-5, lerr
     assert float((outs[True][1] - outs[False][1]).abs().max()) <= 2 * 1e-4 * len(seq) + 1e-6
+
+
+def test_one_step_graph_serves_a_ragged_stream(dev):
+    """the captured step must not be keyed by the lengths.  Ten batches with ten
+    different length patterns run through at most two graphs (packed rows rounded to the row
+    granule); losses and parameters match the exact-row eager steps of the same stream."""
+    from mmda_b200 import MISA, mosei_config
+    from mmda_b200 import trainer as T
+    from mmda_b200.synthetic import batch_for
+    cfg = mosei_config(vocab_size=300, batch_size=64)
+    stream = [batch_for(cfg, seed=40 + i, lengths="ragged" if i % 3 else "shuffled", seq_len=20)
+              for i in range(10)]
+    assert len({tuple(b.lengths.tolist()) for b in stream}) == 10
+
+    def make():
+        torch.manual_seed(12)
+        m = MISA(cfg)
+        for n, p in m.named_parameters():
+            if "weight_hh" in n:
+                torch.nn.init.orthogonal_(p)
+        return m.to(dev).eval()
+
+    outs, old = {}, T.ROW_GRANULE
+    T.ROW_GRANULE = 256
+    try:
+        for mode in (True, False):
+            tr = T.FusedTrainer(make(), use_graph=mode)
+            L = [tr.step(b.sentences.to(dev), b.visual.to(dev), b.acoustic.to(dev), b.lengths,
+                         b.labels.to(dev))[:6].clone() for b in stream + stream]
+            if mode:
+                keys = list(tr._graphs)
+                assert 1 <= len(keys) <= 3, keys
+                assert all(k[3] % 256 == 0 or k[3] == 64 * 20 for k in keys), keys
+            outs[mode] = (torch.stack(L), tr.p_arena[:tr.n_active].clone())
+            tr.close()
+    finally:
+        T.ROW_GRANULE = old
+    lerr = float(((outs[True][0] - outs[False][0]).abs() / outs[False][0].abs().clamp_min(1e-6)).max())
+    assert lerr < 2e-5, lerr
+    assert float((outs[True][1] - outs[False][1]).abs().max()) <= 2 * 1e-4 * 20 + 1e-6
+
+
+def test_padded_rows_gradients_match_exact_rows(dev):
+    """The padded launch (Np > N rows, T_pad > Tmax) must give the exact launch's gradients: same
+    batch, engine.pad set by hand, every parameter gradient compared."""
+    from mmda_b200 import MISA, mosei_config
+    from mmda_b200.synthetic import batch_for
+    from mmda_b200.trainer import FusedTrainer
+    cfg = mosei_config(vocab_size=300, batch_size=32)
+    b = batch_for(cfg, seed=9, lengths="ragged", seq_len=16)
+    b.lengths = b.lengths.clamp(max=11)            # Tmax < T of the tensors
+    torch.manual_seed(13)
+    model = MISA(cfg).to(dev).eval()
+    tr = FusedTrainer(model, use_graph=False)
+    a = (b.sentences.to(dev), b.visual.to(dev), b.acoustic.to(dev), b.lengths, b.labels.to(dev))
+    res = {}
+    for pad in (None, (16, 32 * 16), (16, int(b.lengths.sum()) + 5)):
+        tr.eng.pad = pad
+        tr.g_arena.zero_()
+        losses = tr.forward_backward(*a)
+        res[pad] = (losses[:6].clone(), tr.g_arena[:tr.n_active].clone())
+    tr.eng.pad = None
+    for pad in list(res)[1:]:
+        dl = float((res[pad][0] - res[None][0]).abs().max())
+        g0 = res[None][1]
+        dg = float((res[pad][1] - g0).abs().max() / g0.abs().max())
+        assert dl < 1e-6 and dg < 2e-6, (pad, dl, dg)
+    tr.close()
 
 
 def test_long_ragged_sequences_t130(dev):
