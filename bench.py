@@ -203,12 +203,21 @@ def roofline_block(cfg, batch0, kdur, clk, args):
         ent = json.load(open(tp)).get(key)
         if ent:
             traffic, traffic_src = ent["dram_bytes"], ent["source"]
-    m2 = max(bounds_us, key=bounds_us.get)         # the roofline that bounds this launch (M2 ii: the max)
+    # The roofline this launch is reported against is SURVEY M2(ii)'s: the largest of the HBM,
+    # shared-memory and fp32-FMA times of the ALGORITHMIC work (one product per MAC).  For the
+    # tensor-core kernel the tensor-pipe time of the ISSUED work (3 MMAs per product) is listed
+    # too; it is the smallest of the lot.
+    m2 = max(bounds_us, key=bounds_us.get)
+    top = {"hbm": ("hbm", alg_bytes / dur / 1e9, peak, "GB/s", peak_src),
+           "fp32_fma": ("fp32_fma", flops / dur / 1e12, fma_peak, "TFLOP/s",
+                        "148 SM x 128 FMA/clk x 2 x SM clock sampled during the timed region"),
+           "tensor": ("tensor", flops / dur / 1e12, tensor_peak, "TFLOP/s",
+                      "MEASURED_PEAKS.json bf16_tflops_sustained"),
+           "smem": ("smem", None, None, None, None)}[m2]
+    if m2 == "smem":      # SIMT kernel bound by operand delivery: report it against HBM as the contract asks
+        top = ("hbm", alg_bytes / dur / 1e9, peak, "GB/s", peak_src)
     out = {"kernel": kname + f" (text encoder, H={H}, both directions, {ntok} tokens)",
-           "bound": "tensor" if tc else "hbm",
-           "achieved": (flops / dur / 1e12) if tc else (alg_bytes / dur / 1e9),
-           "peak": tensor_peak if tc else peak, "unit": "TFLOP/s" if tc else "GB/s",
-           "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if tc else peak_src,
+           "bound": top[0], "achieved": top[1], "peak": top[2], "unit": top[3], "peak_source": top[4],
            "traffic": traffic, "traffic_source": traffic_src,
            "algorithmic_bytes": alg_bytes, "algorithmic_flops": flops,
            "launch_ms": timed[kname], "launch_ms_all": timed, "plan": plan,
@@ -226,9 +235,11 @@ def roofline_block(cfg, batch0, kdur, clk, args):
                                 "terms_per_product": terms}
         out["note"] = ("tensor-core recurrence: fp32-accurate operand splits (two fp16 terms per operand, 3 MMAs "
                        "per product); a time step is a serial chain of MMA -> cell update -> L2 exchange, so "
-                       "the launch is latency-bound: `frac` (algorithmic flops vs the tensor peak) is small by "
-                       "construction, `fp32_fma.frac` compares with the best a SIMT fp32 kernel could do "
-                       "(SURVEY M2 ii), and frac_of_binding_roofline with the largest of the rooflines")
+                       "the launch is latency-bound.  `bound`/`frac` are SURVEY M2(ii)'s roofline (the largest of the "
+                       "HBM / fp32-FMA times of the algorithmic work: what the best fp32 SIMT kernel could do); "
+                       "`tensor_issued` is the tensor pipe's share of its measured peak for the MMAs actually "
+                       "issued and `hbm` the algorithmic bytes against the measured copy bandwidth -- both small, "
+                       "because neither pipe is what a 50-step serial chain waits for")
     else:
         out["note"] = "SIMT recurrence: bound by shared-memory operand delivery and fp32 FMA issue, not HBM"
     return out

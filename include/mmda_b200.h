@@ -320,6 +320,19 @@ int mmda_bert_attention_backward(const float* qkv, const float* probs, const flo
                                  float* dqkv, int B, int S, int nhead, int head_dim, float p_drop,
                                  unsigned long long seed, const unsigned long long* seed_dev,
                                  unsigned stream_id, mmda_stream_t stream);
+/* bf16-mode variants of the two calls above (precision='bf16', BASELINE configs[3]): the S x S
+ * score / probability algebra runs on the tensor pipe (mma.sync m16n8k16 bf16, fp32 accumulate,
+ * softmax in fp32 registers), S <= 64, same arguments, same dropout stream; probs stays fp32 so
+ * either backward can consume either forward's probabilities.  HF BertSelfAttention
+ * (transformers, called from src/models.py:186-193). */
+int mmda_bert_attention_forward_mma(const float* qkv, const long long* mask, float* ctx, float* probs,
+                                    int B, int S, int nhead, int head_dim, float p_drop,
+                                    unsigned long long seed, const unsigned long long* seed_dev,
+                                    unsigned stream_id, mmda_stream_t stream);
+int mmda_bert_attention_backward_mma(const float* qkv, const float* probs, const float* dctx,
+                                     float* dqkv, int B, int S, int nhead, int head_dim, float p_drop,
+                                     unsigned long long seed, const unsigned long long* seed_dev,
+                                     unsigned stream_id, mmda_stream_t stream);
 
 /* ---- device-resident collate: collate_fn, src/data_loader.py:59-122, and the
  * per-tensor to_gpu copies, src/utils/convert.py:4-11.  The split lives in HBM as ragged flat

@@ -15,6 +15,8 @@ from __future__ import annotations
 
 from typing import Dict, Optional
 
+import os
+
 import torch
 
 from ._lib import MmdaError
@@ -91,6 +93,11 @@ class BertEngine:
         self.k._c("mmda_gelu_forward", _ptr(pre), _ptr(act), None, M * I)
         return self._op("bert_opI", act)
 
+    def _att_sfx(self, S):
+        """bf16 mode runs the attention core on the tensor pipe (sequences up to 64 tokens)"""
+        return "_mma" if self.eng.tc_kind == 1 and S <= 64 and \
+            os.environ.get("MMDA_BERT_ATT", "mma") != "simt" else ""
+
     def _ln(self, x, res, g, b, y, mean, rstd):
         self.k._c("mmda_layernorm_forward", _ptr(x), x.stride(0), _ptr(res),
                   0 if res is None else res.stride(0), _ptr(g), _ptr(b), _ptr(y), y.stride(0),
@@ -137,7 +144,7 @@ class BertEngine:
                          QKV[:, j * H:(j + 1) * H], bias=P[Lp + f"attention.self.{nm}.bias"])
             ctx = buf(f"bert_ctx_{l}", M, H)
             probs = buf(f"bert_probs_{l}", B, nh, S, S) if train else None
-            k._c("mmda_bert_attention_forward", _ptr(QKV), _ptr(mask), _ptr(ctx), _ptr(probs), B, S,
+            k._c("mmda_bert_attention_forward" + self._att_sfx(S), _ptr(QKV), _ptr(mask), _ptr(ctx), _ptr(probs), B, S,
                  nh, 64, p_a, seed, _ptr(seed_dev), 201 + 4 * l)
             ao = buf(f"bert_ao_{l}", M, H)
             self._mm(0, 0, M, H, H, self._op("bert_opH", ctx),
@@ -272,7 +279,7 @@ class BertEngine:
                 wgrad(dao_op, dao, self._op("bert_opH", ctx), Lp + "attention.output.dense.weight",
                       Lp + "attention.output.dense.bias", H, H)
             dQKV = buf("bert_dqkv", M, 3 * H)
-            k._c("mmda_bert_attention_backward", _ptr(QKV), _ptr(probs), _ptr(dctx), _ptr(dQKV), B, S,
+            k._c("mmda_bert_attention_backward" + self._att_sfx(S), _ptr(QKV), _ptr(probs), _ptr(dctx), _ptr(dQKV), B, S,
                  nh, 64, p_a, seed, _ptr(seed_dev), 201 + 4 * l)
             if l > lowest or any(Lp + f"attention.self.{nm}.{wb}" in train
                                  for nm in ("query", "key", "value") for wb in ("weight", "bias")):

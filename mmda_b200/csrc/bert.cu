@@ -338,6 +338,305 @@ bert_attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ pr
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// bf16-mode attention core on the tensor pipe (BASELINE configs[3] runs the encoder in bf16):
+// mma.sync m16n8k16 bf16 with fp32 accumulation, one (sample, head) per 4-warp CTA, the whole
+// sequence (S <= 64) resident.  Forward is flash-style: the 16 x 64 score fragment of each warp
+// stays in registers through mask -> softmax -> dropout and is re-used as the A operand of P*V.
+// The backward needs dS and the dropped probabilities transposed, so those two go through shared
+// memory once (bf16); everything else is fragments.  Same dropout stream / element indexing as
+// the fp32 kernels above, so either backward matches either forward.  tcgen05 is the wrong tool
+// here: a 52 x 52 x 64 problem per head is a quarter of one 128-row UMMA tile.
+// ------------------------------------------------------------------------------------------
+constexpr int AP = 72;            // smem row pitch, bf16 elements: 144 B keeps ldmatrix conflict-free
+constexpr int ATT_MMA_S = 64;     // resident sequence length
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const __nv_bfloat16* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const __nv_bfloat16* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+// fragment addresses (lane -> the 8x8 matrix row it points ldmatrix at)
+//   A, smem X[m][k]                 : &X[(m0 + (lane & 15)) * AP + k0 + (lane >> 4) * 8]
+//   A, smem W[k][m]   (.trans)      : &W[(k0 + (q >> 1) * 8 + r) * AP + m0 + (q & 1) * 8]
+//   B, smem Y[n][k]   (two n-tiles) : &Y[(n0 + (q >> 1) * 8 + r) * AP + k0 + (q & 1) * 8]
+//   B, smem Z[k][n]   (.trans, two) : &Z[(k0 + (q & 1) * 8 + r) * AP + n0 + (q >> 1) * 8]
+// with q = lane >> 3, r = lane & 7; for B the registers come back as {b0, b1} of n-tile n0 and
+// {b0, b1} of n-tile n0 + 8.
+
+// stage rows [0, 64) x 64 features of a [token][ld] fp32 matrix as bf16 (rows >= S zero)
+__device__ __forceinline__ void stage_bf16(__nv_bfloat16* dst, const float* src, int ld, int S, int tid) {
+#pragma unroll 4
+  for (int idx = tid; idx < ATT_MMA_S * 16; idx += 128) {
+    const int s = idx >> 4, c = (idx & 15) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (s < S) v = *reinterpret_cast<const float4*>(src + (size_t)s * ld + c);
+    uint2 o;
+    o.x = pack_bf16(v.x, v.y);
+    o.y = pack_bf16(v.z, v.w);
+    *reinterpret_cast<uint2*>(dst + s * AP + c) = o;
+  }
+}
+
+__global__ void __launch_bounds__(128)
+bert_attn_fwd_mma_kernel(const float* __restrict__ qkv, const long long* __restrict__ mask,
+                         float* __restrict__ ctx, float* __restrict__ probs, int S, int nhead,
+                         float scale, float p_drop, unsigned long long seed,
+                         const unsigned long long* __restrict__ seed_dev, unsigned stream) {
+  __shared__ __align__(16) __nv_bfloat16 Qs[ATT_MMA_S * AP], Ks[ATT_MMA_S * AP], Vs[ATT_MMA_S * AP];
+  __shared__ float keep_s[ATT_MMA_S];
+  if (seed_dev) seed += seed_dev[0] * 0x9E3779B97F4A7C15ULL;
+  const int b = blockIdx.x / nhead, h = blockIdx.x % nhead;
+  const int Hd = nhead * BHD, ld = 3 * Hd;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float* base = qkv + (size_t)b * S * ld + h * BHD;
+  stage_bf16(Qs, base, ld, S, tid);
+  stage_bf16(Ks, base + Hd, ld, S, tid);
+  stage_bf16(Vs, base + 2 * Hd, ld, S, tid);
+  if (tid < ATT_MMA_S) keep_s[tid] = (tid < S && mask[(size_t)b * S + tid] != 0) ? 1.f : 0.f;
+  __syncthreads();
+  const int m0 = warp * 16;
+  if (m0 >= S) return;                       // no block-wide barrier below
+  const int q = lane >> 3, r = lane & 7, g = lane >> 2, t4 = lane & 3;
+  float sc[8][4];
+#pragma unroll
+  for (int n = 0; n < 8; ++n) sc[n][0] = sc[n][1] = sc[n][2] = sc[n][3] = 0.f;
+#pragma unroll
+  for (int kt = 0; kt < 4; ++kt) {           // scores = Q K^T
+    uint32_t a[4];
+    ldsm_x4(a, &Qs[(m0 + (lane & 15)) * AP + kt * 16 + (lane >> 4) * 8]);
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      uint32_t bk[4];
+      ldsm_x4(bk, &Ks[(np * 16 + (q >> 1) * 8 + r) * AP + kt * 16 + (q & 1) * 8]);
+      mma_bf16(sc[2 * np], a, bk[0], bk[1]);
+      mma_bf16(sc[2 * np + 1], a, bk[2], bk[3]);
+    }
+  }
+  // this thread holds rows i0 = m0 + g (elements 0,1) and i1 = i0 + 8 (elements 2,3), columns
+  // j = 8 n + 2 t4 + {0, 1}
+  const int i0 = m0 + g, i1 = i0 + 8;
+  float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+  for (int n = 0; n < 8; ++n)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int j = n * 8 + t4 * 2 + (e & 1);
+      // HF adds finfo.min to masked keys: the softmax weight is exactly 0
+      const float v = keep_s[j] != 0.f ? sc[n][e] * scale : -INFINITY;
+      sc[n][e] = v;
+      if (e < 2) mx0 = fmaxf(mx0, v); else mx1 = fmaxf(mx1, v);
+    }
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int n = 0; n < 8; ++n)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float ex = expf(sc[n][e] - (e < 2 ? mx0 : mx1));
+      sc[n][e] = ex;
+      if (e < 2) s0 += ex; else s1 += ex;
+    }
+  s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
+  s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+  s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+  s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+  const float inv0 = 1.f / s0, inv1 = 1.f / s1;
+  const float inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  const unsigned base0 = (unsigned)((b * nhead + h) * S * S);
+#pragma unroll
+  for (int n = 0; n < 8; ++n)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int i = e < 2 ? i0 : i1, j = n * 8 + t4 * 2 + (e & 1);
+      const float pr = sc[n][e] * (e < 2 ? inv0 : inv1);
+      float pd = 0.f;
+      if (i < S && j < S) {
+        if (probs) probs[(size_t)base0 + i * S + j] = pr;
+        pd = pr * drop_scale(seed, stream, base0 + i * S + j, p_drop, inv_keep);
+      }
+      sc[n][e] = pd;
+    }
+  float o[8][4];
+#pragma unroll
+  for (int n = 0; n < 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+#pragma unroll
+  for (int kt = 0; kt < 4; ++kt) {           // context = dropped probabilities * V
+    uint32_t a[4];
+    a[0] = pack_bf16(sc[2 * kt][0], sc[2 * kt][1]);
+    a[1] = pack_bf16(sc[2 * kt][2], sc[2 * kt][3]);
+    a[2] = pack_bf16(sc[2 * kt + 1][0], sc[2 * kt + 1][1]);
+    a[3] = pack_bf16(sc[2 * kt + 1][2], sc[2 * kt + 1][3]);
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      uint32_t bv[4];
+      ldsm_x4_t(bv, &Vs[(kt * 16 + (q & 1) * 8 + r) * AP + np * 16 + (q >> 1) * 8]);
+      mma_bf16(o[2 * np], a, bv[0], bv[1]);
+      mma_bf16(o[2 * np + 1], a, bv[2], bv[3]);
+    }
+  }
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    const int c = n * 8 + t4 * 2;
+    if (i0 < S)
+      *reinterpret_cast<float2*>(ctx + (size_t)(b * S + i0) * Hd + h * BHD + c) = make_float2(o[n][0], o[n][1]);
+    if (i1 < S)
+      *reinterpret_cast<float2*>(ctx + (size_t)(b * S + i1) * Hd + h * BHD + c) = make_float2(o[n][2], o[n][3]);
+  }
+}
+
+constexpr int ATT_MMA_BWD_SMEM = 6 * ATT_MMA_S * AP * 2;      // Q K V dO Pd dS, bf16
+
+__global__ void __launch_bounds__(128)
+bert_attn_bwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ probs,
+                         const float* __restrict__ dctx, float* __restrict__ dqkv, int S, int nhead,
+                         float scale, float p_drop, unsigned long long seed,
+                         const unsigned long long* __restrict__ seed_dev, unsigned stream) {
+  extern __shared__ __align__(16) unsigned char att_smem[];
+  __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(att_smem);
+  __nv_bfloat16* Ks = Qs + ATT_MMA_S * AP;
+  __nv_bfloat16* Vs = Ks + ATT_MMA_S * AP;
+  __nv_bfloat16* Cs = Vs + ATT_MMA_S * AP;     // d(context)
+  __nv_bfloat16* Ps = Cs + ATT_MMA_S * AP;     // dropped probabilities [i][j]
+  __nv_bfloat16* Ds = Ps + ATT_MMA_S * AP;     // d(scores) [i][j]
+  if (seed_dev) seed += seed_dev[0] * 0x9E3779B97F4A7C15ULL;
+  const int b = blockIdx.x / nhead, h = blockIdx.x % nhead;
+  const int Hd = nhead * BHD, ld = 3 * Hd;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float* base = qkv + (size_t)b * S * ld + h * BHD;
+  stage_bf16(Qs, base, ld, S, tid);
+  stage_bf16(Ks, base + Hd, ld, S, tid);
+  stage_bf16(Vs, base + 2 * Hd, ld, S, tid);
+  stage_bf16(Cs, dctx + (size_t)b * S * Hd + h * BHD, Hd, S, tid);
+  __syncthreads();
+  const int m0 = warp * 16;
+  const int q = lane >> 3, r = lane & 7, g = lane >> 2, t4 = lane & 3;
+  const int i0 = m0 + g, i1 = i0 + 8;
+  const unsigned base0 = (unsigned)((b * nhead + h) * S * S);
+  const float inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  float dp[8][4];
+#pragma unroll
+  for (int n = 0; n < 8; ++n) dp[n][0] = dp[n][1] = dp[n][2] = dp[n][3] = 0.f;
+#pragma unroll
+  for (int kt = 0; kt < 4; ++kt) {           // d(dropped probs) = dO V^T
+    uint32_t a[4];
+    ldsm_x4(a, &Cs[(m0 + (lane & 15)) * AP + kt * 16 + (lane >> 4) * 8]);
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      uint32_t bv[4];
+      ldsm_x4(bv, &Vs[(np * 16 + (q >> 1) * 8 + r) * AP + kt * 16 + (q & 1) * 8]);
+      mma_bf16(dp[2 * np], a, bv[0], bv[1]);
+      mma_bf16(dp[2 * np + 1], a, bv[2], bv[3]);
+    }
+  }
+  float pr[8][4];
+  float r0 = 0.f, r1 = 0.f;
+#pragma unroll
+  for (int n = 0; n < 8; ++n)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int i = e < 2 ? i0 : i1, j = n * 8 + t4 * 2 + (e & 1);
+      float p = 0.f, f = 0.f;
+      if (i < S && j < S) {
+        p = probs[(size_t)base0 + i * S + j];
+        f = drop_scale(seed, stream, base0 + i * S + j, p_drop, inv_keep);
+      }
+      const float d = dp[n][e] * f;          // d(probs)
+      dp[n][e] = d;
+      pr[n][e] = p;
+      if (e < 2) r0 = fmaf(d, p, r0); else r1 = fmaf(d, p, r1);
+      Ps[i * AP + j] = __float2bfloat16_rn(p * f);     // dropped probability, read transposed for dV
+    }
+  r0 += __shfl_xor_sync(0xffffffffu, r0, 1);
+  r0 += __shfl_xor_sync(0xffffffffu, r0, 2);
+  r1 += __shfl_xor_sync(0xffffffffu, r1, 1);
+  r1 += __shfl_xor_sync(0xffffffffu, r1, 2);
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {              // softmax backward -> d(scores), kept as A fragments
+    const int j = n * 8 + t4 * 2;
+    dp[n][0] = pr[n][0] * (dp[n][0] - r0) * scale;
+    dp[n][1] = pr[n][1] * (dp[n][1] - r0) * scale;
+    dp[n][2] = pr[n][2] * (dp[n][2] - r1) * scale;
+    dp[n][3] = pr[n][3] * (dp[n][3] - r1) * scale;
+    *reinterpret_cast<uint32_t*>(&Ds[i0 * AP + j]) = pack_bf16(dp[n][0], dp[n][1]);
+    *reinterpret_cast<uint32_t*>(&Ds[i1 * AP + j]) = pack_bf16(dp[n][2], dp[n][3]);
+  }
+  float acc[8][4];
+#pragma unroll
+  for (int n = 0; n < 8; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+#pragma unroll
+  for (int kt = 0; kt < 4; ++kt) {           // dQ[i] = sum_j dS[i][j] K[j]
+    uint32_t a[4];
+    a[0] = pack_bf16(dp[2 * kt][0], dp[2 * kt][1]);
+    a[1] = pack_bf16(dp[2 * kt][2], dp[2 * kt][3]);
+    a[2] = pack_bf16(dp[2 * kt + 1][0], dp[2 * kt + 1][1]);
+    a[3] = pack_bf16(dp[2 * kt + 1][2], dp[2 * kt + 1][3]);
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      uint32_t bk[4];
+      ldsm_x4_t(bk, &Ks[(kt * 16 + (q & 1) * 8 + r) * AP + np * 16 + (q >> 1) * 8]);
+      mma_bf16(acc[2 * np], a, bk[0], bk[1]);
+      mma_bf16(acc[2 * np + 1], a, bk[2], bk[3]);
+    }
+  }
+  auto store_rows = [&](float (&v)[8][4], int which) {
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      const int c = n * 8 + t4 * 2;
+      if (i0 < S)
+        *reinterpret_cast<float2*>(dqkv + (size_t)(b * S + i0) * ld + which * Hd + h * BHD + c) =
+            make_float2(v[n][0], v[n][1]);
+      if (i1 < S)
+        *reinterpret_cast<float2*>(dqkv + (size_t)(b * S + i1) * ld + which * Hd + h * BHD + c) =
+            make_float2(v[n][2], v[n][3]);
+    }
+  };
+  store_rows(acc, 0);
+  __syncthreads();                           // every warp's rows of Pd / dS are in shared memory
+  float dv[8][4];
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+    dv[n][0] = dv[n][1] = dv[n][2] = dv[n][3] = 0.f;
+  }
+#pragma unroll
+  for (int kt = 0; kt < 4; ++kt) {           // key rows m0..: dK[j] = sum_i dS[i][j] Q[i]; dV[j] = sum_i Pd[i][j] dO[i]
+    uint32_t ad[4], ap[4];
+    ldsm_x4_t(ad, &Ds[(kt * 16 + (q >> 1) * 8 + r) * AP + m0 + (q & 1) * 8]);
+    ldsm_x4_t(ap, &Ps[(kt * 16 + (q >> 1) * 8 + r) * AP + m0 + (q & 1) * 8]);
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      uint32_t bq[4], bc[4];
+      ldsm_x4_t(bq, &Qs[(kt * 16 + (q & 1) * 8 + r) * AP + np * 16 + (q >> 1) * 8]);
+      mma_bf16(acc[2 * np], ad, bq[0], bq[1]);
+      mma_bf16(acc[2 * np + 1], ad, bq[2], bq[3]);
+      ldsm_x4_t(bc, &Cs[(kt * 16 + (q & 1) * 8 + r) * AP + np * 16 + (q >> 1) * 8]);
+      mma_bf16(dv[2 * np], ap, bc[0], bc[1]);
+      mma_bf16(dv[2 * np + 1], ap, bc[2], bc[3]);
+    }
+  }
+  store_rows(acc, 1);
+  store_rows(dv, 2);
+}
+
 static inline int ew_grid_b(size_t n) {
   size_t g = (n + 255) / 256;
   return (int)(g > 148 * 16 ? 148 * 16 : (g == 0 ? 1 : g));
@@ -436,6 +735,38 @@ int mmda_bert_attention_backward(const float* qkv, const float* probs, const flo
   bert_attn_bwd_kernel<<<B * nhead, ATT_THREADS, smem, stream>>>(qkv, probs, dctx, dqkv, S, nhead,
                                                          1.0f / sqrtf((float)head_dim), p_drop,
                                                          seed, seed_dev, stream_id);
+  MMDA_CHECK_LAUNCH();
+  return MMDA_OK;
+}
+
+// bf16 tensor-core variants (S <= 64): same contract as the fp32 calls above; probs stays fp32.
+int mmda_bert_attention_forward_mma(const float* qkv, const long long* mask, float* ctx, float* probs,
+                                    int B, int S, int nhead, int head_dim, float p_drop,
+                                    unsigned long long seed, const unsigned long long* seed_dev,
+                                    unsigned stream_id, cudaStream_t stream) {
+  MMDA_REQUIRE(head_dim == BHD, "bert_attention: head_dim %d (bert-base uses 64)", head_dim);
+  MMDA_REQUIRE(B > 0 && S > 0 && S <= ATT_MMA_S, "bert_attention_mma: sequence %d > %d", S, ATT_MMA_S);
+  MMDA_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(ctx) & 7) == 0,
+               "bert_attention_mma: unaligned operands");
+  bert_attn_fwd_mma_kernel<<<B * nhead, 128, 0, stream>>>(qkv, mask, ctx, probs, S, nhead,
+                                                          1.0f / sqrtf((float)head_dim), p_drop, seed,
+                                                          seed_dev, stream_id);
+  MMDA_CHECK_LAUNCH();
+  return MMDA_OK;
+}
+
+int mmda_bert_attention_backward_mma(const float* qkv, const float* probs, const float* dctx,
+                                     float* dqkv, int B, int S, int nhead, int head_dim, float p_drop,
+                                     unsigned long long seed, const unsigned long long* seed_dev,
+                                     unsigned stream_id, cudaStream_t stream) {
+  MMDA_REQUIRE(head_dim == BHD, "bert_attention: head_dim %d (bert-base uses 64)", head_dim);
+  MMDA_REQUIRE(B > 0 && S > 0 && S <= ATT_MMA_S, "bert_attention_mma: sequence %d > %d", S, ATT_MMA_S);
+  MMDA_REQUIRE(((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(dctx)) & 15) == 0 &&
+               (reinterpret_cast<uintptr_t>(dqkv) & 7) == 0, "bert_attention_mma: unaligned operands");
+  MMDA_CUDA(cudaFuncSetAttribute(bert_attn_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 ATT_MMA_BWD_SMEM));
+  bert_attn_bwd_mma_kernel<<<B * nhead, 128, ATT_MMA_BWD_SMEM, stream>>>(
+      qkv, probs, dctx, dqkv, S, nhead, 1.0f / sqrtf((float)head_dim), p_drop, seed, seed_dev, stream_id);
   MMDA_CHECK_LAUNCH();
   return MMDA_OK;
 }

@@ -111,6 +111,85 @@ layernorm_bwd_kernel(const float* __restrict__ dy, int lddy, const float* __rest
   }
 }
 
+// Same arithmetic, 16-byte accesses and ONE pass over the row: each lane keeps its float4 chunks of
+// xhat and dy*gamma in registers between the two row reductions and the dx store, so dy / x / res
+// are read once and dx written once (4 x rows x width x 4 B of traffic in all).  Needs width % 4
+// == 0 and 16-byte aligned rows; NV = float4 chunks per lane (width <= 128 * NV).
+template <int NV>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_v4_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ x, int ldx,
+                        const float* __restrict__ res, int ldr, const float* __restrict__ gamma,
+                        const float* __restrict__ mean, const float* __restrict__ rstd,
+                        float* __restrict__ dx, int lddx, float* __restrict__ dgamma,
+                        float* __restrict__ dbeta, int rows, int width, int rows_per_block) {
+  __shared__ float4 red[8][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r_beg = blockIdx.x * rows_per_block;
+  const int r_end = min(rows, r_beg + rows_per_block);
+  const int w4 = width >> 2;
+  float4 ag[NV], ab[NV], g4[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int c = lane + 32 * i;
+    g4[i] = c < w4 ? reinterpret_cast<const float4*>(gamma)[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float inv_w = 1.f / width;
+  for (int row = r_beg + warp; row < r_end; row += 8) {
+    const float4* dyr = reinterpret_cast<const float4*>(dy + (size_t)row * lddy);
+    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * ldx);
+    const float4* rr = res ? reinterpret_cast<const float4*>(res + (size_t)row * ldr) : nullptr;
+    const float mu = mean[row], rs = rstd[row];
+    float4 xh[NV], dg[NV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < w4) {
+        float4 xv = xr[c];
+        const float4 d = dyr[c];
+        if (rr) { const float4 r4 = rr[c]; xv.x += r4.x; xv.y += r4.y; xv.z += r4.z; xv.w += r4.w; }
+        xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+        dg[i] = make_float4(d.x * g4[i].x, d.y * g4[i].y, d.z * g4[i].z, d.w * g4[i].w);
+        s1 += (dg[i].x + dg[i].y) + (dg[i].z + dg[i].w);
+        s2 = fmaf(dg[i].x, xh[i].x, fmaf(dg[i].y, xh[i].y, fmaf(dg[i].z, xh[i].z, fmaf(dg[i].w, xh[i].w, s2))));
+        ag[i].x = fmaf(d.x, xh[i].x, ag[i].x); ag[i].y = fmaf(d.y, xh[i].y, ag[i].y);
+        ag[i].z = fmaf(d.z, xh[i].z, ag[i].z); ag[i].w = fmaf(d.w, xh[i].w, ag[i].w);
+        ab[i].x += d.x; ab[i].y += d.y; ab[i].z += d.z; ab[i].w += d.w;
+      }
+    }
+    s1 = warp_sum(s1) * inv_w;
+    s2 = warp_sum(s2) * inv_w;
+    float4* dxr = reinterpret_cast<float4*>(dx + (size_t)row * lddx);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < w4)
+        dxr[c] = make_float4(rs * (dg[i].x - s1 - xh[i].x * s2), rs * (dg[i].y - s1 - xh[i].y * s2),
+                             rs * (dg[i].z - s1 - xh[i].z * s2), rs * (dg[i].w - s1 - xh[i].w * s2));
+    }
+  }
+  // cross-warp reduction of the per-column partials, one atomic per column per block
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    if (32 * i < w4) {   // block-uniform
+#pragma unroll
+      for (int which = 0; which < 2; ++which) {
+        __syncthreads();
+        red[warp][lane] = which ? ab[i] : ag[i];
+        __syncthreads();
+        if (warp < 4) {          // warp w sums component w of the 32 float4 columns
+          const int c = lane + 32 * i;
+          float t = 0.f;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) t += reinterpret_cast<const float*>(&red[w][lane])[warp];
+          if (c < w4) atomicAdd((which ? dbeta : dgamma) + 4 * c + warp, t);
+        }
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------- elementwise ---------------
 __global__ void act_fwd_kernel(float* __restrict__ x, int ld, int rows, int cols, int act) {
   const size_t n = (size_t)rows * cols;
@@ -337,7 +416,21 @@ int mmda_layernorm_backward(const float* dy, int lddy, const float* x, int ldx, 
   int rpb = (rows + 295) / 296;
   rpb = (rpb + 7) / 8 * 8;
   const int grid = (rows + rpb - 1) / rpb;
-  if (width <= 32 * LN_MAXC)
+  const bool v4 = width % 4 == 0 && lddy % 4 == 0 && ldx % 4 == 0 && lddx % 4 == 0 &&
+                  (!res || ldr % 4 == 0) &&
+                  ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) |
+                    reinterpret_cast<uintptr_t>(res) | reinterpret_cast<uintptr_t>(dx) |
+                    reinterpret_cast<uintptr_t>(gamma)) & 15) == 0;
+  if (v4 && width <= 256)
+    layernorm_bwd_v4_kernel<2><<<grid, 256, 0, stream>>>(dy, lddy, x, ldx, res, ldr, gamma, mean, rstd,
+                                                         dx, lddx, dgamma, dbeta, rows, width, rpb);
+  else if (v4 && width <= 640)
+    layernorm_bwd_v4_kernel<5><<<grid, 256, 0, stream>>>(dy, lddy, x, ldx, res, ldr, gamma, mean, rstd,
+                                                         dx, lddx, dgamma, dbeta, rows, width, rpb);
+  else if (v4)
+    layernorm_bwd_v4_kernel<8><<<grid, 256, 0, stream>>>(dy, lddy, x, ldx, res, ldr, gamma, mean, rstd,
+                                                         dx, lddx, dgamma, dbeta, rows, width, rpb);
+  else if (width <= 32 * LN_MAXC)
     layernorm_bwd_kernel<LN_MAXC><<<grid, 256, 0, stream>>>(dy, lddy, x, ldx, res, ldr, gamma, mean,
                                                             rstd, dx, lddx, dgamma, dbeta, rows,
                                                             width, rpb);

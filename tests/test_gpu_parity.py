@@ -90,7 +90,7 @@ def test_layernorm_attention_colsum(dev):
     k = Kernels(); k.bind_stream()
     g = torch.Generator().manual_seed(1)
     C = Checks("rowwise")
-    for rows, width in [(37, 70), (1536, 128), (999, 600), (8, 148)]:
+    for rows, width in [(37, 70), (1536, 128), (999, 600), (8, 148), (300, 768), (65, 1024)]:
         x = torch.randn(rows, width, generator=g).to(dev); r = torch.randn(rows, width, generator=g).to(dev)
         gam = (torch.rand(width, generator=g) + 0.5).to(dev); bet = torch.randn(width, generator=g).to(dev)
         dy = torch.randn(rows, width, generator=g).to(dev)
@@ -780,6 +780,54 @@ def test_gru_cells(dev, sizes, B, T):
     state = {k: v.clone() for k, v in oracle_build(cfg, 7).state_dict().items()}
     batch = batch_for(cfg, seed=8, lengths="shuffled", seq_len=T)
     _model_checks(f"gru_{sizes[0]}_{B}", cfg, state, batch, dev, None)
+
+
+def test_bert_attention_tensor_core_kernels(dev):
+    """bf16-mode attention core (mma.sync) vs fp64 math built from the bf16-rounded operands'
+    fp32 originals: forward context / probabilities and the three input gradients within the
+    2e-2 bf16 bar (relative to the tensor's max); with dropout on, against the fp32 SIMT kernels
+    of the same dropout stream."""
+    from mmda_b200.engine import Kernels, _ptr
+    k = Kernels(); k.bind_stream()
+    g = torch.Generator().manual_seed(3)
+    C = Checks("bert_attn_mma")
+    for B, S, nh in [(3, 52, 12), (2, 64, 12), (5, 11, 12), (4, 17, 2)]:
+        Hd = nh * 64
+        qkv = (torch.randn(B * S, 3 * Hd, generator=g) * 1.5).to(dev)
+        mask = torch.ones(B, S, dtype=torch.int64)
+        for bi in range(B):
+            mask[bi, S - (bi * 3) % S:] = 0 if bi else 1          # right-padded samples
+        mask = mask.to(dev)
+        do = torch.randn(B * S, Hd, generator=g).to(dev)
+        ctx = torch.empty(B * S, Hd, device=dev); pr = torch.empty(B, nh, S, S, device=dev)
+        k._c("mmda_bert_attention_forward_mma", _ptr(qkv), _ptr(mask), _ptr(ctx), _ptr(pr), B, S, nh, 64,
+             0.0, 1, None, 7)
+        q3 = qkv.double().view(B, S, 3, nh, 64).requires_grad_(True)
+        q, kk, v = q3[:, :, 0], q3[:, :, 1], q3[:, :, 2]
+        s = torch.einsum("bihd,bjhd->bhij", q, kk) / 8.0
+        s = s.masked_fill(mask[:, None, None, :] == 0, float("-inf"))
+        p = torch.softmax(s, -1)
+        o = torch.einsum("bhij,bjhd->bihd", p, v).reshape(B * S, Hd)
+        o.backward(do.double())
+        C.add(f"ctx B={B} S={S} nh={nh}", ctx, o, 2e-2)
+        C.add(f"probs B={B} S={S} nh={nh}", pr, p, 2e-2)
+        dqkv = torch.full_like(qkv, float("nan"))
+        k._c("mmda_bert_attention_backward_mma", _ptr(qkv), _ptr(pr), _ptr(do), _ptr(dqkv), B, S, nh, 64,
+             0.0, 1, None, 7)
+        gq = q3.grad.reshape(B * S, 3, Hd)
+        for j, nm in enumerate(("dQ", "dK", "dV")):
+            C.add(f"{nm} B={B} S={S} nh={nh}", dqkv.view(B * S, 3, Hd)[:, j], gq[:, j], 2e-2)
+        # dropout on: same stream -> same mask as the fp32 kernels
+        ctx1 = torch.empty_like(ctx); pr1 = torch.empty_like(pr); d1 = torch.empty_like(qkv)
+        ctx2 = torch.empty_like(ctx); pr2 = torch.empty_like(pr); d2 = torch.empty_like(qkv)
+        for sfx, (c_, p_, d_) in (("", (ctx1, pr1, d1)), ("_mma", (ctx2, pr2, d2))):
+            k._c("mmda_bert_attention_forward" + sfx, _ptr(qkv), _ptr(mask), _ptr(c_), _ptr(p_), B, S, nh,
+                 64, 0.1, 99, None, 5)
+            k._c("mmda_bert_attention_backward" + sfx, _ptr(qkv), _ptr(p_), _ptr(do), _ptr(d_), B, S, nh,
+                 64, 0.1, 99, None, 5)
+        C.add(f"dropout ctx B={B} S={S}", ctx2, ctx1, 2e-2)
+        C.add(f"dropout dqkv B={B} S={S}", d2, d1, 2e-2)
+    C.finish()
 
 
 def test_bert_bf16_mode_within_2e2(dev):
