@@ -182,6 +182,25 @@ int mmda_layernorm_backward(const float* dy, int lddy, const float* x, int ldx, 
                             int ldr, const float* gamma, const float* mean, const float* rstd,
                             float* dx, int lddx, float* dgamma, float* dbeta, int rows, int width,
                             mmda_stream_t stream);
+/* BERT residual blocks: y = LayerNorm(dropout(x) + res) in one pass over the row (HF BertSelfOutput
+ * / BertOutput: dense -> dropout -> LayerNorm(. + input), called from src/models.py:186-193).  x is
+ * overwritten with dropout(x) when p > 0 (the backward reads it); y_bf16 (nullable, [rows][width])
+ * is the operand copy of y for the GEMMs that consume it.  Dropout element index = row*width+col on
+ * stream stream_id, i.e. what mmda_dropout draws for the same contiguous tensor. */
+int mmda_dropout_layernorm_forward(float* x, int ldx, const float* res, int ldr, const float* gamma,
+                                   const float* beta, float* y, int ldy, void* y_bf16, float* mean,
+                                   float* rstd, int rows, int width, float eps, float p,
+                                   unsigned long long seed, const unsigned long long* seed_dev,
+                                   unsigned stream_id, mmda_stream_t stream);
+/* mmda_layernorm_backward that also emits dropout(dx) -- the gradient of the dense layer's output
+ * that sat under the forward's dropout -- as fp32 (ddrop, nullable) and / or bf16 (ddrop_bf16,
+ * nullable), both contiguous [rows][width]; p = 0 makes them plain copies. */
+int mmda_layernorm_backward_dropout(const float* dy, int lddy, const float* x, int ldx, const float* res,
+                                    int ldr, const float* gamma, const float* mean, const float* rstd,
+                                    float* dx, int lddx, float* dgamma, float* dbeta, int rows, int width,
+                                    float* ddrop, void* ddrop_bf16, float p, unsigned long long seed,
+                                    const unsigned long long* seed_dev, unsigned stream_id,
+                                    mmda_stream_t stream);
 
 /* ---- elementwise ---------------------------------------------------------------------------- */
 int mmda_act_forward(float* x, int ld, int rows, int cols, int act, mmda_stream_t stream);
@@ -323,14 +342,19 @@ int mmda_bert_attention_backward(const float* qkv, const float* probs, const flo
 /* bf16-mode variants of the two calls above (precision='bf16', BASELINE configs[3]): the S x S
  * score / probability algebra runs on the tensor pipe (mma.sync m16n8k16 bf16, fp32 accumulate,
  * softmax in fp32 registers), S <= 64, same arguments, same dropout stream; probs stays fp32 so
- * either backward can consume either forward's probabilities.  HF BertSelfAttention
+ * either backward can consume either forward's probabilities; ctx_bf16 (nullable, [B*S][nhead*64]
+ * bf16) is the copy the output-projection GEMM consumes, written by the same kernel (ctx itself may
+ * then be NULL where no weight gradient will need it); likewise dqkv_bf16 ([B*S][3*nhead*64] bf16)
+ * is the operand copy of d(qkv) for the Q/K/V dgrad / wgrad GEMMs, and dqkv may be NULL where no
+ * bias column sum reads it.  HF BertSelfAttention
  * (transformers, called from src/models.py:186-193). */
-int mmda_bert_attention_forward_mma(const float* qkv, const long long* mask, float* ctx, float* probs,
-                                    int B, int S, int nhead, int head_dim, float p_drop,
+int mmda_bert_attention_forward_mma(const float* qkv, const long long* mask, float* ctx, void* ctx_bf16,
+                                    float* probs, int B, int S, int nhead, int head_dim, float p_drop,
                                     unsigned long long seed, const unsigned long long* seed_dev,
                                     unsigned stream_id, mmda_stream_t stream);
 int mmda_bert_attention_backward_mma(const float* qkv, const float* probs, const float* dctx,
-                                     float* dqkv, int B, int S, int nhead, int head_dim, float p_drop,
+                                     float* dqkv, void* dqkv_bf16, int B, int S, int nhead,
+                                     int head_dim, float p_drop,
                                      unsigned long long seed, const unsigned long long* seed_dev,
                                      unsigned stream_id, mmda_stream_t stream);
 

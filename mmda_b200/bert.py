@@ -45,6 +45,7 @@ class BertEngine:
             raise MmdaError("bert: head_dim must be 64 (bert-base geometry)")
         self._pver = None
         self.saved = None
+        self._wcache, self._par = {}, {}
 
     # ------------------------------------------------------------------ parameters ---------
     def params(self) -> Dict[str, torch.Tensor]:
@@ -59,6 +60,8 @@ class BertEngine:
                     raise MmdaError(f"bert parameter {n} must be a contiguous CUDA float32 tensor "
                                     "(no CPU fallback)")
             self._P = {PFX + n: p.data for n, p in ps}
+            self._par = {PFX + n: p for n, p in ps}
+            self._wcache = {}
             self._pver = ver
         return self._P
 
@@ -72,10 +75,52 @@ class BertEngine:
         return self.eng._prep(name, x)
 
     def _wop(self, P, name):
+        """Tensor-core operand copy of a weight: made once per step for trainable weights, once per
+        (tensor version, storage) for frozen ones (layers 0-8 under Solver.build's freeze,
+        solver.py:69-73) -- their copies live in per-weight workspace buffers nobody else writes.
+        In-place edits through ``param.data`` do not bump the version: call ``drop_weight_cache()``
+        after such an edit."""
         ops = self._wops
         if name not in ops:
-            ops[name] = self.eng._prep("bertW_" + name, P[name], split=True)
+            par = self._par.get(name)
+            if par is not None and not par.requires_grad:
+                ver = (par._version, par.data_ptr(), self.eng.tc_kind)
+                ent = self._wcache.get(name)
+                if ent is None or ent[0] != ver:
+                    ent = (ver, self.eng._prep("bertW_" + name, P[name], split=True))
+                    self._wcache[name] = ent
+                ops[name] = ent[1]
+            else:
+                ops[name] = self.eng._prep("bertW_" + name, P[name], split=True)
         return ops[name]
+
+    def _wqkv(self, P, l):
+        """bf16 mode: the stacked [Wq; Wk; Wv] operand copy ([3H][H]) and bias ([3H]) of layer l,
+        cached like `_wop` (per step if any of the six tensors trains, else per version)."""
+        key = f"qkv{l}"
+        if key in self._wops:
+            return self._wops[key]
+        H, eng = self.H, self.eng
+        Lp = f"{PFX}encoder.layer.{l}.attention.self."
+        names = [Lp + f"{nm}.{wb}" for nm in ("query", "key", "value") for wb in ("weight", "bias")]
+        pars = [self._par[n] for n in names]
+        frozen = not any(p.requires_grad for p in pars)
+        ver = tuple((p._version, p.data_ptr()) for p in pars)
+        ent = self._wcache.get(key) if frozen else None
+        if ent is None or ent[0] != ver:
+            W = eng._prep_buf(f"bertWqkv_{l}", 3 * H, H, 1)
+            b = eng.buf(f"bert_bqkv_{l}", 3 * H)
+            for j in range(3):
+                eng._prep(f"bertWqkv_{l}", P[names[2 * j]], out=W, row0=j * H, kind=1)
+                b[j * H:(j + 1) * H].copy_(P[names[2 * j + 1]], non_blocking=True)
+            ent = (ver, (W, b))
+            if frozen:
+                self._wcache[key] = ent
+        self._wops[key] = ent[1]
+        return ent[1]
+
+    def drop_weight_cache(self):
+        self._wcache = {}
 
     def _mm(self, a_mn, b_mn, M, N, K, A, B, C, bias=None, acc=False):
         self.k.gemm_tc(self.eng.tc_kind, a_mn, b_mn, M, N, K, A, B, C, bias=bias,
@@ -97,6 +142,23 @@ class BertEngine:
         """bf16 mode runs the attention core on the tensor pipe (sequences up to 64 tokens)"""
         return "_mma" if self.eng.tc_kind == 1 and S <= 64 and \
             os.environ.get("MMDA_BERT_ATT", "mma") != "simt" else ""
+
+    def _opbuf(self, name, M):
+        """bf16 operand buffer a producer kernel writes directly (bf16 mode), else None"""
+        return self.eng._prep_buf(name, M, self.H, 1)[0] if self.eng.tc_kind == 1 else None
+
+    def _drop_ln(self, x, res, g, b, y, y_bf, mean, rstd, p, seed, seed_dev, stream_id):
+        """y = LN(dropout(x) + res); x := dropout(x); optional bf16 operand copy of y"""
+        self.k._c("mmda_dropout_layernorm_forward", _ptr(x), x.stride(0), _ptr(res), res.stride(0),
+                  _ptr(g), _ptr(b), _ptr(y), y.stride(0), _ptr(y_bf), _ptr(mean), _ptr(rstd),
+                  x.shape[0], x.shape[1], self.eps, p, seed, _ptr(seed_dev), stream_id)
+
+    def _ln_bwd_drop(self, dy, x, res, g, mean, rstd, dx, dg, db, ddrop, ddrop_bf, p, seed, seed_dev,
+                     stream_id):
+        self.k._c("mmda_layernorm_backward_dropout", _ptr(dy), dy.stride(0), _ptr(x), x.stride(0),
+                  _ptr(res), res.stride(0), _ptr(g), _ptr(mean), _ptr(rstd), _ptr(dx), dx.stride(0),
+                  _ptr(dg), _ptr(db), x.shape[0], x.shape[1], _ptr(ddrop), _ptr(ddrop_bf), p, seed,
+                  _ptr(seed_dev), stream_id)
 
     def _ln(self, x, res, g, b, y, mean, rstd):
         self.k._c("mmda_layernorm_forward", _ptr(x), x.stride(0), _ptr(res),
@@ -135,40 +197,55 @@ class BertEngine:
                  stats[0, 1])
         if p_h > 0:
             k.dropout(x, x, p_h, seed, 200, seed_dev)
+        bf = eng.tc_kind == 1
+        xop = None                   # bf16 operand copy of x written by the producing kernel
         for l in range(self.L):
             Lp = f"{PFX}encoder.layer.{l}."
             QKV = buf(f"bert_qkv_{l}", M, 3 * H)
-            xop = self._op("bert_opH", x)
-            for j, nm in enumerate(("query", "key", "value")):
-                self._mm(0, 0, M, H, H, xop, self._wop(P, Lp + f"attention.self.{nm}.weight"),
-                         QKV[:, j * H:(j + 1) * H], bias=P[Lp + f"attention.self.{nm}.bias"])
+            if xop is None:
+                xop = self._op("bert_opH", x)
+            if bf:       # one N = 3H GEMM against the stacked [Wq; Wk; Wv] operand copy
+                Wqkv, bqkv = self._wqkv(P, l)
+                self._mm(0, 0, M, 3 * H, H, xop, Wqkv, QKV, bias=bqkv)
+            else:
+                for j, nm in enumerate(("query", "key", "value")):
+                    self._mm(0, 0, M, H, H, xop, self._wop(P, Lp + f"attention.self.{nm}.weight"),
+                             QKV[:, j * H:(j + 1) * H], bias=P[Lp + f"attention.self.{nm}.bias"])
             ctx = buf(f"bert_ctx_{l}", M, H)
             probs = buf(f"bert_probs_{l}", B, nh, S, S) if train else None
-            k._c("mmda_bert_attention_forward" + self._att_sfx(S), _ptr(QKV), _ptr(mask), _ptr(ctx), _ptr(probs), B, S,
-                 nh, 64, p_a, seed, _ptr(seed_dev), 201 + 4 * l)
+            sfx = self._att_sfx(S)
+            if sfx:      # tensor-pipe core: writes the out-projection's bf16 operand itself
+                ctx_bf = self._opbuf("bert_opH", M)
+                k._c("mmda_bert_attention_forward_mma", _ptr(QKV), _ptr(mask), _ptr(ctx) if train else None,
+                     _ptr(ctx_bf), _ptr(probs), B, S, nh, 64, p_a, seed, _ptr(seed_dev), 201 + 4 * l)
+                ctx_op = (ctx_bf, None)
+            else:
+                k._c("mmda_bert_attention_forward", _ptr(QKV), _ptr(mask), _ptr(ctx), _ptr(probs), B, S,
+                     nh, 64, p_a, seed, _ptr(seed_dev), 201 + 4 * l)
+                ctx_op = self._op("bert_opH", ctx)
             ao = buf(f"bert_ao_{l}", M, H)
-            self._mm(0, 0, M, H, H, self._op("bert_opH", ctx),
+            self._mm(0, 0, M, H, H, ctx_op,
                      self._wop(P, Lp + "attention.output.dense.weight"), ao,
                      bias=P[Lp + "attention.output.dense.bias"])
-            if p_h > 0:
-                k.dropout(ao, ao, p_h, seed, 202 + 4 * l, seed_dev)
             h1 = buf(f"bert_h1_{l}", M, H)
-            self._ln(ao, x, P[Lp + "attention.output.LayerNorm.weight"],
-                     P[Lp + "attention.output.LayerNorm.bias"], h1, stats[1 + 2 * l, 0],
-                     stats[1 + 2 * l, 1])
+            h1_bf = self._opbuf("bert_opH", M)
+            self._drop_ln(ao, x, P[Lp + "attention.output.LayerNorm.weight"],
+                          P[Lp + "attention.output.LayerNorm.bias"], h1, h1_bf, stats[1 + 2 * l, 0],
+                          stats[1 + 2 * l, 1], p_h, seed, seed_dev, 202 + 4 * l)
             pre = buf(f"bert_pre_{l}", M, I)
-            self._mm(0, 0, M, I, H, self._op("bert_opH", h1),
+            self._mm(0, 0, M, I, H, (h1_bf, None) if bf else self._op("bert_opH", h1),
                      self._wop(P, Lp + "intermediate.dense.weight"), pre,
                      bias=P[Lp + "intermediate.dense.bias"])
             fo = buf(f"bert_fo_{l}", M, H)
             self._mm(0, 0, M, H, I, self._gelu(l, pre, M),
                      self._wop(P, Lp + "output.dense.weight"), fo, bias=P[Lp + "output.dense.bias"])
-            if p_h > 0:
-                k.dropout(fo, fo, p_h, seed, 203 + 4 * l, seed_dev)
             xn = buf(f"bert_x_{l + 1}", M, H)
-            self._ln(fo, h1, P[Lp + "output.LayerNorm.weight"], P[Lp + "output.LayerNorm.bias"], xn,
-                     stats[2 + 2 * l, 0], stats[2 + 2 * l, 1])
+            xn_bf = self._opbuf("bert_opH", M)
+            self._drop_ln(fo, h1, P[Lp + "output.LayerNorm.weight"], P[Lp + "output.LayerNorm.bias"],
+                          xn, xn_bf, stats[2 + 2 * l, 0], stats[2 + 2 * l, 1], p_h, seed, seed_dev,
+                          203 + 4 * l)
             x = xn
+            xop = (xn_bf, None) if bf else None
         utt = buf("bert_utt", B, H)
         k._c("mmda_masked_mean_forward", _ptr(x), _ptr(mask), B, S, H, _ptr(utt))
         self.saved = dict(B=B, S=S, ids=ids, types=types, mask=mask, p_h=p_h, p_a=p_a, seed=seed,
@@ -230,15 +307,18 @@ class BertEngine:
             fo = buf(f"bert_fo_{l}", M, H)
             # ---- output LayerNorm(fo + h1) ----
             dsum = other
-            k.layernorm_bwd(dx, fo, h1, P[Lp + "output.LayerNorm.weight"], stats[2 + 2 * l, 0],
-                            stats[2 + 2 * l, 1], dsum, gw_or(Lp + "output.LayerNorm.weight", scr_g),
-                            gw_or(Lp + "output.LayerNorm.bias", scr_b))
-            dfo = buf("bert_dH", M, H)
-            if p_h > 0:
-                k.dropout(dsum, dfo, p_h, seed, 203 + 4 * l, seed_dev)
-            else:
+            # LN backward + the dropout that sat on the dense output + (bf16 mode) the operand
+            # copy of the result, one kernel; the fp32 copy only where a bias column sum reads it
+            dfo_bf = self._opbuf("bert_opH_d", M)
+            need32 = (not bf and p_h > 0) or (bf and gw(Lp + "output.dense.bias") is not None)
+            dfo = buf("bert_dH", M, H) if need32 else None
+            self._ln_bwd_drop(dx, fo, h1, P[Lp + "output.LayerNorm.weight"], stats[2 + 2 * l, 0],
+                              stats[2 + 2 * l, 1], dsum, gw_or(Lp + "output.LayerNorm.weight", scr_g),
+                              gw_or(Lp + "output.LayerNorm.bias", scr_b), dfo, dfo_bf, p_h, seed,
+                              seed_dev, 203 + 4 * l)
+            if not bf and p_h == 0:
                 dfo = dsum
-            dfo_op = self._op("bert_opH_d", dfo)
+            dfo_op = (dfo_bf, None) if bf else self._op("bert_opH_d", dfo)
             # ---- output.dense: act [M][I] -> fo [M][H] ----
             dact = buf("bert_dI", M, I)
             self._mm(0, 1, M, I, H, dfo_op, self._wop(P, Lp + "output.dense.weight"), dact)
@@ -263,31 +343,44 @@ class BertEngine:
                       Lp + "intermediate.dense.bias", I, H)
             # ---- attention.output LayerNorm(ao + x) ----
             dsum1 = dx
-            k.layernorm_bwd(dsum, ao, x, P[Lp + "attention.output.LayerNorm.weight"],
-                            stats[1 + 2 * l, 0], stats[1 + 2 * l, 1], dsum1,
-                            gw_or(Lp + "attention.output.LayerNorm.weight", scr_g),
-                            gw_or(Lp + "attention.output.LayerNorm.bias", scr_b))
-            dao = buf("bert_dH", M, H)
-            if p_h > 0:
-                k.dropout(dsum1, dao, p_h, seed, 202 + 4 * l, seed_dev)
-            else:
+            dao_bf = self._opbuf("bert_opH_d", M)
+            need32 = (not bf and p_h > 0) or (bf and gw(Lp + "attention.output.dense.bias") is not None)
+            dao = buf("bert_dH", M, H) if need32 else None
+            self._ln_bwd_drop(dsum, ao, x, P[Lp + "attention.output.LayerNorm.weight"],
+                              stats[1 + 2 * l, 0], stats[1 + 2 * l, 1], dsum1,
+                              gw_or(Lp + "attention.output.LayerNorm.weight", scr_g),
+                              gw_or(Lp + "attention.output.LayerNorm.bias", scr_b), dao, dao_bf, p_h,
+                              seed, seed_dev, 202 + 4 * l)
+            if not bf and p_h == 0:
                 dao = dsum1
-            dao_op = self._op("bert_opH_d", dao)
+            dao_op = (dao_bf, None) if bf else self._op("bert_opH_d", dao)
             dctx = buf("bert_dctx", M, H)
             self._mm(0, 1, M, H, H, dao_op, self._wop(P, Lp + "attention.output.dense.weight"), dctx)
             if gw(Lp + "attention.output.dense.weight") is not None:
                 wgrad(dao_op, dao, self._op("bert_opH", ctx), Lp + "attention.output.dense.weight",
                       Lp + "attention.output.dense.bias", H, H)
+            qkv_names = [Lp + f"attention.self.{nm}.{wb}" for nm in ("query", "key", "value")
+                         for wb in ("weight", "bias")]
+            sfx = self._att_sfx(S)
             dQKV = buf("bert_dqkv", M, 3 * H)
-            k._c("mmda_bert_attention_backward" + self._att_sfx(S), _ptr(QKV), _ptr(probs), _ptr(dctx), _ptr(dQKV), B, S,
-                 nh, 64, p_a, seed, _ptr(seed_dev), 201 + 4 * l)
-            if l > lowest or any(Lp + f"attention.self.{nm}.{wb}" in train
-                                 for nm in ("query", "key", "value") for wb in ("weight", "bias")):
-                dq_op = self._op("bert_op3H_d", dQKV)
+            if sfx:      # tensor-pipe core writes the bf16 operand copy of d(qkv) itself; the fp32
+                         # tensor only where a bias column sum reads it
+                dq_bf = eng._prep_buf("bert_op3H_d", M, 3 * H, 1)[0]
+                need32 = any(n.endswith("bias") and n in train for n in qkv_names)
+                k._c("mmda_bert_attention_backward_mma", _ptr(QKV), _ptr(probs), _ptr(dctx),
+                     _ptr(dQKV) if need32 else None, _ptr(dq_bf), B, S, nh, 64, p_a, seed,
+                     _ptr(seed_dev), 201 + 4 * l)
+            else:
+                k._c("mmda_bert_attention_backward", _ptr(QKV), _ptr(probs), _ptr(dctx), _ptr(dQKV), B, S,
+                     nh, 64, p_a, seed, _ptr(seed_dev), 201 + 4 * l)
+            if l > lowest or any(n in train for n in qkv_names):
+                dq_op = (dq_bf, None) if sfx else self._op("bert_op3H_d", dQKV)
                 x_op = None
+                if l > lowest and bf:       # dx += d(qkv) [M x 3H] * [Wq; Wk; Wv]: one K = 3H GEMM
+                    self._mm(0, 1, M, H, 3 * H, dq_op, self._wqkv(P, l)[0], dsum1, acc=True)
                 for j, nm in enumerate(("query", "key", "value")):
                     blk = eng._cols(dq_op, j * H, (j + 1) * H)
-                    if l > lowest:      # the layer below (or the embeddings) needs dx
+                    if l > lowest and not bf:      # the layer below (or the embeddings) needs dx
                         self._mm(0, 1, M, H, H, blk, self._wop(P, Lp + f"attention.self.{nm}.weight"),
                                  dsum1, acc=True)
                     wn, bn = Lp + f"attention.self.{nm}.weight", Lp + f"attention.self.{nm}.bias"

@@ -395,7 +395,8 @@ __device__ __forceinline__ void stage_bf16(__nv_bfloat16* dst, const float* src,
 
 __global__ void __launch_bounds__(128)
 bert_attn_fwd_mma_kernel(const float* __restrict__ qkv, const long long* __restrict__ mask,
-                         float* __restrict__ ctx, float* __restrict__ probs, int S, int nhead,
+                         float* __restrict__ ctx, __nv_bfloat16* __restrict__ ctx_bf16,
+                         float* __restrict__ probs, int S, int nhead,
                          float scale, float p_drop, unsigned long long seed,
                          const unsigned long long* __restrict__ seed_dev, unsigned stream) {
   __shared__ __align__(16) __nv_bfloat16 Qs[ATT_MMA_S * AP], Ks[ATT_MMA_S * AP], Vs[ATT_MMA_S * AP];
@@ -496,10 +497,14 @@ bert_attn_fwd_mma_kernel(const float* __restrict__ qkv, const long long* __restr
 #pragma unroll
   for (int n = 0; n < 8; ++n) {
     const int c = n * 8 + t4 * 2;
-    if (i0 < S)
-      *reinterpret_cast<float2*>(ctx + (size_t)(b * S + i0) * Hd + h * BHD + c) = make_float2(o[n][0], o[n][1]);
-    if (i1 < S)
-      *reinterpret_cast<float2*>(ctx + (size_t)(b * S + i1) * Hd + h * BHD + c) = make_float2(o[n][2], o[n][3]);
+    if (i0 < S) {
+      if (ctx) *reinterpret_cast<float2*>(ctx + (size_t)(b * S + i0) * Hd + h * BHD + c) = make_float2(o[n][0], o[n][1]);
+      if (ctx_bf16) *reinterpret_cast<uint32_t*>(ctx_bf16 + (size_t)(b * S + i0) * Hd + h * BHD + c) = pack_bf16(o[n][0], o[n][1]);
+    }
+    if (i1 < S) {
+      if (ctx) *reinterpret_cast<float2*>(ctx + (size_t)(b * S + i1) * Hd + h * BHD + c) = make_float2(o[n][2], o[n][3]);
+      if (ctx_bf16) *reinterpret_cast<uint32_t*>(ctx_bf16 + (size_t)(b * S + i1) * Hd + h * BHD + c) = pack_bf16(o[n][2], o[n][3]);
+    }
   }
 }
 
@@ -507,7 +512,8 @@ constexpr int ATT_MMA_BWD_SMEM = 6 * ATT_MMA_S * AP * 2;      // Q K V dO Pd dS,
 
 __global__ void __launch_bounds__(128)
 bert_attn_bwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ probs,
-                         const float* __restrict__ dctx, float* __restrict__ dqkv, int S, int nhead,
+                         const float* __restrict__ dctx, float* __restrict__ dqkv,
+                         __nv_bfloat16* __restrict__ dqkv_bf16, int S, int nhead,
                          float scale, float p_drop, unsigned long long seed,
                          const unsigned long long* __restrict__ seed_dev, unsigned stream) {
   extern __shared__ __align__(16) unsigned char att_smem[];
@@ -601,12 +607,16 @@ bert_attn_bwd_mma_kernel(const float* __restrict__ qkv, const float* __restrict_
 #pragma unroll
     for (int n = 0; n < 8; ++n) {
       const int c = n * 8 + t4 * 2;
-      if (i0 < S)
-        *reinterpret_cast<float2*>(dqkv + (size_t)(b * S + i0) * ld + which * Hd + h * BHD + c) =
-            make_float2(v[n][0], v[n][1]);
-      if (i1 < S)
-        *reinterpret_cast<float2*>(dqkv + (size_t)(b * S + i1) * ld + which * Hd + h * BHD + c) =
-            make_float2(v[n][2], v[n][3]);
+      const size_t o0 = (size_t)(b * S + i0) * ld + which * Hd + h * BHD + c;
+      const size_t o1 = (size_t)(b * S + i1) * ld + which * Hd + h * BHD + c;
+      if (i0 < S) {
+        if (dqkv) *reinterpret_cast<float2*>(dqkv + o0) = make_float2(v[n][0], v[n][1]);
+        if (dqkv_bf16) *reinterpret_cast<uint32_t*>(dqkv_bf16 + o0) = pack_bf16(v[n][0], v[n][1]);
+      }
+      if (i1 < S) {
+        if (dqkv) *reinterpret_cast<float2*>(dqkv + o1) = make_float2(v[n][2], v[n][3]);
+        if (dqkv_bf16) *reinterpret_cast<uint32_t*>(dqkv_bf16 + o1) = pack_bf16(v[n][2], v[n][3]);
+      }
     }
   };
   store_rows(acc, 0);
@@ -740,15 +750,17 @@ int mmda_bert_attention_backward(const float* qkv, const float* probs, const flo
 }
 
 // bf16 tensor-core variants (S <= 64): same contract as the fp32 calls above; probs stays fp32.
-int mmda_bert_attention_forward_mma(const float* qkv, const long long* mask, float* ctx, float* probs,
-                                    int B, int S, int nhead, int head_dim, float p_drop,
+int mmda_bert_attention_forward_mma(const float* qkv, const long long* mask, float* ctx, void* ctx_bf16,
+                                    float* probs, int B, int S, int nhead, int head_dim, float p_drop,
                                     unsigned long long seed, const unsigned long long* seed_dev,
                                     unsigned stream_id, cudaStream_t stream) {
   MMDA_REQUIRE(head_dim == BHD, "bert_attention: head_dim %d (bert-base uses 64)", head_dim);
   MMDA_REQUIRE(B > 0 && S > 0 && S <= ATT_MMA_S, "bert_attention_mma: sequence %d > %d", S, ATT_MMA_S);
   MMDA_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(ctx) & 7) == 0,
                "bert_attention_mma: unaligned operands");
-  bert_attn_fwd_mma_kernel<<<B * nhead, 128, 0, stream>>>(qkv, mask, ctx, probs, S, nhead,
+  MMDA_REQUIRE(ctx != nullptr || ctx_bf16 != nullptr, "bert_attention_mma: no output");
+  bert_attn_fwd_mma_kernel<<<B * nhead, 128, 0, stream>>>(qkv, mask, ctx,
+                                                          reinterpret_cast<__nv_bfloat16*>(ctx_bf16), probs, S, nhead,
                                                           1.0f / sqrtf((float)head_dim), p_drop, seed,
                                                           seed_dev, stream_id);
   MMDA_CHECK_LAUNCH();
@@ -756,17 +768,21 @@ int mmda_bert_attention_forward_mma(const float* qkv, const long long* mask, flo
 }
 
 int mmda_bert_attention_backward_mma(const float* qkv, const float* probs, const float* dctx,
-                                     float* dqkv, int B, int S, int nhead, int head_dim, float p_drop,
+                                     float* dqkv, void* dqkv_bf16, int B, int S, int nhead,
+                                     int head_dim, float p_drop,
                                      unsigned long long seed, const unsigned long long* seed_dev,
                                      unsigned stream_id, cudaStream_t stream) {
   MMDA_REQUIRE(head_dim == BHD, "bert_attention: head_dim %d (bert-base uses 64)", head_dim);
   MMDA_REQUIRE(B > 0 && S > 0 && S <= ATT_MMA_S, "bert_attention_mma: sequence %d > %d", S, ATT_MMA_S);
   MMDA_REQUIRE(((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(dctx)) & 15) == 0 &&
-               (reinterpret_cast<uintptr_t>(dqkv) & 7) == 0, "bert_attention_mma: unaligned operands");
+               (reinterpret_cast<uintptr_t>(dqkv) & 7) == 0 && (reinterpret_cast<uintptr_t>(dqkv_bf16) & 3) == 0,
+               "bert_attention_mma: unaligned operands");
+  MMDA_REQUIRE(dqkv != nullptr || dqkv_bf16 != nullptr, "bert_attention_mma: no output");
   MMDA_CUDA(cudaFuncSetAttribute(bert_attn_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  ATT_MMA_BWD_SMEM));
   bert_attn_bwd_mma_kernel<<<B * nhead, 128, ATT_MMA_BWD_SMEM, stream>>>(
-      qkv, probs, dctx, dqkv, S, nhead, 1.0f / sqrtf((float)head_dim), p_drop, seed, seed_dev, stream_id);
+      qkv, probs, dctx, dqkv, reinterpret_cast<__nv_bfloat16*>(dqkv_bf16), S, nhead,
+      1.0f / sqrtf((float)head_dim), p_drop, seed, seed_dev, stream_id);
   MMDA_CHECK_LAUNCH();
   return MMDA_OK;
 }

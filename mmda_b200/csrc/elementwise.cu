@@ -6,6 +6,7 @@
 // ReLU, dropout 0.1 at four places); classifier dropout+sigmoid at :150-153; getBinaryTensor at
 // src/utils/functions.py:112-115.
 #include "common.cuh"
+#include <cuda_bf16.h>
 
 // ---------------------------------------------------------------- LayerNorm ----------------
 // y = LN(x + res) * gamma + beta, one warp per row; saves mean / rstd for the backward.
@@ -34,6 +35,77 @@ __global__ void layernorm_fwd_kernel(const float* __restrict__ x, int ldx,
   for (int c = lane; c < width; c += 32) {
     const float d = xr[c] + (rr ? rr[c] : 0.f) - mean;
     yr[c] = d * rstd * gamma[c] + beta[c];
+  }
+  if (lane == 0 && mean_out) { mean_out[row] = mean; rstd_out[row] = rstd; }
+}
+
+
+// x' = dropout(x) (written back over x when p > 0), y = LN(x' + res) * gamma + beta, optional bf16
+// copy of y for the tensor-core GEMMs that consume it.  One warp per row, the row lives in
+// registers (16-byte accesses, one read of x / res, one write of each output).  Dropout element
+// index = row * width + col: the stream the stand-alone dropout kernel uses on a contiguous tensor.
+template <int NV>
+__global__ void __launch_bounds__(256)
+dropout_layernorm_fwd_kernel(float* __restrict__ x, int ldx, const float* __restrict__ res, int ldr,
+                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                             float* __restrict__ y, int ldy, __nv_bfloat16* __restrict__ y_bf16,
+                             float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows,
+                             int width, float eps, float p, float keep_scale, unsigned long long seed,
+                             const unsigned long long* __restrict__ seed_dev, unsigned stream) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  if (seed_dev) seed += seed_dev[0] * 0x9E3779B97F4A7C15ULL;
+  const int w4 = width >> 2;
+  float4* xr = reinterpret_cast<float4*>(x + (size_t)row * ldx);
+  const float4* rr = res ? reinterpret_cast<const float4*>(res + (size_t)row * ldr) : nullptr;
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + 32 * i;
+    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < w4) {
+      float4 a = xr[c];
+      if (p > 0.f) {
+        const uint32_t e = (uint32_t)((size_t)row * width + 4 * c);
+        a.x = rng_uniform(seed, stream, e) >= p ? a.x * keep_scale : 0.f;
+        a.y = rng_uniform(seed, stream, e + 1) >= p ? a.y * keep_scale : 0.f;
+        a.z = rng_uniform(seed, stream, e + 2) >= p ? a.z * keep_scale : 0.f;
+        a.w = rng_uniform(seed, stream, e + 3) >= p ? a.w * keep_scale : 0.f;
+        xr[c] = a;
+      }
+      if (rr) { const float4 r4 = rr[c]; a.x += r4.x; a.y += r4.y; a.z += r4.z; a.w += r4.w; }
+      v[i] = a;
+      s += (a.x + a.y) + (a.z + a.w);
+    }
+  }
+  const float mean = warp_sum(s) / width;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+    if (lane + 32 * i < w4) {
+      const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+      q = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, fmaf(dw, dw, q))));
+    }
+  const float rstd = rsqrtf(warp_sum(q) / width + eps);
+  float4* yr = reinterpret_cast<float4*>(y + (size_t)row * ldy);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < w4) {
+      const float4 g = reinterpret_cast<const float4*>(gamma)[c], b = reinterpret_cast<const float4*>(beta)[c];
+      const float4 o = make_float4((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y,
+                                   (v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
+      yr[c] = o;
+      if (y_bf16) {
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+        uint2 u;
+        u.x = *reinterpret_cast<const uint32_t*>(&lo);
+        u.y = *reinterpret_cast<const uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(y_bf16 + (size_t)row * width + 4 * c) = u;
+      }
+    }
   }
   if (lane == 0 && mean_out) { mean_out[row] = mean; rstd_out[row] = rstd; }
 }
@@ -121,8 +193,14 @@ layernorm_bwd_v4_kernel(const float* __restrict__ dy, int lddy, const float* __r
                         const float* __restrict__ res, int ldr, const float* __restrict__ gamma,
                         const float* __restrict__ mean, const float* __restrict__ rstd,
                         float* __restrict__ dx, int lddx, float* __restrict__ dgamma,
-                        float* __restrict__ dbeta, int rows, int width, int rows_per_block) {
+                        float* __restrict__ dbeta, int rows, int width, int rows_per_block,
+                        float* __restrict__ ddrop = nullptr, __nv_bfloat16* __restrict__ ddrop_bf16 = nullptr,
+                        float p = 0.f, float keep_scale = 1.f, unsigned long long seed = 0,
+                        const unsigned long long* __restrict__ seed_dev = nullptr, unsigned stream = 0) {
+  // ddrop / ddrop_bf16 (optional, contiguous [rows][width]): dropout(dx) on the stream of the
+  // forward's dropout of the tensor this gradient belongs to (element index row * width + col)
   __shared__ float4 red[8][32];
+  if (seed_dev) seed += seed_dev[0] * 0x9E3779B97F4A7C15ULL;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r_beg = blockIdx.x * rows_per_block;
   const int r_end = min(rows, r_beg + rows_per_block);
@@ -164,9 +242,28 @@ layernorm_bwd_v4_kernel(const float* __restrict__ dy, int lddy, const float* __r
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = lane + 32 * i;
-      if (c < w4)
-        dxr[c] = make_float4(rs * (dg[i].x - s1 - xh[i].x * s2), rs * (dg[i].y - s1 - xh[i].y * s2),
-                             rs * (dg[i].z - s1 - xh[i].z * s2), rs * (dg[i].w - s1 - xh[i].w * s2));
+      if (c < w4) {
+        float4 o = make_float4(rs * (dg[i].x - s1 - xh[i].x * s2), rs * (dg[i].y - s1 - xh[i].y * s2),
+                               rs * (dg[i].z - s1 - xh[i].z * s2), rs * (dg[i].w - s1 - xh[i].w * s2));
+        dxr[c] = o;
+        if (ddrop || ddrop_bf16) {
+          if (p > 0.f) {
+            const uint32_t e = (uint32_t)((size_t)row * width + 4 * c);
+            o.x = rng_uniform(seed, stream, e) >= p ? o.x * keep_scale : 0.f;
+            o.y = rng_uniform(seed, stream, e + 1) >= p ? o.y * keep_scale : 0.f;
+            o.z = rng_uniform(seed, stream, e + 2) >= p ? o.z * keep_scale : 0.f;
+            o.w = rng_uniform(seed, stream, e + 3) >= p ? o.w * keep_scale : 0.f;
+          }
+          if (ddrop) reinterpret_cast<float4*>(ddrop + (size_t)row * width)[c] = o;
+          if (ddrop_bf16) {
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+            uint2 u;
+            u.x = *reinterpret_cast<const uint32_t*>(&lo);
+            u.y = *reinterpret_cast<const uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(ddrop_bf16 + (size_t)row * width + 4 * c) = u;
+          }
+        }
+      }
     }
   }
   // cross-warp reduction of the per-column partials, one atomic per column per block
@@ -188,6 +285,111 @@ layernorm_bwd_v4_kernel(const float* __restrict__ dy, int lddy, const float* __r
       }
     }
   }
+}
+
+
+// Wide rows (width > 256): the warp-per-row kernel above needs ~190 registers there (8 warps per
+// SM: latency-bound at a third of the HBM roofline, measured).  Here a whole CTA works on one row
+// at a time -- one float4 per thread, the next row's loads in flight while this row's two sums go
+// through a warp shuffle + one shared-memory exchange -- at ~60 registers, so several CTAs share an
+// SM and the loads of a dozen rows overlap.  Same arithmetic, same optional dropped outputs.
+__global__ void __launch_bounds__(256)
+layernorm_bwd_row_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ x, int ldx,
+                         const float* __restrict__ res, int ldr, const float* __restrict__ gamma,
+                         const float* __restrict__ mean, const float* __restrict__ rstd,
+                         float* __restrict__ dx, int lddx, float* __restrict__ dgamma,
+                         float* __restrict__ dbeta, int rows, int width, int rows_per_block,
+                         float* __restrict__ ddrop, __nv_bfloat16* __restrict__ ddrop_bf16, float p,
+                         float keep_scale, unsigned long long seed,
+                         const unsigned long long* __restrict__ seed_dev, unsigned stream) {
+  __shared__ float red[2][8][2];
+  if (seed_dev) seed += seed_dev[0] * 0x9E3779B97F4A7C15ULL;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarp = blockDim.x >> 5;
+  const int w4 = width >> 2;
+  const bool act = tid < w4;
+  const int r_beg = blockIdx.x * rows_per_block;
+  const int r_end = min(rows, r_beg + rows_per_block);
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 g = act ? reinterpret_cast<const float4*>(gamma)[tid] : zero4;
+  float4 ag = zero4, ab = zero4;
+  const float inv_w = 1.f / width;
+  float4 nx = zero4, nr = zero4, nd = zero4;
+  float nmu = 0.f, nrs = 0.f;
+  auto fetch = [&](int row) {
+    if (act) {
+      nx = reinterpret_cast<const float4*>(x + (size_t)row * ldx)[tid];
+      nd = reinterpret_cast<const float4*>(dy + (size_t)row * lddy)[tid];
+      if (res) nr = reinterpret_cast<const float4*>(res + (size_t)row * ldr)[tid];
+    }
+    nmu = mean[row];
+    nrs = rstd[row];
+  };
+  if (r_beg < r_end) fetch(r_beg);
+  int par = 0;
+  for (int row = r_beg; row < r_end; ++row, par ^= 1) {
+    const float4 xv = nx, rv = nr, d = nd;
+    const float mu = nmu, rs = nrs;
+    if (row + 1 < r_end) fetch(row + 1);
+    const float4 xh = make_float4((xv.x + rv.x - mu) * rs, (xv.y + rv.y - mu) * rs,
+                                  (xv.z + rv.z - mu) * rs, (xv.w + rv.w - mu) * rs);
+    const float4 dg = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
+    float s1 = (dg.x + dg.y) + (dg.z + dg.w);
+    float s2 = fmaf(dg.x, xh.x, fmaf(dg.y, xh.y, fmaf(dg.z, xh.z, dg.w * xh.w)));
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) { red[par][warp][0] = s1; red[par][warp][1] = s2; }
+    __syncthreads();
+    s1 = 0.f; s2 = 0.f;
+    for (int w = 0; w < nwarp; ++w) { s1 += red[par][w][0]; s2 += red[par][w][1]; }
+    s1 *= inv_w;
+    s2 *= inv_w;
+    if (act) {
+      float4 o = make_float4(rs * (dg.x - s1 - xh.x * s2), rs * (dg.y - s1 - xh.y * s2),
+                             rs * (dg.z - s1 - xh.z * s2), rs * (dg.w - s1 - xh.w * s2));
+      reinterpret_cast<float4*>(dx + (size_t)row * lddx)[tid] = o;
+      ag.x = fmaf(d.x, xh.x, ag.x); ag.y = fmaf(d.y, xh.y, ag.y);
+      ag.z = fmaf(d.z, xh.z, ag.z); ag.w = fmaf(d.w, xh.w, ag.w);
+      ab.x += d.x; ab.y += d.y; ab.z += d.z; ab.w += d.w;
+      if (ddrop || ddrop_bf16) {
+        if (p > 0.f) {
+          const uint32_t e = (uint32_t)((size_t)row * width + 4 * tid);
+          o.x = rng_uniform(seed, stream, e) >= p ? o.x * keep_scale : 0.f;
+          o.y = rng_uniform(seed, stream, e + 1) >= p ? o.y * keep_scale : 0.f;
+          o.z = rng_uniform(seed, stream, e + 2) >= p ? o.z * keep_scale : 0.f;
+          o.w = rng_uniform(seed, stream, e + 3) >= p ? o.w * keep_scale : 0.f;
+        }
+        if (ddrop) reinterpret_cast<float4*>(ddrop + (size_t)row * width)[tid] = o;
+        if (ddrop_bf16) {
+          const __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+          uint2 u;
+          u.x = *reinterpret_cast<const uint32_t*>(&lo);
+          u.y = *reinterpret_cast<const uint32_t*>(&hi);
+          *reinterpret_cast<uint2*>(ddrop_bf16 + (size_t)row * width + 4 * tid) = u;
+        }
+      }
+    }
+  }
+  if (act) {     // one atomic per column per CTA
+    atomicAdd(dgamma + 4 * tid + 0, ag.x); atomicAdd(dgamma + 4 * tid + 1, ag.y);
+    atomicAdd(dgamma + 4 * tid + 2, ag.z); atomicAdd(dgamma + 4 * tid + 3, ag.w);
+    atomicAdd(dbeta + 4 * tid + 0, ab.x); atomicAdd(dbeta + 4 * tid + 1, ab.y);
+    atomicAdd(dbeta + 4 * tid + 2, ab.z); atomicAdd(dbeta + 4 * tid + 3, ab.w);
+  }
+}
+
+static void launch_ln_bwd_row(const float* dy, int lddy, const float* x, int ldx, const float* res, int ldr,
+                              const float* gamma, const float* mean, const float* rstd, float* dx, int lddx,
+                              float* dgamma, float* dbeta, int rows, int width, float* ddrop,
+                              __nv_bfloat16* ddrop_bf16, float p, unsigned long long seed,
+                              const unsigned long long* seed_dev, unsigned stream_id, cudaStream_t stream) {
+  const int threads = ((width / 4) + 31) / 32 * 32;
+  int rpb = (rows + 148 * 6 - 1) / (148 * 6);        // ~6 CTAs per SM, each a contiguous run of rows
+  if (rpb < 4) rpb = 4;
+  const int grid = (rows + rpb - 1) / rpb;
+  layernorm_bwd_row_kernel<<<grid, threads, 0, stream>>>(dy, lddy, x, ldx, res, ldr, gamma, mean, rstd, dx,
+                                                         lddx, dgamma, dbeta, rows, width, rpb, ddrop,
+                                                         ddrop_bf16, p, 1.f / (1.f - p), seed, seed_dev,
+                                                         stream_id);
 }
 
 // ---------------------------------------------------------------- elementwise ---------------
@@ -407,6 +609,67 @@ int mmda_layernorm_forward(const float* x, int ldx, const float* res, int ldr, c
   return MMDA_OK;
 }
 
+int mmda_dropout_layernorm_forward(float* x, int ldx, const float* res, int ldr, const float* gamma,
+                                   const float* beta, float* y, int ldy, void* y_bf16, float* mean,
+                                   float* rstd, int rows, int width, float eps, float p,
+                                   unsigned long long seed, const unsigned long long* seed_dev,
+                                   unsigned stream_id, cudaStream_t stream) {
+  if (rows <= 0) return MMDA_OK;
+  MMDA_REQUIRE(width > 0 && width <= 1024 && width % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 &&
+               (!res || ldr % 4 == 0), "dropout_layernorm: width=%d / pitches must be multiples of 4 (<= 1024)", width);
+  MMDA_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(res) |
+                 reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(gamma) |
+                 reinterpret_cast<uintptr_t>(beta)) & 15) == 0 && (reinterpret_cast<uintptr_t>(y_bf16) & 7) == 0,
+               "dropout_layernorm: operands must be 16-byte aligned");
+  MMDA_REQUIRE(p >= 0.f && p < 1.f && (p == 0.f || ldx == width), "dropout_layernorm: p=%f needs a contiguous x", p);
+  const int grid = (rows + 7) / 8;
+  const float ks = 1.f / (1.f - p);
+  __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(y_bf16);
+  if (width <= 256)
+    dropout_layernorm_fwd_kernel<2><<<grid, 256, 0, stream>>>(x, ldx, res, ldr, gamma, beta, y, ldy, yb, mean,
+                                                              rstd, rows, width, eps, p, ks, seed, seed_dev, stream_id);
+  else if (width <= 640)
+    dropout_layernorm_fwd_kernel<5><<<grid, 256, 0, stream>>>(x, ldx, res, ldr, gamma, beta, y, ldy, yb, mean,
+                                                              rstd, rows, width, eps, p, ks, seed, seed_dev, stream_id);
+  else
+    dropout_layernorm_fwd_kernel<8><<<grid, 256, 0, stream>>>(x, ldx, res, ldr, gamma, beta, y, ldy, yb, mean,
+                                                              rstd, rows, width, eps, p, ks, seed, seed_dev, stream_id);
+  MMDA_CHECK_LAUNCH();
+  return MMDA_OK;
+}
+
+int mmda_layernorm_backward_dropout(const float* dy, int lddy, const float* x, int ldx, const float* res,
+                                    int ldr, const float* gamma, const float* mean, const float* rstd,
+                                    float* dx, int lddx, float* dgamma, float* dbeta, int rows, int width,
+                                    float* ddrop, void* ddrop_bf16, float p, unsigned long long seed,
+                                    const unsigned long long* seed_dev, unsigned stream_id,
+                                    cudaStream_t stream) {
+  if (rows <= 0) return MMDA_OK;
+  MMDA_REQUIRE(width > 0 && width <= 1024 && width % 4 == 0 && lddy % 4 == 0 && ldx % 4 == 0 &&
+               lddx % 4 == 0 && (!res || ldr % 4 == 0),
+               "layernorm_backward_dropout: width=%d / pitches must be multiples of 4 (<= 1024)", width);
+  MMDA_REQUIRE(((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) |
+                 reinterpret_cast<uintptr_t>(res) | reinterpret_cast<uintptr_t>(dx) |
+                 reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(ddrop)) & 15) == 0 &&
+               (reinterpret_cast<uintptr_t>(ddrop_bf16) & 7) == 0,
+               "layernorm_backward_dropout: operands must be 16-byte aligned");
+  MMDA_REQUIRE(p >= 0.f && p < 1.f, "layernorm_backward_dropout: p=%f", p);
+  int rpb = (rows + 295) / 296;
+  rpb = (rpb + 7) / 8 * 8;
+  const int grid = (rows + rpb - 1) / rpb;
+  const float ks = 1.f / (1.f - p);
+  __nv_bfloat16* db = reinterpret_cast<__nv_bfloat16*>(ddrop_bf16);
+  if (width <= 256)
+    layernorm_bwd_v4_kernel<2><<<grid, 256, 0, stream>>>(dy, lddy, x, ldx, res, ldr, gamma, mean, rstd, dx, lddx,
+                                                         dgamma, dbeta, rows, width, rpb, ddrop, db, p, ks, seed,
+                                                         seed_dev, stream_id);
+  else
+    launch_ln_bwd_row(dy, lddy, x, ldx, res, ldr, gamma, mean, rstd, dx, lddx, dgamma, dbeta, rows, width,
+                      ddrop, db, p, seed, seed_dev, stream_id, stream);
+  MMDA_CHECK_LAUNCH();
+  return MMDA_OK;
+}
+
 int mmda_layernorm_backward(const float* dy, int lddy, const float* x, int ldx, const float* res,
                             int ldr, const float* gamma, const float* mean, const float* rstd,
                             float* dx, int lddx, float* dgamma, float* dbeta, int rows, int width,
@@ -424,12 +687,9 @@ int mmda_layernorm_backward(const float* dy, int lddy, const float* x, int ldx, 
   if (v4 && width <= 256)
     layernorm_bwd_v4_kernel<2><<<grid, 256, 0, stream>>>(dy, lddy, x, ldx, res, ldr, gamma, mean, rstd,
                                                          dx, lddx, dgamma, dbeta, rows, width, rpb);
-  else if (v4 && width <= 640)
-    layernorm_bwd_v4_kernel<5><<<grid, 256, 0, stream>>>(dy, lddy, x, ldx, res, ldr, gamma, mean, rstd,
-                                                         dx, lddx, dgamma, dbeta, rows, width, rpb);
   else if (v4)
-    layernorm_bwd_v4_kernel<8><<<grid, 256, 0, stream>>>(dy, lddy, x, ldx, res, ldr, gamma, mean, rstd,
-                                                         dx, lddx, dgamma, dbeta, rows, width, rpb);
+    launch_ln_bwd_row(dy, lddy, x, ldx, res, ldr, gamma, mean, rstd, dx, lddx, dgamma, dbeta, rows, width,
+                      nullptr, nullptr, 0.f, 0, nullptr, 0, stream);
   else if (width <= 32 * LN_MAXC)
     layernorm_bwd_kernel<LN_MAXC><<<grid, 256, 0, stream>>>(dy, lddy, x, ldx, res, ldr, gamma, mean,
                                                             rstd, dx, lddx, dgamma, dbeta, rows,

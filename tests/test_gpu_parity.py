@@ -782,6 +782,51 @@ def test_gru_cells(dev, sizes, B, T):
     _model_checks(f"gru_{sizes[0]}_{B}", cfg, state, batch, dev, None)
 
 
+def test_fused_dropout_layernorm_kernels(dev):
+    """BERT residual blocks: the fused dropout+LayerNorm forward and LayerNorm-backward+dropout
+    kernels against the stand-alone dropout / LayerNorm kernels on the same dropout stream
+    (identical masks), including the bf16 operand copies they emit."""
+    from mmda_b200.engine import Kernels, _ptr
+    k = Kernels(); k.bind_stream()
+    g = torch.Generator().manual_seed(8)
+    C = Checks("fused_ln")
+    for rows, width, p in [(300, 768, 0.1), (65, 1024, 0.3), (41, 128, 0.1), (500, 600, 0.0)]:
+        x = torch.randn(rows, width, generator=g).to(dev); res = torch.randn(rows, width, generator=g).to(dev)
+        gam = (torch.rand(width, generator=g) + 0.5).to(dev); bet = torch.randn(width, generator=g).to(dev)
+        dy = torch.randn(rows, width, generator=g).to(dev)
+        # reference: separate kernels
+        xd = x.clone()
+        if p > 0:
+            k.dropout(xd, xd, p, 77, 9, None)
+        y0 = torch.empty_like(x); mu0 = torch.empty(rows, device=dev); rs0 = torch.empty(rows, device=dev)
+        k.layernorm(xd, res, gam, bet, y0, mu0, rs0)
+        dx0 = torch.empty_like(x); dg0 = torch.zeros(width, device=dev); db0 = torch.zeros(width, device=dev)
+        k.layernorm_bwd(dy, xd, res, gam, mu0, rs0, dx0, dg0, db0)
+        dd0 = dx0.clone()
+        if p > 0:
+            k.dropout(dx0, dd0, p, 77, 9, None)
+        # fused
+        x1 = x.clone(); y1 = torch.empty_like(x); yb = torch.empty(rows, width, device=dev, dtype=torch.bfloat16)
+        mu1 = torch.empty(rows, device=dev); rs1 = torch.empty(rows, device=dev)
+        k._c("mmda_dropout_layernorm_forward", _ptr(x1), width, _ptr(res), width, _ptr(gam), _ptr(bet),
+             _ptr(y1), width, _ptr(yb), _ptr(mu1), _ptr(rs1), rows, width, 1e-5, p, 77, None, 9)
+        assert torch.equal(x1, xd), "dropout mask / scaling differs from the stand-alone kernel"
+        C.add(f"fused ln fwd {rows}x{width}", y1, y0, 2e-6)
+        assert torch.equal(yb, y1.to(torch.bfloat16))
+        dx1 = torch.empty_like(x); dg1 = torch.zeros(width, device=dev); db1 = torch.zeros(width, device=dev)
+        dd1 = torch.empty_like(x); ddb = torch.empty(rows, width, device=dev, dtype=torch.bfloat16)
+        k._c("mmda_layernorm_backward_dropout", _ptr(dy), width, _ptr(x1), width, _ptr(res), width, _ptr(gam),
+             _ptr(mu1), _ptr(rs1), _ptr(dx1), width, _ptr(dg1), _ptr(db1), rows, width, _ptr(dd1), _ptr(ddb),
+             p, 77, None, 9)
+        C.add(f"fused ln dx {rows}x{width}", dx1, dx0, 5e-6)
+        C.add(f"fused ln dropped dx {rows}x{width}", dd1, dd0, 5e-6)
+        assert torch.equal((dd1 == 0), (dd0 == 0)) or p == 0
+        assert torch.equal(ddb, dd1.to(torch.bfloat16))
+        C.add(f"fused ln dgamma {rows}x{width}", dg1, dg0, 5e-6)
+        C.add(f"fused ln dbeta {rows}x{width}", db1, db0, 5e-6)
+    C.finish()
+
+
 def test_bert_attention_tensor_core_kernels(dev):
     """bf16-mode attention core (mma.sync) vs fp64 math built from the bf16-rounded operands'
     fp32 originals: forward context / probabilities and the three input gradients within the
@@ -800,8 +845,10 @@ def test_bert_attention_tensor_core_kernels(dev):
         mask = mask.to(dev)
         do = torch.randn(B * S, Hd, generator=g).to(dev)
         ctx = torch.empty(B * S, Hd, device=dev); pr = torch.empty(B, nh, S, S, device=dev)
-        k._c("mmda_bert_attention_forward_mma", _ptr(qkv), _ptr(mask), _ptr(ctx), _ptr(pr), B, S, nh, 64,
-             0.0, 1, None, 7)
+        ctx_bf = torch.empty(B * S, Hd, device=dev, dtype=torch.bfloat16)
+        k._c("mmda_bert_attention_forward_mma", _ptr(qkv), _ptr(mask), _ptr(ctx), _ptr(ctx_bf), _ptr(pr),
+             B, S, nh, 64, 0.0, 1, None, 7)
+        assert torch.equal(ctx_bf, ctx.to(torch.bfloat16))
         q3 = qkv.double().view(B, S, 3, nh, 64).requires_grad_(True)
         q, kk, v = q3[:, :, 0], q3[:, :, 1], q3[:, :, 2]
         s = torch.einsum("bihd,bjhd->bhij", q, kk) / 8.0
@@ -812,8 +859,10 @@ def test_bert_attention_tensor_core_kernels(dev):
         C.add(f"ctx B={B} S={S} nh={nh}", ctx, o, 2e-2)
         C.add(f"probs B={B} S={S} nh={nh}", pr, p, 2e-2)
         dqkv = torch.full_like(qkv, float("nan"))
-        k._c("mmda_bert_attention_backward_mma", _ptr(qkv), _ptr(pr), _ptr(do), _ptr(dqkv), B, S, nh, 64,
-             0.0, 1, None, 7)
+        dq_bf = torch.empty(B * S, 3 * Hd, device=dev, dtype=torch.bfloat16)
+        k._c("mmda_bert_attention_backward_mma", _ptr(qkv), _ptr(pr), _ptr(do), _ptr(dqkv), _ptr(dq_bf),
+             B, S, nh, 64, 0.0, 1, None, 7)
+        assert torch.equal(dq_bf, dqkv.to(torch.bfloat16))
         gq = q3.grad.reshape(B * S, 3, Hd)
         for j, nm in enumerate(("dQ", "dK", "dV")):
             C.add(f"{nm} B={B} S={S} nh={nh}", dqkv.view(B * S, 3, Hd)[:, j], gq[:, j], 2e-2)
@@ -821,10 +870,10 @@ def test_bert_attention_tensor_core_kernels(dev):
         ctx1 = torch.empty_like(ctx); pr1 = torch.empty_like(pr); d1 = torch.empty_like(qkv)
         ctx2 = torch.empty_like(ctx); pr2 = torch.empty_like(pr); d2 = torch.empty_like(qkv)
         for sfx, (c_, p_, d_) in (("", (ctx1, pr1, d1)), ("_mma", (ctx2, pr2, d2))):
-            k._c("mmda_bert_attention_forward" + sfx, _ptr(qkv), _ptr(mask), _ptr(c_), _ptr(p_), B, S, nh,
-                 64, 0.1, 99, None, 5)
-            k._c("mmda_bert_attention_backward" + sfx, _ptr(qkv), _ptr(p_), _ptr(do), _ptr(d_), B, S, nh,
-                 64, 0.1, 99, None, 5)
+            k._c("mmda_bert_attention_forward" + sfx, _ptr(qkv), _ptr(mask), _ptr(c_),
+                 *((None,) if sfx else ()), _ptr(p_), B, S, nh, 64, 0.1, 99, None, 5)
+            k._c("mmda_bert_attention_backward" + sfx, _ptr(qkv), _ptr(p_), _ptr(do), _ptr(d_),
+                 *((None,) if sfx else ()), B, S, nh, 64, 0.1, 99, None, 5)
         C.add(f"dropout ctx B={B} S={S}", ctx2, ctx1, 2e-2)
         C.add(f"dropout dqkv B={B} S={S}", d2, d1, 2e-2)
     C.finish()
