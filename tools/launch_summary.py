@@ -22,7 +22,8 @@ def load(path):
 def main(path, top=28):
     seq = load(path)
     idx = [i for i, (n, *_r) in enumerate(seq) if "embedding_fwd" in n]
-    a, b = idx[0], idx[1] if len(idx) > 1 else len(seq)
+    # the LAST complete step of the list (the first one also holds the workspace allocation fills)
+    a, b = (idx[-2], idx[-1]) if len(idx) > 1 else (idx[0], len(seq))
     step = seq[a:b]
     tot = sum(t for _, t, _, _ in step)
     print(f"launches in step: {len(step)}   sum of kernel times: {tot:.1f} us")
