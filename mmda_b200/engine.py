@@ -47,6 +47,8 @@ class Kernels:
     def __init__(self):
         self.stream = None
         self.launches = 0
+        self.leaf_on = False            # set by the engine's backward (multi-stream mode)
+        self._leaf_streams, self._leaf_used = {}, {}
 
     def bind_stream(self):
         self.stream = 0 if _DRYRUN else torch.cuda.current_stream().cuda_stream
@@ -82,12 +84,44 @@ class Kernels:
     def linear(self, x, w, b, out, act=ACT_NONE, bias2=None):
         self.gemm(x, w, out, tb=True, bias=b, bias2=bias2, act=act)
 
+    def leaf(self, fn):
+        """Run fn() -- kernels whose results nothing later in the step's dependency chain reads
+        (weight / bias gradients) -- on a side stream paired with the current one, ordered after
+        everything enqueued so far.  `join_leaves()` orders the current stream after all of them.
+        The caller guarantees the operands fn reads are not overwritten before the join."""
+        if not self.leaf_on or _DRYRUN:
+            fn()
+            return
+        cur = torch.cuda.current_stream()
+        st = self._leaf_streams.get(cur.cuda_stream)
+        if st is None:
+            st = self._leaf_streams[cur.cuda_stream] = torch.cuda.Stream(device=cur.device, priority=_PRIO[2])
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        st.wait_event(ev)
+        with torch.cuda.stream(st):
+            self.bind_stream()
+            fn()
+        self.bind_stream()
+        self._leaf_used[st.cuda_stream] = st
+
+    def join_leaves(self):
+        cur = torch.cuda.current_stream() if self._leaf_used else None
+        for st in self._leaf_used.values():
+            ev = torch.cuda.Event()
+            ev.record(st)
+            cur.wait_event(ev)
+        self._leaf_used = {}
+
     def linear_bwd(self, dy, x, w, dw, db, dx=None, dx_beta=0.0, db2=None, dw_split=0):
         """dy: grad of the linear output (pre-activation).  dw/db accumulate (dw_split >= 2
-        forces the atomic split-K path: needed when several streams accumulate into one dw)."""
-        self.gemm(dy, x, dw, ta=True, beta=1.0, split_k=dw_split)
-        if db is not None:
-            self.colsum(dy, db, db2)
+        forces the atomic split-K path: needed when several streams accumulate into one dw).
+        Only dx continues the backward chain: dw / db go to the leaf stream."""
+        def wgrad():
+            self.gemm(dy, x, dw, ta=True, beta=1.0, split_k=dw_split)
+            if db is not None:
+                self.colsum(dy, db, db2)
+        self.leaf(wgrad)
         if dx is not None:
             self.gemm(dy, w, dx, beta=dx_beta, split_k=1 if dx_beta not in (0.0, 1.0) else 0)
 
@@ -468,8 +502,12 @@ class MisaEngine:
         M, N = dy.shape
         K = x.shape[1]
         dyo = self._prep(tag + "_dy", dy, kind=0)
-        self.k.gemm_tc(0, 1, 1, N, K, M, dyo, self._prep(tag + "_x", x, kind=0), dw, mode=1, split_k=0)
-        self.k.colsum(dy, db)
+        xo = self._prep(tag + "_x", x, kind=0)
+
+        def wgrad():
+            self.k.gemm_tc(0, 1, 1, N, K, M, dyo, xo, dw, mode=1, split_k=0)
+            self.k.colsum(dy, db)
+        self.k.leaf(wgrad)
         self.k.gemm_tc(0, 0, 1, M, K, N, dyo, self._prep(tag + "_w", w, kind=0, split=True), dx,
                        mode=1 if dx_acc else 0, split_k=0 if dx_acc else 1)
 
@@ -777,6 +815,11 @@ class MisaEngine:
         TCP, SC = self.buf("TCP", B, 6), self.buf("SCORES", B, NC)
         seed, p_att, p_cls, seed_dev = self.cur_seed, self.p_att, self.p_cls, self.seed_dev
         notify = on_ready or (lambda tag: None)
+        # weight / bias gradients of the dense layers are leaves of the step's dependency graph:
+        # they run on side streams (Kernels.leaf) so that only the dx products sit on the chain
+        # to the BPTT launches; joined before a data-parallel all-reduce needs them, else at the end
+        k.leaf_on = self.multi_stream and not _DRYRUN
+        k._leaf_used = {}
 
         # ---- classifier / confidence ----
         dHf = self.buf("dHf", B, 6 * d)
@@ -822,6 +865,8 @@ class MisaEngine:
                 k.dropout(dF1, dF1, p_att, seed, 3, seed_dev)
             k.act_bwd(dF1, F1, ACT_RELU)
             # dX1 = dS2 + dF1 W1   (accumulate in place into dS2)
+            if dF2 is dS2:
+                k.join_leaves()      # no dropout: dS2 is still being read as linear2's d(output)
             if ffn_tc:
                 self.tc_linear_bwd("ffn1", dF1, X1, P[TL + "linear1.weight"], G[TL + "linear1.weight"],
                                    G[TL + "linear1.bias"], dS2, True)
@@ -853,6 +898,8 @@ class MisaEngine:
             k.add(dXr, d_tokens.view(rows, d))
         else:
             dX0.zero_()
+        if on_ready is not None:
+            k.join_leaves()
         notify("fusion")
 
         # ---- adversarial discriminator + gradient reversal (functions.py:9-21) ----
@@ -874,6 +921,7 @@ class MisaEngine:
                              G["discriminator.discriminator_layer_1.bias"], dS, 0.0)
                 sl = dX0f[:, (3 + i) * d:(4 + i) * d]
                 k.add(sl, sl, dS, 1.0, -lam)
+                k.join_leaves()      # dDH / dS are reused by the next modality
 
         # ---- sp discriminator (only if somebody asked for its gradient) ----
         if d_sp is not None:
@@ -930,6 +978,8 @@ class MisaEngine:
             return run
 
         self._fork({m: head_bwd(i, m) for i, m in enumerate(MODS)})
+        if on_ready is not None:
+            k.join_leaves()
         notify("heads")
 
         # ---- encoders: BPTT + hoisted weight-gradient GEMMs ----
@@ -949,6 +999,8 @@ class MisaEngine:
         self._order_events = {}
         self._fork({m: enc_bwd(m) for m in MODS}, text_first=self.lstm_tc and not self.gru)
         self._order_events = {}
+        k.join_leaves()
+        k.leaf_on = False
         return dutt["t"] if self.use_bert else None
 
     def _encode_backward(self, m, dutt, G, pk, P, notify=None):
