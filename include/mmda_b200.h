@@ -146,10 +146,12 @@ int mmda_lstm_shift_h(const float* y, float* hprev, const int* row_t, const int*
 
 /* ---- tensor-core recurrence for large hidden sizes (text encoder, H = 300): same contract and
  * buffers as mmda_lstm_forward / mmda_lstm_backward (nn.LSTM, src/models.py:48-55,167,176), the
- * per-step h * W_hh^T product runs on tcgen05 with every operand split into three bf16 terms
- * (fp32-accurate, 6 MMAs per K step), W_hh resident in TMEM + shared memory, h_t exchanged between
- * the CTAs of a batch tile through an L2-resident workspace `ws`.  ws[0] (int) is set to 1 if a
- * peer CTA never showed up (the launch then ends with garbage instead of hanging). */
+ * per-step h * W_hh^T product runs on tcgen05 with every operand split into two fp16 terms
+ * (fp32-accurate, 3 MMAs per K step), W_hh resident in TMEM, h_t exchanged between the CTAs of a
+ * batch tile through an L2-resident workspace `ws`.  The caller zero-fills `ws` once, before its
+ * first use; every launch leaves the exchange flags clean for the next one.  ws[0] (int) is set to
+ * 1 if a peer CTA never showed up (the launch then ends with garbage instead of hanging; zero-fill
+ * the workspace again before re-using it). */
 long long mmda_lstm_tc_workspace_bytes(int B, int H, int Tmax);   /* -1: hidden size not covered */
 /* out8 = {slices, groups, batch tile, n tiles, padded K, smem fwd, smem bwd, CTAs} */
 int mmda_lstm_tc_plan(int B, int H, int Tmax, int* out8);

@@ -437,6 +437,19 @@ __global__ void __launch_bounds__(TCL_FWD_THREADS4, 1) lstm_tc_fwd_kernel(const 
   fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc512(tm);
+  // Leave the exchange flags clean for the next launch on this workspace: the last CTA to get
+  // here (nobody reads a flag any more) zeroes them, so no memset node sits between the kernels
+  // that precede a launch and the launch itself (the engine orders other kernels against that
+  // point with events).
+  if (tid == 0) {
+    __threadfence();
+    unsigned* done = reinterpret_cast<unsigned*>(p.err) + 2;
+    if (atomicAdd(done, 1u) == gridDim.x - 1) {
+      for (int i = 0; i < 2 * p.NT * MAXSUB; ++i) p.flags[i] = 0u;
+      *done = 0u;
+      __threadfence();
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -846,6 +859,19 @@ __global__ void __launch_bounds__(TCL_BWD_THREADS4, 1) lstm_tc_bwd_kernel(const 
   fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc512(tm);
+  // Leave the exchange flags clean for the next launch on this workspace: the last CTA to get
+  // here (nobody reads a flag any more) zeroes them, so no memset node sits between the kernels
+  // that precede a launch and the launch itself (the engine orders other kernels against that
+  // point with events).
+  if (tid == 0) {
+    __threadfence();
+    unsigned* done = reinterpret_cast<unsigned*>(p.err) + 2;
+    if (atomicAdd(done, 1u) == gridDim.x - 1) {
+      for (int i = 0; i < 2 * p.NT * MAXSUB; ++i) p.flags[i] = 0u;
+      *done = 0u;
+      __threadfence();
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -981,7 +1007,7 @@ static int tcl_launch(bool bwd, TclArgs& a, int B, int H, int Tmax, void* ws, cu
   else { a.S = pl.S; a.G = pl.G; a.BT = pl.BT; a.NT = pl.NT; a.U = TCL_UNITS; }
   a.Tmax = Tmax;
   a.dbg = g_tcl_dbg;
-  MMDA_CUDA(cudaMemsetAsync(a.flags, 0, (size_t)2 * a.NT * MAXSUB * 4, stream));
+  // flags: zero from the caller's initial fill, then left clean by every launch (kernel epilogue)
   const size_t smem = bwd ? pl.smem_bwd : pl.smem_fwd;
   auto kern = bwd ? lstm_tc_bwd_kernel : lstm_tc_fwd_kernel;
   MMDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -31,8 +31,12 @@ ATT_P = 0.1            # nn.TransformerEncoderLayer default dropout (reference s
 NHEAD = 2
 TL = "transformer_encoder.layers.0."
 # stream priorities (text chain, visual/acoustic chains, weight-gradient leaves); lower = sooner
-_PRIO = tuple(int(x) for x in os.environ.get("MMDA_PRIO", "-2,-1,0").split(","))
-_ORDER = os.environ.get("MMDA_ORDER", "done,pre").split(",")   # side BPTT layer 2 / layer 1 gate
+# (measured, tools/exp_prio.sh: the three encoder chains at equal priority above the leaves: 4.54 ms;
+# text above the side chains 4.64; everything equal 4.60)
+_PRIO = tuple(int(x) for x in os.environ.get("MMDA_PRIO", "-1,-1,0").split(","))
+# side BPTT layer 2 / layer 1 gate against the text BPTT launch: "pre" = wait until the text stream
+# has reached its launch point (4.54 ms), "done" = until it has completed (4.87), "none" (4.56)
+_ORDER = os.environ.get("MMDA_ORDER", "pre,pre").split(",")
 _DRYRUN = False       # tests only: exercise the host orchestration on CPU with a stubbed library
 _DRYRUN_SIMT_ONLY = False
 
@@ -170,6 +174,7 @@ class MisaEngine:
         self.NC = self.cfg.num_classes
         self.H = dict(zip(MODS, model.hidden_sizes))
         self._pack_key = None
+        self._fwd_order = None
         self.pad = None                 # (T_pad, Np) while FusedTrainer runs a padded (graph) step
         self._params = None
         self._params_ver = None
@@ -578,6 +583,20 @@ class MisaEngine:
                      int(train))
                 continue
             tcws = self._lstm_tc_ws(m, B, H, Tmax)
+            if self.multi_stream and not _DRYRUN and r == r1 and self._fwd_order is not None:
+                # The text recurrence launches cooperatively (every CTA resident at once): the
+                # small visual / acoustic recurrences must not grab SMs just before it.  They
+                # wait for the point where the text stream reaches its own layer-1 launch; all
+                # three launches then become eligible together and stream priority puts the
+                # text CTAs first.
+                cur = torch.cuda.current_stream()
+                if m == "t" and tcws is not None:
+                    ev = torch.cuda.Event()
+                    ev.record(cur)
+                    self._fwd_order.append(ev)
+                elif m != "t":
+                    for ev in self._fwd_order:
+                        cur.wait_event(ev)
             if tcws is not None:
                 k._c("mmda_lstm_tc_forward", _ptr(G), _ptr(P[f"{r}.weight_hh_l0"]),
                      _ptr(P[f"{r}.weight_hh_l0_reverse"]), _ptr(Y), _ptr(C), _ptr(pk["lens"]),
@@ -652,7 +671,10 @@ class MisaEngine:
             return run
 
         self.saved = dict(pk=pk, sent=sent, X=X, train=train, srcs=srcs)
-        self._fork({"t": enc_text, "v": enc_side("v"), "a": enc_side("a")})
+        self._fwd_order = [] if (self.lstm_tc and not self.gru and not self.use_bert) else None
+        self._fork({"t": enc_text, "v": enc_side("v"), "a": enc_side("a")},
+                   text_first=self._fwd_order is not None)
+        self._fwd_order = None
 
         # ---- heads: project -> private/shared -> recon (src/models.py:254-279) ----
         A = self.buf("A", 3, B, d)             # activation output (pre-LN)
@@ -991,11 +1013,12 @@ class MisaEngine:
             return run
 
         # The text BPTT launches cooperatively on ~120 SMs: if the small visual / acoustic BPTT
-        # kernels get there first it has to wait for them to drain (0.3 ms, measured).  The side
-        # encoders have slack in this region, so the text stream is enqueued first and the side
-        # streams hold their layer-2 BPTT until the text layer-2 BPTT is done, and their layer-1
-        # BPTT until the text stream has reached its own layer-1 launch (both launches then become
-        # eligible together and the text stream's priority decides).
+        # kernels get there first it has to wait for them to drain (0.3 ms, measured).  So the
+        # text stream is enqueued first and the side streams hold each BPTT launch until the text
+        # stream has reached its own launch point of that layer (`_ORDER`): the launches become
+        # eligible together, the text CTAs are placed first (enqueue order) and the small kernels
+        # run on the SMs the text kernel leaves free.  The recurrence kernels clean their exchange
+        # flags themselves, so no memset node sits between that point and the launch.
         self._order_events = {}
         self._fork({m: enc_bwd(m) for m in MODS}, text_first=self.lstm_tc and not self.gru)
         self._order_events = {}

@@ -150,7 +150,7 @@ def test_engine_kernel_sequence_level1_and_level2(dryrun):
     tr.step(b.sentences, b.visual, b.acoustic, b.lengths, b.labels)
     seq = dryrun.calls
     assert seq[-1] == "mmda_adam_clip_step"
-    order = [seq.index(n) for n in ("mmda_gather_rows", "mmda_lstm_forward",
+    order = [seq.index(n) for n in ("mmda_embedding_forward", "mmda_lstm_forward",
                                     "mmda_attention_forward", "mmda_loss_phase1", "mmda_loss_finalize",
                                     "mmda_attention_backward", "mmda_lstm_backward",
                                     "mmda_embedding_backward", "mmda_adam_clip_step")]
