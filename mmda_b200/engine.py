@@ -1181,6 +1181,11 @@ class MisaEngine:
                     k._c("mmda_embedding_backward", _ptr(G["embed.weight"]),
                          _ptr(self.saved["sent"]), _ptr(dX), _ptr(pk["row_t"]), _ptr(pk["row_j"]),
                          _ptr(pk["sidx"]), N, B, H, V)
+                    if notify is not None:
+                        # the dense embedding gradient (the largest bucket) is complete here, a
+                        # millisecond of weight-gradient GEMMs before the rest of the encoder:
+                        # its all-reduce runs under them
+                        notify("embed")
         for st in side_used:
             done = torch.cuda.Event()
             done.record(st)

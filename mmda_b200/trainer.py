@@ -14,6 +14,8 @@ from __future__ import annotations
 
 from typing import Dict, List, Optional, Tuple
 
+import os
+
 import torch
 
 from ._lib import LIB, MmdaError
@@ -154,6 +156,8 @@ class FusedTrainer:
         self.v = torch.zeros_like(self.p_arena)
         self._pending = []
         self._reduced = set()
+        self._defer_ready = None
+        self.trace_ready = None         # profiling aid: {tag: timed event} of the last step
         # device-resident step state (step counter = dropout seed offset, Adam bias corrections)
         self.state = torch.zeros(4, dtype=torch.float64, device=self.p_arena.device)
         if not _engine._DRYRUN:
@@ -291,20 +295,58 @@ class FusedTrainer:
                             d_orig=dO, d_recon=dR, d_domain=dDL)
 
     # ------------------------------------------------------------------ step ---------------
+    # NCCL runs the collectives of one communicator in the order they were issued.  The encoder
+    # phase of the backward is enqueued text-first, so issuing on notification would put rnn2's
+    # all-reduce (whose gradients complete LATE: the weight-gradient GEMMs run in the tail) in
+    # front of the visual / acoustic / embedding buckets that are complete a millisecond earlier,
+    # and everything would drain after the last kernel (measured: five all-reduces back to back at
+    # the end of the step, 0.2 ms exposed).  Encoder-phase notifications only record an event; the
+    # all-reduces are issued after the backward has been enqueued, in completion order, from a
+    # helper stream that waits for exactly those events.
+    _ISSUE_ORDER = tuple(os.environ.get("MMDA_AR_ORDER", "enc_a,enc_v,embed,enc_t_l2,enc_t").split(","))
+
     def _on_ready(self, tag):
         if self.world == 1 or (tag == "enc_t" and self.use_bert and not self._bert_done):
             return
-        # enc_t_l2: the text rnn2 gradients are complete (issued from the weight-gradient stream,
-        # long before the rest of the text encoder); enc_t: everything else of the text encoder
+        if tag in self._ISSUE_ORDER and not _engine._DRYRUN and self._defer_ready is not None:
+            ev = torch.cuda.Event(enable_timing=self.trace_ready is not None)
+            ev.record(torch.cuda.current_stream())
+            self._defer_ready[tag] = ev
+            if self.trace_ready is not None:
+                self.trace_ready[tag] = ev
+            return
+        self._issue(tag)
+
+    def _issue(self, tag):
+        # enc_t_l2: the text rnn2 gradients are complete (issued from the weight-gradient stream);
+        # embed: the embedding gradient is complete right after the last dX GEMM of the chain;
+        # enc_t: whatever the finer-grained notifications left of the text encoder
         buckets = {"fusion": (0,), "heads": (1,), "enc_v": (2,), "enc_a": (3,), "enc_t_l2": (4,),
-                   "enc_t": (5, 6)}[tag]
-        if tag == "enc_t" and 4 not in self._reduced:
-            buckets = (4,) + buckets          # e.g. BERT text branch: no rnn2 notification
+                   "embed": (6,), "enc_t": (5, 6)}[tag]
+        if tag == "enc_t":
+            buckets = tuple(b for b in (4, 5, 6) if b not in self._reduced)
         for b in buckets:
             lo, hi = self.ranges[b]
             self._reduced.add(b)
             if hi > lo:
                 self._pending.append(self._allreduce(self.g_arena[lo:hi], async_op=True))
+
+    def _flush_ready(self):
+        evs, self._defer_ready = self._defer_ready, None
+        if not evs:
+            return
+        main = torch.cuda.current_stream()
+        if not hasattr(self, "_ar_stream"):
+            self._ar_stream = torch.cuda.Stream(device=self.g_arena.device)
+        h = self._ar_stream
+        with torch.cuda.stream(h):
+            for tag in self._ISSUE_ORDER:
+                if tag in evs:
+                    h.wait_event(evs[tag])
+                    self._issue(tag)
+            done = torch.cuda.Event()
+            done.record(h)
+        main.wait_event(done)
 
     def forward_backward(self, sentences, visual, acoustic, lengths, labels, bert=None):
         """zero_grad + forward + losses + backward (+ gradient all-reduce).  Returns the device
@@ -349,7 +391,9 @@ class FusedTrainer:
         self._pending = []
         self._reduced = set()
         self._bert_done = False
+        self._defer_ready = {} if self.world > 1 else None
         d_utt = eng.backward(self.G, on_ready=self._on_ready, **grads)
+        self._flush_ready()
         if self.use_bert:
             eng.bert.backward(self.G, d_utt)
             self._bert_done = True

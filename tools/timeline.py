@@ -2,6 +2,8 @@
 which stream runs what, when, and where the critical path has gaps.
 
     python tools/timeline.py [out.txt]
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/timeline.py [out.txt]
+        (data-parallel step: rank 0 prints its own timeline, NCCL kernels included)
 """
 import os
 import sys
@@ -15,11 +17,17 @@ def main():
     from torch.profiler import ProfilerActivity, profile
     from mmda_b200 import MISA, FusedTrainer, mosei_config
     from mmda_b200.synthetic import batch_for
-    dev = torch.device("cuda:0")
+    world, rank, pg = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), None
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        pg = dist.group.WORLD
     cfg = mosei_config(vocab_size=20000, batch_size=256)
     torch.manual_seed(0)
-    tr = FusedTrainer(MISA(cfg).to(dev).train())
-    b = batch_for(cfg, seed=1, lengths=os.environ.get("LENGTHS", "full"))
+    tr = FusedTrainer(MISA(cfg).to(dev).train(), process_group=pg)
+    b = batch_for(cfg, seed=1 + rank, lengths=os.environ.get("LENGTHS", "full"))
     args = [b.sentences.to(dev), b.visual.to(dev), b.acoustic.to(dev), b.lengths, b.labels.to(dev)]
     for _ in range(6):
         tr.step(*args)
@@ -27,6 +35,12 @@ def main():
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
         tr.step(*args)
         torch.cuda.synchronize()
+    tr.close()
+    if world > 1:
+        dist.barrier(device_ids=[dev.index])
+        dist.destroy_process_group()
+        if rank != 0:
+            return
     evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
     ks = []
     for e in evs:
