@@ -167,6 +167,9 @@ int mmda_lstm_tc_backward(float* gates, const float* whh_f, const float* whh_r, 
                           int utt_off_r, const int* lens_sorted, const int* sorted_idx,
                           const int* offsets, int B, int H, int Tmax, void* ws,
                           mmda_stream_t stream);
+/* A/B knob: largest batch tile of the forward recurrence (default 64 rows; 48 gives 6 tiles /
+ * 120 CTAs at B = 256 -- faster stand-alone) */
+int mmda_lstm_tc_set_fwd_rows(int rows);
 /* A/B knob: SMs one launch may occupy (default 120: the rest serve the concurrent encoders) */
 int mmda_lstm_tc_set_max_ctas(int n);
 /* diagnostic: per-step phase timestamps of CTA 0 (NULL = off) */

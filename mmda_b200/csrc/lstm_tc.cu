@@ -885,6 +885,7 @@ struct TclPlan {
 };
 
 int g_tcl_max_ctas = 120;   // upper bound on the SMs one launch occupies
+int g_tcl_fwd_rows = TCL_N; // largest forward batch tile (A/B knob: 48 -> 6 tiles / 120 CTAs at B = 256)
 
 int tcl_make_plan(int B, int H, int Tmax, TclPlan* pl) {
   if (H <= 128 || H > 320 || B <= 0) return MMDA_ERR_UNSUPPORTED;
@@ -904,7 +905,7 @@ int tcl_make_plan(int B, int H, int Tmax, TclPlan* pl) {
     *G = (*NT + rounds - 1) / rounds;
   };
   pl->S = (H + TCL_UNITS - 1) / TCL_UNITS;
-  tiles(TCL_N, pl->S, &pl->BT, &pl->NT, &pl->G);
+  tiles(g_tcl_fwd_rows < TCL_N ? g_tcl_fwd_rows : TCL_N, pl->S, &pl->BT, &pl->NT, &pl->G);
   // backward: the whole W^T slice (two fp16 terms, MT tiles of 2U columns) + the accumulators
   // (3 sub-tiles x MT tiles x 16 columns) must fit the 512 TMEM columns; U even
   int Sb = pl->S, Ub = 0;
@@ -971,6 +972,12 @@ int mmda_lstm_tc_plan_select(int backward) {
 }
 
 // upper bound on the CTAs (= SMs) one launch may occupy
+int mmda_lstm_tc_set_fwd_rows(int rows) {
+  MMDA_REQUIRE(rows >= 16 && rows <= TCL_N, "lstm_tc_set_fwd_rows: %d (16..%d)", rows, TCL_N);
+  g_tcl_fwd_rows = rows;
+  return MMDA_OK;
+}
+
 int mmda_lstm_tc_set_max_ctas(int n) {
   MMDA_REQUIRE(n >= 2 && n <= 1024, "lstm_tc: max CTAs must be in [2, 1024]");
   g_tcl_max_ctas = n;

@@ -211,6 +211,8 @@ class MisaEngine:
         self.lstm_tc = os.environ.get("MMDA_LSTM_TC", "1") != "0"
         if "MMDA_LSTM_TC_CTAS" in os.environ and not _DRYRUN:
             LIB.call("mmda_lstm_tc_set_max_ctas", int(os.environ["MMDA_LSTM_TC_CTAS"]))
+        if "MMDA_LSTM_TC_FWD_ROWS" in os.environ and not _DRYRUN:
+            LIB.call("mmda_lstm_tc_set_fwd_rows", int(os.environ["MMDA_LSTM_TC_FWD_ROWS"]))
         # use_bert=True: the BERT encoder runs on the hand-written kernels too
         # (mmda_b200/bert.py); its masked-mean output enters here as `utt_text` and backward()
         # returns the gradient wrt it.
