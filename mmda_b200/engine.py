@@ -86,6 +86,16 @@ class Kernels:
                 split_k, c_ilv)
 
     def linear(self, x, w, b, out, act=ACT_NONE, bias2=None):
+        M, K = x.shape
+        if K >= 1024 and M * w.shape[0] <= 64 * 1024 and bias2 is None and not _DRYRUN_SIMT_ONLY:
+            # long contraction into a small output (text projection: 256 x 128 from K = 1200): 32
+            # CTAs walking 38 k-tiles each is a 60 us latency chain; split K four ways (atomic
+            # accumulate into a zeroed output), then bias + activation in two tiny launches
+            self.gemm(x, w, out, tb=True, split_k=4)
+            self.add(out, out, b.view(1, -1).expand(M, -1))
+            if act != ACT_NONE:
+                self.act(out, act)
+            return
         self.gemm(x, w, out, tb=True, bias=b, bias2=bias2, act=act)
 
     def leaf(self, fn):
@@ -501,8 +511,15 @@ class MisaEngine:
     def tc_linear(self, tag, x, w, b, out):
         """out = x w^T + b on tcgen05 (3xTF32: fp32-accurate in either precision mode)."""
         M, K = x.shape
-        self.k.gemm_tc(0, 0, 0, M, w.shape[0], K, self._prep(tag + "_x", x, kind=0),
-                       self._prep(tag + "_w", w, kind=0, split=True), out, bias=b)
+        N = w.shape[0]
+        xo, wo = self._prep(tag + "_x", x, kind=0), self._prep(tag + "_w", w, kind=0, split=True)
+        if K >= 1024 and ((M + 127) // 128) * ((N + 127) // 128) <= 32:
+            # few output tiles, long K (fusion FFN linear2: 12 tiles x K = 2048): start from the
+            # bias and let the kernel split K over the idle SMs (atomic accumulate)
+            self.k.add(out, b.view(1, -1).expand(M, -1))
+            self.k.gemm_tc(0, 0, 0, M, N, K, xo, wo, out, mode=1, split_k=0)
+            return
+        self.k.gemm_tc(0, 0, 0, M, N, K, xo, wo, out, bias=b)
 
     def tc_linear_bwd(self, tag, dy, x, w, dw, db, dx, dx_acc):
         """dw += dy^T x, db += colsum(dy), dx (+)= dy w   (dy: [M][N], x: [M][K], w: [N][K])"""
