@@ -145,49 +145,72 @@ loss_phase2_kernel(const float* __restrict__ X0, const float* __restrict__ segA,
 
 // one block: loss values + CMD coefficient vectors coef[3][5][d] (d L / d c_k of shared token a,
 // before the w_sim/3 factor)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 loss_finalize_kernel(const float* __restrict__ segA, const float* __restrict__ segB,
                      float* __restrict__ losses, float* __restrict__ coef, int d, int NC, float Bg,
                      float w_diff, float w_sim, float w_recon, float w_conf, int adversarial) {
-  __shared__ float red[8];
-  const int tid = threadIdx.x;
+  // One CTA of 32 warps (the inputs are batch sums: nothing here scales with B).  The Gram
+  // square-sum goes over all threads with 16-byte loads; the 15 CMD terms (3 pairs x 5 moment
+  // orders) are one warp each; the CMD gradient coefficients are then one pass over
+  // [token][order][column] with the 15 norms in shared memory.  (Was: 256 threads walking the 15
+  // terms one after the other with two block barriers each -- 25 us on the step's chain.)
+  __shared__ float red[32];
+  __shared__ float nrm_s[15];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* colsum = segA;
   const float* cls = segA + NTOK * d;
   const float* moments = segB;
   const float* G = segB + 3 * 4 * d;
-  // diff
+  // diff: sum of the squared entries of the six Gram matrices
   float s = 0.f;
   const size_t ng = (size_t)6 * d * d;
-  for (size_t i = tid; i < ng; i += 256) s = fmaf(G[i], G[i], s);
-  const float diff = block_sum_256(s, red) / ((float)d * (float)d);
-  // cmd
-  for (int i = tid; i < 3 * 5 * d; i += 256) coef[i] = 0.f;
-  __syncthreads();
-  const int pa[3] = {0, 0, 2}, pb[3] = {1, 2, 1};
-  float cmd = 0.f;
-  for (int p = 0; p < 3; ++p) {
-    for (int k = 1; k <= 5; ++k) {
-      float part = 0.f;
-      for (int c = tid; c < d; c += 256) {
-        const float va = k == 1 ? colsum[(3 + pa[p]) * d + c] : moments[(pa[p] * 4 + k - 2) * d + c];
-        const float vb = k == 1 ? colsum[(3 + pb[p]) * d + c] : moments[(pb[p] * 4 + k - 2) * d + c];
-        const float dl = (va - vb) / Bg;
-        part = fmaf(dl, dl, part);
-      }
-      const float nrm = sqrtf(block_sum_256(part, red));
-      cmd += nrm;
-      for (int c = tid; c < d; c += 256) {
-        const float va = k == 1 ? colsum[(3 + pa[p]) * d + c] : moments[(pa[p] * 4 + k - 2) * d + c];
-        const float vb = k == 1 ? colsum[(3 + pb[p]) * d + c] : moments[(pb[p] * 4 + k - 2) * d + c];
-        const float g = ((va - vb) / Bg) / nrm;
-        coef[(pa[p] * 5 + k - 1) * d + c] += g;     // same thread owns column c: no race
-        coef[(pb[p] * 5 + k - 1) * d + c] -= g;
-      }
-      __syncthreads();
+  if ((ng & 3) == 0 && (reinterpret_cast<uintptr_t>(G) & 15) == 0) {
+    const float4* G4 = reinterpret_cast<const float4*>(G);
+    for (size_t i = tid; i < ng / 4; i += 1024) {
+      const float4 g = G4[i];
+      s = fmaf(g.x, g.x, fmaf(g.y, g.y, fmaf(g.z, g.z, fmaf(g.w, g.w, s))));
     }
+  } else {
+    for (size_t i = tid; i < ng; i += 1024) s = fmaf(G[i], G[i], s);
   }
-  cmd /= 3.f;
+  s = warp_sum(s);
+  if (lane == 0) red[warp] = s;
+  // cmd: warp w < 15 owns term (pair p = w / 5, order k = w % 5 + 1)
+  const int pa[3] = {0, 0, 2}, pb[3] = {1, 2, 1};
+  auto moment = [&](int tok, int k, int c) {   // k-th moment sum of shared token tok (3 + tok)
+    return k == 1 ? colsum[(3 + tok) * d + c] : moments[(tok * 4 + k - 2) * d + c];
+  };
+  if (warp < 15) {
+    const int p = warp / 5, k = warp % 5 + 1;
+    float part = 0.f;
+    for (int c = lane; c < d; c += 32) {
+      const float dl = (moment(pa[p], k, c) - moment(pb[p], k, c)) / Bg;
+      part = fmaf(dl, dl, part);
+    }
+    part = warp_sum(part);
+    if (lane == 0) nrm_s[warp] = sqrtf(part);
+  }
+  __syncthreads();
+  // gradient coefficients: coef[tok][k-1][c] = sum over the pairs tok takes part in of
+  // +-((m_a - m_b) / Bg) / norm   (+ as the pair's first token, - as its second)
+  for (int i = tid; i < 3 * 5 * d; i += 1024) {
+    const int c = i % d, k = (i / d) % 5 + 1, tok = i / (5 * d);
+    float g = 0.f;
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+      if (pa[p] != tok && pb[p] != tok) continue;
+      const float v = ((moment(pa[p], k, c) - moment(pb[p], k, c)) / Bg) / nrm_s[p * 5 + k - 1];
+      g += pa[p] == tok ? v : -v;
+    }
+    coef[i] = g;
+  }
   if (tid == 0) {
+    float diff = 0.f;
+    for (int w = 0; w < 32; ++w) diff += red[w];
+    diff /= (float)d * (float)d;
+    float cmd = 0.f;
+    for (int t = 0; t < 15; ++t) cmd += nrm_s[t];
+    cmd /= 3.f;
     float l_cls = 0.f, l_conf = 0.f;
     for (int c = 0; c < NC; ++c) {
       l_cls += cls[0 * NC + c] / Bg;
@@ -368,7 +391,7 @@ int mmda_loss_phase2(const float* X0, const float* segA, float* XN, float* inv_n
 int mmda_loss_finalize(const float* segA, const float* segB, float* losses, float* coef, int d,
                        int NC, float Bg, float w_diff, float w_sim, float w_recon, float w_conf,
                        int adversarial, cudaStream_t stream) {
-  loss_finalize_kernel<<<1, 256, 0, stream>>>(segA, segB, losses, coef, d, NC, Bg, w_diff, w_sim,
+  loss_finalize_kernel<<<1, 1024, 0, stream>>>(segA, segB, losses, coef, d, NC, Bg, w_diff, w_sim,
                                               w_recon, w_conf, adversarial);
   MMDA_CHECK_LAUNCH();
   return MMDA_OK;
@@ -512,42 +535,43 @@ __global__ void __launch_bounds__(256) loss_gram_kernel(const float* __restrict_
   }
 }
 
+// One CTA per (output token x, pair p it takes part in, 32 x 32 output tile): 12 (x, p) slots, each a
+// K = d contraction, accumulated into the zeroed DXN with atomics (a private token sits in three
+// pairs; walking them inside one CTA tripled the length of the chain: 30 -> 12 us).
 __global__ void __launch_bounds__(256) loss_dxn_kernel(const float* __restrict__ XN, const float* __restrict__ Gm,
                                                        float* __restrict__ DXN, int B, int d, float alpha) {
   __shared__ float Xs[32][33], Gs[32][33];
-  const int x = blockIdx.z, b0 = blockIdx.y * 32, i0 = blockIdx.x * 32;
+  const int p = blockIdx.z >> 1, is_a = (blockIdx.z & 1) == 0;
+  const int x = is_a ? c_pair_a[p] : c_pair_b[p];
+  const int b0 = blockIdx.y * 32, i0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int p = 0; p < 6; ++p) {
-    const bool is_a = c_pair_a[p] == x, is_b = c_pair_b[p] == x;
-    if (!is_a && !is_b) continue;                              // block-uniform
-    const float* X = XN + (size_t)(is_a ? c_pair_b[p] : c_pair_a[p]) * B * d;
-    const float* G = Gm + (size_t)p * d * d;
-    for (int j0 = 0; j0 < d; j0 += 32) {
+  const float* X = XN + (size_t)(is_a ? c_pair_b[p] : c_pair_a[p]) * B * d;
+  const float* G = Gm + (size_t)p * d * d;
+  for (int j0 = 0; j0 < d; j0 += 32) {
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int rr = ty * 4 + r;
-        Xs[rr][tx] = (b0 + rr < B && j0 + tx < d) ? X[(size_t)(b0 + rr) * d + j0 + tx] : 0.f;
-        // Gs[j][i] = coefficient of X[.][j0+j] in output column i0+i
-        if (is_a)   // out[b][i] += sum_j X[b][j] * G[i][j]
-          Gs[tx][rr] = (i0 + rr < d && j0 + tx < d) ? G[(size_t)(i0 + rr) * d + j0 + tx] : 0.f;
-        else        // out[b][i] += sum_j X[b][j] * G[j][i]
-          Gs[rr][tx] = (j0 + rr < d && i0 + tx < d) ? G[(size_t)(j0 + rr) * d + i0 + tx] : 0.f;
-      }
-      __syncthreads();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float gv = Gs[j][tx];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) acc[r] = fmaf(Xs[ty * 4 + r][j], gv, acc[r]);
-      }
-      __syncthreads();
+    for (int r = 0; r < 4; ++r) {
+      const int rr = ty * 4 + r;
+      Xs[rr][tx] = (b0 + rr < B && j0 + tx < d) ? X[(size_t)(b0 + rr) * d + j0 + tx] : 0.f;
+      // Gs[j][i] = coefficient of X[.][j0+j] in output column i0+i
+      if (is_a)   // out[b][i] += sum_j X[b][j] * G[i][j]
+        Gs[tx][rr] = (i0 + rr < d && j0 + tx < d) ? G[(size_t)(i0 + rr) * d + j0 + tx] : 0.f;
+      else        // out[b][i] += sum_j X[b][j] * G[j][i]
+        Gs[rr][tx] = (j0 + rr < d && i0 + tx < d) ? G[(size_t)(j0 + rr) * d + i0 + tx] : 0.f;
     }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float gv = Gs[j][tx];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[r] = fmaf(Xs[ty * 4 + r][j], gv, acc[r]);
+    }
+    __syncthreads();
   }
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
     const int b = b0 + ty * 4 + r, i = i0 + tx;
-    if (b < B && i < d) DXN[((size_t)x * B + b) * d + i] = alpha * acc[r];
+    if (b < B && i < d) atomicAdd(DXN + ((size_t)x * B + b) * d + i, alpha * acc[r]);
   }
 }
 
@@ -562,7 +586,8 @@ extern "C" int mmda_loss_gram(const float* XN, float* Gm, int B, int d, cudaStre
 extern "C" int mmda_loss_dxn(const float* XN, const float* Gm, float* DXN, int B, int d, float alpha,
                              cudaStream_t stream) {
   MMDA_REQUIRE(B > 0 && d > 0, "loss_dxn: B=%d d=%d", B, d);
-  dim3 grid((d + 31) / 32, (B + 31) / 32, 6);
+  MMDA_CUDA(cudaMemsetAsync(DXN, 0, (size_t)NTOK * B * d * sizeof(float), stream));
+  dim3 grid((d + 31) / 32, (B + 31) / 32, 12);
   loss_dxn_kernel<<<grid, 256, 0, stream>>>(XN, Gm, DXN, B, d, alpha);
   MMDA_CHECK_LAUNCH();
   return MMDA_OK;
