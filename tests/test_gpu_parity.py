@@ -566,14 +566,15 @@ def test_graph_replay_after_other_forwards(dev):
     assert float((outs[True][1] - outs[False][1]).abs().max()) <= 2 * 1e-4 * len(seq) + 1e-6
 
 
-def test_one_step_graph_serves_a_ragged_stream(dev):
+@pytest.mark.parametrize("cell", ["lstm", "gru"])
+def test_one_step_graph_serves_a_ragged_stream(dev, cell):
     """the captured step must not be keyed by the lengths.  Ten batches with ten
     different length patterns run through at most two graphs (packed rows rounded to the row
     granule); losses and parameters match the exact-row eager steps of the same stream."""
     from mmda_b200 import MISA, mosei_config
     from mmda_b200 import trainer as T
     from mmda_b200.synthetic import batch_for
-    cfg = mosei_config(vocab_size=300, batch_size=64)
+    cfg = mosei_config(vocab_size=300, batch_size=64, rnncell=cell)
     stream = [batch_for(cfg, seed=40 + i, lengths="ragged" if i % 3 else "shuffled", seq_len=20)
               for i in range(10)]
     assert len({tuple(b.lengths.tolist()) for b in stream}) == 10
@@ -602,17 +603,51 @@ def test_one_step_graph_serves_a_ragged_stream(dev):
     finally:
         T.ROW_GRANULE = old
     lerr = float(((outs[True][0] - outs[False][0]).abs() / outs[False][0].abs().clamp_min(1e-6)).max())
-    assert lerr < 2e-5, lerr
+    # 20 optimisation steps: padded and exact launches differ in summation order (split-K over Np
+    # vs N rows), and Adam amplifies 1e-7 gradient differences; single-step gradients are compared
+    # tightly in test_padded_rows_gradients_match_exact_rows
+    assert lerr < 1e-4, lerr
     assert float((outs[True][1] - outs[False][1]).abs().max()) <= 2 * 1e-4 * 20 + 1e-6
 
 
-def test_padded_rows_gradients_match_exact_rows(dev):
+def test_step_batch_loss_future(dev):
+    """step_batch(fetch=True): the LossFuture of step i, read after step i+1 was enqueued, holds
+    step i's losses (the bench's e2e loop), for graph-replayed steps too."""
+    from mmda_b200 import MISA, mosei_config
+    from mmda_b200.synthetic import batch_for
+    from mmda_b200.trainer import FusedTrainer
+    cfg = mosei_config(vocab_size=300, batch_size=32)
+    host = [batch_for(cfg, seed=70 + i, lengths="full", seq_len=12) for i in range(3)]
+
+    def make():
+        torch.manual_seed(14)
+        return MISA(cfg).to(dev).eval()
+
+    ref_tr = FusedTrainer(make())
+    ref = [ref_tr.step_batch(host[i % 3]).tolist() for i in range(8)]
+    ref_tr.close()
+    tr = FusedTrainer(make())
+    got, pending = [], None
+    for i in range(8):
+        fut = tr.step_batch(host[i % 3], prefetch=host[(i + 1) % 3], fetch=True)
+        if pending is not None:
+            got.append(pending.result())
+        pending = fut
+    got.append(pending.result())
+    tr.close()
+    assert len(got) == 8
+    for a, b in zip(got, ref):
+        assert max(abs(x - y) / max(abs(y), 1e-6) for x, y in zip(a[:6], b[:6])) < 2e-5, (a, b)
+
+
+@pytest.mark.parametrize("cell", ["lstm", "gru"])
+def test_padded_rows_gradients_match_exact_rows(dev, cell):
     """The padded launch (Np > N rows, T_pad > Tmax) must give the exact launch's gradients: same
     batch, engine.pad set by hand, every parameter gradient compared."""
     from mmda_b200 import MISA, mosei_config
     from mmda_b200.synthetic import batch_for
     from mmda_b200.trainer import FusedTrainer
-    cfg = mosei_config(vocab_size=300, batch_size=32)
+    cfg = mosei_config(vocab_size=300, batch_size=32, rnncell=cell)
     b = batch_for(cfg, seed=9, lengths="ragged", seq_len=16)
     b.lengths = b.lengths.clamp(max=11)            # Tmax < T of the tensors
     torch.manual_seed(13)
