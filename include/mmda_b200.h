@@ -73,7 +73,9 @@ int mmda_embedding_backward(float* dE, const long long* sentences, const float* 
 /* ---- dense contractions: nn.Linear everywhere in src/models.py:61-153 and the hoisted LSTM
  * GEMMs of nn.LSTM (src/models.py:48-55).
  * C = act(alpha*op(A)*op(B) + beta*C + bias + bias2); op(A) = transA ? A[k*lda+m] : A[m*lda+k];
- * op(B) = transB ? B[n*ldb+k] : B[k*ldb+n].  split_k: 0 = auto, 1 = none, >1 = atomic split-K
+ * op(B) = transB ? B[n*ldb+k] : B[k*ldb+n].  split_k: 0 = auto, 1 = none, >1 = atomic split-K,
+ * -1 = deterministic split-K inside the CTA (32x32 tiles, four K groups summed in a fixed order: the
+ * forward's long-K / small-output linears, which must stay bit-reproducible)
  * (requires beta == 1 and no activation).  c_row_interleave = H (else 0): logical row u*4+g of C
  * is stored at row g*H+u -- un-does the gate-interleaved order of dG in the weight-gradient GEMMs. */
 int mmda_sgemm(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda,

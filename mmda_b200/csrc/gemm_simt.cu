@@ -153,6 +153,138 @@ static int launch_sgemm(bool ta, bool tb, const float* A, const float* B, float*
   return MMDA_OK;
 }
 
+// Long contraction into a small output (text projection: 256 x 128 from K = 1200; fusion FFN
+// linear2: 1536 x 128 from K = 2048).  A 32 x 32 tile walking K in 32-wide steps is a latency chain
+// of K/32 load -> barrier -> FMA rounds on a handful of CTAs; split-K over grid.z with atomics would
+// shorten it but makes the FORWARD non-deterministic in its last bits, which the ReLU / LeakyReLU
+// masks of the layers above turn into visible gradient differences between two runs.  Here the
+// K range is split over KS = 4 groups of 64 threads INSIDE the CTA (each group its own tiles and
+// its own named barrier), and the four partial tiles are summed in a fixed order: same chain
+// shortening, bit-reproducible.
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256)
+sgemm_ks_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C,
+                const float* __restrict__ bias, const float* __restrict__ bias2, int M, int N, int K,
+                int lda, int ldb, int ldc, float alpha, float beta, int act, int k_per_group) {
+  constexpr int BM = 32, BN = 32, BK = 32, TM = 4, TN = 4, KS = 4, NT = 64, PAD = 4;
+  constexpr int LA = (BM * BK) / NT, LB = (BN * BK) / NT;
+  __shared__ __align__(16) float As[KS][BK][BM + PAD];
+  __shared__ __align__(16) float Bs[KS][BK][BN + PAD];
+  const int g = threadIdx.x / NT, tid = threadIdx.x % NT;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kbeg = g * k_per_group;
+  const int kend = min(K, kbeg + k_per_group);
+  const int tx = tid % (BN / TN), ty = tid / (BN / TN);
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+  float ra[LA], rb[LB];
+  auto load_tiles = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < LA; ++i) {
+      const int e = tid + i * NT;
+      int m, k;
+      if (TA) { m = e % BM; k = e / BM; } else { k = e % BK; m = e / BK; }
+      const int gm = m0 + m, gk = k0 + k;
+      float v = 0.f;
+      if (gm < M && gk < kend) v = TA ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk];
+      ra[i] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < LB; ++i) {
+      const int e = tid + i * NT;
+      int n, k;
+      if (TB) { k = e % BK; n = e / BK; } else { n = e % BN; k = e / BN; }
+      const int gn = n0 + n, gk = k0 + k;
+      float v = 0.f;
+      if (gn < N && gk < kend) v = TB ? B[(size_t)gn * ldb + gk] : B[(size_t)gk * ldb + gn];
+      rb[i] = v;
+    }
+  };
+  auto store_tiles = [&]() {
+#pragma unroll
+    for (int i = 0; i < LA; ++i) {
+      const int e = tid + i * NT;
+      int m, k;
+      if (TA) { m = e % BM; k = e / BM; } else { k = e % BK; m = e / BK; }
+      As[g][k][m] = ra[i];
+    }
+#pragma unroll
+    for (int i = 0; i < LB; ++i) {
+      const int e = tid + i * NT;
+      int n, k;
+      if (TB) { k = e % BK; n = e / BK; } else { n = e % BN; k = e / BN; }
+      Bs[g][k][n] = rb[i];
+    }
+  };
+  auto group_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(g + 1) : "memory"); };
+  if (kbeg < kend) {
+    load_tiles(kbeg);
+    for (int k0 = kbeg; k0 < kend; k0 += BK) {
+      store_tiles();
+      group_sync();
+      if (k0 + BK < kend) load_tiles(k0 + BK);
+#pragma unroll
+      for (int k = 0; k < BK; ++k) {
+        const float4 av = *reinterpret_cast<const float4*>(&As[g][k][ty * TM]);
+        const float4 bv = *reinterpret_cast<const float4*>(&Bs[g][k][tx * TN]);
+        const float a[4] = {av.x, av.y, av.z, av.w}, b[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+#pragma unroll
+          for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
+      group_sync();
+    }
+  }
+  // fixed-order reduction of the KS partial tiles through shared memory (the A tiles' storage)
+  __syncthreads();
+  float* red = &As[0][0][0];                       // KS * 32 * 32 floats <= KS * 32 * 36
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) red[(g * BM + ty * TM + i) * BN + tx * TN + j] = acc[i][j];
+  __syncthreads();
+  if (g != 0) return;
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int gm = m0 + ty * TM + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int gn = n0 + tx * TN + j;
+      if (gn >= N) continue;
+      const int o = (ty * TM + i) * BN + tx * TN + j;
+      float v = ((red[o] + red[BM * BN + o]) + red[2 * BM * BN + o]) + red[3 * BM * BN + o];
+      v *= alpha;
+      float* cp = C + (size_t)gm * ldc + gn;
+      if (bias != nullptr) v += bias[gn];
+      if (bias2 != nullptr) v += bias2[gn];
+      if (beta != 0.f) v += beta * (*cp);
+      *cp = apply_act(v, act);
+    }
+  }
+}
+
+static int launch_sgemm_ks(bool ta, bool tb, const float* A, const float* B, float* C, const float* bias,
+                           const float* bias2, int M, int N, int K, int lda, int ldb, int ldc, float alpha,
+                           float beta, int act, cudaStream_t st) {
+  dim3 grid((N + 31) / 32, (M + 31) / 32, 1);
+  int kpg = (K + 3) / 4;
+  kpg = (kpg + 31) / 32 * 32;
+#define MMDA_SGEMM_KS(TA_, TB_) \
+  sgemm_ks_kernel<TA_, TB_><<<grid, 256, 0, st>>>(A, B, C, bias, bias2, M, N, K, lda, ldb, ldc, alpha, beta, act, kpg)
+  if (ta && tb) MMDA_SGEMM_KS(true, true);
+  else if (ta) MMDA_SGEMM_KS(true, false);
+  else if (tb) MMDA_SGEMM_KS(false, true);
+  else MMDA_SGEMM_KS(false, false);
+#undef MMDA_SGEMM_KS
+  MMDA_CHECK_LAUNCH();
+  return MMDA_OK;
+}
+
 __global__ void zero2d_kernel(float* __restrict__ c, int ldc, int rows, int cols) {
   const size_t n = (size_t)rows * cols;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
@@ -166,7 +298,12 @@ extern "C" int mmda_sgemm(int transA, int transB, int M, int N, int K, float alp
                           int c_row_interleave, cudaStream_t stream) {
   if (M <= 0 || N <= 0) return MMDA_OK;
   MMDA_REQUIRE(K >= 0 && A && B && C, "sgemm: bad arguments M=%d N=%d K=%d", M, N, K);
-  MMDA_REQUIRE(split_k >= 0 && split_k <= 64, "sgemm: split_k=%d out of range", split_k);
+  MMDA_REQUIRE(split_k >= -1 && split_k <= 64, "sgemm: split_k=%d out of range", split_k);
+  if (split_k == -1) {   // deterministic in-CTA split-K (32 x 32 tiles, 4 K-groups)
+    MMDA_REQUIRE(c_row_interleave == 0, "sgemm: in-CTA split-K has no interleaved store");
+    return launch_sgemm_ks(transA, transB, A, B, C, bias, bias2, M, N, K, lda, ldb, ldc, alpha, beta, act,
+                           stream);
+  }
   const long big_tiles = (long)((M + 127) / 128) * ((N + 127) / 128);
   const long med_tiles = (long)((M + 63) / 64) * ((N + 63) / 64);
   const long small_tiles = (long)((M + 31) / 32) * ((N + 31) / 32);

@@ -86,17 +86,10 @@ class Kernels:
                 split_k, c_ilv)
 
     def linear(self, x, w, b, out, act=ACT_NONE, bias2=None):
-        M, K = x.shape
-        if K >= 1024 and M * w.shape[0] <= 64 * 1024 and bias2 is None and not _DRYRUN_SIMT_ONLY:
-            # long contraction into a small output (text projection: 256 x 128 from K = 1200): 32
-            # CTAs walking 38 k-tiles each is a 60 us latency chain; split K four ways (atomic
-            # accumulate into a zeroed output), then bias + activation in two tiny launches
-            self.gemm(x, w, out, tb=True, split_k=4)
-            self.add(out, out, b.view(1, -1).expand(M, -1))
-            if act != ACT_NONE:
-                self.act(out, act)
-            return
-        self.gemm(x, w, out, tb=True, bias=b, bias2=bias2, act=act)
+        # long contraction into a small output (text projection 256 x 128 from K = 1200, fusion FFN
+        # linear2): deterministic in-CTA split-K instead of a K/32-step latency chain
+        ks = x.shape[1] >= 1024 and x.shape[0] * w.shape[0] <= 256 * 1024
+        self.gemm(x, w, out, tb=True, bias=b, bias2=bias2, act=act, split_k=-1 if ks else 0)
 
     def leaf(self, fn):
         """Run fn() -- kernels whose results nothing later in the step's dependency chain reads
@@ -512,13 +505,12 @@ class MisaEngine:
         """out = x w^T + b on tcgen05 (3xTF32: fp32-accurate in either precision mode)."""
         M, K = x.shape
         N = w.shape[0]
-        xo, wo = self._prep(tag + "_x", x, kind=0), self._prep(tag + "_w", w, kind=0, split=True)
-        if K >= 1024 and ((M + 127) // 128) * ((N + 127) // 128) <= 32:
-            # few output tiles, long K (fusion FFN linear2: 12 tiles x K = 2048): start from the
-            # bias and let the kernel split K over the idle SMs (atomic accumulate)
-            self.k.add(out, b.view(1, -1).expand(M, -1))
-            self.k.gemm_tc(0, 0, 0, M, N, K, xo, wo, out, mode=1, split_k=0)
+        if K >= 1024 and M * N <= 256 * 1024:
+            # 12 output tiles x K = 2048 (fusion FFN linear2) leave the persistent tensor-core GEMM
+            # on 12 SMs for 55 us; the exact-fp32 SIMT kernel with in-CTA split-K takes ~15
+            self.k.linear(x, w, b, out)
             return
+        xo, wo = self._prep(tag + "_x", x, kind=0), self._prep(tag + "_w", w, kind=0, split=True)
         self.k.gemm_tc(0, 0, 0, M, N, K, xo, wo, out, bias=b)
 
     def tc_linear_bwd(self, tag, dy, x, w, dw, db, dx, dx_acc):

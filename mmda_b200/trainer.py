@@ -366,7 +366,7 @@ class FusedTrainer:
         # the gradient arena (43 MB with a 20k-word embedding) is cleared on a side stream under
         # the forward instead of on the chain between the classifier and the losses
         zero_ev = None
-        if eng.multi_stream and not _engine._DRYRUN:
+        if eng.multi_stream and not _engine._DRYRUN and os.environ.get("MMDA_ZERO_SIDE", "1") != "0":
             cur = torch.cuda.current_stream()
             if not hasattr(self, "_zero_stream"):
                 self._zero_stream = torch.cuda.Stream(device=self.g_arena.device)

@@ -70,6 +70,15 @@ def test_sgemm_layouts(dev):
                 k.gemm(A, B, out, ta=ta, tb=tb, bias=bias)
                 ref = (A.double().t() if ta else A.double()) @ (B.double().t() if tb else B.double()) + bias.double()
                 C.add(f"gemm {M}x{N}x{K} ta={ta} tb={tb}", out, ref, 1e-5)
+                # deterministic in-CTA split-K: same answer, bit-identical run to run, beta / act
+                o1 = torch.full((M, N), 0.5, device=dev); o2 = o1.clone()
+                k.gemm(A, B, o1, ta=ta, tb=tb, bias=bias, beta=1.0, split_k=-1)
+                k.gemm(A, B, o2, ta=ta, tb=tb, bias=bias, beta=1.0, split_k=-1)
+                C.add(f"gemm in-CTA split-K {M}x{N}x{K} ta={ta} tb={tb}", o1, ref + 0.5, 1e-5)
+                assert torch.equal(o1, o2)
+                if K <= 64:     # fused activation (absolute check: sigmoid outputs are O(1))
+                    k.gemm(A, B, o2, ta=ta, tb=tb, bias=bias, act=2, split_k=-1)
+                    C.add(f"gemm in-CTA split-K sigmoid {M}x{N}x{K} ta={ta} tb={tb}", o2, torch.sigmoid(ref), 2e-6)
         # split-K accumulate
         A = torch.randn(K, M, generator=g).to(dev); B = torch.randn(K, N, generator=g).to(dev)
         acc = torch.randn(M, N, generator=g).to(dev); ref = acc.double() + A.double().t() @ B.double()
