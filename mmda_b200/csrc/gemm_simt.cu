@@ -327,6 +327,13 @@ extern "C" int mmda_sgemm(int transA, int transB, int M, int N, int K, float alp
     MMDA_CHECK_LAUNCH();
     beta = 1.f;
   }
+  // small tiles without an atomic split: the in-CTA split-K kernel (four K groups per tile, fixed
+  // summation order).  Measured 24.7 vs 63.7 us for the text projection (256 x 128 x 1200) and
+  // 10.6 vs 13.5 us for the 256 x 128 x 128 linears of the heads: a quarter of the k-steps per
+  // group, four times the warps per SM to hide the shared-memory latency behind.
+  if (cfg == 0 && split_k == 1 && K >= 64 && c_row_interleave == 0)
+    return launch_sgemm_ks(transA, transB, A, B, C, bias, bias2, M, N, K, lda, ldb, ldc, alpha, beta, act,
+                           stream);
   if (cfg == 2)
     return launch_sgemm<128, 128, 16, 8, 8>(transA, transB, A, B, C, bias, bias2, M, N, K, lda, ldb, ldc,
                                             alpha, beta, act, split_k, c_row_interleave, stream);

@@ -86,10 +86,7 @@ class Kernels:
                 split_k, c_ilv)
 
     def linear(self, x, w, b, out, act=ACT_NONE, bias2=None):
-        # long contraction into a small output (text projection 256 x 128 from K = 1200, fusion FFN
-        # linear2): deterministic in-CTA split-K instead of a K/32-step latency chain
-        ks = x.shape[1] >= 1024 and x.shape[0] * w.shape[0] <= 256 * 1024
-        self.gemm(x, w, out, tb=True, bias=b, bias2=bias2, act=act, split_k=-1 if ks else 0)
+        self.gemm(x, w, out, tb=True, bias=b, bias2=bias2, act=act)
 
     def leaf(self, fn):
         """Run fn() -- kernels whose results nothing later in the step's dependency chain reads
@@ -505,11 +502,6 @@ class MisaEngine:
         """out = x w^T + b on tcgen05 (3xTF32: fp32-accurate in either precision mode)."""
         M, K = x.shape
         N = w.shape[0]
-        if K >= 1024 and M * N <= 256 * 1024:
-            # 12 output tiles x K = 2048 (fusion FFN linear2) leave the persistent tensor-core GEMM
-            # on 12 SMs for 55 us; the exact-fp32 SIMT kernel with in-CTA split-K takes ~15
-            self.k.linear(x, w, b, out)
-            return
         xo, wo = self._prep(tag + "_x", x, kind=0), self._prep(tag + "_w", w, kind=0, split=True)
         self.k.gemm_tc(0, 0, 0, M, N, K, xo, wo, out, bias=b)
 
