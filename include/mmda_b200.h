@@ -222,6 +222,15 @@ int mmda_colsum(const float* x, int ld, int rows, int cols, float* out, float* o
  * index): nn.Dropout at src/models.py:126,152,160 */
 int mmda_dropout(const float* x, float* out, long long n, float p, unsigned long long seed,
                  const unsigned long long* seed_dev, unsigned stream_id, mmda_stream_t stream);
+/* x = dropout(act(x)) / dy = dropout'(dy) * act'(y), in place on contiguous tensors, one pass: the
+ * hidden activation of the fusion layer's FFN (nn.TransformerEncoderLayer: linear1 -> ReLU ->
+ * dropout, src/models.py:160).  y is the forward's stored output (after the dropout: a dropped
+ * element is 0, where ReLU' is 0 too).  Same dropout stream and indexing as mmda_dropout. */
+int mmda_act_dropout_forward(float* x, long long n, int act, float p, unsigned long long seed,
+                             const unsigned long long* seed_dev, unsigned stream_id, mmda_stream_t stream);
+int mmda_dropout_act_backward(float* dy, const float* y, long long n, int act, float p,
+                              unsigned long long seed, const unsigned long long* seed_dev,
+                              unsigned stream_id, mmda_stream_t stream);
 /* getBinaryTensor, src/utils/functions.py:112-115 */
 int mmda_threshold(const float* x, float* out, long long n, float thr, mmda_stream_t stream);
 
@@ -258,6 +267,11 @@ int mmda_loss_dxn(const float* XN, const float* Gm, float* DXN, int B, int d, fl
  * src/models.py:138-153,247-248 (Linear(6*hidden -> num_classes)). */
 int mmda_linear_skinny(const float* x, int ldx, const float* w, const float* bias, float* y, int ldy,
                        int M, int N, int K, int act, mmda_stream_t stream);
+/* two such heads over the same input in one launch (confidence + classifier, models.py:247-248):
+ * y1 = act1(x w1^T + b1) (N1 columns), y2 = act2(x w2^T + b2) (N2 columns), N1 + N2 <= 16 */
+int mmda_linear_skinny2(const float* x, int ldx, const float* w1, const float* b1, float* y1, int ldy1,
+                        int N1, int act1, const float* w2, const float* b2, float* y2, int ldy2, int N2,
+                        int act2, int M, int K, mmda_stream_t stream);
 /* use_cmd_sim=False: domain cross-entropy of the adversarial discriminator, src/solver.py:388-407.
  * domain_logits (3,B,3) = [pred_t; pred_v; pred_a]; writes the batch sum into segA[6d+6NC+3] (read by
  * mmda_loss_finalize(adversarial=1)) and d(loss)/d(logits) scaled by w_sim/(3*Bg). */

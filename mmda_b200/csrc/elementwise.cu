@@ -453,6 +453,29 @@ __global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ 
        i += (size_t)gridDim.x * blockDim.x)
     out[i] = rng_uniform(seed, stream, (uint32_t)i) >= p ? x[i] * scale : 0.f;
 }
+// x = dropout(act(x)) in place / dy = dropout'(dy) * act'(y) in place, for a contiguous tensor: the
+// fusion layer's FFN hidden activation (nn.TransformerEncoderLayer: linear1 -> ReLU -> dropout,
+// src/models.py:160) in one pass instead of two.  Same dropout stream / index as mmda_dropout.
+__global__ void act_dropout_fwd_kernel(float* __restrict__ x, size_t n, int act, float p, float scale,
+                                       unsigned long long seed,
+                                       const unsigned long long* __restrict__ seed_dev, unsigned stream) {
+  if (seed_dev) seed += seed_dev[0] * 0x9E3779B97F4A7C15ULL;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const float v = apply_act(x[i], act);
+    x[i] = (p > 0.f && rng_uniform(seed, stream, (uint32_t)i) < p) ? 0.f : v * scale;
+  }
+}
+__global__ void dropout_act_bwd_kernel(float* __restrict__ dy, const float* __restrict__ y, size_t n,
+                                       int act, float p, float scale, unsigned long long seed,
+                                       const unsigned long long* __restrict__ seed_dev, unsigned stream) {
+  if (seed_dev) seed += seed_dev[0] * 0x9E3779B97F4A7C15ULL;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const float d = (p > 0.f && rng_uniform(seed, stream, (uint32_t)i) < p) ? 0.f : dy[i] * scale;
+    dy[i] = d * act_grad_from_output(y[i], act);
+  }
+}
 __global__ void threshold_kernel(const float* __restrict__ x, float* __restrict__ out, size_t n,
                                  float thr) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
@@ -745,6 +768,27 @@ int mmda_dropout(const float* x, float* out, long long n, float p, unsigned long
   MMDA_REQUIRE(p >= 0.f && p < 1.f, "dropout: p=%f", p);
   dropout_kernel<<<ew_grid((size_t)n), 256, 0, stream>>>(x, out, (size_t)n, p, 1.f / (1.f - p),
                                                          seed, seed_dev, stream_id);
+  MMDA_CHECK_LAUNCH();
+  return MMDA_OK;
+}
+
+int mmda_act_dropout_forward(float* x, long long n, int act, float p, unsigned long long seed,
+                             const unsigned long long* seed_dev, unsigned stream_id, cudaStream_t stream) {
+  if (n <= 0) return MMDA_OK;
+  MMDA_REQUIRE(p >= 0.f && p < 1.f, "act_dropout: p=%f", p);
+  act_dropout_fwd_kernel<<<ew_grid((size_t)n), 256, 0, stream>>>(x, (size_t)n, act, p, 1.f / (1.f - p), seed,
+                                                                 seed_dev, stream_id);
+  MMDA_CHECK_LAUNCH();
+  return MMDA_OK;
+}
+
+int mmda_dropout_act_backward(float* dy, const float* y, long long n, int act, float p,
+                              unsigned long long seed, const unsigned long long* seed_dev,
+                              unsigned stream_id, cudaStream_t stream) {
+  if (n <= 0) return MMDA_OK;
+  MMDA_REQUIRE(p >= 0.f && p < 1.f, "dropout_act_backward: p=%f", p);
+  dropout_act_bwd_kernel<<<ew_grid((size_t)n), 256, 0, stream>>>(dy, y, (size_t)n, act, p, 1.f / (1.f - p),
+                                                                 seed, seed_dev, stream_id);
   MMDA_CHECK_LAUNCH();
   return MMDA_OK;
 }

@@ -763,11 +763,17 @@ class MisaEngine:
         ffn_tc = self._tc_lin_ok(rows, FF, d)
         if ffn_tc:
             self.tc_linear("ffn1", X1, P[TL + "linear1.weight"], P[TL + "linear1.bias"], F1)
-            k.act(F1, ACT_RELU)
+            if F1.is_contiguous():       # ReLU + dropout in one pass
+                k._c("mmda_act_dropout_forward", _ptr(F1), F1.numel(), ACT_RELU, p_att, seed,
+                     _ptr(seed_dev), 3)
+            else:
+                k.act(F1, ACT_RELU)
+                if p_att > 0:
+                    k.dropout(F1, F1, p_att, seed, 3, seed_dev)
         else:
             k.linear(X1, P[TL + "linear1.weight"], P[TL + "linear1.bias"], F1, act=ACT_RELU)
-        if p_att > 0:
-            k.dropout(F1, F1, p_att, seed, 3, seed_dev)
+            if p_att > 0:
+                k.dropout(F1, F1, p_att, seed, 3, seed_dev)
         if ffn_tc:
             self.tc_linear("ffn2", F1, P[TL + "linear2.weight"], P[TL + "linear2.bias"], F2)
         else:
@@ -788,15 +794,19 @@ class MisaEngine:
             else:
                 k.linear(Hf, P[w], P[b], out, act=act)
 
-        head("confidence.confidence_layer_1.weight", "confidence.confidence_layer_1.bias", TCP,
-             ACT_SIGMOID)
+        cw, cb = "confidence.confidence_layer_1.weight", "confidence.confidence_layer_1.bias"
+        sw, sb = "classifier.classifier_layer.weight", "classifier.classifier_layer.bias"
+        sc_act = ACT_NONE if p_cls > 0 else ACT_SIGMOID
+        if TCP.shape[1] + SC.shape[1] <= 16:      # both heads read the same row: one launch
+            k._c("mmda_linear_skinny2", _ptr(Hf), Hf.stride(0), _ptr(P[cw]), _ptr(P[cb]), _ptr(TCP),
+                 TCP.stride(0), TCP.shape[1], ACT_SIGMOID, _ptr(P[sw]), _ptr(P[sb]), _ptr(SC),
+                 SC.stride(0), SC.shape[1], sc_act, B, Hf.shape[1])
+        else:
+            head(cw, cb, TCP, ACT_SIGMOID)
+            head(sw, sb, SC, sc_act)
         if p_cls > 0:
-            head("classifier.classifier_layer.weight", "classifier.classifier_layer.bias", SC, ACT_NONE)
             k.dropout(SC, SC, p_cls, seed, 5, seed_dev)
             k.act(SC, ACT_SIGMOID)
-        else:
-            head("classifier.classifier_layer.weight", "classifier.classifier_layer.bias", SC,
-                 ACT_SIGMOID)
         k._c("mmda_threshold", _ptr(SC), _ptr(LAB), SC.numel(), float(cfg.threshold))
 
         for i, m in enumerate(MODS):
@@ -886,9 +896,13 @@ class MisaEngine:
             else:
                 k.linear_bwd(dF2, F1, P[TL + "linear2.weight"], G[TL + "linear2.weight"],
                              G[TL + "linear2.bias"], dF1, 0.0)
-            if p_att > 0:
-                k.dropout(dF1, dF1, p_att, seed, 3, seed_dev)
-            k.act_bwd(dF1, F1, ACT_RELU)
+            if dF1.is_contiguous() and F1.is_contiguous():      # dropout' + ReLU' in one pass
+                k._c("mmda_dropout_act_backward", _ptr(dF1), _ptr(F1), dF1.numel(), ACT_RELU, p_att,
+                     seed, _ptr(seed_dev), 3)
+            else:
+                if p_att > 0:
+                    k.dropout(dF1, dF1, p_att, seed, 3, seed_dev)
+                k.act_bwd(dF1, F1, ACT_RELU)
             # dX1 = dS2 + dF1 W1   (accumulate in place into dS2)
             if dF2 is dS2:
                 k.join_leaves()      # no dropout: dS2 is still being read as linear2's d(output)
