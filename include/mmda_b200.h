@@ -267,11 +267,6 @@ int mmda_loss_dxn(const float* XN, const float* Gm, float* DXN, int B, int d, fl
  * src/models.py:138-153,247-248 (Linear(6*hidden -> num_classes)). */
 int mmda_linear_skinny(const float* x, int ldx, const float* w, const float* bias, float* y, int ldy,
                        int M, int N, int K, int act, mmda_stream_t stream);
-/* two such heads over the same input in one launch (confidence + classifier, models.py:247-248):
- * y1 = act1(x w1^T + b1) (N1 columns), y2 = act2(x w2^T + b2) (N2 columns), N1 + N2 <= 16 */
-int mmda_linear_skinny2(const float* x, int ldx, const float* w1, const float* b1, float* y1, int ldy1,
-                        int N1, int act1, const float* w2, const float* b2, float* y2, int ldy2, int N2,
-                        int act2, int M, int K, mmda_stream_t stream);
 /* use_cmd_sim=False: domain cross-entropy of the adversarial discriminator, src/solver.py:388-407.
  * domain_logits (3,B,3) = [pred_t; pred_v; pred_a]; writes the batch sum into segA[6d+6NC+3] (read by
  * mmda_loss_finalize(adversarial=1)) and d(loss)/d(logits) scaled by w_sim/(3*Bg). */

@@ -602,25 +602,18 @@ __global__ void __launch_bounds__(256) linear_skinny_kernel(const float* __restr
                                                             const float* __restrict__ w,
                                                             const float* __restrict__ bias,
                                                             float* __restrict__ y, int ldy, int M,
-                                                            int N, int K, int act,
-                                                            const float* __restrict__ w2,
-                                                            const float* __restrict__ bias2,
-                                                            float* __restrict__ y2, int ldy2, int N2,
-                                                            int act2) {
-  // outputs [0, N) use (w, bias, y, act), outputs [N, N + N2) use (w2, bias2, y2, act2): the
-  // confidence and classifier heads read the same 768-wide row, so one launch serves both
+                                                            int N, int K, int act) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= M) return;
-  const int NT = N + N2;
   float acc[NMAX];
 #pragma unroll
   for (int n = 0; n < NMAX; ++n) acc[n] = 0.f;
   const float* xr = x + (size_t)row * ldx;
-  if ((K & 3) == 0 && (ldx & 3) == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0 &&
-      ((uintptr_t)w2 & 15) == 0) {
+  if ((K & 3) == 0 && (ldx & 3) == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0) {
     // 16-byte loads, 8 k-quads of the row in flight per lane
     const int K4 = K >> 2;
     const float4* x4 = reinterpret_cast<const float4*>(xr);
+    const float4* w4 = reinterpret_cast<const float4*>(w);
     for (int k0 = 0; k0 < K4; k0 += 32 * 8) {
       float4 xv[8];
 #pragma unroll
@@ -634,9 +627,8 @@ __global__ void __launch_bounds__(256) linear_skinny_kernel(const float* __restr
         if (k < K4) {
 #pragma unroll
           for (int n = 0; n < NMAX; ++n)
-            if (n < NT) {
-              const float4* w4 = reinterpret_cast<const float4*>(n < N ? w + (size_t)n * K : w2 + (size_t)(n - N) * K);
-              const float4 wv = __ldg(w4 + k);
+            if (n < N) {
+              const float4 wv = __ldg(w4 + (size_t)n * K4 + k);
               acc[n] = fmaf(xv[j].x, wv.x, fmaf(xv[j].y, wv.y, fmaf(xv[j].z, wv.z, fmaf(xv[j].w, wv.w, acc[n]))));
             }
         }
@@ -647,35 +639,20 @@ __global__ void __launch_bounds__(256) linear_skinny_kernel(const float* __restr
       const float xv = xr[k];
 #pragma unroll
       for (int n = 0; n < NMAX; ++n)
-        if (n < NT) acc[n] = fmaf(xv, __ldg((n < N ? w + (size_t)n * K : w2 + (size_t)(n - N) * K) + k), acc[n]);
+        if (n < N) acc[n] = fmaf(xv, __ldg(w + (size_t)n * K + k), acc[n]);
     }
   }
 #pragma unroll
   for (int n = 0; n < NMAX; ++n) {
     const float s = warp_sum(acc[n]);
-    if (lane == 0 && n < NT) {
-      if (n < N) y[(size_t)row * ldy + n] = apply_act(s + (bias ? bias[n] : 0.f), act);
-      else y2[(size_t)row * ldy2 + n - N] = apply_act(s + (bias2 ? bias2[n - N] : 0.f), act2);
-    }
+    if (n < N && lane == 0) y[(size_t)row * ldy + n] = apply_act(s + (bias ? bias[n] : 0.f), act);
   }
 }
 
 extern "C" int mmda_linear_skinny(const float* x, int ldx, const float* w, const float* bias, float* y,
                                   int ldy, int M, int N, int K, int act, cudaStream_t stream) {
   MMDA_REQUIRE(M > 0 && K > 0 && N >= 1 && N <= 8, "linear_skinny: M=%d N=%d K=%d (N <= 8)", M, N, K);
-  linear_skinny_kernel<8><<<(M + 7) / 8, 256, 0, stream>>>(x, ldx, w, bias, y, ldy, M, N, K, act, nullptr,
-                                                           nullptr, nullptr, 0, 0, 0);
-  MMDA_CHECK_LAUNCH();
-  return MMDA_OK;
-}
-
-extern "C" int mmda_linear_skinny2(const float* x, int ldx, const float* w1, const float* b1, float* y1,
-                                   int ldy1, int N1, int act1, const float* w2, const float* b2, float* y2,
-                                   int ldy2, int N2, int act2, int M, int K, cudaStream_t stream) {
-  MMDA_REQUIRE(M > 0 && K > 0 && N1 >= 1 && N2 >= 1 && N1 + N2 <= 16, "linear_skinny2: M=%d N=%d+%d K=%d",
-               M, N1, N2, K);
-  linear_skinny_kernel<16><<<(M + 7) / 8, 256, 0, stream>>>(x, ldx, w1, b1, y1, ldy1, M, N1, K, act1, w2, b2,
-                                                            y2, ldy2, N2, act2);
+  linear_skinny_kernel<8><<<(M + 7) / 8, 256, 0, stream>>>(x, ldx, w, bias, y, ldy, M, N, K, act);
   MMDA_CHECK_LAUNCH();
   return MMDA_OK;
 }

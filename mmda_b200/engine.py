@@ -797,13 +797,8 @@ class MisaEngine:
         cw, cb = "confidence.confidence_layer_1.weight", "confidence.confidence_layer_1.bias"
         sw, sb = "classifier.classifier_layer.weight", "classifier.classifier_layer.bias"
         sc_act = ACT_NONE if p_cls > 0 else ACT_SIGMOID
-        if TCP.shape[1] + SC.shape[1] <= 16:      # both heads read the same row: one launch
-            k._c("mmda_linear_skinny2", _ptr(Hf), Hf.stride(0), _ptr(P[cw]), _ptr(P[cb]), _ptr(TCP),
-                 TCP.stride(0), TCP.shape[1], ACT_SIGMOID, _ptr(P[sw]), _ptr(P[sb]), _ptr(SC),
-                 SC.stride(0), SC.shape[1], sc_act, B, Hf.shape[1])
-        else:
-            head(cw, cb, TCP, ACT_SIGMOID)
-            head(sw, sb, SC, sc_act)
+        head(cw, cb, TCP, ACT_SIGMOID)
+        head(sw, sb, SC, sc_act)
         if p_cls > 0:
             k.dropout(SC, SC, p_cls, seed, 5, seed_dev)
             k.act(SC, ACT_SIGMOID)
