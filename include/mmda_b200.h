@@ -247,16 +247,23 @@ int mmda_attention_backward(const float* qkv, const float* probs, const float* d
 
 /* ---- fused losses forward + backward, src/solver.py:163-181,373-462 (see csrc/loss.cu) ------
  * X0 (B,6,d) tokens [p_t,p_v,p_a,s_t,s_v,s_a]; O,R (3,B,d); scores,tcp,y (B,NC).
- * segA: 6*d + 6*NC + 4 floats; segB: 12*d + 6*d*d; segC: 6*d.  Bg = GLOBAL batch size. */
+ * segA: 6*d + 6*NC + 4 floats; segB: 12*d + 6*d*d; segC: 6*d.  Bg = GLOBAL batch size.
+ * The DiffLoss / CMD chain (src/solver.py:409-441) reads the six tokens only, which exist before
+ * the fusion layer runs: `roles` / `mode` let a caller run that part early, beside the fusion
+ * layer, and the rest once the model outputs exist.
+ * phase1 roles: bit 0 = token column sums (segA[0, 6d)), bit 1 = classification / confidence /
+ * reconstruction sums (segA[6d, ..)); 3 = both (O, R, scores, tcp, y unused and may be NULL for 1). */
 int mmda_loss_phase1(const float* X0, const float* O, const float* R, const float* scores,
-                     const float* tcp, const float* y, float* segA, int B, int d, int NC,
+                     const float* tcp, const float* y, float* segA, int B, int d, int NC, int roles,
                      mmda_stream_t stream);
 int mmda_loss_phase2(const float* X0, const float* segA, float* XN, float* inv_norm,
                      float* moments, int B, int d, float Bg, mmda_stream_t stream);
-/* losses[6] = {cls, diff, sim, recon, conf, total}; coef (3,5,d) */
+/* losses[6] = {cls, diff, sim, recon, conf, total}; coef (3,5,d).  mode bit 0: diff, sim (CMD) and
+ * coef from the token statistics; bit 1: cls, recon, conf and the total (diff / sim read back from
+ * losses[1], losses[2] when bit 0 ran in an earlier launch); 3 = everything. */
 int mmda_loss_finalize(const float* segA, const float* segB, float* losses, float* coef, int d,
                        int NC, float Bg, float w_diff, float w_sim, float w_recon, float w_conf,
-                       int adversarial, mmda_stream_t stream);
+                       int adversarial, int mode, mmda_stream_t stream);
 /* DiffLoss Gram matrices and their backward, batched over the six pairs of src/solver.py:432-439
  * (src/utils/functions.py:49-78): Gm[p] = XN[a_p]^T XN[b_p]  (XN [6][B][d], Gm [6][d][d]);
  * DXN[x] = alpha * (sum_{a_p = x} XN[b_p] Gm[p]^T + sum_{b_p = x} XN[a_p] Gm[p])  (overwrites). */

@@ -40,11 +40,14 @@ __global__ void __launch_bounds__(256)
 loss_phase1_kernel(const float* __restrict__ X0, const float* __restrict__ O,
                    const float* __restrict__ R, const float* __restrict__ scores,
                    const float* __restrict__ tcp, const float* __restrict__ y,
-                   float* __restrict__ segA, int B, int d, int NC) {
+                   float* __restrict__ segA, int B, int d, int NC, int roles) {
+  // roles bit 0: token column sums (need the six tokens only: available before the fusion layer
+  // runs); bit 1: classification / confidence / reconstruction sums (need the model outputs)
   __shared__ float red[8];
   const int blk = blockIdx.x, tid = threadIdx.x;
   float* colsum = segA;
   float* cls = segA + NTOK * d;
+  if (!(roles & (blk < NTOK ? 1 : 2))) return;      // block-uniform
   if (blk < NTOK) {
     for (int c = tid; c < d; c += 256) {
       float s = 0.f;
@@ -148,7 +151,10 @@ loss_phase2_kernel(const float* __restrict__ X0, const float* __restrict__ segA,
 __global__ void __launch_bounds__(1024)
 loss_finalize_kernel(const float* __restrict__ segA, const float* __restrict__ segB,
                      float* __restrict__ losses, float* __restrict__ coef, int d, int NC, float Bg,
-                     float w_diff, float w_sim, float w_recon, float w_conf, int adversarial) {
+                     float w_diff, float w_sim, float w_recon, float w_conf, int adversarial, int mode) {
+  // mode bit 0: the DiffLoss / CMD values and the CMD gradient coefficients (inputs: token
+  // statistics only); bit 1: the remaining losses and the total (diff / cmd are read back from
+  // `losses` when bit 0 ran in an earlier launch).
   // One CTA of 32 warps (the inputs are batch sums: nothing here scales with B).  The Gram
   // square-sum goes over all threads with 16-byte loads; the 15 CMD terms (3 pairs x 5 moment
   // orders) are one warp each; the CMD gradient coefficients are then one pass over
@@ -161,56 +167,63 @@ loss_finalize_kernel(const float* __restrict__ segA, const float* __restrict__ s
   const float* cls = segA + NTOK * d;
   const float* moments = segB;
   const float* G = segB + 3 * 4 * d;
-  // diff: sum of the squared entries of the six Gram matrices
-  float s = 0.f;
-  const size_t ng = (size_t)6 * d * d;
-  if ((ng & 3) == 0 && (reinterpret_cast<uintptr_t>(G) & 15) == 0) {
-    const float4* G4 = reinterpret_cast<const float4*>(G);
-    for (size_t i = tid; i < ng / 4; i += 1024) {
-      const float4 g = G4[i];
-      s = fmaf(g.x, g.x, fmaf(g.y, g.y, fmaf(g.z, g.z, fmaf(g.w, g.w, s))));
+  if (mode & 1) {
+    // diff: sum of the squared entries of the six Gram matrices
+    float s = 0.f;
+    const size_t ng = (size_t)6 * d * d;
+    if ((ng & 3) == 0 && (reinterpret_cast<uintptr_t>(G) & 15) == 0) {
+      const float4* G4 = reinterpret_cast<const float4*>(G);
+      for (size_t i = tid; i < ng / 4; i += 1024) {
+        const float4 g = G4[i];
+        s = fmaf(g.x, g.x, fmaf(g.y, g.y, fmaf(g.z, g.z, fmaf(g.w, g.w, s))));
+      }
+    } else {
+      for (size_t i = tid; i < ng; i += 1024) s = fmaf(G[i], G[i], s);
     }
-  } else {
-    for (size_t i = tid; i < ng; i += 1024) s = fmaf(G[i], G[i], s);
-  }
-  s = warp_sum(s);
-  if (lane == 0) red[warp] = s;
-  // cmd: warp w < 15 owns term (pair p = w / 5, order k = w % 5 + 1)
-  const int pa[3] = {0, 0, 2}, pb[3] = {1, 2, 1};
-  auto moment = [&](int tok, int k, int c) {   // k-th moment sum of shared token tok (3 + tok)
-    return k == 1 ? colsum[(3 + tok) * d + c] : moments[(tok * 4 + k - 2) * d + c];
-  };
-  if (warp < 15) {
-    const int p = warp / 5, k = warp % 5 + 1;
-    float part = 0.f;
-    for (int c = lane; c < d; c += 32) {
-      const float dl = (moment(pa[p], k, c) - moment(pb[p], k, c)) / Bg;
-      part = fmaf(dl, dl, part);
+    s = warp_sum(s);
+    if (lane == 0) red[warp] = s;
+    // cmd: warp w < 15 owns term (pair p = w / 5, order k = w % 5 + 1)
+    const int pa[3] = {0, 0, 2}, pb[3] = {1, 2, 1};
+    auto moment = [&](int tok, int k, int c) {   // k-th moment sum of shared token tok (3 + tok)
+      return k == 1 ? colsum[(3 + tok) * d + c] : moments[(tok * 4 + k - 2) * d + c];
+    };
+    if (warp < 15) {
+      const int p = warp / 5, k = warp % 5 + 1;
+      float part = 0.f;
+      for (int c = lane; c < d; c += 32) {
+        const float dl = (moment(pa[p], k, c) - moment(pb[p], k, c)) / Bg;
+        part = fmaf(dl, dl, part);
+      }
+      part = warp_sum(part);
+      if (lane == 0) nrm_s[warp] = sqrtf(part);
     }
-    part = warp_sum(part);
-    if (lane == 0) nrm_s[warp] = sqrtf(part);
-  }
-  __syncthreads();
-  // gradient coefficients: coef[tok][k-1][c] = sum over the pairs tok takes part in of
-  // +-((m_a - m_b) / Bg) / norm   (+ as the pair's first token, - as its second)
-  for (int i = tid; i < 3 * 5 * d; i += 1024) {
-    const int c = i % d, k = (i / d) % 5 + 1, tok = i / (5 * d);
-    float g = 0.f;
+    __syncthreads();
+    // gradient coefficients: coef[tok][k-1][c] = sum over the pairs tok takes part in of
+    // +-((m_a - m_b) / Bg) / norm   (+ as the pair's first token, - as its second)
+    for (int i = tid; i < 3 * 5 * d; i += 1024) {
+      const int c = i % d, k = (i / d) % 5 + 1, tok = i / (5 * d);
+      float g = 0.f;
 #pragma unroll
-    for (int p = 0; p < 3; ++p) {
-      if (pa[p] != tok && pb[p] != tok) continue;
-      const float v = ((moment(pa[p], k, c) - moment(pb[p], k, c)) / Bg) / nrm_s[p * 5 + k - 1];
-      g += pa[p] == tok ? v : -v;
+      for (int p = 0; p < 3; ++p) {
+        if (pa[p] != tok && pb[p] != tok) continue;
+        const float v = ((moment(pa[p], k, c) - moment(pb[p], k, c)) / Bg) / nrm_s[p * 5 + k - 1];
+        g += pa[p] == tok ? v : -v;
+      }
+      coef[i] = g;
     }
-    coef[i] = g;
   }
   if (tid == 0) {
-    float diff = 0.f;
-    for (int w = 0; w < 32; ++w) diff += red[w];
-    diff /= (float)d * (float)d;
-    float cmd = 0.f;
-    for (int t = 0; t < 15; ++t) cmd += nrm_s[t];
-    cmd /= 3.f;
+    float diff = losses[1], cmd = losses[2];
+    if (mode & 1) {
+      diff = 0.f;
+      for (int w = 0; w < 32; ++w) diff += red[w];
+      diff /= (float)d * (float)d;
+      cmd = 0.f;
+      for (int t = 0; t < 15; ++t) cmd += nrm_s[t];
+      cmd /= 3.f;
+      losses[1] = diff; losses[2] = cmd;
+    }
+    if (!(mode & 2)) return;
     float l_cls = 0.f, l_conf = 0.f;
     for (int c = 0; c < NC; ++c) {
       l_cls += cls[0 * NC + c] / Bg;
@@ -368,11 +381,12 @@ int mmda_loss_domain(const float* domain_logits, float* d_domain_logits, float* 
 }
 
 int mmda_loss_phase1(const float* X0, const float* O, const float* R, const float* scores,
-                     const float* tcp, const float* y, float* segA, int B, int d, int NC,
+                     const float* tcp, const float* y, float* segA, int B, int d, int NC, int roles,
                      cudaStream_t stream) {
+  MMDA_REQUIRE(roles >= 1 && roles <= 3, "loss_phase1: roles=%d", roles);
   MMDA_REQUIRE(NC >= 1 && NC <= 8, "loss: num_classes=%d (max 8)", NC);
   MMDA_REQUIRE(d >= 1 && d <= 32 * LOSS_MAXC, "loss: hidden_size=%d (max %d)", d, 32 * LOSS_MAXC);
-  loss_phase1_kernel<<<NTOK + 1 + 3, 256, 0, stream>>>(X0, O, R, scores, tcp, y, segA, B, d, NC);
+  loss_phase1_kernel<<<NTOK + 1 + 3, 256, 0, stream>>>(X0, O, R, scores, tcp, y, segA, B, d, NC, roles);
   MMDA_CHECK_LAUNCH();
   return MMDA_OK;
 }
@@ -390,9 +404,10 @@ int mmda_loss_phase2(const float* X0, const float* segA, float* XN, float* inv_n
 
 int mmda_loss_finalize(const float* segA, const float* segB, float* losses, float* coef, int d,
                        int NC, float Bg, float w_diff, float w_sim, float w_recon, float w_conf,
-                       int adversarial, cudaStream_t stream) {
+                       int adversarial, int mode, cudaStream_t stream) {
+  MMDA_REQUIRE(mode >= 1 && mode <= 3, "loss_finalize: mode=%d", mode);
   loss_finalize_kernel<<<1, 1024, 0, stream>>>(segA, segB, losses, coef, d, NC, Bg, w_diff, w_sim,
-                                              w_recon, w_conf, adversarial);
+                                              w_recon, w_conf, adversarial, mode);
   MMDA_CHECK_LAUNCH();
   return MMDA_OK;
 }

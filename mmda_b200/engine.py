@@ -616,7 +616,7 @@ class MisaEngine:
 
     def forward(self, sentences, visual, acoustic, lengths, train: bool, want_sp: bool = True,
                 dropout: Optional[bool] = None, seed_dev: Optional[torch.Tensor] = None,
-                utt_text: Optional[torch.Tensor] = None):
+                utt_text: Optional[torch.Tensor] = None, after_heads=None):
         """Returns a dict of device tensors (views into the workspace, valid until the next call).
         ``train`` keeps what the backward needs; ``dropout`` (default: = model.training) enables
         the five Bernoulli sites."""
@@ -706,6 +706,10 @@ class MisaEngine:
             return run
 
         self._fork({m: head_fwd(i, m) for i, m in enumerate(MODS)})
+        if after_heads is not None:
+            # the six tokens (X0) are complete: the fused trainer forks the token-only part of the
+            # losses (DiffLoss / CMD) from here, beside the fusion layer
+            after_heads()
         out = {}
         if self.adversarial:
             # models.py:219-227: domain_label_m = discriminator(GradReverse(utt_shared_m)); the

@@ -244,29 +244,44 @@ class FusedTrainer:
         coef = st[o:o + 15 * d]
         return st, segA, segB, segC, losses, coef
 
-    def loss_and_grads(self, out, labels, B):
-        """Fused losses forward + backward wrt the model outputs (csrc/loss.cu)."""
+    def _loss_early(self, B):
+        """DiffLoss / CMD chain on a side stream, forked right after the heads' forward (it reads
+        the six tokens only) so that it -- and, data-parallel, its three dependent statistics
+        all-reduces -- runs beside the fusion layer and the classifier instead of on the chain
+        behind them.  Returns the event the late part waits for."""
         eng, k = self.eng, self.eng.k
         d, NC, cfg = eng.d, eng.NC, self.cfg
         Bg = float(B * self.world) if self.global_stats else float(B)
         sync = self.global_stats and self.world > 1
         st, segA, segB, segC, losses, coef = self._loss_buffers(B)
-        st.zero_()
-        X0, O, R = out["tokens"], out["orig"], out["recon"]
-        SC, TCP = out["scores"], out["tcp"]
-        y = labels
-        w_conf = float(cfg.conf_weight) if self.use_confid else 0.0
-        k._c("mmda_loss_phase1", _ptr(X0), _ptr(O), _ptr(R), _ptr(SC), _ptr(TCP), _ptr(y),
-             _ptr(segA), B, d, NC)
+        X0 = eng.buf("X0", B, 6, d)
+        main = torch.cuda.current_stream()
+        if not hasattr(self, "_loss_stream"):
+            self._loss_stream = torch.cuda.Stream(device=self.g_arena.device)
+        s = self._loss_stream
+        ev0 = torch.cuda.Event()
+        ev0.record(main)
+        s.wait_event(ev0)
+        with torch.cuda.stream(s):
+            k.bind_stream()
+            st.zero_()
+            k._c("mmda_loss_phase1", _ptr(X0), None, None, None, None, None, _ptr(segA), B, d, NC, 1)
+            if sync:
+                self._allreduce(segA[:6 * d])
+            self._loss_tokens(X0, segA, segB, segC, losses, coef, B, Bg, sync, mode=1)
+            ev = torch.cuda.Event()
+            ev.record(s)
+        k.bind_stream()
+        return ev
+
+    def _loss_tokens(self, X0, segA, segB, segC, losses, coef, B, Bg, sync, mode):
+        """phase 2 .. 4b: centred / normalised tokens, moments, Grams, diff + CMD values and the
+        gradient wrt the tokens (dZ)"""
+        eng, k = self.eng, self.eng.k
+        d, NC, cfg = eng.d, eng.NC, self.cfg
         adv = eng.adversarial
         w_sim = 0.0 if adv else float(cfg.sim_weight)     # CMD part off in the adversarial variant
-        dDL = None
-        if adv:
-            dDL = eng.buf("dDL", 3, B, 3)
-            k._c("mmda_loss_domain", _ptr(out["domain"]), _ptr(dDL), _ptr(segA), B, d, NC, Bg,
-                 float(cfg.sim_weight))
-        if sync:
-            self._allreduce(segA)
+        w_conf = float(cfg.conf_weight) if self.use_confid else 0.0
         XN = eng.buf("XN", 6, B, d)
         inv = eng.buf("inv_norm", 6, B)
         k._c("mmda_loss_phase2", _ptr(X0), _ptr(segA), _ptr(XN), _ptr(inv), _ptr(segB), B, d, Bg)
@@ -276,7 +291,7 @@ class FusedTrainer:
             self._allreduce(segB)
         k._c("mmda_loss_finalize", _ptr(segA), _ptr(segB), _ptr(losses), _ptr(coef), d, NC, Bg,
              float(cfg.diff_weight), float(cfg.sim_weight), float(cfg.recon_weight), w_conf,
-             int(adv))
+             int(adv), mode)
         DXN = eng.buf("DXN", 6, B, d)
         alpha = float(cfg.diff_weight) * 2.0 / float(d * d)
         k._c("mmda_loss_dxn", _ptr(XN), _ptr(Gm), _ptr(DXN), B, d, alpha)
@@ -286,6 +301,45 @@ class FusedTrainer:
         dZ = eng.buf("dZ", B, 6, d)
         k._c("mmda_loss_phase4b", _ptr(X0), _ptr(DXN), _ptr(segA), _ptr(segB), _ptr(segC),
              _ptr(coef), _ptr(dZ), B, d, Bg, w_sim, 0)
+        return dZ
+
+    def loss_and_grads(self, out, labels, B, early_ev=None):
+        """Fused losses forward + backward wrt the model outputs (csrc/loss.cu).  ``early_ev``:
+        the token-only part already ran (`_loss_early`); wait for it and do the rest."""
+        eng, k = self.eng, self.eng.k
+        d, NC, cfg = eng.d, eng.NC, self.cfg
+        Bg = float(B * self.world) if self.global_stats else float(B)
+        sync = self.global_stats and self.world > 1
+        st, segA, segB, segC, losses, coef = self._loss_buffers(B)
+        X0, O, R = out["tokens"], out["orig"], out["recon"]
+        SC, TCP = out["scores"], out["tcp"]
+        y = labels
+        w_conf = float(cfg.conf_weight) if self.use_confid else 0.0
+        adv = eng.adversarial
+        if early_ev is None:
+            st.zero_()
+            k._c("mmda_loss_phase1", _ptr(X0), _ptr(O), _ptr(R), _ptr(SC), _ptr(TCP), _ptr(y),
+                 _ptr(segA), B, d, NC, 3)
+        else:
+            torch.cuda.current_stream().wait_event(early_ev)
+            k._c("mmda_loss_phase1", _ptr(X0), _ptr(O), _ptr(R), _ptr(SC), _ptr(TCP), _ptr(y),
+                 _ptr(segA), B, d, NC, 2)
+        dDL = None
+        if adv:
+            dDL = eng.buf("dDL", 3, B, 3)
+            k._c("mmda_loss_domain", _ptr(out["domain"]), _ptr(dDL), _ptr(segA), B, d, NC, Bg,
+                 float(cfg.sim_weight))
+        if early_ev is None:
+            if sync:
+                self._allreduce(segA)
+            dZ = self._loss_tokens(X0, segA, segB, segC, losses, coef, B, Bg, sync, mode=3)
+        else:
+            if sync:
+                self._allreduce(segA[6 * d:])
+            k._c("mmda_loss_finalize", _ptr(segA), _ptr(segB), _ptr(losses), _ptr(coef), d, NC, Bg,
+                 float(cfg.diff_weight), float(cfg.sim_weight), float(cfg.recon_weight), w_conf,
+                 int(adv), 2)
+            dZ = eng.buf("dZ", B, 6, d)
         dSC, dTCP = eng.buf("dSCORES", B, NC), eng.buf("dTCP", B, NC)
         dR, dO = eng.buf("dR", 3, B, d), eng.buf("dOrig", 3, B, d)
         k._c("mmda_loss_grad_misc", _ptr(SC), _ptr(TCP), _ptr(y), _ptr(O), _ptr(R), _ptr(segA),
@@ -377,8 +431,13 @@ class FusedTrainer:
                 self.g_arena[:self.n_active].zero_()
                 zero_ev = torch.cuda.Event()
                 zero_ev.record(self._zero_stream)
+        early = {}
+        hook = None
+        if eng.multi_stream and not _engine._DRYRUN and os.environ.get("MMDA_LOSS_EARLY", "1") != "0":
+            def hook():
+                early["ev"] = self._loss_early(int(lengths.numel()))
         out = eng.forward(sentences, visual, acoustic, lengths, train=True, want_sp=False,
-                          seed_dev=self.state, utt_text=utt_text)
+                          seed_dev=self.state, utt_text=utt_text, after_heads=hook)
         B = out["scores"].shape[0]
         if labels.shape != (B, eng.NC) or labels.dtype != torch.float32 or \
                 not (labels.is_cuda or _engine._DRYRUN):
@@ -387,7 +446,7 @@ class FusedTrainer:
             torch.cuda.current_stream().wait_event(zero_ev)
         else:
             self.g_arena[:self.n_active].zero_()
-        losses, grads = self.loss_and_grads(out, labels.contiguous(), B)
+        losses, grads = self.loss_and_grads(out, labels.contiguous(), B, early_ev=early.get("ev"))
         self._pending = []
         self._reduced = set()
         self._bert_done = False
