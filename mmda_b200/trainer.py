@@ -32,6 +32,13 @@ MAX_GRAPHS = 24    # live step graphs per trainer before the cache is flushed
 N_BUCKETS = 7      # gradient buckets 0..6 (all-reduced); N_BUCKETS = parameters without a gradient
 
 
+def padded_rows(n_rows: int, batch: int, t_pad: int, granule: int = 0) -> int:
+    """Launch row count of a captured step for a batch with ``n_rows`` = sum(lengths) packed rows:
+    rounded up to the row granule, capped at batch * t_pad (pure function, CPU-tested)."""
+    g = granule or ROW_GRANULE
+    return min(batch * t_pad, -(-n_rows // g) * g)
+
+
 def bucket_of(name: str) -> int:
     """Gradient-ready order of the backward (engine.backward): 0 fusion+classifier, 1 heads,
     2 visual encoder, 3 acoustic encoder, 4 text rnn2, 5 text LayerNorm + rnn1, 6 embedding (+ the
@@ -500,7 +507,7 @@ class FusedTrainer:
         T, B = int(sentences.shape[0]), int(sentences.shape[1])
         N = int(lengths.sum())
         cap = B * T
-        Np = min(cap, -(-N // ROW_GRANULE) * ROW_GRANULE)
+        Np = padded_rows(N, B, T)
         if visual.shape[0] != T or acoustic.shape[0] != T or int(lengths.max()) > T:
             return self._eager_step(sentences, visual, acoustic, lengths, labels)
         key = (tuple(sentences.shape), tuple(visual.shape), tuple(acoustic.shape), Np, N == Np,

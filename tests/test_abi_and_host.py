@@ -229,3 +229,24 @@ def test_bert_branch_kernel_sequence_and_freeze_contract(dryrun):
         < seq.index("mmda_bert_embed_backward") < seq.index("mmda_adam_clip_step")
     with pytest.raises(MmdaError):
         tr.step(b.sentences, b.visual, b.acoustic, b.lengths, b.labels)     # bert inputs missing
+
+
+def test_padded_row_buckets():
+    """Row count a captured step is launched with (FusedTrainer.step): never below the real count,
+    at most one granule above it, capped at B*T, and equal to it for full-length batches."""
+    from mmda_b200.trainer import padded_rows, ROW_GRANULE
+    assert ROW_GRANULE == 512
+    assert padded_rows(12800, 256, 50) == 12800                  # full lengths: exact
+    assert padded_rows(6500, 256, 50) == 6656
+    assert padded_rows(6656, 256, 50) == 6656
+    assert padded_rows(12799, 256, 50) == 12800                  # cap
+    assert padded_rows(90, 8, 12) == 96                          # small batches: one bucket = the cap
+    assert padded_rows(1, 8, 12, granule=4) == 4
+    import random
+    rnd = random.Random(0)
+    for _ in range(200):
+        B, T = rnd.randint(1, 300), rnd.randint(1, 60)
+        n = rnd.randint(B, B * T)
+        p = padded_rows(n, B, T)
+        assert n <= p <= B * T and p - n < ROW_GRANULE
+        assert p == B * T or p % ROW_GRANULE == 0
