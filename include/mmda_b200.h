@@ -8,7 +8,8 @@
  * Conventions
  *   - every function returns 0 on success or a negative code (MMDA_ERR_*); nothing throws;
  *     mmda_last_error() returns a thread-local message for the last failure on this thread;
- *   - all buffers are caller-owned DEVICE pointers; no hidden allocation, no hidden sync;
+ *   - all buffers are caller-owned DEVICE pointers; no hidden sync, and no hidden allocation except
+ *     the 256 KB of GEMM scheduler slots per device (see mmda_ctx_info);
  *   - every launch takes an explicit cudaStream_t (passed as void*-sized handle);
  *   - matrices are row-major fp32 with an explicit leading dimension (elements);
  *   - packed-sequence layout: token (t, sorted position j) lives at row offsets[t] + j, i.e.
@@ -39,6 +40,17 @@ const char* mmda_last_error(void);
 int mmda_abi_version(void);
 /* out5 = {SM count, max opt-in smem per block, cc major, cc minor, L2 bytes} */
 int mmda_device_info(int* out5);
+/* Per-(process, device) context.  The reference keeps no device state of its own
+ * (torch's allocator and handles do, behind `.to(device)`, src/solver.py:94); this library keeps
+ * exactly one small context per device ordinal -- cached attributes, the occupancy probe of the
+ * clustered recurrence kernel, and the tile-scheduler slots of the persistent tensor-core GEMM
+ * (256 KB of device memory, allocated by the first tensor-core GEMM on that device: the one
+ * allocation the library makes itself).  It is selected implicitly by the calling thread's current
+ * device, so a process that drives several GPUs (one thread or one torch.cuda.device scope per
+ * GPU) never shares state between them.  out6 = {device ordinal, SM count, max opt-in smem per
+ * block, co-resident 8-CTA clusters (0 until a plan probed it), scheduler slots allocated (0/1),
+ * scheduler slots held by captured graphs}. */
+int mmda_ctx_info(int* out6);
 
 /* ---- packing: pack_padded_sequence(enforce_sorted=False), src/models.py:164,173 -------------
  * lens_sorted: lengths after the host's descending torch.sort (device int32, B entries).

@@ -14,6 +14,24 @@
 void mmda_set_error(const char* fmt, ...);
 int mmda_cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
+// ---- per-(process, device) context -------------------------------------------
+// Everything the host side caches about ONE device: attributes, occupancy probes and the tensor-
+// core GEMM's tile-scheduler slots (the library's only device allocation, 256 KB per device).  A
+// process that drives several GPUs gets one context per device, selected by the calling thread's
+// current device; a context is not shared between threads that launch concurrently.
+struct MmdaDeviceCtx {
+  int device;             // ordinal this context belongs to (-1: not initialised yet)
+  int sm_count;
+  int max_smem_optin;     // cudaDevAttrMaxSharedMemoryPerBlockOptin
+  int max_clusters8;      // co-resident 8-CTA clusters of the SIMT recurrence kernel (0 = not probed)
+  int* sched;             // tile-scheduler slots of the persistent tcgen05 GEMM (device memory)
+  int sched_next;         // ring cursor of the eager launches
+  int sched_graph_next;   // slots handed to launches recorded into CUDA graphs
+};
+// Context of the calling thread's current device (created on first use); nullptr + error message on
+// a CUDA failure.
+MmdaDeviceCtx* mmda_device_ctx();
+
 #define MMDA_CUDA(expr)                                                          \
   do {                                                                           \
     cudaError_t _e = (expr);                                                     \

@@ -782,44 +782,42 @@ int encode_map(CUtensorMap* map, int kind, const void* ptr, long rows, long cols
   return MMDA_OK;
 }
 
-int g_tc_version = 2;          // 2 = persistent kernel (default), 1 = one tile per CTA
-int* g_sched = nullptr;        // ring of self-resetting scheduler slots (2 ints each)
-int g_sched_next = 0;
-// Scheduler slots: eager launches rotate through a ring (a slot is re-armed by its own kernel, and
-// 4096 launches never overlap in flight); launches recorded into a CUDA graph get slots of their
-// own that are never handed out again, because a graph may be replayed at any later time next to
-// eager launches on other streams.
+int g_tc_version = 2;          // 2 = persistent kernel (default), 1 = one tile per CTA (process-wide A/B knob)
+// Scheduler slots (2 ints each, self-resetting) live in the per-device context (common.cuh): eager
+// launches rotate through a ring (a slot is re-armed by its own kernel, and 4096 launches never
+// overlap in flight); launches recorded into a CUDA graph get slots of their own that are only
+// handed out again once the owner of the graphs gives them back (mmda_gemm_tc_graph_slots),
+// because a graph may be replayed at any later time next to eager launches on other streams.
 constexpr int SCHED_RING = 4096, SCHED_GRAPH = 28672, SCHED_SLOTS = SCHED_RING + SCHED_GRAPH;
-int g_sched_graph_next = 0;
 
-int* next_sched_slot(cudaStream_t stream) {
+int* next_sched_slot(MmdaDeviceCtx* ctx, cudaStream_t stream) {
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess) {
     cudaGetLastError();
     cap = cudaStreamCaptureStatusNone;
   }
-  if (g_sched == nullptr) {
+  if (ctx->sched == nullptr) {
     if (cap != cudaStreamCaptureStatusNone) {
       mmda_set_error("gemm_tc: first use inside a CUDA graph capture (run one eager step first)");
       return nullptr;
     }
-    if (cudaMalloc(&g_sched, SCHED_SLOTS * 2 * sizeof(int)) != cudaSuccess ||
-        cudaMemset(g_sched, 0, SCHED_SLOTS * 2 * sizeof(int)) != cudaSuccess) {
+    if (cudaMalloc(&ctx->sched, SCHED_SLOTS * 2 * sizeof(int)) != cudaSuccess ||
+        cudaMemset(ctx->sched, 0, SCHED_SLOTS * 2 * sizeof(int)) != cudaSuccess) {
       cudaGetLastError();
-      g_sched = nullptr;
+      ctx->sched = nullptr;
       mmda_set_error("gemm_tc: cannot allocate the tile scheduler slots");
       return nullptr;
     }
   }
   if (cap != cudaStreamCaptureStatusNone) {
-    if (g_sched_graph_next >= SCHED_GRAPH) {
+    if (ctx->sched_graph_next >= SCHED_GRAPH) {
       mmda_set_error("gemm_tc: out of scheduler slots for captured launches (%d used)", SCHED_GRAPH);
       return nullptr;
     }
-    return g_sched + 2 * (SCHED_RING + g_sched_graph_next++);
+    return ctx->sched + 2 * (SCHED_RING + ctx->sched_graph_next++);
   }
-  int* slot = g_sched + 2 * g_sched_next;
-  g_sched_next = (g_sched_next + 1) % SCHED_RING;
+  int* slot = ctx->sched + 2 * ctx->sched_next;
+  ctx->sched_next = (ctx->sched_next + 1) % SCHED_RING;
   return slot;
 }
 
@@ -831,8 +829,10 @@ extern "C" {
 // release_to >= 0 the slots [release_to, in use) are handed back first -- the caller guarantees that
 // every graph recorded since its mark (= the value returned before its capture) is destroyed.
 int mmda_gemm_tc_graph_slots(int release_to) {
-  if (release_to >= 0 && release_to <= g_sched_graph_next) g_sched_graph_next = release_to;
-  return g_sched_graph_next;
+  MmdaDeviceCtx* ctx = mmda_device_ctx();     // the calling thread's current device
+  if (ctx == nullptr) return MMDA_ERR_CUDA;
+  if (release_to >= 0 && release_to <= ctx->sched_graph_next) ctx->sched_graph_next = release_to;
+  return ctx->sched_graph_next;
 }
 
 // A/B knob: 2 = persistent tile loop with overlapped epilogue (default), 1 = one tile per CTA
@@ -941,14 +941,11 @@ int mmda_gemm_tc(int kind, int a_mn, int b_mn, int M, int N, int K, const void* 
     a2.a = a;
     a2.tiles_m = (M + BM - 1) / BM; a2.tiles_n = (N + BN - 1) / BN; a2.split = split_k;
     a2.total = a2.tiles_m * a2.tiles_n * split_k;
-    a2.sched = next_sched_slot(stream);
+    MmdaDeviceCtx* ctx = mmda_device_ctx();
+    if (ctx == nullptr) return MMDA_ERR_CUDA;
+    a2.sched = next_sched_slot(ctx, stream);
     if (a2.sched == nullptr) return MMDA_ERR_CUDA;
-    static int n_sm = 0;
-    if (n_sm == 0) {
-      int dev = 0;
-      MMDA_CUDA(cudaGetDevice(&dev));
-      MMDA_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    }
+    const int n_sm = ctx->sm_count;
     const int ctas = a2.total < n_sm ? a2.total : n_sm;
     constexpr int smem2 = 12 * TILE_BYTES + 1024 + 512 + 4 * 32 * 33 * 4;
     if (kind == 0 && raw_mode == 1) {

@@ -604,10 +604,10 @@ struct LstmPlan {
   size_t smem_fwd, smem_bwd, scratch_bytes;
 };
 
-static int g_max_smem = 0;
+// process-wide A/B knob; everything device-dependent (opt-in shared memory, co-resident 8-CTA
+// clusters of the big-H kernel -- B200: 15) lives in the per-device context (common.cuh)
 static int g_small_bt = 32; // batch tile of the small-H plan for B >= 64: few large CTAs leave the SMs next to the
                             // text recurrence to the weight-gradient GEMMs (7.65 -> 7.59 ms); 8 = many small CTAs
-static int g_max_clusters8 = 0;   // co-resident 8-CTA clusters of the big-H kernel (B200: 15)
 
 template <int BT> static int probe_clusters8(int threads, size_t smem) {
   auto kern = lstm_fwd_kernel<BT, 0>;
@@ -627,13 +627,9 @@ template <int BT> static int probe_clusters8(int threads, size_t smem) {
 }
 
 static int lstm_make_plan(int B, int H, int Tmax, LstmPlan* pl) {
-  if (g_max_smem == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return MMDA_ERR_CUDA;
-    if (cudaDeviceGetAttribute(&g_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) !=
-        cudaSuccess)
-      return MMDA_ERR_CUDA;
-  }
+  MmdaDeviceCtx* ctx = mmda_device_ctx();
+  if (ctx == nullptr) return MMDA_ERR_CUDA;
+  const size_t max_smem = (size_t)ctx->max_smem_optin;
   const int Kpad = (H + 3) & ~3;
   // batch tile: large hidden sizes are shared-memory bound (W slice + h tile must fit), small
   // ones want many CTAs
@@ -650,7 +646,7 @@ static int lstm_make_plan(int B, int H, int Tmax, LstmPlan* pl) {
       const int HR = C * Hs > Kpad ? C * Hs : Kpad;
       const size_t fwd = (size_t)4 * Kpad * Hs * 4 + (size_t)HR * BTP * 4 + misc;
       const size_t bwd = (size_t)R * Kpad * 4 + (size_t)R * BTP * 4 + misc + (size_t)(Tmax + 1) * 4;
-      if (fwd > (size_t)g_max_smem || bwd > (size_t)g_max_smem) continue;
+      if (fwd > max_smem || bwd > max_smem) continue;
       const int UG = (Hs + 7) / 8, BG = BT / 8, K4 = Kpad / 4;
       const int KG = (K4 + KS - 1) / KS;
       const int wf = UG * BG, wb = (UG > KG ? UG : KG) * BG;
@@ -658,9 +654,9 @@ static int lstm_make_plan(int B, int H, int Tmax, LstmPlan* pl) {
       if (BT == 40) {
         // the 40-row tile only pays when it lets the whole batch run as ONE wave of clusters
         // (B200 co-schedules 15 clusters of 8 CTAs; 2 directions x ceil(B/32) tiles may not fit)
-        if (C == 8 && g_max_clusters8 == 0) g_max_clusters8 = probe_clusters8<40>(wf * 32, fwd);
+        if (C == 8 && ctx->max_clusters8 == 0) ctx->max_clusters8 = probe_clusters8<40>(wf * 32, fwd);
         const int t32 = (B + 31) / 32, t40 = (B + 39) / 40;
-        const int cap = C == 8 ? g_max_clusters8 : 1 << 30;
+        const int cap = C == 8 ? ctx->max_clusters8 : 1 << 30;
         const int waves32 = (2 * t32 + cap - 1) / cap, waves40 = (2 * t40 + cap - 1) / cap;
         if (cap <= 0 || waves40 * 40 >= waves32 * 32) continue;   // no gain: try BT = 32
       }
