@@ -164,6 +164,7 @@ class FusedTrainer:
         self._pending = []
         self._reduced = set()
         self._defer_ready = None
+        self._equal_B = None            # local batch size last verified equal on every rank
         self.trace_ready = None         # profiling aid: {tag: timed event} of the last step
         # device-resident step state (step counter = dropout seed offset, Adam bias corrections)
         self.state = torch.zeros(4, dtype=torch.float64, device=self.p_arena.device)
@@ -235,6 +236,22 @@ class FusedTrainer:
             return self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.pg,
                                         async_op=async_op)
         return None
+
+    def _check_equal_batch(self, B):
+        """Data parallel only: the loss normalisers (``Bg = B * world``) and the DDP-style gradient
+        average assume that every rank holds the same number of samples.  Verified with one tiny
+        MAX all-reduce whenever the local batch size changes (first step, a short last batch) --
+        never inside a graph capture -- so that a ragged last shard raises on every rank instead of
+        silently skewing the means, CMD moments and DiffLoss Grams."""
+        if self.world == 1 or B == self._equal_B:
+            return
+        t = torch.tensor([B, -B], dtype=torch.int64, device=self.p_arena.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.pg)
+        hi, lo = int(t[0]), -int(t[1])
+        if hi != lo:
+            raise MmdaError(f"data-parallel step with unequal local batches ({lo}..{hi} samples per "
+                            "rank): shard the global batch evenly (drop or pad the last partial batch)")
+        self._equal_B = B
 
     # ------------------------------------------------------------------ losses -------------
     def _loss_buffers(self, B):
@@ -414,6 +431,7 @@ class FusedTrainer:
         tensor of the six loss values [cls, diff, sim, recon, conf, total].  ``bert`` =
         (bert_sent, bert_sent_type, bert_sent_mask) when ``config.use_bert``."""
         self._check_alias()
+        self._check_equal_batch(int(lengths.numel()))
         eng = self.eng
         eng.k.bind_stream()
         eng.k._c("mmda_step_state_advance", _ptr(self.state), self.lr, 0.9, 0.999)
@@ -492,6 +510,7 @@ class FusedTrainer:
         """One optimisation step.  With ``use_graph`` (default on one GPU) the kernel sequence of
         a repeated (shapes, lengths) pattern is captured once into a CUDA graph -- multi-stream
         forks included -- and replayed; per-step scalars live in ``self.state`` on the device."""
+        self._check_equal_batch(int(lengths.numel()))     # before any capture: it reads a value back
         if self.use_bert:       # long step (12 transformer layers): launch overhead is noise
             return self._eager_step(sentences, visual, acoustic, lengths, labels,
                                     (bert_sent, bert_sent_type, bert_sent_mask))

@@ -89,7 +89,35 @@ def _worker_buckets(rank, world, port, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("worker", [_worker_loss, _worker_buckets])
+def _worker_unequal(rank, world, port, q):
+    """ranks with different local batch sizes: every rank raises (no deadlock, no skewed means)"""
+    _init(rank, world, port)
+    import mmda_b200.engine as E
+    from mmda_b200._lib import LIB, MmdaError
+    E._DRYRUN = True
+    LIB.call = lambda name, *a: 0
+    LIB.raw = lambda name: (lambda *a: 4096)
+    from mmda_b200 import MISA, mosei_config
+    from mmda_b200.trainer import FusedTrainer
+    from mmda_b200.synthetic import batch_for
+    torch.manual_seed(0)
+    model = MISA(mosei_config(vocab_size=40))
+    tr = FusedTrainer(model, process_group=dist.group.WORLD)
+    b = batch_for(model.config, seed=rank, lengths="ragged", batch=8 - 2 * rank, seq_len=5)
+    try:
+        tr.step(b.sentences, b.visual, b.acoustic, b.lengths, b.labels)
+        ok = False
+    except MmdaError as e:
+        ok = "unequal local batches (6..8" in str(e)
+    # equal batches afterwards: the step goes through and the size is remembered
+    b = batch_for(model.config, seed=rank, lengths="ragged", batch=8, seq_len=5)
+    tr.step(b.sentences, b.visual, b.acoustic, b.lengths, b.labels)
+    ok = ok and tr._equal_B == 8
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("worker", [_worker_loss, _worker_buckets, _worker_unequal])
 def test_world2_gloo(worker):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
