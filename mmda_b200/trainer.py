@@ -495,6 +495,75 @@ class FusedTrainer:
              _ptr(self.v), self.n_active, self.step_count, self.lr, self.clip, 0.9, 0.999, 1e-8,
              self._grad_scale(), _ptr(self.state))
 
+    # -- checkpoint interop: the reference saves / reloads ``optimizer.state_dict()`` next to the
+    # model's (src/solver.py:219-220, :238-239); the fused step owns the Adam moments, so it speaks
+    # torch.optim.Adam's format in both directions ------------------------------------------------
+    def _adam_params(self):
+        """[(index, name, parameter)] in the order ``Adam(filter(requires_grad, parameters()))``
+        (src/solver.py:97-99) numbers them"""
+        return [(i, n, p) for i, (n, p) in enumerate(
+            (n, p) for n, p in self.model.named_parameters() if p.requires_grad)]
+
+    def optimizer_state_dict(self):
+        """The Adam state in ``torch.optim.Adam.state_dict()`` layout: loadable by the reference's
+        optimizer (``self.optimizer.load_state_dict``) built over the same model.  Parameters that
+        never received a gradient (``grad=None`` in the reference: Adam keeps no state for them)
+        have no entry, exactly as torch leaves them."""
+        params = self._adam_params()
+        state = {}
+        if self.step_count > 0:
+            for i, n, p in params:
+                off, sz = self.layout[n]
+                if off >= self.n_active:
+                    continue
+                state[i] = {"step": torch.tensor(float(self.step_count)),
+                            "exp_avg": self.m[off:off + sz].view(p.shape).clone(),
+                            "exp_avg_sq": self.v[off:off + sz].view(p.shape).clone()}
+        group = {"lr": self.lr, "betas": (0.9, 0.999), "eps": 1e-8, "weight_decay": 0,
+                 "amsgrad": False, "maximize": False, "foreach": None, "capturable": False,
+                 "differentiable": False, "fused": None, "decoupled_weight_decay": False,
+                 "params": [i for i, _, _ in params]}
+        return {"state": state, "param_groups": [group]}
+
+    def load_optimizer_state_dict(self, sd):
+        """Inverse of ``optimizer_state_dict``; also accepts a checkpoint written by the
+        reference's ``torch.optim.Adam`` (``checkpoints/optim_*.std``).  Restores the moments, the
+        step count (bias corrections, dropout stream) and the learning rate."""
+        groups = sd["param_groups"]
+        if len(groups) != 1:
+            raise MmdaError("optimizer state with %d param groups (the reference uses one)" % len(groups))
+        g = groups[0]
+        if tuple(g.get("betas", (0.9, 0.999))) != (0.9, 0.999) or float(g.get("eps", 1e-8)) != 1e-8 \
+                or g.get("weight_decay", 0) or g.get("amsgrad", False):
+            raise MmdaError("only Adam(betas=(0.9, 0.999), eps=1e-8, weight_decay=0) is implemented "
+                            "(src/solver.py:97-99 with config.optimizer = Adam)")
+        params = self._adam_params()
+        if len(g["params"]) != len(params):
+            raise MmdaError(f"optimizer state covers {len(g['params'])} parameters, the model has "
+                            f"{len(params)} trainable ones")
+        pos = {pid: j for j, pid in enumerate(g["params"])}     # saved id -> position in the group
+        self.m.zero_()
+        self.v.zero_()
+        steps = set()
+        for pid, st in sd["state"].items():
+            _, n, p = params[pos[pid]]
+            off, sz = self.layout[n]
+            if tuple(st["exp_avg"].shape) != tuple(p.shape):
+                raise MmdaError(f"optimizer state of {n}: shape {tuple(st['exp_avg'].shape)} != {tuple(p.shape)}")
+            if off >= self.n_active:
+                raise MmdaError(f"optimizer state for {n}, which this variant never differentiates")
+            self.m[off:off + sz].view(p.shape).copy_(st["exp_avg"])
+            self.v[off:off + sz].view(p.shape).copy_(st["exp_avg_sq"])
+            steps.add(int(st["step"]))
+        if len(steps) > 1:
+            raise MmdaError(f"parameters at different Adam steps {sorted(steps)}: one fused step count only")
+        self.step_count = steps.pop() if steps else 0
+        self.lr = float(g["lr"])
+        if not _engine._DRYRUN:
+            self.eng.k.bind_stream()
+        self.eng.k._c("mmda_step_state_init", _ptr(self.state), self.step_count, 0.9, 0.999)
+        self._drop_graph()       # the learning rate is a captured scalar
+
     def _grad_scale(self):
         """Per-shard losses (global_batch_stats=False) are normalised by the LOCAL batch, so the
         summed gradients are world x the data-parallel average (DDP semantics: divide)."""

@@ -250,3 +250,55 @@ def test_padded_row_buckets():
         p = padded_rows(n, B, T)
         assert n <= p <= B * T and p - n < ROW_GRANULE
         assert p == B * T or p % ROW_GRANULE == 0
+
+
+def test_optimizer_state_dict_round_trips_with_torch_adam(dryrun):
+    """S1 boundary (src/solver.py:97-99, :219-220): the fused step's Adam state is written / read in
+    torch.optim.Adam's own state_dict layout, in both directions."""
+    from mmda_b200.trainer import FusedTrainer
+    from mmda_b200._lib import MmdaError
+    cfg = mosei_config(vocab_size=60, batch_size=4)
+    torch.manual_seed(0)
+    model = MISA(cfg)
+    tr = FusedTrainer(model, lr=3e-4)
+    skip = set(model.param_names_without_grad())
+    # (1) reference -> fused: a torch Adam that took two steps over the same parameter list
+    ref_params = [torch.nn.Parameter(p.detach().clone()) for p in model.parameters() if p.requires_grad]
+    names = [n for n, p in model.named_parameters() if p.requires_grad]
+    opt = torch.optim.Adam(ref_params, lr=5e-5)
+    g = torch.Generator().manual_seed(1)
+    for _ in range(2):
+        for n, p in zip(names, ref_params):
+            p.grad = None if n in skip else torch.randn(p.shape, generator=g)
+        opt.step()
+    sd = opt.state_dict()
+    assert set(sd["state"]) == {i for i, n in enumerate(names) if n not in skip}
+    tr.load_optimizer_state_dict(sd)
+    assert tr.step_count == 2 and tr.lr == 5e-5
+    assert dryrun.calls[-1] == "mmda_step_state_init"
+    for i, n in enumerate(names):
+        off, sz = tr.layout[n]
+        if n in skip:
+            assert off >= tr.n_active
+            continue
+        assert torch.equal(tr.m[off:off + sz].view(ref_params[i].shape), sd["state"][i]["exp_avg"])
+        assert torch.equal(tr.v[off:off + sz].view(ref_params[i].shape), sd["state"][i]["exp_avg_sq"])
+    # (2) fused -> reference: torch accepts it and sees the same tensors
+    out = tr.optimizer_state_dict()
+    assert set(out["state"]) == set(sd["state"]) and out["param_groups"][0]["lr"] == 5e-5
+    opt2 = torch.optim.Adam([torch.nn.Parameter(p.detach().clone()) for p in ref_params], lr=1.0)
+    opt2.load_state_dict(out)
+    sd2 = opt2.state_dict()
+    assert sd2["param_groups"][0]["lr"] == 5e-5
+    for i in sd["state"]:
+        assert float(sd2["state"][i]["step"]) == 2.0
+        assert torch.equal(sd2["state"][i]["exp_avg"], sd["state"][i]["exp_avg"])
+        assert torch.equal(sd2["state"][i]["exp_avg_sq"], sd["state"][i]["exp_avg_sq"])
+    # (3) a fresh trainer has no per-parameter state, like a fresh torch optimizer
+    tr0 = FusedTrainer(MISA(cfg))
+    assert tr0.optimizer_state_dict()["state"] == {}
+    # (4) anything but the reference's Adam settings is refused
+    bad = opt.state_dict()
+    bad["param_groups"][0]["weight_decay"] = 0.01
+    with pytest.raises(MmdaError):
+        tr.load_optimizer_state_dict(bad)

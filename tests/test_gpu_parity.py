@@ -957,3 +957,47 @@ def test_bert_bf16_mode_within_2e2(dev):
         cos = float((a @ b) / (a.norm() * b.norm() + 1e-30))
         C.flag(f"grad direction {n} cos={cos:.5f}", cos > 0.99)
     C.finish()
+
+
+def test_checkpoint_resume_matches_uninterrupted_run(dev):
+    """src/solver.py:219-220: model + optimizer state_dict saved after step 3, loaded into a fresh
+    model / trainer (through torch.optim.Adam's own layout, as the reference's checkpoint files hold
+    it) and resumed: steps 4..6 -- train mode, so the dropout stream is part of the state -- match
+    the uninterrupted run."""
+    from mmda_b200 import MISA, mosei_config
+    from mmda_b200.synthetic import batch_for
+    from mmda_b200.trainer import FusedTrainer
+    cfg = mosei_config(vocab_size=300, batch_size=32, use_confidNet=True)
+    batches = [batch_for(cfg, seed=90 + i, lengths="ragged", seq_len=10) for i in range(6)]
+
+    def step(tr, b):
+        return tr.step(b.sentences.to(dev), b.visual.to(dev), b.acoustic.to(dev), b.lengths,
+                       b.labels.to(dev))[:6].clone().cpu()
+
+    torch.manual_seed(11)
+    model = MISA(cfg).to(dev).train()
+    tr = FusedTrainer(model, use_graph=False)
+    for b in batches[:3]:
+        step(tr, b)
+    ckpt_model = {k: v.detach().clone().cpu() for k, v in model.state_dict().items()}
+    ckpt_optim = tr.optimizer_state_dict()
+    # the optimizer checkpoint is a genuine torch.optim.Adam state: pass it through one
+    adam = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1.0)
+    adam.load_state_dict(ckpt_optim)
+    ckpt_optim = adam.state_dict()
+    ref = [step(tr, b) for b in batches[3:]]
+    ref_params = tr.p_arena[:tr.n_active].clone().cpu()
+
+    torch.manual_seed(12)                                  # different init: everything comes from the files
+    model2 = MISA(cfg).to(dev).train()
+    model2.load_state_dict(ckpt_model)
+    tr2 = FusedTrainer(model2, use_graph=False)
+    tr2.load_optimizer_state_dict(ckpt_optim)
+    assert tr2.step_count == 3 and tr2.lr == cfg.learning_rate
+    got = [step(tr2, b) for b in batches[3:]]
+    C = Checks("checkpoint_resume")
+    C.add("losses of steps 4..6", torch.stack(got), torch.stack(ref), 1e-5)
+    dp = float((tr2.p_arena[:tr2.n_active].cpu() - ref_params).abs().max())
+    C.rows.append((f"parameters after step 6: max |delta| = {dp:.3e} <= 2*lr*steps", dp,
+                   2 * cfg.learning_rate * 3, dp <= 2 * cfg.learning_rate * 3))
+    C.finish()
