@@ -302,3 +302,38 @@ def test_optimizer_state_dict_round_trips_with_torch_adam(dryrun):
     bad["param_groups"][0]["weight_decay"] = 0.01
     with pytest.raises(MmdaError):
         tr.load_optimizer_state_dict(bad)
+
+
+def test_bench_roofline_block_is_derived_from_the_live_plan():
+    """bench.py's roofline object (SURVEY.md M2/M3): every figure follows from the batch, the live
+    recurrence plan (mmda_lstm_tc_plan, a host-side query) and the measured launch time -- no
+    literals tied to one shape (VERDICT r1 weak #9)."""
+    import argparse
+    import importlib.util
+    import os
+    from mmda_b200.synthetic import batch_for
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for B, T in ((256, 50), (512, 120)):
+        cfg = mosei_config(vocab_size=100, batch_size=B)
+        b = batch_for(cfg, seed=3, lengths="full", seq_len=T)
+        args = argparse.Namespace(batch=B, lengths="full")
+        ntok, H = B * T, 300
+        ms = 0.60 * ntok / 12800          # a launch time in proportion to the C2 one
+        kdur = {"mmda_lstm_tc_forward": ms / 2, "mmda_lstm_tc_backward": ms, "mmda_lstm_forward": 0.0}
+        r = bench.roofline_block(cfg, b, kdur, {"sm_mhz": 1965.0}, args)
+        assert r["kernel"].startswith("mmda_lstm_tc_backward")
+        assert r["algorithmic_bytes"] == 2 * 10 * H * 4 * ntok              # M3: 10H words / token / direction
+        assert r["algorithmic_flops"] == 2 * 2 * 4 * H * H * ntok
+        assert r["binding_roofline"] == "fp32_fma" and r["bound"] == "fp32_fma"
+        assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+        assert abs(r["frac"] - r["frac_of_binding_roofline"]) < 1e-9
+        assert abs(r["peak"] - 148 * 128 * 2 * 1965.0e6 / 1e12) < 1e-9
+        assert abs(r["achieved"] - r["algorithmic_flops"] / (ms * 1e-3) / 1e12) < 1e-9
+        plan = r["plan"]
+        assert plan["ctas"] == 2 * plan["slices"] * plan["groups"] <= 148
+        assert plan["groups"] * plan["batch_tile"] >= B or plan["tiles"] * plan["batch_tile"] >= B
+        assert r["hbm"]["frac"] < r["frac"] < 1.0
+    assert bench.roofline_block(cfg, b, {"mmda_lstm_tc_backward": 0.0}, None, args) is None
