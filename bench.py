@@ -49,7 +49,7 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.rows, self.proc, self.idx = [], None, gpu_index
+        self.rows, self.proc, self.idx, self.first = [], None, gpu_index, 0
 
     def start(self):
         try:
@@ -65,14 +65,28 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
+    def wait_first(self, timeout_s=4.0):
+        """Block until nvidia-smi has delivered its first sample (its start-up takes 0.1-0.5 s,
+        longer than a 20-step timed region), so that the following samples fall INSIDE the timed
+        regions.  Gives up quietly after ``timeout_s``."""
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.rows and time.perf_counter() - t0 < timeout_s:
+            time.sleep(0.01)
+
+    def mark(self):
+        """Samples from here on were taken under load (call right before the timed region)."""
+        self.first = len(self.rows)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        if len(self.rows) <= self.first:
+            time.sleep(0.15)          # very short run: take the next sample, right behind the region
         self.proc.terminate()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = self.rows[self.first:] or self.rows
+        for r in rows:
             try:
                 sm.append(float(r[1])); mx = float(r[2])
                 for nm, v in zip(names, r[4:8]):
@@ -340,6 +354,13 @@ def run_ours(args):
 
     dp = dp_check(dist, pg, rank, world, dev) if world > 1 else None
 
+    # nvidia-smi sampler: started (and its first sample awaited) BEFORE the warm-up, so that the
+    # tool's start-up neither leaves the GPU idle in front of the timed region nor eats it
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+        clocks.wait_first()
+
     # ---- warm-up (also captures the CUDA graph of the step on a single GPU) ----
     # (ragged lengths: one graph per packed-row bucket, so a few more passes until every batch of
     # the rotation replays from a graph)
@@ -353,13 +374,11 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- timed region: device-resident inputs ----
-    clocks = ClockSampler(local)
     barrier()
-    if rank == 0:
-        clocks.start()
     l0 = eng.k.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    clocks.mark()
     e0.record()
     h0 = time.perf_counter()
     for i in range(args.steps):
@@ -371,7 +390,6 @@ def run_ours(args):
     launches = (args.steps * tr.launches_per_step) if graph_on else (eng.k.launches - l0)
     n_graphs = len(tr._graphs)
     ms = e0.elapsed_time(e1)
-    clk = clocks.stop() if rank == 0 else None
     t = torch.tensor([ms], device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -426,6 +444,9 @@ def run_ours(args):
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e = world * args.batch * args.steps / (float(t) * 1e-3)
+    # the sampler ran through all three timed regions (device-resident steps, per-launch kernel
+    # timing, end-to-end steps): every sample after mark() was taken under load
+    clk = clocks.stop() if rank == 0 else None
 
     # captured CUDA graphs hold references to the NCCL communicator: drop them before teardown
     tr.close()

@@ -337,3 +337,40 @@ def test_bench_roofline_block_is_derived_from_the_live_plan():
         assert plan["groups"] * plan["batch_tile"] >= B or plan["tiles"] * plan["batch_tile"] >= B
         assert r["hbm"]["frac"] < r["frac"] < 1.0
     assert bench.roofline_block(cfg, b, {"mmda_lstm_tc_backward": 0.0}, None, args) is None
+
+
+def test_bench_clock_sampler_covers_short_runs(tmp_path, monkeypatch):
+    """bench.py's nvidia-smi sampler: waits for the tool's (slow) start-up before the timed region,
+    reports only samples taken after mark(), and still yields one for a region shorter than the
+    sampling period; a box without nvidia-smi is reported, not fatal."""
+    import importlib.util
+    import os
+    import stat
+    import time
+    fake = tmp_path / "nvidia-smi"
+    fake.write_text("#!/bin/bash\nsleep 0.3\ni=0\nwhile true; do\n"
+                    "if [ $i -lt 1 ]; then echo '0, 345, 1965, 150.0, Not Active, Not Active, Not Active, Not Active';\n"
+                    "else echo '0, 1950, 1965, 600.0, Not Active, Not Active, Not Active, Active'; fi\n"
+                    "i=$((i+1)); sleep 0.05\ndone\n")
+    fake.chmod(fake.stat().st_mode | stat.S_IEXEC)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod2", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    monkeypatch.setenv("PATH", f"{tmp_path}:{os.environ['PATH']}")
+    c = bench.ClockSampler(0)
+    c.start(); c.wait_first()
+    assert len(c.rows) >= 1                      # the idle-clock sample before the region
+    c.mark()
+    time.sleep(0.25)
+    out = c.stop()
+    assert out["samples"] >= 2 and out["sm_mhz"] == 1950.0 and out["sm_max_mhz"] == 1965.0
+    assert out["reasons"] == ["sw_power_cap"]
+    c = bench.ClockSampler(0)
+    c.start(); c.wait_first(); c.mark()
+    out = c.stop()                               # empty region: the next sample is taken
+    assert out["samples"] >= 1 and out["sm_mhz"] == 1950.0
+    monkeypatch.setenv("PATH", str(tmp_path / "nowhere"))
+    c = bench.ClockSampler(0)
+    c.start(); c.wait_first(); c.mark()
+    assert c.stop()["reasons"] == ["nvidia-smi unavailable"]
