@@ -6,6 +6,7 @@ Public surface:
   MisaConfig      the config attributes the hot path reads
   FusedTrainer    level-2 fused step (losses + backward + clip + Adam, optional data parallel)
   synthetic       seeded MOSI/MOSEI-shaped batches
+  collate         device-resident dataset + collate; wordpiece: the BERT tokenizer of its host side
 All arithmetic runs in libmmda_b200.so (hand-written CUDA behind a C ABI, include/mmda_b200.h).
 """
 from .config import MisaConfig, mosei_config, mosi_config  # noqa: F401
@@ -16,4 +17,7 @@ def __getattr__(name):
     if name == "FusedTrainer":
         from .trainer import FusedTrainer
         return FusedTrainer
+    if name == "WordPieceTokenizer":
+        from .wordpiece import WordPieceTokenizer
+        return WordPieceTokenizer
     raise AttributeError(name)
