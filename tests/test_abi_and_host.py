@@ -374,3 +374,36 @@ def test_bench_clock_sampler_covers_short_runs(tmp_path, monkeypatch):
     c = bench.ClockSampler(0)
     c.start(); c.wait_first(); c.mark()
     assert c.stop()["reasons"] == ["nvidia-smi unavailable"]
+
+
+@pytest.mark.parametrize("variant", [dict(rnncell="gru"), dict(use_cmd_sim=False),
+                                     dict(rnncell="gru", use_cmd_sim=False, use_confidNet=True)])
+def test_variant_kernel_sequences(dryrun, variant):
+    """Host orchestration of the non-default variants (GRU cells,
+    src/models.py:39; adversarial branch, src/models.py:219-227 + src/solver.py:388-407) on the
+    stubbed library: the right entry points are reached, level 1 and level 2."""
+    from mmda_b200.synthetic import batch_for
+    from mmda_b200.trainer import FusedTrainer
+    cfg = mosei_config(vocab_size=50, batch_size=6, **variant)
+    torch.manual_seed(0)
+    model = MISA(cfg).train()
+    b = batch_for(cfg, seed=2, lengths="ragged", seq_len=5)
+    scores, _ = model(*b.model_args())
+    extra = model.domain_label_t.sum() if not cfg.use_cmd_sim else 0.0
+    (scores.sum() + extra).backward()
+    c1 = collections.Counter(dryrun.calls)
+    gru = variant.get("rnncell") == "gru"
+    assert c1["mmda_gru_forward" if gru else "mmda_lstm_forward"] == 6
+    assert c1["mmda_gru_backward" if gru else "mmda_lstm_backward"] == 6
+    assert (c1["mmda_gru_expand_weights"] > 0) == gru and (c1["mmda_gru_fold_grads"] > 0) == gru
+    dryrun.calls.clear()
+    tr = FusedTrainer(model)
+    tr.step(b.sentences, b.visual, b.acoustic, b.lengths, b.labels)
+    c2 = collections.Counter(dryrun.calls)
+    assert (c2["mmda_loss_domain"] == 1) == (not cfg.use_cmd_sim)
+    assert dryrun.calls[-1] == "mmda_adam_clip_step"
+    # the discriminator exists (src/models.py:122-127) and trains only in the adversarial variant
+    name = "discriminator.discriminator_layer_1.weight"
+    assert (name in tr.layout) == (not cfg.use_cmd_sim)
+    if name in tr.layout:
+        assert tr.layout[name][0] < tr.n_active
