@@ -546,6 +546,8 @@ class FusedTrainer:
         self.v.zero_()
         steps = set()
         for pid, st in sd["state"].items():
+            if pid not in pos:
+                raise MmdaError(f"optimizer state for parameter id {pid!r}, which its param group does not list")
             _, n, p = params[pos[pid]]
             off, sz = self.layout[n]
             if tuple(st["exp_avg"].shape) != tuple(p.shape):
