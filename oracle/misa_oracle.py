@@ -1,7 +1,8 @@
 """CPU oracle for the MISA hot path.  TEST INFRASTRUCTURE -- NOT PART OF THE PRODUCT.
 
-Only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference`` legs of
-``bench.py`` may import this module, and only as the checker or as the timed CPU baseline.  The
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py`` -- its ``cpu_baseline`` / ``--impl
+reference`` legs (the timed CPU baseline) and, at N > 1, the ``dp_check`` parity evidence outside any
+timed region (the checker of the data-parallel step) -- may import this module.  The
 product path (``mmda_b200``) never routes through it and fails loudly without its CUDA library.
 
 What it restates (all citations are into /root/reference):
